@@ -1,0 +1,83 @@
+"""ctypes binding of libglb200.so (C-ABI declared in include/glb200.h).
+
+There is NO CPU fallback: if the library is missing or a call fails, a RuntimeError is raised.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_void_p
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libglb200.so")
+
+_lib = None
+
+# name -> (restype, argtypes).  Mirrors include/glb200.h one to one (tests/test_abi.py checks that).
+SIGNATURES = {
+    "glb_version": (c_int, []),
+    "glb_last_error": (c_char_p, []),
+    "glb_device_info": (c_int, [POINTER(c_int), POINTER(c_int), POINTER(c_int), POINTER(c_int64)]),
+    "glb_padded_ld": (c_int, [c_int]),
+    "glb_csr_degree": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p]),
+    "glb_csr_transpose_work_bytes": (c_int64, [c_int64, c_int64]),
+    "glb_csr_transpose": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p,
+                                  c_void_p, c_int64, c_void_p]),
+    "glb_poisson_scale": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
+    "glb_pack_f64_to_f32": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int, c_void_p]),
+    "glb_unpack_f32_to_f64": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p]),
+    "glb_poisson_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
+    "glb_poisson_plan_create": (c_int, [POINTER(c_void_p), c_void_p, c_int64, c_int64, c_int, c_void_p]),
+    "glb_poisson_plan_destroy": (c_int, [c_void_p]),
+    "glb_poisson_plan_is_persistent": (c_int, [c_void_p]),
+    "glb_poisson_iterate": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                                    POINTER(c_int), POINTER(c_int), c_void_p]),
+    "glb_poisson_mixing_T": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int,
+                                     POINTER(c_int), POINTER(c_int), c_void_p]),
+    "glb_poisson_gd_host": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int, c_void_p, c_int64,
+                                    c_int, c_int, c_void_p, POINTER(c_int), POINTER(c_int)]),
+}
+
+
+class GlbError(RuntimeError):
+    pass
+
+
+def load():
+    """Load libglb200.so; raises RuntimeError (never falls back) when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError("libglb200.so not found at %s - build it with `python -m graphlearning_b200.build` "
+                           "(there is no CPU fallback)" % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = load().glb_last_error()
+        raise GlbError("%s failed (code %d): %s" % (what or "libglb200 call", rc, msg.decode() if msg else ""))
+
+
+def call(name, *args):
+    check(getattr(load(), name)(*args), name)
+
+
+def device_info():
+    sm, maj, mnr, mem = c_int(), c_int(), c_int(), c_int64()
+    call("glb_device_info", ctypes.byref(sm), ctypes.byref(maj), ctypes.byref(mnr), ctypes.byref(mem))
+    return dict(sm_count=sm.value, cc=(maj.value, mnr.value), hbm_bytes=mem.value)
+
+
+def padded_ld(c):
+    ld = load().glb_padded_ld(int(c))
+    if ld <= 0:
+        raise GlbError("glb_padded_ld(%r) rejected" % (c,))
+    return ld

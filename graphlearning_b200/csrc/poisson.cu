@@ -1,0 +1,475 @@
+// poisson.cu - the Poisson-learning iterate u <- Db + P u on sm_100a.
+//
+// Replaces the hot loop of ssl.poisson._fit, gradient-descent branch
+// (reference graphlearning/ssl.py:667-669; third-party arithmetic: scipy _sparsetools csr_matvecs).
+//
+// Two kernels:
+//   poisson_step_kernel        one iteration per launch.  CSR (col,val) streamed coalesced, rows of the
+//                              row-major n x ldu label matrix gathered with 128-bit loads, D^-1 folded into
+//                              the values, "+ Db" fused into the store.  For graphs too big for the
+//                              persistent kernel; genuinely HBM/L2-gather bound.
+//   poisson_persistent_kernel  T iterations in ONE cooperative launch, one CTA per SM.  Each CTA stages the
+//                              CSR slab and Db slab of its row block in shared memory once, so per iteration
+//                              only the u gathers (L2) and the u store touch global memory; iterations are
+//                              separated by a hand-rolled grid barrier.  For the 70k-node north-star
+//                              graph the whole working set is L2 resident and a launch per iteration
+//                              (~2-3 us) would cost as much as the iteration itself.
+//
+// Lane mapping (both kernels): GROUP lanes cooperate on one matrix row.  LANES = ldu/4 lanes cover one
+// gathered row of u with one float4 each, so GROUP/LANES nonzeros are in flight per group and step.  Each
+// group first loads GROUP consecutive (col,val) pairs (coalesced / conflict-free), then broadcasts them
+// with shuffles.  Partial sums are combined across the GROUP/LANES sub-groups with xor-shuffles.
+#include <string.h>
+#include "common.cuh"
+
+namespace glb {
+
+template <int GROUP>
+__device__ __forceinline__ unsigned group_mask(int lane)
+{
+    if (GROUP == 32) return 0xffffffffu;
+    return ((1u << GROUP) - 1u) << ((lane / GROUP) * GROUP);
+}
+
+__device__ __forceinline__ void fma4(float4 &acc, float a, const float4 &x)
+{
+    acc.x = fmaf(a, x.x, acc.x);
+    acc.y = fmaf(a, x.y, acc.y);
+    acc.z = fmaf(a, x.z, acc.z);
+    acc.w = fmaf(a, x.w, acc.w);
+}
+
+template <bool NC>
+__device__ __forceinline__ float4 load_u4(const float *p)
+{
+    if (NC) return __ldg(reinterpret_cast<const float4 *>(p));
+    return *reinterpret_cast<const float4 *>(p);   // coherent at L1 after the grid barrier's fence
+}
+
+// One matrix row times u, for the column tile starting at `ctile`.  beg/end index col/val (global or
+// shared).  Returns the finished float4 (valid in the lanes of sub-group 0).
+template <int GROUP, int LANES, bool NC>
+__device__ __forceinline__ float4 row_times_u(const int *__restrict__ col, const float *__restrict__ val, int beg,
+                                              int end, const float *__restrict__ u, int ldu, int ctile, int lane)
+{
+    constexpr int NPAR = GROUP / LANES;
+    const unsigned mask = group_mask<GROUP>(lane);
+    const int gl = lane % GROUP;
+    const int sub = gl / LANES;
+    const int li = gl % LANES;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int base = beg; base < end; base += GROUP) {
+        const int my = base + gl;
+        int cj = 0;
+        float aj = 0.f;
+        if (my < end) {
+            cj = col[my];
+            aj = val[my];
+        }
+        const int cnt = min(GROUP, end - base);
+#pragma unroll
+        for (int s = 0; s < GROUP / NPAR; ++s) {
+            if (s * NPAR >= cnt) break;                      // uniform inside the group
+            const int src = s * NPAR + sub;
+            const int c = __shfl_sync(mask, cj, src, GROUP);
+            const float a = __shfl_sync(mask, aj, src, GROUP);
+            if (src < cnt) {
+                const float4 x = load_u4<NC>(u + (size_t)c * ldu + ctile + li * 4);
+                fma4(acc, a, x);
+            }
+        }
+    }
+#pragma unroll
+    for (int off = LANES; off < GROUP; off <<= 1) {
+        acc.x += __shfl_xor_sync(mask, acc.x, off, GROUP);
+        acc.y += __shfl_xor_sync(mask, acc.y, off, GROUP);
+        acc.z += __shfl_xor_sync(mask, acc.z, off, GROUP);
+        acc.w += __shfl_xor_sync(mask, acc.w, off, GROUP);
+    }
+    return acc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1: one iteration per launch
+// ------------------------------------------------------------------------------------------------
+template <int GROUP, int LANES>
+__global__ void __launch_bounds__(256)
+poisson_step_kernel(const int *__restrict__ rowptr, const int *__restrict__ col, const float *__restrict__ val,
+                    const float *__restrict__ Db, const float *__restrict__ u_in, float *__restrict__ u_out,
+                    int n, int ldu)
+{
+    const int lane = threadIdx.x & 31;
+    const int gl = lane % GROUP;
+    const long long gid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / GROUP;
+    const long long ngroups = ((long long)gridDim.x * blockDim.x) / GROUP;
+    for (long long row = gid; row < n; row += ngroups) {
+        const int beg = __ldg(rowptr + row), end = __ldg(rowptr + row + 1);
+        for (int ctile = 0; ctile < ldu; ctile += LANES * 4) {
+            float4 acc = row_times_u<GROUP, LANES, true>(col, val, beg, end, u_in, ldu, ctile, lane);
+            if (gl < LANES) {
+                const size_t o = (size_t)row * ldu + ctile + gl * 4;
+                const float4 b = __ldg(reinterpret_cast<const float4 *>(Db + o));
+                acc.x += b.x; acc.y += b.y; acc.z += b.z; acc.w += b.w;
+                *reinterpret_cast<float4 *>(u_out + o) = acc;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2: persistent, T iterations per launch
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned ld_acquire(const unsigned *p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// All CTAs of the (cooperatively launched, co-resident) grid meet here.  `target` is the value the
+// monotone counter reaches once every CTA has arrived for this phase.
+__device__ __forceinline__ void grid_barrier(unsigned *counter, unsigned target)
+{
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();                       // publish this CTA's u stores
+        atomicAdd(counter, 1u);
+        while (ld_acquire(counter) < target) { }
+        __threadfence();                       // acquire: also invalidates this SM's L1 (CCTL.IVALL)
+    }
+    __syncthreads();
+}
+
+constexpr int kPersistThreads = 1024;
+
+template <int GROUP, int LANES>
+__global__ void __launch_bounds__(kPersistThreads, 1)
+poisson_persistent_kernel(const int *__restrict__ rowptr, const int *__restrict__ col,
+                          const float *__restrict__ val, const float *__restrict__ Db, float *u0, float *u1, int n,
+                          int ldu, int T, int rows_per_cta, int slab_cap, unsigned *barrier_counter)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    // layout: Db slab [rows_per_cta*ldu] f32 | val [slab_cap] f32 | col [slab_cap] i32 | rp [rows_per_cta+1] i32
+    float *s_Db = reinterpret_cast<float *>(smem_raw);
+    float *s_val = s_Db + (size_t)rows_per_cta * ldu;
+    int *s_col = reinterpret_cast<int *>(s_val + slab_cap);
+    int *s_rp = s_col + slab_cap;
+
+    const int r0 = min(n, (int)blockIdx.x * rows_per_cta);
+    const int r1 = min(n, r0 + rows_per_cta);
+    const int nrows = r1 - r0;
+    const int nz0 = rowptr[r0];
+    const int nnz_slab = rowptr[r1] - nz0;
+    for (int i = threadIdx.x; i < nnz_slab; i += blockDim.x) {
+        s_col[i] = col[nz0 + i];
+        s_val[i] = val[nz0 + i];
+    }
+    for (int i = threadIdx.x; i <= nrows; i += blockDim.x) s_rp[i] = rowptr[r0 + i] - nz0;
+    for (int i = threadIdx.x; i < nrows * (ldu / 4); i += blockDim.x)
+        reinterpret_cast<float4 *>(s_Db)[i] = reinterpret_cast<const float4 *>(Db + (size_t)r0 * ldu)[i];
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31;
+    const int gl = lane % GROUP;
+    const int gid = threadIdx.x / GROUP;
+    constexpr int NGROUPS = kPersistThreads / GROUP;
+
+    for (int t = 0; t < T; ++t) {
+        const float *u_in = (t & 1) ? u1 : u0;
+        float *u_out = (t & 1) ? u0 : u1;
+        for (int lr = gid; lr < nrows; lr += NGROUPS) {
+            const int beg = s_rp[lr], end = s_rp[lr + 1];
+            for (int ctile = 0; ctile < ldu; ctile += LANES * 4) {
+                float4 acc = row_times_u<GROUP, LANES, false>(s_col, s_val, beg, end, u_in, ldu, ctile, lane);
+                if (gl < LANES) {
+                    const float4 b = *reinterpret_cast<const float4 *>(s_Db + (size_t)lr * ldu + ctile + gl * 4);
+                    acc.x += b.x; acc.y += b.y; acc.z += b.z; acc.w += b.w;
+                    *reinterpret_cast<float4 *>(u_out + (size_t)(r0 + lr) * ldu + ctile + gl * 4) = acc;
+                }
+            }
+        }
+        if (t + 1 < T) grid_barrier(barrier_counter, (unsigned)(t + 1) * gridDim.x);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// mixing vector v <- RW v (fp64) and max|v - vinf|     (ssl.py:667,669)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void block_max_to_global(double m, unsigned long long *out)
+{
+    // non-negative doubles (and NaN, which sorts above +inf) compare like their bit patterns
+    for (int off = 16; off > 0; off >>= 1) {
+        double o = __shfl_xor_sync(0xffffffffu, m, off);
+        m = (__double_as_longlong(o) > __double_as_longlong(m)) ? o : m;
+    }
+    if ((threadIdx.x & 31) == 0) atomicMax(out, (unsigned long long)__double_as_longlong(m));
+}
+
+__global__ void __launch_bounds__(256)
+mixing_step_kernel(const int *__restrict__ rowptr, const int *__restrict__ col, const double *__restrict__ val,
+                   const double *__restrict__ vinf, const double *__restrict__ v_in, double *__restrict__ v_out,
+                   int n, unsigned long long *err_out)
+{
+    constexpr int G = 8;
+    const int lane = threadIdx.x & 31;
+    const int gl = lane % G;
+    const long long gid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const long long ngroups = ((long long)gridDim.x * blockDim.x) / G;
+    double worst = 0.0;
+    for (long long rb = 0; rb < n; rb += ngroups) {          // uniform trip count: shuffles stay converged
+        const long long row = rb + gid;
+        double s = 0.0;
+        if (row < n) {
+            const int beg = rowptr[row], end = rowptr[row + 1];
+            for (int j = beg + gl; j < end; j += G) s += val[j] * v_in[col[j]];
+        }
+        for (int off = G / 2; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off, G);
+        if (row < n && gl == 0) {
+            v_out[row] = s;
+            const double d = fabs(s - vinf[row]);
+            // fabs(NaN) is NaN: keep it (np.max propagates NaN, ssl.py:667)
+            worst = (d > worst || d != d) ? d : worst;
+        }
+    }
+    block_max_to_global(worst, err_out);
+}
+
+__global__ void __launch_bounds__(256)
+maxdiff_kernel(const double *__restrict__ v, const double *__restrict__ vinf, int n, unsigned long long *err_out)
+{
+    double worst = 0.0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const double d = fabs(v[i] - vinf[i]);
+        worst = (d > worst || d != d) ? d : worst;
+    }
+    block_max_to_global(worst, err_out);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+template <int GROUP, int LANES>
+static int launch_step(const int *rp, const int *col, const float *val, const float *Db, const float *u_in,
+                       float *u_out, int64_t n, int ldu, cudaStream_t st)
+{
+    const int threads = 256;
+    const int64_t groups_per_block = threads / GROUP;
+    int64_t blocks = (n + groups_per_block - 1) / groups_per_block;
+    const int64_t cap = (int64_t)sm_count() * 8 * 8;           // 8 resident CTAs/SM x 8 waves, then grid-stride
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    poisson_step_kernel<GROUP, LANES><<<(unsigned)blocks, threads, 0, st>>>(rp, col, val, Db, u_in, u_out, (int)n, ldu);
+    return 0;
+}
+
+static int dispatch_step(const int *rp, const int *col, const float *val, const float *Db, const float *u_in,
+                         float *u_out, int64_t n, int ldu, cudaStream_t st)
+{
+    switch (ldu) {
+        case 4: return launch_step<8, 1>(rp, col, val, Db, u_in, u_out, n, ldu, st);
+        case 8: return launch_step<16, 2>(rp, col, val, Db, u_in, u_out, n, ldu, st);
+        case 16: return launch_step<16, 4>(rp, col, val, Db, u_in, u_out, n, ldu, st);
+        case 32: return launch_step<32, 8>(rp, col, val, Db, u_in, u_out, n, ldu, st);
+        case 64: return launch_step<32, 16>(rp, col, val, Db, u_in, u_out, n, ldu, st);
+        default: return launch_step<32, 32>(rp, col, val, Db, u_in, u_out, n, ldu, st);
+    }
+}
+
+static bool valid_ld(int ldu)
+{
+    if (ldu < 4) return false;
+    if (ldu <= 128) return (ldu & (ldu - 1)) == 0;
+    return ldu % 128 == 0;
+}
+
+}  // namespace glb
+
+using namespace glb;
+
+extern "C" GLB_API int glb_poisson_step(const int32_t *d_rowptr, const int32_t *d_col, const float *d_val, const float *d_Db,
+                                const float *d_u_in, float *d_u_out, int64_t n, int ldu, void *stream)
+{
+    GLB_CHECK_ARG(d_rowptr && d_col && d_val && d_Db && d_u_in && d_u_out, "null pointer");
+    GLB_CHECK_ARG(n > 0 && n < (1ll << 31), "n out of range");
+    GLB_CHECK_ARG(valid_ld(ldu), "ldu must be a power of two in [4,128] or a multiple of 128");
+    GLB_CHECK_ARG(d_u_in != d_u_out, "u_in and u_out must differ");
+    dispatch_step(d_rowptr, d_col, d_val, d_Db, d_u_in, d_u_out, n, ldu, (cudaStream_t)stream);
+    GLB_LAUNCH_CHECK();
+    return 0;
+}
+
+struct glb_poisson_plan {
+    int64_t n, nnz;
+    int ldu;
+    int persistent;
+    int grid, rows_per_cta, slab_cap;
+    size_t smem_bytes;
+    unsigned *d_counter;
+};
+
+template <int GROUP, int LANES>
+static const void *persistent_fn() { return (const void *)poisson_persistent_kernel<GROUP, LANES>; }
+
+static const void *pick_persistent(int ldu)
+{
+    switch (ldu) {
+        case 4: return persistent_fn<8, 1>();
+        case 8: return persistent_fn<16, 2>();
+        case 16: return persistent_fn<16, 4>();
+        case 32: return persistent_fn<32, 8>();
+        case 64: return persistent_fn<32, 16>();
+        default: return persistent_fn<32, 32>();
+    }
+}
+
+extern "C" GLB_API int glb_poisson_plan_create(glb_poisson_plan **plan, const int32_t *d_rowptr, int64_t n, int64_t nnz,
+                                       int ldu, void *stream)
+{
+    GLB_CHECK_ARG(plan && d_rowptr, "null pointer");
+    GLB_CHECK_ARG(n > 0 && n < (1ll << 31) && nnz >= 0 && nnz < (1ll << 31), "size out of range");
+    GLB_CHECK_ARG(valid_ld(ldu), "bad ldu");
+    cudaStream_t st = (cudaStream_t)stream;
+    glb_poisson_plan *p = new glb_poisson_plan();
+    p->n = n; p->nnz = nnz; p->ldu = ldu; p->persistent = 0; p->d_counter = nullptr;
+    p->grid = 0; p->rows_per_cta = 0; p->slab_cap = 0; p->smem_bytes = 0;
+
+    int dev = 0, coop = 0, max_smem = 0;
+    GLB_CUDA(cudaGetDevice(&dev));
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+    cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    const int sms = sm_count();
+    // at least 2 passes of row groups per CTA so tiny graphs do not spread over 148 barriers' worth of CTAs
+    int grid = (int)((n + 127) / 128);
+    if (grid > sms) grid = sms;
+    if (grid < 1) grid = 1;
+    const int rpc = (int)((n + grid - 1) / grid);
+    grid = (int)((n + rpc - 1) / rpc);
+    if (coop && grid >= 1) {
+        // slab sizes: rowptr at the CTA boundaries, strided device->host copy
+        int *h_b = new int[grid + 1];
+        cudaError_t e = cudaMemcpy2DAsync(h_b, sizeof(int), d_rowptr, (size_t)rpc * sizeof(int), sizeof(int), grid,
+                                          cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess)
+            e = cudaMemcpyAsync(h_b + grid, d_rowptr + n, sizeof(int), cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) {
+            delete[] h_b; delete p;
+            set_error("glb_poisson_plan_create: reading rowptr failed: %s", cudaGetErrorString(e));
+            return (int)e;
+        }
+        int cap = 0;
+        for (int b = 0; b < grid; ++b) cap = (h_b[b + 1] - h_b[b] > cap) ? h_b[b + 1] - h_b[b] : cap;
+        delete[] h_b;
+        cap = (cap + 3) & ~3;
+        const size_t smem = (size_t)rpc * ldu * 4 + (size_t)cap * 8 + (size_t)(rpc + 1) * 4;
+        if (smem <= (size_t)max_smem) {
+            const void *fn = pick_persistent(ldu);
+            GLB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            int per_sm = 0;
+            GLB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kPersistThreads, smem));
+            if (per_sm >= 1 && grid <= per_sm * sms) {
+                p->persistent = 1;
+                p->grid = grid; p->rows_per_cta = rpc; p->slab_cap = cap; p->smem_bytes = smem;
+                GLB_CUDA(cudaMalloc(&p->d_counter, sizeof(unsigned)));
+            }
+        }
+    }
+    *plan = p;
+    return 0;
+}
+
+extern "C" GLB_API int glb_poisson_plan_destroy(glb_poisson_plan *plan)
+{
+    if (!plan) return 0;
+    if (plan->d_counter) cudaFree(plan->d_counter);
+    delete plan;
+    return 0;
+}
+
+extern "C" GLB_API int glb_poisson_plan_is_persistent(const glb_poisson_plan *plan) { return plan ? plan->persistent : 0; }
+
+extern "C" GLB_API int glb_poisson_iterate(glb_poisson_plan *plan, const int32_t *d_rowptr, const int32_t *d_col,
+                                   const float *d_val, const float *d_Db, float *d_u0, float *d_u1, int T,
+                                   int *result_in_u1, int *launches, void *stream)
+{
+    GLB_CHECK_ARG(plan && d_rowptr && d_col && d_val && d_Db && d_u0 && d_u1, "null pointer");
+    GLB_CHECK_ARG(T >= 0, "T must be >= 0");
+    GLB_CHECK_ARG(d_u0 != d_u1, "u0 and u1 must differ");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (result_in_u1) *result_in_u1 = T & 1;
+    if (T == 0) return 0;
+    if (plan->persistent) {
+        GLB_CUDA(cudaMemsetAsync(plan->d_counter, 0, sizeof(unsigned), st));
+        int n = (int)plan->n, ldu = plan->ldu, rpc = plan->rows_per_cta, cap = plan->slab_cap;
+        void *args[] = {(void *)&d_rowptr, (void *)&d_col, (void *)&d_val, (void *)&d_Db, (void *)&d_u0, (void *)&d_u1,
+                        (void *)&n, (void *)&ldu, (void *)&T, (void *)&rpc, (void *)&cap, (void *)&plan->d_counter};
+        GLB_CUDA(cudaLaunchCooperativeKernel(pick_persistent(ldu), dim3(plan->grid), dim3(kPersistThreads), args,
+                                             plan->smem_bytes, st));
+        if (launches) *launches += 1;
+    } else {
+        for (int t = 0; t < T; ++t) {
+            const float *in = (t & 1) ? d_u1 : d_u0;
+            float *out = (t & 1) ? d_u0 : d_u1;
+            dispatch_step(d_rowptr, d_col, d_val, d_Db, in, out, plan->n, plan->ldu, st);
+        }
+        GLB_LAUNCH_CHECK();
+        if (launches) *launches += T;
+    }
+    return 0;
+}
+
+extern "C" GLB_API int glb_poisson_mixing_T(const int32_t *d_rw_rowptr, const int32_t *d_rw_col, const double *d_rw_val,
+                                    const double *d_vinf, double *d_v, double *d_tmp, int64_t n, int min_iter,
+                                    int max_iter, int *T_out, int *launches, void *stream)
+{
+    GLB_CHECK_ARG(d_rw_rowptr && d_rw_col && d_rw_val && d_vinf && d_v && d_tmp && T_out, "null pointer");
+    GLB_CHECK_ARG(n > 0 && n < (1ll << 31), "n out of range");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int BATCH = 64;
+    unsigned long long *d_err = nullptr;
+    GLB_CUDA(cudaMalloc(&d_err, sizeof(unsigned long long) * (BATCH + 1)));
+    unsigned long long h_err[BATCH + 1];
+    const double thr = 1.0 / (double)n;
+    const int threads = 256;
+    int blocks = ceil_div(n * 8, threads);
+    if (blocks > sm_count() * 16) blocks = sm_count() * 16;
+    int T = 0, rc = 0;
+    bool done = false;
+    // err_0
+    cudaMemsetAsync(d_err, 0, sizeof(unsigned long long) * (BATCH + 1), st);
+    maxdiff_kernel<<<blocks, threads, 0, st>>>(d_v, d_vinf, (int)n, d_err);
+    if (launches) *launches += 1;
+    cudaMemcpyAsync(h_err, d_err, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st);
+    cudaStreamSynchronize(st);
+    double err;
+    memcpy(&err, &h_err[0], sizeof(double));
+    double *cur = d_v, *nxt = d_tmp;
+    while (!done) {
+        // condition of ssl.py:667 evaluated BEFORE each step, with err = max|v_T - vinf|
+        if (!((T < min_iter || err > thr) && T < max_iter)) break;
+        int steps = max_iter - T;
+        if (steps > BATCH) steps = BATCH;
+        cudaMemsetAsync(d_err, 0, sizeof(unsigned long long) * (BATCH + 1), st);
+        for (int s = 0; s < steps; ++s) {
+            mixing_step_kernel<<<blocks, threads, 0, st>>>(d_rw_rowptr, d_rw_col, d_rw_val, d_vinf, cur, nxt, (int)n,
+                                                           d_err + s);
+            double *t = cur; cur = nxt; nxt = t;
+        }
+        if (launches) *launches += steps;
+        cudaError_t e = cudaMemcpyAsync(h_err, d_err, sizeof(unsigned long long) * steps, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) { rc = (int)e; set_error("glb_poisson_mixing_T: %s", cudaGetErrorString(e)); break; }
+        for (int s = 0; s < steps; ++s) {
+            T += 1;
+            memcpy(&err, &h_err[s], sizeof(double));
+            if (!((T < min_iter || err > thr) && T < max_iter)) { done = true; break; }
+        }
+    }
+    cudaFree(d_err);
+    if (rc == 0) {
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) { rc = (int)e; set_error("glb_poisson_mixing_T: %s", cudaGetErrorString(e)); }
+    }
+    *T_out = T;
+    return rc;
+}

@@ -1,0 +1,161 @@
+"""Device-resident building blocks: CSR graphs and the Poisson operator held in HBM.
+
+torch is used only as the owner of device memory and streams (tensor.data_ptr(), current stream); every
+kernel is launched through the C-ABI of libglb200.so.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+from scipy import sparse
+
+from . import _lib
+
+
+def _torch():
+    import torch
+    if not torch.cuda.is_available():
+        raise RuntimeError("graphlearning_b200 needs a CUDA device (B200); there is no CPU fallback")
+    return torch
+
+
+def ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def cur_stream():
+    return ctypes.c_void_p(_torch().cuda.current_stream().cuda_stream)
+
+
+class DeviceCSR:
+    """A CSR matrix in HBM: int32 rowptr/col, values fp64 (setup) and/or fp32 (iterate)."""
+
+    def __init__(self, rowptr, col, val, n):
+        self.rowptr, self.col, self.val, self.n = rowptr, col, val, int(n)
+        self.nnz = int(col.numel())
+
+    @classmethod
+    def from_scipy(cls, W, device="cuda"):
+        torch = _torch()
+        W = sparse.csr_matrix(W)
+        if W.shape[0] != W.shape[1]:
+            raise ValueError("weight matrix must be square")
+        rp = torch.from_numpy(np.ascontiguousarray(W.indptr, dtype=np.int32)).to(device)
+        col = torch.from_numpy(np.ascontiguousarray(W.indices, dtype=np.int32)).to(device)
+        val = torch.from_numpy(np.ascontiguousarray(W.data, dtype=np.float64)).to(device)
+        return cls(rp, col, val, W.shape[0])
+
+    def to_scipy(self):
+        return sparse.csr_matrix((self.val.cpu().numpy(), self.col.cpu().numpy(), self.rowptr.cpu().numpy()),
+                                 shape=(self.n, self.n))
+
+    def degree(self, skip_diagonal=False):
+        """graph.degree_vector (reference graphlearning/graph.py:108-122) on the device."""
+        torch = _torch()
+        deg = torch.empty(self.n, dtype=torch.float64, device=self.val.device)
+        _lib.call("glb_csr_degree", ptr(self.rowptr), ptr(self.col), ptr(self.val), self.n, int(skip_diagonal),
+                  ptr(deg), cur_stream())
+        return deg
+
+    def transpose(self):
+        torch = _torch()
+        dev = self.val.device
+        wb = _lib.load().glb_csr_transpose_work_bytes(self.n, self.nnz)
+        work = torch.empty(int(wb), dtype=torch.uint8, device=dev)
+        t_rp = torch.empty(self.n + 1, dtype=torch.int32, device=dev)
+        t_col = torch.empty(max(self.nnz, 1), dtype=torch.int32, device=dev)[: self.nnz]
+        t_val = torch.empty(max(self.nnz, 1), dtype=torch.float64, device=dev)[: self.nnz]
+        _lib.call("glb_csr_transpose", ptr(self.rowptr), ptr(self.col), ptr(self.val), self.n, self.nnz, ptr(t_rp),
+                  ptr(t_col), ptr(t_val), ptr(work), int(wb), cur_stream())
+        return DeviceCSR(t_rp, t_col, t_val, self.n)
+
+
+class PoissonOperator:
+    """P = D^-1 W^T (fp32 CSR) and RW = W^T D^-1 (fp64 values on the same pattern), device resident.
+    Setup lines of ssl.poisson._fit, reference graphlearning/ssl.py:615-617, 634-644."""
+
+    def __init__(self, W):
+        torch = _torch()
+        self.W = W if isinstance(W, DeviceCSR) else DeviceCSR.from_scipy(W)
+        self.n = self.W.n
+        self.deg = self.W.degree(skip_diagonal=True)
+        Wt = self.W.transpose()
+        self.rowptr, self.col, self.nnz = Wt.rowptr, Wt.col, Wt.nnz
+        self.P_val = torch.empty(max(self.nnz, 1), dtype=torch.float32, device=self.deg.device)
+        self.RW_val = torch.empty(max(self.nnz, 1), dtype=torch.float64, device=self.deg.device)
+        _lib.call("glb_poisson_scale", ptr(Wt.rowptr), ptr(Wt.col), ptr(Wt.val), ptr(self.deg), self.n,
+                  ptr(self.P_val), ptr(self.RW_val), cur_stream())
+        self._plans = {}
+
+    def __del__(self):
+        try:
+            for p in self._plans.values():
+                _lib.load().glb_poisson_plan_destroy(p)
+        except Exception:
+            pass
+
+    def plan(self, ldu):
+        if ldu not in self._plans:
+            h = ctypes.c_void_p()
+            _lib.call("glb_poisson_plan_create", ctypes.byref(h), ptr(self.rowptr), self.n, self.nnz, int(ldu),
+                      cur_stream())
+            self._plans[ldu] = h
+        return self._plans[ldu]
+
+    def is_persistent(self, ldu):
+        return bool(_lib.load().glb_poisson_plan_is_persistent(self.plan(ldu)))
+
+    def pack(self, X):
+        """host/device (n,c) float64 -> device (n,ldu) fp32, zero padded."""
+        torch = _torch()
+        X = torch.as_tensor(X, dtype=torch.float64).to(self.deg.device).contiguous()
+        n, c = X.shape
+        ldu = _lib.padded_ld(c)
+        out = torch.empty((n, ldu), dtype=torch.float32, device=X.device)
+        _lib.call("glb_pack_f64_to_f32", ptr(X), n, c, ptr(out), ldu, cur_stream())
+        return out
+
+    def unpack(self, U, c):
+        torch = _torch()
+        n, ldu = U.shape
+        out = torch.empty((n, c), dtype=torch.float64, device=U.device)
+        _lib.call("glb_unpack_f32_to_f64", ptr(U), n, c, ldu, ptr(out), cur_stream())
+        return out
+
+    def source_to_Db(self, source):
+        """Db = D^-1 source (ssl.py:636) in the padded fp32 layout."""
+        torch = _torch()
+        src = torch.as_tensor(source, dtype=torch.float64).to(self.deg.device)
+        return self.pack((1.0 / self.deg)[:, None] * src)
+
+    def step(self, Db, u_in, u_out):
+        _lib.call("glb_poisson_step", ptr(self.rowptr), ptr(self.col), ptr(self.P_val), ptr(Db), ptr(u_in), ptr(u_out),
+                  self.n, int(Db.shape[1]), cur_stream())
+
+    def iterate(self, Db, T, u0=None, u1=None):
+        """T iterations of u <- Db + P u from u0 (zeros by default).  Returns (u, launches)."""
+        torch = _torch()
+        ldu = int(Db.shape[1])
+        if u0 is None:
+            u0 = torch.zeros_like(Db)
+        if u1 is None:
+            u1 = torch.zeros_like(Db)
+        which, launches = ctypes.c_int(0), ctypes.c_int(0)
+        _lib.call("glb_poisson_iterate", self.plan(ldu), ptr(self.rowptr), ptr(self.col), ptr(self.P_val), ptr(Db),
+                  ptr(u0), ptr(u1), int(T), ctypes.byref(which), ctypes.byref(launches), cur_stream())
+        return (u1 if which.value else u0), launches.value
+
+    def mixing_T(self, train_ind, min_iter, max_iter):
+        """Iteration count by the reference's stopping rule (ssl.py:639-644, 667, 669)."""
+        torch = _torch()
+        dev = self.deg.device
+        v = torch.zeros(self.n, dtype=torch.float64, device=dev)
+        v[torch.as_tensor(np.asarray(train_ind), dtype=torch.long, device=dev)] = 1
+        v = v / v.sum()
+        vinf = self.deg / self.deg.sum()
+        tmp = torch.empty_like(v)
+        T, launches = ctypes.c_int(0), ctypes.c_int(0)
+        _lib.call("glb_poisson_mixing_T", ptr(self.rowptr), ptr(self.col), ptr(self.RW_val), ptr(vinf), ptr(v), ptr(tmp),
+                  self.n, int(min_iter), int(max_iter), ctypes.byref(T), ctypes.byref(launches), cur_stream())
+        return T.value

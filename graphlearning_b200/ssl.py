@@ -1,0 +1,176 @@
+"""Graph-based semi-supervised learning on the B200 backend: mirror of the hot-path classes of the reference
+graphlearning/ssl.py (base class :131-511, poisson :513-693, laplace :1106-1261).
+
+Same constructor kwargs, same fit/predict/fit_predict contract ((n,c) float64 scores in, int labels out).
+Reference errors that were sys.exit(...) strings are ValueError / RuntimeError here.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+from scipy import sparse
+
+from . import _lib, graph, utils
+
+
+class ssl:
+    """Base class.  Reference graphlearning/ssl.py:131-290, 439-481."""
+
+    def __init__(self, W, class_priors):
+        if W is None:
+            self.graph = None
+        else:
+            self.set_graph(W)
+        self.prob = None
+        self.fitted = False
+        self.name = ""
+        self.accuracy_filename = ""
+        self.requires_eig = False
+        self.onevsrest = False
+        self.similarity = True
+        self.class_priors = class_priors
+        if self.class_priors is not None:
+            self.class_priors = self.class_priors / np.sum(self.class_priors)
+        self.weights = 1
+        self.class_priors_error = 1
+
+    def set_graph(self, W):
+        self.graph = W if type(W) == graph.graph else graph.graph(W)
+
+    def volume_label_projection(self):
+        """ssl.py:172-209 (host post-processing of the scores; not on the device path)."""
+        k = self.prob.shape[1]
+        if type(self.weights) == int:
+            self.weights = np.ones((k,))
+        dt = -0.1 if self.similarity else 0.1
+        i, err = 0, 1
+        while i < 1e4 and err > 1e-3:
+            i += 1
+            class_size = np.mean(utils.labels_to_onehot(self.predict(), k), axis=0)
+            grad = class_size - self.class_priors
+            err = np.max(np.absolute(grad))
+            self.weights += dt * grad
+            self.weights = self.weights / self.weights[0]
+        self.class_priors_error = err
+        return self.predict()
+
+    def predict(self, ignore_class_priors=False):
+        """ssl.py:230-266: global min-max scaling, then argmax (first maximum wins)."""
+        if not self.fitted:
+            raise RuntimeError("Model has not been fitted yet.")
+        w = 1 if ignore_class_priors else self.weights
+        scores = self.prob - np.min(self.prob)
+        scores = scores / np.max(scores)
+        if self.similarity:
+            return np.argmax(scores * w, axis=1)
+        return np.argmin(scores * w, axis=1)
+
+    def fit_predict(self, train_ind, train_labels, all_labels=None):
+        self.fit(train_ind, train_labels, all_labels=all_labels)
+        return self.predict()
+
+    def fit(self, train_ind, train_labels, all_labels=None):
+        """ssl.py:439-481."""
+        if self.graph is None:
+            raise RuntimeError("SSL object has no graph. Use set_graph() to provide a graph for SSL.")
+        self.fitted = True
+        train_ind = np.asarray(train_ind)
+        train_labels = np.asarray(train_labels)
+        if self.onevsrest:
+            unique_labels = np.unique(train_labels)
+            self.prob = np.zeros((self.graph.num_nodes, len(unique_labels)))
+            for i, l in enumerate(unique_labels):
+                self.prob[:, i] = self._fit(train_ind, train_labels == l)
+        else:
+            self.prob = self._fit(train_ind, train_labels, all_labels=all_labels)
+        if self.class_priors is not None:
+            self.volume_label_projection()
+        return self.prob
+
+    def _fit(self, train_ind, train_labels, all_labels=None):
+        raise NotImplementedError("Must override _fit")
+
+
+def _as_ptr(a):
+    return ctypes.c_void_p(a.ctypes.data)
+
+
+class poisson(ssl):
+    """Poisson learning.  Reference graphlearning/ssl.py:513-693.
+
+    solver='gradient_descent' runs the fused CSR-SpMM iterate on the GPU (poisson.cu) through the
+    host-buffer entry point glb_poisson_gd_host; `use_cuda` is accepted for API compatibility (the GPU
+    is always used).  Attribute `iterations` holds the iteration count T of the last fit.
+    """
+
+    def __init__(self, W=None, class_priors=None, solver="conjugate_gradient", p=1, use_cuda=False, min_iter=50,
+                 max_iter=1000, tol=1e-3, spectral_cutoff=10):
+        super().__init__(W, class_priors)
+        if solver not in ["conjugate_gradient", "spectral", "gradient_descent"]:
+            raise ValueError("Invalid Poisson solver")
+        self.solver = solver
+        self.p = p
+        if p != 1:
+            self.solver = "spectral"
+        self.use_cuda = use_cuda
+        self.min_iter = min_iter
+        self.max_iter = max_iter
+        self.tol = tol
+        self.spectral_cutoff = spectral_cutoff
+        self.iterations = None
+        self.gpu_launches = 0
+        fname = "_poisson"
+        if self.p != 1:
+            fname += "_p%.2f" % p
+        if self.solver == "spectral":
+            fname += "_N%d" % self.spectral_cutoff
+        self.accuracy_filename = fname
+        self.name = "Poisson Learning"
+
+    def _source(self, train_ind, train_labels):
+        """ssl.py:611-622."""
+        n = self.graph.num_nodes
+        k = len(np.unique(train_labels))
+        onehot = utils.labels_to_onehot(train_labels, k)
+        source = np.zeros((n, onehot.shape[1]))
+        source[train_ind] = onehot - np.mean(onehot, axis=0)
+        return source, k
+
+    def _fit(self, train_ind, train_labels, all_labels=None):
+        W = self.graph.weight_matrix
+        n = self.graph.num_nodes
+        source, k = self._source(train_ind, train_labels)
+        if self.solver == "gradient_descent":
+            if source.shape[1] != k:
+                # the reference adds an (n,k) array to an (n,width) one here and fails in numpy broadcasting
+                raise ValueError("train_labels must be 0..k-1 for the gradient_descent solver")
+            rp = np.ascontiguousarray(W.indptr, dtype=np.int32)
+            col = np.ascontiguousarray(W.indices, dtype=np.int32)
+            val = np.ascontiguousarray(W.data, dtype=np.float64)
+            src = np.ascontiguousarray(source, dtype=np.float64)
+            ti = np.ascontiguousarray(train_ind, dtype=np.int64)
+            u = np.empty((n, k), dtype=np.float64)
+            T, nl = ctypes.c_int(0), ctypes.c_int(0)
+            _lib.call("glb_poisson_gd_host", _as_ptr(rp), _as_ptr(col), _as_ptr(val), n, len(col), _as_ptr(src), k,
+                      _as_ptr(ti), len(ti), int(self.min_iter), int(self.max_iter), _as_ptr(u), ctypes.byref(T),
+                      ctypes.byref(nl))
+            self.iterations = T.value
+            self.gpu_launches = nl.value
+            return u
+        raise NotImplementedError("poisson solver %r is not built on the B200 backend yet" % self.solver)
+
+
+def ssl_accuracy(pred_labels, true_labels, train_ind):
+    """Accuracy over the unlabelled points, in percent.  Reference graphlearning/ssl.py:1795-1834."""
+    pred_labels = np.asarray(pred_labels)
+    true_labels = np.asarray(true_labels)
+    mask = np.ones(len(pred_labels), dtype=bool)
+    if type(train_ind) != np.ndarray:
+        print("Warning: ssl_accuracy has been updated and now requires the user to provide the indices of the "
+              "labeled points, and not just the number of labels.")
+    else:
+        mask[train_ind] = False
+    p, t = pred_labels[mask], true_labels[mask]
+    I = t >= 0
+    return 100 * np.mean(p[I] == t[I])

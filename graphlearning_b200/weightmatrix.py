@@ -1,0 +1,94 @@
+"""kNN weight matrices: mirror of reference graphlearning/weightmatrix.py:68-187 (knn) and :297-429 (knnsearch).
+
+knnsearch routes method in {None (d>5), 'brute', 'annoy'} with euclidean/angular similarity to the exact
+tiled brute-force search on the GPU (knn.cu) - a strict quality superset of the reference's approximate
+annoy default.  method='kdtree' (the reference default for d<=5) stays scipy's cKDTree, exactly as in the
+reference (weightmatrix.py:349-352).
+"""
+from __future__ import annotations
+
+import numpy as np
+from scipy import sparse, spatial
+
+
+def sparse_max(A, B):
+    """Elementwise max of two sparse matrices.  Reference graphlearning/utils.py:263-286."""
+    I = (A + B) > 0
+    IB = B > A
+    IA = I - IB
+    return A.multiply(IA) + B.multiply(IB)
+
+
+def knnsearch(X, k, method=None, similarity="euclidean", dataset=None, metric="raw"):
+    """k nearest neighbours including self -> (knn_ind (n,k) int, knn_dist (n,k) float64), ascending."""
+    X = np.asarray(X)
+    d = X.shape[1]
+    if method is None:
+        method = "kdtree" if d <= 5 else "brute"
+    if method == "annoy":
+        method = "brute"
+    if method not in ("kdtree", "brute"):
+        raise ValueError("Invalid choice of knnsearch method " + str(method))
+    if similarity not in ("angular", "euclidean"):
+        raise ValueError("Invalid choice of similarity " + str(similarity))
+    if method == "kdtree":
+        Y = X / np.linalg.norm(X, axis=1)[:, None] if similarity == "angular" else X
+        tree = spatial.cKDTree(Y)
+        knn_dist, knn_ind = tree.query(Y, k=k)
+        return knn_ind, knn_dist
+    from . import knn_gpu
+    return knn_gpu.knnsearch_gpu(X, k, similarity=similarity)
+
+
+def knn(data, k, kernel="gaussian", eta=None, symmetrize=True, metric="raw", similarity="euclidean", knn_data=None):
+    """kNN weight matrix as a scipy CSR (float64, zero diagonal).  Reference weightmatrix.py:68-187."""
+    k += 1                                                        # :119 (self is counted)
+    if knn_data is not None:
+        knn_ind, knn_dist = knn_data
+    elif type(data) is str:
+        raise NotImplementedError("loading stored kNN data by dataset name is outside the B200 hot path")
+    else:
+        knn_ind, knn_dist = knnsearch(data, k, similarity=similarity)
+    knn_ind = np.asarray(knn_ind)
+    knn_dist = np.asarray(knn_dist, dtype=np.float64)
+    n = knn_ind.shape[0]
+    k = np.minimum(knn_ind.shape[1], k)
+    knn_ind = knn_ind[:, :k]
+    knn_dist = knn_dist[:, :k]
+    if eta is None:
+        if kernel == "uniform":
+            weights = np.ones_like(knn_dist)
+        elif kernel == "gaussian":
+            D = knn_dist * knn_dist
+            eps = D[:, k - 1]
+            weights = np.exp(-4 * D / eps[:, None])
+        elif kernel == "symgaussian":
+            eps = knn_dist[:, k - 1]
+            weights = np.exp(-4 * knn_dist * knn_dist / eps[:, None] / eps[knn_ind])
+        elif kernel == "distance":
+            weights = knn_dist
+        elif kernel == "singular":
+            weights = knn_dist.copy()
+            weights[knn_dist == 0] = 1
+            weights = 1 / weights
+        else:
+            raise ValueError("Invalid choice of kernel: " + str(kernel))
+    else:
+        D = knn_dist * knn_dist
+        eps = D[:, k - 1]
+        weights = eta(D / eps)
+    knn_ind = knn_ind.flatten()
+    weights = weights.flatten()
+    self_ind = (np.ones((n, k)) * np.arange(n)[:, None]).flatten()
+    W = sparse.coo_matrix((weights, (self_ind, knn_ind)), shape=(n, n)).tocsr()
+    if symmetrize:
+        if kernel in ["distance", "uniform", "singular"]:
+            W = sparse_max(W, W.transpose())
+        elif kernel == "symgaussian":
+            W = W + W.T.multiply(W.T > W) - W.multiply(W.T > W)
+        else:
+            W = (W + W.transpose()) / 2
+    W = sparse.csr_matrix(W)
+    W.setdiag(0)
+    W.eliminate_zeros()
+    return W

@@ -1,0 +1,120 @@
+/* glb200.h - C-ABI of libglb200.so: the B200 (sm_100a) implementation of GraphLearning's
+ * data-parallel hot path (kNN graph build -> Laplacian normalisation -> repeated sparse x dense
+ * iterate of ssl.poisson / ssl.laplace).
+ *
+ * The reference (jwcalder/GraphLearning v1.7.5) has no plugin registry; its only FFI is the CPython
+ * module c_code/cextensions.cpp:346-373 (raw pointers + sizes, in-place mutation, None return).
+ * Every entry point below states which reference code it replaces (file:line under /root/reference).
+ *
+ * Conventions
+ *  - every function returns 0 on success, a negative GLB_E_* for argument errors, a positive
+ *    cudaError_t for CUDA failures; glb_last_error() returns the message of the calling thread.
+ *  - "d_" pointers are DEVICE pointers, "h_" pointers are HOST pointers.  The caller owns every
+ *    buffer; the library owns only opaque plan handles (explicit create/destroy).
+ *  - `stream` is a cudaStream_t passed as void* (NULL = default stream).  Device entry points are
+ *    stream-ordered and do not synchronise unless stated.
+ *  - CSR matrices: int32 rowptr[n+1], int32 col[nnz], values fp32 (iterate) or fp64 (setup).
+ *  - dense label matrices on the device are row-major n x ldu fp32 with ldu >= c, ldu a power of two
+ *    in {4,8,...,128} or a multiple of 128 (glb_padded_ld(c) gives it); padding columns are zero.
+ */
+#ifndef GLB200_H
+#define GLB200_H
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define GLB_API __attribute__((visibility("default")))
+#else
+#define GLB_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GLB_E_INVALID   (-1)   /* bad argument (null pointer, negative size, unsupported option) */
+#define GLB_E_NOGPU     (-2)   /* no CUDA device / wrong architecture */
+#define GLB_E_NOMEM     (-3)
+#define GLB_E_UNSUPPORTED (-4)
+
+GLB_API int glb_version(void);
+GLB_API const char *glb_last_error(void);
+/* Number of SMs etc. of the current device; fails with GLB_E_NOGPU when there is none. */
+GLB_API int glb_device_info(int *sm_count, int *cc_major, int *cc_minor, int64_t *hbm_bytes);
+/* Leading dimension used for an n x c dense label matrix. */
+GLB_API int glb_padded_ld(int c);
+
+/* ---------------------------------------------------------------------------------------------
+ * Graph normalisation.   graph.degree_vector (graphlearning/graph.py:108-122), degree_matrix(p=-1)
+ * (:210-233) and the setup lines of ssl.poisson._fit (graphlearning/ssl.py:615-616, 634-644).
+ * ------------------------------------------------------------------------------------------- */
+/* deg[i] = sum_j W[i,j] (fp64, stored order).  Replaces W*ones (graph.py:121).  skip_diagonal != 0 leaves
+ * W[i,i] out (the degrees of W - diag(W), ssl.py:615-617); d_col may be NULL otherwise. */
+GLB_API int glb_csr_degree(const int32_t *d_rowptr, const int32_t *d_col, const double *d_val, int64_t n, int skip_diagonal,
+                   double *d_deg, void *stream);
+
+/* Transpose a CSR matrix (fp64 values); output is canonical (columns sorted inside each row).
+ * Replaces W.transpose() + the CSC->CSR conversion scipy does inside ssl.py:635,644.
+ * d_work: scratch of glb_csr_transpose_work_bytes(nnz) bytes. */
+GLB_API int64_t glb_csr_transpose_work_bytes(int64_t n, int64_t nnz);
+GLB_API int glb_csr_transpose(const int32_t *d_rowptr, const int32_t *d_col, const double *d_val, int64_t n, int64_t nnz,
+                      int32_t *d_t_rowptr, int32_t *d_t_col, double *d_t_val, void *d_work, int64_t work_bytes,
+                      void *stream);
+
+/* From Wt = W^T (CSR, fp64; diagonal entries are treated as zero, ssl.py:615-616) and deg = W*1:
+ *   P_val[j]  = (float)( Wt_val[j] / deg[row(j)] )      P  = D^-1 W^T   (ssl.py:634-635)
+ *   RW_val[j] =          Wt_val[j] / deg[col(j)]        RW = W^T D^-1   (ssl.py:644)
+ * Either output may be NULL. */
+GLB_API int glb_poisson_scale(const int32_t *d_t_rowptr, const int32_t *d_t_col, const double *d_t_val, const double *d_deg,
+                      int64_t n, float *d_P_val, double *d_RW_val, void *stream);
+
+/* dst (n x ldu fp32, padded with zeros) <- src (n x c fp64), and back.  labels <-> device layout. */
+GLB_API int glb_pack_f64_to_f32(const double *d_src, int64_t n, int c, float *d_dst, int ldu, void *stream);
+GLB_API int glb_unpack_f32_to_f64(const float *d_src, int64_t n, int c, int ldu, double *d_dst, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Poisson iterate  u <- Db + P u.   Replaces the loop body graphlearning/ssl.py:668 (CPU: scipy
+ * csr_matvecs) and :658 (torch.sparse.addmm).
+ * ------------------------------------------------------------------------------------------- */
+/* One iteration per call (one kernel launch): d_u_out = d_Db + P * d_u_in.  u_in != u_out. */
+GLB_API int glb_poisson_step(const int32_t *d_rowptr, const int32_t *d_col, const float *d_val, const float *d_Db,
+                     const float *d_u_in, float *d_u_out, int64_t n, int ldu, void *stream);
+
+/* Plan for T iterations in ONE persistent cooperative launch (CSR slab + Db slab staged in shared
+ * memory, hand-rolled grid barrier between iterations, u ping-pongs between d_u0 and d_u1).
+ * The plan only records the row partition and launch geometry for (rowptr, n, ldu). */
+typedef struct glb_poisson_plan glb_poisson_plan;
+GLB_API int glb_poisson_plan_create(glb_poisson_plan **plan, const int32_t *d_rowptr, int64_t n, int64_t nnz, int ldu,
+                            void *stream);
+GLB_API int glb_poisson_plan_destroy(glb_poisson_plan *plan);
+/* 1 when the plan runs as a single persistent kernel, 0 when it falls back to one launch per iteration
+ * (graph too large for the shared-memory slabs or the cooperative grid). */
+GLB_API int glb_poisson_plan_is_persistent(const glb_poisson_plan *plan);
+/* Runs T iterations starting from d_u0.  The result is in d_u0 when T is even, d_u1 when T is odd;
+ * *result_in_u1 (host int, may be NULL) says which.  launches (host, may be NULL) += kernels launched. */
+GLB_API int glb_poisson_iterate(glb_poisson_plan *plan, const int32_t *d_rowptr, const int32_t *d_col, const float *d_val,
+                        const float *d_Db, float *d_u0, float *d_u1, int T, int *result_in_u1, int *launches,
+                        void *stream);
+
+/* Stopping rule of ssl.py:667,669: v <- RW v (fp64) from v0 = indicator(train)/m until
+ * T >= min_iter and max|v - vinf| <= 1/n, or T == max_iter.  Synchronises the stream (T is a host
+ * value).  d_v is overwritten; d_tmp is n doubles of scratch. */
+GLB_API int glb_poisson_mixing_T(const int32_t *d_rw_rowptr, const int32_t *d_rw_col, const double *d_rw_val,
+                         const double *d_vinf, double *d_v, double *d_tmp, int64_t n, int min_iter, int max_iter,
+                         int *T_out, int *launches, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Host-buffer entry point: the whole gradient-descent branch of ssl.poisson._fit
+ * (graphlearning/ssl.py:615-670) with HOST inputs/outputs - what the reference's Python would bind in
+ * place of its `while` loop.  W is the scipy CSR weight matrix (canonical or not), source is the
+ * n x c fp64 Poisson source term (ssl.py:619-622), train_ind the m labelled nodes.  u_out is n x c fp64.
+ * Copies host->device, builds P/RW on the device, finds T by the reference's stopping rule (or uses
+ * min_iter == max_iter), iterates, copies back.  T_done/launches may be NULL.
+ * ------------------------------------------------------------------------------------------- */
+GLB_API int glb_poisson_gd_host(const int32_t *h_rowptr, const int32_t *h_col, const double *h_val, int64_t n, int64_t nnz,
+                        const double *h_source, int c, const int64_t *h_train_ind, int64_t m, int min_iter,
+                        int max_iter, double *h_u_out, int *T_done, int *launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GLB200_H */

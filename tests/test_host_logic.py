@@ -1,0 +1,76 @@
+"""Host-side mirror of the reference interface (no GPU): weight matrices, graph, predict, accuracy, trainsets."""
+import numpy as np
+import pytest
+from scipy import sparse
+
+import graphlearning_b200 as gl
+from oracle import gl_oracle as orc
+
+
+def same_csr(A, B):
+    A = sparse.csr_matrix(A); B = sparse.csr_matrix(B)
+    A.sort_indices(); B.sort_indices()
+    assert np.array_equal(A.indptr, B.indptr) and np.array_equal(A.indices, B.indices)
+    assert np.array_equal(A.data, B.data)
+
+
+@pytest.mark.parametrize("kernel", ["gaussian", "uniform", "symgaussian", "distance", "singular"])
+@pytest.mark.parametrize("sym", [True, False])
+def test_knn_weights_match_reference(small, kernel, sym):
+    W = gl.weightmatrix.knn(None, 7, kernel=kernel, symmetrize=sym,
+                            knn_data=(small["knn_ind"].copy(), small["knn_dist"].copy()))
+    same_csr(W, small.csr("W_%s_%d" % (kernel, int(sym))))
+
+
+def test_knn_kdtree_path_matches_reference(moons):
+    ind, dist = gl.weightmatrix.knnsearch(moons["X"], 11)          # d=2 -> kdtree, as in the reference
+    assert np.array_equal(ind, moons["knn_ind"]) and np.array_equal(dist, moons["knn_dist"])
+    same_csr(gl.weightmatrix.knn(moons["X"], 10), moons.csr("W"))
+    same_csr(gl.weightmatrix.knn(moons["X"], 10, symmetrize=False), moons.csr("Wd"))
+
+
+def test_graph_degree_and_laplacian(moons):
+    G = gl.graph(moons.csr("W"))
+    assert G.num_nodes == 500
+    assert np.array_equal(G.degree_vector(), moons["deg"])
+    for nm in ("combinatorial", "randomwalk", "normalized"):
+        same_csr(G.laplacian(normalization=nm), moons.csr("L_" + nm))
+    with pytest.raises(ValueError):
+        G.laplacian(normalization="bogus")
+
+
+def test_predict_and_accuracy(moons):
+    m = gl.ssl.poisson(moons.csr("W"), solver="gradient_descent")
+    with pytest.raises(RuntimeError):
+        m.predict()
+    m.prob = moons["u_gd"]; m.fitted = True
+    assert np.array_equal(m.predict(), moons["p_gd"])
+    acc = gl.ssl.ssl_accuracy(m.predict(), moons["labels"], moons["train_ind"])
+    assert acc == orc.ssl_accuracy(moons["p_gd"], moons["labels"], moons["train_ind"])
+    assert acc > 95
+
+
+def test_invalid_options():
+    with pytest.raises(ValueError):
+        gl.ssl.poisson(None, solver="nope")
+    with pytest.raises(ValueError):
+        gl.weightmatrix.knnsearch(np.zeros((4, 2)), 2, method="bogus")
+    with pytest.raises(ValueError):
+        gl.weightmatrix.knnsearch(np.zeros((4, 2)), 2, similarity="hamming")
+    with pytest.raises(RuntimeError):
+        gl.ssl.poisson(None, solver="gradient_descent").fit(np.array([0]), np.array([0]))
+
+
+def test_trainsets_generate_is_stratified_and_seeded():
+    labels = np.repeat(np.arange(4), 25)
+    a = gl.trainsets.generate(labels, rate=3, seed=5)
+    b = gl.trainsets.generate(labels, rate=3, seed=5)
+    assert np.array_equal(a, b) and len(a) == 12
+    assert np.array_equal(np.bincount(labels[a]), [3, 3, 3, 3])
+    sets = gl.trainsets.generate(labels, rate=2, num_trials=3, seed=1)
+    assert len(sets) == 3
+
+
+def test_labels_to_onehot_widens():
+    oh = gl.utils.labels_to_onehot(np.array([0, 3, 1]), 2)
+    assert oh.shape == (3, 4) and oh.sum() == 3

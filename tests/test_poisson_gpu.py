@@ -1,0 +1,260 @@
+"""Parity of the CUDA Poisson path (through the C-ABI) against the oracle and the reference-generated goldens.
+
+Tolerance (north_star): label scores fp32 within 1e-5 relative = max|u - u_ref| / max|u_ref| <= 1e-5 after the
+same iteration count; predicted labels identical; integer/index work (transpose pattern, T) bit-exact.
+"""
+import ctypes
+
+import numpy as np
+import pytest
+from scipy import sparse
+
+from conftest import rel_err
+from oracle import c_oracle
+from oracle import gl_oracle as orc
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def gl():
+    import graphlearning_b200 as gl
+    return gl
+
+
+@pytest.fixture(scope="module")
+def dev():
+    from graphlearning_b200 import device
+    return device
+
+
+def random_knn_graph(n, k, seed=0, symmetric=True):
+    """kNN-shaped random graph without a search: k random neighbours per row, gaussian-like weights."""
+    rng = np.random.default_rng(seed)
+    rows = np.repeat(np.arange(n), k)
+    cols = rng.integers(0, n, n * k)
+    w = np.exp(-4 * rng.random(n * k))
+    W = sparse.coo_matrix((w, (rows, cols)), shape=(n, n)).tocsr()
+    if symmetric:
+        W = (W + W.T) / 2
+    W = sparse.csr_matrix(W)
+    W.setdiag(0)
+    W.eliminate_zeros()
+    return W
+
+
+# ---- through the reference-facing API (host buffers in, host buffers out) ----------------------------
+def test_two_moons_default_stopping_rule(gl, moons):
+    ti = moons["train_ind"]; tl = moons["labels"][ti]
+    _, T_ref = orc.poisson_gd(moons.csr("W"), ti, tl, return_iters=True)
+    m = gl.ssl.poisson(moons.csr("W"), solver="gradient_descent")
+    u = m.fit(ti, tl)
+    assert m.iterations == T_ref                       # integer work: exact
+    assert u.shape == (500, 2) and u.dtype == np.float64
+    assert rel_err(u, moons["u_gd"]) <= TOL
+    assert np.array_equal(m.predict(), moons["p_gd"])
+    assert m.gpu_launches > 0
+
+
+def test_two_moons_fixed_T_and_directed(gl, moons):
+    ti = moons["train_ind"]; tl = moons["labels"][ti]
+    u = gl.ssl.poisson(moons.csr("W"), solver="gradient_descent", min_iter=80, max_iter=80).fit(ti, tl)
+    assert rel_err(u, moons["u_gd_T80"]) <= TOL
+    md = gl.ssl.poisson(moons.csr("Wd"), solver="gradient_descent")      # examples/poisson_directed.py
+    ud = md.fit(ti, tl)
+    _, T_ref = orc.poisson_gd(moons.csr("Wd"), ti, tl, return_iters=True)
+    assert md.iterations == T_ref
+    assert rel_err(ud, moons["u_gd_directed"]) <= TOL
+    assert np.array_equal(md.predict(), moons["p_gd_directed"])
+
+
+@pytest.mark.parametrize("T", [50, 200])
+def test_blobs_ten_classes(gl, blobs, T):
+    tb = blobs["train_ind"]
+    m = gl.ssl.poisson(blobs.csr("W"), solver="gradient_descent", min_iter=T, max_iter=T)
+    u = m.fit(tb, blobs["labels"][tb])
+    assert m.iterations == T
+    assert rel_err(u, blobs["u_gd_T%d" % T]) <= TOL
+    assert np.array_equal(m.predict(), blobs["p_gd_T%d" % T])
+
+
+def test_fit_predict_accuracy(gl, moons):
+    ti = moons["train_ind"]
+    pred = gl.ssl.poisson(moons.csr("W"), solver="gradient_descent").fit_predict(ti, moons["labels"][ti])
+    assert gl.ssl.ssl_accuracy(pred, moons["labels"], ti) > 95
+
+
+def test_unsorted_and_diagonal_input(gl, moons):
+    """W with explicit diagonal entries and unsorted column indices gives the same answer (ssl.py:615-616)."""
+    W = moons.csr("W")
+    ti = moons["train_ind"]; tl = moons["labels"][ti]
+    Wd = sparse.csr_matrix(W + sparse.identity(500) * 3.0)
+    perm = np.random.default_rng(0)
+    for i in range(500):                                   # shuffle the stored order inside each row
+        s, e = Wd.indptr[i], Wd.indptr[i + 1]
+        p = perm.permutation(e - s)
+        Wd.indices[s:e] = Wd.indices[s:e][p]; Wd.data[s:e] = Wd.data[s:e][p]
+    Wd.has_sorted_indices = False
+    g = gl.graph(W); g.weight_matrix = Wd
+    u = gl.ssl.poisson(g, solver="gradient_descent", min_iter=80, max_iter=80).fit(ti, tl)
+    assert rel_err(u, moons["u_gd_T80"]) <= TOL
+
+
+def test_isolated_node_propagates_nan_like_reference(gl):
+    W = random_knn_graph(200, 5, seed=1).tolil()
+    W[7, :] = 0; W[:, 7] = 0
+    W = sparse.csr_matrix(W); W.eliminate_zeros()
+    ti = np.array([0, 1, 2, 3]); tl = np.array([0, 1, 0, 1])
+    with np.errstate(all="ignore"):
+        u_ref = orc.poisson_gd(W, ti, tl, min_iter=20, max_iter=20)
+    u = gl.ssl.poisson(W, solver="gradient_descent", min_iter=20, max_iter=20).fit(ti, tl)
+    assert np.array_equal(np.isnan(u), np.isnan(u_ref))
+    ok = ~np.isnan(u_ref)
+    assert np.max(np.abs(u[ok] - u_ref[ok])) <= TOL * np.max(np.abs(u_ref[ok]))
+
+
+def test_bad_sizes_raise(gl):
+    from graphlearning_b200 import _lib
+    lib = _lib.load()
+    assert lib.glb_poisson_gd_host(None, None, None, 0, 0, None, 2, None, 0, 1, 1, None, None, None) == -1
+
+
+# ---- device-resident building blocks ------------------------------------------------------------------
+def test_degree_transpose_scale_bit_exact(dev, blobs):
+    W = random_knn_graph(3000, 7, seed=3, symmetric=False)
+    W = sparse.csr_matrix(W + sparse.identity(3000) * 0.5)        # with a diagonal to be skipped
+    d = dev.DeviceCSR.from_scipy(W)
+    W0 = sparse.csr_matrix(W - sparse.spdiags(W.diagonal(), 0, 3000, 3000)); W0.eliminate_zeros()
+    assert np.array_equal(d.degree(skip_diagonal=False).cpu().numpy(), W * np.ones(3000))
+    assert np.allclose(d.degree(skip_diagonal=True).cpu().numpy(), W0 * np.ones(3000), rtol=1e-15, atol=0)
+    Wt = d.transpose().to_scipy()
+    ref = sparse.csr_matrix(W.T); ref.sort_indices()
+    assert np.array_equal(Wt.indptr, ref.indptr) and np.array_equal(Wt.indices, ref.indices)
+    assert np.array_equal(Wt.data, ref.data)
+    op = dev.PoissonOperator(W)
+    s = orc.poisson_gd_setup(W, np.array([0, 1]), np.array([0, 1]))
+    P = sparse.csr_matrix((op.P_val.cpu().numpy()[:op.nnz], op.col.cpu().numpy(), op.rowptr.cpu().numpy()),
+                          shape=(3000, 3000))
+    P.eliminate_zeros()
+    Pref = s["P"].copy(); Pref.sort_indices(); Pref.eliminate_zeros()
+    assert np.array_equal(P.indices, Pref.indices)
+    assert np.allclose(P.data, Pref.data, rtol=1e-7, atol=0)          # fp32 rounding of an fp64 product
+    RW = sparse.csr_matrix((op.RW_val.cpu().numpy()[:op.nnz], op.col.cpu().numpy(), op.rowptr.cpu().numpy()),
+                           shape=(3000, 3000))
+    RW.eliminate_zeros()
+    RWref = s["RW"].copy(); RWref.sort_indices(); RWref.eliminate_zeros()
+    assert np.allclose(RW.data, RWref.data, rtol=1e-15, atol=0)
+
+
+@pytest.mark.parametrize("c", [1, 2, 3, 4, 7, 10, 16, 17, 40, 100, 130])
+def test_step_and_persistent_kernels_every_width(dev, c):
+    """Both kernels against the plain-C fp64 oracle for every lane mapping (ldu = 4 ... 256)."""
+    import torch
+    W = random_knn_graph(2500, 9, seed=c)
+    op = dev.PoissonOperator(W)
+    rng = np.random.default_rng(c)
+    Db64 = rng.normal(size=(2500, c)) * (rng.random((2500, 1)) < 0.05)     # sparse-ish dense source
+    s = orc.poisson_gd_setup(W, np.array([0]), np.array([0]))
+    Db = op.pack(Db64)
+    assert Db.shape[1] == dev._lib.padded_ld(c)
+    T = 25
+    ref = c_oracle.poisson_iterate(s["P"], Db64, T)
+    # one launch per iteration
+    u_in = torch.zeros_like(Db); u_out = torch.zeros_like(Db)
+    for _ in range(T):
+        op.step(Db, u_in, u_out)
+        u_in, u_out = u_out, u_in
+    got_step = op.unpack(u_in, c).cpu().numpy()
+    assert rel_err(got_step, ref) <= TOL
+    # planned iterate (persistent cooperative kernel when it fits)
+    u, launches = op.iterate(Db, T)
+    got = op.unpack(u, c).cpu().numpy()
+    assert rel_err(got, ref) <= TOL
+    if op.is_persistent(Db.shape[1]):
+        assert launches == 1
+        assert np.array_equal(got, got_step)             # same arithmetic order in both kernels
+    assert float(u[:, c:].abs().max()) == 0.0 if Db.shape[1] > c else True
+
+
+def test_iterate_T_zero_and_odd_even(dev):
+    import torch
+    W = random_knn_graph(1000, 6, seed=5)
+    op = dev.PoissonOperator(W)
+    Db = op.pack(np.random.default_rng(0).normal(size=(1000, 10)))
+    u0, _ = op.iterate(Db, 0)
+    assert float(u0.abs().max()) == 0.0
+    u3, _ = op.iterate(Db, 3)
+    u4, _ = op.iterate(Db, 4)
+    a = torch.zeros_like(Db); b = torch.zeros_like(Db)
+    op.step(Db, u3, a)
+    assert torch.equal(a, u4)
+
+
+def test_mixing_T_matches_reference_rule(dev, blobs, moons):
+    for g, key in ((moons, "W"), (moons, "Wd"), (blobs, "W")):
+        W = g.csr(key); ti = g["train_ind"]
+        _, T_ref = orc.poisson_gd(W, ti, g["labels"][ti], return_iters=True)
+        op = dev.PoissonOperator(W)
+        assert op.mixing_T(ti, 50, 1000) == T_ref
+        assert op.mixing_T(ti, 0, 7) == 7
+        assert op.mixing_T(ti, 5, 5) == 5
+
+
+# ---- north-star size (70k nodes, k=10, 10 classes) ----------------------------------------------------
+@pytest.fixture(scope="module")
+def big():
+    W = random_knn_graph(70000, 10, seed=0)
+    labels = np.random.default_rng(1).integers(0, 10, 70000)
+    ti = orc.one_per_class(labels, rate=1, seed=0)
+    return W, labels, ti
+
+
+def test_full_size_against_c_oracle(dev, big):
+    W, labels, ti = big
+    s = orc.poisson_gd_setup(W, ti, labels[ti])
+    op = dev.PoissonOperator(W)
+    assert op.is_persistent(16)
+    Db = op.source_to_Db(orc.poisson_source(70000, ti, labels[ti])[0])
+    T = 60
+    ref = c_oracle.poisson_iterate(s["P"], s["Db"], T)
+    u, launches = op.iterate(Db, T)
+    assert launches == 1
+    assert rel_err(op.unpack(u, 10).cpu().numpy(), ref) <= TOL
+
+
+def test_full_size_properties(dev, big):
+    """Size-independent properties: linearity in the source, zero class-sum invariant, step/persistent equality."""
+    import torch
+    W, labels, ti = big
+    op = dev.PoissonOperator(W)
+    rng = np.random.default_rng(2)
+    A = op.pack(rng.normal(size=(70000, 10))); B = op.pack(rng.normal(size=(70000, 10)))
+    T = 30
+    uA = op.iterate(A, T)[0].clone(); uB = op.iterate(B, T)[0].clone()
+    uAB = op.iterate(A * 2 - B, T)[0]
+    lin = 2 * uA - uB
+    assert float((uAB - lin).abs().max() / lin.abs().max()) <= 2e-5
+    src = orc.poisson_source(70000, ti, labels[ti])[0]
+    u = op.iterate(op.source_to_Db(src), 100)[0]
+    rowsum = u[:, :10].double().sum(1).abs().max()
+    assert float(rowsum) <= 1e-5 * float(u.abs().max())          # columns of the source sum to zero per row
+    a = torch.zeros_like(A); b = torch.zeros_like(A)
+    for _ in range(T):
+        op.step(A, a, b); a, b = b, a
+    assert torch.equal(a, uA)
+
+
+def test_full_size_through_host_api(gl, big):
+    W, labels, ti = big
+    m = gl.ssl.poisson(W, solver="gradient_descent", min_iter=40, max_iter=40)
+    u = m.fit(ti, labels[ti])
+    s = orc.poisson_gd_setup(W, ti, labels[ti])
+    ref = c_oracle.poisson_iterate(s["P"], s["Db"], 40)
+    assert rel_err(u, ref) <= TOL
+    # labels identical except where the reference's own top-2 margin is below the score tolerance
+    pred, pref = m.predict(), orc.predict(ref)
+    srt = np.sort(ref, axis=1)
+    margin = (srt[:, -1] - srt[:, -2]) / np.max(np.abs(ref))
+    assert np.all((pred == pref) | (margin < 2 * TOL))
+    assert np.mean(pred == pref) > 0.999
