@@ -15,21 +15,19 @@
 //                              graph the whole working set is L2 resident and a launch per iteration
 //                              (~2-3 us) would cost as much as the iteration itself.
 //
-// Lane mapping (both kernels): GROUP lanes cooperate on one matrix row.  LANES = ldu/4 lanes cover one
-// gathered row of u with one float4 each, so GROUP/LANES nonzeros are in flight per group and step.  Each
-// group first loads GROUP consecutive (col,val) pairs (coalesced / conflict-free), then broadcasts them
-// with shuffles.  Partial sums are combined across the GROUP/LANES sub-groups with xor-shuffles.
+// Lane mapping (both kernels): LANES = ldu/4 lanes own one matrix row; lane li holds the float4 of output
+// columns [4*li, 4*li+4) (for ldu > 128 it loops over column tiles).  One warp-wide LDG.128 therefore
+// gathers 32/LANES complete rows of u, each row = one 64-byte (ldu=16) piece of a single 128-byte line,
+// which is what the L1TEX tag stage likes (one tag look-up per gathered row).  Each lane walks the
+// nonzeros of its row UNROLL at a time: all UNROLL gathers are issued before the first FMA so that
+// every thread keeps UNROLL L2 requests in flight; there is no cross-lane reduction at all.
+#include <stdlib.h>
 #include <string.h>
 #include "common.cuh"
 
 namespace glb {
 
-template <int GROUP>
-__device__ __forceinline__ unsigned group_mask(int lane)
-{
-    if (GROUP == 32) return 0xffffffffu;
-    return ((1u << GROUP) - 1u) << ((lane / GROUP) * GROUP);
-}
+constexpr int kUnroll = 8;      // nonzeros in flight per lane in the one-launch-per-iteration kernel
 
 __device__ __forceinline__ void fma4(float4 &acc, float a, const float4 &x)
 {
@@ -46,72 +44,70 @@ __device__ __forceinline__ float4 load_u4(const float *p)
     return *reinterpret_cast<const float4 *>(p);   // coherent at L1 after the grid barrier's fence
 }
 
-// One matrix row times u, for the column tile starting at `ctile`.  beg/end index col/val (global or
-// shared).  Returns the finished float4 (valid in the lanes of sub-group 0).
-template <int GROUP, int LANES, bool NC>
-__device__ __forceinline__ float4 row_times_u(const int *__restrict__ col, const float *__restrict__ val, int beg,
-                                              int end, const float *__restrict__ u, int ldu, int ctile, int lane)
-{
-    constexpr int NPAR = GROUP / LANES;
-    const unsigned mask = group_mask<GROUP>(lane);
-    const int gl = lane % GROUP;
-    const int sub = gl / LANES;
-    const int li = gl % LANES;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int base = beg; base < end; base += GROUP) {
-        const int my = base + gl;
-        int cj = 0;
-        float aj = 0.f;
-        if (my < end) {
-            cj = col[my];
-            aj = val[my];
-        }
-        const int cnt = min(GROUP, end - base);
-#pragma unroll
-        for (int s = 0; s < GROUP / NPAR; ++s) {
-            if (s * NPAR >= cnt) break;                      // uniform inside the group
-            const int src = s * NPAR + sub;
-            const int c = __shfl_sync(mask, cj, src, GROUP);
-            const float a = __shfl_sync(mask, aj, src, GROUP);
-            if (src < cnt) {
-                const float4 x = load_u4<NC>(u + (size_t)c * ldu + ctile + li * 4);
-                fma4(acc, a, x);
-            }
-        }
+// (col, val) of nonzero j: from the interleaved shared-memory slab or from the global CSR arrays
+struct CsrGlobal {
+    const int *__restrict__ col;
+    const float *__restrict__ val;
+    __device__ __forceinline__ void get(int j, int &c, float &a) const { c = __ldg(col + j); a = __ldg(val + j); }
+};
+struct CsrShared {
+    const int2 *cv;
+    __device__ __forceinline__ void get(int j, int &c, float &a) const
+    {
+        const int2 e = cv[j];
+        c = e.x;
+        a = __int_as_float(e.y);
     }
+};
+
+// sum_j val[j] * u[col[j], ctile + 4*li ...] over the nonzeros [beg, end) of one row
+template <bool NC, int UNROLL, typename Csr>
+__device__ __forceinline__ float4 row_times_u(const Csr &csr, int beg, int end, const float *__restrict__ u, int ldu,
+                                              int coff)
+{
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j = beg; j < end; j += UNROLL) {
+        int c[UNROLL];
+        float a[UNROLL];
+        float4 x[UNROLL];
 #pragma unroll
-    for (int off = LANES; off < GROUP; off <<= 1) {
-        acc.x += __shfl_xor_sync(mask, acc.x, off, GROUP);
-        acc.y += __shfl_xor_sync(mask, acc.y, off, GROUP);
-        acc.z += __shfl_xor_sync(mask, acc.z, off, GROUP);
-        acc.w += __shfl_xor_sync(mask, acc.w, off, GROUP);
+        for (int i = 0; i < UNROLL; ++i) {
+            c[i] = 0;
+            a[i] = 0.f;
+            if (j + i < end) csr.get(j + i, c[i], a[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < UNROLL; ++i) {
+            x[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (j + i < end) x[i] = load_u4<NC>(u + (size_t)c[i] * ldu + coff);
+        }
+#pragma unroll
+        for (int i = 0; i < UNROLL; ++i) fma4(acc, a[i], x[i]);      // a = 0, x = 0 past the end of the row
     }
     return acc;
 }
 
 // ------------------------------------------------------------------------------------------------
-// K1: one iteration per launch
+// K1: one iteration per launch, CSR read from global memory
 // ------------------------------------------------------------------------------------------------
-template <int GROUP, int LANES>
+template <int LANES>
 __global__ void __launch_bounds__(256)
 poisson_step_kernel(const int *__restrict__ rowptr, const int *__restrict__ col, const float *__restrict__ val,
                     const float *__restrict__ Db, const float *__restrict__ u_in, float *__restrict__ u_out,
                     int n, int ldu)
 {
-    const int lane = threadIdx.x & 31;
-    const int gl = lane % GROUP;
-    const long long gid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / GROUP;
-    const long long ngroups = ((long long)gridDim.x * blockDim.x) / GROUP;
-    for (long long row = gid; row < n; row += ngroups) {
+    const int li = threadIdx.x % LANES;
+    const long long rid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / LANES;
+    const long long nrid = ((long long)gridDim.x * blockDim.x) / LANES;
+    const CsrGlobal csr{col, val};
+    for (long long row = rid; row < n; row += nrid) {
         const int beg = __ldg(rowptr + row), end = __ldg(rowptr + row + 1);
-        for (int ctile = 0; ctile < ldu; ctile += LANES * 4) {
-            float4 acc = row_times_u<GROUP, LANES, true>(col, val, beg, end, u_in, ldu, ctile, lane);
-            if (gl < LANES) {
-                const size_t o = (size_t)row * ldu + ctile + gl * 4;
-                const float4 b = __ldg(reinterpret_cast<const float4 *>(Db + o));
-                acc.x += b.x; acc.y += b.y; acc.z += b.z; acc.w += b.w;
-                *reinterpret_cast<float4 *>(u_out + o) = acc;
-            }
+        for (int coff = li * 4; coff < ldu; coff += LANES * 4) {
+            float4 acc = row_times_u<true, kUnroll>(csr, beg, end, u_in, ldu, coff);
+            const size_t o = (size_t)row * ldu + coff;
+            const float4 b = __ldg(reinterpret_cast<const float4 *>(Db + o));
+            acc.x += b.x; acc.y += b.y; acc.z += b.z; acc.w += b.w;
+            *reinterpret_cast<float4 *>(u_out + o) = acc;
         }
     }
 }
@@ -125,70 +121,81 @@ __device__ __forceinline__ unsigned ld_acquire(const unsigned *p)
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ void red_release_add(unsigned *p, unsigned v)
+{
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void st_release(unsigned *p, unsigned v)
+{
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 
-// All CTAs of the (cooperatively launched, co-resident) grid meet here.  `target` is the value the
-// monotone counter reaches once every CTA has arrived for this phase.
-__device__ __forceinline__ void grid_barrier(unsigned *counter, unsigned target)
+// Grid-wide barrier between iterations (all CTAs are co-resident: cooperative launch, one per SM).
+// The u stores of a CTA are ordered before its arrival by bar.sync + a gpu-scope release; the acquire loads
+// order the next iteration's gathers after every other CTA's arrival (and drop this SM's stale L1 lines).
+//   FLAGS = false: one monotone counter, red.add by thread 0, spin until it reaches epoch * gridDim.x
+//   FLAGS = true : one flag word per CTA (128 bytes apart); CTA b stores `epoch` into its flag, thread i
+//                  spins on flag i - no serialised atomics on one L2 line.
+constexpr int kFlagStride = 32;          // unsigned words = 128 bytes
+template <bool FLAGS>
+__device__ __forceinline__ void grid_barrier(unsigned *sync_words, unsigned epoch)
 {
     __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();                       // publish this CTA's u stores
-        atomicAdd(counter, 1u);
-        while (ld_acquire(counter) < target) { }
-        __threadfence();                       // acquire: also invalidates this SM's L1 (CCTL.IVALL)
+    if (FLAGS) {
+        if (threadIdx.x == 0) st_release(sync_words + (size_t)blockIdx.x * kFlagStride, epoch);
+        if (threadIdx.x < gridDim.x)
+            while (ld_acquire(sync_words + (size_t)threadIdx.x * kFlagStride) < epoch) { }
+    } else {
+        if (threadIdx.x == 0) {
+            red_release_add(sync_words, 1u);
+            while (ld_acquire(sync_words) < epoch * gridDim.x) { }
+        }
     }
     __syncthreads();
 }
 
-constexpr int kPersistThreads = 1024;
-
-template <int GROUP, int LANES>
-__global__ void __launch_bounds__(kPersistThreads, 1)
+template <int LANES, int THREADS, int UNROLL, bool FLAGS>
+__global__ void __launch_bounds__(THREADS, 1)
 poisson_persistent_kernel(const int *__restrict__ rowptr, const int *__restrict__ col,
                           const float *__restrict__ val, const float *__restrict__ Db, float *u0, float *u1, int n,
                           int ldu, int T, int rows_per_cta, int slab_cap, unsigned *barrier_counter)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    // layout: Db slab [rows_per_cta*ldu] f32 | val [slab_cap] f32 | col [slab_cap] i32 | rp [rows_per_cta+1] i32
+    // layout: Db slab [rows_per_cta*ldu] f32 | (col,val) [slab_cap] int2 | rp [rows_per_cta+1] i32
     float *s_Db = reinterpret_cast<float *>(smem_raw);
-    float *s_val = s_Db + (size_t)rows_per_cta * ldu;
-    int *s_col = reinterpret_cast<int *>(s_val + slab_cap);
-    int *s_rp = s_col + slab_cap;
+    int2 *s_cv = reinterpret_cast<int2 *>(s_Db + (size_t)rows_per_cta * ldu);
+    int *s_rp = reinterpret_cast<int *>(s_cv + slab_cap);
 
     const int r0 = min(n, (int)blockIdx.x * rows_per_cta);
     const int r1 = min(n, r0 + rows_per_cta);
     const int nrows = r1 - r0;
     const int nz0 = rowptr[r0];
     const int nnz_slab = rowptr[r1] - nz0;
-    for (int i = threadIdx.x; i < nnz_slab; i += blockDim.x) {
-        s_col[i] = col[nz0 + i];
-        s_val[i] = val[nz0 + i];
-    }
+    for (int i = threadIdx.x; i < nnz_slab; i += blockDim.x)
+        s_cv[i] = make_int2(col[nz0 + i], __float_as_int(val[nz0 + i]));
     for (int i = threadIdx.x; i <= nrows; i += blockDim.x) s_rp[i] = rowptr[r0 + i] - nz0;
     for (int i = threadIdx.x; i < nrows * (ldu / 4); i += blockDim.x)
         reinterpret_cast<float4 *>(s_Db)[i] = reinterpret_cast<const float4 *>(Db + (size_t)r0 * ldu)[i];
     __syncthreads();
 
-    const int lane = threadIdx.x & 31;
-    const int gl = lane % GROUP;
-    const int gid = threadIdx.x / GROUP;
-    constexpr int NGROUPS = kPersistThreads / GROUP;
+    const int li = threadIdx.x % LANES;
+    const int rid = threadIdx.x / LANES;
+    constexpr int RPP = THREADS / LANES;            // rows per pass of the CTA
+    const CsrShared csr{s_cv};
 
     for (int t = 0; t < T; ++t) {
         const float *u_in = (t & 1) ? u1 : u0;
         float *u_out = (t & 1) ? u0 : u1;
-        for (int lr = gid; lr < nrows; lr += NGROUPS) {
+        for (int lr = rid; lr < nrows; lr += RPP) {
             const int beg = s_rp[lr], end = s_rp[lr + 1];
-            for (int ctile = 0; ctile < ldu; ctile += LANES * 4) {
-                float4 acc = row_times_u<GROUP, LANES, false>(s_col, s_val, beg, end, u_in, ldu, ctile, lane);
-                if (gl < LANES) {
-                    const float4 b = *reinterpret_cast<const float4 *>(s_Db + (size_t)lr * ldu + ctile + gl * 4);
-                    acc.x += b.x; acc.y += b.y; acc.z += b.z; acc.w += b.w;
-                    *reinterpret_cast<float4 *>(u_out + (size_t)(r0 + lr) * ldu + ctile + gl * 4) = acc;
-                }
+            for (int coff = li * 4; coff < ldu; coff += LANES * 4) {
+                float4 acc = row_times_u<false, UNROLL>(csr, beg, end, u_in, ldu, coff);
+                const float4 b = *reinterpret_cast<const float4 *>(s_Db + (size_t)lr * ldu + coff);
+                acc.x += b.x; acc.y += b.y; acc.z += b.z; acc.w += b.w;
+                *reinterpret_cast<float4 *>(u_out + (size_t)(r0 + lr) * ldu + coff) = acc;
             }
         }
-        if (t + 1 < T) grid_barrier(barrier_counter, (unsigned)(t + 1) * gridDim.x);
+        if (t + 1 < T) grid_barrier<FLAGS>(barrier_counter, (unsigned)(t + 1));
     }
 }
 
@@ -248,17 +255,17 @@ maxdiff_kernel(const double *__restrict__ v, const double *__restrict__ vinf, in
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-template <int GROUP, int LANES>
+template <int LANES>
 static int launch_step(const int *rp, const int *col, const float *val, const float *Db, const float *u_in,
                        float *u_out, int64_t n, int ldu, cudaStream_t st)
 {
     const int threads = 256;
-    const int64_t groups_per_block = threads / GROUP;
-    int64_t blocks = (n + groups_per_block - 1) / groups_per_block;
+    const int64_t rows_per_block = threads / LANES;
+    int64_t blocks = (n + rows_per_block - 1) / rows_per_block;
     const int64_t cap = (int64_t)sm_count() * 8 * 8;           // 8 resident CTAs/SM x 8 waves, then grid-stride
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    poisson_step_kernel<GROUP, LANES><<<(unsigned)blocks, threads, 0, st>>>(rp, col, val, Db, u_in, u_out, (int)n, ldu);
+    poisson_step_kernel<LANES><<<(unsigned)blocks, threads, 0, st>>>(rp, col, val, Db, u_in, u_out, (int)n, ldu);
     return 0;
 }
 
@@ -266,12 +273,12 @@ static int dispatch_step(const int *rp, const int *col, const float *val, const 
                          float *u_out, int64_t n, int ldu, cudaStream_t st)
 {
     switch (ldu) {
-        case 4: return launch_step<8, 1>(rp, col, val, Db, u_in, u_out, n, ldu, st);
-        case 8: return launch_step<16, 2>(rp, col, val, Db, u_in, u_out, n, ldu, st);
-        case 16: return launch_step<16, 4>(rp, col, val, Db, u_in, u_out, n, ldu, st);
-        case 32: return launch_step<32, 8>(rp, col, val, Db, u_in, u_out, n, ldu, st);
-        case 64: return launch_step<32, 16>(rp, col, val, Db, u_in, u_out, n, ldu, st);
-        default: return launch_step<32, 32>(rp, col, val, Db, u_in, u_out, n, ldu, st);
+        case 4: return launch_step<1>(rp, col, val, Db, u_in, u_out, n, ldu, st);
+        case 8: return launch_step<2>(rp, col, val, Db, u_in, u_out, n, ldu, st);
+        case 16: return launch_step<4>(rp, col, val, Db, u_in, u_out, n, ldu, st);
+        case 32: return launch_step<8>(rp, col, val, Db, u_in, u_out, n, ldu, st);
+        case 64: return launch_step<16>(rp, col, val, Db, u_in, u_out, n, ldu, st);
+        default: return launch_step<32>(rp, col, val, Db, u_in, u_out, n, ldu, st);
     }
 }
 
@@ -303,22 +310,53 @@ struct glb_poisson_plan {
     int ldu;
     int persistent;
     int grid, rows_per_cta, slab_cap;
+    int threads;
+    const void *fn;
     size_t smem_bytes;
-    unsigned *d_counter;
+    unsigned *d_counter;      // barrier words: kFlagStride * grid unsigned
 };
 
-template <int GROUP, int LANES>
-static const void *persistent_fn() { return (const void *)poisson_persistent_kernel<GROUP, LANES>; }
+// Launch geometry of the persistent kernel.  Default: 1024 threads, 8 gathers in flight per lane, per-CTA flag
+// barrier.  GLB_POISSON_VARIANT="threads,unroll,flags" (e.g. "512,16,0") selects another instantiation for
+// experiments; unknown combinations fall back to the default.
+struct PersistVariant { int threads, unroll, flags; };
 
-static const void *pick_persistent(int ldu)
+static PersistVariant persist_variant()
 {
+    PersistVariant v{1024, 8, 1};
+    const char *e = getenv("GLB_POISSON_VARIANT");
+    if (e) {
+        int t = 0, u = 0, f = 0;
+        if (sscanf(e, "%d,%d,%d", &t, &u, &f) == 3) { v.threads = t; v.unroll = u; v.flags = f; }
+    }
+    return v;
+}
+
+template <int LANES>
+static const void *persistent_fn(const PersistVariant &v, int *threads)
+{
+#define GLB_PV(T_, U_, F_)                                                      \
+    if (v.threads == T_ && v.unroll == U_ && v.flags == F_) {                   \
+        *threads = T_;                                                          \
+        return (const void *)poisson_persistent_kernel<LANES, T_, U_, (F_) != 0>; \
+    }
+    GLB_PV(1024, 8, 1) GLB_PV(1024, 8, 0) GLB_PV(1024, 4, 1) GLB_PV(1024, 4, 0)
+    GLB_PV(512, 8, 1) GLB_PV(512, 16, 1) GLB_PV(512, 16, 0) GLB_PV(768, 8, 1)
+#undef GLB_PV
+    *threads = 1024;
+    return (const void *)poisson_persistent_kernel<LANES, 1024, 8, true>;
+}
+
+static const void *pick_persistent(int ldu, int *threads)
+{
+    const PersistVariant v = persist_variant();
     switch (ldu) {
-        case 4: return persistent_fn<8, 1>();
-        case 8: return persistent_fn<16, 2>();
-        case 16: return persistent_fn<16, 4>();
-        case 32: return persistent_fn<32, 8>();
-        case 64: return persistent_fn<32, 16>();
-        default: return persistent_fn<32, 32>();
+        case 4: return persistent_fn<1>(v, threads);
+        case 8: return persistent_fn<2>(v, threads);
+        case 16: return persistent_fn<4>(v, threads);
+        case 32: return persistent_fn<8>(v, threads);
+        case 64: return persistent_fn<16>(v, threads);
+        default: return persistent_fn<32>(v, threads);
     }
 }
 
@@ -331,7 +369,7 @@ extern "C" GLB_API int glb_poisson_plan_create(glb_poisson_plan **plan, const in
     cudaStream_t st = (cudaStream_t)stream;
     glb_poisson_plan *p = new glb_poisson_plan();
     p->n = n; p->nnz = nnz; p->ldu = ldu; p->persistent = 0; p->d_counter = nullptr;
-    p->grid = 0; p->rows_per_cta = 0; p->slab_cap = 0; p->smem_bytes = 0;
+    p->grid = 0; p->rows_per_cta = 0; p->slab_cap = 0; p->smem_bytes = 0; p->threads = 0; p->fn = nullptr;
 
     int dev = 0, coop = 0, max_smem = 0;
     GLB_CUDA(cudaGetDevice(&dev));
@@ -361,16 +399,18 @@ extern "C" GLB_API int glb_poisson_plan_create(glb_poisson_plan **plan, const in
         for (int b = 0; b < grid; ++b) cap = (h_b[b + 1] - h_b[b] > cap) ? h_b[b + 1] - h_b[b] : cap;
         delete[] h_b;
         cap = (cap + 3) & ~3;
-        const size_t smem = (size_t)rpc * ldu * 4 + (size_t)cap * 8 + (size_t)(rpc + 1) * 4;
+        const size_t smem = (size_t)rpc * ldu * 4 + (size_t)cap * 8 + (size_t)(rpc + 1) * 4 + 16;
         if (smem <= (size_t)max_smem) {
-            const void *fn = pick_persistent(ldu);
+            int threads = 0;
+            const void *fn = pick_persistent(ldu, &threads);
             GLB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             int per_sm = 0;
-            GLB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kPersistThreads, smem));
-            if (per_sm >= 1 && grid <= per_sm * sms) {
+            GLB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, threads, smem));
+            if (per_sm >= 1 && grid <= per_sm * sms && grid <= threads) {
                 p->persistent = 1;
                 p->grid = grid; p->rows_per_cta = rpc; p->slab_cap = cap; p->smem_bytes = smem;
-                GLB_CUDA(cudaMalloc(&p->d_counter, sizeof(unsigned)));
+                p->threads = threads; p->fn = fn;
+                GLB_CUDA(cudaMalloc(&p->d_counter, sizeof(unsigned) * kFlagStride * grid));
             }
         }
     }
@@ -399,11 +439,11 @@ extern "C" GLB_API int glb_poisson_iterate(glb_poisson_plan *plan, const int32_t
     if (result_in_u1) *result_in_u1 = T & 1;
     if (T == 0) return 0;
     if (plan->persistent) {
-        GLB_CUDA(cudaMemsetAsync(plan->d_counter, 0, sizeof(unsigned), st));
+        GLB_CUDA(cudaMemsetAsync(plan->d_counter, 0, sizeof(unsigned) * kFlagStride * plan->grid, st));
         int n = (int)plan->n, ldu = plan->ldu, rpc = plan->rows_per_cta, cap = plan->slab_cap;
         void *args[] = {(void *)&d_rowptr, (void *)&d_col, (void *)&d_val, (void *)&d_Db, (void *)&d_u0, (void *)&d_u1,
                         (void *)&n, (void *)&ldu, (void *)&T, (void *)&rpc, (void *)&cap, (void *)&plan->d_counter};
-        GLB_CUDA(cudaLaunchCooperativeKernel(pick_persistent(ldu), dim3(plan->grid), dim3(kPersistThreads), args,
+        GLB_CUDA(cudaLaunchCooperativeKernel(plan->fn, dim3(plan->grid), dim3(plan->threads), args,
                                              plan->smem_bytes, st));
         if (launches) *launches += 1;
     } else {

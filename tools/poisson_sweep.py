@@ -1,0 +1,55 @@
+"""GPU experiment: time the persistent Poisson kernel variants (GLB_POISSON_VARIANT=threads,unroll,flags) on the
+bench graph and on a tiny graph (barrier latency).  Prints one line per variant.  Not part of the product."""
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench                                           # noqa: E402
+from graphlearning_b200 import device as gdev          # noqa: E402
+from oracle import gl_oracle as orc                    # noqa: E402
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from test_poisson_gpu import random_knn_graph          # noqa: E402
+
+
+def time_variant(W, src, variant, iters=1000, reps=3):
+    os.environ["GLB_POISSON_VARIANT"] = variant
+    op = gdev.PoissonOperator(W)
+    Db = op.source_to_Db(src)
+    u0 = torch.zeros_like(Db); u1 = torch.zeros_like(Db)
+    best = 1e9
+    for _ in range(reps + 1):
+        u0.zero_()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        u, _ = op.iterate(Db, iters, u0, u1)
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    return best * 1e3 / iters, u.clone(), op.is_persistent(int(Db.shape[1]))
+
+
+def main():
+    W, labels = bench.build_workload()
+    ti = orc.one_per_class(labels, rate=1, seed=0)
+    src = orc.poisson_source(W.shape[0], ti, labels[ti])[0]
+    Wt = random_knn_graph(148 * 16, 4, seed=1)
+    srct = np.random.default_rng(0).normal(size=(Wt.shape[0], 10))
+    ref = None
+    variants = sys.argv[1:] or ["1024,8,1", "1024,8,0", "1024,4,1", "1024,4,0", "512,8,1", "512,16,1", "512,16,0", "768,8,1"]
+    for v in variants:
+        us, u, pers = time_variant(W, src, v)
+        ust, _, _ = time_variant(Wt, srct, v, iters=2000)
+        if ref is None:
+            ref = u
+        same = bool(torch.equal(ref, u))
+        print("variant %-10s persistent=%s  %.3f us/iter (70k graph)  %.3f us/iter (tiny graph ~ barrier)  bit-equal=%s"
+              % (v, pers, us, ust, same), flush=True)
+
+
+if __name__ == "__main__":
+    main()
