@@ -24,8 +24,11 @@ SIGNATURES = {
     "glb_csr_transpose": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p,
                                   c_void_p, c_int64, c_void_p]),
     "glb_poisson_scale": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
-    "glb_pack_f64_to_f32": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int, c_void_p]),
-    "glb_unpack_f32_to_f64": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p]),
+    "glb_pack_f64_to_f32": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int, c_void_p, c_void_p]),
+    "glb_unpack_f32_to_f64": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "glb_locality_order_host": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
+    "glb_csr_permute": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
+                                c_void_p, c_void_p]),
     "glb_poisson_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
     "glb_poisson_plan_create": (c_int, [POINTER(c_void_p), c_void_p, c_int64, c_int64, c_int, c_void_p]),
     "glb_poisson_plan_destroy": (c_int, [c_void_p]),

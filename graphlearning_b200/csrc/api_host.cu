@@ -6,6 +6,9 @@
 
 namespace glb {
 
+// reorder the graph when T * nnz exceeds this (the host RCM costs about as much as ~100 iterations)
+constexpr long long kReorderMinWork = 200ll * 1000 * 1000;
+
 struct DeviceArena {           // frees everything on scope exit, whatever the return path
     std::vector<void *> ptrs;
     ~DeviceArena() { for (void *p : ptrs) cudaFree(p); }
@@ -23,13 +26,14 @@ struct DeviceArena {           // frees everything on scope exit, whatever the r
 // Db[i,:] = (1/deg[i]) * source[i,:]   (ssl.py:636), packed to n x ldu fp32
 __global__ void __launch_bounds__(256)
 scaled_pack_kernel(const double *__restrict__ src, const double *__restrict__ deg, long long n, int c,
-                   float *__restrict__ dst, int ldu)
+                   float *__restrict__ dst, int ldu, const int *__restrict__ perm)
 {
     const long long total = n * ldu;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const long long r = i / ldu;
         const int k = (int)(i - r * ldu);
-        dst[i] = (k < c) ? (float)((1.0 / deg[r]) * src[r * c + k]) : 0.f;
+        const long long sr = perm ? perm[r] : r;
+        dst[i] = (k < c) ? (float)((1.0 / deg[sr]) * src[sr * c + k]) : 0.f;
     }
 }
 
@@ -133,9 +137,7 @@ extern "C" GLB_API int glb_poisson_gd_host(const int32_t *h_rowptr, const int32_
     nl += 1;
     if ((rc = glb_poisson_scale(t_rp, t_col, t_val, deg, n, P_val, rw_val, st))) return rc;
     nl += 1;
-    scaled_pack_kernel<<<sm_count() * 8, 256, 0, st>>>(src, deg, n, c, Db, ldu);
-    nl += 1;
-    GLB_LAUNCH_CHECK();
+    // Iteration count first (the ordering below only pays off for long runs).
 
     // iteration count by the reference's stopping rule
     int T = max_iter;
@@ -150,15 +152,35 @@ extern "C" GLB_API int glb_poisson_gd_host(const int32_t *h_rowptr, const int32_
         if ((rc = glb_poisson_mixing_T(t_rp, t_col, rw_val, vinf, v, vtmp, n, min_iter, max_iter, &T, &nl, st))) return rc;
     }
 
+    // Locality ordering for long runs: RCM on the host pattern, relabelling on the device.
+    const int *it_rp = t_rp, *it_col = t_col;
+    const float *it_val = P_val;
+    int *perm = nullptr;
+    if ((int64_t)T * nnz >= (int64_t)kReorderMinWork && nnz > 0) {
+        std::vector<int> h_perm((size_t)n);
+        if ((rc = glb_locality_order_host(h_rowptr, h_col, n, h_perm.data()))) return rc;
+        int *iperm, *p_rp, *p_col;
+        float *p_val;
+        GLB_CUDA(A.alloc(&perm, n));   GLB_CUDA(A.alloc(&iperm, n));
+        GLB_CUDA(A.alloc(&p_rp, n + 1)); GLB_CUDA(A.alloc(&p_col, nnz)); GLB_CUDA(A.alloc(&p_val, nnz));
+        GLB_CUDA(cudaMemcpyAsync(perm, h_perm.data(), n * sizeof(int), cudaMemcpyHostToDevice, st));
+        if ((rc = glb_csr_permute(t_rp, t_col, P_val, n, nnz, perm, iperm, p_rp, p_col, p_val, st))) return rc;
+        nl += 3;
+        it_rp = p_rp; it_col = p_col; it_val = p_val;
+    }
+    scaled_pack_kernel<<<sm_count() * 8, 256, 0, st>>>(src, deg, n, c, Db, ldu, perm);
+    nl += 1;
+    GLB_LAUNCH_CHECK();
+
     glb_poisson_plan *plan = nullptr;
-    if ((rc = glb_poisson_plan_create(&plan, t_rp, n, nnz, ldu, st))) return rc;
+    if ((rc = glb_poisson_plan_create(&plan, it_rp, n, nnz, ldu, st))) return rc;
     GLB_CUDA(cudaMemsetAsync(u0, 0, n * ldu * sizeof(float), st));
     GLB_CUDA(cudaMemsetAsync(u1, 0, n * ldu * sizeof(float), st));
     int in_u1 = 0;
-    rc = glb_poisson_iterate(plan, t_rp, t_col, P_val, Db, u0, u1, T, &in_u1, &nl, st);
+    rc = glb_poisson_iterate(plan, it_rp, it_col, it_val, Db, u0, u1, T, &in_u1, &nl, st);
     glb_poisson_plan_destroy(plan);
     if (rc) return rc;
-    if ((rc = glb_unpack_f32_to_f64(in_u1 ? u1 : u0, n, c, ldu, u64, st))) return rc;
+    if ((rc = glb_unpack_f32_to_f64(in_u1 ? u1 : u0, n, c, ldu, u64, perm, st))) return rc;
     nl += 1;
     GLB_CUDA(cudaMemcpyAsync(h_u_out, u64, n * c * sizeof(double), cudaMemcpyDeviceToHost, st));
     GLB_CUDA(cudaStreamSynchronize(st));

@@ -23,6 +23,8 @@
 // every thread keeps UNROLL L2 requests in flight; there is no cross-lane reduction at all.
 #include <stdlib.h>
 #include <string.h>
+#include <algorithm>
+#include <vector>
 #include "common.cuh"
 
 namespace glb {
@@ -154,48 +156,101 @@ __device__ __forceinline__ void grid_barrier(unsigned *sync_words, unsigned epoc
     __syncthreads();
 }
 
+constexpr int kLongRow = 32;     // rows with more nonzeros are split over the lane groups of a whole warp
+
 template <int LANES, int THREADS, int UNROLL, bool FLAGS>
 __global__ void __launch_bounds__(THREADS, 1)
 poisson_persistent_kernel(const int *__restrict__ rowptr, const int *__restrict__ col,
                           const float *__restrict__ val, const float *__restrict__ Db, float *u0, float *u1, int n,
-                          int ldu, int T, int rows_per_cta, int slab_cap, unsigned *barrier_counter)
+                          int ldu, int T, const int *__restrict__ cta_rows, int max_rows, int slab_cap,
+                          unsigned *sync_words)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    // layout: Db slab [rows_per_cta*ldu] f32 | (col,val) [slab_cap] int2 | rp [rows_per_cta+1] i32
-    float *s_Db = reinterpret_cast<float *>(smem_raw);
-    int2 *s_cv = reinterpret_cast<int2 *>(s_Db + (size_t)rows_per_cta * ldu);
+    // layout: (col,val) [slab_cap] int2 | rp [max_rows+1] i32 | long rows [max_rows] i32 | n_long i32 |
+    //         has-source flag [max_rows] u8
+    int2 *s_cv = reinterpret_cast<int2 *>(smem_raw);
     int *s_rp = reinterpret_cast<int *>(s_cv + slab_cap);
+    int *s_long = s_rp + (max_rows + 1);
+    int *s_nlong = s_long + max_rows;
+    unsigned char *s_src = reinterpret_cast<unsigned char *>(s_nlong + 1);
 
-    const int r0 = min(n, (int)blockIdx.x * rows_per_cta);
-    const int r1 = min(n, r0 + rows_per_cta);
+    const int r0 = cta_rows[blockIdx.x];
+    const int r1 = cta_rows[blockIdx.x + 1];
     const int nrows = r1 - r0;
     const int nz0 = rowptr[r0];
     const int nnz_slab = rowptr[r1] - nz0;
-    for (int i = threadIdx.x; i < nnz_slab; i += blockDim.x)
+    if (threadIdx.x == 0) *s_nlong = 0;
+    for (int i = threadIdx.x; i < nnz_slab; i += THREADS)
         s_cv[i] = make_int2(col[nz0 + i], __float_as_int(val[nz0 + i]));
-    for (int i = threadIdx.x; i <= nrows; i += blockDim.x) s_rp[i] = rowptr[r0 + i] - nz0;
-    for (int i = threadIdx.x; i < nrows * (ldu / 4); i += blockDim.x)
-        reinterpret_cast<float4 *>(s_Db)[i] = reinterpret_cast<const float4 *>(Db + (size_t)r0 * ldu)[i];
+    for (int i = threadIdx.x; i <= nrows; i += THREADS) s_rp[i] = rowptr[r0 + i] - nz0;
     __syncthreads();
+    // The Poisson source Db is zero except on the labelled rows: remember which rows of this block have
+    // one instead of streaming n x ldu zeros every iteration.  Rows too long for one lane group are listed.
+    for (int lr = threadIdx.x; lr < nrows; lr += THREADS) {
+        bool nz = false;
+        const float4 *b = reinterpret_cast<const float4 *>(Db + (size_t)(r0 + lr) * ldu);
+        for (int q = 0; q < ldu / 4; ++q) {
+            const float4 v = __ldg(b + q);
+            nz |= (v.x != 0.f) | (v.y != 0.f) | (v.z != 0.f) | (v.w != 0.f);      // NaN != 0 is true
+        }
+        s_src[lr] = nz ? 1 : 0;
+        if (s_rp[lr + 1] - s_rp[lr] > kLongRow) s_long[atomicAdd(s_nlong, 1)] = lr;
+    }
+    __syncthreads();
+    const int n_long = *s_nlong;
 
     const int li = threadIdx.x % LANES;
     const int rid = threadIdx.x / LANES;
     constexpr int RPP = THREADS / LANES;            // rows per pass of the CTA
+    constexpr int NG = 32 / LANES;                  // lane groups per warp
+    const int lane = threadIdx.x & 31;
+    const int grp = lane / LANES;
+    const int warp = threadIdx.x >> 5;
     const CsrShared csr{s_cv};
 
     for (int t = 0; t < T; ++t) {
         const float *u_in = (t & 1) ? u1 : u0;
         float *u_out = (t & 1) ? u0 : u1;
+        // phase A: one lane group per (short) row
         for (int lr = rid; lr < nrows; lr += RPP) {
             const int beg = s_rp[lr], end = s_rp[lr + 1];
+            if (end - beg > kLongRow) continue;
             for (int coff = li * 4; coff < ldu; coff += LANES * 4) {
                 float4 acc = row_times_u<false, UNROLL>(csr, beg, end, u_in, ldu, coff);
-                const float4 b = *reinterpret_cast<const float4 *>(s_Db + (size_t)lr * ldu + coff);
-                acc.x += b.x; acc.y += b.y; acc.z += b.z; acc.w += b.w;
-                *reinterpret_cast<float4 *>(u_out + (size_t)(r0 + lr) * ldu + coff) = acc;
+                const size_t o = (size_t)(r0 + lr) * ldu + coff;
+                if (s_src[lr]) {
+                    const float4 b = __ldg(reinterpret_cast<const float4 *>(Db + o));
+                    acc.x += b.x; acc.y += b.y; acc.z += b.z; acc.w += b.w;
+                }
+                *reinterpret_cast<float4 *>(u_out + o) = acc;
             }
         }
-        if (t + 1 < T) grid_barrier<FLAGS>(barrier_counter, (unsigned)(t + 1));
+        // phase B: one warp per long row, nonzeros split over its NG lane groups, fixed-order shuffle reduction
+        for (int q = warp; q < n_long; q += THREADS / 32) {
+            const int lr = s_long[q];
+            const int beg = s_rp[lr], end = s_rp[lr + 1];
+            const int per = (end - beg + NG - 1) / NG;
+            const int gb = min(end, beg + grp * per), ge = min(end, gb + per);
+            for (int coff = li * 4; coff < ldu; coff += LANES * 4) {
+                float4 acc = row_times_u<false, UNROLL>(csr, gb, ge, u_in, ldu, coff);
+#pragma unroll
+                for (int off = LANES; off < 32; off <<= 1) {
+                    acc.x += __shfl_xor_sync(0xffffffffu, acc.x, off);
+                    acc.y += __shfl_xor_sync(0xffffffffu, acc.y, off);
+                    acc.z += __shfl_xor_sync(0xffffffffu, acc.z, off);
+                    acc.w += __shfl_xor_sync(0xffffffffu, acc.w, off);
+                }
+                if (grp == 0) {
+                    const size_t o = (size_t)(r0 + lr) * ldu + coff;
+                    if (s_src[lr]) {
+                        const float4 b = __ldg(reinterpret_cast<const float4 *>(Db + o));
+                        acc.x += b.x; acc.y += b.y; acc.z += b.z; acc.w += b.w;
+                    }
+                    *reinterpret_cast<float4 *>(u_out + o) = acc;
+                }
+            }
+        }
+        if (t + 1 < T) grid_barrier<FLAGS>(sync_words, (unsigned)(t + 1));
     }
 }
 
@@ -309,21 +364,22 @@ struct glb_poisson_plan {
     int64_t n, nnz;
     int ldu;
     int persistent;
-    int grid, rows_per_cta, slab_cap;
+    int grid, max_rows, slab_cap;
     int threads;
     const void *fn;
     size_t smem_bytes;
     unsigned *d_counter;      // barrier words: kFlagStride * grid unsigned
+    int *d_cta_rows;          // grid + 1 row boundaries of the work-balanced partition
 };
 
-// Launch geometry of the persistent kernel.  Default: 1024 threads, 8 gathers in flight per lane, per-CTA flag
-// barrier.  GLB_POISSON_VARIANT="threads,unroll,flags" (e.g. "512,16,0") selects another instantiation for
+// Launch geometry of the persistent kernel.  Default: 1024 threads, 4 gathers in flight per lane, counter
+// barrier (fastest in the r1b sweep, profiles/).  GLB_POISSON_VARIANT="threads,unroll,flags" (e.g. "512,16,0") selects another instantiation for
 // experiments; unknown combinations fall back to the default.
 struct PersistVariant { int threads, unroll, flags; };
 
 static PersistVariant persist_variant()
 {
-    PersistVariant v{1024, 8, 1};
+    PersistVariant v{1024, 4, 0};
     const char *e = getenv("GLB_POISSON_VARIANT");
     if (e) {
         int t = 0, u = 0, f = 0;
@@ -344,7 +400,7 @@ static const void *persistent_fn(const PersistVariant &v, int *threads)
     GLB_PV(512, 8, 1) GLB_PV(512, 16, 1) GLB_PV(512, 16, 0) GLB_PV(768, 8, 1)
 #undef GLB_PV
     *threads = 1024;
-    return (const void *)poisson_persistent_kernel<LANES, 1024, 8, true>;
+    return (const void *)poisson_persistent_kernel<LANES, 1024, 4, false>;
 }
 
 static const void *pick_persistent(int ldu, int *threads)
@@ -368,53 +424,57 @@ extern "C" GLB_API int glb_poisson_plan_create(glb_poisson_plan **plan, const in
     GLB_CHECK_ARG(valid_ld(ldu), "bad ldu");
     cudaStream_t st = (cudaStream_t)stream;
     glb_poisson_plan *p = new glb_poisson_plan();
-    p->n = n; p->nnz = nnz; p->ldu = ldu; p->persistent = 0; p->d_counter = nullptr;
-    p->grid = 0; p->rows_per_cta = 0; p->slab_cap = 0; p->smem_bytes = 0; p->threads = 0; p->fn = nullptr;
+    p->n = n; p->nnz = nnz; p->ldu = ldu; p->persistent = 0; p->d_counter = nullptr; p->d_cta_rows = nullptr;
+    p->grid = 0; p->max_rows = 0; p->slab_cap = 0; p->smem_bytes = 0; p->threads = 0; p->fn = nullptr;
+    *plan = p;
 
     int dev = 0, coop = 0, max_smem = 0;
     GLB_CUDA(cudaGetDevice(&dev));
     cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
     cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     const int sms = sm_count();
-    // at least 2 passes of row groups per CTA so tiny graphs do not spread over 148 barriers' worth of CTAs
-    int grid = (int)((n + 127) / 128);
+    // Upper bound for a graph that could fit the shared-memory slabs at all (8 bytes per nonzero per CTA).
+    if (!coop || (double)nnz * 8.0 / sms > (double)max_smem) return 0;
+    int grid = (int)((n + 127) / 128);          // tiny graphs: at least ~128 rows per CTA
     if (grid > sms) grid = sms;
     if (grid < 1) grid = 1;
-    const int rpc = (int)((n + grid - 1) / grid);
-    grid = (int)((n + rpc - 1) / rpc);
-    if (coop && grid >= 1) {
-        // slab sizes: rowptr at the CTA boundaries, strided device->host copy
-        int *h_b = new int[grid + 1];
-        cudaError_t e = cudaMemcpy2DAsync(h_b, sizeof(int), d_rowptr, (size_t)rpc * sizeof(int), sizeof(int), grid,
-                                          cudaMemcpyDeviceToHost, st);
-        if (e == cudaSuccess)
-            e = cudaMemcpyAsync(h_b + grid, d_rowptr + n, sizeof(int), cudaMemcpyDeviceToHost, st);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-        if (e != cudaSuccess) {
-            delete[] h_b; delete p;
-            set_error("glb_poisson_plan_create: reading rowptr failed: %s", cudaGetErrorString(e));
-            return (int)e;
+
+    // work-balanced contiguous row partition from the host copy of rowptr: cost(row) = nnz(row) + 4
+    std::vector<int> h_rp((size_t)n + 1);
+    GLB_CUDA(cudaMemcpyAsync(h_rp.data(), d_rowptr, sizeof(int) * (size_t)(n + 1), cudaMemcpyDeviceToHost, st));
+    GLB_CUDA(cudaStreamSynchronize(st));
+    std::vector<int> bounds((size_t)grid + 1, 0);
+    const double total = (double)h_rp[n] + 4.0 * (double)n;
+    {
+        int b = 1;
+        for (int64_t i = 0; i < n && b < grid; ++i) {
+            const double pref = (double)h_rp[i + 1] + 4.0 * (double)(i + 1);
+            while (b < grid && pref >= total * b / grid) bounds[b++] = (int)(i + 1);
         }
-        int cap = 0;
-        for (int b = 0; b < grid; ++b) cap = (h_b[b + 1] - h_b[b] > cap) ? h_b[b + 1] - h_b[b] : cap;
-        delete[] h_b;
-        cap = (cap + 3) & ~3;
-        const size_t smem = (size_t)rpc * ldu * 4 + (size_t)cap * 8 + (size_t)(rpc + 1) * 4 + 16;
-        if (smem <= (size_t)max_smem) {
-            int threads = 0;
-            const void *fn = pick_persistent(ldu, &threads);
-            GLB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            int per_sm = 0;
-            GLB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, threads, smem));
-            if (per_sm >= 1 && grid <= per_sm * sms && grid <= threads) {
-                p->persistent = 1;
-                p->grid = grid; p->rows_per_cta = rpc; p->slab_cap = cap; p->smem_bytes = smem;
-                p->threads = threads; p->fn = fn;
-                GLB_CUDA(cudaMalloc(&p->d_counter, sizeof(unsigned) * kFlagStride * grid));
-            }
-        }
+        for (; b <= grid; ++b) bounds[b] = (int)n;
+        bounds[grid] = (int)n;
     }
-    *plan = p;
+    int cap = 0, max_rows = 0;
+    for (int b = 0; b < grid; ++b) {
+        cap = std::max(cap, h_rp[bounds[b + 1]] - h_rp[bounds[b]]);
+        max_rows = std::max(max_rows, bounds[b + 1] - bounds[b]);
+    }
+    cap = (cap + 3) & ~3;
+    const size_t smem = (size_t)cap * 8 + (size_t)(2 * max_rows + 2) * 4 + (size_t)((max_rows + 15) & ~15) + 16;
+    if (smem > (size_t)max_smem) return 0;
+    int threads = 0;
+    const void *fn = pick_persistent(ldu, &threads);
+    GLB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    GLB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, threads, smem));
+    if (per_sm < 1 || grid > per_sm * sms || grid > threads) return 0;
+    GLB_CUDA(cudaMalloc(&p->d_counter, sizeof(unsigned) * kFlagStride * grid));
+    GLB_CUDA(cudaMalloc(&p->d_cta_rows, sizeof(int) * (grid + 1)));
+    GLB_CUDA(cudaMemcpyAsync(p->d_cta_rows, bounds.data(), sizeof(int) * (grid + 1), cudaMemcpyHostToDevice, st));
+    GLB_CUDA(cudaStreamSynchronize(st));        // bounds is a local
+    p->persistent = 1;
+    p->grid = grid; p->max_rows = max_rows; p->slab_cap = cap; p->smem_bytes = smem;
+    p->threads = threads; p->fn = fn;
     return 0;
 }
 
@@ -422,6 +482,7 @@ extern "C" GLB_API int glb_poisson_plan_destroy(glb_poisson_plan *plan)
 {
     if (!plan) return 0;
     if (plan->d_counter) cudaFree(plan->d_counter);
+    if (plan->d_cta_rows) cudaFree(plan->d_cta_rows);
     delete plan;
     return 0;
 }
@@ -440,9 +501,10 @@ extern "C" GLB_API int glb_poisson_iterate(glb_poisson_plan *plan, const int32_t
     if (T == 0) return 0;
     if (plan->persistent) {
         GLB_CUDA(cudaMemsetAsync(plan->d_counter, 0, sizeof(unsigned) * kFlagStride * plan->grid, st));
-        int n = (int)plan->n, ldu = plan->ldu, rpc = plan->rows_per_cta, cap = plan->slab_cap;
+        int n = (int)plan->n, ldu = plan->ldu, max_rows = plan->max_rows, cap = plan->slab_cap;
         void *args[] = {(void *)&d_rowptr, (void *)&d_col, (void *)&d_val, (void *)&d_Db, (void *)&d_u0, (void *)&d_u1,
-                        (void *)&n, (void *)&ldu, (void *)&T, (void *)&rpc, (void *)&cap, (void *)&plan->d_counter};
+                        (void *)&n, (void *)&ldu, (void *)&T, (void *)&plan->d_cta_rows, (void *)&max_rows, (void *)&cap,
+                        (void *)&plan->d_counter};
         GLB_CUDA(cudaLaunchCooperativeKernel(plan->fn, dim3(plan->grid), dim3(plan->threads), args,
                                              plan->smem_bytes, st));
         if (launches) *launches += 1;

@@ -75,9 +75,13 @@ class PoissonOperator:
     """P = D^-1 W^T (fp32 CSR) and RW = W^T D^-1 (fp64 values on the same pattern), device resident.
     Setup lines of ssl.poisson._fit, reference graphlearning/ssl.py:615-617, 634-644."""
 
-    def __init__(self, W):
+    def __init__(self, W, reorder=True):
+        """W: scipy CSR (host) or DeviceCSR.  reorder=True relabels the nodes with a locality ordering
+        (reverse Cuthill-McKee from the host pattern) for the iterate; inputs/outputs keep the caller's
+        numbering.  Only possible when W arrives as a host matrix."""
         torch = _torch()
-        self.W = W if isinstance(W, DeviceCSR) else DeviceCSR.from_scipy(W)
+        host_W = None if isinstance(W, DeviceCSR) else sparse.csr_matrix(W)
+        self.W = W if isinstance(W, DeviceCSR) else DeviceCSR.from_scipy(host_W)
         self.n = self.W.n
         self.deg = self.W.degree(skip_diagonal=True)
         Wt = self.W.transpose()
@@ -86,6 +90,24 @@ class PoissonOperator:
         self.RW_val = torch.empty(max(self.nnz, 1), dtype=torch.float64, device=self.deg.device)
         _lib.call("glb_poisson_scale", ptr(Wt.rowptr), ptr(Wt.col), ptr(Wt.val), ptr(self.deg), self.n,
                   ptr(self.P_val), ptr(self.RW_val), cur_stream())
+        # the arrays the iterate reads (relabelled when a locality ordering is in use)
+        self.perm = None
+        self.it_rowptr, self.it_col, self.it_val = self.rowptr, self.col, self.P_val
+        if reorder and host_W is not None and self.nnz > 0:
+            rp = np.ascontiguousarray(host_W.indptr, dtype=np.int32)
+            ci = np.ascontiguousarray(host_W.indices, dtype=np.int32)
+            perm = np.empty(self.n, dtype=np.int32)
+            _lib.call("glb_locality_order_host", ctypes.c_void_p(rp.ctypes.data), ctypes.c_void_p(ci.ctypes.data),
+                      self.n, ctypes.c_void_p(perm.ctypes.data))
+            dev = self.deg.device
+            self.perm = torch.from_numpy(perm).to(dev)
+            self._iperm = torch.empty(self.n, dtype=torch.int32, device=dev)
+            self.it_rowptr = torch.empty(self.n + 1, dtype=torch.int32, device=dev)
+            self.it_col = torch.empty(self.nnz, dtype=torch.int32, device=dev)
+            self.it_val = torch.empty(self.nnz, dtype=torch.float32, device=dev)
+            _lib.call("glb_csr_permute", ptr(self.rowptr), ptr(self.col), ptr(self.P_val), self.n, self.nnz,
+                      ptr(self.perm), ptr(self._iperm), ptr(self.it_rowptr), ptr(self.it_col), ptr(self.it_val),
+                      cur_stream())
         self._plans = {}
 
     def __del__(self):
@@ -98,7 +120,7 @@ class PoissonOperator:
     def plan(self, ldu):
         if ldu not in self._plans:
             h = ctypes.c_void_p()
-            _lib.call("glb_poisson_plan_create", ctypes.byref(h), ptr(self.rowptr), self.n, self.nnz, int(ldu),
+            _lib.call("glb_poisson_plan_create", ctypes.byref(h), ptr(self.it_rowptr), self.n, self.nnz, int(ldu),
                       cur_stream())
             self._plans[ldu] = h
         return self._plans[ldu]
@@ -113,14 +135,14 @@ class PoissonOperator:
         n, c = X.shape
         ldu = _lib.padded_ld(c)
         out = torch.empty((n, ldu), dtype=torch.float32, device=X.device)
-        _lib.call("glb_pack_f64_to_f32", ptr(X), n, c, ptr(out), ldu, cur_stream())
+        _lib.call("glb_pack_f64_to_f32", ptr(X), n, c, ptr(out), ldu, ptr(self.perm), cur_stream())
         return out
 
     def unpack(self, U, c):
         torch = _torch()
         n, ldu = U.shape
         out = torch.empty((n, c), dtype=torch.float64, device=U.device)
-        _lib.call("glb_unpack_f32_to_f64", ptr(U), n, c, ldu, ptr(out), cur_stream())
+        _lib.call("glb_unpack_f32_to_f64", ptr(U), n, c, ldu, ptr(out), ptr(self.perm), cur_stream())
         return out
 
     def source_to_Db(self, source):
@@ -130,8 +152,8 @@ class PoissonOperator:
         return self.pack((1.0 / self.deg)[:, None] * src)
 
     def step(self, Db, u_in, u_out):
-        _lib.call("glb_poisson_step", ptr(self.rowptr), ptr(self.col), ptr(self.P_val), ptr(Db), ptr(u_in), ptr(u_out),
-                  self.n, int(Db.shape[1]), cur_stream())
+        _lib.call("glb_poisson_step", ptr(self.it_rowptr), ptr(self.it_col), ptr(self.it_val), ptr(Db), ptr(u_in),
+                  ptr(u_out), self.n, int(Db.shape[1]), cur_stream())
 
     def iterate(self, Db, T, u0=None, u1=None):
         """T iterations of u <- Db + P u from u0 (zeros by default).  Returns (u, launches)."""
@@ -142,8 +164,8 @@ class PoissonOperator:
         if u1 is None:
             u1 = torch.zeros_like(Db)
         which, launches = ctypes.c_int(0), ctypes.c_int(0)
-        _lib.call("glb_poisson_iterate", self.plan(ldu), ptr(self.rowptr), ptr(self.col), ptr(self.P_val), ptr(Db),
-                  ptr(u0), ptr(u1), int(T), ctypes.byref(which), ctypes.byref(launches), cur_stream())
+        _lib.call("glb_poisson_iterate", self.plan(ldu), ptr(self.it_rowptr), ptr(self.it_col), ptr(self.it_val),
+                  ptr(Db), ptr(u0), ptr(u1), int(T), ctypes.byref(which), ctypes.byref(launches), cur_stream())
         return (u1 if which.value else u0), launches.value
 
     def mixing_T(self, train_ind, min_iter, max_iter):

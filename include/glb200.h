@@ -67,9 +67,20 @@ GLB_API int glb_csr_transpose(const int32_t *d_rowptr, const int32_t *d_col, con
 GLB_API int glb_poisson_scale(const int32_t *d_t_rowptr, const int32_t *d_t_col, const double *d_t_val, const double *d_deg,
                       int64_t n, float *d_P_val, double *d_RW_val, void *stream);
 
-/* dst (n x ldu fp32, padded with zeros) <- src (n x c fp64), and back.  labels <-> device layout. */
-GLB_API int glb_pack_f64_to_f32(const double *d_src, int64_t n, int c, float *d_dst, int ldu, void *stream);
-GLB_API int glb_unpack_f32_to_f64(const float *d_src, int64_t n, int c, int ldu, double *d_dst, void *stream);
+/* dst (n x ldu fp32, padded with zeros) <- src (n x c fp64), and back.  labels <-> device layout.
+ * d_perm (may be NULL) is a locality ordering: device row r holds the caller's row d_perm[r]. */
+GLB_API int glb_pack_f64_to_f32(const double *d_src, int64_t n, int c, float *d_dst, int ldu, const int32_t *d_perm,
+                                void *stream);
+GLB_API int glb_unpack_f32_to_f64(const float *d_src, int64_t n, int c, int ldu, double *d_dst, const int32_t *d_perm,
+                                  void *stream);
+
+/* Locality ordering (no counterpart in the reference: scipy's single-core SpMM does not care about node
+ * numbering).  Reverse Cuthill-McKee on the HOST from the CSR pattern the caller holds there; integers only.
+ * h_perm[new] = old.  glb_csr_permute relabels an fp32 CSR matrix on the device: B = Pi A Pi^T. */
+GLB_API int glb_locality_order_host(const int32_t *h_rowptr, const int32_t *h_col, int64_t n, int32_t *h_perm);
+GLB_API int glb_csr_permute(const int32_t *d_rowptr, const int32_t *d_col, const float *d_val, int64_t n, int64_t nnz,
+                            const int32_t *d_perm, int32_t *d_iperm, int32_t *d_out_rowptr, int32_t *d_out_col,
+                            float *d_out_val, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Poisson iterate  u <- Db + P u.   Replaces the loop body graphlearning/ssl.py:668 (CPU: scipy

@@ -16,9 +16,9 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 from test_poisson_gpu import random_knn_graph          # noqa: E402
 
 
-def time_variant(W, src, variant, iters=1000, reps=3):
+def time_variant(W, src, variant, iters=1000, reps=3, reorder=True):
     os.environ["GLB_POISSON_VARIANT"] = variant
-    op = gdev.PoissonOperator(W)
+    op = gdev.PoissonOperator(W, reorder=reorder)
     Db = op.source_to_Db(src)
     u0 = torch.zeros_like(Db); u1 = torch.zeros_like(Db)
     best = 1e9
@@ -30,7 +30,7 @@ def time_variant(W, src, variant, iters=1000, reps=3):
         e1.record()
         torch.cuda.synchronize()
         best = min(best, e0.elapsed_time(e1))
-    return best * 1e3 / iters, u.clone(), op.is_persistent(int(Db.shape[1]))
+    return best * 1e3 / iters, op.unpack(u, src.shape[1]).clone(), op.is_persistent(int(Db.shape[1]))
 
 
 def main():
@@ -43,12 +43,13 @@ def main():
     variants = sys.argv[1:] or ["1024,8,1", "1024,8,0", "1024,4,1", "1024,4,0", "512,8,1", "512,16,1", "512,16,0", "768,8,1"]
     for v in variants:
         us, u, pers = time_variant(W, src, v)
+        usn, un, _ = time_variant(W, src, v, reorder=False)
         ust, _, _ = time_variant(Wt, srct, v, iters=2000)
         if ref is None:
-            ref = u
-        same = bool(torch.equal(ref, u))
-        print("variant %-10s persistent=%s  %.3f us/iter (70k graph)  %.3f us/iter (tiny graph ~ barrier)  bit-equal=%s"
-              % (v, pers, us, ust, same), flush=True)
+            ref = un
+        err = float((u - ref).abs().max() / ref.abs().max())
+        print("variant %-10s persistent=%s  rcm %.3f us/iter  natural %.3f us/iter  tiny graph (~barrier) %.3f us/iter  "
+              "natural bit-equal=%s  rcm rel diff=%.1e" % (v, pers, us, usn, ust, bool(torch.equal(ref, un)), err), flush=True)
 
 
 if __name__ == "__main__":
