@@ -178,7 +178,11 @@ def run_ours(args, rank, world):
 
     # ---- e2e: the call a user makes, host buffers in and out ------------------------------------------
     model = gl.ssl.poisson(W, solver="gradient_descent", min_iter=iters, max_iter=iters)
-    model.fit(ti, labels[ti])                              # warm-up (context, allocator)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    model.fit(ti, labels[ti])                              # first fit on this graph: uploads W, builds P/RW on the device
+    cold_s = time.perf_counter() - t0
+    model.fit(ti, labels[ti])
     barrier()
     t0 = time.perf_counter()
     e2e_steps = max(1, min(args.steps, 5))
@@ -187,7 +191,8 @@ def run_ours(args, rank, world):
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     clocks = sampler.stop() if rank == 0 else None
-    h2d = (n + 1) * 4 + nnz * 4 + nnz * 8 + n * c * 8 + len(ti) * 8
+    h2d = n * c * 8                                        # per fit: the fp64 source term (graph state is cached)
+    graph_h2d = (n + 1) * 4 + nnz * 4 + nnz * 8           # once per graph, inside the first fit
     d2h = n * c * 8
 
     if world > 1:
@@ -230,7 +235,9 @@ def run_ours(args, rank, world):
                          "sample": "%d iterations of the reference loop (ssl.py:667-669, scipy csr_matvecs fp64) on the "
                                    "same graph, best of 2; host has %d cores, scipy SpMM uses 1" % (cpu_iters, os.cpu_count())},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "steps": e2e_steps, "call": "gl.ssl.poisson(W, solver='gradient_descent').fit -> glb_poisson_gd_host"},
+                "steps": e2e_steps, "call": "gl.ssl.poisson(W, solver='gradient_descent').fit -> glb_poisson_graph_fit "
+                "(device graph state cached on the gl.graph object after the first fit, as in ssl_trials)",
+                "first_fit_value": iters / cold_s, "graph_h2d_bytes_once": int(graph_h2d)},
         "gpu_launches": int(launches),
         "clocks": clocks,
     }

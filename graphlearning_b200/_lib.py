@@ -37,6 +37,10 @@ SIGNATURES = {
                                     POINTER(c_int), POINTER(c_int), c_void_p]),
     "glb_poisson_mixing_T": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int,
                                      POINTER(c_int), POINTER(c_int), c_void_p]),
+    "glb_poisson_graph_create": (c_int, [POINTER(c_void_p), c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int]),
+    "glb_poisson_graph_destroy": (c_int, [c_void_p]),
+    "glb_poisson_graph_fit": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int64, c_int, c_int, c_void_p,
+                                      POINTER(c_int), POINTER(c_int)]),
     "glb_poisson_gd_host": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int, c_void_p, c_int64,
                                     c_int, c_int, c_void_p, POINTER(c_int), POINTER(c_int)]),
 }

@@ -6,8 +6,9 @@
 
 namespace glb {
 
-// reorder the graph when T * nnz exceeds this (the host RCM costs about as much as ~100 iterations)
-constexpr long long kReorderMinWork = 200ll * 1000 * 1000;
+// auto mode reorders the graph only when two ping-pong label matrices exceed this many bytes (about the L2
+// size): below it every gather is an L2 hit anyway and the r1c/r1e sweeps (profiles/) show no gain from RCM
+constexpr double kReorderMinBytes = 120.0 * 1024 * 1024;
 
 struct DeviceArena {           // frees everything on scope exit, whatever the return path
     std::vector<void *> ptrs;
@@ -86,105 +87,159 @@ __global__ void __launch_bounds__(256) scale_by_sum_kernel(double *__restrict__ 
 
 using namespace glb;
 
-extern "C" GLB_API int glb_poisson_gd_host(const int32_t *h_rowptr, const int32_t *h_col, const double *h_val, int64_t n,
-                                   int64_t nnz, const double *h_source, int c, const int64_t *h_train_ind, int64_t m,
-                                   int min_iter, int max_iter, double *h_u_out, int *T_done, int *launches)
+// Device-resident state of one weight matrix: everything ssl.poisson._fit recomputes on every call
+// (graph.graph(W), D, P = D^-1 W^T, RW = W^T D^-1, deg/sum(deg); ssl.py:615-617, 634-644) is built once here.
+struct glb_poisson_graph {
+    int64_t n = 0, nnz = 0;
+    DeviceArena A;                       // owns every device buffer below
+    int *t_rp = nullptr, *t_col = nullptr;               // pattern of W^T
+    float *P_val = nullptr;
+    double *rw_val = nullptr, *deg = nullptr, *vinf = nullptr, *v = nullptr, *vtmp = nullptr, *part = nullptr;
+    // iterate arrays (relabelled when a locality ordering is in use)
+    const int *it_rp = nullptr, *it_col = nullptr;
+    const float *it_val = nullptr;
+    int *perm = nullptr;
+    // per-width work buffers and plan (kept for the last width used)
+    int ldu = 0, c_cap = 0;
+    int64_t m_cap = 0;
+    double *src64 = nullptr;             // n x c staging (source in, result out)
+    float *Db = nullptr, *u0 = nullptr, *u1 = nullptr;
+    long long *tind = nullptr;
+    glb_poisson_plan *plan = nullptr;
+    int setup_launches = 0;
+    ~glb_poisson_graph() { if (plan) glb_poisson_plan_destroy(plan); }
+};
+
+static const int NPART = 256;
+
+extern "C" GLB_API int glb_poisson_graph_create(glb_poisson_graph **out, const int32_t *h_rowptr, const int32_t *h_col,
+                                                const double *h_val, int64_t n, int64_t nnz, int reorder)
 {
-    GLB_CHECK_ARG(h_rowptr && h_col && h_val && h_source && h_u_out, "null pointer");
+    GLB_CHECK_ARG(out && h_rowptr && (nnz == 0 || (h_col && h_val)), "null pointer");
     GLB_CHECK_ARG(n > 0 && n < (1ll << 31) && nnz >= 0 && nnz < (1ll << 31), "size out of range");
-    GLB_CHECK_ARG(c > 0, "c must be positive");
-    GLB_CHECK_ARG(min_iter >= 0 && max_iter >= 0, "iteration counts must be >= 0");
-    GLB_CHECK_ARG(m == 0 || h_train_ind, "train_ind is null");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
         cudaGetLastError();
-        set_error("glb_poisson_gd_host: no CUDA device visible");
+        set_error("glb_poisson_graph_create: no CUDA device visible");
         return GLB_E_NOGPU;
     }
-    const int ldu = glb_padded_ld(c);
     cudaStream_t st = 0;
-    DeviceArena A;
-    int nl = 0;
-
-    int *rp, *col, *t_rp, *t_col;
-    double *val, *t_val, *deg, *src, *rw_val, *vinf, *v, *vtmp, *part, *u64;
-    float *P_val, *Db, *u0, *u1;
-    long long *tind;
+    glb_poisson_graph *g = new glb_poisson_graph();
+    struct Guard { glb_poisson_graph *g; ~Guard() { delete g; } } guard{g};
+    g->n = n; g->nnz = nnz;
+    int *rp, *col;
+    double *val, *t_val;
     void *work;
+    DeviceArena tmp;                    // freed when this function returns
     const int64_t work_bytes = glb_csr_transpose_work_bytes(n, nnz);
-    const int NPART = 256;
-    GLB_CUDA(A.alloc(&rp, n + 1));      GLB_CUDA(A.alloc(&col, nnz));      GLB_CUDA(A.alloc(&val, nnz));
-    GLB_CUDA(A.alloc(&t_rp, n + 1));    GLB_CUDA(A.alloc(&t_col, nnz));    GLB_CUDA(A.alloc(&t_val, nnz));
-    GLB_CUDA(A.alloc(&deg, n));         GLB_CUDA(A.alloc(&src, n * c));    GLB_CUDA(A.alloc(&rw_val, nnz));
-    GLB_CUDA(A.alloc(&vinf, n));        GLB_CUDA(A.alloc(&v, n));          GLB_CUDA(A.alloc(&vtmp, n));
-    GLB_CUDA(A.alloc(&part, NPART));    GLB_CUDA(A.alloc(&P_val, nnz));    GLB_CUDA(A.alloc(&Db, n * ldu));
-    GLB_CUDA(A.alloc(&u0, n * ldu));    GLB_CUDA(A.alloc(&u1, n * ldu));   GLB_CUDA(A.alloc(&tind, m));
-    GLB_CUDA(A.alloc((unsigned char **)&work, (size_t)work_bytes));
-    u64 = src;                          // reused for the fp64 result once Db is built
-
+    GLB_CUDA(tmp.alloc(&rp, n + 1));      GLB_CUDA(tmp.alloc(&col, nnz));      GLB_CUDA(tmp.alloc(&val, nnz));
+    GLB_CUDA(tmp.alloc(&t_val, nnz));     GLB_CUDA(tmp.alloc((unsigned char **)&work, (size_t)work_bytes));
+    GLB_CUDA(g->A.alloc(&g->t_rp, n + 1)); GLB_CUDA(g->A.alloc(&g->t_col, nnz)); GLB_CUDA(g->A.alloc(&g->P_val, nnz));
+    GLB_CUDA(g->A.alloc(&g->rw_val, nnz)); GLB_CUDA(g->A.alloc(&g->deg, n));     GLB_CUDA(g->A.alloc(&g->vinf, n));
+    GLB_CUDA(g->A.alloc(&g->v, n));        GLB_CUDA(g->A.alloc(&g->vtmp, n));    GLB_CUDA(g->A.alloc(&g->part, NPART));
     GLB_CUDA(cudaMemcpyAsync(rp, h_rowptr, (n + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
     GLB_CUDA(cudaMemcpyAsync(col, h_col, nnz * sizeof(int), cudaMemcpyHostToDevice, st));
     GLB_CUDA(cudaMemcpyAsync(val, h_val, nnz * sizeof(double), cudaMemcpyHostToDevice, st));
-    GLB_CUDA(cudaMemcpyAsync(src, h_source, n * c * sizeof(double), cudaMemcpyHostToDevice, st));
-    if (m) GLB_CUDA(cudaMemcpyAsync(tind, h_train_ind, m * sizeof(long long), cudaMemcpyHostToDevice, st));
 
     // W <- W - diag(W) (ssl.py:615-616) is never materialised: the degree kernel skips diagonal entries and
     // glb_poisson_scale writes zeros for them.
     int rc;
-    if ((rc = glb_csr_transpose(rp, col, val, n, nnz, t_rp, t_col, t_val, work, work_bytes, st))) return rc;
-    nl += 4;
-    if ((rc = glb_csr_degree(rp, col, val, n, 1, deg, st))) return rc;
-    nl += 1;
-    if ((rc = glb_poisson_scale(t_rp, t_col, t_val, deg, n, P_val, rw_val, st))) return rc;
-    nl += 1;
-    // Iteration count first (the ordering below only pays off for long runs).
+    if ((rc = glb_csr_transpose(rp, col, val, n, nnz, g->t_rp, g->t_col, t_val, work, work_bytes, st))) return rc;
+    if ((rc = glb_csr_degree(rp, col, val, n, 1, g->deg, st))) return rc;
+    if ((rc = glb_poisson_scale(g->t_rp, g->t_col, t_val, g->deg, n, g->P_val, g->rw_val, st))) return rc;
+    partial_sum_kernel<<<NPART, 256, 0, st>>>(g->deg, n, g->part);
+    mixing_init_kernel<<<sm_count() * 4, 256, 0, st>>>(g->deg, g->part, NPART, n, g->vinf, g->v);
+    g->setup_launches = 4 + 1 + 1 + 2;
+    GLB_LAUNCH_CHECK();
 
-    // iteration count by the reference's stopping rule
-    int T = max_iter;
-    if (min_iter < max_iter) {
-        partial_sum_kernel<<<NPART, 256, 0, st>>>(deg, n, part);
-        mixing_init_kernel<<<sm_count() * 4, 256, 0, st>>>(deg, part, NPART, n, vinf, v);
-        if (m) mixing_seed_kernel<<<ceil_div(m, 256), 256, 0, st>>>(tind, m, n, v);
-        partial_sum_kernel<<<NPART, 256, 0, st>>>(v, n, part);
-        scale_by_sum_kernel<<<sm_count() * 4, 256, 0, st>>>(v, part, NPART, n);
-        nl += 5;
-        GLB_LAUNCH_CHECK();
-        if ((rc = glb_poisson_mixing_T(t_rp, t_col, rw_val, vinf, v, vtmp, n, min_iter, max_iter, &T, &nl, st))) return rc;
-    }
-
-    // Locality ordering for long runs: RCM on the host pattern, relabelling on the device.
-    const int *it_rp = t_rp, *it_col = t_col;
-    const float *it_val = P_val;
-    int *perm = nullptr;
-    if ((int64_t)T * nnz >= (int64_t)kReorderMinWork && nnz > 0) {
+    g->it_rp = g->t_rp; g->it_col = g->t_col; g->it_val = g->P_val;
+    // Locality ordering: worth its host time only when the label matrix cannot live in L2 (reorder < 0 = auto).
+    const bool want = reorder > 0 || (reorder < 0 && (double)n * 16.0 * 4.0 * 2.0 > kReorderMinBytes);
+    if (want && nnz > 0) {
         std::vector<int> h_perm((size_t)n);
         if ((rc = glb_locality_order_host(h_rowptr, h_col, n, h_perm.data()))) return rc;
         int *iperm, *p_rp, *p_col;
         float *p_val;
-        GLB_CUDA(A.alloc(&perm, n));   GLB_CUDA(A.alloc(&iperm, n));
-        GLB_CUDA(A.alloc(&p_rp, n + 1)); GLB_CUDA(A.alloc(&p_col, nnz)); GLB_CUDA(A.alloc(&p_val, nnz));
-        GLB_CUDA(cudaMemcpyAsync(perm, h_perm.data(), n * sizeof(int), cudaMemcpyHostToDevice, st));
-        if ((rc = glb_csr_permute(t_rp, t_col, P_val, n, nnz, perm, iperm, p_rp, p_col, p_val, st))) return rc;
-        nl += 3;
-        it_rp = p_rp; it_col = p_col; it_val = p_val;
+        GLB_CUDA(g->A.alloc(&g->perm, n));  GLB_CUDA(tmp.alloc(&iperm, n));
+        GLB_CUDA(g->A.alloc(&p_rp, n + 1)); GLB_CUDA(g->A.alloc(&p_col, nnz)); GLB_CUDA(g->A.alloc(&p_val, nnz));
+        GLB_CUDA(cudaMemcpyAsync(g->perm, h_perm.data(), n * sizeof(int), cudaMemcpyHostToDevice, st));
+        if ((rc = glb_csr_permute(g->t_rp, g->t_col, g->P_val, n, nnz, g->perm, iperm, p_rp, p_col, p_val, st))) return rc;
+        g->setup_launches += 3;
+        g->it_rp = p_rp; g->it_col = p_col; g->it_val = p_val;
     }
-    scaled_pack_kernel<<<sm_count() * 8, 256, 0, st>>>(src, deg, n, c, Db, ldu, perm);
-    nl += 1;
-    GLB_LAUNCH_CHECK();
+    GLB_CUDA(cudaStreamSynchronize(st));
+    guard.g = nullptr;
+    *out = g;
+    return 0;
+}
 
-    glb_poisson_plan *plan = nullptr;
-    if ((rc = glb_poisson_plan_create(&plan, it_rp, n, nnz, ldu, st))) return rc;
-    GLB_CUDA(cudaMemsetAsync(u0, 0, n * ldu * sizeof(float), st));
-    GLB_CUDA(cudaMemsetAsync(u1, 0, n * ldu * sizeof(float), st));
-    int in_u1 = 0;
-    rc = glb_poisson_iterate(plan, it_rp, it_col, it_val, Db, u0, u1, T, &in_u1, &nl, st);
-    glb_poisson_plan_destroy(plan);
-    if (rc) return rc;
-    if ((rc = glb_unpack_f32_to_f64(in_u1 ? u1 : u0, n, c, ldu, u64, perm, st))) return rc;
+extern "C" GLB_API int glb_poisson_graph_destroy(glb_poisson_graph *g)
+{
+    delete g;
+    return 0;
+}
+
+extern "C" GLB_API int glb_poisson_graph_fit(glb_poisson_graph *g, const double *h_source, int c, const int64_t *h_train_ind,
+                                             int64_t m, int min_iter, int max_iter, double *h_u_out, int *T_done,
+                                             int *launches)
+{
+    GLB_CHECK_ARG(g && h_source && h_u_out, "null pointer");
+    GLB_CHECK_ARG(c > 0, "c must be positive");
+    GLB_CHECK_ARG(min_iter >= 0 && max_iter >= 0, "iteration counts must be >= 0");
+    GLB_CHECK_ARG(m == 0 || h_train_ind, "train_ind is null");
+    const int64_t n = g->n, nnz = g->nnz;
+    const int ldu = glb_padded_ld(c);
+    cudaStream_t st = 0;
+    int nl = 0, rc;
+    if (ldu != g->ldu || c > g->c_cap) {                 // (re)size the per-width buffers and the plan
+        if (g->plan) { glb_poisson_plan_destroy(g->plan); g->plan = nullptr; }
+        GLB_CUDA(g->A.alloc(&g->src64, n * c));  GLB_CUDA(g->A.alloc(&g->Db, n * ldu));
+        GLB_CUDA(g->A.alloc(&g->u0, n * ldu));   GLB_CUDA(g->A.alloc(&g->u1, n * ldu));
+        if ((rc = glb_poisson_plan_create(&g->plan, g->it_rp, n, nnz, ldu, st))) return rc;
+        g->ldu = ldu; g->c_cap = c;
+    }
+    if (m > g->m_cap) { GLB_CUDA(g->A.alloc(&g->tind, m)); g->m_cap = m; }
+    GLB_CUDA(cudaMemcpyAsync(g->src64, h_source, n * c * sizeof(double), cudaMemcpyHostToDevice, st));
+    scaled_pack_kernel<<<sm_count() * 8, 256, 0, st>>>(g->src64, g->deg, n, c, g->Db, ldu, g->perm);
     nl += 1;
-    GLB_CUDA(cudaMemcpyAsync(h_u_out, u64, n * c * sizeof(double), cudaMemcpyDeviceToHost, st));
+
+    // iteration count by the reference's stopping rule (ssl.py:639-644, 667, 669)
+    int T = max_iter;
+    if (min_iter < max_iter) {
+        GLB_CUDA(cudaMemcpyAsync(g->tind, h_train_ind, m * sizeof(long long), cudaMemcpyHostToDevice, st));
+        GLB_CUDA(cudaMemsetAsync(g->v, 0, n * sizeof(double), st));
+        if (m) mixing_seed_kernel<<<ceil_div(m, 256), 256, 0, st>>>(g->tind, m, n, g->v);
+        partial_sum_kernel<<<NPART, 256, 0, st>>>(g->v, n, g->part);
+        scale_by_sum_kernel<<<sm_count() * 4, 256, 0, st>>>(g->v, g->part, NPART, n);
+        nl += 3;
+        GLB_LAUNCH_CHECK();
+        if ((rc = glb_poisson_mixing_T(g->t_rp, g->t_col, g->rw_val, g->vinf, g->v, g->vtmp, n, min_iter, max_iter, &T, &nl,
+                                       st)))
+            return rc;
+    }
+    GLB_CUDA(cudaMemsetAsync(g->u0, 0, n * ldu * sizeof(float), st));
+    int in_u1 = 0;
+    if ((rc = glb_poisson_iterate(g->plan, g->it_rp, g->it_col, g->it_val, g->Db, g->u0, g->u1, T, &in_u1, &nl, st))) return rc;
+    if ((rc = glb_unpack_f32_to_f64(in_u1 ? g->u1 : g->u0, n, c, ldu, g->src64, g->perm, st))) return rc;
+    nl += 1;
+    GLB_CUDA(cudaMemcpyAsync(h_u_out, g->src64, n * c * sizeof(double), cudaMemcpyDeviceToHost, st));
     GLB_CUDA(cudaStreamSynchronize(st));
     if (T_done) *T_done = T;
     if (launches) *launches = nl;
     return 0;
+}
+
+extern "C" GLB_API int glb_poisson_gd_host(const int32_t *h_rowptr, const int32_t *h_col, const double *h_val, int64_t n,
+                                           int64_t nnz, const double *h_source, int c, const int64_t *h_train_ind,
+                                           int64_t m, int min_iter, int max_iter, double *h_u_out, int *T_done,
+                                           int *launches)
+{
+    GLB_CHECK_ARG(h_rowptr && h_col && h_val && h_source && h_u_out, "null pointer");
+    glb_poisson_graph *g = nullptr;
+    int rc = glb_poisson_graph_create(&g, h_rowptr, h_col, h_val, n, nnz, -1);
+    if (rc) return rc;
+    rc = glb_poisson_graph_fit(g, h_source, c, h_train_ind, m, min_iter, max_iter, h_u_out, T_done, launches);
+    if (rc == 0 && launches) *launches += g->setup_launches;
+    glb_poisson_graph_destroy(g);
+    return rc;
 }

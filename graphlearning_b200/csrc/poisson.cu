@@ -46,45 +46,62 @@ __device__ __forceinline__ float4 load_u4(const float *p)
     return *reinterpret_cast<const float4 *>(p);   // coherent at L1 after the grid barrier's fence
 }
 
-// (col, val) of nonzero j: from the interleaved shared-memory slab or from the global CSR arrays
+// Nonzero j as (byte offset of row col[j] inside u, value).  Offsets are 32-bit: n * ldu * 4 < 2^32 is checked
+// on the host.  The persistent kernel keeps the pairs in shared memory, precomputed once per launch.
 struct CsrGlobal {
     const int *__restrict__ col;
     const float *__restrict__ val;
-    __device__ __forceinline__ void get(int j, int &c, float &a) const { c = __ldg(col + j); a = __ldg(val + j); }
+    unsigned row_bytes;
+    __device__ __forceinline__ void get(int j, unsigned &off, float &a) const
+    {
+        off = (unsigned)__ldg(col + j) * row_bytes;
+        a = __ldg(val + j);
+    }
 };
 struct CsrShared {
     const int2 *cv;
-    __device__ __forceinline__ void get(int j, int &c, float &a) const
+    __device__ __forceinline__ void get(int j, unsigned &off, float &a) const
     {
         const int2 e = cv[j];
-        c = e.x;
+        off = (unsigned)e.x;
         a = __int_as_float(e.y);
     }
 };
 
-// sum_j val[j] * u[col[j], ctile + 4*li ...] over the nonzeros [beg, end) of one row
+// sum_j val[j] * u[col[j], 4 columns] over the nonzeros [beg, end) of one row; ubase = u + column offset.
+// Full batches of UNROLL run without predicates (all gathers issued before the first FMA); the tail is predicated.
 template <bool NC, int UNROLL, typename Csr>
-__device__ __forceinline__ float4 row_times_u(const Csr &csr, int beg, int end, const float *__restrict__ u, int ldu,
-                                              int coff)
+__device__ __forceinline__ float4 row_times_u(const Csr &csr, int beg, int end, const char *__restrict__ ubase)
 {
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int j = beg; j < end; j += UNROLL) {
-        int c[UNROLL];
+    int j = beg;
+    for (; j + UNROLL <= end; j += UNROLL) {
+        unsigned off[UNROLL];
         float a[UNROLL];
         float4 x[UNROLL];
 #pragma unroll
-        for (int i = 0; i < UNROLL; ++i) {
-            c[i] = 0;
-            a[i] = 0.f;
-            if (j + i < end) csr.get(j + i, c[i], a[i]);
+        for (int i = 0; i < UNROLL; ++i) csr.get(j + i, off[i], a[i]);
+#pragma unroll
+        for (int i = 0; i < UNROLL; ++i) x[i] = load_u4<NC>(reinterpret_cast<const float *>(ubase + off[i]));
+#pragma unroll
+        for (int i = 0; i < UNROLL; ++i) fma4(acc, a[i], x[i]);
+    }
+    if (j < end) {
+        unsigned off[UNROLL];
+        float a[UNROLL];
+        float4 x[UNROLL];
+#pragma unroll
+        for (int i = 0; i < UNROLL - 1; ++i) {
+            off[i] = 0; a[i] = 0.f;
+            if (j + i < end) csr.get(j + i, off[i], a[i]);
         }
 #pragma unroll
-        for (int i = 0; i < UNROLL; ++i) {
+        for (int i = 0; i < UNROLL - 1; ++i) {
             x[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (j + i < end) x[i] = load_u4<NC>(u + (size_t)c[i] * ldu + coff);
+            if (j + i < end) x[i] = load_u4<NC>(reinterpret_cast<const float *>(ubase + off[i]));
         }
 #pragma unroll
-        for (int i = 0; i < UNROLL; ++i) fma4(acc, a[i], x[i]);      // a = 0, x = 0 past the end of the row
+        for (int i = 0; i < UNROLL - 1; ++i) fma4(acc, a[i], x[i]);      // a = 0, x = 0 past the end of the row
     }
     return acc;
 }
@@ -101,11 +118,11 @@ poisson_step_kernel(const int *__restrict__ rowptr, const int *__restrict__ col,
     const int li = threadIdx.x % LANES;
     const long long rid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / LANES;
     const long long nrid = ((long long)gridDim.x * blockDim.x) / LANES;
-    const CsrGlobal csr{col, val};
+    const CsrGlobal csr{col, val, (unsigned)ldu * 4u};
     for (long long row = rid; row < n; row += nrid) {
         const int beg = __ldg(rowptr + row), end = __ldg(rowptr + row + 1);
         for (int coff = li * 4; coff < ldu; coff += LANES * 4) {
-            float4 acc = row_times_u<true, kUnroll>(csr, beg, end, u_in, ldu, coff);
+            float4 acc = row_times_u<true, kUnroll>(csr, beg, end, reinterpret_cast<const char *>(u_in + coff));
             const size_t o = (size_t)row * ldu + coff;
             const float4 b = __ldg(reinterpret_cast<const float4 *>(Db + o));
             acc.x += b.x; acc.y += b.y; acc.z += b.z; acc.w += b.w;
@@ -117,40 +134,48 @@ poisson_step_kernel(const int *__restrict__ rowptr, const int *__restrict__ col,
 // ------------------------------------------------------------------------------------------------
 // K2: persistent, T iterations per launch
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned ld_acquire(const unsigned *p)
+__device__ __forceinline__ unsigned ld_relaxed(const unsigned *p)
 {
     unsigned v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ void red_release_add(unsigned *p, unsigned v)
+__device__ __forceinline__ void red_relaxed_add(unsigned *p, unsigned v)
 {
-    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+    asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-__device__ __forceinline__ void st_release(unsigned *p, unsigned v)
+__device__ __forceinline__ void st_relaxed(unsigned *p, unsigned v)
 {
-    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 
 // Grid-wide barrier between iterations (all CTAs are co-resident: cooperative launch, one per SM).
-// The u stores of a CTA are ordered before its arrival by bar.sync + a gpu-scope release; the acquire loads
-// order the next iteration's gathers after every other CTA's arrival (and drop this SM's stale L1 lines).
-//   FLAGS = false: one monotone counter, red.add by thread 0, spin until it reaches epoch * gridDim.x
-//   FLAGS = true : one flag word per CTA (128 bytes apart); CTA b stores `epoch` into its flag, thread i
-//                  spins on flag i - no serialised atomics on one L2 line.
+// bar.sync orders the CTA's u stores before thread 0's release fence; the arrival is a relaxed red/st; the
+// waiters poll with relaxed loads (no L1 invalidation per poll) and issue ONE acquire fence when the epoch
+// is complete, which also drops this SM's stale L1 lines before the next iteration's gathers.
+//   FLAGS = false: one monotone counter, spin until it reaches epoch * gridDim.x
+//   FLAGS = true : one flag word per CTA (128 bytes apart); thread i spins on the flag of CTA i
 constexpr int kFlagStride = 32;          // unsigned words = 128 bytes
 template <bool FLAGS>
 __device__ __forceinline__ void grid_barrier(unsigned *sync_words, unsigned epoch)
 {
     __syncthreads();
     if (FLAGS) {
-        if (threadIdx.x == 0) st_release(sync_words + (size_t)blockIdx.x * kFlagStride, epoch);
-        if (threadIdx.x < gridDim.x)
-            while (ld_acquire(sync_words + (size_t)threadIdx.x * kFlagStride) < epoch) { }
+        if (threadIdx.x == 0) {
+            fence_acq_rel_gpu();
+            st_relaxed(sync_words + (size_t)blockIdx.x * kFlagStride, epoch);
+        }
+        if (threadIdx.x < gridDim.x) {
+            while (ld_relaxed(sync_words + (size_t)threadIdx.x * kFlagStride) < epoch) { }
+            fence_acq_rel_gpu();
+        }
     } else {
         if (threadIdx.x == 0) {
-            red_release_add(sync_words, 1u);
-            while (ld_acquire(sync_words) < epoch * gridDim.x) { }
+            fence_acq_rel_gpu();
+            red_relaxed_add(sync_words, 1u);
+            while (ld_relaxed(sync_words) < epoch * gridDim.x) { }
+            fence_acq_rel_gpu();
         }
     }
     __syncthreads();
@@ -181,7 +206,7 @@ poisson_persistent_kernel(const int *__restrict__ rowptr, const int *__restrict_
     const int nnz_slab = rowptr[r1] - nz0;
     if (threadIdx.x == 0) *s_nlong = 0;
     for (int i = threadIdx.x; i < nnz_slab; i += THREADS)
-        s_cv[i] = make_int2(col[nz0 + i], __float_as_int(val[nz0 + i]));
+        s_cv[i] = make_int2((int)((unsigned)col[nz0 + i] * (unsigned)ldu * 4u), __float_as_int(val[nz0 + i]));
     for (int i = threadIdx.x; i <= nrows; i += THREADS) s_rp[i] = rowptr[r0 + i] - nz0;
     __syncthreads();
     // The Poisson source Db is zero except on the labelled rows: remember which rows of this block have
@@ -216,7 +241,7 @@ poisson_persistent_kernel(const int *__restrict__ rowptr, const int *__restrict_
             const int beg = s_rp[lr], end = s_rp[lr + 1];
             if (end - beg > kLongRow) continue;
             for (int coff = li * 4; coff < ldu; coff += LANES * 4) {
-                float4 acc = row_times_u<false, UNROLL>(csr, beg, end, u_in, ldu, coff);
+                float4 acc = row_times_u<false, UNROLL>(csr, beg, end, reinterpret_cast<const char *>(u_in + coff));
                 const size_t o = (size_t)(r0 + lr) * ldu + coff;
                 if (s_src[lr]) {
                     const float4 b = __ldg(reinterpret_cast<const float4 *>(Db + o));
@@ -232,7 +257,7 @@ poisson_persistent_kernel(const int *__restrict__ rowptr, const int *__restrict_
             const int per = (end - beg + NG - 1) / NG;
             const int gb = min(end, beg + grp * per), ge = min(end, gb + per);
             for (int coff = li * 4; coff < ldu; coff += LANES * 4) {
-                float4 acc = row_times_u<false, UNROLL>(csr, gb, ge, u_in, ldu, coff);
+                float4 acc = row_times_u<false, UNROLL>(csr, gb, ge, reinterpret_cast<const char *>(u_in + coff));
 #pragma unroll
                 for (int off = LANES; off < 32; off <<= 1) {
                     acc.x += __shfl_xor_sync(0xffffffffu, acc.x, off);
@@ -354,6 +379,7 @@ extern "C" GLB_API int glb_poisson_step(const int32_t *d_rowptr, const int32_t *
     GLB_CHECK_ARG(d_rowptr && d_col && d_val && d_Db && d_u_in && d_u_out, "null pointer");
     GLB_CHECK_ARG(n > 0 && n < (1ll << 31), "n out of range");
     GLB_CHECK_ARG(valid_ld(ldu), "ldu must be a power of two in [4,128] or a multiple of 128");
+    GLB_CHECK_ARG((double)n * ldu * 4.0 < 4294967296.0, "label matrix larger than 4 GiB: 32-bit row offsets overflow");
     GLB_CHECK_ARG(d_u_in != d_u_out, "u_in and u_out must differ");
     dispatch_step(d_rowptr, d_col, d_val, d_Db, d_u_in, d_u_out, n, ldu, (cudaStream_t)stream);
     GLB_LAUNCH_CHECK();
@@ -422,6 +448,7 @@ extern "C" GLB_API int glb_poisson_plan_create(glb_poisson_plan **plan, const in
     GLB_CHECK_ARG(plan && d_rowptr, "null pointer");
     GLB_CHECK_ARG(n > 0 && n < (1ll << 31) && nnz >= 0 && nnz < (1ll << 31), "size out of range");
     GLB_CHECK_ARG(valid_ld(ldu), "bad ldu");
+    GLB_CHECK_ARG((double)n * ldu * 4.0 < 4294967296.0, "label matrix larger than 4 GiB: 32-bit row offsets overflow");
     cudaStream_t st = (cudaStream_t)stream;
     glb_poisson_plan *p = new glb_poisson_plan();
     p->n = n; p->nnz = nnz; p->ldu = ldu; p->persistent = 0; p->d_counter = nullptr; p->d_cta_rows = nullptr;

@@ -75,7 +75,7 @@ class PoissonOperator:
     """P = D^-1 W^T (fp32 CSR) and RW = W^T D^-1 (fp64 values on the same pattern), device resident.
     Setup lines of ssl.poisson._fit, reference graphlearning/ssl.py:615-617, 634-644."""
 
-    def __init__(self, W, reorder=True):
+    def __init__(self, W, reorder=False):
         """W: scipy CSR (host) or DeviceCSR.  reorder=True relabels the nodes with a locality ordering
         (reverse Cuthill-McKee from the host pattern) for the iterate; inputs/outputs keep the caller's
         numbering.  Only possible when W arrives as a host matrix."""
@@ -181,3 +181,42 @@ class PoissonOperator:
         _lib.call("glb_poisson_mixing_T", ptr(self.rowptr), ptr(self.col), ptr(self.RW_val), ptr(vinf), ptr(v), ptr(tmp),
                   self.n, int(min_iter), int(max_iter), ctypes.byref(T), ctypes.byref(launches), cur_stream())
         return T.value
+
+
+class PoissonGraphHandle:
+    """Owner of a glb_poisson_graph (include/glb200.h): the device-resident P / RW / degree state of one weight
+    matrix, reused by every fit on that graph (the reference rebuilds all of it inside each _fit call)."""
+
+    def __init__(self, W, reorder=-1):
+        W = sparse.csr_matrix(W)
+        if W.shape[0] != W.shape[1]:
+            raise ValueError("weight matrix must be square")
+        self.n = W.shape[0]
+        rp = np.ascontiguousarray(W.indptr, dtype=np.int32)
+        col = np.ascontiguousarray(W.indices, dtype=np.int32)
+        val = np.ascontiguousarray(W.data, dtype=np.float64)
+        self._h = ctypes.c_void_p()
+        _lib.call("glb_poisson_graph_create", ctypes.byref(self._h), ctypes.c_void_p(rp.ctypes.data),
+                  ctypes.c_void_p(col.ctypes.data), ctypes.c_void_p(val.ctypes.data), self.n, len(col), int(reorder))
+        self.h2d_bytes = rp.nbytes + col.nbytes + val.nbytes
+
+    def fit(self, source, train_ind, min_iter, max_iter):
+        """-> (u (n,c) float64, T, kernel launches)."""
+        src = np.ascontiguousarray(source, dtype=np.float64)
+        ti = np.ascontiguousarray(train_ind, dtype=np.int64)
+        n, c = src.shape
+        if n != self.n:
+            raise ValueError("source has %d rows, graph has %d nodes" % (n, self.n))
+        u = np.empty((n, c), dtype=np.float64)
+        T, nl = ctypes.c_int(0), ctypes.c_int(0)
+        _lib.call("glb_poisson_graph_fit", self._h, ctypes.c_void_p(src.ctypes.data), c, ctypes.c_void_p(ti.ctypes.data),
+                  len(ti), int(min_iter), int(max_iter), ctypes.c_void_p(u.ctypes.data), ctypes.byref(T), ctypes.byref(nl))
+        return u, T.value, nl.value
+
+    def __del__(self):
+        try:
+            if self._h:
+                _lib.load().glb_poisson_graph_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass

@@ -19,6 +19,19 @@ class graph:
         self.num_nodes = W.shape[0]
         self.label_names = label_names
         self.node_names = node_names
+        self._device = {}
+
+    def poisson_handle(self):
+        """Device-resident Poisson state of this graph's weight matrix (built on first use, then shared by every
+        model/fit on the graph; rebuilt if weight_matrix is replaced)."""
+        from . import device
+        W = self.weight_matrix
+        key = (id(W), W.nnz, id(W.data))
+        ent = self._device.get("poisson")
+        if ent is None or ent[0] != key:
+            ent = (key, device.PoissonGraphHandle(W))
+            self._device["poisson"] = ent
+        return ent[1]
 
     def degree_vector(self):
         """graph.py:108-122."""

@@ -145,18 +145,9 @@ class poisson(ssl):
             if source.shape[1] != k:
                 # the reference adds an (n,k) array to an (n,width) one here and fails in numpy broadcasting
                 raise ValueError("train_labels must be 0..k-1 for the gradient_descent solver")
-            rp = np.ascontiguousarray(W.indptr, dtype=np.int32)
-            col = np.ascontiguousarray(W.indices, dtype=np.int32)
-            val = np.ascontiguousarray(W.data, dtype=np.float64)
-            src = np.ascontiguousarray(source, dtype=np.float64)
-            ti = np.ascontiguousarray(train_ind, dtype=np.int64)
-            u = np.empty((n, k), dtype=np.float64)
-            T, nl = ctypes.c_int(0), ctypes.c_int(0)
-            _lib.call("glb_poisson_gd_host", _as_ptr(rp), _as_ptr(col), _as_ptr(val), n, len(col), _as_ptr(src), k,
-                      _as_ptr(ti), len(ti), int(self.min_iter), int(self.max_iter), _as_ptr(u), ctypes.byref(T),
-                      ctypes.byref(nl))
-            self.iterations = T.value
-            self.gpu_launches = nl.value
+            u, T, nl = self.graph.poisson_handle().fit(source, train_ind, self.min_iter, self.max_iter)
+            self.iterations = T
+            self.gpu_launches = nl
             return u
         raise NotImplementedError("poisson solver %r is not built on the B200 backend yet" % self.solver)
 

@@ -114,16 +114,28 @@ GLB_API int glb_poisson_mixing_T(const int32_t *d_rw_rowptr, const int32_t *d_rw
                          int *T_out, int *launches, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
- * Host-buffer entry point: the whole gradient-descent branch of ssl.poisson._fit
- * (graphlearning/ssl.py:615-670) with HOST inputs/outputs - what the reference's Python would bind in
- * place of its `while` loop.  W is the scipy CSR weight matrix (canonical or not), source is the
- * n x c fp64 Poisson source term (ssl.py:619-622), train_ind the m labelled nodes.  u_out is n x c fp64.
- * Copies host->device, builds P/RW on the device, finds T by the reference's stopping rule (or uses
- * min_iter == max_iter), iterates, copies back.  T_done/launches may be NULL.
+ * Host-buffer entry points: the gradient-descent branch of ssl.poisson._fit (graphlearning/ssl.py:615-670)
+ * with HOST inputs/outputs in the reference's own dtypes - what the reference's Python binds in place of
+ * its `while` loop.
+ *
+ * glb_poisson_graph_create uploads the scipy CSR weight matrix W (canonical or not, diagonal ignored) and
+ * builds, on the device, everything the reference recomputes in every _fit call: degrees, P = D^-1 W^T,
+ * RW = W^T D^-1, vinf = deg/sum(deg).  reorder: 0 = keep the node numbering, 1 = relabel with a locality
+ * ordering (results are still returned in the caller's numbering), -1 = automatic.
+ * glb_poisson_graph_fit runs one fit on that graph: source is the n x c fp64 Poisson source term
+ * (ssl.py:619-622), train_ind the m labelled nodes (used by the stopping rule of ssl.py:639-641,667,669
+ * when min_iter < max_iter; T = max_iter otherwise), u_out the n x c fp64 scores.  Synchronous.
+ * glb_poisson_gd_host = create + fit + destroy.  T_done / launches may be NULL.
  * ------------------------------------------------------------------------------------------- */
+typedef struct glb_poisson_graph glb_poisson_graph;
+GLB_API int glb_poisson_graph_create(glb_poisson_graph **graph, const int32_t *h_rowptr, const int32_t *h_col,
+                                     const double *h_val, int64_t n, int64_t nnz, int reorder);
+GLB_API int glb_poisson_graph_destroy(glb_poisson_graph *graph);
+GLB_API int glb_poisson_graph_fit(glb_poisson_graph *graph, const double *h_source, int c, const int64_t *h_train_ind,
+                                  int64_t m, int min_iter, int max_iter, double *h_u_out, int *T_done, int *launches);
 GLB_API int glb_poisson_gd_host(const int32_t *h_rowptr, const int32_t *h_col, const double *h_val, int64_t n, int64_t nnz,
-                        const double *h_source, int c, const int64_t *h_train_ind, int64_t m, int min_iter,
-                        int max_iter, double *h_u_out, int *T_done, int *launches);
+                                const double *h_source, int c, const int64_t *h_train_ind, int64_t m, int min_iter,
+                                int max_iter, double *h_u_out, int *T_done, int *launches);
 
 #ifdef __cplusplus
 }

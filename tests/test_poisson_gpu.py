@@ -173,7 +173,9 @@ def test_step_and_persistent_kernels_every_width(dev, c):
     assert rel_err(got, ref) <= TOL
     if op.is_persistent(Db.shape[1]):
         assert launches == 1
-        assert np.array_equal(got, got_step)             # same arithmetic order in both kernels
+        assert rel_err(got, got_step) <= 2e-6            # long rows are summed in a different (fixed) order
+    u_again, _ = op.iterate(Db, T)
+    assert np.array_equal(op.unpack(u_again, c).cpu().numpy(), got)      # run-to-run deterministic
     assert float(u[:, c:].abs().max()) == 0.0 if Db.shape[1] > c else True
 
 
@@ -242,7 +244,8 @@ def test_full_size_properties(dev, big):
     a = torch.zeros_like(A); b = torch.zeros_like(A)
     for _ in range(T):
         op.step(A, a, b); a, b = b, a
-    assert torch.equal(a, uA)
+    # same kernel arithmetic except for rows split over a warp (different, fixed, summation order)
+    assert float((a - uA).abs().max() / uA.abs().max()) <= 2e-6
 
 
 def test_full_size_through_host_api(gl, big):
