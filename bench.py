@@ -146,7 +146,7 @@ def run_ours(args, rank, world):
     op = gdev.PoissonOperator(W)
     Db = op.source_to_Db(source)
     ldu = int(Db.shape[1])
-    persistent = op.is_persistent(ldu)
+    kind = op.kind(c)
     u0 = torch.zeros_like(Db); u1 = torch.zeros_like(Db)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
@@ -224,7 +224,8 @@ def run_ours(args, rank, world):
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": "cfg2: 70k nodes, k=10 kNN graph (10 Gaussian blobs), 10 classes, 1 label/class",
                    "n": int(n), "nnz": int(nnz), "classes": c, "iterations_per_step": iters, "ldu": ldu,
-                   "kernel": "poisson_persistent_kernel" if persistent else "poisson_step_kernel",
+                   "kernel": {"dataflow": "poisson_dataflow_kernel", "barrier": "poisson_persistent_kernel",
+                              "step": "poisson_step_kernel"}[kind],
                    "l2": "flushed between steps (256 MiB write); inside a step the 16.8 MB working set is "
                          "L2 resident by construction",
                    "parallelism": "replicas x%d (independent label sets, no collective)" % world},

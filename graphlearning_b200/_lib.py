@@ -24,17 +24,20 @@ SIGNATURES = {
     "glb_csr_transpose": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p,
                                   c_void_p, c_int64, c_void_p]),
     "glb_poisson_scale": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
-    "glb_pack_f64_to_f32": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int, c_void_p, c_void_p]),
-    "glb_unpack_f32_to_f64": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "glb_locality_order_host": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     "glb_csr_permute": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
                                 c_void_p, c_void_p]),
-    "glb_poisson_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
-    "glb_poisson_plan_create": (c_int, [POINTER(c_void_p), c_void_p, c_int64, c_int64, c_int, c_void_p]),
+    "glb_poisson_plan_create": (c_int, [POINTER(c_void_p), c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int,
+                                        c_void_p]),
     "glb_poisson_plan_destroy": (c_int, [c_void_p]),
-    "glb_poisson_plan_is_persistent": (c_int, [c_void_p]),
-    "glb_poisson_iterate": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
-                                    POINTER(c_int), POINTER(c_int), c_void_p]),
+    "glb_poisson_plan_kind": (c_int, [c_void_p]),
+    "glb_poisson_plan_ld": (c_int, [c_void_p]),
+    "glb_poisson_plan_fill": (c_double, [c_void_p]),
+    "glb_poisson_pack": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "glb_poisson_unpack": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "glb_poisson_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "glb_poisson_iterate": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, POINTER(c_int), POINTER(c_int),
+                                    c_void_p]),
     "glb_poisson_mixing_T": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int,
                                      POINTER(c_int), POINTER(c_int), c_void_p]),
     "glb_poisson_graph_create": (c_int, [POINTER(c_void_p), c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int]),

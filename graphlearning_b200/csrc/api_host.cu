@@ -24,20 +24,6 @@ struct DeviceArena {           // frees everything on scope exit, whatever the r
     }
 };
 
-// Db[i,:] = (1/deg[i]) * source[i,:]   (ssl.py:636), packed to n x ldu fp32
-__global__ void __launch_bounds__(256)
-scaled_pack_kernel(const double *__restrict__ src, const double *__restrict__ deg, long long n, int c,
-                   float *__restrict__ dst, int ldu, const int *__restrict__ perm)
-{
-    const long long total = n * ldu;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const long long r = i / ldu;
-        const int k = (int)(i - r * ldu);
-        const long long sr = perm ? perm[r] : r;
-        dst[i] = (k < c) ? (float)((1.0 / deg[sr]) * src[sr * c + k]) : 0.f;
-    }
-}
-
 // deterministic two-pass sum of deg (fixed grid, fixed order)
 __global__ void __launch_bounds__(256) partial_sum_kernel(const double *__restrict__ x, long long n, double *__restrict__ part)
 {
@@ -100,7 +86,7 @@ struct glb_poisson_graph {
     const float *it_val = nullptr;
     int *perm = nullptr;
     // per-width work buffers and plan (kept for the last width used)
-    int ldu = 0, c_cap = 0;
+    int ldu = 0, c_plan = 0;
     int64_t m_cap = 0;
     double *src64 = nullptr;             // n x c staging (source in, result out)
     float *Db = nullptr, *u0 = nullptr, *u1 = nullptr;
@@ -188,19 +174,21 @@ extern "C" GLB_API int glb_poisson_graph_fit(glb_poisson_graph *g, const double 
     GLB_CHECK_ARG(min_iter >= 0 && max_iter >= 0, "iteration counts must be >= 0");
     GLB_CHECK_ARG(m == 0 || h_train_ind, "train_ind is null");
     const int64_t n = g->n, nnz = g->nnz;
-    const int ldu = glb_padded_ld(c);
     cudaStream_t st = 0;
     int nl = 0, rc;
-    if (ldu != g->ldu || c > g->c_cap) {                 // (re)size the per-width buffers and the plan
-        if (g->plan) { glb_poisson_plan_destroy(g->plan); g->plan = nullptr; }
-        GLB_CUDA(g->A.alloc(&g->src64, n * c));  GLB_CUDA(g->A.alloc(&g->Db, n * ldu));
-        GLB_CUDA(g->A.alloc(&g->u0, n * ldu));   GLB_CUDA(g->A.alloc(&g->u1, n * ldu));
-        if ((rc = glb_poisson_plan_create(&g->plan, g->it_rp, n, nnz, ldu, st))) return rc;
-        g->ldu = ldu; g->c_cap = c;
+    if (c != g->c_plan) {                                // (re)build the plan and the per-width buffers
+        if (g->plan) { glb_poisson_plan_destroy(g->plan); g->plan = nullptr; g->c_plan = 0; }
+        if ((rc = glb_poisson_plan_create(&g->plan, g->it_rp, g->it_col, g->it_val, n, nnz, c, GLB_POISSON_KIND_AUTO, st)))
+            return rc;
+        const int ld = glb_poisson_plan_ld(g->plan);
+        GLB_CUDA(g->A.alloc(&g->src64, n * c));  GLB_CUDA(g->A.alloc(&g->Db, n * ld));
+        GLB_CUDA(g->A.alloc(&g->u0, n * ld));    GLB_CUDA(g->A.alloc(&g->u1, n * ld));
+        g->ldu = ld; g->c_plan = c;
     }
+    const int ldu = g->ldu;
     if (m > g->m_cap) { GLB_CUDA(g->A.alloc(&g->tind, m)); g->m_cap = m; }
     GLB_CUDA(cudaMemcpyAsync(g->src64, h_source, n * c * sizeof(double), cudaMemcpyHostToDevice, st));
-    scaled_pack_kernel<<<sm_count() * 8, 256, 0, st>>>(g->src64, g->deg, n, c, g->Db, ldu, g->perm);
+    if ((rc = glb_poisson_pack(g->plan, g->src64, g->deg, g->perm, g->Db, st))) return rc;
     nl += 1;
 
     // iteration count by the reference's stopping rule (ssl.py:639-644, 667, 669)
@@ -219,8 +207,8 @@ extern "C" GLB_API int glb_poisson_graph_fit(glb_poisson_graph *g, const double 
     }
     GLB_CUDA(cudaMemsetAsync(g->u0, 0, n * ldu * sizeof(float), st));
     int in_u1 = 0;
-    if ((rc = glb_poisson_iterate(g->plan, g->it_rp, g->it_col, g->it_val, g->Db, g->u0, g->u1, T, &in_u1, &nl, st))) return rc;
-    if ((rc = glb_unpack_f32_to_f64(in_u1 ? g->u1 : g->u0, n, c, ldu, g->src64, g->perm, st))) return rc;
+    if ((rc = glb_poisson_iterate(g->plan, g->Db, g->u0, g->u1, T, &in_u1, &nl, st))) return rc;
+    if ((rc = glb_poisson_unpack(g->plan, in_u1 ? g->u1 : g->u0, g->perm, g->src64, st))) return rc;
     nl += 1;
     GLB_CUDA(cudaMemcpyAsync(h_u_out, g->src64, n * c * sizeof(double), cudaMemcpyDeviceToHost, st));
     GLB_CUDA(cudaStreamSynchronize(st));

@@ -79,32 +79,6 @@ poisson_scale_kernel(const int *__restrict__ rowptr, const int *__restrict__ col
     }
 }
 
-__global__ void __launch_bounds__(256)
-pack_kernel(const double *__restrict__ src, long long n, int c, float *__restrict__ dst, int ldu,
-            const int *__restrict__ perm)
-{
-    const long long total = n * ldu;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const long long r = i / ldu;
-        const int k = (int)(i - r * ldu);
-        const long long sr = perm ? perm[r] : r;                 // device row r holds the caller's row perm[r]
-        dst[i] = (k < c) ? (float)src[sr * c + k] : 0.f;
-    }
-}
-
-__global__ void __launch_bounds__(256)
-unpack_kernel(const float *__restrict__ src, long long n, int c, int ldu, double *__restrict__ dst,
-              const int *__restrict__ perm)
-{
-    const long long total = n * c;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const long long r = i / c;
-        const int k = (int)(i - r * c);
-        const long long dr = perm ? perm[r] : r;
-        dst[dr * c + k] = (double)src[r * ldu + k];
-    }
-}
-
 static int stream_blocks(int64_t work, int threads = 256)
 {
     int64_t b = (work + threads - 1) / threads;
@@ -189,22 +163,3 @@ extern "C" GLB_API int glb_poisson_scale(const int32_t *d_t_rowptr, const int32_
     return 0;
 }
 
-extern "C" GLB_API int glb_pack_f64_to_f32(const double *d_src, int64_t n, int c, float *d_dst, int ldu,
-                                           const int32_t *d_perm, void *stream)
-{
-    GLB_CHECK_ARG(d_src && d_dst, "null pointer");
-    GLB_CHECK_ARG(n > 0 && c > 0 && ldu >= c, "bad shape");
-    pack_kernel<<<stream_blocks(n * ldu), 256, 0, (cudaStream_t)stream>>>(d_src, n, c, d_dst, ldu, d_perm);
-    GLB_LAUNCH_CHECK();
-    return 0;
-}
-
-extern "C" GLB_API int glb_unpack_f32_to_f64(const float *d_src, int64_t n, int c, int ldu, double *d_dst,
-                                             const int32_t *d_perm, void *stream)
-{
-    GLB_CHECK_ARG(d_src && d_dst, "null pointer");
-    GLB_CHECK_ARG(n > 0 && c > 0 && ldu >= c, "bad shape");
-    unpack_kernel<<<stream_blocks(n * c), 256, 0, (cudaStream_t)stream>>>(d_src, n, c, ldu, d_dst, d_perm);
-    GLB_LAUNCH_CHECK();
-    return 0;
-}

@@ -3,24 +3,34 @@
 // Replaces the hot loop of ssl.poisson._fit, gradient-descent branch
 // (reference graphlearning/ssl.py:667-669; third-party arithmetic: scipy _sparsetools csr_matvecs).
 //
-// Two kernels:
-//   poisson_step_kernel        one iteration per launch.  CSR (col,val) streamed coalesced, rows of the
-//                              row-major n x ldu label matrix gathered with 128-bit loads, D^-1 folded into
-//                              the values, "+ Db" fused into the store.  For graphs too big for the
-//                              persistent kernel; genuinely HBM/L2-gather bound.
-//   poisson_persistent_kernel  T iterations in ONE cooperative launch, one CTA per SM.  Each CTA stages the
-//                              CSR slab and Db slab of its row block in shared memory once, so per iteration
-//                              only the u gathers (L2) and the u store touch global memory; iterations are
-//                              separated by a hand-rolled grid barrier.  For the 70k-node north-star
-//                              graph the whole working set is L2 resident and a launch per iteration
-//                              (~2-3 us) would cost as much as the iteration itself.
+// On a kNN graph one iteration is nnz random gathers of a 64-byte row of the label matrix (c = 10 classes).
+// tools/gather_microbench.cu measured what one SM can gather from L2: 1.0 row per cycle through LDG.128
+// (one L1 wavefront per row; 17 TB/s chip-wide), 3.5-5 cycles per row through the TMA unit (bulk copies,
+// tile::gather4).  So the iterate is bound by L1 wavefronts, ~6800 per SM per iteration on the 70k-node
+// graph = 3.5 us, and every cycle spent elsewhere (grid barriers, instruction issue, divergence) is on top.
 //
-// Lane mapping (both kernels): LANES = ldu/4 lanes own one matrix row; lane li holds the float4 of output
-// columns [4*li, 4*li+4) (for ldu > 128 it loops over column tiles).  One warp-wide LDG.128 therefore
-// gathers 32/LANES complete rows of u, each row = one 64-byte (ldu=16) piece of a single 128-byte line,
-// which is what the L1TEX tag stage likes (one tag look-up per gathered row).  Each lane walks the
-// nonzeros of its row UNROLL at a time: all UNROLL gathers are issued before the first FMA so that
-// every thread keeps UNROLL L2 requests in flight; there is no cross-lane reduction at all.
+// Three kernels, chosen per graph by glb_poisson_plan_create:
+//   poisson_dataflow_kernel    T iterations in ONE launch, one CTA per SM, NO grid barrier: every 16-byte chunk
+//                              of a label row carries three values plus the iteration number that produced it
+//                              ("flag in data"), so a gather doubles as the synchronisation - a lane whose chunk
+//                              is still from an older iteration simply re-polls it.  Rows of the CTA are sorted by
+//                              length and stored as sliced ELL (8 rows per warp pass) in shared memory, so warps
+//                              run without divergence and read their (offset,value) pairs conflict-free.  Needs a
+//                              structurally symmetric pattern (then two ping-pong buffers are race-free: a row
+//                              can only be overwritten after every reader of it has moved on, see below).
+//   poisson_persistent_kernel  T iterations in one cooperative launch with a hand-rolled grid barrier between
+//                              iterations; CSR slab in shared memory.  For directed graphs (symmetrize=False).
+//   poisson_step_kernel        one iteration per launch, CSR read from global memory.  For graphs too big for the
+//                              shared-memory slabs; genuinely HBM/L2-gather bound.
+//
+// Lane mapping (all kernels): LANES lanes own one matrix row, each lane one 16-byte piece of it; a warp-wide
+// LDG.128 gathers 32/LANES complete rows.  Each lane walks the nonzeros of its row UNROLL at a time: all UNROLL
+// gathers are issued before the first FMA; there is no cross-lane reduction at all.
+//
+// Label-matrix layouts (glb_poisson_plan_ld gives the row stride):
+//   plain    row-major n x ldu fp32, ldu = glb_padded_ld(c)                        (step / barrier kernels)
+//   flagged  row-major n x ldu fp32, ldu = 4 * LANES; chunk q of a row = {x[3q], x[3q+1], x[3q+2], epoch}
+//            (dataflow kernel; the step kernel can read and write it too, ignoring the epoch word)
 #include <stdlib.h>
 #include <string.h>
 #include <algorithm>
@@ -109,7 +119,7 @@ __device__ __forceinline__ float4 row_times_u(const Csr &csr, int beg, int end, 
 // ------------------------------------------------------------------------------------------------
 // K1: one iteration per launch, CSR read from global memory
 // ------------------------------------------------------------------------------------------------
-template <int LANES>
+template <int LANES, bool FLAGGED>
 __global__ void __launch_bounds__(256)
 poisson_step_kernel(const int *__restrict__ rowptr, const int *__restrict__ col, const float *__restrict__ val,
                     const float *__restrict__ Db, const float *__restrict__ u_in, float *__restrict__ u_out,
@@ -126,6 +136,7 @@ poisson_step_kernel(const int *__restrict__ rowptr, const int *__restrict__ col,
             const size_t o = (size_t)row * ldu + coff;
             const float4 b = __ldg(reinterpret_cast<const float4 *>(Db + o));
             acc.x += b.x; acc.y += b.y; acc.z += b.z; acc.w += b.w;
+            if (FLAGGED) acc.w = 0.f;                      // the epoch word of the chunk is not data
             *reinterpret_cast<float4 *>(u_out + o) = acc;
         }
     }
@@ -280,6 +291,186 @@ poisson_persistent_kernel(const int *__restrict__ rowptr, const int *__restrict_
 }
 
 // ------------------------------------------------------------------------------------------------
+// K3: persistent, barrier-free ("flag in data"), T iterations per launch
+// ------------------------------------------------------------------------------------------------
+// Version v of the label matrix (v = number of iterations applied) lives in buffer v & 1 and every 16-byte
+// chunk of it carries the word 1 + v.  Iteration t gathers chunks of version t, re-polling any chunk whose
+// word is not 1 + t yet, and stores its own chunk of version t + 1.  Loads and stores are 16-byte single
+// transactions at L2 (ld/st.relaxed.gpu, L1 bypassed), so a chunk is seen whole or not at all.
+//
+// Why two buffers are enough when the sparsity pattern is symmetric: chunk q of u_{v+2}[i] overwrites chunk q
+// of u_v[i].  Its readers are lane q of the rows j with i in row j's pattern; by symmetry j is in row i's
+// pattern, so lane q of row i gathered u_{v+1}[j] (chunk q) before it stored u_{v+2}[i], and lane q of row j
+// stored u_{v+1}[j] only after its own gather of u_v[i] had returned.  Every row is owned by the same lane
+// group in every iteration and a lane group finishes iteration t before it starts t + 1, so the chain holds
+// chunk by chunk without any fence.  Progress: the unfinished work item with the smallest iteration number
+// always has all its inputs, all CTAs are co-resident (cooperative launch), so no wait cycle can form.
+constexpr unsigned kPadOff = 0xFFFFFFFFu;        // (offset) of a padding entry of the sliced-ELL slab
+constexpr int kRowSrcBit = 0x40000000;           // slot_rows: row has a nonzero source term Db
+
+__device__ __forceinline__ uint4 ld_chunk(const char *p)
+{
+    uint4 v;
+    asm volatile("ld.relaxed.gpu.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_chunk(char *p, float a, float b, float c, unsigned w)
+{
+    asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(__float_as_uint(a)), "r"(__float_as_uint(b)),
+                 "r"(__float_as_uint(c)), "r"(w) : "memory");
+}
+
+template <int LANES, int THREADS, int U>
+__global__ void __launch_bounds__(THREADS, 1)
+poisson_dataflow_kernel(const int2 *__restrict__ slabs, const long long *__restrict__ slab_off,
+                        const int2 *__restrict__ slots, const int *__restrict__ slot_off,
+                        const int *__restrict__ slot_rows, const float *__restrict__ Db, float *u0, float *u1, int T,
+                        int cap_entries, int cap_slots, unsigned long long *stats, int nopoll)
+{
+    constexpr int RPW = 32 / LANES;              // rows per warp pass = slice height of the ELL slab
+    constexpr int NW = THREADS / 32;
+    constexpr unsigned ROWB = LANES * 16;        // bytes per label row
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    int2 *s_cv = reinterpret_cast<int2 *>(smem_raw);
+    int2 *s_slot = s_cv + cap_entries;
+    int *s_rows = reinterpret_cast<int *>(s_slot + cap_slots);
+
+    const long long e0 = slab_off[blockIdx.x];
+    const int nent = (int)(slab_off[blockIdx.x + 1] - e0);
+    const int sl0 = slot_off[blockIdx.x];
+    const int nslots = slot_off[blockIdx.x + 1] - sl0;
+    for (int i = threadIdx.x; i < nent; i += THREADS) s_cv[i] = slabs[e0 + i];
+    for (int i = threadIdx.x; i < nslots; i += THREADS) s_slot[i] = slots[sl0 + i];
+    // The Poisson source Db is zero except on the labelled rows: remember which rows have one
+    for (int i = threadIdx.x; i < nslots * RPW; i += THREADS) {
+        int r = slot_rows[(size_t)sl0 * RPW + i];
+        if (r >= 0) {
+            bool nz = false;
+            const float4 *b = reinterpret_cast<const float4 *>(Db + (size_t)r * (ROWB / 4));
+            for (int q = 0; q < LANES; ++q) {
+                const float4 v = __ldg(b + q);
+                nz |= (v.x != 0.f) | (v.y != 0.f) | (v.z != 0.f);               // NaN != 0 is true
+            }
+            if (nz) r |= kRowSrcBit;
+        }
+        s_rows[i] = r;
+    }
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane / LANES, li = lane % LANES;
+    unsigned long long n_poll = 0, n_badbatch = 0;      // stats only (GLB_POISSON_STATS)
+    const long long clk0 = clock64();
+    for (int t = 0; t < T; ++t) {
+        const char *in = reinterpret_cast<const char *>(((t & 1) && !(nopoll & 4)) ? u1 : u0) + li * 16;
+        char *out = reinterpret_cast<char *>(((t & 1) && !(nopoll & 4)) ? u0 : u1) + li * 16;
+        const unsigned expect = 1u + (unsigned)t;
+        for (int s = warp; s < nslots; s += NW) {
+            const int2 sl = s_slot[s];                       // (first entry, slice width)
+            const int2 *cv = s_cv + sl.x + g;                // entry j of this lane group's row: cv[j * RPW]
+            const int L = sl.y;
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+            for (int j0 = 0; j0 < L; j0 += U) {
+                unsigned off[U];
+                float val[U];
+                uint4 x[U];
+#pragma unroll
+                for (int i = 0; i < U; ++i) {
+                    int2 e = make_int2((int)kPadOff, 0);
+                    if (j0 + i < L) e = cv[(j0 + i) * RPW];
+                    off[i] = (unsigned)e.x;
+                    val[i] = __int_as_float(e.y);
+                }
+#pragma unroll
+                for (int i = 0; i < U; ++i) {
+                    x[i] = make_uint4(0u, 0u, 0u, expect);
+                    if (off[i] != kPadOff) x[i] = ld_chunk(in + off[i]);
+                }
+                unsigned bad = 0;
+#pragma unroll
+                for (int i = 0; i < U; ++i) bad |= x[i].w ^ expect;
+                while (bad && !(nopoll & 1)) {                     // some producer is still behind: re-poll the stale chunks together
+                    ++n_badbatch;
+#pragma unroll
+                    for (int i = 0; i < U; ++i)
+                        if (x[i].w != expect) { x[i] = ld_chunk(in + off[i]); ++n_poll; }
+                    bad = 0;
+#pragma unroll
+                    for (int i = 0; i < U; ++i) bad |= x[i].w ^ expect;
+                }
+#pragma unroll
+                for (int i = 0; i < U; ++i) {
+                    a0 = fmaf(val[i], __uint_as_float(x[i].x), a0);
+                    a1 = fmaf(val[i], __uint_as_float(x[i].y), a1);
+                    a2 = fmaf(val[i], __uint_as_float(x[i].z), a2);
+                }
+            }
+            const int rinfo = s_rows[s * RPW + g];
+            if (rinfo >= 0) {
+                const unsigned row = (unsigned)(rinfo & (kRowSrcBit - 1));
+                if (rinfo & kRowSrcBit) {
+                    const float4 b = __ldg(reinterpret_cast<const float4 *>(Db + (size_t)row * (ROWB / 4)) + li);
+                    a0 += b.x; a1 += b.y; a2 += b.z;
+                }
+                if (!(nopoll & 2) || a0 == 123.456f) st_chunk(out + (size_t)row * ROWB, a0, a1, a2, expect + 1u);
+            }
+        }
+    }
+    if (stats) {
+        atomicAdd(stats + 0, n_poll);
+        atomicAdd(stats + 1, n_badbatch);
+        if (lane == 0) atomicMax(stats + 2, (unsigned long long)(clock64() - clk0));
+        if (threadIdx.x == 0) atomicAdd(stats + 3, 1ull);
+    }
+}
+
+// epoch words of the two buffers before a launch: version 0 in u0 (word 1), nothing valid in u1 (word 0)
+__global__ void __launch_bounds__(256) stamp_kernel(float *u0, float *u1, long long nchunks)
+{
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nchunks; i += (long long)gridDim.x * blockDim.x) {
+        reinterpret_cast<unsigned *>(u0)[i * 4 + 3] = 1u;
+        reinterpret_cast<unsigned *>(u1)[i * 4 + 3] = 0u;
+    }
+}
+
+// label matrix <-> device layout.  dst (n x ldu fp32) <- scale_row * src (n x c fp64); device row r = caller's
+// row perm[r].  FLAGGED: column k lives at float (k / 3) * 4 + k % 3 of the row.
+template <bool FLAGGED>
+__global__ void __launch_bounds__(256)
+pack_kernel(const double *__restrict__ src, const double *__restrict__ inv_scale, long long n, int c,
+            float *__restrict__ dst, int ldu, const int *__restrict__ perm)
+{
+    const long long total = n * ldu;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / ldu;
+        const int p = (int)(i - r * ldu);
+        const int k = FLAGGED ? ((p & 3) == 3 ? c : (p >> 2) * 3 + (p & 3)) : p;
+        const long long sr = perm ? perm[r] : r;
+        float v = 0.f;
+        if (k < c) {
+            const double s = src[sr * c + k];
+            v = (float)(inv_scale ? (1.0 / inv_scale[sr]) * s : s);           // D^-1 * source, ssl.py:636
+        }
+        dst[i] = v;
+    }
+}
+
+template <bool FLAGGED>
+__global__ void __launch_bounds__(256)
+unpack_kernel(const float *__restrict__ src, long long n, int c, int ldu, double *__restrict__ dst,
+              const int *__restrict__ perm)
+{
+    const long long total = n * c;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / c;
+        const int k = (int)(i - r * c);
+        const long long dr = perm ? perm[r] : r;
+        const int p = FLAGGED ? (k / 3) * 4 + k % 3 : k;
+        dst[dr * c + k] = (double)src[r * ldu + p];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // mixing vector v <- RW v (fp64) and max|v - vinf|     (ssl.py:667,669)
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void block_max_to_global(double m, unsigned long long *out)
@@ -335,7 +526,7 @@ maxdiff_kernel(const double *__restrict__ v, const double *__restrict__ vinf, in
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-template <int LANES>
+template <int LANES, bool FLAGGED>
 static int launch_step(const int *rp, const int *col, const float *val, const float *Db, const float *u_in,
                        float *u_out, int64_t n, int ldu, cudaStream_t st)
 {
@@ -345,142 +536,269 @@ static int launch_step(const int *rp, const int *col, const float *val, const fl
     const int64_t cap = (int64_t)sm_count() * 8 * 8;           // 8 resident CTAs/SM x 8 waves, then grid-stride
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    poisson_step_kernel<LANES><<<(unsigned)blocks, threads, 0, st>>>(rp, col, val, Db, u_in, u_out, (int)n, ldu);
+    poisson_step_kernel<LANES, FLAGGED><<<(unsigned)blocks, threads, 0, st>>>(rp, col, val, Db, u_in, u_out, (int)n, ldu);
     return 0;
 }
 
+template <bool FLAGGED>
 static int dispatch_step(const int *rp, const int *col, const float *val, const float *Db, const float *u_in,
                          float *u_out, int64_t n, int ldu, cudaStream_t st)
 {
     switch (ldu) {
-        case 4: return launch_step<1>(rp, col, val, Db, u_in, u_out, n, ldu, st);
-        case 8: return launch_step<2>(rp, col, val, Db, u_in, u_out, n, ldu, st);
-        case 16: return launch_step<4>(rp, col, val, Db, u_in, u_out, n, ldu, st);
-        case 32: return launch_step<8>(rp, col, val, Db, u_in, u_out, n, ldu, st);
-        case 64: return launch_step<16>(rp, col, val, Db, u_in, u_out, n, ldu, st);
-        default: return launch_step<32>(rp, col, val, Db, u_in, u_out, n, ldu, st);
+        case 4: return launch_step<1, FLAGGED>(rp, col, val, Db, u_in, u_out, n, ldu, st);
+        case 8: return launch_step<2, FLAGGED>(rp, col, val, Db, u_in, u_out, n, ldu, st);
+        case 16: return launch_step<4, FLAGGED>(rp, col, val, Db, u_in, u_out, n, ldu, st);
+        case 32: return launch_step<8, FLAGGED>(rp, col, val, Db, u_in, u_out, n, ldu, st);
+        case 64: return launch_step<16, FLAGGED>(rp, col, val, Db, u_in, u_out, n, ldu, st);
+        default: return launch_step<32, FLAGGED>(rp, col, val, Db, u_in, u_out, n, ldu, st);
     }
 }
 
-static bool valid_ld(int ldu)
+static inline int float_bits(float f) { int i; memcpy(&i, &f, sizeof(i)); return i; }
+
+static int flagged_lanes(int c)           // lanes per row of the flagged layout: 3 values per 16-byte chunk
 {
-    if (ldu < 4) return false;
-    if (ldu <= 128) return (ldu & (ldu - 1)) == 0;
-    return ldu % 128 == 0;
+    int lanes = 1;
+    while (lanes * 3 < c && lanes < 32) lanes <<= 1;
+    return lanes * 3 >= c ? lanes : 0;    // 0: too wide (c > 96)
+}
+
+static int stream_blocks_p(int64_t work, int threads = 256)
+{
+    int64_t b = (work + threads - 1) / threads;
+    const int64_t cap = (int64_t)sm_count() * 16;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return (int)b;
 }
 
 }  // namespace glb
 
 using namespace glb;
 
-extern "C" GLB_API int glb_poisson_step(const int32_t *d_rowptr, const int32_t *d_col, const float *d_val, const float *d_Db,
-                                const float *d_u_in, float *d_u_out, int64_t n, int ldu, void *stream)
-{
-    GLB_CHECK_ARG(d_rowptr && d_col && d_val && d_Db && d_u_in && d_u_out, "null pointer");
-    GLB_CHECK_ARG(n > 0 && n < (1ll << 31), "n out of range");
-    GLB_CHECK_ARG(valid_ld(ldu), "ldu must be a power of two in [4,128] or a multiple of 128");
-    GLB_CHECK_ARG((double)n * ldu * 4.0 < 4294967296.0, "label matrix larger than 4 GiB: 32-bit row offsets overflow");
-    GLB_CHECK_ARG(d_u_in != d_u_out, "u_in and u_out must differ");
-    dispatch_step(d_rowptr, d_col, d_val, d_Db, d_u_in, d_u_out, n, ldu, (cudaStream_t)stream);
-    GLB_LAUNCH_CHECK();
-    return 0;
-}
-
 struct glb_poisson_plan {
-    int64_t n, nnz;
-    int ldu;
-    int persistent;
-    int grid, max_rows, slab_cap;
-    int threads;
-    const void *fn;
-    size_t smem_bytes;
-    unsigned *d_counter;      // barrier words: kFlagStride * grid unsigned
-    int *d_cta_rows;          // grid + 1 row boundaries of the work-balanced partition
+    int64_t n = 0, nnz = 0;
+    int c = 0, ldu = 0, kind = GLB_POISSON_KIND_STEP;
+    const int *d_rowptr = nullptr, *d_col = nullptr;       // caller-owned CSR of P
+    const float *d_val = nullptr;
+    int grid = 0, threads = 0;
+    const void *fn = nullptr;
+    size_t smem_bytes = 0;
+    // barrier kernel
+    int max_rows = 0, slab_cap = 0;
+    unsigned *d_counter = nullptr;      // barrier words: kFlagStride * grid unsigned
+    int *d_cta_rows = nullptr;          // grid + 1 row boundaries of the work-balanced partition
+    // dataflow kernel: sliced-ELL slabs of every CTA, back to back
+    int2 *d_slabs = nullptr, *d_slots = nullptr;
+    long long *d_slab_off = nullptr;
+    int *d_slot_off = nullptr, *d_slot_rows = nullptr;
+    int cap_entries = 0, cap_slots = 0;
+    double ell_fill = 0.0;              // nnz / stored entries of the slabs
+    float tuned_ms[2] = {0.f, 0.f};     // AUTO: measured ms of the trial run, {dataflow, barrier}
+    unsigned long long *d_stats = nullptr;   // GLB_POISSON_STATS=1: {re-polls, batches that had to poll, max warp cycles, CTAs}
 };
 
-// Launch geometry of the persistent kernel.  Default: 1024 threads, 4 gathers in flight per lane, counter
-// barrier (fastest in the r1b sweep, profiles/).  GLB_POISSON_VARIANT="threads,unroll,flags" (e.g. "512,16,0") selects another instantiation for
-// experiments; unknown combinations fall back to the default.
-struct PersistVariant { int threads, unroll, flags; };
+// Launch geometry of the persistent kernels.  GLB_POISSON_VARIANT="threads,unroll" selects another
+// instantiation for experiments (tools/poisson_sweep.py); unknown combinations fall back to the default.
+struct PersistVariant { int threads, unroll; };
 
-static PersistVariant persist_variant()
+static PersistVariant persist_variant(int def_threads, int def_unroll)
 {
-    PersistVariant v{1024, 4, 0};
+    PersistVariant v{def_threads, def_unroll};
     const char *e = getenv("GLB_POISSON_VARIANT");
     if (e) {
-        int t = 0, u = 0, f = 0;
-        if (sscanf(e, "%d,%d,%d", &t, &u, &f) == 3) { v.threads = t; v.unroll = u; v.flags = f; }
+        int t = 0, u = 0;
+        if (sscanf(e, "%d,%d", &t, &u) == 2) { v.threads = t; v.unroll = u; }
     }
     return v;
 }
 
 template <int LANES>
-static const void *persistent_fn(const PersistVariant &v, int *threads)
+static const void *barrier_fn(int *threads)
 {
-#define GLB_PV(T_, U_, F_)                                                      \
-    if (v.threads == T_ && v.unroll == U_ && v.flags == F_) {                   \
-        *threads = T_;                                                          \
-        return (const void *)poisson_persistent_kernel<LANES, T_, U_, (F_) != 0>; \
-    }
-    GLB_PV(1024, 8, 1) GLB_PV(1024, 8, 0) GLB_PV(1024, 4, 1) GLB_PV(1024, 4, 0)
-    GLB_PV(512, 8, 1) GLB_PV(512, 16, 1) GLB_PV(512, 16, 0) GLB_PV(768, 8, 1)
-#undef GLB_PV
     *threads = 1024;
     return (const void *)poisson_persistent_kernel<LANES, 1024, 4, false>;
 }
 
-static const void *pick_persistent(int ldu, int *threads)
+static const void *pick_barrier(int ldu, int *threads)
 {
-    const PersistVariant v = persist_variant();
     switch (ldu) {
-        case 4: return persistent_fn<1>(v, threads);
-        case 8: return persistent_fn<2>(v, threads);
-        case 16: return persistent_fn<4>(v, threads);
-        case 32: return persistent_fn<8>(v, threads);
-        case 64: return persistent_fn<16>(v, threads);
-        default: return persistent_fn<32>(v, threads);
+        case 4: return barrier_fn<1>(threads);
+        case 8: return barrier_fn<2>(threads);
+        case 16: return barrier_fn<4>(threads);
+        case 32: return barrier_fn<8>(threads);
+        case 64: return barrier_fn<16>(threads);
+        default: return barrier_fn<32>(threads);
     }
 }
 
-extern "C" GLB_API int glb_poisson_plan_create(glb_poisson_plan **plan, const int32_t *d_rowptr, int64_t n, int64_t nnz,
-                                       int ldu, void *stream)
+template <int LANES>
+static const void *dataflow_fn(const PersistVariant &v, int *threads)
 {
-    GLB_CHECK_ARG(plan && d_rowptr, "null pointer");
-    GLB_CHECK_ARG(n > 0 && n < (1ll << 31) && nnz >= 0 && nnz < (1ll << 31), "size out of range");
-    GLB_CHECK_ARG(valid_ld(ldu), "bad ldu");
-    GLB_CHECK_ARG((double)n * ldu * 4.0 < 4294967296.0, "label matrix larger than 4 GiB: 32-bit row offsets overflow");
-    cudaStream_t st = (cudaStream_t)stream;
-    glb_poisson_plan *p = new glb_poisson_plan();
-    p->n = n; p->nnz = nnz; p->ldu = ldu; p->persistent = 0; p->d_counter = nullptr; p->d_cta_rows = nullptr;
-    p->grid = 0; p->max_rows = 0; p->slab_cap = 0; p->smem_bytes = 0; p->threads = 0; p->fn = nullptr;
-    *plan = p;
+#define GLB_DV(T_, U_)                                                  \
+    if (v.threads == T_ && v.unroll == U_) {                            \
+        *threads = T_;                                                  \
+        return (const void *)poisson_dataflow_kernel<LANES, T_, U_>;    \
+    }
+    GLB_DV(1024, 4) GLB_DV(1024, 8) GLB_DV(768, 8) GLB_DV(512, 8) GLB_DV(512, 16) GLB_DV(256, 16)
+#undef GLB_DV
+    *threads = 512;
+    return (const void *)poisson_dataflow_kernel<LANES, 512, 16>;
+}
 
-    int dev = 0, coop = 0, max_smem = 0;
-    GLB_CUDA(cudaGetDevice(&dev));
-    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
-    cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-    const int sms = sm_count();
+static const void *pick_dataflow(int lanes, int *threads)
+{
+    const PersistVariant v = persist_variant(512, 16);     // r1i probe (profiles/): one batch per row keeps the producers ahead
+    switch (lanes) {
+        case 1: return dataflow_fn<1>(v, threads);
+        case 2: return dataflow_fn<2>(v, threads);
+        case 4: return dataflow_fn<4>(v, threads);
+        case 8: return dataflow_fn<8>(v, threads);
+        case 16: return dataflow_fn<16>(v, threads);
+        default: return dataflow_fn<32>(v, threads);
+    }
+}
+
+// work-balanced contiguous row partition: cost(row) = nnz(row) + extra
+static void balanced_bounds(const std::vector<int> &h_rp, int64_t n, int grid, double extra, std::vector<int> &bounds)
+{
+    bounds.assign((size_t)grid + 1, 0);
+    const double total = (double)h_rp[n] + extra * (double)n;
+    int b = 1;
+    for (int64_t i = 0; i < n && b < grid; ++i) {
+        const double pref = (double)h_rp[i + 1] + extra * (double)(i + 1);
+        while (b < grid && pref >= total * b / grid) bounds[b++] = (int)(i + 1);
+    }
+    for (; b <= grid; ++b) bounds[b] = (int)n;
+    bounds[grid] = (int)n;
+}
+
+// is (j,i) stored for every stored (i,j)?  (explicit zeros count: only the pattern matters)
+static bool pattern_symmetric(const std::vector<int> &rp, const std::vector<int> &col, int64_t n)
+{
+    std::vector<int> sorted(col);
+    for (int64_t i = 0; i < n; ++i)
+        if (!std::is_sorted(sorted.begin() + rp[i], sorted.begin() + rp[i + 1]))
+            std::sort(sorted.begin() + rp[i], sorted.begin() + rp[i + 1]);
+    for (int64_t i = 0; i < n; ++i)
+        for (int j = rp[i]; j < rp[i + 1]; ++j) {
+            const int cj = sorted[j];
+            if (cj < 0 || cj >= n) return false;
+            if (!std::binary_search(sorted.begin() + rp[cj], sorted.begin() + rp[cj + 1], (int)i)) return false;
+        }
+    return true;
+}
+
+// Try to set the plan up for the dataflow kernel.  Returns 0 and leaves kind untouched when the graph does not
+// qualify (pattern not symmetric, slabs too large for shared memory, label rows too wide).
+static int plan_try_dataflow(glb_poisson_plan *p, const std::vector<int> &h_rp, int sms, int max_smem, cudaStream_t st)
+{
+    const int64_t n = p->n, nnz = p->nnz;
+    const int lanes = flagged_lanes(p->c);
+    if (!lanes) return 0;
+    const int rowb = lanes * 16, rpw = 32 / lanes;
+    if ((double)n * rowb >= 4294967295.0 || n >= kRowSrcBit) return 0;
+    int grid = (int)((n + 63) / 64);                  // tiny graphs: at least ~64 rows per CTA
+    if (grid > sms) grid = sms;
+    if (grid < 1) grid = 1;
+    if ((double)nnz * 8.0 / grid > (double)max_smem) return 0;
+
+    std::vector<int> h_col((size_t)nnz);
+    std::vector<float> h_val((size_t)nnz);
+    if (nnz) {
+        GLB_CUDA(cudaMemcpyAsync(h_col.data(), p->d_col, sizeof(int) * (size_t)nnz, cudaMemcpyDeviceToHost, st));
+        GLB_CUDA(cudaMemcpyAsync(h_val.data(), p->d_val, sizeof(float) * (size_t)nnz, cudaMemcpyDeviceToHost, st));
+        GLB_CUDA(cudaStreamSynchronize(st));
+    }
+    if (!pattern_symmetric(h_rp, h_col, n)) return 0;
+
+    std::vector<int> bounds;
+    balanced_bounds(h_rp, n, grid, 2.0, bounds);
+    std::vector<int2> slab, slots;
+    std::vector<long long> slab_off((size_t)grid + 1, 0);
+    std::vector<int> slot_off((size_t)grid + 1, 0), slot_rows, order;
+    slab.reserve((size_t)nnz + (size_t)nnz / 8 + 1024);
+    int cap_entries = 0, cap_slots = 0;
+    for (int b = 0; b < grid; ++b) {
+        const int r0 = bounds[b], r1 = bounds[b + 1];
+        order.resize((size_t)(r1 - r0));
+        for (int i = 0; i < r1 - r0; ++i) order[i] = r0 + i;
+        std::stable_sort(order.begin(), order.end(), [&](int a, int c2) {
+            return h_rp[a + 1] - h_rp[a] > h_rp[c2 + 1] - h_rp[c2];
+        });
+        const int nslots = (r1 - r0 + rpw - 1) / rpw;
+        const long long base0 = (long long)slab.size();
+        for (int s = 0; s < nslots; ++s) {
+            const int first = order[(size_t)s * rpw];
+            const int L = h_rp[first + 1] - h_rp[first];              // longest row of the slice comes first
+            slots.push_back(make_int2((int)((long long)slab.size() - base0), L));
+            for (int g = 0; g < rpw; ++g) {
+                const size_t k = (size_t)s * rpw + g;
+                slot_rows.push_back(k < order.size() ? order[k] : -1);
+            }
+            for (int j = 0; j < L; ++j)
+                for (int g = 0; g < rpw; ++g) {
+                    const size_t k = (size_t)s * rpw + g;
+                    int2 e = make_int2((int)kPadOff, 0);
+                    if (k < order.size()) {
+                        const int r = order[k];
+                        if (j < h_rp[r + 1] - h_rp[r]) {
+                            const int q = h_rp[r] + j;
+                            e = make_int2((int)((unsigned)h_col[q] * (unsigned)rowb), float_bits(h_val[q]));
+                        }
+                    }
+                    slab.push_back(e);
+                }
+        }
+        slab_off[b + 1] = (long long)slab.size();
+        slot_off[b + 1] = (int)slots.size();
+        cap_entries = std::max(cap_entries, (int)(slab_off[b + 1] - slab_off[b]));
+        cap_slots = std::max(cap_slots, nslots);
+    }
+    cap_entries = (cap_entries + 1) & ~1;
+    const size_t smem = (size_t)cap_entries * 8 + (size_t)cap_slots * 8 + (size_t)cap_slots * rpw * 4;
+    if (smem > (size_t)max_smem) return 0;
+    int threads = 0;
+    const void *fn = pick_dataflow(lanes, &threads);
+    GLB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    GLB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, threads, smem));
+    if (per_sm < 1 || grid > per_sm * sms) return 0;
+
+    const size_t nslab = slab.size() ? slab.size() : 1, nsl = slots.size() ? slots.size() : 1;
+    GLB_CUDA(cudaMalloc(&p->d_slabs, sizeof(int2) * nslab));
+    GLB_CUDA(cudaMalloc(&p->d_slots, sizeof(int2) * nsl));
+    GLB_CUDA(cudaMalloc(&p->d_slab_off, sizeof(long long) * (grid + 1)));
+    GLB_CUDA(cudaMalloc(&p->d_slot_off, sizeof(int) * (grid + 1)));
+    GLB_CUDA(cudaMalloc(&p->d_slot_rows, sizeof(int) * nsl * rpw));
+    GLB_CUDA(cudaMemcpyAsync(p->d_slabs, slab.data(), sizeof(int2) * slab.size(), cudaMemcpyHostToDevice, st));
+    GLB_CUDA(cudaMemcpyAsync(p->d_slots, slots.data(), sizeof(int2) * slots.size(), cudaMemcpyHostToDevice, st));
+    GLB_CUDA(cudaMemcpyAsync(p->d_slab_off, slab_off.data(), sizeof(long long) * (grid + 1), cudaMemcpyHostToDevice, st));
+    GLB_CUDA(cudaMemcpyAsync(p->d_slot_off, slot_off.data(), sizeof(int) * (grid + 1), cudaMemcpyHostToDevice, st));
+    GLB_CUDA(cudaMemcpyAsync(p->d_slot_rows, slot_rows.data(), sizeof(int) * slot_rows.size(), cudaMemcpyHostToDevice, st));
+    GLB_CUDA(cudaStreamSynchronize(st));            // the staging vectors are locals
+    p->kind = GLB_POISSON_KIND_DATAFLOW;
+    p->ldu = lanes * 4;
+    p->grid = grid; p->threads = threads; p->fn = fn; p->smem_bytes = smem;
+    p->cap_entries = cap_entries; p->cap_slots = cap_slots;
+    p->ell_fill = slab.size() ? (double)nnz / (double)slab.size() : 1.0;
+    if (getenv("GLB_POISSON_STATS")) {
+        GLB_CUDA(cudaMalloc(&p->d_stats, 4 * sizeof(unsigned long long)));
+    }
+    return 0;
+}
+
+static int plan_try_barrier(glb_poisson_plan *p, const std::vector<int> &h_rp, int sms, int max_smem, cudaStream_t st)
+{
+    const int64_t n = p->n, nnz = p->nnz;
+    const int ldu = glb_padded_ld(p->c);
     // Upper bound for a graph that could fit the shared-memory slabs at all (8 bytes per nonzero per CTA).
-    if (!coop || (double)nnz * 8.0 / sms > (double)max_smem) return 0;
+    if ((double)nnz * 8.0 / sms > (double)max_smem) return 0;
     int grid = (int)((n + 127) / 128);          // tiny graphs: at least ~128 rows per CTA
     if (grid > sms) grid = sms;
     if (grid < 1) grid = 1;
-
-    // work-balanced contiguous row partition from the host copy of rowptr: cost(row) = nnz(row) + 4
-    std::vector<int> h_rp((size_t)n + 1);
-    GLB_CUDA(cudaMemcpyAsync(h_rp.data(), d_rowptr, sizeof(int) * (size_t)(n + 1), cudaMemcpyDeviceToHost, st));
-    GLB_CUDA(cudaStreamSynchronize(st));
-    std::vector<int> bounds((size_t)grid + 1, 0);
-    const double total = (double)h_rp[n] + 4.0 * (double)n;
-    {
-        int b = 1;
-        for (int64_t i = 0; i < n && b < grid; ++i) {
-            const double pref = (double)h_rp[i + 1] + 4.0 * (double)(i + 1);
-            while (b < grid && pref >= total * b / grid) bounds[b++] = (int)(i + 1);
-        }
-        for (; b <= grid; ++b) bounds[b] = (int)n;
-        bounds[grid] = (int)n;
-    }
+    std::vector<int> bounds;
+    balanced_bounds(h_rp, n, grid, 4.0, bounds);
     int cap = 0, max_rows = 0;
     for (int b = 0; b < grid; ++b) {
         cap = std::max(cap, h_rp[bounds[b + 1]] - h_rp[bounds[b]]);
@@ -490,7 +808,7 @@ extern "C" GLB_API int glb_poisson_plan_create(glb_poisson_plan **plan, const in
     const size_t smem = (size_t)cap * 8 + (size_t)(2 * max_rows + 2) * 4 + (size_t)((max_rows + 15) & ~15) + 16;
     if (smem > (size_t)max_smem) return 0;
     int threads = 0;
-    const void *fn = pick_persistent(ldu, &threads);
+    const void *fn = pick_barrier(ldu, &threads);
     GLB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     GLB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, threads, smem));
@@ -499,37 +817,188 @@ extern "C" GLB_API int glb_poisson_plan_create(glb_poisson_plan **plan, const in
     GLB_CUDA(cudaMalloc(&p->d_cta_rows, sizeof(int) * (grid + 1)));
     GLB_CUDA(cudaMemcpyAsync(p->d_cta_rows, bounds.data(), sizeof(int) * (grid + 1), cudaMemcpyHostToDevice, st));
     GLB_CUDA(cudaStreamSynchronize(st));        // bounds is a local
-    p->persistent = 1;
+    p->kind = GLB_POISSON_KIND_BARRIER;
+    p->ldu = ldu;
     p->grid = grid; p->max_rows = max_rows; p->slab_cap = cap; p->smem_bytes = smem;
     p->threads = threads; p->fn = fn;
+    return 0;
+}
+
+// device time of a short trial run of the plan's kernel on an all-zero problem (second of two launches)
+static int plan_time(glb_poisson_plan *p, float *ms, cudaStream_t st)
+{
+    const int T = 32;
+    const size_t bytes = (size_t)p->n * p->ldu * sizeof(float);
+    float *buf = nullptr;
+    GLB_CUDA(cudaMalloc(&buf, 3 * bytes));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    int rc = 0;
+    cudaError_t ce = cudaMemsetAsync(buf, 0, 3 * bytes, st);
+    for (int rep = 0; rep < 2 && rc == 0 && ce == cudaSuccess; ++rep) {
+        cudaEventRecord(e0, st);
+        rc = glb_poisson_iterate(p, buf, buf + (size_t)p->n * p->ldu, buf + 2 * (size_t)p->n * p->ldu, T, nullptr, nullptr, st);
+        cudaEventRecord(e1, st);
+    }
+    if (ce == cudaSuccess) ce = cudaEventSynchronize(e1);
+    if (ce == cudaSuccess && rc == 0) cudaEventElapsedTime(ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(buf);
+    if (rc == 0 && ce != cudaSuccess) { set_error("plan_time: %s", cudaGetErrorString(ce)); rc = (int)ce; }
+    return rc;
+}
+
+extern "C" GLB_API int glb_poisson_plan_create(glb_poisson_plan **plan, const int32_t *d_rowptr, const int32_t *d_col,
+                                               const float *d_val, int64_t n, int64_t nnz, int c, int kind, void *stream)
+{
+    GLB_CHECK_ARG(plan && d_rowptr && (nnz == 0 || (d_col && d_val)), "null pointer");
+    GLB_CHECK_ARG(n > 0 && n < (1ll << 31) && nnz >= 0 && nnz < (1ll << 31), "size out of range");
+    GLB_CHECK_ARG(c > 0, "c must be positive");
+    GLB_CHECK_ARG(kind >= GLB_POISSON_KIND_AUTO && kind <= GLB_POISSON_KIND_DATAFLOW, "unknown kernel kind");
+    GLB_CHECK_ARG((double)n * glb_padded_ld(c) * 4.0 < 4294967296.0, "label matrix larger than 4 GiB: 32-bit row offsets overflow");
+    cudaStream_t st = (cudaStream_t)stream;
+    glb_poisson_plan *p = new glb_poisson_plan();
+    p->n = n; p->nnz = nnz; p->c = c; p->ldu = glb_padded_ld(c);
+    p->d_rowptr = d_rowptr; p->d_col = d_col; p->d_val = d_val;
+    struct Guard { glb_poisson_plan *p; ~Guard() { if (p) glb_poisson_plan_destroy(p); } } guard{p};
+
+    const char *env_kind = getenv("GLB_POISSON_KIND");          // experiments / tests: overrides AUTO only
+    if (kind == GLB_POISSON_KIND_AUTO && env_kind) {
+        const int k = atoi(env_kind);
+        if (k >= GLB_POISSON_KIND_STEP && k <= GLB_POISSON_KIND_DATAFLOW) kind = k;
+    }
+    int dev = 0, coop = 0, max_smem = 0;
+    GLB_CUDA(cudaGetDevice(&dev));
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+    cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    const int sms = sm_count();
+    if (kind != GLB_POISSON_KIND_STEP && coop) {
+        std::vector<int> h_rp((size_t)n + 1);
+        GLB_CUDA(cudaMemcpyAsync(h_rp.data(), d_rowptr, sizeof(int) * (size_t)(n + 1), cudaMemcpyDeviceToHost, st));
+        GLB_CUDA(cudaStreamSynchronize(st));
+        GLB_CHECK_ARG(h_rp[0] == 0 && h_rp[n] == nnz, "rowptr does not match nnz");
+        int rc = 0;
+        if (kind == GLB_POISSON_KIND_AUTO || kind == GLB_POISSON_KIND_DATAFLOW)
+            if ((rc = plan_try_dataflow(p, h_rp, sms, max_smem, st))) return rc;
+        if (p->kind == GLB_POISSON_KIND_STEP && (kind == GLB_POISSON_KIND_AUTO || kind == GLB_POISSON_KIND_BARRIER))
+            if ((rc = plan_try_barrier(p, h_rp, sms, max_smem, st))) return rc;
+        if (kind == GLB_POISSON_KIND_AUTO && p->kind == GLB_POISSON_KIND_DATAFLOW && !getenv("GLB_POISSON_NOTUNE")) {
+            // Measure, don't guess: the dataflow kernel wins when every SM has enough rows to keep its producers
+            // ahead of its consumers, the barrier kernel on small or oddly shaped graphs.  Time both on zeros.
+            glb_poisson_plan *alt = nullptr;
+            rc = glb_poisson_plan_create(&alt, d_rowptr, d_col, d_val, n, nnz, c, GLB_POISSON_KIND_BARRIER, stream);
+            if (rc == 0) {
+                float ms_df = 0.f, ms_bar = 0.f;
+                rc = plan_time(p, &ms_df, st);
+                if (rc == 0) rc = plan_time(alt, &ms_bar, st);
+                if (rc) { glb_poisson_plan_destroy(alt); return rc; }
+                if (ms_bar < ms_df) {              // keep the barrier plan: swap contents, destroy the dataflow one
+                    std::swap(*p, *alt);
+                }
+                p->tuned_ms[0] = ms_df; p->tuned_ms[1] = ms_bar;
+                glb_poisson_plan_destroy(alt);
+            } else if (rc != GLB_E_UNSUPPORTED) {
+                return rc;
+            }
+        }
+    }
+    if (kind != GLB_POISSON_KIND_AUTO && p->kind != kind) {
+        set_error("glb_poisson_plan_create: kernel kind %d is not applicable to this graph", kind);
+        return GLB_E_UNSUPPORTED;
+    }
+    guard.p = nullptr;
+    *plan = p;
     return 0;
 }
 
 extern "C" GLB_API int glb_poisson_plan_destroy(glb_poisson_plan *plan)
 {
     if (!plan) return 0;
-    if (plan->d_counter) cudaFree(plan->d_counter);
-    if (plan->d_cta_rows) cudaFree(plan->d_cta_rows);
+    cudaFree(plan->d_counter);  cudaFree(plan->d_cta_rows);
+    cudaFree(plan->d_slabs);    cudaFree(plan->d_slots);
+    cudaFree(plan->d_slab_off); cudaFree(plan->d_slot_off); cudaFree(plan->d_slot_rows); cudaFree(plan->d_stats);
     delete plan;
     return 0;
 }
 
-extern "C" GLB_API int glb_poisson_plan_is_persistent(const glb_poisson_plan *plan) { return plan ? plan->persistent : 0; }
+extern "C" GLB_API int glb_poisson_plan_kind(const glb_poisson_plan *plan) { return plan ? plan->kind : GLB_E_INVALID; }
+extern "C" GLB_API int glb_poisson_plan_ld(const glb_poisson_plan *plan) { return plan ? plan->ldu : GLB_E_INVALID; }
+extern "C" GLB_API double glb_poisson_plan_fill(const glb_poisson_plan *plan) { return plan ? plan->ell_fill : 0.0; }
 
-extern "C" GLB_API int glb_poisson_iterate(glb_poisson_plan *plan, const int32_t *d_rowptr, const int32_t *d_col,
-                                   const float *d_val, const float *d_Db, float *d_u0, float *d_u1, int T,
-                                   int *result_in_u1, int *launches, void *stream)
+extern "C" GLB_API int glb_poisson_pack(const glb_poisson_plan *plan, const double *d_src, const double *d_deg,
+                                        const int32_t *d_perm, float *d_dst, void *stream)
 {
-    GLB_CHECK_ARG(plan && d_rowptr && d_col && d_val && d_Db && d_u0 && d_u1, "null pointer");
+    GLB_CHECK_ARG(plan && d_src && d_dst, "null pointer");
+    const int blocks = stream_blocks_p(plan->n * plan->ldu);
+    if (plan->kind == GLB_POISSON_KIND_DATAFLOW)
+        pack_kernel<true><<<blocks, 256, 0, (cudaStream_t)stream>>>(d_src, d_deg, plan->n, plan->c, d_dst, plan->ldu, d_perm);
+    else
+        pack_kernel<false><<<blocks, 256, 0, (cudaStream_t)stream>>>(d_src, d_deg, plan->n, plan->c, d_dst, plan->ldu, d_perm);
+    GLB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" GLB_API int glb_poisson_unpack(const glb_poisson_plan *plan, const float *d_src, const int32_t *d_perm,
+                                          double *d_dst, void *stream)
+{
+    GLB_CHECK_ARG(plan && d_src && d_dst, "null pointer");
+    const int blocks = stream_blocks_p(plan->n * plan->c);
+    if (plan->kind == GLB_POISSON_KIND_DATAFLOW)
+        unpack_kernel<true><<<blocks, 256, 0, (cudaStream_t)stream>>>(d_src, plan->n, plan->c, plan->ldu, d_dst, d_perm);
+    else
+        unpack_kernel<false><<<blocks, 256, 0, (cudaStream_t)stream>>>(d_src, plan->n, plan->c, plan->ldu, d_dst, d_perm);
+    GLB_LAUNCH_CHECK();
+    return 0;
+}
+
+static int plan_step(const glb_poisson_plan *p, const float *Db, const float *u_in, float *u_out, cudaStream_t st)
+{
+    if (p->kind == GLB_POISSON_KIND_DATAFLOW)
+        return dispatch_step<true>(p->d_rowptr, p->d_col, p->d_val, Db, u_in, u_out, p->n, p->ldu, st);
+    return dispatch_step<false>(p->d_rowptr, p->d_col, p->d_val, Db, u_in, u_out, p->n, p->ldu, st);
+}
+
+extern "C" GLB_API int glb_poisson_step(const glb_poisson_plan *plan, const float *d_Db, const float *d_u_in,
+                                        float *d_u_out, void *stream)
+{
+    GLB_CHECK_ARG(plan && d_Db && d_u_in && d_u_out, "null pointer");
+    GLB_CHECK_ARG(d_u_in != d_u_out, "u_in and u_out must differ");
+    plan_step(plan, d_Db, d_u_in, d_u_out, (cudaStream_t)stream);
+    GLB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" GLB_API int glb_poisson_iterate(glb_poisson_plan *plan, const float *d_Db, float *d_u0, float *d_u1, int T,
+                                           int *result_in_u1, int *launches, void *stream)
+{
+    GLB_CHECK_ARG(plan && d_Db && d_u0 && d_u1, "null pointer");
     GLB_CHECK_ARG(T >= 0, "T must be >= 0");
     GLB_CHECK_ARG(d_u0 != d_u1, "u0 and u1 must differ");
     cudaStream_t st = (cudaStream_t)stream;
     if (result_in_u1) *result_in_u1 = T & 1;
     if (T == 0) return 0;
-    if (plan->persistent) {
+    const int *rp = plan->d_rowptr, *col = plan->d_col;
+    const float *val = plan->d_val;
+    if (plan->kind == GLB_POISSON_KIND_DATAFLOW) {
+        int nopoll = getenv("GLB_POISSON_NOPOLL") ? atoi(getenv("GLB_POISSON_NOPOLL")) : 0;     // experiment only: ignores the epoch words (results are wrong)
+        stamp_kernel<<<stream_blocks_p(plan->n * (plan->ldu / 4)), 256, 0, st>>>(d_u0, d_u1, plan->n * (plan->ldu / 4));
+        void *args[] = {(void *)&plan->d_slabs, (void *)&plan->d_slab_off, (void *)&plan->d_slots, (void *)&plan->d_slot_off,
+                        (void *)&plan->d_slot_rows, (void *)&d_Db, (void *)&d_u0, (void *)&d_u1, (void *)&T,
+                        (void *)&plan->cap_entries, (void *)&plan->cap_slots, (void *)&plan->d_stats, (void *)&nopoll};
+        if (plan->d_stats) GLB_CUDA(cudaMemsetAsync(plan->d_stats, 0, 4 * sizeof(unsigned long long), st));
+        GLB_CUDA(cudaLaunchCooperativeKernel(plan->fn, dim3(plan->grid), dim3(plan->threads), args, plan->smem_bytes, st));
+        if (plan->d_stats) {
+            unsigned long long h[4];
+            GLB_CUDA(cudaMemcpyAsync(h, plan->d_stats, sizeof(h), cudaMemcpyDeviceToHost, st));
+            GLB_CUDA(cudaStreamSynchronize(st));
+            fprintf(stderr, "[glb] dataflow T=%d grid=%d: re-polls %llu (%.2f per nonzero-lane), polling batches %llu, max warp cycles/iter %.0f\n",
+                    T, plan->grid, h[0], (double)h[0] / ((double)plan->nnz * (plan->ldu / 4) * T + 1), h[1], (double)h[2] / T);
+        }
+        if (launches) *launches += 2;
+    } else if (plan->kind == GLB_POISSON_KIND_BARRIER) {
         GLB_CUDA(cudaMemsetAsync(plan->d_counter, 0, sizeof(unsigned) * kFlagStride * plan->grid, st));
         int n = (int)plan->n, ldu = plan->ldu, max_rows = plan->max_rows, cap = plan->slab_cap;
-        void *args[] = {(void *)&d_rowptr, (void *)&d_col, (void *)&d_val, (void *)&d_Db, (void *)&d_u0, (void *)&d_u1,
+        void *args[] = {(void *)&rp, (void *)&col, (void *)&val, (void *)&d_Db, (void *)&d_u0, (void *)&d_u1,
                         (void *)&n, (void *)&ldu, (void *)&T, (void *)&plan->d_cta_rows, (void *)&max_rows, (void *)&cap,
                         (void *)&plan->d_counter};
         GLB_CUDA(cudaLaunchCooperativeKernel(plan->fn, dim3(plan->grid), dim3(plan->threads), args,
@@ -539,7 +1008,7 @@ extern "C" GLB_API int glb_poisson_iterate(glb_poisson_plan *plan, const int32_t
         for (int t = 0; t < T; ++t) {
             const float *in = (t & 1) ? d_u1 : d_u0;
             float *out = (t & 1) ? d_u0 : d_u1;
-            dispatch_step(d_rowptr, d_col, d_val, d_Db, in, out, plan->n, plan->ldu, st);
+            plan_step(plan, d_Db, in, out, st);
         }
         GLB_LAUNCH_CHECK();
         if (launches) *launches += T;

@@ -75,14 +75,18 @@ class PoissonOperator:
     """P = D^-1 W^T (fp32 CSR) and RW = W^T D^-1 (fp64 values on the same pattern), device resident.
     Setup lines of ssl.poisson._fit, reference graphlearning/ssl.py:615-617, 634-644."""
 
-    def __init__(self, W, reorder=False):
+    KINDS = {"auto": -1, "step": 0, "barrier": 1, "dataflow": 2}
+
+    def __init__(self, W, reorder=False, kind="auto"):
         """W: scipy CSR (host) or DeviceCSR.  reorder=True relabels the nodes with a locality ordering
         (reverse Cuthill-McKee from the host pattern) for the iterate; inputs/outputs keep the caller's
-        numbering.  Only possible when W arrives as a host matrix."""
+        numbering.  Only possible when W arrives as a host matrix.  kind: which iterate kernel the plans
+        of this operator use ("auto" picks dataflow -> barrier -> step, see include/glb200.h)."""
         torch = _torch()
         host_W = None if isinstance(W, DeviceCSR) else sparse.csr_matrix(W)
         self.W = W if isinstance(W, DeviceCSR) else DeviceCSR.from_scipy(host_W)
         self.n = self.W.n
+        self.kind_request = self.KINDS[kind] if isinstance(kind, str) else int(kind)
         self.deg = self.W.degree(skip_diagonal=True)
         Wt = self.W.transpose()
         self.rowptr, self.col, self.nnz = Wt.rowptr, Wt.col, Wt.nnz
@@ -109,6 +113,7 @@ class PoissonOperator:
                       ptr(self.perm), ptr(self._iperm), ptr(self.it_rowptr), ptr(self.it_col), ptr(self.it_val),
                       cur_stream())
         self._plans = {}
+        self._last_c = None
 
     def __del__(self):
         try:
@@ -117,55 +122,67 @@ class PoissonOperator:
         except Exception:
             pass
 
-    def plan(self, ldu):
-        if ldu not in self._plans:
+    def plan(self, c=None):
+        """The glb_poisson_plan for label matrices with c columns (built on first use)."""
+        c = int(self._last_c if c is None else c)
+        if c not in self._plans:
             h = ctypes.c_void_p()
-            _lib.call("glb_poisson_plan_create", ctypes.byref(h), ptr(self.it_rowptr), self.n, self.nnz, int(ldu),
-                      cur_stream())
-            self._plans[ldu] = h
-        return self._plans[ldu]
+            _lib.call("glb_poisson_plan_create", ctypes.byref(h), ptr(self.it_rowptr), ptr(self.it_col), ptr(self.it_val),
+                      self.n, self.nnz, c, self.kind_request, cur_stream())
+            self._plans[c] = h
+        self._last_c = c
+        return self._plans[c]
 
-    def is_persistent(self, ldu):
-        return bool(_lib.load().glb_poisson_plan_is_persistent(self.plan(ldu)))
+    def kind(self, c=None):
+        """'step' | 'barrier' | 'dataflow': the kernel the plan for width c runs."""
+        k = _lib.load().glb_poisson_plan_kind(self.plan(c))
+        return {v: n for n, v in self.KINDS.items()}[k]
 
-    def pack(self, X):
-        """host/device (n,c) float64 -> device (n,ldu) fp32, zero padded."""
+    def ld(self, c=None):
+        return int(_lib.load().glb_poisson_plan_ld(self.plan(c)))
+
+    def fill(self, c=None):
+        return float(_lib.load().glb_poisson_plan_fill(self.plan(c)))
+
+    def is_persistent(self, c=None):
+        return self.kind(c) != "step"
+
+    def pack(self, X, scale_by_degree=False):
+        """host/device (n,c) float64 -> device (n,ld) fp32 in the layout of the plan for width c."""
         torch = _torch()
         X = torch.as_tensor(X, dtype=torch.float64).to(self.deg.device).contiguous()
         n, c = X.shape
-        ldu = _lib.padded_ld(c)
-        out = torch.empty((n, ldu), dtype=torch.float32, device=X.device)
-        _lib.call("glb_pack_f64_to_f32", ptr(X), n, c, ptr(out), ldu, ptr(self.perm), cur_stream())
+        plan = self.plan(c)
+        out = torch.empty((n, self.ld(c)), dtype=torch.float32, device=X.device)
+        _lib.call("glb_poisson_pack", plan, ptr(X), ptr(self.deg) if scale_by_degree else None, ptr(self.perm), ptr(out),
+                  cur_stream())
         return out
 
-    def unpack(self, U, c):
+    def unpack(self, U, c=None):
         torch = _torch()
-        n, ldu = U.shape
-        out = torch.empty((n, c), dtype=torch.float64, device=U.device)
-        _lib.call("glb_unpack_f32_to_f64", ptr(U), n, c, ldu, ptr(out), ptr(self.perm), cur_stream())
+        plan = self.plan(c)
+        c = self._last_c
+        out = torch.empty((U.shape[0], c), dtype=torch.float64, device=U.device)
+        _lib.call("glb_poisson_unpack", plan, ptr(U), ptr(self.perm), ptr(out), cur_stream())
         return out
 
     def source_to_Db(self, source):
-        """Db = D^-1 source (ssl.py:636) in the padded fp32 layout."""
-        torch = _torch()
-        src = torch.as_tensor(source, dtype=torch.float64).to(self.deg.device)
-        return self.pack((1.0 / self.deg)[:, None] * src)
+        """Db = D^-1 source (ssl.py:636) in the device layout."""
+        return self.pack(source, scale_by_degree=True)
 
-    def step(self, Db, u_in, u_out):
-        _lib.call("glb_poisson_step", ptr(self.it_rowptr), ptr(self.it_col), ptr(self.it_val), ptr(Db), ptr(u_in),
-                  ptr(u_out), self.n, int(Db.shape[1]), cur_stream())
+    def step(self, Db, u_in, u_out, c=None):
+        _lib.call("glb_poisson_step", self.plan(c), ptr(Db), ptr(u_in), ptr(u_out), cur_stream())
 
-    def iterate(self, Db, T, u0=None, u1=None):
+    def iterate(self, Db, T, u0=None, u1=None, c=None):
         """T iterations of u <- Db + P u from u0 (zeros by default).  Returns (u, launches)."""
         torch = _torch()
-        ldu = int(Db.shape[1])
         if u0 is None:
             u0 = torch.zeros_like(Db)
         if u1 is None:
             u1 = torch.zeros_like(Db)
         which, launches = ctypes.c_int(0), ctypes.c_int(0)
-        _lib.call("glb_poisson_iterate", self.plan(ldu), ptr(self.it_rowptr), ptr(self.it_col), ptr(self.it_val),
-                  ptr(Db), ptr(u0), ptr(u1), int(T), ctypes.byref(which), ctypes.byref(launches), cur_stream())
+        _lib.call("glb_poisson_iterate", self.plan(c), ptr(Db), ptr(u0), ptr(u1), int(T), ctypes.byref(which),
+                  ctypes.byref(launches), cur_stream())
         return (u1 if which.value else u0), launches.value
 
     def mixing_T(self, train_ind, min_iter, max_iter):

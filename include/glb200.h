@@ -14,8 +14,8 @@
  *  - `stream` is a cudaStream_t passed as void* (NULL = default stream).  Device entry points are
  *    stream-ordered and do not synchronise unless stated.
  *  - CSR matrices: int32 rowptr[n+1], int32 col[nnz], values fp32 (iterate) or fp64 (setup).
- *  - dense label matrices on the device are row-major n x ldu fp32 with ldu >= c, ldu a power of two
- *    in {4,8,...,128} or a multiple of 128 (glb_padded_ld(c) gives it); padding columns are zero.
+ *  - dense label matrices on the device are row-major n x ld fp32 in the layout of the glb_poisson_plan
+ *    they are used with (glb_poisson_plan_ld; see the Poisson section).
  */
 #ifndef GLB200_H
 #define GLB200_H
@@ -40,7 +40,7 @@ GLB_API int glb_version(void);
 GLB_API const char *glb_last_error(void);
 /* Number of SMs etc. of the current device; fails with GLB_E_NOGPU when there is none. */
 GLB_API int glb_device_info(int *sm_count, int *cc_major, int *cc_minor, int64_t *hbm_bytes);
-/* Leading dimension used for an n x c dense label matrix. */
+/* Leading dimension of the plain layout of an n x c label matrix: power of two in {4..128} or a multiple of 128. */
 GLB_API int glb_padded_ld(int c);
 
 /* ---------------------------------------------------------------------------------------------
@@ -67,13 +67,6 @@ GLB_API int glb_csr_transpose(const int32_t *d_rowptr, const int32_t *d_col, con
 GLB_API int glb_poisson_scale(const int32_t *d_t_rowptr, const int32_t *d_t_col, const double *d_t_val, const double *d_deg,
                       int64_t n, float *d_P_val, double *d_RW_val, void *stream);
 
-/* dst (n x ldu fp32, padded with zeros) <- src (n x c fp64), and back.  labels <-> device layout.
- * d_perm (may be NULL) is a locality ordering: device row r holds the caller's row d_perm[r]. */
-GLB_API int glb_pack_f64_to_f32(const double *d_src, int64_t n, int c, float *d_dst, int ldu, const int32_t *d_perm,
-                                void *stream);
-GLB_API int glb_unpack_f32_to_f64(const float *d_src, int64_t n, int c, int ldu, double *d_dst, const int32_t *d_perm,
-                                  void *stream);
-
 /* Locality ordering (no counterpart in the reference: scipy's single-core SpMM does not care about node
  * numbering).  Reverse Cuthill-McKee on the HOST from the CSR pattern the caller holds there; integers only.
  * h_perm[new] = old.  glb_csr_permute relabels an fp32 CSR matrix on the device: B = Pi A Pi^T. */
@@ -85,26 +78,52 @@ GLB_API int glb_csr_permute(const int32_t *d_rowptr, const int32_t *d_col, const
 /* ---------------------------------------------------------------------------------------------
  * Poisson iterate  u <- Db + P u.   Replaces the loop body graphlearning/ssl.py:668 (CPU: scipy
  * csr_matvecs) and :658 (torch.sparse.addmm).
+ *
+ * A plan binds the CSR matrix P (device arrays owned by the caller, which must outlive the plan) and the
+ * number of label columns c to one of three kernels:
+ *   GLB_POISSON_KIND_DATAFLOW  all T iterations in ONE persistent launch without any grid barrier: every
+ *                              16-byte chunk of a label row carries the iteration that produced it, so the
+ *                              gathers themselves synchronise.  Needs a structurally symmetric pattern,
+ *                              c <= 96 and a graph whose per-SM slab fits shared memory.
+ *   GLB_POISSON_KIND_BARRIER   all T iterations in one cooperative launch with a grid barrier per iteration
+ *                              (directed graphs).
+ *   GLB_POISSON_KIND_STEP      one launch per iteration (graphs too large for the shared-memory slabs).
+ * GLB_POISSON_KIND_AUTO picks the first applicable one in that order; asking for a specific kind that does
+ * not apply returns GLB_E_UNSUPPORTED.
+ *
+ * Device label matrices (Db, u) are row-major n x glb_poisson_plan_ld(plan) fp32 in the plan's layout: plain
+ * (columns 0..c-1, zero padded) or, for the dataflow kernel, chunks {x[3q], x[3q+1], x[3q+2], epoch}.
+ * glb_poisson_pack / glb_poisson_unpack convert from / to the reference's n x c float64 arrays.
  * ------------------------------------------------------------------------------------------- */
-/* One iteration per call (one kernel launch): d_u_out = d_Db + P * d_u_in.  u_in != u_out. */
-GLB_API int glb_poisson_step(const int32_t *d_rowptr, const int32_t *d_col, const float *d_val, const float *d_Db,
-                     const float *d_u_in, float *d_u_out, int64_t n, int ldu, void *stream);
-
-/* Plan for T iterations in ONE persistent cooperative launch (CSR slab + Db slab staged in shared
- * memory, hand-rolled grid barrier between iterations, u ping-pongs between d_u0 and d_u1).
- * The plan only records the row partition and launch geometry for (rowptr, n, ldu). */
+#define GLB_POISSON_KIND_AUTO     (-1)
+#define GLB_POISSON_KIND_STEP     0
+#define GLB_POISSON_KIND_BARRIER  1
+#define GLB_POISSON_KIND_DATAFLOW 2
 typedef struct glb_poisson_plan glb_poisson_plan;
-GLB_API int glb_poisson_plan_create(glb_poisson_plan **plan, const int32_t *d_rowptr, int64_t n, int64_t nnz, int ldu,
-                            void *stream);
+GLB_API int glb_poisson_plan_create(glb_poisson_plan **plan, const int32_t *d_rowptr, const int32_t *d_col,
+                                    const float *d_val, int64_t n, int64_t nnz, int c, int kind, void *stream);
 GLB_API int glb_poisson_plan_destroy(glb_poisson_plan *plan);
-/* 1 when the plan runs as a single persistent kernel, 0 when it falls back to one launch per iteration
- * (graph too large for the shared-memory slabs or the cooperative grid). */
-GLB_API int glb_poisson_plan_is_persistent(const glb_poisson_plan *plan);
-/* Runs T iterations starting from d_u0.  The result is in d_u0 when T is even, d_u1 when T is odd;
+GLB_API int glb_poisson_plan_kind(const glb_poisson_plan *plan);
+GLB_API int glb_poisson_plan_ld(const glb_poisson_plan *plan);
+/* nnz / stored entries of the dataflow kernel's sliced-ELL slabs (1.0 = no padding; 0 for other kinds) */
+GLB_API double glb_poisson_plan_fill(const glb_poisson_plan *plan);
+
+/* d_dst (n x ld fp32, plan layout) <- d_src (n x c fp64), each row divided by d_deg[row] when d_deg is not
+ * NULL (Db = D^-1 source, ssl.py:636).  d_perm (may be NULL) is a locality ordering: device row r holds the
+ * caller's row d_perm[r].  glb_poisson_unpack is the inverse (no scaling). */
+GLB_API int glb_poisson_pack(const glb_poisson_plan *plan, const double *d_src, const double *d_deg, const int32_t *d_perm,
+                             float *d_dst, void *stream);
+GLB_API int glb_poisson_unpack(const glb_poisson_plan *plan, const float *d_src, const int32_t *d_perm, double *d_dst,
+                               void *stream);
+
+/* One iteration, one kernel launch: d_u_out = d_Db + P * d_u_in (any plan kind).  u_in != u_out. */
+GLB_API int glb_poisson_step(const glb_poisson_plan *plan, const float *d_Db, const float *d_u_in, float *d_u_out,
+                             void *stream);
+
+/* T iterations starting from d_u0.  The result is in d_u0 when T is even, d_u1 when T is odd;
  * *result_in_u1 (host int, may be NULL) says which.  launches (host, may be NULL) += kernels launched. */
-GLB_API int glb_poisson_iterate(glb_poisson_plan *plan, const int32_t *d_rowptr, const int32_t *d_col, const float *d_val,
-                        const float *d_Db, float *d_u0, float *d_u1, int T, int *result_in_u1, int *launches,
-                        void *stream);
+GLB_API int glb_poisson_iterate(glb_poisson_plan *plan, const float *d_Db, float *d_u0, float *d_u1, int T,
+                                int *result_in_u1, int *launches, void *stream);
 
 /* Stopping rule of ssl.py:667,669: v <- RW v (fp64) from v0 = indicator(train)/m until
  * T >= min_iter and max|v - vinf| <= 1/n, or T == max_iter.  Synchronises the stream (T is a host

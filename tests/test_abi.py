@@ -46,11 +46,12 @@ def test_version_and_padding(lib):
 
 
 def test_argument_errors_are_reported_not_crashes(lib):
-    rc = lib.glb_poisson_step(None, None, None, None, None, None, 10, 16, None)
+    rc = lib.glb_poisson_step(None, None, None, None, None)
     assert rc == -1
     assert b"null pointer" in lib.glb_last_error()
     h = ctypes.c_void_p()
-    assert lib.glb_poisson_plan_create(ctypes.byref(h), None, 10, 10, 16, None) == -1
+    assert lib.glb_poisson_plan_create(ctypes.byref(h), None, None, None, 10, 10, 10, -1, None) == -1
+    assert lib.glb_poisson_plan_kind(None) < 0 and lib.glb_poisson_plan_ld(None) < 0
     assert lib.glb_csr_transpose_work_bytes(10, -5) < 0
 
 

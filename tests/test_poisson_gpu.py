@@ -147,50 +147,101 @@ def test_degree_transpose_scale_bit_exact(dev, blobs):
     assert np.allclose(RW.data, RWref.data, rtol=1e-15, atol=0)
 
 
-@pytest.mark.parametrize("c", [1, 2, 3, 4, 7, 10, 16, 17, 40, 100, 130])
-def test_step_and_persistent_kernels_every_width(dev, c):
-    """Both kernels against the plain-C fp64 oracle for every lane mapping (ldu = 4 ... 256)."""
+@pytest.mark.parametrize("kind", ["dataflow", "barrier", "step"])
+@pytest.mark.parametrize("c", [1, 2, 3, 4, 7, 10, 16, 17, 40, 96, 100, 130])
+def test_every_kernel_every_width(dev, c, kind):
+    """All three iterate kernels against the plain-C fp64 oracle for every lane mapping."""
     import torch
     W = random_knn_graph(2500, 9, seed=c)
-    op = dev.PoissonOperator(W)
+    if kind == "dataflow" and c > 96:
+        with pytest.raises(dev._lib.GlbError, match="not applicable"):
+            dev.PoissonOperator(W, kind=kind).plan(c)
+        return
+    op = dev.PoissonOperator(W, kind=kind)
     rng = np.random.default_rng(c)
     Db64 = rng.normal(size=(2500, c)) * (rng.random((2500, 1)) < 0.05)     # sparse-ish dense source
     s = orc.poisson_gd_setup(W, np.array([0]), np.array([0]))
     Db = op.pack(Db64)
-    assert Db.shape[1] == dev._lib.padded_ld(c)
+    assert op.kind(c) == kind
+    assert Db.shape[1] == op.ld(c) >= c
+    if kind != "dataflow":
+        assert op.ld(c) == dev._lib.padded_ld(c)
+    assert np.array_equal(op.unpack(Db, c).cpu().numpy(), Db64.astype(np.float32).astype(np.float64))   # pack/unpack round trip
     T = 25
     ref = c_oracle.poisson_iterate(s["P"], Db64, T)
-    # one launch per iteration
+    # one launch per iteration (the step kernel reads either layout)
     u_in = torch.zeros_like(Db); u_out = torch.zeros_like(Db)
     for _ in range(T):
         op.step(Db, u_in, u_out)
         u_in, u_out = u_out, u_in
     got_step = op.unpack(u_in, c).cpu().numpy()
     assert rel_err(got_step, ref) <= TOL
-    # planned iterate (persistent cooperative kernel when it fits)
+    # planned iterate
     u, launches = op.iterate(Db, T)
     got = op.unpack(u, c).cpu().numpy()
     assert rel_err(got, ref) <= TOL
-    if op.is_persistent(Db.shape[1]):
-        assert launches == 1
-        assert rel_err(got, got_step) <= 2e-6            # long rows are summed in a different (fixed) order
+    assert launches == {"dataflow": 2, "barrier": 1, "step": T}[kind]
+    if kind == "dataflow":
+        assert np.array_equal(got, got_step)             # same fp32 operations in the same order: bit-identical
+    else:
+        assert rel_err(got, got_step) <= 2e-6            # barrier kernel sums long rows in a different (fixed) order
     u_again, _ = op.iterate(Db, T)
     assert np.array_equal(op.unpack(u_again, c).cpu().numpy(), got)      # run-to-run deterministic
-    assert float(u[:, c:].abs().max()) == 0.0 if Db.shape[1] > c else True
 
 
-def test_iterate_T_zero_and_odd_even(dev):
+@pytest.mark.parametrize("kind", ["dataflow", "barrier", "step"])
+def test_iterate_T_zero_and_odd_even(dev, kind):
     import torch
     W = random_knn_graph(1000, 6, seed=5)
-    op = dev.PoissonOperator(W)
+    op = dev.PoissonOperator(W, kind=kind)
     Db = op.pack(np.random.default_rng(0).normal(size=(1000, 10)))
     u0, _ = op.iterate(Db, 0)
-    assert float(u0.abs().max()) == 0.0
+    assert float(op.unpack(u0, 10).abs().max()) == 0.0
     u3, _ = op.iterate(Db, 3)
     u4, _ = op.iterate(Db, 4)
-    a = torch.zeros_like(Db); b = torch.zeros_like(Db)
+    a = torch.zeros_like(Db)
     op.step(Db, u3, a)
-    assert torch.equal(a, u4)
+    assert torch.equal(op.unpack(a, 10), op.unpack(u4, 10))
+    # a warm start: T1 + T2 iterations in two calls == T1 + T2 in one
+    u7, _ = op.iterate(Db, 7)
+    u34, _ = op.iterate(Db, 3, u0=u4.clone())
+    assert torch.equal(op.unpack(u34, 10), op.unpack(u7, 10))
+
+
+def test_kernel_choice(dev):
+    """auto: symmetric pattern -> dataflow; directed -> barrier; explicit request that does not apply -> error."""
+    Ws = random_knn_graph(3000, 8, seed=2)
+    Wd = random_knn_graph(3000, 8, seed=2, symmetric=False)
+    assert dev.PoissonOperator(Ws).kind(10) in ("dataflow", "barrier")   # auto times both on a trial run
+    assert dev.PoissonOperator(Ws, kind="dataflow").kind(10) == "dataflow"
+    assert dev.PoissonOperator(Wd).kind(10) == "barrier"
+    assert dev.PoissonOperator(Ws).kind(200) == "barrier"         # too wide for the flagged layout
+    with pytest.raises(dev._lib.GlbError, match="not applicable"):
+        dev.PoissonOperator(Wd, kind="dataflow").plan(10)
+    op = dev.PoissonOperator(Ws, kind="dataflow")
+    assert 0.8 < op.fill(10) <= 1.0                               # sliced-ELL padding stays small
+
+
+def test_dataflow_ragged_rows(dev):
+    """Empty rows, one very long row (hub), rows shorter than the unroll: the sliced-ELL slabs stay exact."""
+    rng = np.random.default_rng(7)
+    n = 1500
+    W = random_knn_graph(n, 3, seed=9).tolil()
+    W[5, :] = 0; W[:, 5] = 0                                      # isolated node
+    hub = rng.choice(n, 400, replace=False)
+    hub = hub[(hub != 11) & (hub != 5)]
+    W[11, hub] = 0.5; W[hub, 11] = 0.5                            # one row with ~400 nonzeros
+    W = sparse.csr_matrix(W); W.eliminate_zeros()
+    op = dev.PoissonOperator(W, kind="dataflow")
+    # the operator's own fp32 P (row 5 and column 5 are empty, so the zero degree injects nothing)
+    P = sparse.csr_matrix((op.P_val.cpu().numpy()[:op.nnz].astype(np.float64), op.col.cpu().numpy(),
+                           op.rowptr.cpu().numpy()), shape=(n, n))
+    assert np.isfinite(P.data).all() and np.diff(P.indptr).max() > 300 and np.diff(P.indptr).min() == 0
+    Db64 = rng.normal(size=(n, 5))
+    ref = c_oracle.poisson_iterate(P, Db64, 12)
+    Db = op.pack(Db64)
+    got = op.unpack(op.iterate(Db, 12)[0], 5).cpu().numpy()
+    assert rel_err(got, ref) <= TOL
 
 
 def test_mixing_T_matches_reference_rule(dev, blobs, moons):
@@ -215,37 +266,37 @@ def big():
 def test_full_size_against_c_oracle(dev, big):
     W, labels, ti = big
     s = orc.poisson_gd_setup(W, ti, labels[ti])
-    op = dev.PoissonOperator(W)
-    assert op.is_persistent(16)
-    Db = op.source_to_Db(orc.poisson_source(70000, ti, labels[ti])[0])
-    T = 60
-    ref = c_oracle.poisson_iterate(s["P"], s["Db"], T)
-    u, launches = op.iterate(Db, T)
-    assert launches == 1
-    assert rel_err(op.unpack(u, 10).cpu().numpy(), ref) <= TOL
+    ref = c_oracle.poisson_iterate(s["P"], s["Db"], 60)
+    for kind, nl in (("dataflow", 2), ("barrier", 1)):
+        op = dev.PoissonOperator(W, kind=kind)
+        Db = op.source_to_Db(orc.poisson_source(70000, ti, labels[ti])[0])
+        assert op.kind(10) == kind
+        u, launches = op.iterate(Db, 60)
+        assert launches == nl
+        assert rel_err(op.unpack(u, 10).cpu().numpy(), ref) <= TOL
 
 
 def test_full_size_properties(dev, big):
     """Size-independent properties: linearity in the source, zero class-sum invariant, step/persistent equality."""
     import torch
     W, labels, ti = big
-    op = dev.PoissonOperator(W)
+    op = dev.PoissonOperator(W, kind="dataflow")
     rng = np.random.default_rng(2)
     A = op.pack(rng.normal(size=(70000, 10))); B = op.pack(rng.normal(size=(70000, 10)))
     T = 30
-    uA = op.iterate(A, T)[0].clone(); uB = op.iterate(B, T)[0].clone()
-    uAB = op.iterate(A * 2 - B, T)[0]
+    assert op.kind(10) == "dataflow"
+    uA = op.unpack(op.iterate(A, T)[0], 10); uB = op.unpack(op.iterate(B, T)[0], 10)
+    uAB = op.unpack(op.iterate(A * 2 - B, T)[0], 10)
     lin = 2 * uA - uB
     assert float((uAB - lin).abs().max() / lin.abs().max()) <= 2e-5
     src = orc.poisson_source(70000, ti, labels[ti])[0]
-    u = op.iterate(op.source_to_Db(src), 100)[0]
-    rowsum = u[:, :10].double().sum(1).abs().max()
+    u = op.unpack(op.iterate(op.source_to_Db(src), 1000)[0], 10)
+    rowsum = u.sum(1).abs().max()
     assert float(rowsum) <= 1e-5 * float(u.abs().max())          # columns of the source sum to zero per row
     a = torch.zeros_like(A); b = torch.zeros_like(A)
     for _ in range(T):
         op.step(A, a, b); a, b = b, a
-    # same kernel arithmetic except for rows split over a warp (different, fixed, summation order)
-    assert float((a - uA).abs().max() / uA.abs().max()) <= 2e-6
+    assert torch.equal(op.unpack(a, 10), uA)                     # dataflow kernel == T single steps, bit for bit
 
 
 def test_full_size_through_host_api(gl, big):
