@@ -149,7 +149,98 @@ class poisson(ssl):
             self.iterations = T
             self.gpu_launches = nl
             return u
-        raise NotImplementedError("poisson solver %r is not built on the B200 backend yet" % self.solver)
+        if self.solver == "conjugate_gradient":
+            # ssl.py:624-629: u = D^-1/2 conjgrad(L_normalized, D^-1/2 source, tol)
+            if source.shape[1] != k:
+                raise ValueError("train_labels must be 0..k-1")
+            W0 = sparse.csr_matrix(W - sparse.spdiags(W.diagonal(), 0, n, n))          # :615-616
+            G = graph.graph(W0)
+            L = G.laplacian(normalization="normalized")
+            D = G.degree_matrix(p=-0.5)
+            v, (it, err, nl) = utils.conjgrad(L, D * source, tol=self.tol, return_info=True)
+            self.iterations = it
+            self.gpu_launches = nl
+            return D * v
+        raise NotImplementedError("poisson solver %r (needs graph.eigen_decomp) is not built on the B200 backend yet"
+                                  % self.solver)
+
+
+class laplace(ssl):
+    """Laplace learning (label propagation).  Reference graphlearning/ssl.py:1106-1261.
+
+    Solves tau u + L u = 0 on the unlabelled nodes with the labels as Dirichlet data: the Jacobi-scaled
+    sub-system M A M v = M b is assembled with the same scipy expressions as the reference (ssl.py:1222-1246)
+    and solved by the multi-column CG on the GPU (cg.cu).  reweighting other than 'none' needs
+    graph.reweight, which is outside the hot path and not built.
+    """
+
+    def __init__(self, W=None, class_priors=None, X=None, reweighting="none", normalization="combinatorial", tau=0,
+                 order=1, mean_shift=False, tol=1e-5, alpha=2, zeta=1e7, r=0.1):
+        super().__init__(W, class_priors)
+        if reweighting != "none":
+            raise NotImplementedError("laplace(reweighting=%r) needs graph.reweight, outside the B200 hot path"
+                                      % reweighting)
+        self.reweighting = reweighting
+        self.normalization = normalization
+        self.mean_shift = mean_shift
+        self.tol = tol
+        self.order = order
+        self.X = X
+        if type(tau) in [float, int]:
+            self.tau = np.ones(self.graph.num_nodes) * tau
+        elif type(tau) is np.ndarray:
+            self.tau = tau
+        else:
+            raise ValueError("tau must be a number or a numpy array")
+        self.iterations = None
+        self.gpu_launches = 0
+        fname = "_laplace"
+        self.name = "Laplace Learning"
+        if self.normalization != "combinatorial":
+            fname += "_" + self.normalization
+            self.name += " " + self.normalization
+        if self.mean_shift:
+            fname += "_meanshift"
+            self.name += " with meanshift"
+        if self.order > 1:
+            fname += "_order%d" % int(self.order)
+            self.name += " order %d" % int(self.order)
+        if np.max(self.tau) > 0:
+            fname += "_tau_%.3f" % np.max(self.tau)
+            self.name += " tau=%.3f" % np.max(self.tau)
+        self.accuracy_filename = fname
+
+    def system(self, train_ind, train_labels):
+        """(M A M, M b, M, idx, F): the linear system of ssl.py:1217-1246."""
+        G = self.graph
+        n = G.num_nodes
+        k = len(np.unique(train_labels))
+        L = sparse.spdiags(self.tau, 0, n, n) + G.laplacian(normalization=self.normalization)
+        Lp = L
+        for _ in range(1, int(self.order)):
+            Lp = L * Lp
+        L = sparse.csr_matrix(Lp)
+        F = utils.labels_to_onehot(train_labels, k)
+        idx = np.full((n,), True, dtype=bool)
+        idx[train_ind] = False
+        b = (-L[:, train_ind] * F)[idx, :]
+        A = L[idx, :][:, idx]
+        m = A.shape[0]
+        M = sparse.spdiags(1 / np.sqrt(A.diagonal() + 1e-10), 0, m, m).tocsr()
+        return sparse.csr_matrix(M * A * M), M * b, M, idx, F
+
+    def _fit(self, train_ind, train_labels, all_labels=None):
+        n = self.graph.num_nodes
+        MAM, Mb, M, idx, F = self.system(train_ind, train_labels)
+        v, (it, err, nl) = utils.conjgrad(MAM, Mb, tol=self.tol, return_info=True)
+        self.iterations = it
+        self.gpu_launches = nl
+        u = np.zeros((n, F.shape[1]))
+        u[idx, :] = M * v
+        u[train_ind, :] = F
+        if self.mean_shift:
+            u -= np.mean(u, axis=0)
+        return u
 
 
 def ssl_accuracy(pred_labels, true_labels, train_ind):

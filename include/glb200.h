@@ -156,6 +156,26 @@ GLB_API int glb_poisson_gd_host(const int32_t *h_rowptr, const int32_t *h_col, c
                                 const double *h_source, int c, const int64_t *h_train_ind, int64_t m, int min_iter,
                                 int max_iter, double *h_u_out, int *T_done, int *launches);
 
+/* ---------------------------------------------------------------------------------------------
+ * Conjugate gradient with c right-hand sides.  Replaces utils.conjgrad (graphlearning/utils.py:483-532):
+ * per-column alpha/beta, one stopping norm err = sqrt(sum over all columns of |r|^2), loop test
+ * `err > tol and i < max_iter` with err initialised to 1.  Called by ssl.laplace._fit (ssl.py:1249) and the
+ * default solver of ssl.poisson._fit (ssl.py:624-629).  fp64 throughout, dot products in a fixed order.
+ * c <= 128 (GLB_E_UNSUPPORTED otherwise).
+ *
+ * glb_cg_solve: device arrays; A = CSR fp64, b / x0 / x row-major n x glb_padded_ld(c) fp64 (plain layout, zero
+ * padded), x0 may be NULL.  Synchronises the stream once per 64 iterations (iters / err are host values).
+ * glb_cg_host: the same with HOST buffers in the reference's own types (scipy CSR int32/float64, numpy
+ * float64 n x c; a 1-D right-hand side is c = 1).
+ * ------------------------------------------------------------------------------------------- */
+GLB_API int64_t glb_cg_work_bytes(int64_t n, int c);
+GLB_API int glb_cg_solve(const int32_t *d_rowptr, const int32_t *d_col, const double *d_val, int64_t n, int64_t nnz,
+                         const double *d_b, const double *d_x0, int c, double tol, int64_t max_iter, double *d_x, void *d_work,
+                         int64_t work_bytes, int64_t *iters, double *err, int *launches, void *stream);
+GLB_API int glb_cg_host(const int32_t *h_rowptr, const int32_t *h_col, const double *h_val, int64_t n, int64_t nnz,
+                        const double *h_b, const double *h_x0, int c, double tol, int64_t max_iter, double *h_x,
+                        int64_t *iters, double *err, int *launches);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,138 @@
+"""Parity of the CUDA conjugate-gradient path (cg.cu through the C-ABI) against the oracle and the
+reference-generated goldens.  The solver is fp64 like the reference; only the order of the dot-product sums
+differs, so the bar is below SURVEY.md 8d's 1e-5: max|x - x_ref| / max|x_ref| <= 1e-6 at the same
+iteration count, and the tolerance-based stop must give the reference's iteration count (within one when a
+residual norm sits on the threshold)."""
+import numpy as np
+import pytest
+from scipy import sparse
+
+from conftest import rel_err
+from oracle import gl_oracle as orc
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-6
+
+
+@pytest.fixture(scope="module")
+def gl():
+    import graphlearning_b200 as gl
+    return gl
+
+
+def test_conjgrad_golden_fixed_iterations(gl, small):
+    A = small.csr("A"); B = small["B"]
+    x5 = gl.utils.conjgrad(A, B, max_iter=5, tol=0.0)
+    assert rel_err(x5, small["cg_x_it5"]) <= TOL
+    x_ref, it_ref = orc.conjgrad(A, B, return_iters=True)
+    x, (it, err, nl) = gl.utils.conjgrad(A, B, max_iter=it_ref, tol=0.0, return_info=True)
+    assert it == it_ref and nl > 0
+    assert rel_err(x, small["cg_x"]) <= TOL
+    assert x.shape == B.shape and x.dtype == np.float64
+
+
+def test_conjgrad_one_dimensional_rhs_and_x0(gl, small):
+    A = small.csr("A"); b1 = small["b1"]
+    x1 = gl.utils.conjgrad(A, b1, tol=1e-6)
+    assert x1.shape == b1.shape
+    assert rel_err(x1, small["cg_x1"]) <= TOL
+    # warm start from the solution: one iteration, stays there
+    x2, (it, err, _) = gl.utils.conjgrad(A, b1, x0=small["cg_x1"], tol=1e-3, return_info=True)
+    assert it == 1 and rel_err(x2, small["cg_x1"]) <= TOL
+
+
+def test_conjgrad_tolerance_stop(gl, small):
+    A = small.csr("A"); B = small["B"]
+    for tol in (1e-2, 1e-4):
+        x_ref, it_ref = orc.conjgrad(A, B, tol=tol, return_iters=True)
+        x, (it, err, _) = gl.utils.conjgrad(A, B, tol=tol, return_info=True)
+        assert abs(it - it_ref) <= 1 and err <= tol
+        assert np.max(np.abs(x - x_ref)) <= 10 * tol
+    # tol >= 1: the loop never runs (err starts at 1, utils.py:519-521)
+    x, (it, _, _) = gl.utils.conjgrad(A, B, tol=2.0, return_info=True)
+    assert it == 0 and not x.any()
+
+
+@pytest.mark.parametrize("c", [1, 3, 10, 17, 64, 128])
+def test_conjgrad_widths(gl, c):
+    rng = np.random.default_rng(c)
+    n = 1500
+    R = sparse.random(n, n, 0.004, format="csr", random_state=c)
+    A = sparse.csr_matrix(R + R.T + sparse.identity(n) * 20.0)       # diagonally dominant: SPD
+    B = rng.normal(size=(n, c))
+    x_ref, it_ref = orc.conjgrad(A, B, tol=1e-6, return_iters=True)
+    x, (it, err, _) = gl.utils.conjgrad(A, B, max_iter=it_ref, tol=0.0, return_info=True)
+    assert it == it_ref
+    assert rel_err(x, x_ref) <= TOL
+    again = gl.utils.conjgrad(A, B, max_iter=it_ref, tol=0.0)
+    assert np.array_equal(x, again)                       # deterministic reductions
+
+
+def test_conjgrad_too_wide_is_an_error(gl):
+    A = sparse.identity(10, format="csr")
+    with pytest.raises(RuntimeError, match="right-hand sides|unsupported"):
+        gl.utils.conjgrad(A, np.ones((10, 200)))
+
+
+def test_poisson_default_solver(gl, moons, blobs):
+    # two-moons: connected graph, the system is consistent -> same iteration count, scores to 1e-5
+    ti = moons["train_ind"]; tl = moons["labels"][ti]
+    m = gl.ssl.poisson(moons.csr("W"))
+    u = m.fit(ti, tl)
+    _, it_ref = orc.poisson_cg(moons.csr("W"), ti, tl, return_iters=True)
+    assert m.iterations == it_ref
+    assert rel_err(u, moons["u_cg"]) <= 1e-5
+    assert np.array_equal(m.predict(), moons["p_cg"])
+    # blobs2000: the kNN graph has one component per blob and one label per component, so D^-1/2 b is not in
+    # the range of the singular normalised Laplacian.  CG on that system is driven by rounding noise (the
+    # reference itself needs 1475 iterations to drift below tol=1e-3); the iteration count and the drift along
+    # the null space depend on the summation order and cannot be reproduced, the labels can.
+    tb = blobs["train_ind"]
+    mb = gl.ssl.poisson(blobs.csr("W"))
+    mb.fit(tb, blobs["labels"][tb])
+    assert 0 < mb.iterations < 100000
+    assert np.mean(mb.predict() == blobs["p_cg"]) > 0.99
+
+
+def test_laplace_learning(gl, moons, blobs):
+    ti = moons["train_ind"]; tl = moons["labels"][ti]
+    for kwargs, key in (({}, "u_lap"), ({"normalization": "normalized", "tau": 0.01}, "u_lap_norm"), ({"mean_shift": True}, "u_lap_ms")):
+        m = gl.ssl.laplace(moons.csr("W"), **kwargs)
+        u = m.fit(ti, tl)
+        assert rel_err(u, moons[key]) <= 1e-6              # same iteration count unless a norm sits on the threshold
+        assert u.shape == (500, 2)
+    assert np.array_equal(gl.ssl.laplace(moons.csr("W")).fit_predict(ti, tl), moons["p_lap"])
+    tb = blobs["train_ind5"]
+    m = gl.ssl.laplace(blobs.csr("W"))
+    u = m.fit(tb, blobs["labels"][tb])
+    u_ref, it_ref = orc.laplace_fit(blobs.csr("W"), tb, blobs["labels"][tb], return_iters=True)
+    assert abs(m.iterations - it_ref) <= 1
+    assert rel_err(u, u_ref) <= 1e-6
+    assert np.array_equal(u[tb], np.eye(u.shape[1])[blobs["labels"][tb]])      # labels are returned exactly (ssl.py:1255)
+
+
+def test_laplace_system_matches_oracle_at_fixed_iterations(gl, blobs):
+    """The CG itself at the oracle's iteration count on the real Laplace system: the 1e-5 bar."""
+    tb = blobs["train_ind5"]; tl = blobs["labels"][tb]
+    s = orc.laplace_system(blobs.csr("W"), tb, tl)
+    v_ref, it_ref = orc.conjgrad(s["MAM"], s["Mb"], tol=1e-5, return_iters=True)
+    v = gl.utils.conjgrad(s["MAM"], s["Mb"], max_iter=it_ref, tol=0.0)
+    assert rel_err(v, v_ref) <= TOL
+
+
+def test_full_size_cg(gl):
+    """config 3 shape: 60k nodes, ~29 nnz/row, 10 columns; property checks (residual, determinism) + oracle."""
+    from test_poisson_gpu import random_knn_graph
+    n = 60000
+    W = random_knn_graph(n, 20, seed=3)
+    labels = np.random.default_rng(4).integers(0, 10, n)
+    ti = orc.one_per_class(labels, rate=5, seed=0)
+    m = gl.ssl.laplace(W)
+    u = m.fit(ti, labels[ti])
+    MAM, Mb, M, idx, F = m.system(ti, labels[ti])
+    v = (1.0 / M.diagonal())[:, None] * u[idx]
+    res = np.sqrt(np.sum((MAM @ v - Mb) ** 2))
+    assert res <= 2e-5                                     # solver tol 1e-5
+    u_ref, it_ref = orc.laplace_fit(W, ti, labels[ti], return_iters=True)
+    assert abs(m.iterations - it_ref) <= 1
+    assert rel_err(u, u_ref) <= 1e-6
