@@ -1,0 +1,451 @@
+// knn.cu - exact k-nearest-neighbour search (Euclidean) on sm_100a.
+//
+// Replaces weightmatrix.knnsearch, exact branches (reference graphlearning/weightmatrix.py:349-361: cKDTree
+// `query` and the brute-force `norm(Y - Y[i])` + `argsort` loop) and stands in for its approximate `annoy` default
+// (:368-409).  Output contract of the reference: (n, k) neighbour indices INCLUDING self, ascending by fp64
+// Euclidean distance, and the (n, k) float64 distances.
+//
+// Exactness.  The reference ranks in fp64.  Ranking n^2 fp32 Gram-form distances mis-orders near ties (SURVEY.md
+// 7.3(3)), so the search is two-stage with a checked error margin:
+//   1. knn_prepare      centre the features (distances are translation invariant, smaller norms = smaller absolute
+//                       error), round to fp32, squared norms, R = max norm.
+//   2. knn_dist_kernel  tiled fp32 distance block  D[q][j] = |q|^2 + |x_j|^2 - 2 q.x_j  for a block of QB queries
+//                       against all n points (128 x 128 x 16 register-tiled, operands staged through shared memory).
+//   3. knn_select       one warp per query: streams its row of D once and keeps the C = 32 * NPL smallest
+//                       (key = distance bits << 32 | index) in a register-resident sorted list spread over the
+//                       lanes; insertions are shuffles, a ballot against the running threshold filters the stream.
+//   4. knn_rerank       one warp per query: recomputes the C candidates as sum((x_i - x_j)^2) in fp64 from the
+//                       ORIGINAL fp64 features, sorts them by (distance, index) and writes the first k.
+//                       The row is certified when  approx[C-1] - approx[k-1] > 2 E_i  with the rigorous bound
+//                       E_i = 2 (d + 8) 2^-24 (|x_i| + R)^2  on the error of any approximate distance of row i:
+//                       then every point outside the candidate list is provably farther than k points inside it.
+//   5. knn_exact_rows   rows that fail the certificate (near-degenerate data) are redone by brute force in fp64.
+// So the returned indices are those of an exact fp64 ranking (ties between exactly equal distances are broken by
+// index; the reference's tie order is unspecified, weightmatrix.py:352,359-361).
+//
+// Roofline: stage 2 is 2 n^2 d flops of fp32 FMA work (tensor-core version: next round); stages 2+3 move
+// 2 * 4 n^2 bytes through HBM/L2 (the distance block), stage 4 gathers C rows of fp64 features per query.
+#include <float.h>
+#include <math.h>
+#include <vector>
+#include "common.cuh"
+
+namespace glb {
+
+typedef unsigned long long u64;
+
+constexpr int BM = 128, BN = 128, BK = 16;          // distance tile
+constexpr int kDistThreads = 256;
+
+// ---------------------------------------------------------------------------------------------------------
+// 1. prepare
+// ---------------------------------------------------------------------------------------------------------
+// column sums (fp64) -> mean; deterministic: one block per column chunk, fixed order
+__global__ void __launch_bounds__(256)
+knn_colsum_kernel(const double *__restrict__ X, long long n, int d, double *__restrict__ mean)
+{
+    __shared__ double sh[256];
+    const int col = blockIdx.x;
+    double s = 0.0;
+    for (long long i = threadIdx.x; i < n; i += 256) s += X[i * d + col];
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int off = 128; off > 0; off >>= 1) {
+        if ((int)threadIdx.x < off) sh[threadIdx.x] += sh[threadIdx.x + off];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) mean[col] = sh[0] / (double)n;
+}
+
+// Xc (n x dpad fp32, zero padded) = fp32(X - mean); norm2[i] = fp32(|Xc_i|^2 in fp64); rmax2 = max_i |Xc_i|^2
+__global__ void __launch_bounds__(256)
+knn_center_kernel(const double *__restrict__ X, const double *__restrict__ mean, long long n, int d, int dpad,
+                  float *__restrict__ Xc, float *__restrict__ norm2, unsigned long long *rmax2_bits)
+{
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    double worst = 0.0;
+    for (long long i = warp; i < n; i += nwarps) {
+        double s = 0.0;
+        for (int t = lane; t < dpad; t += 32) {
+            float v = 0.f;
+            if (t < d) v = (float)(X[i * d + t] - mean[t]);
+            Xc[i * dpad + t] = v;
+            s += (double)v * (double)v;
+        }
+        for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+        if (lane == 0) norm2[i] = (float)s;
+        worst = fmax(worst, s);
+    }
+    if (lane == 0) atomicMax(rmax2_bits, (unsigned long long)__double_as_longlong(worst));   // s >= 0: bit order = value order
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// 2. distance block: D[q - q0][j] = max(0, nq + nj - 2 <Xc_q, Xc_j>), q in [q0, q0 + nq), j in [0, n); j >= n -> +inf
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kDistThreads, 2)
+knn_dist_kernel(const float *__restrict__ Xc, const float *__restrict__ norm2, int n, int dpad, int q0, int nq,
+                float *__restrict__ D, long long ldD)
+{
+    __shared__ __align__(16) float As[2][BK][BM + 4];
+    __shared__ __align__(16) float Bs[2][BK][BN + 4];
+    const int tid = threadIdx.x;
+    const int tx = tid % 16, ty = tid / 16;                  // 16 x 16 threads, 8 x 8 outputs each
+    const int row0 = q0 + blockIdx.y * BM;                   // first query of the tile (global index)
+    const int col0 = blockIdx.x * BN;                        // first database point of the tile
+    // global -> register staging: thread loads 2 float4 of A and 2 of B per K step (128 rows x 16 floats = 512 float4)
+    const int lr = tid / 4, lc = (tid % 4) * 4;              // row within tile (0..63, +64), float offset within BK
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+    auto load_tile = [&](int k0, float4 ra[2], float4 rb[2]) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int r = lr + h * 64;
+            const int qa = row0 + r, pb = col0 + r;
+            ra[h] = (qa < q0 + nq && qa < n) ? __ldg(reinterpret_cast<const float4 *>(Xc + (size_t)qa * dpad + k0 + lc)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            rb[h] = (pb < n) ? __ldg(reinterpret_cast<const float4 *>(Xc + (size_t)pb * dpad + k0 + lc)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    };
+    auto store_tile = [&](int buf, const float4 ra[2], const float4 rb[2]) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int r = lr + h * 64;
+            As[buf][lc + 0][r] = ra[h].x; As[buf][lc + 1][r] = ra[h].y; As[buf][lc + 2][r] = ra[h].z; As[buf][lc + 3][r] = ra[h].w;
+            Bs[buf][lc + 0][r] = rb[h].x; Bs[buf][lc + 1][r] = rb[h].y; Bs[buf][lc + 2][r] = rb[h].z; Bs[buf][lc + 3][r] = rb[h].w;
+        }
+    };
+    float4 ra[2], rb[2];
+    load_tile(0, ra, rb);
+    store_tile(0, ra, rb);
+    __syncthreads();
+    const int nk = dpad / BK;
+    for (int kt = 0; kt < nk; ++kt) {
+        const int buf = kt & 1;
+        if (kt + 1 < nk) load_tile((kt + 1) * BK, ra, rb);
+#pragma unroll
+        for (int k = 0; k < BK; ++k) {
+            const float4 a0 = *reinterpret_cast<const float4 *>(&As[buf][k][ty * 8]);
+            const float4 a1 = *reinterpret_cast<const float4 *>(&As[buf][k][ty * 8 + 4]);
+            const float4 b0 = *reinterpret_cast<const float4 *>(&Bs[buf][k][tx * 8]);
+            const float4 b1 = *reinterpret_cast<const float4 *>(&Bs[buf][k][tx * 8 + 4]);
+            const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        if (kt + 1 < nk) {
+            store_tile(buf ^ 1, ra, rb);
+            __syncthreads();
+        }
+    }
+    // epilogue
+    float nb[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int p = col0 + tx * 8 + j;
+        nb[j] = p < n ? __ldg(norm2 + p) : INFINITY;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int q = row0 + ty * 8 + i;
+        if (q >= q0 + nq || q >= n) continue;
+        const float na = __ldg(norm2 + q);
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = fmaxf(0.f, fmaf(-2.f, acc[i][j], na + nb[j]));     // +inf stays +inf
+        float *dst = D + (size_t)(q - q0) * ldD + col0 + tx * 8;
+        *reinterpret_cast<float4 *>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+        *reinterpret_cast<float4 *>(dst + 4) = make_float4(o[4], o[5], o[6], o[7]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// 3. selection: one warp per query row, C = 32 * NPL candidates
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ u64 make_key(float d2, int idx) { return ((u64)__float_as_uint(d2) << 32) | (u64)(unsigned)idx; }
+
+// sorted list of C keys spread over the warp: lane l holds positions [l * NPL, (l + 1) * NPL)
+template <int NPL>
+struct WarpList {
+    u64 e[NPL];
+    __device__ __forceinline__ void init() {
+#pragma unroll
+        for (int i = 0; i < NPL; ++i) e[i] = ~0ull;
+    }
+    __device__ __forceinline__ u64 last(int lane) const { (void)lane; return __shfl_sync(0xffffffffu, e[NPL - 1], 31); }
+    // insert key (warp-uniform value) keeping the list sorted; the largest element falls off
+    __device__ __forceinline__ void insert(u64 key, int lane)
+    {
+        int below = 0;
+#pragma unroll
+        for (int i = 0; i < NPL; ++i) below += (e[i] < key) ? 1 : 0;
+        const int p = __reduce_add_sync(0xffffffffu, below);            // insertion position
+        u64 carry = __shfl_up_sync(0xffffffffu, e[NPL - 1], 1);          // last element of the previous lane
+#pragma unroll
+        for (int i = NPL - 1; i >= 0; --i) {
+            const int g = lane * NPL + i;
+            const u64 prev = (i == 0) ? carry : e[i - 1];
+            if (g > p) e[i] = prev;
+            else if (g == p) e[i] = key;
+        }
+    }
+};
+
+template <int NPL>
+__global__ void __launch_bounds__(256)
+knn_select_kernel(const float *__restrict__ D, long long ldD, int n_pad, int nq, u64 *__restrict__ cand)
+{
+    const int lane = threadIdx.x & 31;
+    const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (q >= nq) return;
+    const float *row = D + (size_t)q * ldD;
+    WarpList<NPL> list;
+    list.init();
+    float tau = INFINITY;                      // current C-th smallest distance; a candidate must be <= tau
+    u64 tau_key = ~0ull;
+    for (int base = 0; base < n_pad; base += 128) {
+        const float4 v4 = __ldg(reinterpret_cast<const float4 *>(row + base) + lane);
+        const float v[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int idx = base + lane * 4 + c;
+            unsigned m = __ballot_sync(0xffffffffu, v[c] <= tau && v[c] < INFINITY);
+            while (m) {
+                const int src = __ffs(m) - 1;
+                m &= m - 1;
+                const float dv = __shfl_sync(0xffffffffu, v[c], src);
+                const int di = __shfl_sync(0xffffffffu, idx, src);
+                const u64 key = make_key(dv, di);
+                if (key < tau_key) {
+                    list.insert(key, lane);
+                    tau_key = list.last(lane);
+                    tau = __uint_as_float((unsigned)(tau_key >> 32));
+                    if (tau_key == ~0ull) tau = INFINITY;
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < NPL; ++i) cand[(size_t)q * (32 * NPL) + lane * NPL + i] = list.e[i];
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// 4. exact re-rank of the candidates + certificate
+// ---------------------------------------------------------------------------------------------------------
+struct ExactKey { double d2; int idx; };
+__device__ __forceinline__ bool key_less(double da, int ia, double db, int ib) { return da < db || (da == db && ia < ib); }
+
+template <int NPL>
+__global__ void __launch_bounds__(256)
+knn_rerank_kernel(const double *__restrict__ X, int n, int d, const float *__restrict__ norm2,
+                  const unsigned long long *__restrict__ rmax2_bits, const u64 *__restrict__ cand, int q0, int nq, int k,
+                  long long *__restrict__ out_ind, double *__restrict__ out_dist, int *__restrict__ fail_rows,
+                  int *__restrict__ fail_count)
+{
+    constexpr int C = 32 * NPL;
+    const int lane = threadIdx.x & 31;
+    const int wq = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (wq >= nq) return;
+    const int q = q0 + wq;
+    const double *xq = X + (size_t)q * d;
+    u64 keys[NPL];
+    double d2[NPL];
+    int idx[NPL];
+#pragma unroll
+    for (int i = 0; i < NPL; ++i) {
+        keys[i] = cand[(size_t)wq * C + lane * NPL + i];
+        idx[i] = (int)(unsigned)(keys[i] & 0xffffffffull);
+        d2[i] = INFINITY;
+        if (keys[i] != ~0ull) {
+            const double *xc = X + (size_t)idx[i] * d;
+            double s = 0.0;
+            for (int t = 0; t < d; ++t) { const double df = xq[t] - xc[t]; s = fma(df, df, s); }
+            d2[i] = s;
+        } else {
+            idx[i] = 0x7fffffff;
+        }
+    }
+    // certificate: approximate distances of list positions k-1 and C-1 (list is sorted ascending by approximate key)
+    const int pk = k - 1;
+    u64 mine_k = keys[0];
+#pragma unroll
+    for (int i = 1; i < NPL; ++i) if (i == pk % NPL) mine_k = keys[i];
+    const u64 key_k = __shfl_sync(0xffffffffu, mine_k, pk / NPL);
+    const u64 key_c = __shfl_sync(0xffffffffu, keys[NPL - 1], 31);
+    const float ak = __uint_as_float((unsigned)(key_k >> 32)), ac = __uint_as_float((unsigned)(key_c >> 32));
+    const double R = sqrt(__longlong_as_double((long long)*rmax2_bits));
+    const double ni = sqrt((double)norm2[q]);
+    const double E = 2.0 * (double)(d + 8) * 5.9604644775390625e-8 * (ni + R) * (ni + R);
+    // fewer than C points in total (n <= C): the list holds everything, nothing can be missing
+    const bool certified = (key_c == ~0ull) || ((double)ac - (double)ak > 2.0 * E);
+    // rank of every candidate among the C by (exact d2, index): O(C) shuffles per element, C <= 128
+    int rank[NPL];
+#pragma unroll
+    for (int i = 0; i < NPL; ++i) rank[i] = 0;
+    for (int src = 0; src < 32; ++src) {
+#pragma unroll
+        for (int j = 0; j < NPL; ++j) {
+            const double od = __shfl_sync(0xffffffffu, d2[j], src);
+            const int oi = __shfl_sync(0xffffffffu, idx[j], src);
+#pragma unroll
+            for (int i = 0; i < NPL; ++i) rank[i] += key_less(od, oi, d2[i], idx[i]) ? 1 : 0;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < NPL; ++i) {
+        if (rank[i] < k) {
+            out_ind[(size_t)q * k + rank[i]] = idx[i];
+            out_dist[(size_t)q * k + rank[i]] = sqrt(d2[i]);
+        }
+    }
+    if (!certified && lane == 0) fail_rows[atomicAdd(fail_count, 1)] = q;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// 5. brute force in fp64 for the rows without certificate: one CTA per row
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+knn_exact_rows_kernel(const double *__restrict__ X, int n, int d, const int *__restrict__ rows, const int *__restrict__ nrows_ptr,
+                      int k, double *__restrict__ scratch, long long *__restrict__ out_ind, double *__restrict__ out_dist)
+{
+    __shared__ double sh_d[256];
+    __shared__ int sh_i[256];
+    const int nrows = *nrows_ptr;
+    for (int r = blockIdx.x; r < nrows; r += gridDim.x) {
+        const int q = rows[r];
+        double *dist = scratch + (size_t)blockIdx.x * n;
+        const double *xq = X + (size_t)q * d;
+        for (int j = threadIdx.x; j < n; j += 256) {
+            const double *xc = X + (size_t)j * d;
+            double s = 0.0;
+            for (int t = 0; t < d; ++t) { const double df = xq[t] - xc[t]; s = fma(df, df, s); }
+            dist[j] = s;
+        }
+        __syncthreads();
+        for (int sel = 0; sel < k; ++sel) {                 // k rounds of block-wide argmin by (distance, index)
+            double bd = INFINITY; int bi = 0x7fffffff;
+            for (int j = threadIdx.x; j < n; j += 256) {
+                const double v = dist[j];
+                if (key_less(v, j, bd, bi)) { bd = v; bi = j; }
+            }
+            sh_d[threadIdx.x] = bd; sh_i[threadIdx.x] = bi;
+            __syncthreads();
+            for (int off = 128; off > 0; off >>= 1) {
+                if ((int)threadIdx.x < off && key_less(sh_d[threadIdx.x + off], sh_i[threadIdx.x + off], sh_d[threadIdx.x], sh_i[threadIdx.x])) {
+                    sh_d[threadIdx.x] = sh_d[threadIdx.x + off]; sh_i[threadIdx.x] = sh_i[threadIdx.x + off];
+                }
+                __syncthreads();
+            }
+            if (threadIdx.x == 0) {
+                out_ind[(size_t)q * k + sel] = sh_i[0];
+                out_dist[(size_t)q * k + sel] = sqrt(sh_d[0]);
+                if (sh_i[0] < n) dist[sh_i[0]] = INFINITY;
+            }
+            __syncthreads();
+        }
+    }
+}
+
+struct KnnArena {
+    std::vector<void *> v;
+    ~KnnArena() { for (void *p : v) cudaFree(p); }
+    cudaError_t alloc(void **p, size_t bytes) { cudaError_t e = cudaMalloc(p, bytes ? bytes : 1); if (e == cudaSuccess) v.push_back(*p); return e; }
+};
+
+template <int NPL>
+static int knn_run(const double *d_X, int64_t n, int d, int k, long long *d_ind, double *d_dist, int *launches, int *fallback_rows,
+                   cudaStream_t st)
+{
+    constexpr int C = 32 * NPL;
+    KnnArena A;
+    const int dpad = (d + BK - 1) / BK * BK;
+    const int n_pad = (int)((n + BN - 1) / BN * BN);
+    int QB = 2048;                                            // queries per distance block: QB x n_pad fp32 in HBM
+    while ((double)QB * n_pad * 4.0 > 2.0e9 && QB > 128) QB /= 2;
+    if (QB > n) QB = (int)((n + BM - 1) / BM * BM);
+    double *mean; float *Xc, *norm2, *D; unsigned long long *rmax2; u64 *cand; int *fail_rows, *fail_count; double *scratch;
+    GLB_CUDA(A.alloc((void **)&mean, sizeof(double) * d));
+    GLB_CUDA(A.alloc((void **)&Xc, sizeof(float) * (size_t)n * dpad));
+    GLB_CUDA(A.alloc((void **)&norm2, sizeof(float) * (size_t)n));
+    GLB_CUDA(A.alloc((void **)&rmax2, sizeof(unsigned long long)));
+    GLB_CUDA(A.alloc((void **)&D, sizeof(float) * (size_t)QB * n_pad));
+    GLB_CUDA(A.alloc((void **)&cand, sizeof(u64) * (size_t)QB * C));
+    GLB_CUDA(A.alloc((void **)&fail_rows, sizeof(int) * (size_t)n));
+    GLB_CUDA(A.alloc((void **)&fail_count, sizeof(int)));
+    const int exact_ctas = sm_count();
+    GLB_CUDA(A.alloc((void **)&scratch, sizeof(double) * (size_t)exact_ctas * n));
+    GLB_CUDA(cudaMemsetAsync(rmax2, 0, sizeof(unsigned long long), st));
+    GLB_CUDA(cudaMemsetAsync(fail_count, 0, sizeof(int), st));
+    int nl = 0;
+    knn_colsum_kernel<<<d, 256, 0, st>>>(d_X, n, d, mean); ++nl;
+    knn_center_kernel<<<sm_count() * 8, 256, 0, st>>>(d_X, mean, n, d, dpad, Xc, norm2, rmax2); ++nl;
+    for (int64_t q0 = 0; q0 < n; q0 += QB) {
+        const int nq = (int)std::min<int64_t>(QB, n - q0);
+        dim3 grid((unsigned)(n_pad / BN), (unsigned)((nq + BM - 1) / BM));
+        knn_dist_kernel<<<grid, kDistThreads, 0, st>>>(Xc, norm2, (int)n, dpad, (int)q0, nq, D, (long long)n_pad); ++nl;
+        knn_select_kernel<NPL><<<(nq * 32 + 255) / 256, 256, 0, st>>>(D, (long long)n_pad, n_pad, nq, cand); ++nl;
+        knn_rerank_kernel<NPL><<<(nq * 32 + 255) / 256, 256, 0, st>>>(d_X, (int)n, d, norm2, rmax2, cand, (int)q0, nq, k, d_ind, d_dist,
+                                                                       fail_rows, fail_count); ++nl;
+    }
+    knn_exact_rows_kernel<<<exact_ctas, 256, 0, st>>>(d_X, (int)n, d, fail_rows, fail_count, k, scratch, d_ind, d_dist); ++nl;
+    GLB_LAUNCH_CHECK();
+    int h_fail = 0;
+    GLB_CUDA(cudaMemcpyAsync(&h_fail, fail_count, sizeof(int), cudaMemcpyDeviceToHost, st));
+    GLB_CUDA(cudaStreamSynchronize(st));                      // the arena is freed on return
+    if (launches) *launches += nl;
+    if (fallback_rows) *fallback_rows = h_fail;
+    return 0;
+}
+
+}  // namespace glb
+
+using namespace glb;
+
+extern "C" GLB_API int glb_knn_search(const double *d_X, int64_t n, int d, int k, int64_t *d_ind, double *d_dist, int *launches,
+                                      int *fallback_rows, void *stream)
+{
+    GLB_CHECK_ARG(d_X && d_ind && d_dist, "null pointer");
+    GLB_CHECK_ARG(n > 0 && n < (1ll << 31) - 256, "n out of range");
+    GLB_CHECK_ARG(d > 0 && d <= 65536, "d out of range");
+    GLB_CHECK_ARG(k > 0 && k <= n, "k must be in [1, n]");
+    if (k > 112) { set_error("glb_knn_search: k = %d (> 112) is not supported", k); return GLB_E_UNSUPPORTED; }
+    cudaStream_t st = (cudaStream_t)stream;
+    // candidates: at least k + 8 and 1.25 k, in steps of 32
+    if (k + 8 <= 32 && k * 5 / 4 <= 32) return knn_run<1>(d_X, n, d, k, (long long *)d_ind, d_dist, launches, fallback_rows, st);
+    if (k + 8 <= 64 && k * 5 / 4 <= 64) return knn_run<2>(d_X, n, d, k, (long long *)d_ind, d_dist, launches, fallback_rows, st);
+    return knn_run<4>(d_X, n, d, k, (long long *)d_ind, d_dist, launches, fallback_rows, st);
+}
+
+extern "C" GLB_API int glb_knn_search_host(const double *h_X, int64_t n, int d, int k, int64_t *h_ind, double *h_dist, int *launches,
+                                           int *fallback_rows)
+{
+    GLB_CHECK_ARG(h_X && h_ind && h_dist, "null pointer");
+    GLB_CHECK_ARG(n > 0 && d > 0 && k > 0 && k <= n, "bad shape");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        set_error("glb_knn_search_host: no CUDA device visible");
+        return GLB_E_NOGPU;
+    }
+    KnnArena A;
+    double *X, *dist; long long *ind;
+    GLB_CUDA(A.alloc((void **)&X, sizeof(double) * (size_t)n * d));
+    GLB_CUDA(A.alloc((void **)&ind, sizeof(long long) * (size_t)n * k));
+    GLB_CUDA(A.alloc((void **)&dist, sizeof(double) * (size_t)n * k));
+    cudaStream_t st = 0;
+    GLB_CUDA(cudaMemcpyAsync(X, h_X, sizeof(double) * (size_t)n * d, cudaMemcpyHostToDevice, st));
+    if (launches) *launches = 0;
+    int rc = glb_knn_search(X, n, d, k, (int64_t *)ind, dist, launches, fallback_rows, st);
+    if (rc) return rc;
+    GLB_CUDA(cudaMemcpyAsync(h_ind, ind, sizeof(long long) * (size_t)n * k, cudaMemcpyDeviceToHost, st));
+    GLB_CUDA(cudaMemcpyAsync(h_dist, dist, sizeof(double) * (size_t)n * k, cudaMemcpyDeviceToHost, st));
+    GLB_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}

@@ -176,6 +176,25 @@ GLB_API int glb_cg_host(const int32_t *h_rowptr, const int32_t *h_col, const dou
                         const double *h_b, const double *h_x0, int c, double tol, int64_t max_iter, double *h_x,
                         int64_t *iters, double *err, int *launches);
 
+/* ---------------------------------------------------------------------------------------------
+ * Exact k-nearest-neighbour search, Euclidean.  Replaces weightmatrix.knnsearch
+ * (graphlearning/weightmatrix.py:297-429): the exact branches (cKDTree :349-352, brute force :354-361) and,
+ * as a quality superset, the approximate annoy default (:368-409).  For similarity='angular' pass
+ * row-normalised features (:344-345).
+ *
+ * X: n x d float64 row-major.  ind: n x k int64, dist: n x k float64, neighbours INCLUDING self, ascending by
+ * fp64 distance (equal distances ordered by index).  The result is that of an exact fp64 ranking: an fp32
+ * tiled distance pass picks 32..128 candidates per row, they are re-ranked in fp64 from the original
+ * features, and a per-row error-margin certificate proves that no true neighbour was missed; rows without
+ * certificate are redone by fp64 brute force (*fallback_rows counts them, may be NULL).  k <= 112.
+ * glb_knn_search: device pointers, allocates its scratch internally, synchronises the stream before
+ * returning.  glb_knn_search_host: host pointers.
+ * ------------------------------------------------------------------------------------------- */
+GLB_API int glb_knn_search(const double *d_X, int64_t n, int d, int k, int64_t *d_ind, double *d_dist, int *launches,
+                           int *fallback_rows, void *stream);
+GLB_API int glb_knn_search_host(const double *h_X, int64_t n, int d, int k, int64_t *h_ind, double *h_dist, int *launches,
+                                int *fallback_rows);
+
 #ifdef __cplusplus
 }
 #endif

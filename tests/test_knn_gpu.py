@@ -1,0 +1,105 @@
+"""Parity of the CUDA kNN search (knn.cu through the C-ABI) with the reference's exact searches.
+
+Bar (north_star): bit-exact neighbour indices against knnsearch(method='kdtree'|'brute') on duplicate-free input;
+distances are fp64 and may differ from scipy's in the last bits (different summation order): rtol 1e-12."""
+import numpy as np
+import pytest
+
+from oracle import gl_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gl():
+    import graphlearning_b200 as gl
+    return gl
+
+
+@pytest.fixture(scope="module")
+def kg():
+    from graphlearning_b200 import knn_gpu
+    return knn_gpu
+
+
+def check(ind, dist, ref_ind, ref_dist):
+    assert ind.dtype == np.int64 and dist.dtype == np.float64
+    assert np.array_equal(ind, ref_ind)
+    assert np.allclose(dist, ref_dist, rtol=1e-12, atol=1e-300)
+
+
+def test_goldens_from_the_reference(kg, moons, blobs, small):
+    for g in (moons, blobs, small):
+        k = g["knn_ind"].shape[1]
+        ind, dist = kg.knnsearch_gpu(g["X"], k)
+        check(ind, dist, g["knn_ind"], g["knn_dist"])
+        assert kg.last_stats["launches"] > 0
+    ind, dist = kg.knnsearch_gpu(blobs["X"], blobs["knn_ind_angular"].shape[1], similarity="angular")
+    check(ind, dist, blobs["knn_ind_angular"], blobs["knn_dist_angular"])
+
+
+def test_knnsearch_dispatch(gl, blobs, moons):
+    """weightmatrix.knnsearch: d <= 5 -> cKDTree as the reference, otherwise (and for 'brute'/'annoy') the GPU."""
+    k = blobs["knn_ind"].shape[1]
+    for method in (None, "brute", "annoy"):
+        ind, dist = gl.weightmatrix.knnsearch(blobs["X"], k, method=method)
+        check(ind, dist, blobs["knn_ind"], blobs["knn_dist"])
+    ind, _ = gl.weightmatrix.knnsearch(moons["X"], 11, method="brute")
+    assert np.array_equal(ind, moons["knn_ind"])
+    W = gl.weightmatrix.knn(blobs["X"], k - 1)
+    Wref = blobs.csr("W")
+    assert np.array_equal(W.indptr, Wref.indptr) and np.array_equal(W.indices, Wref.indices)
+    assert np.allclose(W.data, Wref.data, rtol=1e-11)
+
+
+@pytest.mark.parametrize("n,d,k", [(5000, 128, 11), (3000, 17, 31), (1500, 300, 101), (700, 1, 5), (40, 6, 40)])
+def test_shapes_against_fp64_brute_force(kg, n, d, k):
+    X, _ = orc.synthetic_blobs(n, d, c=5, seed=n + d)
+    X = X.astype(np.float64)
+    ind, dist = kg.knnsearch_gpu(X, k)
+    rows = np.random.default_rng(0).choice(n, min(n, 300), replace=False)
+    ref_ind, ref_dist = orc.knnsearch_rows(X, rows, k)
+    check(ind[rows], dist[rows], ref_ind, ref_dist)
+    assert np.array_equal(ind[:, 0], np.arange(n)) and np.all(dist[:, 0] == 0)
+    assert np.all(np.diff(dist, axis=1) >= 0)
+
+
+def test_duplicates_and_degenerate_data_use_the_exact_fallback(kg):
+    rng = np.random.default_rng(3)
+    X = rng.normal(size=(600, 20))
+    X[100:140] = X[5]                               # 41 copies of one point: equal distances, certificate fails there
+    ind, dist = kg.knnsearch_gpu(X, 11)
+    assert kg.last_stats["fallback_rows"] >= 40
+    ref_ind, ref_dist = orc.knnsearch_rows(X, np.arange(600), 11)
+    assert np.allclose(dist, ref_dist, rtol=1e-12, atol=0)      # tie ORDER among equal distances is unspecified in the reference
+    same = np.all(np.diff(ref_dist, axis=1) > 0, axis=1)        # rows without ties: indices exact
+    assert np.array_equal(ind[same], ref_ind[same])
+    assert np.all(dist[100:140, :11] == 0) and np.all(np.sort(ind[100:140], axis=1)[:, 0] == 5)
+    Xc = np.ones((300, 8))                           # all points equal
+    ind, dist = kg.knnsearch_gpu(Xc, 4)
+    assert not dist.any() and np.array_equal(ind, np.tile(np.arange(4), (300, 1)))
+
+
+def test_bad_arguments(kg):
+    from graphlearning_b200._lib import GlbError
+    with pytest.raises(GlbError):
+        kg.knnsearch_gpu(np.zeros((10, 3)), 11)
+    with pytest.raises(GlbError, match="not supported"):
+        kg.knnsearch_gpu(np.zeros((500, 3)), 200)
+
+
+def test_full_size_config2(kg):
+    """70k x 128, k+1 = 11 (BASELINE config 2): exact on a 300-row sample, structural properties on all rows."""
+    X, _ = orc.synthetic_blobs(70000, 128, c=10, seed=0)
+    X = X.astype(np.float64)
+    ind, dist = kg.knnsearch_gpu(X, 11)
+    assert kg.last_stats["fallback_rows"] < 70                 # the certificate holds for (nearly) every row
+    rows = np.random.default_rng(1).choice(70000, 300, replace=False)
+    ref_ind, ref_dist = orc.knnsearch_rows(X, rows, 11)
+    check(ind[rows], dist[rows], ref_ind, ref_dist)
+    assert np.array_equal(ind[:, 0], np.arange(70000))
+    assert np.all(np.diff(dist, axis=1) > 0)
+    # symmetry of the distance: d(i, j) reported by row i equals |x_i - x_j| recomputed
+    i = rows[:50]
+    rec = np.sqrt(((X[i][:, None, :] - X[ind[i]]) ** 2).sum(-1))
+    assert np.allclose(rec, dist[i], rtol=1e-12)
