@@ -320,20 +320,28 @@ __device__ __forceinline__ void st_chunk(char *p, float a, float b, float c, uns
                  "r"(__float_as_uint(c)), "r"(w) : "memory");
 }
 
+// Slot types of the sliced-ELL slabs.  NORMAL: 32/LANES rows side by side.  The other three hold ONE (part of a)
+// long row whose nonzeros are dealt round-robin to the lane groups of the warp and summed with shuffles:
+// LONG = whole row; OWNER/PART = a hub row split over several warps, the PART warps leave their partial sums
+// (3 floats + iteration number per lane) in shared memory and the OWNER warp adds them in a fixed order.
+constexpr int kSlotNormal = 0, kSlotLong = 1, kSlotPart = 2, kSlotOwner = 3;
+constexpr int kLongRowDf = 32;                   // rows with more nonzeros get a warp (or several) of their own
+
 template <int LANES, int THREADS, int U>
 __global__ void __launch_bounds__(THREADS, 1)
 poisson_dataflow_kernel(const int2 *__restrict__ slabs, const long long *__restrict__ slab_off,
-                        const int2 *__restrict__ slots, const int *__restrict__ slot_off,
+                        const int4 *__restrict__ slots, const int *__restrict__ slot_off,
                         const int *__restrict__ slot_rows, const float *__restrict__ Db, float *u0, float *u1, int T,
-                        int cap_entries, int cap_slots, unsigned long long *stats, int nopoll)
+                        int cap_entries, int cap_slots, int cap_parts, unsigned long long *stats, int nopoll)
 {
     constexpr int RPW = 32 / LANES;              // rows per warp pass = slice height of the ELL slab
     constexpr int NW = THREADS / 32;
     constexpr unsigned ROWB = LANES * 16;        // bytes per label row
     extern __shared__ __align__(16) unsigned char smem_raw[];
     int2 *s_cv = reinterpret_cast<int2 *>(smem_raw);
-    int2 *s_slot = s_cv + cap_entries;
-    int *s_rows = reinterpret_cast<int *>(s_slot + cap_slots);
+    int4 *s_slot = reinterpret_cast<int4 *>(s_cv + cap_entries);
+    volatile float *s_part = reinterpret_cast<volatile float *>(s_slot + cap_slots);     // [cap_parts][2][LANES][4]
+    int *s_rows = reinterpret_cast<int *>(const_cast<float *>(s_part) + (size_t)cap_parts * 2 * LANES * 4);
 
     const long long e0 = slab_off[blockIdx.x];
     const int nent = (int)(slab_off[blockIdx.x + 1] - e0);
@@ -341,6 +349,7 @@ poisson_dataflow_kernel(const int2 *__restrict__ slabs, const long long *__restr
     const int nslots = slot_off[blockIdx.x + 1] - sl0;
     for (int i = threadIdx.x; i < nent; i += THREADS) s_cv[i] = slabs[e0 + i];
     for (int i = threadIdx.x; i < nslots; i += THREADS) s_slot[i] = slots[sl0 + i];
+    for (int i = threadIdx.x; i < cap_parts * 2 * LANES * 4; i += THREADS) s_part[i] = 0.f;
     // The Poisson source Db is zero except on the labelled rows: remember which rows have one
     for (int i = threadIdx.x; i < nslots * RPW; i += THREADS) {
         int r = slot_rows[(size_t)sl0 * RPW + i];
@@ -365,9 +374,9 @@ poisson_dataflow_kernel(const int2 *__restrict__ slabs, const long long *__restr
         const char *in = reinterpret_cast<const char *>(((t & 1) && !(nopoll & 4)) ? u1 : u0) + li * 16;
         char *out = reinterpret_cast<char *>(((t & 1) && !(nopoll & 4)) ? u0 : u1) + li * 16;
         const unsigned expect = 1u + (unsigned)t;
-        for (int s = warp; s < nslots; s += NW) {
-            const int2 sl = s_slot[s];                       // (first entry, slice width)
-            const int2 *cv = s_cv + sl.x + g;                // entry j of this lane group's row: cv[j * RPW]
+        for (int s = warp; s < nslots; s += NW) {            // slot k of warp w is stored at k * NW + w
+            const int4 sl = s_slot[s];                       // (first entry, slice width, type | parts << 8, partial index)
+            const int2 *cv = s_cv + sl.x + g;                // entry j of this lane group: cv[j * RPW]
             const int L = sl.y;
             float a0 = 0.f, a1 = 0.f, a2 = 0.f;
             for (int j0 = 0; j0 < L; j0 += U) {
@@ -389,7 +398,7 @@ poisson_dataflow_kernel(const int2 *__restrict__ slabs, const long long *__restr
                 unsigned bad = 0;
 #pragma unroll
                 for (int i = 0; i < U; ++i) bad |= x[i].w ^ expect;
-                while (bad && !(nopoll & 1)) {                     // some producer is still behind: re-poll the stale chunks together
+                while (bad && !(nopoll & 1)) {               // some producer is still behind: re-poll the stale chunks together
                     ++n_badbatch;
 #pragma unroll
                     for (int i = 0; i < U; ++i)
@@ -403,6 +412,33 @@ poisson_dataflow_kernel(const int2 *__restrict__ slabs, const long long *__restr
                     a0 = fmaf(val[i], __uint_as_float(x[i].x), a0);
                     a1 = fmaf(val[i], __uint_as_float(x[i].y), a1);
                     a2 = fmaf(val[i], __uint_as_float(x[i].z), a2);
+                }
+            }
+            const int type = sl.z & 0xff;
+            if (type != kSlotNormal) {                       // warp-uniform: one long row dealt over the lane groups
+#pragma unroll
+                for (int o = LANES; o < 32; o <<= 1) {
+                    a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+                    a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+                    a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+                }
+                if (type == kSlotPart) {
+                    if (g == 0) {
+                        volatile float *pb = s_part + ((size_t)(sl.w * 2 + (t & 1)) * LANES + li) * 4;
+                        pb[0] = a0; pb[1] = a1; pb[2] = a2;
+                        __threadfence_block();
+                        pb[3] = __uint_as_float(expect + 1u);
+                    }
+                    continue;
+                }
+                if (type == kSlotOwner) {
+                    const int nparts = sl.z >> 8;
+                    for (int q = 0; q < nparts; ++q) {       // partial sums of the other warps, fixed order
+                        volatile float *pb = s_part + ((size_t)((sl.w + q) * 2 + (t & 1)) * LANES + li) * 4;
+                        while (__float_as_uint(pb[3]) != expect + 1u && !(nopoll & 1)) { }
+                        __threadfence_block();
+                        a0 += pb[0]; a1 += pb[1]; a2 += pb[2];
+                    }
                 }
             }
             const int rinfo = s_rows[s * RPW + g];
@@ -589,10 +625,11 @@ struct glb_poisson_plan {
     unsigned *d_counter = nullptr;      // barrier words: kFlagStride * grid unsigned
     int *d_cta_rows = nullptr;          // grid + 1 row boundaries of the work-balanced partition
     // dataflow kernel: sliced-ELL slabs of every CTA, back to back
-    int2 *d_slabs = nullptr, *d_slots = nullptr;
+    int2 *d_slabs = nullptr;
+    int4 *d_slots = nullptr;
     long long *d_slab_off = nullptr;
     int *d_slot_off = nullptr, *d_slot_rows = nullptr;
-    int cap_entries = 0, cap_slots = 0;
+    int cap_entries = 0, cap_slots = 0, cap_parts = 0;
     double ell_fill = 0.0;              // nnz / stored entries of the slabs
     float tuned_ms[2] = {0.f, 0.f};     // AUTO: measured ms of the trial run, {dataflow, barrier}
     unsigned long long *d_stats = nullptr;   // GLB_POISSON_STATS=1: {re-polls, batches that had to poll, max warp cycles, CTAs}
@@ -712,54 +749,129 @@ static int plan_try_dataflow(glb_poisson_plan *p, const std::vector<int> &h_rp, 
     }
     if (!pattern_symmetric(h_rp, h_col, n)) return 0;
 
+    int threads = 0;
+    const void *fn = pick_dataflow(lanes, &threads);
+    const int nw = threads / 32;
     std::vector<int> bounds;
     balanced_bounds(h_rp, n, grid, 2.0, bounds);
-    std::vector<int2> slab, slots;
+    std::vector<int2> slab;
+    std::vector<int4> slots;
     std::vector<long long> slab_off((size_t)grid + 1, 0);
     std::vector<int> slot_off((size_t)grid + 1, 0), slot_rows, order;
-    slab.reserve((size_t)nnz + (size_t)nnz / 8 + 1024);
-    int cap_entries = 0, cap_slots = 0;
+    slab.reserve((size_t)nnz + (size_t)nnz / 4 + 1024);
+    int cap_entries = 0, cap_slots = 0, cap_parts = 0;
+    const int part_max = kLongRowDf * rpw;            // nonzeros of one warp-wide piece of a long row (2 batches per lane group)
+    struct Slot { int type, nparts, pbuf, L, first /*entry or row list start*/, cost; int rows[32]; int nz0, nz1; };
+    std::vector<Slot> cta_slots;
+    std::vector<std::vector<int>> per_warp((size_t)nw);
+    std::vector<long long> load((size_t)nw);
     for (int b = 0; b < grid; ++b) {
         const int r0 = bounds[b], r1 = bounds[b + 1];
-        order.resize((size_t)(r1 - r0));
-        for (int i = 0; i < r1 - r0; ++i) order[i] = r0 + i;
-        std::stable_sort(order.begin(), order.end(), [&](int a, int c2) {
-            return h_rp[a + 1] - h_rp[a] > h_rp[c2 + 1] - h_rp[c2];
-        });
-        const int nslots = (r1 - r0 + rpw - 1) / rpw;
-        const long long base0 = (long long)slab.size();
-        for (int s = 0; s < nslots; ++s) {
-            const int first = order[(size_t)s * rpw];
-            const int L = h_rp[first + 1] - h_rp[first];              // longest row of the slice comes first
-            slots.push_back(make_int2((int)((long long)slab.size() - base0), L));
-            for (int g = 0; g < rpw; ++g) {
-                const size_t k = (size_t)s * rpw + g;
-                slot_rows.push_back(k < order.size() ? order[k] : -1);
-            }
-            for (int j = 0; j < L; ++j)
-                for (int g = 0; g < rpw; ++g) {
-                    const size_t k = (size_t)s * rpw + g;
-                    int2 e = make_int2((int)kPadOff, 0);
-                    if (k < order.size()) {
-                        const int r = order[k];
-                        if (j < h_rp[r + 1] - h_rp[r]) {
-                            const int q = h_rp[r] + j;
-                            e = make_int2((int)((unsigned)h_col[q] * (unsigned)rowb), float_bits(h_val[q]));
-                        }
-                    }
-                    slab.push_back(e);
-                }
+        cta_slots.clear();
+        // short rows: sorted by length, rpw per slot
+        order.clear();
+        for (int r = r0; r < r1; ++r) if (h_rp[r + 1] - h_rp[r] <= kLongRowDf) order.push_back(r);
+        std::stable_sort(order.begin(), order.end(), [&](int a, int c2) { return h_rp[a + 1] - h_rp[a] > h_rp[c2 + 1] - h_rp[c2]; });
+        for (size_t k0 = 0; k0 < order.size(); k0 += rpw) {
+            Slot sl{};
+            sl.type = kSlotNormal;
+            sl.L = h_rp[order[k0] + 1] - h_rp[order[k0]];
+            for (int g = 0; g < rpw; ++g) sl.rows[g] = k0 + g < order.size() ? order[k0 + g] : -1;
+            sl.cost = (sl.L + 15) / 16 + 1;
+            cta_slots.push_back(sl);
         }
+        // long rows: one warp-wide slot per piece of at most part_max nonzeros
+        int nparts_cta = 0;
+        for (int r = r0; r < r1; ++r) {
+            const int len = h_rp[r + 1] - h_rp[r];
+            if (len <= kLongRowDf) continue;
+            const int m = (len + part_max - 1) / part_max;
+            const int chunk = (len + m - 1) / m;
+            for (int q = 0; q < m; ++q) {
+                Slot sl{};
+                sl.nz0 = h_rp[r] + q * chunk;
+                sl.nz1 = std::min(h_rp[r + 1], sl.nz0 + chunk);
+                sl.L = (sl.nz1 - sl.nz0 + rpw - 1) / rpw;
+                for (int g = 0; g < rpw; ++g) sl.rows[g] = -1;
+                if (q == 0) {
+                    sl.type = m == 1 ? kSlotLong : kSlotOwner;
+                    sl.nparts = m - 1;
+                    sl.pbuf = nparts_cta;                 // partial sums nparts_cta .. nparts_cta + m - 2
+                    sl.rows[0] = r;
+                } else {
+                    sl.type = kSlotPart;
+                    sl.pbuf = nparts_cta + q - 1;
+                }
+                sl.cost = (sl.L + 15) / 16 + 1 + (q == 0 ? m - 1 : 0);
+                cta_slots.push_back(sl);
+            }
+            nparts_cta += m - 1;
+        }
+        // deal the slots to the warps: PART pieces first, then OWNER/LONG, then NORMAL (a warp never waits in shared
+        // memory for a piece it has not produced yet itself); inside a class longest first to the least loaded warp
+        for (auto &v : per_warp) v.clear();
+        std::fill(load.begin(), load.end(), 0ll);
+        std::vector<int> idx(cta_slots.size());
+        for (size_t i = 0; i < idx.size(); ++i) idx[i] = (int)i;
+        auto cls = [&](int i) { const int t = cta_slots[i].type; return t == kSlotPart ? 0 : (t == kSlotNormal ? 2 : 1); };
+        std::stable_sort(idx.begin(), idx.end(), [&](int a, int c2) {
+            if (cls(a) != cls(c2)) return cls(a) < cls(c2);
+            return cta_slots[a].cost > cta_slots[c2].cost;
+        });
+        // Experiment (GLB_POISSON_HUBWARPS=1): warps of their own for the long rows, as many as their share of the
+        // work.  Measured slower than mixing them (r1q probe, profiles/): 40 vs 23 us/iteration on the 128-d graph.
+        long long cost_long = 0, cost_all = 0;
+        for (int i : idx) { cost_all += cta_slots[i].cost; if (cls(i) != 2) cost_long += cta_slots[i].cost; }
+        int hub_warps = 0;
+        if (cost_long > 0 && cost_long < cost_all && getenv("GLB_POISSON_HUBWARPS")) {
+            hub_warps = (int)((double)cost_long / (double)cost_all * nw + 0.5);
+            hub_warps = std::max(1, std::min(nw - 1, hub_warps));
+        }
+        for (int i : idx) {
+            int lo = 0, hi = nw;
+            if (hub_warps) { if (cls(i) != 2) hi = hub_warps; else lo = hub_warps; }
+            int w = lo;
+            for (int q = lo + 1; q < hi; ++q) if (load[q] < load[w]) w = q;
+            per_warp[w].push_back(i);
+            load[w] += cta_slots[i].cost;
+        }
+        size_t depth = 0;
+        for (auto &v : per_warp) depth = std::max(depth, v.size());
+        const long long base0 = (long long)slab.size();
+        for (size_t k = 0; k < depth; ++k)
+            for (int w = 0; w < nw; ++w) {
+                if (k >= per_warp[w].size()) {            // empty slot: nothing to gather, nothing to store
+                    slots.push_back(make_int4(0, 0, kSlotNormal, 0));
+                    for (int g = 0; g < rpw; ++g) slot_rows.push_back(-1);
+                    continue;
+                }
+                const Slot &sl = cta_slots[per_warp[w][k]];
+                slots.push_back(make_int4((int)((long long)slab.size() - base0), sl.L, sl.type | (sl.nparts << 8), sl.pbuf));
+                for (int g = 0; g < rpw; ++g) slot_rows.push_back(sl.rows[g]);
+                for (int j = 0; j < sl.L; ++j)
+                    for (int g = 0; g < rpw; ++g) {
+                        int2 e = make_int2((int)kPadOff, 0);
+                        int q = -1;
+                        if (sl.type == kSlotNormal) {
+                            const int r = sl.rows[g];
+                            if (r >= 0 && j < h_rp[r + 1] - h_rp[r]) q = h_rp[r] + j;
+                        } else {
+                            const int qq = sl.nz0 + j * rpw + g;          // round-robin over the lane groups
+                            if (qq < sl.nz1) q = qq;
+                        }
+                        if (q >= 0) e = make_int2((int)((unsigned)h_col[q] * (unsigned)rowb), float_bits(h_val[q]));
+                        slab.push_back(e);
+                    }
+            }
         slab_off[b + 1] = (long long)slab.size();
         slot_off[b + 1] = (int)slots.size();
         cap_entries = std::max(cap_entries, (int)(slab_off[b + 1] - slab_off[b]));
-        cap_slots = std::max(cap_slots, nslots);
+        cap_slots = std::max(cap_slots, (int)(depth * nw));
+        cap_parts = std::max(cap_parts, nparts_cta);
     }
     cap_entries = (cap_entries + 1) & ~1;
-    const size_t smem = (size_t)cap_entries * 8 + (size_t)cap_slots * 8 + (size_t)cap_slots * rpw * 4;
+    const size_t smem = (size_t)cap_entries * 8 + (size_t)cap_slots * 16 + (size_t)cap_parts * 2 * lanes * 16 + (size_t)cap_slots * rpw * 4;
     if (smem > (size_t)max_smem) return 0;
-    int threads = 0;
-    const void *fn = pick_dataflow(lanes, &threads);
     GLB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     GLB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, threads, smem));
@@ -767,12 +879,12 @@ static int plan_try_dataflow(glb_poisson_plan *p, const std::vector<int> &h_rp, 
 
     const size_t nslab = slab.size() ? slab.size() : 1, nsl = slots.size() ? slots.size() : 1;
     GLB_CUDA(cudaMalloc(&p->d_slabs, sizeof(int2) * nslab));
-    GLB_CUDA(cudaMalloc(&p->d_slots, sizeof(int2) * nsl));
+    GLB_CUDA(cudaMalloc(&p->d_slots, sizeof(int4) * nsl));
     GLB_CUDA(cudaMalloc(&p->d_slab_off, sizeof(long long) * (grid + 1)));
     GLB_CUDA(cudaMalloc(&p->d_slot_off, sizeof(int) * (grid + 1)));
     GLB_CUDA(cudaMalloc(&p->d_slot_rows, sizeof(int) * nsl * rpw));
     GLB_CUDA(cudaMemcpyAsync(p->d_slabs, slab.data(), sizeof(int2) * slab.size(), cudaMemcpyHostToDevice, st));
-    GLB_CUDA(cudaMemcpyAsync(p->d_slots, slots.data(), sizeof(int2) * slots.size(), cudaMemcpyHostToDevice, st));
+    GLB_CUDA(cudaMemcpyAsync(p->d_slots, slots.data(), sizeof(int4) * slots.size(), cudaMemcpyHostToDevice, st));
     GLB_CUDA(cudaMemcpyAsync(p->d_slab_off, slab_off.data(), sizeof(long long) * (grid + 1), cudaMemcpyHostToDevice, st));
     GLB_CUDA(cudaMemcpyAsync(p->d_slot_off, slot_off.data(), sizeof(int) * (grid + 1), cudaMemcpyHostToDevice, st));
     GLB_CUDA(cudaMemcpyAsync(p->d_slot_rows, slot_rows.data(), sizeof(int) * slot_rows.size(), cudaMemcpyHostToDevice, st));
@@ -780,7 +892,7 @@ static int plan_try_dataflow(glb_poisson_plan *p, const std::vector<int> &h_rp, 
     p->kind = GLB_POISSON_KIND_DATAFLOW;
     p->ldu = lanes * 4;
     p->grid = grid; p->threads = threads; p->fn = fn; p->smem_bytes = smem;
-    p->cap_entries = cap_entries; p->cap_slots = cap_slots;
+    p->cap_entries = cap_entries; p->cap_slots = cap_slots; p->cap_parts = cap_parts;
     p->ell_fill = slab.size() ? (double)nnz / (double)slab.size() : 1.0;
     if (getenv("GLB_POISSON_STATS")) {
         GLB_CUDA(cudaMalloc(&p->d_stats, 4 * sizeof(unsigned long long)));
@@ -984,7 +1096,8 @@ extern "C" GLB_API int glb_poisson_iterate(glb_poisson_plan *plan, const float *
         stamp_kernel<<<stream_blocks_p(plan->n * (plan->ldu / 4)), 256, 0, st>>>(d_u0, d_u1, plan->n * (plan->ldu / 4));
         void *args[] = {(void *)&plan->d_slabs, (void *)&plan->d_slab_off, (void *)&plan->d_slots, (void *)&plan->d_slot_off,
                         (void *)&plan->d_slot_rows, (void *)&d_Db, (void *)&d_u0, (void *)&d_u1, (void *)&T,
-                        (void *)&plan->cap_entries, (void *)&plan->cap_slots, (void *)&plan->d_stats, (void *)&nopoll};
+                        (void *)&plan->cap_entries, (void *)&plan->cap_slots, (void *)&plan->cap_parts, (void *)&plan->d_stats,
+                        (void *)&nopoll};
         if (plan->d_stats) GLB_CUDA(cudaMemsetAsync(plan->d_stats, 0, 4 * sizeof(unsigned long long), st));
         GLB_CUDA(cudaLaunchCooperativeKernel(plan->fn, dim3(plan->grid), dim3(plan->threads), args, plan->smem_bytes, st));
         if (plan->d_stats) {

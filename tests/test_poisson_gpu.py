@@ -222,26 +222,31 @@ def test_kernel_choice(dev):
     assert 0.8 < op.fill(10) <= 1.0                               # sliced-ELL padding stays small
 
 
-def test_dataflow_ragged_rows(dev):
-    """Empty rows, one very long row (hub), rows shorter than the unroll: the sliced-ELL slabs stay exact."""
+@pytest.mark.parametrize("c", [5, 10, 40])
+def test_dataflow_ragged_rows(dev, c):
+    """Empty rows, hub rows split over several warps (400 and 1700 nonzeros), rows shorter than the unroll: the
+    sliced-ELL slabs and the shared-memory partial sums stay exact for every lane mapping."""
     rng = np.random.default_rng(7)
-    n = 1500
+    n = 2500
     W = random_knn_graph(n, 3, seed=9).tolil()
     W[5, :] = 0; W[:, 5] = 0                                      # isolated node
-    hub = rng.choice(n, 400, replace=False)
-    hub = hub[(hub != 11) & (hub != 5)]
-    W[11, hub] = 0.5; W[hub, 11] = 0.5                            # one row with ~400 nonzeros
+    for hub_node, deg in ((11, 400), (12, 1700), (2499, 40)):
+        hub = rng.choice(n, deg, replace=False)
+        hub = hub[(hub != hub_node) & (hub != 5)]
+        W[hub_node, hub] = 0.5; W[hub, hub_node] = 0.5
     W = sparse.csr_matrix(W); W.eliminate_zeros()
     op = dev.PoissonOperator(W, kind="dataflow")
     # the operator's own fp32 P (row 5 and column 5 are empty, so the zero degree injects nothing)
     P = sparse.csr_matrix((op.P_val.cpu().numpy()[:op.nnz].astype(np.float64), op.col.cpu().numpy(),
                            op.rowptr.cpu().numpy()), shape=(n, n))
-    assert np.isfinite(P.data).all() and np.diff(P.indptr).max() > 300 and np.diff(P.indptr).min() == 0
-    Db64 = rng.normal(size=(n, 5))
+    assert np.isfinite(P.data).all() and np.diff(P.indptr).max() > 1500 and np.diff(P.indptr).min() == 0
+    Db64 = rng.normal(size=(n, c))
     ref = c_oracle.poisson_iterate(P, Db64, 12)
     Db = op.pack(Db64)
-    got = op.unpack(op.iterate(Db, 12)[0], 5).cpu().numpy()
+    got = op.unpack(op.iterate(Db, 12)[0], c).cpu().numpy()
     assert rel_err(got, ref) <= TOL
+    again = op.unpack(op.iterate(Db, 12)[0], c).cpu().numpy()
+    assert np.array_equal(got, again)                             # fixed summation order: run-to-run identical
 
 
 def test_mixing_T_matches_reference_rule(dev, blobs, moons):
@@ -296,7 +301,8 @@ def test_full_size_properties(dev, big):
     a = torch.zeros_like(A); b = torch.zeros_like(A)
     for _ in range(T):
         op.step(A, a, b); a, b = b, a
-    assert torch.equal(op.unpack(a, 10), uA)                     # dataflow kernel == T single steps, bit for bit
+    # same arithmetic as T single steps except for rows longer than 32 (summed by a whole warp in a fixed order)
+    assert float((op.unpack(a, 10) - uA).abs().max() / uA.abs().max()) <= 2e-6
 
 
 def test_full_size_through_host_api(gl, big):
