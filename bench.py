@@ -35,14 +35,69 @@ UNIT = "iterations/s"
 
 
 def build_workload(seed=0):
-    """Config 2 graph.  Until the GPU kNN search is wired into bench, the 70k-point kNN graph is built from
-    10 Gaussian blobs in R^8 with scipy's cKDTree (reference path for low d, ~10 s, untimed setup)."""
+    """The synthetic 70k-node graph BASELINE.md section 2 measured the reference on ("Poisson GD iterate, synthetic":
+    70 000 points, 10 Gaussian blobs in R^8, k=10, nnz = 1 004 292 - within 1 % of the real MNIST graph's 1 014 572
+    that section 3 quotes the roofline on), built with scipy's cKDTree exactly as the reference does for low d
+    (~10 s, untimed setup, identical for both arms).  The graph the GPU kNN search builds from 128-d features is
+    measured too (`other_rows`): isotropic 128-d Gaussians give hub nodes with > 1000 neighbours, which real
+    kNN graphs (MNIST: max 45) do not have."""
     from oracle import gl_oracle as orc
     from scipy import sparse
     X, labels = orc.synthetic_blobs(N_NODES, 8, c=N_CLASSES, seed=seed)
     ind, dist = orc.knnsearch(X.astype(np.float64), K_NN + 1, method="kdtree")
     W = orc.knn_weights(ind, dist, K_NN)
     return sparse.csr_matrix(W), labels
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel (ncu, profiles/r1_*_ncu_details.txt)
+NCU_DRAM_BYTES_PER_LAUNCH = {"dataflow": 18520576 + 1468672, "barrier": 17295360 + 296704, "step": None}
+
+
+def other_rows(W, labels, ti):
+    """Short measurements of the other rows of SURVEY.md 8(a) on this box (rank 0, untimed part of the bench line):
+    kNN build at config-2 size, the iterate on the 128-d (hub-heavy) graph that search produces, Laplace CG."""
+    import torch
+    import graphlearning_b200 as gl
+    from graphlearning_b200 import device as gdev, knn_gpu
+    from oracle import gl_oracle as orc
+    out = {}
+    try:
+        X, lab = orc.synthetic_blobs(N_NODES, 128, c=N_CLASSES, seed=0)
+        X = X.astype(np.float64)
+        knn_gpu.knnsearch_gpu(X[:4096], K_NN + 1)
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        ind, dist_ = knn_gpu.knnsearch_gpu(X, K_NN + 1)
+        torch.cuda.synchronize(); t = time.perf_counter() - t0
+        out["knn_70k_x_128_k10"] = {"seconds_host_to_host": t, "fp32_TFLOPs_on_2n2d": 2.0 * N_NODES * N_NODES * 128 / t / 1e12,
+                                    "fallback_rows": knn_gpu.last_stats.get("fallback_rows"),
+                                    "reference_cpu_seconds": "2460 (cKDTree, 1 thread, BASELINE.md section 2)"}
+        Wh = orc.knn_weights(ind, dist_, K_NN)
+        deg = np.diff(Wh.indptr)
+        th = orc.one_per_class(lab, rate=1, seed=0)
+        op = gdev.PoissonOperator(Wh)
+        Db = op.source_to_Db(orc.poisson_source(N_NODES, th, lab[th])[0])
+        u0 = torch.zeros_like(Db); u1 = torch.zeros_like(Db)
+        best = 1e30
+        for _ in range(3):
+            u0.zero_()
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            e0.record(); op.iterate(Db, 500, u0, u1); e1.record(); torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        b = algorithmic_bytes(N_NODES, Wh.nnz, N_CLASSES)
+        out["poisson_on_128d_graph"] = {"nnz": int(Wh.nnz), "max_row": int(deg.max()), "p99_row": int(np.percentile(deg, 99)),
+                                        "kernel": op.kind(N_CLASSES), "us_per_iteration": best * 1e3 / 500,
+                                        "iterations_per_s": 500 / (best * 1e-3), "achieved_GBs": b * 500 / (best * 1e-3) / 1e9}
+        m = gl.ssl.laplace(W)
+        t5 = orc.one_per_class(labels, rate=5, seed=0)
+        m.fit(t5, labels[t5])
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        m.fit(t5, labels[t5])
+        t = time.perf_counter() - t0
+        out["laplace_cg_fit"] = {"seconds": t, "cg_iterations": int(m.iterations), "gpu_launches": int(m.gpu_launches),
+                                 "note": "gl.ssl.laplace(W).fit, 5 labels/class, tol 1e-5; includes the scipy system assembly"}
+    except Exception as e:                                   # never lose the headline line over an extra
+        out["error"] = repr(e)
+    return out
 
 
 def algorithmic_bytes(n, nnz, c):
@@ -207,6 +262,7 @@ def run_ours(args, rank, world):
 
     value = world * iters * args.steps / (total_ms * 1e-3)
     e2e_value = world * iters * e2e_steps / e2e_s
+    extras = other_rows(W, labels, ti) if not args.no_extras else None
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
         peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json, burst copy)"
@@ -230,7 +286,10 @@ def run_ours(args, rank, world):
                          "L2 resident by construction",
                    "parallelism": "replicas x%d (independent label sets, no collective)" % world},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src,
+                     "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get(kind), "peak_source": peak_src,
+                     "traffic_note": "dram__bytes_read+write of one launch from the ncu capture under profiles/ (T=100 "
+                                     "iterations per launch there; the traffic is the one-time load of slabs, Db and u - every "
+                                     "iteration after the first runs out of L2, which is why achieved > traffic/time)",
                      "bytes_per_iteration": algorithmic_bytes(n, nnz, c)},
         "cpu_baseline": {"value": cpu_iters / cpu_s, "unit": UNIT, "cores": 1, "kind": "port",
                          "sample": "%d iterations of the reference loop (ssl.py:667-669, scipy csr_matvecs fp64) on the "
@@ -241,6 +300,7 @@ def run_ours(args, rank, world):
                 "first_fit_value": iters / cold_s, "graph_h2d_bytes_once": int(graph_h2d)},
         "gpu_launches": int(launches),
         "clocks": clocks,
+        "other_rows": extras,
     }
     assert np.isfinite(u_host).all()
     print(json.dumps(out), flush=True)
@@ -257,6 +317,7 @@ def main():
     ap.add_argument("--iters", type=int, default=1000, help="Poisson iterations per step (one persistent launch)")
     ap.add_argument("--ref-iters", type=int, default=100, help="iterations per step of the CPU reference arm")
     ap.add_argument("--cpu-iters", type=int, default=200, help="bounded CPU sample inside the GPU arm")
+    ap.add_argument("--no-extras", action="store_true", help="skip the short measurements of the other 8(a) rows")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))

@@ -332,7 +332,8 @@ __global__ void __launch_bounds__(THREADS, 1)
 poisson_dataflow_kernel(const int2 *__restrict__ slabs, const long long *__restrict__ slab_off,
                         const int4 *__restrict__ slots, const int *__restrict__ slot_off,
                         const int *__restrict__ slot_rows, const float *__restrict__ Db, float *u0, float *u1, int T,
-                        int cap_entries, int cap_slots, int cap_parts, unsigned long long *stats, int nopoll)
+                        int cap_entries, int cap_slots, int cap_parts, unsigned long long *stats, int nopoll,
+                        unsigned *start_gate, int gate_every)
 {
     constexpr int RPW = 32 / LANES;              // rows per warp pass = slice height of the ELL slab
     constexpr int NW = THREADS / 32;
@@ -365,12 +366,34 @@ poisson_dataflow_kernel(const int2 *__restrict__ slabs, const long long *__restr
         s_rows[i] = r;
     }
     __syncthreads();
+    // One-time start gate: all CTAs enter iteration 0 together.  Without it the CTAs leave this prologue up to a few
+    // microseconds apart and about one launch in seven never recovers from that skew (consumers stay on the heels
+    // of their producers and every batch re-polls: 26 instead of 6.3 us/iteration, profiles/r1_stability.txt).
+    if (start_gate) {
+        if (threadIdx.x == 0) {
+            red_relaxed_add(start_gate, 1u);
+            while (ld_relaxed(start_gate) < gridDim.x) { }
+        }
+        __syncthreads();
+    }
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane / LANES, li = lane % LANES;
     unsigned long long n_poll = 0, n_badbatch = 0;      // stats only (GLB_POISSON_STATS)
     const long long clk0 = clock64();
     for (int t = 0; t < T; ++t) {
+        // Re-alignment gate every gate_every iterations: the low-polling regime is metastable (a CTA that falls behind
+        // drags its consumers into re-polling and they theirs); bringing all CTAs back into phase - exactly what
+        // the start gate does - ends such an episode.  ~3 us per gate, amortised over gate_every iterations.
+        if (start_gate && gate_every > 0 && t > 0 && t % gate_every == 0) {
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                red_relaxed_add(start_gate, 1u);
+                const unsigned want = gridDim.x * (unsigned)(t / gate_every + 1);
+                while (ld_relaxed(start_gate) < want) { }
+            }
+            __syncthreads();
+        }
         const char *in = reinterpret_cast<const char *>(((t & 1) && !(nopoll & 4)) ? u1 : u0) + li * 16;
         char *out = reinterpret_cast<char *>(((t & 1) && !(nopoll & 4)) ? u0 : u1) + li * 16;
         const unsigned expect = 1u + (unsigned)t;
@@ -632,6 +655,7 @@ struct glb_poisson_plan {
     int cap_entries = 0, cap_slots = 0, cap_parts = 0;
     double ell_fill = 0.0;              // nnz / stored entries of the slabs
     float tuned_ms[2] = {0.f, 0.f};     // AUTO: measured ms of the trial run, {dataflow, barrier}
+    unsigned *d_gate = nullptr;         // dataflow kernel: start gate counter
     unsigned long long *d_stats = nullptr;   // GLB_POISSON_STATS=1: {re-polls, batches that had to poll, max warp cycles, CTAs}
 };
 
@@ -894,6 +918,7 @@ static int plan_try_dataflow(glb_poisson_plan *p, const std::vector<int> &h_rp, 
     p->grid = grid; p->threads = threads; p->fn = fn; p->smem_bytes = smem;
     p->cap_entries = cap_entries; p->cap_slots = cap_slots; p->cap_parts = cap_parts;
     p->ell_fill = slab.size() ? (double)nnz / (double)slab.size() : 1.0;
+    GLB_CUDA(cudaMalloc(&p->d_gate, sizeof(unsigned)));
     if (getenv("GLB_POISSON_STATS")) {
         GLB_CUDA(cudaMalloc(&p->d_stats, 4 * sizeof(unsigned long long)));
     }
@@ -1028,7 +1053,7 @@ extern "C" GLB_API int glb_poisson_plan_destroy(glb_poisson_plan *plan)
     if (!plan) return 0;
     cudaFree(plan->d_counter);  cudaFree(plan->d_cta_rows);
     cudaFree(plan->d_slabs);    cudaFree(plan->d_slots);
-    cudaFree(plan->d_slab_off); cudaFree(plan->d_slot_off); cudaFree(plan->d_slot_rows); cudaFree(plan->d_stats);
+    cudaFree(plan->d_slab_off); cudaFree(plan->d_slot_off); cudaFree(plan->d_slot_rows); cudaFree(plan->d_stats); cudaFree(plan->d_gate);
     delete plan;
     return 0;
 }
@@ -1093,11 +1118,14 @@ extern "C" GLB_API int glb_poisson_iterate(glb_poisson_plan *plan, const float *
     const float *val = plan->d_val;
     if (plan->kind == GLB_POISSON_KIND_DATAFLOW) {
         int nopoll = getenv("GLB_POISSON_NOPOLL") ? atoi(getenv("GLB_POISSON_NOPOLL")) : 0;     // experiment only: ignores the epoch words (results are wrong)
+        unsigned *gate = getenv("GLB_POISSON_NOGATE") ? nullptr : plan->d_gate;
+        if (gate) GLB_CUDA(cudaMemsetAsync(gate, 0, sizeof(unsigned), st));
+        int gate_every = getenv("GLB_POISSON_GATE_EVERY") ? atoi(getenv("GLB_POISSON_GATE_EVERY")) : 32;
         stamp_kernel<<<stream_blocks_p(plan->n * (plan->ldu / 4)), 256, 0, st>>>(d_u0, d_u1, plan->n * (plan->ldu / 4));
         void *args[] = {(void *)&plan->d_slabs, (void *)&plan->d_slab_off, (void *)&plan->d_slots, (void *)&plan->d_slot_off,
                         (void *)&plan->d_slot_rows, (void *)&d_Db, (void *)&d_u0, (void *)&d_u1, (void *)&T,
                         (void *)&plan->cap_entries, (void *)&plan->cap_slots, (void *)&plan->cap_parts, (void *)&plan->d_stats,
-                        (void *)&nopoll};
+                        (void *)&nopoll, (void *)&gate, (void *)&gate_every};
         if (plan->d_stats) GLB_CUDA(cudaMemsetAsync(plan->d_stats, 0, 4 * sizeof(unsigned long long), st));
         GLB_CUDA(cudaLaunchCooperativeKernel(plan->fn, dim3(plan->grid), dim3(plan->threads), args, plan->smem_bytes, st));
         if (plan->d_stats) {
