@@ -85,7 +85,7 @@ def other_rows(W, labels, ti):
             best = min(best, e0.elapsed_time(e1))
         b = algorithmic_bytes(N_NODES, Wh.nnz, N_CLASSES)
         out["poisson_on_128d_graph"] = {"nnz": int(Wh.nnz), "max_row": int(deg.max()), "p99_row": int(np.percentile(deg, 99)),
-                                        "kernel": op.kind(N_CLASSES), "us_per_iteration": best * 1e3 / 500,
+                                        "kernel": op.kind(N_CLASSES), "gate_every": op.gate(N_CLASSES), "us_per_iteration": best * 1e3 / 500,
                                         "iterations_per_s": 500 / (best * 1e-3), "achieved_GBs": b * 500 / (best * 1e-3) / 1e9}
         m = gl.ssl.laplace(W)
         t5 = orc.one_per_class(labels, rate=5, seed=0)
@@ -282,6 +282,7 @@ def run_ours(args, rank, world):
                    "n": int(n), "nnz": int(nnz), "classes": c, "iterations_per_step": iters, "ldu": ldu,
                    "kernel": {"dataflow": "poisson_dataflow_kernel", "barrier": "poisson_persistent_kernel",
                               "step": "poisson_step_kernel"}[kind],
+                   "gate_every": op.gate(c),
                    "l2": "flushed between steps (256 MiB write); inside a step the 16.8 MB working set is "
                          "L2 resident by construction",
                    "parallelism": "replicas x%d (independent label sets, no collective)" % world},

@@ -655,7 +655,9 @@ struct glb_poisson_plan {
     int cap_entries = 0, cap_slots = 0, cap_parts = 0;
     double ell_fill = 0.0;              // nnz / stored entries of the slabs
     float tuned_ms[2] = {0.f, 0.f};     // AUTO: measured ms of the trial run, {dataflow, barrier}
+    int tuned_gate = 32;
     unsigned *d_gate = nullptr;         // dataflow kernel: start gate counter
+    int gate_every = 32;                // dataflow kernel: iterations between re-alignment gates (tuned at plan time)
     unsigned long long *d_stats = nullptr;   // GLB_POISSON_STATS=1: {re-polls, batches that had to poll, max warp cycles, CTAs}
 };
 
@@ -964,7 +966,7 @@ static int plan_try_barrier(glb_poisson_plan *p, const std::vector<int> &h_rp, i
 // device time of a short trial run of the plan's kernel on an all-zero problem (second of two launches)
 static int plan_time(glb_poisson_plan *p, float *ms, cudaStream_t st)
 {
-    const int T = 32;
+    const int T = 96;
     const size_t bytes = (size_t)p->n * p->ldu * sizeof(float);
     float *buf = nullptr;
     GLB_CUDA(cudaMalloc(&buf, 3 * bytes));
@@ -1019,14 +1021,29 @@ extern "C" GLB_API int glb_poisson_plan_create(glb_poisson_plan **plan, const in
             if ((rc = plan_try_dataflow(p, h_rp, sms, max_smem, st))) return rc;
         if (p->kind == GLB_POISSON_KIND_STEP && (kind == GLB_POISSON_KIND_AUTO || kind == GLB_POISSON_KIND_BARRIER))
             if ((rc = plan_try_barrier(p, h_rp, sms, max_smem, st))) return rc;
-        if (kind == GLB_POISSON_KIND_AUTO && p->kind == GLB_POISSON_KIND_DATAFLOW && !getenv("GLB_POISSON_NOTUNE")) {
-            // Measure, don't guess: the dataflow kernel wins when every SM has enough rows to keep its producers
-            // ahead of its consumers, the barrier kernel on small or oddly shaped graphs.  Time both on zeros.
+        const bool tune = !getenv("GLB_POISSON_NOTUNE");
+        float ms_df = 0.f;
+        if (p->kind == GLB_POISSON_KIND_DATAFLOW && tune && !getenv("GLB_POISSON_GATE_EVERY")) {
+            // Measure, don't guess.  Gate period of the dataflow kernel: graphs with hub rows (every hub is a meeting
+            // point of hundreds of producers) run best with a gate every few iterations, hub-free graphs with rare gates.
+            const int cand[3] = {32, 4, 1};
+            float best = 0.f;
+            for (int i = 0; i < 3; ++i) {
+                p->gate_every = cand[i];
+                float ms = 0.f;
+                if ((rc = plan_time(p, &ms, st))) return rc;
+                if (i == 0 || ms < best) { best = ms; ms_df = ms; p->tuned_gate = cand[i]; }
+            }
+            p->gate_every = p->tuned_gate;
+        }
+        if (kind == GLB_POISSON_KIND_AUTO && p->kind == GLB_POISSON_KIND_DATAFLOW && tune) {
+            // ... and the dataflow kernel against the barrier kernel (small graphs: too few rows per SM to hide the
+            // producer-consumer latency).  Both timed on zeros.
             glb_poisson_plan *alt = nullptr;
             rc = glb_poisson_plan_create(&alt, d_rowptr, d_col, d_val, n, nnz, c, GLB_POISSON_KIND_BARRIER, stream);
             if (rc == 0) {
-                float ms_df = 0.f, ms_bar = 0.f;
-                rc = plan_time(p, &ms_df, st);
+                float ms_bar = 0.f;
+                if (ms_df == 0.f) rc = plan_time(p, &ms_df, st);
                 if (rc == 0) rc = plan_time(alt, &ms_bar, st);
                 if (rc) { glb_poisson_plan_destroy(alt); return rc; }
                 if (ms_bar < ms_df) {              // keep the barrier plan: swap contents, destroy the dataflow one
@@ -1061,6 +1078,7 @@ extern "C" GLB_API int glb_poisson_plan_destroy(glb_poisson_plan *plan)
 extern "C" GLB_API int glb_poisson_plan_kind(const glb_poisson_plan *plan) { return plan ? plan->kind : GLB_E_INVALID; }
 extern "C" GLB_API int glb_poisson_plan_ld(const glb_poisson_plan *plan) { return plan ? plan->ldu : GLB_E_INVALID; }
 extern "C" GLB_API double glb_poisson_plan_fill(const glb_poisson_plan *plan) { return plan ? plan->ell_fill : 0.0; }
+extern "C" GLB_API int glb_poisson_plan_gate(const glb_poisson_plan *plan) { return plan && plan->kind == GLB_POISSON_KIND_DATAFLOW ? plan->gate_every : 0; }
 
 extern "C" GLB_API int glb_poisson_pack(const glb_poisson_plan *plan, const double *d_src, const double *d_deg,
                                         const int32_t *d_perm, float *d_dst, void *stream)
@@ -1120,7 +1138,7 @@ extern "C" GLB_API int glb_poisson_iterate(glb_poisson_plan *plan, const float *
         int nopoll = getenv("GLB_POISSON_NOPOLL") ? atoi(getenv("GLB_POISSON_NOPOLL")) : 0;     // experiment only: ignores the epoch words (results are wrong)
         unsigned *gate = getenv("GLB_POISSON_NOGATE") ? nullptr : plan->d_gate;
         if (gate) GLB_CUDA(cudaMemsetAsync(gate, 0, sizeof(unsigned), st));
-        int gate_every = getenv("GLB_POISSON_GATE_EVERY") ? atoi(getenv("GLB_POISSON_GATE_EVERY")) : 32;
+        int gate_every = getenv("GLB_POISSON_GATE_EVERY") ? atoi(getenv("GLB_POISSON_GATE_EVERY")) : plan->gate_every;
         stamp_kernel<<<stream_blocks_p(plan->n * (plan->ldu / 4)), 256, 0, st>>>(d_u0, d_u1, plan->n * (plan->ldu / 4));
         void *args[] = {(void *)&plan->d_slabs, (void *)&plan->d_slab_off, (void *)&plan->d_slots, (void *)&plan->d_slot_off,
                         (void *)&plan->d_slot_rows, (void *)&d_Db, (void *)&d_u0, (void *)&d_u1, (void *)&T,

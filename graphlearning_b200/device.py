@@ -144,6 +144,9 @@ class PoissonOperator:
     def fill(self, c=None):
         return float(_lib.load().glb_poisson_plan_fill(self.plan(c)))
 
+    def gate(self, c=None):
+        return int(_lib.load().glb_poisson_plan_gate(self.plan(c)))
+
     def is_persistent(self, c=None):
         return self.kind(c) != "step"
 

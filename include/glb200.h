@@ -107,6 +107,8 @@ GLB_API int glb_poisson_plan_kind(const glb_poisson_plan *plan);
 GLB_API int glb_poisson_plan_ld(const glb_poisson_plan *plan);
 /* nnz / stored entries of the dataflow kernel's sliced-ELL slabs (1.0 = no padding; 0 for other kinds) */
 GLB_API double glb_poisson_plan_fill(const glb_poisson_plan *plan);
+/* iterations between two re-alignment gates of the dataflow kernel (tuned at plan time; 0 for other kinds) */
+GLB_API int glb_poisson_plan_gate(const glb_poisson_plan *plan);
 
 /* d_dst (n x ld fp32, plan layout) <- d_src (n x c fp64), each row divided by d_deg[row] when d_deg is not
  * NULL (Db = D^-1 source, ssl.py:636).  d_perm (may be NULL) is a locality ordering: device row r holds the

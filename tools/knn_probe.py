@@ -34,4 +34,4 @@ for (n, d, k) in ((70000, 128, 10), (60000, 512, 20)):
             e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
             e0.record(); op.iterate(Db, 500, u0, u1); e1.record(); torch.cuda.synchronize()
             best = min(best, e0.elapsed_time(e1))
-        print("  poisson %-8s -> %-8s fill %.3f  %.3f us/iter" % (kind, op.kind(10), op.fill(10), best * 1e3 / 500), flush=True)
+        print("  poisson %-8s -> %-8s gate %d fill %.3f  %.3f us/iter" % (kind, op.kind(10), op.gate(10), op.fill(10), best * 1e3 / 500), flush=True)
