@@ -52,6 +52,10 @@ SIGNATURES = {
                              c_void_p, c_void_p, c_int64, POINTER(c_int64), POINTER(c_double), POINTER(c_int), c_void_p]),
     "glb_cg_host": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int, c_double, c_int64,
                             c_void_p, POINTER(c_int64), POINTER(c_double), POINTER(c_int)]),
+    "glb_lp_iterate_host": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_double, c_int,
+                                    c_double, c_int, c_int, c_int, POINTER(c_int), POINTER(c_int)]),
+    "glb_lip_iterate_host": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_double, c_int,
+                                     c_double, c_double, c_int, c_int, c_int, POINTER(c_int), POINTER(c_int)]),
     "glb_poisson_gd_host": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int, c_void_p, c_int64,
                                     c_int, c_int, c_void_p, POINTER(c_int), POINTER(c_int)]),
 }

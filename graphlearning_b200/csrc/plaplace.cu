@@ -1,0 +1,502 @@
+// plaplace.cu - the p-Laplace / AMLE neighbour sweeps of the reference's C extension on sm_100a.
+//
+// Replaces c_code/lp_iterate.cpp (reached through cextensions.lp_iterate / lip_iterate,
+// c_code/cextensions.cpp:19-107, from graph.plaplace / graph.amle, graphlearning/graph.py:1177-1332):
+//   lp_iterate_main            :35-125   Jacobi sweeps of an upper and a lower barrier function
+//   lip_iterate_main           :129-187  Gauss-Seidel sweeps, game-theoretic p-Laplacian with 0/1 weights in L_inf
+//   lip_iterate_weighted_main  :190-259  Gauss-Seidel sweeps, weighted infinity Laplacian by 30-step bisection
+//
+// All arithmetic is fp64 with explicit round-to-nearest intrinsics (no FMA contraction) and every per-row sum
+// runs in stored order, so the iterates are BIT-IDENTICAL to the reference's (built without -ffast-math).
+//
+// Jacobi (lp): one persistent cooperative launch, one thread per row and round, (upper, lower) interleaved as one
+// 16-byte cell so a neighbour costs one gather for both functions; one grid barrier per sweep which also carries
+// the sweep's error (max(uu - ul)) for the reference's stopping rule `err < tol && it > 10`.  The reference swaps
+// its buffer pointers after every sweep (:116-123), so the caller's arrays hold the result of the last ODD sweep;
+// the two device buffers play exactly the same roles and buffer 0 is what is returned.
+//
+// Gauss-Seidel (lip): the reference updates u in place in row order, so row i sees the NEW value of neighbours j < i
+// and the OLD value of neighbours j >= i.  That is a dependency DAG (depth 37 on the 70k-node benchmark graph), not
+// a sequential chain.  The kernel runs it as a dataflow: every value lives in a 16-byte cell {value, version}
+// written and read as ONE 16-byte transaction at L2; sweep t reads neighbours j >= i from buffer t&1 (complete
+// since the barrier that ended sweep t-1) and neighbours j < i from buffer (t+1)&1, re-polling a cell until its
+// version is t+1.  Threads own rows in increasing order, so the smallest unfinished (sweep,row) never waits:
+// no deadlock (all CTAs co-resident: cooperative launch).  One grid barrier per sweep carries the error for the
+// stopping rule `err < tol && it > 20`.  Result: exactly the reference's sequential sweep, at any sweep count.
+#include <math.h>
+#include <vector>
+#include "common.cuh"
+
+namespace glb {
+namespace {
+
+struct __align__(16) Cell { double a; unsigned long long b; };     // lip: {u, version};  lp: {uu, bits(ul)}
+
+__device__ __forceinline__ Cell ld_cell(const Cell *p)
+{
+    Cell c;
+    unsigned long long x;
+    asm volatile("ld.relaxed.gpu.global.v2.u64 {%0,%1}, [%2];" : "=l"(x), "=l"(c.b) : "l"(p) : "memory");
+    c.a = __longlong_as_double((long long)x);
+    return c;
+}
+__device__ __forceinline__ void st_cell(Cell *p, double a, unsigned long long b)
+{
+    asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1,%2};" ::"l"(p), "l"((unsigned long long)__double_as_longlong(a)), "l"(b) : "memory");
+}
+__device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned *p)
+{
+    unsigned v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void fence_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+
+// Grid barrier that also returns the maximum of one non-negative double per thread (the sweep's error).
+// slots[3]: sweep t accumulates into slots[t % 3]; slot (t+1) % 3 is cleared during sweep t (its last readers left
+// it before the barrier that ended sweep t-1).
+__device__ __forceinline__ double barrier_max(double mine, unsigned long long *slots, unsigned *counter, unsigned t)
+{
+    __shared__ unsigned long long s_max;
+    unsigned long long bits = (unsigned long long)__double_as_longlong(mine);    // mine >= 0: bit order = value order
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, bits, o);
+        bits = other > bits ? other : bits;
+    }
+    if (threadIdx.x == 0) s_max = 0ull;
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0 && bits) atomicMax(&s_max, bits);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (blockIdx.x == 0) slots[(t + 1) % 3] = 0ull;
+        if (s_max) atomicMax(slots + t % 3, s_max);
+        fence_gpu();
+        asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(counter), "r"(1u) : "memory");
+        const unsigned want = (t + 1) * gridDim.x;
+        while (ld_relaxed_u32(counter) < want) { }
+        fence_gpu();
+        s_max = ld_relaxed_u64(slots + t % 3);
+    }
+    __syncthreads();
+    const double r = __longlong_as_double((long long)s_max);
+    __syncthreads();                                   // s_max is rewritten by the next call
+    return r;
+}
+
+// row offsets from the row-sorted COO row index: start[i] = first k with row[k] >= i   (lp_iterate.cpp:48-57)
+__global__ void __launch_bounds__(256) row_start_kernel(const int *__restrict__ row, int M, int n, int *__restrict__ start)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i <= n; i += gridDim.x * blockDim.x) {
+        int lo = 0, hi = M;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (__ldg(row + mid) < i) lo = mid + 1; else hi = mid;
+        }
+        start[i] = lo;
+    }
+}
+
+// status[0] |= 1 when the row index is not sorted / out of range, |= 2 when a neighbour index is out of range
+__global__ void __launch_bounds__(256) check_coo_kernel(const int *__restrict__ row, const int *__restrict__ nbr, int M, int n, int *status)
+{
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < M; k += gridDim.x * blockDim.x) {
+        const int r = row[k];
+        if (r < 0 || r >= n || (k > 0 && row[k - 1] > r)) atomicOr(status, 1);
+        const int j = nbr[k];
+        if (j < 0 || j >= n) atomicOr(status, 2);
+    }
+}
+
+__global__ void __launch_bounds__(256) max_weight_kernel(const double *__restrict__ W, int M, unsigned long long *out)
+{
+    double mx = 0.0;                                                       // maxWGT starts at 0 (:60-62)
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < M; k += gridDim.x * blockDim.x) {
+        const double w = W[k];
+        if (w > mx) mx = w;
+    }
+    if (mx > 0.0) atomicMax(out, (unsigned long long)__double_as_longlong(mx));
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Jacobi: lp_iterate_main
+// ------------------------------------------------------------------------------------------------------------
+struct LpArgs {
+    const int *start, *nbr;
+    const double *W;
+    const int *lab;                 // lab[i] = index into labval or -1
+    const double *labval;
+    Cell *c0, *c1;
+    double *invdeg;
+    unsigned long long *slots;      // [3] error slots + [1] max weight at slots[3]
+    unsigned *counter;
+    int *sweeps;
+    int n, T;
+    double p, tol;
+};
+
+__global__ void __launch_bounds__(256) lp_jacobi_kernel(LpArgs A)
+{
+    const int NT = gridDim.x * blockDim.x, gt = blockIdx.x * blockDim.x + threadIdx.x;
+    const double alpha = __ddiv_rn(1.0, A.p);
+    const double delta = __dsub_rn(1.0, __ddiv_rn(2.0, A.p));
+    double dt = __ddiv_rn(0.9, __dadd_rn(alpha, __dmul_rn(2.0, delta)));
+    dt = __ddiv_rn(dt, __longlong_as_double((long long)A.slots[3]));
+    for (int i = gt; i < A.n; i += NT) {                                   // invdeg[i] = alpha / sum_j W_ij (:47-58)
+        double s = 0.0;
+        for (int k = A.start[i]; k < A.start[i + 1]; ++k) s = __dadd_rn(s, A.W[k]);
+        A.invdeg[i] = __ddiv_rn(alpha, s);
+    }
+    int it = 0, done = 0;
+    for (; it < A.T; ++it) {
+        const Cell *cur = (it & 1) ? A.c1 : A.c0;
+        Cell *nxt = (it & 1) ? A.c0 : A.c1;
+        double err = 0.0;
+        for (int i = gt; i < A.n; i += NT) {
+            const Cell me = ld_cell(cur + i);
+            const double uu = me.a, ul = __longlong_as_double((long long)me.b);
+            double minu = 0.0, maxu = 0.0, sumu = 0.0, minl = 0.0, maxl = 0.0, suml = 0.0;
+            const int e = A.start[i + 1];
+            for (int k = A.start[i]; k < e; ++k) {
+                const Cell c = ld_cell(cur + __ldg(A.nbr + k));
+                const double w = __ldg(A.W + k);
+                const double du = __dmul_rn(w, __dsub_rn(c.a, uu));
+                const double dl = __dmul_rn(w, __dsub_rn(__longlong_as_double((long long)c.b), ul));
+                minu = du < minu ? du : minu;  maxu = du > maxu ? du : maxu;  sumu = __dadd_rn(sumu, du);
+                minl = dl < minl ? dl : minl;  maxl = dl > maxl ? dl : maxl;  suml = __dadd_rn(suml, dl);
+            }
+            const double idg = A.invdeg[i];
+            double vu = __dadd_rn(uu, __dmul_rn(dt, __dadd_rn(__dmul_rn(idg, sumu), __dmul_rn(delta, __dadd_rn(minu, maxu)))));
+            double vl = __dadd_rn(ul, __dmul_rn(dt, __dadd_rn(__dmul_rn(idg, suml), __dmul_rn(delta, __dadd_rn(minl, maxl)))));
+            const double d = __dsub_rn(uu, ul);
+            if (d > err) err = d;
+            const int l = A.lab[i];
+            if (l >= 0) vu = vl = A.labval[l];                             // Dirichlet values into the new buffer (:106-110)
+            st_cell(nxt + i, vu, (unsigned long long)__double_as_longlong(vl));
+        }
+        const double gerr = barrier_max(err, A.slots, A.counter, (unsigned)it);
+        if (gerr < A.tol && it > 10) { done = it + 1; break; }
+    }
+    if (gt == 0) *A.sweeps = done ? done : it;
+}
+
+__global__ void __launch_bounds__(256) lp_pack_kernel(const double *uu, const double *ul, Cell *c0, Cell *c1, int n)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        c0[i].a = uu[i]; c0[i].b = (unsigned long long)__double_as_longlong(ul[i]);
+        c1[i].a = 0.0;   c1[i].b = 0ull;                                   // the reference's vu, vl start at 0 (:69-70)
+    }
+}
+__global__ void __launch_bounds__(256) lp_unpack_kernel(const Cell *c0, double *uu, double *ul, int n)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        uu[i] = c0[i].a; ul[i] = __longlong_as_double((long long)c0[i].b);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Gauss-Seidel dataflow: lip_iterate_main / lip_iterate_weighted_main
+// ------------------------------------------------------------------------------------------------------------
+struct LipArgs {
+    const int *start, *nbr;
+    const double *W;
+    const int *lab;
+    Cell *c0, *c1;
+    double *u_out;
+    unsigned long long *slots;
+    unsigned *counter;
+    int *sweeps;
+    int n, M, T;
+    double tol, alpha, beta;
+};
+
+constexpr unsigned long long kVerFixed = ~0ull;      // Dirichlet rows: valid in every sweep
+constexpr int kLipCap = 32;                          // neighbour values kept in local memory for the bisection
+
+// One row per lane and round.  A lane must never spin on a cell: its producer may be another lane of the same warp
+// (a lower-numbered neighbour in the same round), and a lane that leaves a spin loop waits at the loop's
+// reconvergence point for the lanes still inside.  So the warp runs a retry loop instead: per pass every pending lane
+// consumes, IN STORED ORDER, as many of its neighbours as are ready (8 gathers in flight), keeps its running
+// (min, max, sum, degree) in registers, and finishes the row once all neighbours have been consumed.
+template <bool WEIGHTED>
+__global__ void __launch_bounds__(256) lip_gauss_seidel_kernel(LipArgs A)
+{
+    const int NT = gridDim.x * blockDim.x, gt = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const double qnan = __longlong_as_double(0x7ff8000000000000ll);
+    int it = 0, done = 0;
+    for (; it < A.T; ++it) {
+        const Cell *cur = (it & 1) ? A.c1 : A.c0;
+        Cell *nxt = (it & 1) ? A.c0 : A.c1;
+        const unsigned long long want = (unsigned long long)it + 1ull;
+        double err = 0.0;
+        for (int i0 = gt - lane; i0 < A.n; i0 += NT) {                       // warp-uniform trip count
+            const int i = i0 + lane;
+            bool pending = i < A.n && A.lab[i] < 0;
+            int s = 0, L = 0, k = 0;
+            double uv[kLipCap];
+            double minu = 0.0, maxu = 0.0, sumu = 0.0, deg = 0.0;
+            bool empty_row = false;
+            if (pending) {
+                s = A.start[i];
+                L = A.start[i + 1] - s;
+                if (L == 0) {
+                    // the reference reads u[I[start[i]]] (the next row's first neighbour) even for an empty row (:163, :223):
+                    // treat that entry as the row's only "neighbour" for min/max and skip the sums
+                    empty_row = true;
+                    if (s < A.M) L = 1; else { minu = maxu = qnan; }
+                }
+            }
+            while (__any_sync(0xffffffffu, pending)) {
+                if (!pending) continue;
+                int jj[8];
+                Cell c[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    jj[q] = k + q < L ? __ldg(A.nbr + s + k + q) : -1;
+                    if (jj[q] >= 0) c[q] = ld_cell((jj[q] < i ? nxt : cur) + jj[q]);
+                }
+                bool stop = false;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    if (stop || jj[q] < 0) continue;
+                    if (jj[q] < i && c[q].b < want) { stop = true; continue; }   // producer not there yet: retry from here
+                    const double v = c[q].a;
+                    if (k == 0) { minu = v; maxu = v; }
+                    if (!WEIGHTED && !empty_row) {
+                        const double w = __ldg(A.W + s + k);
+                        sumu = __dadd_rn(sumu, __dmul_rn(w, v));
+                        deg = __dadd_rn(deg, w);
+                    }
+                    minu = v < minu ? v : minu;
+                    maxu = v > maxu ? v : maxu;
+                    if (WEIGHTED && k < kLipCap) uv[k] = v;
+                    ++k;
+                }
+                if (k < L) continue;
+                double ne;
+                if (!WEIGHTED) {
+                    ne = __dadd_rn(__ddiv_rn(__dmul_rn(A.alpha, sumu), deg), __ddiv_rn(__dmul_rn(A.beta, __dadd_rn(minu, maxu)), 2.0));
+                } else {
+                    double a = minu, b = maxu;
+                    const int Lr = empty_row ? 0 : L;
+                    for (int r = 0; r < 30; ++r) {                         // bisection on min_j w(t-u_j) + max_j w(t-u_j) (:229-243)
+                        const double tm = __ddiv_rn(__dadd_rn(a, b), 2.0);
+                        double minw = 0.0, maxw = 0.0;
+                        for (int kk = 0; kk < Lr; ++kk) {
+                            double v;
+                            if (kk < kLipCap) v = uv[kk];
+                            else {                                         // beyond the local cache: final for this sweep, read again
+                                const int j = __ldg(A.nbr + s + kk);
+                                v = ld_cell((j < i ? nxt : cur) + j).a;
+                            }
+                            const double d = __dmul_rn(__ldg(A.W + s + kk), __dsub_rn(tm, v));
+                            minw = d < minw ? d : minw;
+                            maxw = d > maxw ? d : maxw;
+                        }
+                        if (__dadd_rn(minw, maxw) > 0.0) b = tm; else a = tm;
+                    }
+                    ne = __ddiv_rn(__dadd_rn(a, b), 2.0);
+                }
+                double d = __dsub_rn(ld_cell(cur + i).a, ne);
+                d = d < 0.0 ? -d : d;
+                if (d > err) err = d;
+                st_cell(nxt + i, ne, want);
+                pending = false;
+            }
+        }
+        const double gerr = barrier_max(err, A.slots, A.counter, (unsigned)it);
+        if (gerr < A.tol && it > 20) { done = it + 1; break; }
+    }
+    const int nsweeps = done ? done : it;
+    const Cell *fin = (nsweeps & 1) ? A.c1 : A.c0;      // sweep t writes buffer (t+1)&1
+    for (int i = gt; i < A.n; i += NT) A.u_out[i] = ld_cell(fin + i).a;
+    if (gt == 0) *A.sweeps = nsweeps;
+}
+
+__global__ void __launch_bounds__(256) lip_pack_kernel(const double *u, const int *lab, const double *labval, Cell *c0, Cell *c1, int n)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int l = lab[i];
+        if (l >= 0) {
+            c0[i].a = labval[l]; c0[i].b = kVerFixed;
+            c1[i].a = labval[l]; c1[i].b = kVerFixed;
+        } else {
+            c0[i].a = u[i]; c0[i].b = 0ull;
+            c1[i].a = u[i]; c1[i].b = 0ull;
+        }
+    }
+}
+
+struct Arena {
+    std::vector<void *> ptrs;
+    ~Arena() { for (void *p : ptrs) cudaFree(p); }
+    template <typename T>
+    cudaError_t alloc(T **p, size_t count)
+    {
+        void *q = nullptr;
+        cudaError_t e = cudaMalloc(&q, (count ? count : 1) * sizeof(T));
+        if (e == cudaSuccess) ptrs.push_back(q);
+        *p = (T *)q;
+        return e;
+    }
+};
+
+int coop_grid(const void *fn, int threads, int *grid)
+{
+    int per_sm = 0;
+    GLB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, threads, 0));
+    if (per_sm < 1) { set_error("kernel does not fit on an SM"); return GLB_E_INVALID; }
+    *grid = per_sm * sm_count();
+    return 0;
+}
+
+// label map: lab[i] = LAST j with ind[j] == i (the reference's loops assign in order, the last one wins), -1 otherwise
+int build_labels(const int32_t *h_ind, int n, int m, std::vector<int> &lab)
+{
+    lab.assign((size_t)n, -1);
+    for (int j = 0; j < m; ++j) {
+        int i = h_ind[j];
+        if (i < 0) i += n;                                        // numpy-style negative indices never reach the C code; be lenient
+        if (i < 0 || i >= n) { set_error("boundary index %d out of range", h_ind[j]); return GLB_E_INVALID; }
+        lab[i] = j;
+    }
+    return 0;
+}
+
+struct Common {
+    Arena A;
+    int *start = nullptr, *nbr = nullptr, *row = nullptr, *lab = nullptr, *status = nullptr, *sweeps = nullptr;
+    double *W = nullptr, *labval = nullptr;
+    Cell *c0 = nullptr, *c1 = nullptr;
+    unsigned long long *slots = nullptr;
+    unsigned *counter = nullptr;
+};
+
+int upload_common(Common &C, const int32_t *h_nbr, const int32_t *h_row, const double *h_w, const int32_t *h_ind,
+                  const double *h_val, int n, int M, int m, cudaStream_t st, int *nl)
+{
+    std::vector<int> lab;
+    int rc = build_labels(h_ind, n, m, lab);
+    if (rc) return rc;
+    GLB_CUDA(C.A.alloc(&C.start, (size_t)n + 1)); GLB_CUDA(C.A.alloc(&C.nbr, (size_t)M)); GLB_CUDA(C.A.alloc(&C.row, (size_t)M));
+    GLB_CUDA(C.A.alloc(&C.W, (size_t)M));         GLB_CUDA(C.A.alloc(&C.lab, (size_t)n)); GLB_CUDA(C.A.alloc(&C.labval, (size_t)m));
+    GLB_CUDA(C.A.alloc(&C.c0, (size_t)n));        GLB_CUDA(C.A.alloc(&C.c1, (size_t)n));
+    GLB_CUDA(C.A.alloc(&C.slots, 4));             GLB_CUDA(C.A.alloc(&C.counter, 1));
+    GLB_CUDA(C.A.alloc(&C.status, 1));            GLB_CUDA(C.A.alloc(&C.sweeps, 1));
+    GLB_CUDA(cudaMemcpyAsync(C.nbr, h_nbr, (size_t)M * sizeof(int), cudaMemcpyHostToDevice, st));
+    GLB_CUDA(cudaMemcpyAsync(C.row, h_row, (size_t)M * sizeof(int), cudaMemcpyHostToDevice, st));
+    GLB_CUDA(cudaMemcpyAsync(C.W, h_w, (size_t)M * sizeof(double), cudaMemcpyHostToDevice, st));
+    GLB_CUDA(cudaMemcpyAsync(C.lab, lab.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice, st));
+    if (m) GLB_CUDA(cudaMemcpyAsync(C.labval, h_val, (size_t)m * sizeof(double), cudaMemcpyHostToDevice, st));
+    GLB_CUDA(cudaMemsetAsync(C.slots, 0, 4 * sizeof(unsigned long long), st));
+    GLB_CUDA(cudaMemsetAsync(C.counter, 0, sizeof(unsigned), st));
+    GLB_CUDA(cudaMemsetAsync(C.status, 0, sizeof(int), st));
+    GLB_CUDA(cudaMemsetAsync(C.sweeps, 0, sizeof(int), st));
+    const int gb = sm_count() * 4;
+    if (M) check_coo_kernel<<<gb, 256, 0, st>>>(C.row, C.nbr, M, n, C.status);
+    row_start_kernel<<<gb, 256, 0, st>>>(C.row, M, n, C.start);
+    if (M) max_weight_kernel<<<gb, 256, 0, st>>>(C.W, M, C.slots + 3);
+    *nl += 3;
+    GLB_LAUNCH_CHECK();
+    int status = 0;
+    GLB_CUDA(cudaMemcpyAsync(&status, C.status, sizeof(int), cudaMemcpyDeviceToHost, st));
+    GLB_CUDA(cudaStreamSynchronize(st));
+    if (status & 1) { set_error("row index array must be sorted ascending with entries in [0,n) (graph.__ccode_init__ order)"); return GLB_E_INVALID; }
+    if (status & 2) { set_error("neighbour index out of range"); return GLB_E_INVALID; }
+    return 0;
+}
+
+int no_gpu()
+{
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        set_error("no CUDA device visible (there is no CPU fallback)");
+        return GLB_E_NOGPU;
+    }
+    return 0;
+}
+
+}  // namespace
+}  // namespace glb
+
+using namespace glb;
+
+extern "C" GLB_API int glb_lp_iterate_host(double *h_uu, double *h_ul, const int32_t *h_nbr, const int32_t *h_row,
+                                           const double *h_w, const int32_t *h_ind, const double *h_val, double p, int T,
+                                           double tol, int n, int M, int m, int *sweeps, int *launches)
+{
+    GLB_CHECK_ARG(h_uu && h_ul && (M == 0 || (h_nbr && h_row && h_w)) && (m == 0 || (h_ind && h_val)), "null pointer");
+    GLB_CHECK_ARG(n > 0 && M >= 0 && m >= 0 && T >= 0, "size out of range");
+    int rc = no_gpu();
+    if (rc) return rc;
+    cudaStream_t st = 0;
+    int nl = 0;
+    Common C;
+    if ((rc = upload_common(C, h_nbr, h_row, h_w, h_ind, h_val, n, M, m, st, &nl))) return rc;
+    double *uu, *ul, *invdeg;
+    GLB_CUDA(C.A.alloc(&uu, (size_t)n)); GLB_CUDA(C.A.alloc(&ul, (size_t)n)); GLB_CUDA(C.A.alloc(&invdeg, (size_t)n));
+    GLB_CUDA(cudaMemcpyAsync(uu, h_uu, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, st));
+    GLB_CUDA(cudaMemcpyAsync(ul, h_ul, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, st));
+    const int gb = sm_count() * 4;
+    lp_pack_kernel<<<gb, 256, 0, st>>>(uu, ul, C.c0, C.c1, n);
+    LpArgs A{C.start, C.nbr, C.W, C.lab, C.labval, C.c0, C.c1, invdeg, C.slots, C.counter, C.sweeps, n, T, p, tol};
+    int grid = 0;
+    if ((rc = coop_grid((const void *)lp_jacobi_kernel, 256, &grid))) return rc;
+    grid = std::min(grid, std::max(1, ceil_div(n, 256)));
+    void *args[] = {&A};
+    GLB_CUDA(cudaLaunchCooperativeKernel((const void *)lp_jacobi_kernel, dim3(grid), dim3(256), args, 0, st));
+    lp_unpack_kernel<<<gb, 256, 0, st>>>(C.c0, uu, ul, n);
+    nl += 3;
+    GLB_LAUNCH_CHECK();
+    int sw = 0;
+    GLB_CUDA(cudaMemcpyAsync(h_uu, uu, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    GLB_CUDA(cudaMemcpyAsync(h_ul, ul, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    GLB_CUDA(cudaMemcpyAsync(&sw, C.sweeps, sizeof(int), cudaMemcpyDeviceToHost, st));
+    GLB_CUDA(cudaStreamSynchronize(st));
+    if (sweeps) *sweeps = sw;
+    if (launches) *launches = nl;
+    return 0;
+}
+
+extern "C" GLB_API int glb_lip_iterate_host(double *h_u, const int32_t *h_nbr, const int32_t *h_row, const double *h_w,
+                                            const int32_t *h_ind, const double *h_val, int T, double tol, int weighted,
+                                            double alpha, double beta, int n, int M, int m, int *sweeps, int *launches)
+{
+    GLB_CHECK_ARG(h_u && (M == 0 || (h_nbr && h_row && h_w)) && (m == 0 || (h_ind && h_val)), "null pointer");
+    GLB_CHECK_ARG(n > 0 && M >= 0 && m >= 0 && T >= 0, "size out of range");
+    int rc = no_gpu();
+    if (rc) return rc;
+    cudaStream_t st = 0;
+    int nl = 0;
+    Common C;
+    if ((rc = upload_common(C, h_nbr, h_row, h_w, h_ind, h_val, n, M, m, st, &nl))) return rc;
+    double *u, *u_out;
+    GLB_CUDA(C.A.alloc(&u, (size_t)n)); GLB_CUDA(C.A.alloc(&u_out, (size_t)n));
+    GLB_CUDA(cudaMemcpyAsync(u, h_u, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, st));
+    const int gb = sm_count() * 4;
+    lip_pack_kernel<<<gb, 256, 0, st>>>(u, C.lab, C.labval, C.c0, C.c1, n);
+    LipArgs A{C.start, C.nbr, C.W, C.lab, C.c0, C.c1, u_out, C.slots, C.counter, C.sweeps, n, M, T, tol, alpha, beta};
+    const void *fn = weighted ? (const void *)lip_gauss_seidel_kernel<true> : (const void *)lip_gauss_seidel_kernel<false>;
+    int grid = 0;
+    if ((rc = coop_grid(fn, 256, &grid))) return rc;
+    grid = std::min(grid, std::max(1, ceil_div(n, 256)));
+    void *args[] = {&A};
+    GLB_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(256), args, 0, st));
+    nl += 2;
+    GLB_LAUNCH_CHECK();
+    int sw = 0;
+    GLB_CUDA(cudaMemcpyAsync(h_u, u_out, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    GLB_CUDA(cudaMemcpyAsync(&sw, C.sweeps, sizeof(int), cudaMemcpyDeviceToHost, st));
+    GLB_CUDA(cudaStreamSynchronize(st));
+    if (sweeps) *sweeps = sw;
+    if (launches) *launches = nl;
+    return 0;
+}

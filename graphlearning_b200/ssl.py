@@ -243,6 +243,46 @@ class laplace(ssl):
         return u
 
 
+class amle(ssl):
+    """AMLE learning, one-vs-rest.  Reference graphlearning/ssl.py:1569-1614; sweeps on the GPU (plaplace.cu)."""
+
+    def __init__(self, W=None, class_priors=None, tol=1e-3, max_num_it=1e5, weighted=False, prog=False):
+        super().__init__(W, class_priors)
+        self.tol = tol
+        self.max_num_it = max_num_it
+        self.weighted = weighted
+        self.prog = prog
+        self.onevsrest = True
+        self.accuracy_filename = "_amle"
+        if not self.weighted:
+            self.accuracy_filename += "_unweighted"
+        self.name = "AMLE"
+
+    def _fit(self, train_ind, train_labels, all_labels=None):
+        return self.graph.amle(train_ind, train_labels, tol=self.tol, max_num_it=self.max_num_it,
+                               weighted=self.weighted, prog=self.prog)
+
+
+class plaplace(ssl):
+    """Graph p-Laplace classifier, one-vs-rest.  Reference graphlearning/ssl.py:1681-1727."""
+
+    def __init__(self, W=None, class_priors=None, p=10, max_num_it=1e6, tol=1e-1, fast=True):
+        super().__init__(W, class_priors)
+        self.p = p
+        self.max_num_it = max_num_it
+        self.tol = tol
+        self.onevsrest = True
+        self.fast = fast
+        if fast:
+            self.tol = 1e-5
+        self.accuracy_filename = "_plaplace_p%.2f" % self.p
+        self.name = "p-Laplace (p=%.2f)" % self.p
+
+    def _fit(self, train_ind, train_labels, all_labels=None):
+        return self.graph.plaplace(train_ind, train_labels, self.p, max_num_it=self.max_num_it, tol=self.tol,
+                                   fast=self.fast)
+
+
 def ssl_accuracy(pred_labels, true_labels, train_ind):
     """Accuracy over the unlabelled points, in percent.  Reference graphlearning/ssl.py:1795-1834."""
     pred_labels = np.asarray(pred_labels)

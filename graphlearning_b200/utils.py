@@ -20,6 +20,18 @@ def labels_to_onehot(labels, k=None):
     return onehot
 
 
+def _boundary_handling(bdy_set, bdy_val):
+    """Boolean mask / list / scalar boundary data -> index and value arrays.  Reference graphlearning/utils.py:144-173."""
+    if type(bdy_set) == list:
+        bdy_set = np.array(bdy_set)
+    if bdy_set.dtype == bool:
+        bdy_set = np.where(bdy_set)[0]
+    m = len(bdy_set)
+    if type(bdy_val) != np.ndarray:
+        bdy_val = np.ones((m,)) * bdy_val
+    return bdy_set, bdy_val
+
+
 def conjgrad(A, b, x0=None, max_iter=1e5, tol=1e-10, return_info=False):
     """Conjugate gradient for A x = b with one or several right-hand sides, on the GPU (cg.cu).
 

@@ -197,6 +197,30 @@ GLB_API int glb_knn_search(const double *d_X, int64_t n, int d, int k, int64_t *
 GLB_API int glb_knn_search_host(const double *h_X, int64_t n, int d, int k, int64_t *h_ind, double *h_dist, int *launches,
                                 int *fallback_rows);
 
+/* ---------------------------------------------------------------------------------------------
+ * p-Laplace / AMLE neighbour sweeps.  Replace the reference's C extension entry points
+ * cextensions.lp_iterate / cextensions.lip_iterate (c_code/cextensions.cpp:19-107), i.e.
+ * lp_iterate_main (c_code/lp_iterate.cpp:35-125, Jacobi, upper + lower barrier function),
+ * lip_iterate_main (:129-187, Gauss-Seidel) and lip_iterate_weighted_main (:190-259, Gauss-Seidel with a
+ * 30-step bisection per row), called from graph.plaplace / graph.amle (graphlearning/graph.py:1261,1276,1330).
+ *
+ * Same arguments as the C functions they replace (lp_iterate.h:33-35): the graph as row-sorted COO triplets
+ * exactly as graph.__ccode_init__ (graph.py:69-84) prepares them - nbr = neighbour (column) index of entry k
+ * [the reference's `I`/`II` argument], row = row index, ascending [`J`], w = weight; M entries; ind/val = m
+ * Dirichlet nodes and values; uu/ul/u are n doubles, read as the initial iterate and overwritten with the
+ * result as the reference leaves it in the caller's arrays (lp: the last ODD sweep, because the reference swaps
+ * its buffer pointers, :116-123).  weighted != 0 selects lip_iterate_weighted_main (alpha/beta ignored).
+ * The iterates are bit-identical to the reference's at every sweep count (fp64, same operation order), the
+ * Gauss-Seidel sweeps included: they run as a dependency dataflow, not as a Jacobi substitute.
+ * HOST pointers; synchronous; *sweeps = sweeps executed; sweeps / launches may be NULL.
+ * ------------------------------------------------------------------------------------------- */
+GLB_API int glb_lp_iterate_host(double *h_uu, double *h_ul, const int32_t *h_nbr, const int32_t *h_row, const double *h_w,
+                                const int32_t *h_ind, const double *h_val, double p, int T, double tol, int n, int M, int m,
+                                int *sweeps, int *launches);
+GLB_API int glb_lip_iterate_host(double *h_u, const int32_t *h_nbr, const int32_t *h_row, const double *h_w,
+                                 const int32_t *h_ind, const double *h_val, int T, double tol, int weighted, double alpha,
+                                 double beta, int n, int M, int m, int *sweeps, int *launches);
+
 #ifdef __cplusplus
 }
 #endif

@@ -138,3 +138,16 @@ def lip_iterate(u, I, J, W, ind, val, T, tol, alpha, beta, use_ref=False):
                                    ctypes.c_double(tol), ctypes.c_int(n), ctypes.c_int(M), ctypes.c_int(m),
                                    ctypes.c_double(alpha), ctypes.c_double(beta))
     return u, sweeps
+
+
+def lip_iterate_weighted(u, I, J, W, ind, val, T, tol, use_ref=False):
+    """c_code/lp_iterate.cpp:190-259.  Returns u (reference build) or (u, sweeps) (restatement)."""
+    u = np.ascontiguousarray(u, dtype=np.float64).copy()
+    I_ = _pad1(I, np.int32); J_ = _pad1(J, np.int32); W_ = _pad1(W, np.float64)
+    I_[-1] = 0                              # an empty LAST row makes the reference read u[I[M]]: keep that read in bounds
+    ind = np.ascontiguousarray(ind, dtype=np.int32); val = np.ascontiguousarray(val, dtype=np.float64)
+    n, M, m = len(u), len(I), len(ind)
+    fn = ref().ref_lip_iterate_weighted if use_ref else lib().orc_lip_iterate_weighted
+    sweeps = fn(_d(u), _i(I_), _i(J_), _d(W_), _i(ind), _d(val), ctypes.c_int(int(T)), ctypes.c_double(tol),
+                ctypes.c_int(n), ctypes.c_int(M), ctypes.c_int(m))
+    return u if use_ref else (u, sweeps)

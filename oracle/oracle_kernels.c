@@ -173,3 +173,45 @@ int orc_lip_iterate(double *u, const int *I, const int *J, const double *W, cons
     free(num); free(start); free(mask);
     return sweeps;
 }
+
+/* c_code/lp_iterate.cpp:190-259 (lip_iterate_weighted_main): Gauss-Seidel sweeps of the weighted infinity
+ * Laplacian; every row solves min_j w(t-u_j) + max_j w(t-u_j) = 0 for t by 30 bisection steps on [min u_j, max u_j]. */
+int orc_lip_iterate_weighted(double *u, const int *I, const int *J, const double *W, const int *ind,
+                             const double *val, int T, double tol, int n, int M, int m)
+{
+    int *num = (int *)malloc(sizeof(int) * n), *start = (int *)malloc(sizeof(int) * n);
+    char *mask = (char *)malloc(n);
+    memset(mask, 1, n);
+    row_scan(J, n, M, start, num);
+    for (int j = 0; j < m; j++) { u[ind[j]] = val[j]; mask[ind[j]] = 0; }
+    int it, sweeps = 0;
+    for (it = 0; it < T; it++) {
+        sweeps++;
+        double err = 0;
+        for (int i = 0; i < n; i++) {
+            if (!mask[i]) continue;
+            double minu = u[I[start[i]]], maxu = minu;
+            for (int j = start[i]; j < start[i] + num[i]; j++) {
+                minu = ORC_MIN(u[I[j]], minu);
+                maxu = ORC_MAX(u[I[j]], maxu);
+            }
+            double a = minu, b = maxu;
+            for (int k = 0; k < 30; k++) {
+                double minw = 0, maxw = 0, t = (a + b) / 2.0;
+                for (int j = start[i]; j < start[i] + num[i]; j++) {
+                    double d = W[j] * (t - u[I[j]]);
+                    minw = ORC_MIN(d, minw);
+                    maxw = ORC_MAX(d, maxw);
+                }
+                if (minw + maxw > 0) b = t; else a = t;
+            }
+            double ne = (a + b) / 2.0;
+            double d = fabs(u[i] - ne);
+            err = ORC_MAX(d, err);
+            u[i] = ne;
+        }
+        if (err < tol && it > 20) break;
+    }
+    free(num); free(start); free(mask);
+    return sweeps;
+}

@@ -38,6 +38,11 @@ def blobs():
 
 
 @pytest.fixture(scope="session")
+def plap():
+    return Golden("plaplace2000")
+
+
+@pytest.fixture(scope="session")
 def small():
     return Golden("small300")
 
