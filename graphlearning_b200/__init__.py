@@ -16,6 +16,7 @@ from . import trainsets    # noqa: F401
 from . import weightmatrix  # noqa: F401
 from . import graph as _graph_module
 from . import ssl          # noqa: F401
+from . import clustering   # noqa: F401
 from .graph import graph   # noqa: F401  (reference: `from .graph import graph`, graphlearning/__init__.py:8)
 
 __version__ = "0.1.0"

@@ -56,6 +56,11 @@ SIGNATURES = {
                                     c_double, c_int, c_int, c_int, POINTER(c_int), POINTER(c_int)]),
     "glb_lip_iterate_host": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_double, c_int,
                                      c_double, c_double, c_int, c_int, c_int, POINTER(c_int), POINTER(c_int)]),
+    "glb_spmm_f64": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int, c_void_p, c_int, c_int, c_double,
+                             c_void_p, c_int, c_double, c_void_p, c_void_p, c_int, c_double, c_void_p]),
+    "glb_gram_work_bytes": (c_int64, [c_int, c_int]),
+    "glb_gram_f64": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int64, c_void_p, c_void_p, c_int64, c_void_p]),
+    "glb_right_mul_f64": (c_int, [c_void_p, c_int, c_int64, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p]),
     "glb_poisson_gd_host": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int, c_void_p, c_int64,
                                     c_int, c_int, c_void_p, POINTER(c_int), POINTER(c_int)]),
 }

@@ -207,19 +207,22 @@ struct LipArgs {
     const int *start, *nbr;
     const double *W;
     const int *lab;
+    const int *order, *crit;        // level schedule: row of sorted position p, and the row's latest-level producer (or -1)
     Cell *c0, *c1;
     double *u_out;
     unsigned long long *slots;
     unsigned *counter;
     int *sweeps;
-    int n, M, T;
+    int n, M, T, n_active;
     double tol, alpha, beta;
 };
 
 constexpr unsigned long long kVerFixed = ~0ull;      // Dirichlet rows: valid in every sweep
 constexpr int kLipCap = 32;                          // neighbour values kept in local memory for the bisection
 
-// One row per lane and round.  A lane must never spin on a cell: its producer may be another lane of the same warp
+// One row per lane and round, rows dealt to lanes in LEVEL order (level = longest chain of same-sweep producers, computed
+// on the host per call): the lanes of a warp then become ready together and run the 30-step bisection in lockstep, and
+// a waiting lane polls only its latest-level producer.  A lane must never spin on a cell: its producer may be another lane of the same warp
 // (a lower-numbered neighbour in the same round), and a lane that leaves a spin loop waits at the loop's
 // reconvergence point for the lanes still inside.  So the warp runs a retry loop instead: per pass every pending lane
 // consumes, IN STORED ORDER, as many of its neighbours as are ready (8 gathers in flight), keeps its running
@@ -236,16 +239,18 @@ __global__ void __launch_bounds__(256) lip_gauss_seidel_kernel(LipArgs A)
         Cell *nxt = (it & 1) ? A.c0 : A.c1;
         const unsigned long long want = (unsigned long long)it + 1ull;
         double err = 0.0;
-        for (int i0 = gt - lane; i0 < A.n; i0 += NT) {                       // warp-uniform trip count
-            const int i = i0 + lane;
-            bool pending = i < A.n && A.lab[i] < 0;
-            int s = 0, L = 0, k = 0;
+        for (int p0 = gt - lane; p0 < A.n_active; p0 += NT) {                // warp-uniform trip count
+            bool pending = p0 + lane < A.n_active;
+            const int i = pending ? __ldg(A.order + p0 + lane) : 0;
+            int s = 0, L = 0, k = 0, crit = -1;
             double uv[kLipCap];
-            double minu = 0.0, maxu = 0.0, sumu = 0.0, deg = 0.0;
+            double minu = 0.0, maxu = 0.0, sumu = 0.0, deg = 0.0, uold = 0.0;
             bool empty_row = false;
             if (pending) {
                 s = A.start[i];
                 L = A.start[i + 1] - s;
+                crit = __ldg(A.crit + i);
+                uold = ld_cell(cur + i).a;
                 if (L == 0) {
                     // the reference reads u[I[start[i]]] (the next row's first neighbour) even for an empty row (:163, :223):
                     // treat that entry as the row's only "neighbour" for min/max and skip the sums
@@ -255,6 +260,10 @@ __global__ void __launch_bounds__(256) lip_gauss_seidel_kernel(LipArgs A)
             }
             while (__any_sync(0xffffffffu, pending)) {
                 if (!pending) continue;
+                if (crit >= 0) {                                  // one cheap poll on the producer expected last
+                    if (ld_cell(nxt + crit).b < want) continue;
+                    crit = -1;
+                }
                 int jj[8];
                 Cell c[8];
 #pragma unroll
@@ -304,7 +313,7 @@ __global__ void __launch_bounds__(256) lip_gauss_seidel_kernel(LipArgs A)
                     }
                     ne = __ddiv_rn(__dadd_rn(a, b), 2.0);
                 }
-                double d = __dsub_rn(ld_cell(cur + i).a, ne);
+                double d = __dsub_rn(uold, ne);
                 d = d < 0.0 ? -d : d;
                 if (d > err) err = d;
                 st_cell(nxt + i, ne, want);
@@ -380,9 +389,8 @@ struct Common {
 };
 
 int upload_common(Common &C, const int32_t *h_nbr, const int32_t *h_row, const double *h_w, const int32_t *h_ind,
-                  const double *h_val, int n, int M, int m, cudaStream_t st, int *nl)
+                  const double *h_val, int n, int M, int m, cudaStream_t st, int *nl, std::vector<int> &lab)
 {
-    std::vector<int> lab;
     int rc = build_labels(h_ind, n, m, lab);
     if (rc) return rc;
     GLB_CUDA(C.A.alloc(&C.start, (size_t)n + 1)); GLB_CUDA(C.A.alloc(&C.nbr, (size_t)M)); GLB_CUDA(C.A.alloc(&C.row, (size_t)M));
@@ -413,6 +421,40 @@ int upload_common(Common &C, const int32_t *h_nbr, const int32_t *h_row, const d
     return 0;
 }
 
+// Level schedule of one Gauss-Seidel sweep (arrays validated by upload_common before this runs): level[i] = 1 + the
+// largest level among the unlabelled neighbours j < i of the unlabelled row i (those are the values row i must wait for
+// inside a sweep), rows sorted by (level, index); crit[i] = a neighbour attaining that maximum, -1 without producers.
+void level_schedule(const int32_t *h_nbr, const int32_t *h_row, const std::vector<int> &lab, int n, int M,
+                    std::vector<int> &order, std::vector<int> &crit, int *depth)
+{
+    std::vector<int> start((size_t)n + 1, 0), level((size_t)n, -1);
+    for (int k = 0; k < M; ++k) ++start[(size_t)h_row[k] + 1];
+    for (int i = 0; i < n; ++i) start[i + 1] += start[i];
+    crit.assign((size_t)n, -1);
+    int maxl = -1;
+    std::vector<int> count;
+    for (int i = 0; i < n; ++i) {
+        if (lab[i] >= 0) continue;
+        int s = start[i], e = start[i + 1];
+        if (e == s && s < M) e = s + 1;                        // the empty row's stray read of the next entry
+        int l = -1, c = -1;
+        for (int k = s; k < e; ++k) {
+            const int j = h_nbr[k];
+            if (j < i && lab[j] < 0 && level[j] > l) { l = level[j]; c = j; }
+        }
+        level[i] = l + 1;
+        crit[i] = c;
+        if (level[i] > maxl) { maxl = level[i]; count.resize((size_t)maxl + 1, 0); }
+        ++count[level[i]];
+    }
+    std::vector<int> pos((size_t)maxl + 2, 0);
+    for (int l = 0; l <= maxl; ++l) pos[l + 1] = pos[l] + count[l];
+    order.assign((size_t)pos[maxl + 1], 0);
+    for (int i = 0; i < n; ++i)
+        if (level[i] >= 0) order[pos[level[i]]++] = i;
+    *depth = maxl + 1;
+}
+
 int no_gpu()
 {
     int ndev = 0;
@@ -440,7 +482,8 @@ extern "C" GLB_API int glb_lp_iterate_host(double *h_uu, double *h_ul, const int
     cudaStream_t st = 0;
     int nl = 0;
     Common C;
-    if ((rc = upload_common(C, h_nbr, h_row, h_w, h_ind, h_val, n, M, m, st, &nl))) return rc;
+    std::vector<int> lab;
+    if ((rc = upload_common(C, h_nbr, h_row, h_w, h_ind, h_val, n, M, m, st, &nl, lab))) return rc;
     double *uu, *ul, *invdeg;
     GLB_CUDA(C.A.alloc(&uu, (size_t)n)); GLB_CUDA(C.A.alloc(&ul, (size_t)n)); GLB_CUDA(C.A.alloc(&invdeg, (size_t)n));
     GLB_CUDA(cudaMemcpyAsync(uu, h_uu, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, st));
@@ -477,13 +520,21 @@ extern "C" GLB_API int glb_lip_iterate_host(double *h_u, const int32_t *h_nbr, c
     cudaStream_t st = 0;
     int nl = 0;
     Common C;
-    if ((rc = upload_common(C, h_nbr, h_row, h_w, h_ind, h_val, n, M, m, st, &nl))) return rc;
+    std::vector<int> lab, order, crit;
+    if ((rc = upload_common(C, h_nbr, h_row, h_w, h_ind, h_val, n, M, m, st, &nl, lab))) return rc;
+    int depth = 0;
+    level_schedule(h_nbr, h_row, lab, n, M, order, crit, &depth);
     double *u, *u_out;
+    int *d_order, *d_crit;
     GLB_CUDA(C.A.alloc(&u, (size_t)n)); GLB_CUDA(C.A.alloc(&u_out, (size_t)n));
+    GLB_CUDA(C.A.alloc(&d_order, order.size())); GLB_CUDA(C.A.alloc(&d_crit, (size_t)n));
+    if (!order.empty()) GLB_CUDA(cudaMemcpyAsync(d_order, order.data(), order.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    GLB_CUDA(cudaMemcpyAsync(d_crit, crit.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice, st));
     GLB_CUDA(cudaMemcpyAsync(u, h_u, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, st));
     const int gb = sm_count() * 4;
     lip_pack_kernel<<<gb, 256, 0, st>>>(u, C.lab, C.labval, C.c0, C.c1, n);
-    LipArgs A{C.start, C.nbr, C.W, C.lab, C.c0, C.c1, u_out, C.slots, C.counter, C.sweeps, n, M, T, tol, alpha, beta};
+    LipArgs A{C.start, C.nbr, C.W, C.lab, d_order, d_crit, C.c0, C.c1, u_out, C.slots, C.counter, C.sweeps, n, M, T,
+              (int)order.size(), tol, alpha, beta};
     const void *fn = weighted ? (const void *)lip_gauss_seidel_kernel<true> : (const void *)lip_gauss_seidel_kernel<false>;
     int grid = 0;
     if ((rc = coop_grid(fn, 256, &grid))) return rc;

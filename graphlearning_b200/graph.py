@@ -21,6 +21,10 @@ class graph:
         self.node_names = node_names
         self._device = {}
         self._coo = None
+        self.eigendata = {}
+        for norm in ("normalized", "randomwalk", "combinatorial"):
+            self.eigendata[norm] = dict(eigenvectors=None, eigenvalues=None, method=None, k=None, c=None, gamma=None,
+                                        tol=None, q=None)
 
     def _ccode_arrays(self):
         """Row-sorted COO triplets (I=row, J=column, V=weight) built with the reference's own expressions
@@ -147,3 +151,47 @@ class graph:
                   1 if weighted else 0, 0.0, 1.0, n, len(I), len(bs), ctypes.byref(sw), ctypes.byref(nl))
         self.sweeps, self.gpu_launches = sw.value, nl.value
         return u
+
+    # ---- spectral decomposition on the GPU (spectral.cu / spectral.py) --------------------------------------
+    def eigen_decomp(self, normalization="combinatorial", method="exact", k=10, c=None, gamma=0, tol=0, q=1):
+        """Smallest k eigenpairs of the graph Laplacian.  Reference graphlearning/graph.py:623-806: same shifted /
+        normalised matrices, same post-processing (vals = 1 - s or M - s, randomwalk vectors scaled by D^-1/2), same
+        result cache.  method='exact' (ARPACK svds in the reference) runs the block Chebyshev subspace iteration,
+        method='lowrank' the randomized SVD, both on the device.  The modularity variant (gamma != 0, eigsh on a
+        LinearOperator, :772-799) is outside the hot path."""
+        from . import spectral
+        if c is None:
+            c = 2 * k
+        ed = self.eigendata[normalization] if normalization in self.eigendata else None
+        if ed is None:
+            raise ValueError("Invalid choice of normalization")
+        if (ed["method"] == method and ed["k"] == k and ed["c"] == c and ed["gamma"] == gamma and ed["tol"] == tol
+                and ed["q"] == q):
+            return ed["eigenvalues"], ed["eigenvectors"]
+        if gamma != 0:
+            raise NotImplementedError("eigen_decomp(gamma != 0) (modularity) is not on the B200 hot path")
+        if method not in ("exact", "lowrank"):
+            raise ValueError("Invalid eigensolver method " + str(method))
+        n = self.num_nodes
+        if normalization in ("randomwalk", "normalized"):
+            D = self.degree_matrix(p=-0.5)
+            A = D * self.weight_matrix * D
+            shift = 1.0
+        else:
+            L = self.laplacian()
+            shift = 2 * np.max(self.degree_vector())
+            A = shift * sparse.identity(n) - L
+        if method == "exact":
+            u, s, info = spectral.svd_topk(A, k, tol=tol, return_info=True)
+        else:
+            u, s, vt, info = spectral.randomized_svd(A, k=k, c=c, q=q, return_info=True)
+        self.gpu_launches = info["launches"]
+        self.eigen_info = info
+        vals = shift - s
+        ind = np.argsort(vals)
+        vals = vals[ind]
+        vecs = u[:, ind]
+        if normalization == "randomwalk":
+            vecs = D @ vecs
+        ed.update(method=method, k=k, c=c, gamma=gamma, tol=tol, q=q, eigenvalues=vals, eigenvectors=vecs)
+        return vals, vecs

@@ -161,8 +161,17 @@ class poisson(ssl):
             self.iterations = it
             self.gpu_launches = nl
             return D * v
-        raise NotImplementedError("poisson solver %r (needs graph.eigen_decomp) is not built on the B200 backend yet"
-                                  % self.solver)
+        # ssl.py:680-688: spectral solver on the leading eigenvectors of the random-walk Laplacian
+        W0 = sparse.csr_matrix(W - sparse.spdiags(W.diagonal(), 0, n, n))              # :615-617
+        G = graph.graph(W0)
+        vals, vecs = G.eigen_decomp(normalization="randomwalk", k=self.spectral_cutoff + 1)
+        self.gpu_launches = G.gpu_launches
+        V = vecs[:, 1:]
+        vals = vals[1:]
+        if self.p != 1:
+            vals = vals ** self.p
+        L = sparse.spdiags(1 / vals, 0, self.spectral_cutoff, self.spectral_cutoff)
+        return V @ (L @ (V.T @ source))
 
 
 class laplace(ssl):

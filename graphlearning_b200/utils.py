@@ -62,3 +62,9 @@ def conjgrad(A, b, x0=None, max_iter=1e5, tol=1e-10, return_info=False):
     if return_info:
         return x, (iters.value, err.value, nl.value)
     return x
+
+
+def randomized_svd(A, k=10, c=None, q=1):
+    """Randomized SVD on the GPU; mirror of reference graphlearning/utils.py:576-642 (see spectral.randomized_svd)."""
+    from . import spectral
+    return spectral.randomized_svd(A, k=k, c=c, q=q)

@@ -221,6 +221,29 @@ GLB_API int glb_lip_iterate_host(double *h_u, const int32_t *h_nbr, const int32_
                                  const int32_t *h_ind, const double *h_val, int T, double tol, int weighted, double alpha,
                                  double beta, int n, int M, int m, int *sweeps, int *launches);
 
+/* ---------------------------------------------------------------------------------------------
+ * fp64 block operations for the spectral path: graph.eigen_decomp (graphlearning/graph.py:623-806, ARPACK svds
+ * at :734,756 and utils.randomized_svd at :736,758) and utils.randomized_svd itself
+ * (graphlearning/utils.py:576-642, whose cost is the repeated product Y <- A (A^T Y), :618-621).
+ * Tall-skinny matrices are row-major n x ld fp64 with c <= 256 used columns; ld even and >= c rounded up to
+ * even for glb_spmm_f64 (16-byte accesses), ld >= c for the other two.  Device pointers, stream-ordered.
+ *
+ * glb_spmm_f64:       Z = alpha * A X + beta * Y1 * diag(bcol) + gamma * Y2.   A = CSR fp64; Y1, bcol, Y2 may be
+ *                     NULL (bcol NULL = all ones); Z may alias Y1 / Y2 but not X.  Replaces scipy csr_matvecs /
+ *                     csr_matmat at the call sites above, with the Chebyshev / power recurrence fused in.
+ * glb_gram_f64:       G = X^T Y, c1 x c2 row-major (device), partial sums reduced in a fixed order.
+ *                     d_work: glb_gram_work_bytes(c1, c2) bytes.
+ * glb_right_mul_f64:  Y = X S, S = c1 x c2 row-major (device); padding columns of Y (c2..ldy-1) are zeroed.
+ * ------------------------------------------------------------------------------------------- */
+GLB_API int glb_spmm_f64(const int32_t *d_rowptr, const int32_t *d_col, const double *d_val, int64_t n, const double *d_X,
+                         int ldx, double *d_Z, int ldz, int c, double alpha, const double *d_Y1, int ldy1, double beta,
+                         const double *d_bcol, const double *d_Y2, int ldy2, double gamma, void *stream);
+GLB_API int64_t glb_gram_work_bytes(int c1, int c2);
+GLB_API int glb_gram_f64(const double *d_X, int ldx, int c1, const double *d_Y, int ldy, int c2, int64_t n, double *d_G,
+                         void *d_work, int64_t work_bytes, void *stream);
+GLB_API int glb_right_mul_f64(const double *d_X, int ldx, int64_t n, int c1, const double *d_S, int c2, double *d_Y, int ldy,
+                              void *stream);
+
 #ifdef __cplusplus
 }
 #endif
