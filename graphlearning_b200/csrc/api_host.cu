@@ -87,6 +87,7 @@ struct glb_poisson_graph {
     int *perm = nullptr;
     // per-width work buffers and plan (kept for the last width used)
     int ldu = 0, c_plan = 0;
+    int64_t rows = 0;                    // rows of Db / u0 / u1 (glb_poisson_plan_rows)
     int64_t m_cap = 0;
     double *src64 = nullptr;             // n x c staging (source in, result out)
     float *Db = nullptr, *u0 = nullptr, *u1 = nullptr;
@@ -181,8 +182,12 @@ extern "C" GLB_API int glb_poisson_graph_fit(glb_poisson_graph *g, const double 
         if ((rc = glb_poisson_plan_create(&g->plan, g->it_rp, g->it_col, g->it_val, n, nnz, c, GLB_POISSON_KIND_AUTO, st)))
             return rc;
         const int ld = glb_poisson_plan_ld(g->plan);
-        GLB_CUDA(g->A.alloc(&g->src64, n * c));  GLB_CUDA(g->A.alloc(&g->Db, n * ld));
-        GLB_CUDA(g->A.alloc(&g->u0, n * ld));    GLB_CUDA(g->A.alloc(&g->u1, n * ld));
+        const int64_t rows = glb_poisson_plan_rows(g->plan);          // n, or n + 1 with the library's scratch row
+        GLB_CUDA(g->A.alloc(&g->src64, n * c));  GLB_CUDA(g->A.alloc(&g->Db, rows * ld));
+        GLB_CUDA(g->A.alloc(&g->u0, rows * ld)); GLB_CUDA(g->A.alloc(&g->u1, rows * ld));
+        GLB_CUDA(cudaMemsetAsync(g->Db, 0, rows * ld * sizeof(float), st));
+        GLB_CUDA(cudaMemsetAsync(g->u1, 0, rows * ld * sizeof(float), st));
+        g->rows = rows;
         g->ldu = ld; g->c_plan = c;
     }
     const int ldu = g->ldu;
@@ -205,7 +210,7 @@ extern "C" GLB_API int glb_poisson_graph_fit(glb_poisson_graph *g, const double 
                                        st)))
             return rc;
     }
-    GLB_CUDA(cudaMemsetAsync(g->u0, 0, n * ldu * sizeof(float), st));
+    GLB_CUDA(cudaMemsetAsync(g->u0, 0, g->rows * ldu * sizeof(float), st));
     int in_u1 = 0;
     if ((rc = glb_poisson_iterate(g->plan, g->Db, g->u0, g->u1, T, &in_u1, &nl, st))) return rc;
     if ((rc = glb_poisson_unpack(g->plan, in_u1 ? g->u1 : g->u0, g->perm, g->src64, st))) return rc;

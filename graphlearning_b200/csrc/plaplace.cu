@@ -221,8 +221,9 @@ constexpr unsigned long long kVerFixed = ~0ull;      // Dirichlet rows: valid in
 constexpr int kLipCap = 32;                          // neighbour values kept in local memory for the bisection
 
 // One row per lane and round, rows dealt to lanes in LEVEL order (level = longest chain of same-sweep producers, computed
-// on the host per call): the lanes of a warp then become ready together and run the 30-step bisection in lockstep, and
-// a waiting lane polls only its latest-level producer.  A lane must never spin on a cell: its producer may be another lane of the same warp
+// on the host per call, a warp never mixes levels): the lanes of a warp become ready together, first consume their
+// neighbours and then run the update - for AMLE the 30-step bisection - in lockstep; a waiting lane polls only its
+// latest-level producer.  A lane must never spin on a cell: its producer may be another lane of the same warp
 // (a lower-numbered neighbour in the same round), and a lane that leaves a spin loop waits at the loop's
 // reconvergence point for the lanes still inside.  So the warp runs a retry loop instead: per pass every pending lane
 // consumes, IN STORED ORDER, as many of its neighbours as are ready (8 gathers in flight), keeps its running
@@ -240,13 +241,16 @@ __global__ void __launch_bounds__(256) lip_gauss_seidel_kernel(LipArgs A)
         const unsigned long long want = (unsigned long long)it + 1ull;
         double err = 0.0;
         for (int p0 = gt - lane; p0 < A.n_active; p0 += NT) {                // warp-uniform trip count
-            bool pending = p0 + lane < A.n_active;
-            const int i = pending ? __ldg(A.order + p0 + lane) : 0;
+            // the schedule pads every level to a multiple of 32 (-1 entries): a warp holds rows of ONE level, which
+            // have no dependencies among themselves
+            const int i = p0 + lane < A.n_active ? __ldg(A.order + p0 + lane) : -1;
+            const bool active = i >= 0;
+            bool pending = active;
             int s = 0, L = 0, k = 0, crit = -1;
-            double uv[kLipCap];
+            double uv[kLipCap], wv[kLipCap];
             double minu = 0.0, maxu = 0.0, sumu = 0.0, deg = 0.0, uold = 0.0;
             bool empty_row = false;
-            if (pending) {
+            if (active) {
                 s = A.start[i];
                 L = A.start[i + 1] - s;
                 crit = __ldg(A.crit + i);
@@ -258,10 +262,11 @@ __global__ void __launch_bounds__(256) lip_gauss_seidel_kernel(LipArgs A)
                     if (s < A.M) L = 1; else { minu = maxu = qnan; }
                 }
             }
+            // phase 1: consume the neighbours in stored order as they become ready (retry loop, never a spin)
             while (__any_sync(0xffffffffu, pending)) {
                 if (!pending) continue;
                 if (crit >= 0) {                                  // one cheap poll on the producer expected last
-                    if (ld_cell(nxt + crit).b < want) continue;
+                    if (ld_cell(nxt + crit).b < want) { __nanosleep(64); continue; }
                     crit = -1;
                 }
                 int jj[8];
@@ -278,34 +283,41 @@ __global__ void __launch_bounds__(256) lip_gauss_seidel_kernel(LipArgs A)
                     if (jj[q] < i && c[q].b < want) { stop = true; continue; }   // producer not there yet: retry from here
                     const double v = c[q].a;
                     if (k == 0) { minu = v; maxu = v; }
-                    if (!WEIGHTED && !empty_row) {
+                    if (!empty_row) {
                         const double w = __ldg(A.W + s + k);
-                        sumu = __dadd_rn(sumu, __dmul_rn(w, v));
-                        deg = __dadd_rn(deg, w);
+                        if (!WEIGHTED) {
+                            sumu = __dadd_rn(sumu, __dmul_rn(w, v));
+                            deg = __dadd_rn(deg, w);
+                        } else if (k < kLipCap) {
+                            uv[k] = v; wv[k] = w;
+                        }
                     }
                     minu = v < minu ? v : minu;
                     maxu = v > maxu ? v : maxu;
-                    if (WEIGHTED && k < kLipCap) uv[k] = v;
                     ++k;
                 }
-                if (k < L) continue;
+                if (k >= L) pending = false;
+            }
+            // phase 2: the whole warp updates its rows in lockstep
+            if (active) {
                 double ne;
                 if (!WEIGHTED) {
                     ne = __dadd_rn(__ddiv_rn(__dmul_rn(A.alpha, sumu), deg), __ddiv_rn(__dmul_rn(A.beta, __dadd_rn(minu, maxu)), 2.0));
                 } else {
                     double a = minu, b = maxu;
                     const int Lr = empty_row ? 0 : L;
+                    const int Lc = Lr < kLipCap ? Lr : kLipCap;
                     for (int r = 0; r < 30; ++r) {                         // bisection on min_j w(t-u_j) + max_j w(t-u_j) (:229-243)
                         const double tm = __ddiv_rn(__dadd_rn(a, b), 2.0);
                         double minw = 0.0, maxw = 0.0;
-                        for (int kk = 0; kk < Lr; ++kk) {
-                            double v;
-                            if (kk < kLipCap) v = uv[kk];
-                            else {                                         // beyond the local cache: final for this sweep, read again
-                                const int j = __ldg(A.nbr + s + kk);
-                                v = ld_cell((j < i ? nxt : cur) + j).a;
-                            }
-                            const double d = __dmul_rn(__ldg(A.W + s + kk), __dsub_rn(tm, v));
+                        for (int kk = 0; kk < Lc; ++kk) {
+                            const double d = __dmul_rn(wv[kk], __dsub_rn(tm, uv[kk]));
+                            minw = d < minw ? d : minw;
+                            maxw = d > maxw ? d : maxw;
+                        }
+                        for (int kk = kLipCap; kk < Lr; ++kk) {            // beyond the local cache: final for this sweep, read again
+                            const int j = __ldg(A.nbr + s + kk);
+                            const double d = __dmul_rn(__ldg(A.W + s + kk), __dsub_rn(tm, ld_cell((j < i ? nxt : cur) + j).a));
                             minw = d < minw ? d : minw;
                             maxw = d > maxw ? d : maxw;
                         }
@@ -317,7 +329,6 @@ __global__ void __launch_bounds__(256) lip_gauss_seidel_kernel(LipArgs A)
                 d = d < 0.0 ? -d : d;
                 if (d > err) err = d;
                 st_cell(nxt + i, ne, want);
-                pending = false;
             }
         }
         const double gerr = barrier_max(err, A.slots, A.counter, (unsigned)it);
@@ -423,7 +434,7 @@ int upload_common(Common &C, const int32_t *h_nbr, const int32_t *h_row, const d
 
 // Level schedule of one Gauss-Seidel sweep (arrays validated by upload_common before this runs): level[i] = 1 + the
 // largest level among the unlabelled neighbours j < i of the unlabelled row i (those are the values row i must wait for
-// inside a sweep), rows sorted by (level, index); crit[i] = a neighbour attaining that maximum, -1 without producers.
+// inside a sweep), rows sorted by (level, index), every level padded with -1 to a multiple of 32; crit[i] = a neighbour attaining that maximum, -1 without producers.
 void level_schedule(const int32_t *h_nbr, const int32_t *h_row, const std::vector<int> &lab, int n, int M,
                     std::vector<int> &order, std::vector<int> &crit, int *depth)
 {
@@ -448,8 +459,8 @@ void level_schedule(const int32_t *h_nbr, const int32_t *h_row, const std::vecto
         ++count[level[i]];
     }
     std::vector<int> pos((size_t)maxl + 2, 0);
-    for (int l = 0; l <= maxl; ++l) pos[l + 1] = pos[l] + count[l];
-    order.assign((size_t)pos[maxl + 1], 0);
+    for (int l = 0; l <= maxl; ++l) pos[l + 1] = pos[l] + ((count[l] + 31) & ~31);      // a warp never straddles two levels
+    order.assign((size_t)pos[maxl + 1], -1);
     for (int i = 0; i < n; ++i)
         if (level[i] >= 0) order[pos[level[i]]++] = i;
     *depth = maxl + 1;

@@ -327,7 +327,60 @@ __device__ __forceinline__ void st_chunk(char *p, float a, float b, float c, uns
 constexpr int kSlotNormal = 0, kSlotLong = 1, kSlotPart = 2, kSlotOwner = 3;
 constexpr int kLongRowDf = 32;                   // rows with more nonzeros get a warp (or several) of their own
 
-template <int LANES, int THREADS, int U>
+// Inner loop of the second-generation slab format (V2): no per-entry predicates at all.  Entries of a lane group are
+// stored in PAIRS (one LDS.128 = two (offset,value) entries, 8 lane groups side by side = one 128-byte wavefront),
+// padding entries point at the scratch row n of the label matrix (value 0, epoch 0xffffffff: always "ready"), the
+// epoch test is `>=` (a chunk only ever holds version t-2 or t of its row, see the two-buffer argument above), the
+// address is one IMAD.WIDE (64-bit base + 32-bit byte offset), and a slice of width L is walked as 16-entry batches plus
+// 8/4/2/1 tails selected by the bits of L (warp-uniform), so exactly L gathers are issued per row.
+__device__ __forceinline__ const char *df_addr(const char *base, unsigned off)
+{
+    unsigned long long a;
+    asm("mad.wide.u32 %0, %1, 1, %2;" : "=l"(a) : "r"(off), "l"(base));
+    return reinterpret_cast<const char *>(a);
+}
+
+template <int N, int RPW>
+__device__ __forceinline__ void df_batch(const int2 *cvp, const char *in, unsigned expect, int nopoll, float &a0, float &a1,
+                                         float &a2, unsigned long long &n_poll, unsigned long long &n_badbatch)
+{
+    unsigned off[N];
+    float val[N];
+    uint4 x[N];
+    if (N == 1) {
+        const int2 e = cvp[0];
+        off[0] = (unsigned)e.x; val[0] = __int_as_float(e.y);
+    } else {
+#pragma unroll
+        for (int i = 0; i < N / 2; ++i) {
+            const int4 e = *reinterpret_cast<const int4 *>(cvp + i * 2 * RPW);
+            off[2 * i] = (unsigned)e.x;     val[2 * i] = __int_as_float(e.y);
+            off[2 * i + 1] = (unsigned)e.z; val[2 * i + 1] = __int_as_float(e.w);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) x[i] = ld_chunk(df_addr(in, off[i]));
+    bool ok = true;
+#pragma unroll
+    for (int i = 0; i < N; ++i) ok &= x[i].w >= expect;
+    while (!ok && !(nopoll & 1)) {                       // some producer is still behind: re-poll the stale chunks together
+        ++n_badbatch;
+#pragma unroll
+        for (int i = 0; i < N; ++i)
+            if (x[i].w < expect) { x[i] = ld_chunk(df_addr(in, off[i])); ++n_poll; }
+        ok = true;
+#pragma unroll
+        for (int i = 0; i < N; ++i) ok &= x[i].w >= expect;
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        a0 = fmaf(val[i], __uint_as_float(x[i].x), a0);
+        a1 = fmaf(val[i], __uint_as_float(x[i].y), a1);
+        a2 = fmaf(val[i], __uint_as_float(x[i].z), a2);
+    }
+}
+
+template <int LANES, int THREADS, int U, bool V2>
 __global__ void __launch_bounds__(THREADS, 1)
 poisson_dataflow_kernel(const int2 *__restrict__ slabs, const long long *__restrict__ slab_off,
                         const int4 *__restrict__ slots, const int *__restrict__ slot_off,
@@ -399,9 +452,18 @@ poisson_dataflow_kernel(const int2 *__restrict__ slabs, const long long *__restr
         const unsigned expect = 1u + (unsigned)t;
         for (int s = warp; s < nslots; s += NW) {            // slot k of warp w is stored at k * NW + w
             const int4 sl = s_slot[s];                       // (first entry, slice width, type | parts << 8, partial index)
-            const int2 *cv = s_cv + sl.x + g;                // entry j of this lane group: cv[j * RPW]
             const int L = sl.y;
             float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+            if constexpr (V2) {
+                const int2 *cv = s_cv + sl.x + g * 2;        // pair q of this lane group: 16 bytes at cv[q * 2 * RPW]
+                int j = 0;
+                for (; j + U <= L; j += U) df_batch<U, RPW>(cv + j * RPW, in, expect, nopoll, a0, a1, a2, n_poll, n_badbatch);
+                if (U > 8 && (L & 8)) { df_batch<8, RPW>(cv + j * RPW, in, expect, nopoll, a0, a1, a2, n_poll, n_badbatch); j += 8; }
+                if (L & 4) { df_batch<4, RPW>(cv + j * RPW, in, expect, nopoll, a0, a1, a2, n_poll, n_badbatch); j += 4; }
+                if (L & 2) { df_batch<2, RPW>(cv + j * RPW, in, expect, nopoll, a0, a1, a2, n_poll, n_badbatch); j += 2; }
+                if (L & 1) df_batch<1, RPW>(cv + j * RPW, in, expect, nopoll, a0, a1, a2, n_poll, n_badbatch);
+            } else {
+            const int2 *cv = s_cv + sl.x + g;                // entry j of this lane group: cv[j * RPW]
             for (int j0 = 0; j0 < L; j0 += U) {
                 unsigned off[U];
                 float val[U];
@@ -436,6 +498,7 @@ poisson_dataflow_kernel(const int2 *__restrict__ slabs, const long long *__restr
                     a1 = fmaf(val[i], __uint_as_float(x[i].y), a1);
                     a2 = fmaf(val[i], __uint_as_float(x[i].z), a2);
                 }
+            }
             }
             const int type = sl.z & 0xff;
             if (type != kSlotNormal) {                       // warp-uniform: one long row dealt over the lane groups
@@ -484,11 +547,17 @@ poisson_dataflow_kernel(const int2 *__restrict__ slabs, const long long *__restr
 }
 
 // epoch words of the two buffers before a launch: version 0 in u0 (word 1), nothing valid in u1 (word 0)
-__global__ void __launch_bounds__(256) stamp_kernel(float *u0, float *u1, long long nchunks)
+// chunks nchunks .. nchunks + nscratch - 1 (the scratch row n, if the plan has one): value 0, epoch 0xffffffff in both
+__global__ void __launch_bounds__(256) stamp_kernel(float *u0, float *u1, long long nchunks, int nscratch)
 {
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nchunks; i += (long long)gridDim.x * blockDim.x) {
-        reinterpret_cast<unsigned *>(u0)[i * 4 + 3] = 1u;
-        reinterpret_cast<unsigned *>(u1)[i * 4 + 3] = 0u;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nchunks + nscratch; i += (long long)gridDim.x * blockDim.x) {
+        if (i < nchunks) {
+            reinterpret_cast<unsigned *>(u0)[i * 4 + 3] = 1u;
+            reinterpret_cast<unsigned *>(u1)[i * 4 + 3] = 0u;
+        } else {
+            reinterpret_cast<uint4 *>(u0)[i] = make_uint4(0u, 0u, 0u, 0xffffffffu);
+            reinterpret_cast<uint4 *>(u1)[i] = make_uint4(0u, 0u, 0u, 0xffffffffu);
+        }
     }
 }
 
@@ -658,6 +727,7 @@ struct glb_poisson_plan {
     int tuned_gate = 32;
     unsigned *d_gate = nullptr;         // dataflow kernel: start gate counter
     int gate_every = 32;                // dataflow kernel: iterations between re-alignment gates (tuned at plan time)
+    int scratch_row = 0;                // 1: the label matrices carry a row n owned by the library (padding target of the V2 slabs)
     unsigned long long *d_stats = nullptr;   // GLB_POISSON_STATS=1: {re-polls, batches that had to poll, max warp cycles, CTAs}
 };
 
@@ -701,17 +771,45 @@ static const void *dataflow_fn(const PersistVariant &v, int *threads)
 #define GLB_DV(T_, U_)                                                  \
     if (v.threads == T_ && v.unroll == U_) {                            \
         *threads = T_;                                                  \
-        return (const void *)poisson_dataflow_kernel<LANES, T_, U_>;    \
+        return (const void *)poisson_dataflow_kernel<LANES, T_, U_, false>;    \
     }
     GLB_DV(1024, 4) GLB_DV(1024, 8) GLB_DV(768, 8) GLB_DV(512, 8) GLB_DV(512, 16) GLB_DV(256, 16)
 #undef GLB_DV
     *threads = 512;
-    return (const void *)poisson_dataflow_kernel<LANES, 512, 16>;
+    return (const void *)poisson_dataflow_kernel<LANES, 512, 16, false>;
+}
+
+// second-generation slab format (pairs + scratch-row padding); GLB_POISSON_VARIANT picks the CTA size
+template <int LANES>
+static const void *dataflow2_fn(const PersistVariant &v, int *threads)
+{
+    if (v.threads == 1024) { *threads = 1024; return (const void *)poisson_dataflow_kernel<LANES, 1024, 8, true>; }
+    if (v.threads == 768) { *threads = 768; return (const void *)poisson_dataflow_kernel<LANES, 768, 8, true>; }
+    if (v.threads == 512 && v.unroll == 8) { *threads = 512; return (const void *)poisson_dataflow_kernel<LANES, 512, 8, true>; }
+    if (v.threads == 256) { *threads = 256; return (const void *)poisson_dataflow_kernel<LANES, 256, 16, true>; }
+    *threads = 512;
+    return (const void *)poisson_dataflow_kernel<LANES, 512, 16, true>;
+}
+
+static int dataflow_version()          // GLB_POISSON_DF=1 keeps the first-generation kernel for A/B runs
+{
+    const char *e = getenv("GLB_POISSON_DF");
+    return (e && atoi(e) == 1) ? 1 : 2;
 }
 
 static const void *pick_dataflow(int lanes, int *threads)
 {
     const PersistVariant v = persist_variant(512, 16);     // r1i probe (profiles/): one batch per row keeps the producers ahead
+    if (dataflow_version() == 2) {
+        switch (lanes) {
+            case 1: return dataflow2_fn<1>(v, threads);
+            case 2: return dataflow2_fn<2>(v, threads);
+            case 4: return dataflow2_fn<4>(v, threads);
+            case 8: return dataflow2_fn<8>(v, threads);
+            case 16: return dataflow2_fn<16>(v, threads);
+            default: return dataflow2_fn<32>(v, threads);
+        }
+    }
     switch (lanes) {
         case 1: return dataflow_fn<1>(v, threads);
         case 2: return dataflow_fn<2>(v, threads);
@@ -760,7 +858,9 @@ static int plan_try_dataflow(glb_poisson_plan *p, const std::vector<int> &h_rp, 
     const int lanes = flagged_lanes(p->c);
     if (!lanes) return 0;
     const int rowb = lanes * 16, rpw = 32 / lanes;
-    if ((double)n * rowb >= 4294967295.0 || n >= kRowSrcBit) return 0;
+    if ((double)(n + 1) * rowb >= 4294967295.0 || n >= kRowSrcBit) return 0;
+    const bool v2 = dataflow_version() == 2;
+    const unsigned pad_off = v2 ? (unsigned)n * (unsigned)rowb : kPadOff;     // V2: the scratch row n (value 0, always ready)
     int grid = (int)((n + 63) / 64);                  // tiny graphs: at least ~64 rows per CTA
     if (grid > sms) grid = sms;
     if (grid < 1) grid = 1;
@@ -874,9 +974,13 @@ static int plan_try_dataflow(glb_poisson_plan *p, const std::vector<int> &h_rp, 
                 const Slot &sl = cta_slots[per_warp[w][k]];
                 slots.push_back(make_int4((int)((long long)slab.size() - base0), sl.L, sl.type | (sl.nparts << 8), sl.pbuf));
                 for (int g = 0; g < rpw; ++g) slot_rows.push_back(sl.rows[g]);
+                // V1: entry j of lane group g at j * rpw + g.  V2: entries in pairs, (j/2 * rpw + g) * 2 + (j & 1), width
+                // rounded up to even.
+                const int Lst = v2 ? (sl.L + 1) & ~1 : sl.L;
+                const size_t s0 = slab.size();
+                slab.resize(s0 + (size_t)Lst * rpw, make_int2((int)pad_off, 0));
                 for (int j = 0; j < sl.L; ++j)
                     for (int g = 0; g < rpw; ++g) {
-                        int2 e = make_int2((int)kPadOff, 0);
                         int q = -1;
                         if (sl.type == kSlotNormal) {
                             const int r = sl.rows[g];
@@ -885,8 +989,9 @@ static int plan_try_dataflow(glb_poisson_plan *p, const std::vector<int> &h_rp, 
                             const int qq = sl.nz0 + j * rpw + g;          // round-robin over the lane groups
                             if (qq < sl.nz1) q = qq;
                         }
-                        if (q >= 0) e = make_int2((int)((unsigned)h_col[q] * (unsigned)rowb), float_bits(h_val[q]));
-                        slab.push_back(e);
+                        if (q < 0) continue;
+                        const size_t at = v2 ? s0 + ((size_t)(j / 2) * rpw + g) * 2 + (j & 1) : s0 + (size_t)j * rpw + g;
+                        slab[at] = make_int2((int)((unsigned)h_col[q] * (unsigned)rowb), float_bits(h_val[q]));
                     }
             }
         slab_off[b + 1] = (long long)slab.size();
@@ -919,6 +1024,7 @@ static int plan_try_dataflow(glb_poisson_plan *p, const std::vector<int> &h_rp, 
     p->ldu = lanes * 4;
     p->grid = grid; p->threads = threads; p->fn = fn; p->smem_bytes = smem;
     p->cap_entries = cap_entries; p->cap_slots = cap_slots; p->cap_parts = cap_parts;
+    p->scratch_row = v2 ? 1 : 0;
     p->ell_fill = slab.size() ? (double)nnz / (double)slab.size() : 1.0;
     GLB_CUDA(cudaMalloc(&p->d_gate, sizeof(unsigned)));
     if (getenv("GLB_POISSON_STATS")) {
@@ -1077,6 +1183,7 @@ extern "C" GLB_API int glb_poisson_plan_destroy(glb_poisson_plan *plan)
 
 extern "C" GLB_API int glb_poisson_plan_kind(const glb_poisson_plan *plan) { return plan ? plan->kind : GLB_E_INVALID; }
 extern "C" GLB_API int glb_poisson_plan_ld(const glb_poisson_plan *plan) { return plan ? plan->ldu : GLB_E_INVALID; }
+extern "C" GLB_API int64_t glb_poisson_plan_rows(const glb_poisson_plan *plan) { return plan ? plan->n + plan->scratch_row : GLB_E_INVALID; }
 extern "C" GLB_API double glb_poisson_plan_fill(const glb_poisson_plan *plan) { return plan ? plan->ell_fill : 0.0; }
 extern "C" GLB_API int glb_poisson_plan_gate(const glb_poisson_plan *plan) { return plan && plan->kind == GLB_POISSON_KIND_DATAFLOW ? plan->gate_every : 0; }
 
@@ -1139,7 +1246,8 @@ extern "C" GLB_API int glb_poisson_iterate(glb_poisson_plan *plan, const float *
         unsigned *gate = getenv("GLB_POISSON_NOGATE") ? nullptr : plan->d_gate;
         if (gate) GLB_CUDA(cudaMemsetAsync(gate, 0, sizeof(unsigned), st));
         int gate_every = getenv("GLB_POISSON_GATE_EVERY") ? atoi(getenv("GLB_POISSON_GATE_EVERY")) : plan->gate_every;
-        stamp_kernel<<<stream_blocks_p(plan->n * (plan->ldu / 4)), 256, 0, st>>>(d_u0, d_u1, plan->n * (plan->ldu / 4));
+        stamp_kernel<<<stream_blocks_p(plan->n * (plan->ldu / 4)), 256, 0, st>>>(d_u0, d_u1, plan->n * (plan->ldu / 4),
+                                                                                 plan->scratch_row ? plan->ldu / 4 : 0);
         void *args[] = {(void *)&plan->d_slabs, (void *)&plan->d_slab_off, (void *)&plan->d_slots, (void *)&plan->d_slot_off,
                         (void *)&plan->d_slot_rows, (void *)&d_Db, (void *)&d_u0, (void *)&d_u1, (void *)&T,
                         (void *)&plan->cap_entries, (void *)&plan->cap_slots, (void *)&plan->cap_parts, (void *)&plan->d_stats,

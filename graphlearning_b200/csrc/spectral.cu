@@ -19,9 +19,9 @@ namespace glb {
 namespace {
 
 // ---------------------------------------------------------------------------------------------------------
-// SpMM: one warp per row, lane l owns columns {2l, 2l+1} + 64 p, p < CP
+// SpMM: one warp per row, lane l owns columns {2l, 2l+1} + 64 p, p < CP; sums run in stored order
 // ---------------------------------------------------------------------------------------------------------
-template <int CP>
+template <int CP, int UN>
 __global__ void __launch_bounds__(256)
 spmm_f64_kernel(const int *__restrict__ rowptr, const int *__restrict__ col, const double *__restrict__ val, long long n,
                 const double *__restrict__ X, int ldx, double *__restrict__ Z, int ldz, int c, double alpha,
@@ -35,36 +35,28 @@ spmm_f64_kernel(const int *__restrict__ rowptr, const int *__restrict__ col, con
 #pragma unroll
     for (int p = 0; p < CP; ++p) acc[p] = make_double2(0.0, 0.0);
     const int beg = __ldg(rowptr + row), end = __ldg(rowptr + row + 1);
-    int k = beg;
-    for (; k + 1 < end; k += 2) {                               // two neighbour rows in flight
-        const int j0 = __ldg(col + k), j1 = __ldg(col + k + 1);
-        const double a0 = __ldg(val + k), a1 = __ldg(val + k + 1);
-        const double *x0 = X + (size_t)j0 * ldx, *x1 = X + (size_t)j1 * ldx;
-        double2 v0[CP], v1[CP];
+    for (int k = beg; k < end; k += UN) {                       // UN neighbour rows in flight (UN * CP 16-byte loads per lane)
+        double a[UN];
+        double2 v[UN][CP];
 #pragma unroll
-        for (int p = 0; p < CP; ++p) {
-            const int cc = 2 * lane + 64 * p;
-            v0[p] = v1[p] = make_double2(0.0, 0.0);
-            if (cc < c) { v0[p] = *reinterpret_cast<const double2 *>(x0 + cc); v1[p] = *reinterpret_cast<const double2 *>(x1 + cc); }
-        }
+        for (int u = 0; u < UN; ++u) {
+            const bool on = k + u < end;
+            a[u] = on ? __ldg(val + k + u) : 0.0;
+            const double *x = X + (size_t)(on ? __ldg(col + k + u) : 0) * ldx;
 #pragma unroll
-        for (int p = 0; p < CP; ++p) {
-            acc[p].x = fma(a0, v0[p].x, acc[p].x); acc[p].y = fma(a0, v0[p].y, acc[p].y);
-            acc[p].x = fma(a1, v1[p].x, acc[p].x); acc[p].y = fma(a1, v1[p].y, acc[p].y);
-        }
-    }
-    if (k < end) {
-        const int j0 = __ldg(col + k);
-        const double a0 = __ldg(val + k);
-        const double *x0 = X + (size_t)j0 * ldx;
-#pragma unroll
-        for (int p = 0; p < CP; ++p) {
-            const int cc = 2 * lane + 64 * p;
-            if (cc < c) {
-                const double2 v = *reinterpret_cast<const double2 *>(x0 + cc);
-                acc[p].x = fma(a0, v.x, acc[p].x); acc[p].y = fma(a0, v.y, acc[p].y);
+            for (int p = 0; p < CP; ++p) {
+                const int cc = 2 * lane + 64 * p;
+                v[u][p] = make_double2(0.0, 0.0);
+                if (on && cc < c) v[u][p] = *reinterpret_cast<const double2 *>(x + cc);
             }
         }
+#pragma unroll
+        for (int u = 0; u < UN; ++u)
+#pragma unroll
+            for (int p = 0; p < CP; ++p) {
+                acc[p].x = fma(a[u], v[u][p].x, acc[p].x);
+                acc[p].y = fma(a[u], v[u][p].y, acc[p].y);
+            }
     }
 #pragma unroll
     for (int p = 0; p < CP; ++p) {
@@ -149,42 +141,53 @@ __global__ void __launch_bounds__(256) gram_reduce_kernel(const double *__restri
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Right multiply: Y = X S.  CTA = 32 rows; thread t: row t/8, output columns t%8 + 8 j.
+// Right multiply: Y = X S.  CTA = 64 rows, the inner dimension is walked in chunks of 16 staged in shared memory;
+// thread t owns rows t/8 and t/8 + 32 and output columns t%8 + 8 j, j < TJ.
 // ---------------------------------------------------------------------------------------------------------
+constexpr int kRmRows = 64, kRmK = 16;
 template <int TJ>
 __global__ void __launch_bounds__(256)
-right_mul_kernel(const double *__restrict__ X, int ldx, long long n, int c1, const double *__restrict__ S, int c2,
-                 double *__restrict__ Y, int ldy)
+right_mul_kernel(const double *__restrict__ X, int ldx, long long n, int c1, const double *__restrict__ S, int lds, int c2,
+                 double *__restrict__ Y, int ldy, int wlim)
 {
-    extern __shared__ double sm[];
-    double *ss = sm;                       // c1 x (8*TJ), zero padded
-    double *sx = sm + (size_t)c1 * 8 * TJ; // 32 x c1
-    const int W = 8 * TJ;
-    for (int i = threadIdx.x; i < c1 * W; i += 256) {
-        const int r = i / W, cc = i % W;
-        ss[i] = cc < c2 ? S[(size_t)r * c2 + cc] : 0.0;
-    }
-    const long long r0 = (long long)blockIdx.x * 32;
-    for (int i = threadIdx.x; i < 32 * c1; i += 256) {
-        const int r = i / c1, cc = i % c1;
-        sx[i] = (r0 + r < n) ? X[(size_t)(r0 + r) * ldx + cc] : 0.0;
-    }
-    __syncthreads();
+    // S: c1 x c2 panel with row stride lds; columns c2..wlim-1 of Y are written as zeros
+    constexpr int W = 8 * TJ;
+    __shared__ double ss[kRmK * W];            // chunk of S, zero padded to W columns
+    __shared__ double sx[kRmRows * (kRmK + 1)];
+    const long long r0 = (long long)blockIdx.x * kRmRows;
     const int r = threadIdx.x >> 3, cg = threadIdx.x & 7;
-    double acc[TJ];
+    double acc0[TJ], acc1[TJ];
 #pragma unroll
-    for (int j = 0; j < TJ; ++j) acc[j] = 0.0;
-    for (int kk = 0; kk < c1; ++kk) {
-        const double x = sx[r * c1 + kk];
-#pragma unroll
-        for (int j = 0; j < TJ; ++j) acc[j] = fma(x, ss[kk * W + cg + 8 * j], acc[j]);
-    }
-    if (r0 + r < n) {
-#pragma unroll
-        for (int j = 0; j < TJ; ++j) {
-            const int cc = cg + 8 * j;
-            if (cc < ldy) Y[(size_t)(r0 + r) * ldy + cc] = cc < c2 ? acc[j] : 0.0;      // padding columns are zeroed
+    for (int j = 0; j < TJ; ++j) acc0[j] = acc1[j] = 0.0;
+    for (int k0 = 0; k0 < c1; k0 += kRmK) {
+        const int kc = min(kRmK, c1 - k0);
+        for (int i = threadIdx.x; i < kRmK * W; i += 256) {
+            const int kk = i / W, cc = i % W;
+            ss[i] = (kk < kc && cc < c2) ? S[(size_t)(k0 + kk) * lds + cc] : 0.0;
         }
+        for (int i = threadIdx.x; i < kRmRows * kRmK; i += 256) {
+            const int rr = i / kRmK, kk = i % kRmK;
+            sx[rr * (kRmK + 1) + kk] = (r0 + rr < n && kk < kc) ? X[(size_t)(r0 + rr) * ldx + k0 + kk] : 0.0;
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int kk = 0; kk < kRmK; ++kk) {
+            const double x0 = sx[r * (kRmK + 1) + kk], x1 = sx[(r + 32) * (kRmK + 1) + kk];
+#pragma unroll
+            for (int j = 0; j < TJ; ++j) {
+                const double sv = ss[kk * W + cg + 8 * j];
+                acc0[j] = fma(x0, sv, acc0[j]);
+                acc1[j] = fma(x1, sv, acc1[j]);
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int j = 0; j < TJ; ++j) {
+        const int cc = cg + 8 * j;
+        if (cc >= wlim) continue;
+        if (r0 + r < n) Y[(size_t)(r0 + r) * ldy + cc] = cc < c2 ? acc0[j] : 0.0;           // padding columns are zeroed
+        if (r0 + r + 32 < n) Y[(size_t)(r0 + r + 32) * ldy + cc] = cc < c2 ? acc1[j] : 0.0;
     }
 }
 
@@ -198,11 +201,10 @@ int launch_gram(const double *X, int ldx, int c1, const double *Y, int ldy, int 
 }
 
 template <int TJ>
-int launch_right_mul(const double *X, int ldx, long long n, int c1, const double *S, int c2, double *Y, int ldy, cudaStream_t st)
+int launch_right_mul(const double *X, int ldx, long long n, int c1, const double *S, int lds, int c2, double *Y, int ldy, int wlim,
+                     cudaStream_t st)
 {
-    const size_t smem = ((size_t)c1 * 8 * TJ + 32 * (size_t)c1) * sizeof(double);
-    GLB_CUDA(cudaFuncSetAttribute(right_mul_kernel<TJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    right_mul_kernel<TJ><<<ceil_div(n, 32), 256, smem, st>>>(X, ldx, n, c1, S, c2, Y, ldy);
+    right_mul_kernel<TJ><<<ceil_div(n, kRmRows), 256, 0, st>>>(X, ldx, n, c1, S, lds, c2, Y, ldy, wlim);
     return 0;
 }
 
@@ -227,8 +229,8 @@ extern "C" GLB_API int glb_spmm_f64(const int32_t *d_rowptr, const int32_t *d_co
     cudaStream_t st = (cudaStream_t)stream;
     const int grid = ceil_div(n * 32, 256);
     const int cp = (c + 63) / 64;
-#define GLB_SPMM(CP) spmm_f64_kernel<CP><<<grid, 256, 0, st>>>(d_rowptr, d_col, d_val, n, d_X, ldx, d_Z, ldz, c, alpha, d_Y1, ldy1, beta, d_bcol, d_Y2, ldy2, gamma)
-    if (cp == 1) GLB_SPMM(1); else if (cp == 2) GLB_SPMM(2); else if (cp == 3) GLB_SPMM(3); else GLB_SPMM(4);
+#define GLB_SPMM(CP, UN) spmm_f64_kernel<CP, UN><<<grid, 256, 0, st>>>(d_rowptr, d_col, d_val, n, d_X, ldx, d_Z, ldz, c, alpha, d_Y1, ldy1, beta, d_bcol, d_Y2, ldy2, gamma)
+    if (cp == 1) GLB_SPMM(1, 8); else if (cp == 2) GLB_SPMM(2, 4); else if (cp == 3) GLB_SPMM(3, 2); else GLB_SPMM(4, 2);
 #undef GLB_SPMM
     GLB_LAUNCH_CHECK();
     return 0;
@@ -236,7 +238,7 @@ extern "C" GLB_API int glb_spmm_f64(const int32_t *d_rowptr, const int32_t *d_co
 
 extern "C" GLB_API int64_t glb_gram_work_bytes(int c1, int c2)
 {
-    return (int64_t)sm_count() * 2 * c1 * c2 * (int64_t)sizeof(double);
+    return ((int64_t)sm_count() * 2 * c1 * c2 + 128 * 128) * (int64_t)sizeof(double);
 }
 
 extern "C" GLB_API int glb_gram_f64(const double *d_X, int ldx, int c1, const double *d_Y, int ldy, int c2, int64_t n,
@@ -293,12 +295,19 @@ extern "C" GLB_API int glb_right_mul_f64(const double *d_X, int ldx, int64_t n, 
     GLB_CHECK_ARG(n > 0 && c1 > 0 && c2 > 0 && c1 <= kMaxBlockCols && c2 <= kMaxBlockCols && ldx >= c1 && ldy >= c2, "bad shape");
     GLB_CHECK_ARG(d_Y != d_X, "Y must not alias X");
     cudaStream_t st = (cudaStream_t)stream;
-    const int tj = (std::max(c2, std::min(ldy, kMaxBlockCols)) + 7) / 8;      // cover the padding columns of Y too
-    int rc;
-    if (tj <= 4) rc = launch_right_mul<4>(d_X, ldx, n, c1, d_S, c2, d_Y, ldy, st);
-    else if (tj <= 8) rc = launch_right_mul<8>(d_X, ldx, n, c1, d_S, c2, d_Y, ldy, st);
-    else if (tj <= 16) rc = launch_right_mul<16>(d_X, ldx, n, c1, d_S, c2, d_Y, ldy, st);
-    else rc = launch_right_mul<32>(d_X, ldx, n, c1, d_S, c2, d_Y, ldy, st);
+    // panels of <= 128 output columns (16 accumulators per row and thread); the last panel also zeroes the padding
+    int rc = 0;
+    for (int j0 = 0; j0 < c2 && !rc; j0 += 128) {
+        const int cj = std::min(128, c2 - j0);
+        const bool last = j0 + cj == c2;
+        const int ldp = last ? std::min(ldy - j0, 128) : cj;             // columns this panel may write
+        const int tj = (std::max(cj, ldp) + 7) / 8;
+        // a panel sees S and Y shifted by j0 columns; its "c2" is cj, its padding limit ldp
+        if (tj <= 2) rc = launch_right_mul<2>(d_X, ldx, n, c1, d_S + j0, c2, cj, d_Y + j0, ldy, ldp, st);
+        else if (tj <= 4) rc = launch_right_mul<4>(d_X, ldx, n, c1, d_S + j0, c2, cj, d_Y + j0, ldy, ldp, st);
+        else if (tj <= 8) rc = launch_right_mul<8>(d_X, ldx, n, c1, d_S + j0, c2, cj, d_Y + j0, ldy, ldp, st);
+        else rc = launch_right_mul<16>(d_X, ldx, n, c1, d_S + j0, c2, cj, d_Y + j0, ldy, ldp, st);
+    }
     if (rc) return rc;
     GLB_LAUNCH_CHECK();
     return 0;

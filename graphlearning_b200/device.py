@@ -141,6 +141,10 @@ class PoissonOperator:
     def ld(self, c=None):
         return int(_lib.load().glb_poisson_plan_ld(self.plan(c)))
 
+    def rows(self, c=None):
+        """Rows of a device label matrix: n, plus the library's scratch row for the dataflow kernel."""
+        return int(_lib.load().glb_poisson_plan_rows(self.plan(c)))
+
     def fill(self, c=None):
         return float(_lib.load().glb_poisson_plan_fill(self.plan(c)))
 
@@ -156,7 +160,7 @@ class PoissonOperator:
         X = torch.as_tensor(X, dtype=torch.float64).to(self.deg.device).contiguous()
         n, c = X.shape
         plan = self.plan(c)
-        out = torch.empty((n, self.ld(c)), dtype=torch.float32, device=X.device)
+        out = torch.zeros((self.rows(c), self.ld(c)), dtype=torch.float32, device=X.device)
         _lib.call("glb_poisson_pack", plan, ptr(X), ptr(self.deg) if scale_by_degree else None, ptr(self.perm), ptr(out),
                   cur_stream())
         return out
@@ -165,7 +169,7 @@ class PoissonOperator:
         torch = _torch()
         plan = self.plan(c)
         c = self._last_c
-        out = torch.empty((U.shape[0], c), dtype=torch.float64, device=U.device)
+        out = torch.empty((self.n, c), dtype=torch.float64, device=U.device)
         _lib.call("glb_poisson_unpack", plan, ptr(U), ptr(self.perm), ptr(out), cur_stream())
         return out
 

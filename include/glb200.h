@@ -91,9 +91,11 @@ GLB_API int glb_csr_permute(const int32_t *d_rowptr, const int32_t *d_col, const
  * GLB_POISSON_KIND_AUTO picks the first applicable one in that order; asking for a specific kind that does
  * not apply returns GLB_E_UNSUPPORTED.
  *
- * Device label matrices (Db, u) are row-major n x glb_poisson_plan_ld(plan) fp32 in the plan's layout: plain
- * (columns 0..c-1, zero padded) or, for the dataflow kernel, chunks {x[3q], x[3q+1], x[3q+2], epoch}.
- * glb_poisson_pack / glb_poisson_unpack convert from / to the reference's n x c float64 arrays.
+ * Device label matrices (Db, u) are row-major glb_poisson_plan_rows(plan) x glb_poisson_plan_ld(plan) fp32 in the
+ * plan's layout: plain (columns 0..c-1, zero padded) or, for the dataflow kernel, chunks {x[3q], x[3q+1], x[3q+2],
+ * epoch}.  rows = n, or n + 1 for the dataflow kernel: row n is a scratch row owned by the library (the padding
+ * entries of its slabs point there); allocate it, never read it.
+ * glb_poisson_pack / glb_poisson_unpack convert rows 0..n-1 from / to the reference's n x c float64 arrays.
  * ------------------------------------------------------------------------------------------- */
 #define GLB_POISSON_KIND_AUTO     (-1)
 #define GLB_POISSON_KIND_STEP     0
@@ -105,6 +107,7 @@ GLB_API int glb_poisson_plan_create(glb_poisson_plan **plan, const int32_t *d_ro
 GLB_API int glb_poisson_plan_destroy(glb_poisson_plan *plan);
 GLB_API int glb_poisson_plan_kind(const glb_poisson_plan *plan);
 GLB_API int glb_poisson_plan_ld(const glb_poisson_plan *plan);
+GLB_API int64_t glb_poisson_plan_rows(const glb_poisson_plan *plan);
 /* nnz / stored entries of the dataflow kernel's sliced-ELL slabs (1.0 = no padding; 0 for other kinds) */
 GLB_API double glb_poisson_plan_fill(const glb_poisson_plan *plan);
 /* iterations between two re-alignment gates of the dataflow kernel (tuned at plan time; 0 for other kinds) */
