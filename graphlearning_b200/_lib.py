@@ -33,6 +33,7 @@ SIGNATURES = {
     "glb_poisson_plan_kind": (c_int, [c_void_p]),
     "glb_poisson_plan_ld": (c_int, [c_void_p]),
     "glb_poisson_plan_rows": (c_int64, [c_void_p]),
+    "glb_poisson_plan_check": (c_int, [c_void_p, c_void_p]),
     "glb_poisson_plan_fill": (c_double, [c_void_p]),
     "glb_poisson_plan_gate": (c_int, [c_void_p]),
     "glb_poisson_pack": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -216,7 +216,7 @@ extern "C" GLB_API int glb_poisson_graph_fit(glb_poisson_graph *g, const double 
     if ((rc = glb_poisson_unpack(g->plan, in_u1 ? g->u1 : g->u0, g->perm, g->src64, st))) return rc;
     nl += 1;
     GLB_CUDA(cudaMemcpyAsync(h_u_out, g->src64, n * c * sizeof(double), cudaMemcpyDeviceToHost, st));
-    GLB_CUDA(cudaStreamSynchronize(st));
+    if ((rc = glb_poisson_plan_check(g->plan, st))) return rc;          // synchronises
     if (T_done) *T_done = T;
     if (launches) *launches = nl;
     return 0;

@@ -58,6 +58,19 @@ __device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long
 }
 __device__ __forceinline__ void fence_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 
+// Watchdog of the waiting loops (a wait normally ends within microseconds): after ~2 s without progress the flag is
+// raised, every other loop sees it within a thousand spins, the kernel drains and the host entry point reports
+// GLB_E_TIMEOUT instead of leaving a hung GPU.  counter[1] is the flag (counter[0] the barrier counter).
+constexpr long long kWaitLimit = 4000000000ll;
+__device__ __forceinline__ bool wait_expired(unsigned *flag, unsigned &spins, long long &t0)
+{
+    if ((++spins & 1023u) != 0u) return false;
+    if (t0 == 0) { t0 = clock64(); return false; }
+    if (ld_relaxed_u32(flag) != 0u) return true;
+    if (clock64() - t0 > kWaitLimit) { asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(flag), "r"(1u) : "memory"); return true; }
+    return false;
+}
+
 // Grid barrier that also returns the maximum of one non-negative double per thread (the sweep's error).
 // slots[3]: sweep t accumulates into slots[t % 3]; slot (t+1) % 3 is cleared during sweep t (its last readers left
 // it before the barrier that ended sweep t-1).
@@ -80,7 +93,9 @@ __device__ __forceinline__ double barrier_max(double mine, unsigned long long *s
         fence_gpu();
         asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(counter), "r"(1u) : "memory");
         const unsigned want = (t + 1) * gridDim.x;
-        while (ld_relaxed_u32(counter) < want) { }
+        unsigned spins = 0;
+        long long t0 = 0;
+        while (ld_relaxed_u32(counter) < want && !wait_expired(counter + 1, spins, t0)) { }
         fence_gpu();
         s_max = ld_relaxed_u64(slots + t % 3);
     }
@@ -263,8 +278,11 @@ __global__ void __launch_bounds__(256) lip_gauss_seidel_kernel(LipArgs A)
                 }
             }
             // phase 1: consume the neighbours in stored order as they become ready (retry loop, never a spin)
+            unsigned spins = 0;
+            long long tw0 = 0;
             while (__any_sync(0xffffffffu, pending)) {
                 if (!pending) continue;
+                if (wait_expired(A.counter + 1, spins, tw0)) { pending = false; continue; }
                 if (crit >= 0) {                                  // one cheap poll on the producer expected last
                     if (ld_cell(nxt + crit).b < want) { __nanosleep(64); continue; }
                     crit = -1;
@@ -407,7 +425,7 @@ int upload_common(Common &C, const int32_t *h_nbr, const int32_t *h_row, const d
     GLB_CUDA(C.A.alloc(&C.start, (size_t)n + 1)); GLB_CUDA(C.A.alloc(&C.nbr, (size_t)M)); GLB_CUDA(C.A.alloc(&C.row, (size_t)M));
     GLB_CUDA(C.A.alloc(&C.W, (size_t)M));         GLB_CUDA(C.A.alloc(&C.lab, (size_t)n)); GLB_CUDA(C.A.alloc(&C.labval, (size_t)m));
     GLB_CUDA(C.A.alloc(&C.c0, (size_t)n));        GLB_CUDA(C.A.alloc(&C.c1, (size_t)n));
-    GLB_CUDA(C.A.alloc(&C.slots, 4));             GLB_CUDA(C.A.alloc(&C.counter, 1));
+    GLB_CUDA(C.A.alloc(&C.slots, 4));             GLB_CUDA(C.A.alloc(&C.counter, 2));
     GLB_CUDA(C.A.alloc(&C.status, 1));            GLB_CUDA(C.A.alloc(&C.sweeps, 1));
     GLB_CUDA(cudaMemcpyAsync(C.nbr, h_nbr, (size_t)M * sizeof(int), cudaMemcpyHostToDevice, st));
     GLB_CUDA(cudaMemcpyAsync(C.row, h_row, (size_t)M * sizeof(int), cudaMemcpyHostToDevice, st));
@@ -415,7 +433,7 @@ int upload_common(Common &C, const int32_t *h_nbr, const int32_t *h_row, const d
     GLB_CUDA(cudaMemcpyAsync(C.lab, lab.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice, st));
     if (m) GLB_CUDA(cudaMemcpyAsync(C.labval, h_val, (size_t)m * sizeof(double), cudaMemcpyHostToDevice, st));
     GLB_CUDA(cudaMemsetAsync(C.slots, 0, 4 * sizeof(unsigned long long), st));
-    GLB_CUDA(cudaMemsetAsync(C.counter, 0, sizeof(unsigned), st));
+    GLB_CUDA(cudaMemsetAsync(C.counter, 0, 2 * sizeof(unsigned), st));
     GLB_CUDA(cudaMemsetAsync(C.status, 0, sizeof(int), st));
     GLB_CUDA(cudaMemsetAsync(C.sweeps, 0, sizeof(int), st));
     const int gb = sm_count() * 4;
@@ -514,7 +532,10 @@ extern "C" GLB_API int glb_lp_iterate_host(double *h_uu, double *h_ul, const int
     GLB_CUDA(cudaMemcpyAsync(h_uu, uu, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, st));
     GLB_CUDA(cudaMemcpyAsync(h_ul, ul, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, st));
     GLB_CUDA(cudaMemcpyAsync(&sw, C.sweeps, sizeof(int), cudaMemcpyDeviceToHost, st));
+    unsigned timed_out = 0;
+    GLB_CUDA(cudaMemcpyAsync(&timed_out, C.counter + 1, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
     GLB_CUDA(cudaStreamSynchronize(st));
+    if (timed_out) { set_error("%s: a waiting loop of the sweep kernel hit its watchdog; results are invalid", __func__); return GLB_E_TIMEOUT; }
     if (sweeps) *sweeps = sw;
     if (launches) *launches = nl;
     return 0;
@@ -557,7 +578,10 @@ extern "C" GLB_API int glb_lip_iterate_host(double *h_u, const int32_t *h_nbr, c
     int sw = 0;
     GLB_CUDA(cudaMemcpyAsync(h_u, u_out, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, st));
     GLB_CUDA(cudaMemcpyAsync(&sw, C.sweeps, sizeof(int), cudaMemcpyDeviceToHost, st));
+    unsigned timed_out = 0;
+    GLB_CUDA(cudaMemcpyAsync(&timed_out, C.counter + 1, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
     GLB_CUDA(cudaStreamSynchronize(st));
+    if (timed_out) { set_error("%s: a waiting loop of the sweep kernel hit its watchdog; results are invalid", __func__); return GLB_E_TIMEOUT; }
     if (sweeps) *sweeps = sw;
     if (launches) *launches = nl;
     return 0;

@@ -161,6 +161,20 @@ __device__ __forceinline__ void st_relaxed(unsigned *p, unsigned v)
 }
 __device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 
+// Watchdog of the polling loops: a poll normally ends within microseconds.  One that is still waiting after
+// kPollLimit cycles (~2 s) can only mean a broken invariant (wrong buffer size, a lost CTA); it raises the flag, every
+// other polling loop sees the flag within a thousand spins, the kernel drains with garbage results and
+// glb_poisson_plan_check reports GLB_E_TIMEOUT instead of a hung GPU.
+constexpr long long kPollLimit = 4000000000ll;
+__device__ __forceinline__ bool poll_expired(unsigned *watchdog, unsigned &spins, long long &t0)
+{
+    if ((++spins & 1023u) != 0u) return false;
+    if (t0 == 0) { t0 = clock64(); return false; }
+    if (ld_relaxed(watchdog) != 0u) return true;
+    if (clock64() - t0 > kPollLimit) { st_relaxed(watchdog, 1u); return true; }
+    return false;
+}
+
 // Grid-wide barrier between iterations (all CTAs are co-resident: cooperative launch, one per SM).
 // bar.sync orders the CTA's u stores before thread 0's release fence; the arrival is a relaxed red/st; the
 // waiters poll with relaxed loads (no L1 invalidation per poll) and issue ONE acquire fence when the epoch
@@ -342,7 +356,7 @@ __device__ __forceinline__ const char *df_addr(const char *base, unsigned off)
 
 template <int N, int RPW>
 __device__ __forceinline__ void df_batch(const int2 *cvp, const char *in, unsigned expect, int nopoll, float &a0, float &a1,
-                                         float &a2, unsigned long long &n_poll, unsigned long long &n_badbatch)
+                                         float &a2, unsigned long long &n_poll, unsigned long long &n_badbatch, unsigned *watchdog)
 {
     unsigned off[N];
     float val[N];
@@ -363,8 +377,11 @@ __device__ __forceinline__ void df_batch(const int2 *cvp, const char *in, unsign
     bool ok = true;
 #pragma unroll
     for (int i = 0; i < N; ++i) ok &= x[i].w >= expect;
+    unsigned spins = 0;
+    long long t0 = 0;
     while (!ok && !(nopoll & 1)) {                       // some producer is still behind: re-poll the stale chunks together
         ++n_badbatch;
+        if (poll_expired(watchdog, spins, t0)) break;
 #pragma unroll
         for (int i = 0; i < N; ++i)
             if (x[i].w < expect) { x[i] = ld_chunk(df_addr(in, off[i])); ++n_poll; }
@@ -386,7 +403,7 @@ poisson_dataflow_kernel(const int2 *__restrict__ slabs, const long long *__restr
                         const int4 *__restrict__ slots, const int *__restrict__ slot_off,
                         const int *__restrict__ slot_rows, const float *__restrict__ Db, float *u0, float *u1, int T,
                         int cap_entries, int cap_slots, int cap_parts, unsigned long long *stats, int nopoll,
-                        unsigned *start_gate, int gate_every)
+                        unsigned *start_gate, int gate_every, unsigned *watchdog)
 {
     constexpr int RPW = 32 / LANES;              // rows per warp pass = slice height of the ELL slab
     constexpr int NW = THREADS / 32;
@@ -425,7 +442,9 @@ poisson_dataflow_kernel(const int2 *__restrict__ slabs, const long long *__restr
     if (start_gate) {
         if (threadIdx.x == 0) {
             red_relaxed_add(start_gate, 1u);
-            while (ld_relaxed(start_gate) < gridDim.x) { }
+            unsigned spins = 0;
+            long long t0 = 0;
+            while (ld_relaxed(start_gate) < gridDim.x && !poll_expired(watchdog, spins, t0)) { }
         }
         __syncthreads();
     }
@@ -443,7 +462,9 @@ poisson_dataflow_kernel(const int2 *__restrict__ slabs, const long long *__restr
             if (threadIdx.x == 0) {
                 red_relaxed_add(start_gate, 1u);
                 const unsigned want = gridDim.x * (unsigned)(t / gate_every + 1);
-                while (ld_relaxed(start_gate) < want) { }
+                unsigned spins = 0;
+                long long t0 = 0;
+                while (ld_relaxed(start_gate) < want && !poll_expired(watchdog, spins, t0)) { }
             }
             __syncthreads();
         }
@@ -457,11 +478,11 @@ poisson_dataflow_kernel(const int2 *__restrict__ slabs, const long long *__restr
             if constexpr (V2) {
                 const int2 *cv = s_cv + sl.x + g * 2;        // pair q of this lane group: 16 bytes at cv[q * 2 * RPW]
                 int j = 0;
-                for (; j + U <= L; j += U) df_batch<U, RPW>(cv + j * RPW, in, expect, nopoll, a0, a1, a2, n_poll, n_badbatch);
-                if (U > 8 && (L & 8)) { df_batch<8, RPW>(cv + j * RPW, in, expect, nopoll, a0, a1, a2, n_poll, n_badbatch); j += 8; }
-                if (L & 4) { df_batch<4, RPW>(cv + j * RPW, in, expect, nopoll, a0, a1, a2, n_poll, n_badbatch); j += 4; }
-                if (L & 2) { df_batch<2, RPW>(cv + j * RPW, in, expect, nopoll, a0, a1, a2, n_poll, n_badbatch); j += 2; }
-                if (L & 1) df_batch<1, RPW>(cv + j * RPW, in, expect, nopoll, a0, a1, a2, n_poll, n_badbatch);
+                for (; j + U <= L; j += U) df_batch<U, RPW>(cv + j * RPW, in, expect, nopoll, a0, a1, a2, n_poll, n_badbatch, watchdog);
+                if (U > 8 && (L & 8)) { df_batch<8, RPW>(cv + j * RPW, in, expect, nopoll, a0, a1, a2, n_poll, n_badbatch, watchdog); j += 8; }
+                if (L & 4) { df_batch<4, RPW>(cv + j * RPW, in, expect, nopoll, a0, a1, a2, n_poll, n_badbatch, watchdog); j += 4; }
+                if (L & 2) { df_batch<2, RPW>(cv + j * RPW, in, expect, nopoll, a0, a1, a2, n_poll, n_badbatch, watchdog); j += 2; }
+                if (L & 1) df_batch<1, RPW>(cv + j * RPW, in, expect, nopoll, a0, a1, a2, n_poll, n_badbatch, watchdog);
             } else {
             const int2 *cv = s_cv + sl.x + g;                // entry j of this lane group: cv[j * RPW]
             for (int j0 = 0; j0 < L; j0 += U) {
@@ -483,8 +504,11 @@ poisson_dataflow_kernel(const int2 *__restrict__ slabs, const long long *__restr
                 unsigned bad = 0;
 #pragma unroll
                 for (int i = 0; i < U; ++i) bad |= x[i].w ^ expect;
+                unsigned spins = 0;
+                long long tw0 = 0;
                 while (bad && !(nopoll & 1)) {               // some producer is still behind: re-poll the stale chunks together
                     ++n_badbatch;
+                    if (poll_expired(watchdog, spins, tw0)) break;
 #pragma unroll
                     for (int i = 0; i < U; ++i)
                         if (x[i].w != expect) { x[i] = ld_chunk(in + off[i]); ++n_poll; }
@@ -521,7 +545,9 @@ poisson_dataflow_kernel(const int2 *__restrict__ slabs, const long long *__restr
                     const int nparts = sl.z >> 8;
                     for (int q = 0; q < nparts; ++q) {       // partial sums of the other warps, fixed order
                         volatile float *pb = s_part + ((size_t)((sl.w + q) * 2 + (t & 1)) * LANES + li) * 4;
-                        while (__float_as_uint(pb[3]) != expect + 1u && !(nopoll & 1)) { }
+                        unsigned spins = 0;
+                        long long tw0 = 0;
+                        while (__float_as_uint(pb[3]) != expect + 1u && !(nopoll & 1) && !poll_expired(watchdog, spins, tw0)) { }
                         __threadfence_block();
                         a0 += pb[0]; a1 += pb[1]; a2 += pb[2];
                     }
@@ -1026,7 +1052,8 @@ static int plan_try_dataflow(glb_poisson_plan *p, const std::vector<int> &h_rp, 
     p->cap_entries = cap_entries; p->cap_slots = cap_slots; p->cap_parts = cap_parts;
     p->scratch_row = v2 ? 1 : 0;
     p->ell_fill = slab.size() ? (double)nnz / (double)slab.size() : 1.0;
-    GLB_CUDA(cudaMalloc(&p->d_gate, sizeof(unsigned)));
+    GLB_CUDA(cudaMalloc(&p->d_gate, 2 * sizeof(unsigned)));          // [0] gate counter, [1] watchdog flag
+    GLB_CUDA(cudaMemsetAsync(p->d_gate, 0, 2 * sizeof(unsigned), st));
     if (getenv("GLB_POISSON_STATS")) {
         GLB_CUDA(cudaMalloc(&p->d_stats, 4 * sizeof(unsigned long long)));
     }
@@ -1073,7 +1100,8 @@ static int plan_try_barrier(glb_poisson_plan *p, const std::vector<int> &h_rp, i
 static int plan_time(glb_poisson_plan *p, float *ms, cudaStream_t st)
 {
     const int T = 96;
-    const size_t bytes = (size_t)p->n * p->ldu * sizeof(float);
+    const size_t rows = (size_t)p->n + (size_t)p->scratch_row;             // label matrices carry the scratch row
+    const size_t bytes = rows * p->ldu * sizeof(float);
     float *buf = nullptr;
     GLB_CUDA(cudaMalloc(&buf, 3 * bytes));
     cudaEvent_t e0, e1;
@@ -1082,11 +1110,12 @@ static int plan_time(glb_poisson_plan *p, float *ms, cudaStream_t st)
     cudaError_t ce = cudaMemsetAsync(buf, 0, 3 * bytes, st);
     for (int rep = 0; rep < 2 && rc == 0 && ce == cudaSuccess; ++rep) {
         cudaEventRecord(e0, st);
-        rc = glb_poisson_iterate(p, buf, buf + (size_t)p->n * p->ldu, buf + 2 * (size_t)p->n * p->ldu, T, nullptr, nullptr, st);
+        rc = glb_poisson_iterate(p, buf, buf + rows * p->ldu, buf + 2 * rows * p->ldu, T, nullptr, nullptr, st);
         cudaEventRecord(e1, st);
     }
     if (ce == cudaSuccess) ce = cudaEventSynchronize(e1);
     if (ce == cudaSuccess && rc == 0) cudaEventElapsedTime(ms, e0, e1);
+    if (ce == cudaSuccess && rc == 0) rc = glb_poisson_plan_check(p, st);
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     cudaFree(buf);
     if (rc == 0 && ce != cudaSuccess) { set_error("plan_time: %s", cudaGetErrorString(ce)); rc = (int)ce; }
@@ -1181,6 +1210,26 @@ extern "C" GLB_API int glb_poisson_plan_destroy(glb_poisson_plan *plan)
     return 0;
 }
 
+extern "C" GLB_API int glb_poisson_plan_check(glb_poisson_plan *plan, void *stream)
+{
+    GLB_CHECK_ARG(plan, "null plan");
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned flag = 0;
+    if (plan->d_gate) {
+        GLB_CUDA(cudaMemcpyAsync(&flag, plan->d_gate + 1, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+        GLB_CUDA(cudaStreamSynchronize(st));
+        if (flag) {
+            cudaMemsetAsync(plan->d_gate + 1, 0, sizeof(unsigned), st);
+            set_error("glb_poisson_iterate: a polling loop of the dataflow kernel timed out (label matrices smaller than "
+                      "glb_poisson_plan_rows x glb_poisson_plan_ld, or a CTA was lost); results are invalid");
+            return GLB_E_TIMEOUT;
+        }
+    } else {
+        GLB_CUDA(cudaStreamSynchronize(st));
+    }
+    return 0;
+}
+
 extern "C" GLB_API int glb_poisson_plan_kind(const glb_poisson_plan *plan) { return plan ? plan->kind : GLB_E_INVALID; }
 extern "C" GLB_API int glb_poisson_plan_ld(const glb_poisson_plan *plan) { return plan ? plan->ldu : GLB_E_INVALID; }
 extern "C" GLB_API int64_t glb_poisson_plan_rows(const glb_poisson_plan *plan) { return plan ? plan->n + plan->scratch_row : GLB_E_INVALID; }
@@ -1244,6 +1293,7 @@ extern "C" GLB_API int glb_poisson_iterate(glb_poisson_plan *plan, const float *
     if (plan->kind == GLB_POISSON_KIND_DATAFLOW) {
         int nopoll = getenv("GLB_POISSON_NOPOLL") ? atoi(getenv("GLB_POISSON_NOPOLL")) : 0;     // experiment only: ignores the epoch words (results are wrong)
         unsigned *gate = getenv("GLB_POISSON_NOGATE") ? nullptr : plan->d_gate;
+        unsigned *watchdog = plan->d_gate + 1;                // sticky: cleared only by glb_poisson_plan_check
         if (gate) GLB_CUDA(cudaMemsetAsync(gate, 0, sizeof(unsigned), st));
         int gate_every = getenv("GLB_POISSON_GATE_EVERY") ? atoi(getenv("GLB_POISSON_GATE_EVERY")) : plan->gate_every;
         stamp_kernel<<<stream_blocks_p(plan->n * (plan->ldu / 4)), 256, 0, st>>>(d_u0, d_u1, plan->n * (plan->ldu / 4),
@@ -1251,7 +1301,7 @@ extern "C" GLB_API int glb_poisson_iterate(glb_poisson_plan *plan, const float *
         void *args[] = {(void *)&plan->d_slabs, (void *)&plan->d_slab_off, (void *)&plan->d_slots, (void *)&plan->d_slot_off,
                         (void *)&plan->d_slot_rows, (void *)&d_Db, (void *)&d_u0, (void *)&d_u1, (void *)&T,
                         (void *)&plan->cap_entries, (void *)&plan->cap_slots, (void *)&plan->cap_parts, (void *)&plan->d_stats,
-                        (void *)&nopoll, (void *)&gate, (void *)&gate_every};
+                        (void *)&nopoll, (void *)&gate, (void *)&gate_every, (void *)&watchdog};
         if (plan->d_stats) GLB_CUDA(cudaMemsetAsync(plan->d_stats, 0, 4 * sizeof(unsigned long long), st));
         GLB_CUDA(cudaLaunchCooperativeKernel(plan->fn, dim3(plan->grid), dim3(plan->threads), args, plan->smem_bytes, st));
         if (plan->d_stats) {

@@ -170,6 +170,7 @@ class PoissonOperator:
         plan = self.plan(c)
         c = self._last_c
         out = torch.empty((self.n, c), dtype=torch.float64, device=U.device)
+        _lib.call("glb_poisson_plan_check", plan, cur_stream())        # raises if a polling loop hit its watchdog
         _lib.call("glb_poisson_unpack", plan, ptr(U), ptr(self.perm), ptr(out), cur_stream())
         return out
 

@@ -35,6 +35,7 @@ extern "C" {
 #define GLB_E_NOGPU     (-2)   /* no CUDA device / wrong architecture */
 #define GLB_E_NOMEM     (-3)
 #define GLB_E_UNSUPPORTED (-4)
+#define GLB_E_TIMEOUT   (-5)   /* a polling loop of a persistent kernel hit its watchdog; results are invalid */
 
 GLB_API int glb_version(void);
 GLB_API const char *glb_last_error(void);
@@ -108,6 +109,9 @@ GLB_API int glb_poisson_plan_destroy(glb_poisson_plan *plan);
 GLB_API int glb_poisson_plan_kind(const glb_poisson_plan *plan);
 GLB_API int glb_poisson_plan_ld(const glb_poisson_plan *plan);
 GLB_API int64_t glb_poisson_plan_rows(const glb_poisson_plan *plan);
+/* Synchronises the stream and reports GLB_E_TIMEOUT if a polling loop of the dataflow kernel hit its ~2 s watchdog since
+ * the last check (the kernel then drains instead of hanging the GPU; the results of that launch are invalid). */
+GLB_API int glb_poisson_plan_check(glb_poisson_plan *plan, void *stream);
 /* nnz / stored entries of the dataflow kernel's sliced-ELL slabs (1.0 = no padding; 0 for other kinds) */
 GLB_API double glb_poisson_plan_fill(const glb_poisson_plan *plan);
 /* iterations between two re-alignment gates of the dataflow kernel (tuned at plan time; 0 for other kinds) */
