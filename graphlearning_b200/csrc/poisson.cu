@@ -319,7 +319,8 @@ poisson_persistent_kernel(const int *__restrict__ rowptr, const int *__restrict_
 // group in every iteration and a lane group finishes iteration t before it starts t + 1, so the chain holds
 // chunk by chunk without any fence.  Progress: the unfinished work item with the smallest iteration number
 // always has all its inputs, all CTAs are co-resident (cooperative launch), so no wait cycle can form.
-constexpr unsigned kPadOff = 0xFFFFFFFFu;        // (offset) of a padding entry of the sliced-ELL slab
+constexpr unsigned kPadOff = 0xFFFFFFFFu;        // (offset) of a padding entry of the sliced-ELL slab (first generation)
+constexpr int kScratchRows = 256;                // second generation: rows n .. n+255 of the label matrices are padding targets
 constexpr int kRowSrcBit = 0x40000000;           // slot_rows: row has a nonzero source term Db
 
 __device__ __forceinline__ uint4 ld_chunk(const char *p)
@@ -753,7 +754,8 @@ struct glb_poisson_plan {
     int tuned_gate = 32;
     unsigned *d_gate = nullptr;         // dataflow kernel: start gate counter
     int gate_every = 32;                // dataflow kernel: iterations between re-alignment gates (tuned at plan time)
-    int scratch_row = 0;                // 1: the label matrices carry a row n owned by the library (padding target of the V2 slabs)
+    int scratch_row = 0;                // > 0: the label matrices carry that many rows behind row n-1, owned by the library
+                                        // (padding targets of the V2 slabs)
     unsigned long long *d_stats = nullptr;   // GLB_POISSON_STATS=1: {re-polls, batches that had to poll, max warp cycles, CTAs}
 };
 
@@ -813,8 +815,9 @@ static const void *dataflow2_fn(const PersistVariant &v, int *threads)
     if (v.threads == 768) { *threads = 768; return (const void *)poisson_dataflow_kernel<LANES, 768, 8, true>; }
     if (v.threads == 512 && v.unroll == 8) { *threads = 512; return (const void *)poisson_dataflow_kernel<LANES, 512, 8, true>; }
     if (v.threads == 256) { *threads = 256; return (const void *)poisson_dataflow_kernel<LANES, 256, 16, true>; }
+    if (v.threads == 512 && v.unroll == 16) { *threads = 512; return (const void *)poisson_dataflow_kernel<LANES, 512, 16, true>; }
     *threads = 512;
-    return (const void *)poisson_dataflow_kernel<LANES, 512, 16, true>;
+    return (const void *)poisson_dataflow_kernel<LANES, 512, 8, true>;
 }
 
 static int dataflow_version()          // GLB_POISSON_DF=1 keeps the first-generation kernel for A/B runs
@@ -825,7 +828,8 @@ static int dataflow_version()          // GLB_POISSON_DF=1 keeps the first-gener
 
 static const void *pick_dataflow(int lanes, int *threads)
 {
-    const PersistVariant v = persist_variant(512, 16);     // r1i probe (profiles/): one batch per row keeps the producers ahead
+    const PersistVariant v = dataflow_version() == 2 ? persist_variant(512, 8)      // r1 visit 4: 16-entry batches spill
+                                                     : persist_variant(512, 16);    // r1i probe: one batch per row
     if (dataflow_version() == 2) {
         switch (lanes) {
             case 1: return dataflow2_fn<1>(v, threads);
@@ -884,9 +888,12 @@ static int plan_try_dataflow(glb_poisson_plan *p, const std::vector<int> &h_rp, 
     const int lanes = flagged_lanes(p->c);
     if (!lanes) return 0;
     const int rowb = lanes * 16, rpw = 32 / lanes;
-    if ((double)(n + 1) * rowb >= 4294967295.0 || n >= kRowSrcBit) return 0;
+    if ((double)(n + kScratchRows) * rowb >= 4294967295.0 || n >= kRowSrcBit) return 0;
     const bool v2 = dataflow_version() == 2;
-    const unsigned pad_off = v2 ? (unsigned)n * (unsigned)rowb : kPadOff;     // V2: the scratch row n (value 0, always ready)
+    // V2: padding entries gather one of the kScratchRows scratch rows behind row n-1 (value 0, always ready), dealt round
+    // robin so that no single L2 line takes all of them
+    unsigned pad_next = 0;
+    auto pad_off = [&]() -> unsigned { return v2 ? (unsigned)(n + (pad_next++ % kScratchRows)) * (unsigned)rowb : kPadOff; };
     int grid = (int)((n + 63) / 64);                  // tiny graphs: at least ~64 rows per CTA
     if (grid > sms) grid = sms;
     if (grid < 1) grid = 1;
@@ -1004,7 +1011,8 @@ static int plan_try_dataflow(glb_poisson_plan *p, const std::vector<int> &h_rp, 
                 // rounded up to even.
                 const int Lst = v2 ? (sl.L + 1) & ~1 : sl.L;
                 const size_t s0 = slab.size();
-                slab.resize(s0 + (size_t)Lst * rpw, make_int2((int)pad_off, 0));
+                slab.resize(s0 + (size_t)Lst * rpw);
+                for (size_t q = s0; q < slab.size(); ++q) slab[q] = make_int2((int)pad_off(), 0);
                 for (int j = 0; j < sl.L; ++j)
                     for (int g = 0; g < rpw; ++g) {
                         int q = -1;
@@ -1050,7 +1058,7 @@ static int plan_try_dataflow(glb_poisson_plan *p, const std::vector<int> &h_rp, 
     p->ldu = lanes * 4;
     p->grid = grid; p->threads = threads; p->fn = fn; p->smem_bytes = smem;
     p->cap_entries = cap_entries; p->cap_slots = cap_slots; p->cap_parts = cap_parts;
-    p->scratch_row = v2 ? 1 : 0;
+    p->scratch_row = v2 ? kScratchRows : 0;
     p->ell_fill = slab.size() ? (double)nnz / (double)slab.size() : 1.0;
     GLB_CUDA(cudaMalloc(&p->d_gate, 2 * sizeof(unsigned)));          // [0] gate counter, [1] watchdog flag
     GLB_CUDA(cudaMemsetAsync(p->d_gate, 0, 2 * sizeof(unsigned), st));
@@ -1297,7 +1305,7 @@ extern "C" GLB_API int glb_poisson_iterate(glb_poisson_plan *plan, const float *
         if (gate) GLB_CUDA(cudaMemsetAsync(gate, 0, sizeof(unsigned), st));
         int gate_every = getenv("GLB_POISSON_GATE_EVERY") ? atoi(getenv("GLB_POISSON_GATE_EVERY")) : plan->gate_every;
         stamp_kernel<<<stream_blocks_p(plan->n * (plan->ldu / 4)), 256, 0, st>>>(d_u0, d_u1, plan->n * (plan->ldu / 4),
-                                                                                 plan->scratch_row ? plan->ldu / 4 : 0);
+                                                                                 plan->scratch_row * (plan->ldu / 4));
         void *args[] = {(void *)&plan->d_slabs, (void *)&plan->d_slab_off, (void *)&plan->d_slots, (void *)&plan->d_slot_off,
                         (void *)&plan->d_slot_rows, (void *)&d_Db, (void *)&d_u0, (void *)&d_u1, (void *)&T,
                         (void *)&plan->cap_entries, (void *)&plan->cap_slots, (void *)&plan->cap_parts, (void *)&plan->d_stats,

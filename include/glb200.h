@@ -94,8 +94,8 @@ GLB_API int glb_csr_permute(const int32_t *d_rowptr, const int32_t *d_col, const
  *
  * Device label matrices (Db, u) are row-major glb_poisson_plan_rows(plan) x glb_poisson_plan_ld(plan) fp32 in the
  * plan's layout: plain (columns 0..c-1, zero padded) or, for the dataflow kernel, chunks {x[3q], x[3q+1], x[3q+2],
- * epoch}.  rows = n, or n + 1 for the dataflow kernel: row n is a scratch row owned by the library (the padding
- * entries of its slabs point there); allocate it, never read it.
+ * epoch}.  rows = n, or n + 256 for the dataflow kernel: rows n.. are scratch rows owned by the library (the padding
+ * entries of its slabs point there); allocate them, never read them.
  * glb_poisson_pack / glb_poisson_unpack convert rows 0..n-1 from / to the reference's n x c float64 arrays.
  * ------------------------------------------------------------------------------------------- */
 #define GLB_POISSON_KIND_AUTO     (-1)

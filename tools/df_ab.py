@@ -14,6 +14,8 @@ src = orc.poisson_source(W.shape[0], ti, labels[ti])[0]
 ref = None
 configs = [("1", "512,16", "0"), ("2", "512,16", "0"), ("2", "512,8", "0"), ("2", "1024,8", "0"), ("2", "768,8", "0"), ("2", "256,16", "0"),
            ("1", "512,16", "1"), ("2", "512,16", "1"), ("2", "1024,8", "1"), ("2", "512,16", "3"), ("1", "512,16", "0"), ("2", "512,16", "0")]
+if len(sys.argv) > 1 and sys.argv[1] == "short":
+    configs = [("1", "512,16", "0"), ("2", "512,8", "0"), ("2", "512,8", "1"), ("2", "512,8", "3"), ("1", "512,16", "0"), ("2", "512,8", "0")]
 for df, variant, nopoll in configs:
     os.environ["GLB_POISSON_DF"] = df
     os.environ["GLB_POISSON_VARIANT"] = variant
