@@ -178,13 +178,20 @@ __global__ void __launch_bounds__(256) lp_jacobi_kernel(LpArgs A)
             const double uu = me.a, ul = __longlong_as_double((long long)me.b);
             double minu = 0.0, maxu = 0.0, sumu = 0.0, minl = 0.0, maxl = 0.0, suml = 0.0;
             const int e = A.start[i + 1];
-            for (int k = A.start[i]; k < e; ++k) {
-                const Cell c = ld_cell(cur + __ldg(A.nbr + k));
-                const double w = __ldg(A.W + k);
-                const double du = __dmul_rn(w, __dsub_rn(c.a, uu));
-                const double dl = __dmul_rn(w, __dsub_rn(__longlong_as_double((long long)c.b), ul));
-                minu = du < minu ? du : minu;  maxu = du > maxu ? du : maxu;  sumu = __dadd_rn(sumu, du);
-                minl = dl < minl ? dl : minl;  maxl = dl > maxl ? dl : maxl;  suml = __dadd_rn(suml, dl);
+            for (int k0 = A.start[i]; k0 < e; k0 += 8) {                   // 8 gathers in flight, consumed in stored order
+                Cell c[8];
+                double w[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    if (k0 + q < e) { c[q] = ld_cell(cur + __ldg(A.nbr + k0 + q)); w[q] = __ldg(A.W + k0 + q); }
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    if (k0 + q >= e) continue;
+                    const double du = __dmul_rn(w[q], __dsub_rn(c[q].a, uu));
+                    const double dl = __dmul_rn(w[q], __dsub_rn(__longlong_as_double((long long)c[q].b), ul));
+                    minu = du < minu ? du : minu;  maxu = du > maxu ? du : maxu;  sumu = __dadd_rn(sumu, du);
+                    minl = dl < minl ? dl : minl;  maxl = dl > maxl ? dl : maxl;  suml = __dadd_rn(suml, dl);
+                }
             }
             const double idg = A.invdeg[i];
             double vu = __dadd_rn(uu, __dmul_rn(dt, __dadd_rn(__dmul_rn(idg, sumu), __dmul_rn(delta, __dadd_rn(minu, maxu)))));
@@ -233,6 +240,7 @@ struct LipArgs {
 };
 
 constexpr unsigned long long kVerFixed = ~0ull;      // Dirichlet rows: valid in every sweep
+constexpr int kLipBatch = 16;                        // neighbour cells in flight per retry (most rows: one round trip)
 constexpr int kLipCap = 32;                          // neighbour values kept in local memory for the bisection
 
 // One row per lane and round, rows dealt to lanes in LEVEL order (level = longest chain of same-sweep producers, computed
@@ -241,10 +249,10 @@ constexpr int kLipCap = 32;                          // neighbour values kept in
 // latest-level producer.  A lane must never spin on a cell: its producer may be another lane of the same warp
 // (a lower-numbered neighbour in the same round), and a lane that leaves a spin loop waits at the loop's
 // reconvergence point for the lanes still inside.  So the warp runs a retry loop instead: per pass every pending lane
-// consumes, IN STORED ORDER, as many of its neighbours as are ready (8 gathers in flight), keeps its running
+// consumes, IN STORED ORDER, as many of its neighbours as are ready (16 gathers in flight), keeps its running
 // (min, max, sum, degree) in registers, and finishes the row once all neighbours have been consumed.
 template <bool WEIGHTED>
-__global__ void __launch_bounds__(256) lip_gauss_seidel_kernel(LipArgs A)
+__global__ void __launch_bounds__(256, 2) lip_gauss_seidel_kernel(LipArgs A)
 {
     const int NT = gridDim.x * blockDim.x, gt = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
@@ -287,16 +295,16 @@ __global__ void __launch_bounds__(256) lip_gauss_seidel_kernel(LipArgs A)
                     if (ld_cell(nxt + crit).b < want) { __nanosleep(64); continue; }
                     crit = -1;
                 }
-                int jj[8];
-                Cell c[8];
+                int jj[kLipBatch];
+                Cell c[kLipBatch];
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
+                for (int q = 0; q < kLipBatch; ++q) {
                     jj[q] = k + q < L ? __ldg(A.nbr + s + k + q) : -1;
                     if (jj[q] >= 0) c[q] = ld_cell((jj[q] < i ? nxt : cur) + jj[q]);
                 }
                 bool stop = false;
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
+                for (int q = 0; q < kLipBatch; ++q) {
                     if (stop || jj[q] < 0) continue;
                     if (jj[q] < i && c[q].b < want) { stop = true; continue; }   // producer not there yet: retry from here
                     const double v = c[q].a;
