@@ -24,6 +24,7 @@
 // no deadlock (all CTAs co-resident: cooperative launch).  One grid barrier per sweep carries the error for the
 // stopping rule `err < tol && it > 20`.  Result: exactly the reference's sequential sweep, at any sweep count.
 #include <math.h>
+#include <stdlib.h>
 #include <vector>
 #include "common.cuh"
 
@@ -236,6 +237,7 @@ struct LipArgs {
     unsigned *counter;
     int *sweeps;
     int n, M, T, n_active;
+    int use_crit;                   // poll the latest-level producer alone before gathering the whole row
     double tol, alpha, beta;
 };
 
@@ -251,7 +253,7 @@ constexpr int kLipCap = 32;                          // neighbour values kept in
 // reconvergence point for the lanes still inside.  So the warp runs a retry loop instead: per pass every pending lane
 // consumes, IN STORED ORDER, as many of its neighbours as are ready (16 gathers in flight), keeps its running
 // (min, max, sum, degree) in registers, and finishes the row once all neighbours have been consumed.
-template <bool WEIGHTED>
+template <bool WEIGHTED, bool LOCKSTEP>
 __global__ void __launch_bounds__(256, 2) lip_gauss_seidel_kernel(LipArgs A)
 {
     const int NT = gridDim.x * blockDim.x, gt = blockIdx.x * blockDim.x + threadIdx.x;
@@ -276,7 +278,7 @@ __global__ void __launch_bounds__(256, 2) lip_gauss_seidel_kernel(LipArgs A)
             if (active) {
                 s = A.start[i];
                 L = A.start[i + 1] - s;
-                crit = __ldg(A.crit + i);
+                crit = A.use_crit ? __ldg(A.crit + i) : -1;
                 uold = ld_cell(cur + i).a;
                 if (L == 0) {
                     // the reference reads u[I[start[i]]] (the next row's first neighbour) even for an empty row (:163, :223):
@@ -285,47 +287,8 @@ __global__ void __launch_bounds__(256, 2) lip_gauss_seidel_kernel(LipArgs A)
                     if (s < A.M) L = 1; else { minu = maxu = qnan; }
                 }
             }
-            // phase 1: consume the neighbours in stored order as they become ready (retry loop, never a spin)
-            unsigned spins = 0;
-            long long tw0 = 0;
-            while (__any_sync(0xffffffffu, pending)) {
-                if (!pending) continue;
-                if (wait_expired(A.counter + 1, spins, tw0)) { pending = false; continue; }
-                if (crit >= 0) {                                  // one cheap poll on the producer expected last
-                    if (ld_cell(nxt + crit).b < want) { __nanosleep(64); continue; }
-                    crit = -1;
-                }
-                int jj[kLipBatch];
-                Cell c[kLipBatch];
-#pragma unroll
-                for (int q = 0; q < kLipBatch; ++q) {
-                    jj[q] = k + q < L ? __ldg(A.nbr + s + k + q) : -1;
-                    if (jj[q] >= 0) c[q] = ld_cell((jj[q] < i ? nxt : cur) + jj[q]);
-                }
-                bool stop = false;
-#pragma unroll
-                for (int q = 0; q < kLipBatch; ++q) {
-                    if (stop || jj[q] < 0) continue;
-                    if (jj[q] < i && c[q].b < want) { stop = true; continue; }   // producer not there yet: retry from here
-                    const double v = c[q].a;
-                    if (k == 0) { minu = v; maxu = v; }
-                    if (!empty_row) {
-                        const double w = __ldg(A.W + s + k);
-                        if (!WEIGHTED) {
-                            sumu = __dadd_rn(sumu, __dmul_rn(w, v));
-                            deg = __dadd_rn(deg, w);
-                        } else if (k < kLipCap) {
-                            uv[k] = v; wv[k] = w;
-                        }
-                    }
-                    minu = v < minu ? v : minu;
-                    maxu = v > maxu ? v : maxu;
-                    ++k;
-                }
-                if (k >= L) pending = false;
-            }
-            // phase 2: the whole warp updates its rows in lockstep
-            if (active) {
+            auto update_row = [&]() {
+
                 double ne;
                 if (!WEIGHTED) {
                     ne = __dadd_rn(__ddiv_rn(__dmul_rn(A.alpha, sumu), deg), __ddiv_rn(__dmul_rn(A.beta, __dadd_rn(minu, maxu)), 2.0));
@@ -355,7 +318,50 @@ __global__ void __launch_bounds__(256, 2) lip_gauss_seidel_kernel(LipArgs A)
                 d = d < 0.0 ? -d : d;
                 if (d > err) err = d;
                 st_cell(nxt + i, ne, want);
+            };
+            // phase 1: consume the neighbours in stored order as they become ready (retry loop, never a spin)
+            unsigned spins = 0;
+            long long tw0 = 0;
+            while (__any_sync(0xffffffffu, pending)) {
+                if (!pending) continue;
+                if (wait_expired(A.counter + 1, spins, tw0)) { pending = false; continue; }
+                if (crit >= 0) {                                  // one cheap poll on the producer expected last
+                    if (ld_cell(nxt + crit).b < want) continue;
+                    crit = -1;
+                }
+                int jj[kLipBatch];
+                Cell c[kLipBatch];
+#pragma unroll
+                for (int q = 0; q < kLipBatch; ++q) {
+                    jj[q] = k + q < L ? __ldg(A.nbr + s + k + q) : -1;
+                    if (jj[q] >= 0) c[q] = ld_cell((jj[q] < i ? nxt : cur) + jj[q]);
+                }
+                bool stop = false;
+#pragma unroll
+                for (int q = 0; q < kLipBatch; ++q) {
+                    if (stop || jj[q] < 0) continue;
+                    if (jj[q] < i && c[q].b < want) { stop = true; continue; }   // producer not there yet: retry from here
+                    const double v = c[q].a;
+                    if (k == 0) { minu = v; maxu = v; }
+                    if (!empty_row) {
+                        const double w = __ldg(A.W + s + k);
+                        if (!WEIGHTED) {
+                            sumu = __dadd_rn(sumu, __dmul_rn(w, v));
+                            deg = __dadd_rn(deg, w);
+                        } else if (k < kLipCap) {
+                            uv[k] = v; wv[k] = w;
+                        }
+                    }
+                    minu = v < minu ? v : minu;
+                    maxu = v > maxu ? v : maxu;
+                    ++k;
+                }
+                if (k < L) continue;
+                pending = false;
+                if (!LOCKSTEP) update_row();                      // store at once: the next level is waiting for it
             }
+            // lockstep variant: the whole warp updates its rows together (one pass through the 30-step bisection)
+            if (LOCKSTEP && active) update_row();
         }
         const double gerr = barrier_max(err, A.slots, A.counter, (unsigned)it);
         if (gerr < A.tol && it > 20) { done = it + 1; break; }
@@ -562,8 +568,20 @@ extern "C" GLB_API int glb_lip_iterate_host(double *h_u, const int32_t *h_nbr, c
     Common C;
     std::vector<int> lab, order, crit;
     if ((rc = upload_common(C, h_nbr, h_row, h_w, h_ind, h_val, n, M, m, st, &nl, lab))) return rc;
+    // Schedule (GLB_LIP_MODE overrides for experiments; bit 0 level order, bit 1 critical-producer poll, bit 2 lockstep):
+    //   AMLE (weighted): level order + producer poll + lockstep - the 30-step bisection dominates and runs once per
+    //                    warp with all 32 lanes busy;
+    //   unweighted:      rows in natural order, every lane gathers and stores on its own - the update is a handful of
+    //                    flops, so the shortest path from "last neighbour ready" to "value published" wins.
+    int mode = weighted ? 7 : 0;
+    if (getenv("GLB_LIP_MODE")) mode = atoi(getenv("GLB_LIP_MODE"));
+    if (mode & 4) mode |= 1;                                      // lockstep needs warps of one level
     int depth = 0;
     level_schedule(h_nbr, h_row, lab, n, M, order, crit, &depth);
+    if (!(mode & 1)) {
+        order.clear();
+        for (int i = 0; i < n; ++i) if (lab[i] < 0) order.push_back(i);
+    }
     double *u, *u_out;
     int *d_order, *d_crit;
     GLB_CUDA(C.A.alloc(&u, (size_t)n)); GLB_CUDA(C.A.alloc(&u_out, (size_t)n));
@@ -574,8 +592,9 @@ extern "C" GLB_API int glb_lip_iterate_host(double *h_u, const int32_t *h_nbr, c
     const int gb = sm_count() * 4;
     lip_pack_kernel<<<gb, 256, 0, st>>>(u, C.lab, C.labval, C.c0, C.c1, n);
     LipArgs A{C.start, C.nbr, C.W, C.lab, d_order, d_crit, C.c0, C.c1, u_out, C.slots, C.counter, C.sweeps, n, M, T,
-              (int)order.size(), tol, alpha, beta};
-    const void *fn = weighted ? (const void *)lip_gauss_seidel_kernel<true> : (const void *)lip_gauss_seidel_kernel<false>;
+              (int)order.size(), (mode & 2) ? 1 : 0, tol, alpha, beta};
+    const void *fn = weighted ? ((mode & 4) ? (const void *)lip_gauss_seidel_kernel<true, true> : (const void *)lip_gauss_seidel_kernel<true, false>)
+                              : ((mode & 4) ? (const void *)lip_gauss_seidel_kernel<false, true> : (const void *)lip_gauss_seidel_kernel<false, false>);
     int grid = 0;
     if ((rc = coop_grid(fn, 256, &grid))) return rc;
     grid = std::min(grid, std::max(1, ceil_div(n, 256)));
