@@ -49,8 +49,9 @@ def build_workload(seed=0):
     return sparse.csr_matrix(W), labels
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel (ncu, profiles/r1_*_ncu_details.txt)
-NCU_DRAM_BYTES_PER_LAUNCH = {"dataflow": 18520576 + 1468672, "barrier": 17295360 + 296704, "step": None}
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel (ncu --set full,
+# profiles/r1_dataflow_v2_nopoll_ncu_details.txt / r1_barrier_ncu_details.txt)
+NCU_DRAM_BYTES_PER_LAUNCH = {"dataflow": 18776064 + 1025024, "barrier": 17295360 + 296704, "step": None}
 
 
 def other_rows(W, labels, ti):

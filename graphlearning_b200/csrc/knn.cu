@@ -23,9 +23,13 @@
 // So the returned indices are those of an exact fp64 ranking (ties between exactly equal distances are broken by
 // index; the reference's tie order is unspecified, weightmatrix.py:352,359-361).
 //
-// Roofline: stage 2 is 2 n^2 d flops of fp32 FMA work (tensor-core version: next round); stages 2+3 move
+//   2b. knn_dist_tc_kernel  the same block on the tensor cores when d >= 64: bf16 hi/lo split, three tcgen05.mma per
+//                       k-step into one fp32 TMEM accumulator (see the kernel).
+// Roofline: stage 2 is 2 n^2 d flops (fp32 FMA for d < 64, 3 x bf16 tensor-core MMAs for d >= 64); stages 2+3 move
 // 2 * 4 n^2 bytes through HBM/L2 (the distance block), stage 4 gathers C rows of fp64 features per query.
+#include <cuda_bf16.h>
 #include <float.h>
+#include <stdlib.h>
 #include <math.h>
 #include <vector>
 #include "common.cuh"
@@ -166,6 +170,177 @@ knn_dist_kernel(const float *__restrict__ Xc, const float *__restrict__ norm2, i
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// 2b. distance block on the 5th-generation tensor cores (d >= 64): tcgen05.mma, accumulator in TMEM
+// ---------------------------------------------------------------------------------------------------------
+// The certificate of stage 4 needs the cross term to ~2^-16 relative, bf16 carries 2^-9.  The centred fp32 features are
+// split x = hi + lo (hi = bf16(x), lo = bf16(x - hi), |x - hi - lo| <= 2^-18 |x|) and the cross term is accumulated as
+// hi.hi + hi.lo + lo.hi - three bf16 MMAs per k-step into the same fp32 TMEM accumulator (the dropped lo.lo term and the
+// two split residuals are <= 3 * 2^-18 |x||y|).
+//
+// One CTA (128 threads) = one 128 x 128 tile of D.  Operands are K-major bf16 in shared memory in the canonical
+// no-swizzle UMMA layout: 8 x 16-byte core matrices, K-adjacent core matrices 128 B apart (LBO), 8-row groups
+// (BK/8) * 128 B apart (SBO); filled with 16-byte cp.async (out-of-range rows zero-filled), made visible to the async
+// proxy with fence.proxy.async.  Two stages of BK = 64: thread 0 issues the 3 * 4 tcgen05.mma (M = N = 128, K = 16) of a
+// stage and commits them to the stage's mbarrier, so the next stage's loads overlap the tensor-core work.  Epilogue:
+// warp w reads TMEM lanes 32w..32w+31 (one query row per thread) with tcgen05.ld 32x32b.x32, applies
+// max(0, |q|^2 + |x_j|^2 - 2 acc) and writes 128-byte runs of its row of D.
+constexpr int TBM = 128, TBN = 128, TBK = 64;
+constexpr int kTcThreads = 128;
+constexpr int kTcStageBytes = 4 * TBM * TBK * 2;                 // A hi, A lo, B hi, B lo
+constexpr int kTcSmemBytes = 2 * kTcStageBytes + 64;
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ unsigned long long umma_desc(unsigned saddr)
+{
+    // start address [0,14) | leading byte offset [16,30) = 128 B | stride byte offset [32,46) = 1024 B | version [46,48) = 1
+    // | layout type [61,64) = 0 (no swizzle); all offsets in 16-byte units
+    return (unsigned long long)((saddr & 0x3FFFFu) >> 4) | ((unsigned long long)(128u >> 4) << 16) |
+           ((unsigned long long)((TBK / 8 * 128u) >> 4) << 32) | (1ull << 46);
+}
+
+__device__ __forceinline__ void umma_bf16(unsigned tmem_d, unsigned long long adesc, unsigned long long bdesc, unsigned idesc, unsigned accumulate)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(unsigned mbar, unsigned parity)
+{
+    // bounded: a tensor-core batch completes within microseconds; ~1 s of polling means a broken descriptor -> trap
+    for (unsigned spins = 0; spins < (1u << 26); ++spins) {
+        unsigned done;
+        asm volatile("{\n\t.reg .pred p;\n\t"
+                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                     "selp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(done) : "r"(mbar), "r"(parity) : "memory");
+        if (done) return;
+    }
+    __trap();
+}
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+knn_dist_tc_kernel(const __nv_bfloat16 *__restrict__ Xh, const __nv_bfloat16 *__restrict__ Xl, const float *__restrict__ norm2, int n,
+                   int dpad, int q0, int nq, float *__restrict__ D, long long ldD)
+{
+    extern __shared__ __align__(1024) unsigned char tc_smem[];
+    unsigned long long *mbar = reinterpret_cast<unsigned long long *>(tc_smem + 2 * kTcStageBytes);       // [0,1] stage free, [2] done
+    unsigned *tmem_slot = reinterpret_cast<unsigned *>(tc_smem + 2 * kTcStageBytes + 32);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int row0 = q0 + blockIdx.y * TBM;                  // first query of the tile
+    const int col0 = blockIdx.x * TBN;                       // first database point of the tile
+    if (tid == 0) {
+        for (int i = 0; i < 3; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(mbar + i)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" ::"r"(smem_u32(tmem_slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const unsigned tmem_d = *tmem_slot;
+
+    // one stage = 4 operand blocks of 128 rows x 64 bf16; 16-byte chunk (r, c) of a block lives at (r/8)*1024 + c*128 + (r%8)*16
+    auto fill = [&](int stage, int k0) {
+        unsigned char *base = tc_smem + stage * kTcStageBytes;
+#pragma unroll
+        for (int it = 0; it < 4 * TBM * (TBK / 8) / kTcThreads; ++it) {      // 4096 chunks / 128 threads = 32
+            const int ch = it * kTcThreads + tid;
+            const int blk = ch >> 10, r = (ch >> 3) & 127, c = ch & 7;           // consecutive threads: the 8 chunks of a row
+            const int grow = (blk < 2 ? row0 : col0) + r;
+            const bool ok = blk < 2 ? (grow < q0 + nq && grow < n) : (grow < n);
+            const __nv_bfloat16 *src = ((blk & 1) ? Xl : Xh) + (size_t)(ok ? grow : 0) * dpad + k0 + c * 8;
+            const unsigned dst = smem_u32(base + blk * (TBM * TBK * 2) + (r >> 3) * 1024 + c * 128 + (r & 7) * 16);
+            const int bytes = ok ? 16 : 0;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    // instruction descriptor: D = F32 (bits 4-5 = 1), A = B = BF16 (bits 7-9, 10-12 = 1), K-major both, N >> 3 at 17, M >> 4 at 24
+    const unsigned idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(TBN >> 3) << 17) | ((unsigned)(TBM >> 4) << 24);
+    const int nkb = dpad / TBK;
+    fill(0, 0);
+    for (int kb = 0; kb < nkb; ++kb) {
+        const int stage = kb & 1;
+        if (kb + 1 < nkb) {
+            if (kb + 1 >= 2) mbar_wait(smem_u32(mbar + ((kb + 1) & 1)), (unsigned)(((kb - 1) >> 1) & 1));   // MMAs of block kb-1 done with that stage
+            fill((kb + 1) & 1, (kb + 1) * TBK);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const unsigned sb = smem_u32(tc_smem + stage * kTcStageBytes);
+            const unsigned a_hi = sb, a_lo = sb + TBM * TBK * 2, b_hi = sb + 2 * TBM * TBK * 2, b_lo = sb + 3 * TBM * TBK * 2;
+#pragma unroll
+            for (int ks = 0; ks < TBK / 16; ++ks) {            // K = 16 per instruction = two core matrices = 256 B
+                const unsigned o = ks * 256;
+                umma_bf16(tmem_d, umma_desc(a_hi + o), umma_desc(b_hi + o), idesc, (kb | ks) ? 1u : 0u);
+                umma_bf16(tmem_d, umma_desc(a_hi + o), umma_desc(b_lo + o), idesc, 1u);
+                umma_bf16(tmem_d, umma_desc(a_lo + o), umma_desc(b_hi + o), idesc, 1u);
+            }
+            // arrives on the barrier when every MMA issued so far has completed (implies fence::before_thread_sync)
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(mbar + stage)) : "memory");
+            if (kb + 1 == nkb)
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(mbar + 2)) : "memory");
+        }
+    }
+    mbar_wait(smem_u32(mbar + 2), 0u);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    // epilogue: thread = query row (TMEM lane), 4 x 32 columns
+    const int q = row0 + warp * 32 + lane;
+    const bool qok = q < q0 + nq && q < n;
+    const float na = qok ? __ldg(norm2 + q) : 0.f;
+#pragma unroll 1
+    for (int cb = 0; cb < TBN / 32; ++cb) {
+        unsigned v[32];
+        const unsigned taddr = tmem_d + ((unsigned)(warp * 32) << 16) + (unsigned)(cb * 32);
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                     : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+                       "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+                       "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+                       "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                     : "r"(taddr) : "memory");
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (qok) {
+            float *dst = D + (size_t)(q - q0) * ldD + col0 + cb * 32;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+                float o[4];
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const int p = col0 + cb * 32 + j + t;
+                    const float nb = p < n ? __ldg(norm2 + p) : INFINITY;
+                    o[t] = fmaxf(0.f, fmaf(-2.f, __uint_as_float(v[j + t]), na + nb));           // +inf stays +inf
+                }
+                *reinterpret_cast<float4 *>(dst + j) = make_float4(o[0], o[1], o[2], o[3]);
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(tmem_d) : "memory");
+}
+
+// hi / lo bf16 split of the centred features (n x dpad fp32 -> 2 x n x dpad bf16)
+__global__ void __launch_bounds__(256)
+knn_split_kernel(const float *__restrict__ Xc, long long total, __nv_bfloat16 *__restrict__ Xh, __nv_bfloat16 *__restrict__ Xl)
+{
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const float x = Xc[i];
+        const __nv_bfloat16 h = __float2bfloat16_rn(x);
+        Xh[i] = h;
+        Xl[i] = __float2bfloat16_rn(x - __bfloat162float(h));
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // 3. selection: one warp per query row, C = 32 * NPL candidates
 // ---------------------------------------------------------------------------------------------------------
@@ -247,7 +422,7 @@ __global__ void __launch_bounds__(256)
 knn_rerank_kernel(const double *__restrict__ X, int n, int d, const float *__restrict__ norm2,
                   const unsigned long long *__restrict__ rmax2_bits, const u64 *__restrict__ cand, int q0, int nq, int k,
                   long long *__restrict__ out_ind, double *__restrict__ out_dist, int *__restrict__ fail_rows,
-                  int *__restrict__ fail_count)
+                  int *__restrict__ fail_count, double err_rel)
 {
     constexpr int C = 32 * NPL;
     const int lane = threadIdx.x & 31;
@@ -282,7 +457,7 @@ knn_rerank_kernel(const double *__restrict__ X, int n, int d, const float *__res
     const float ak = __uint_as_float((unsigned)(key_k >> 32)), ac = __uint_as_float((unsigned)(key_c >> 32));
     const double R = sqrt(__longlong_as_double((long long)*rmax2_bits));
     const double ni = sqrt((double)norm2[q]);
-    const double E = 2.0 * (double)(d + 8) * 5.9604644775390625e-8 * (ni + R) * (ni + R);
+    const double E = 2.0 * err_rel * (ni + R) * (ni + R);      // err_rel: bound on |approx cross term - exact| / (|x||y|)
     // fewer than C points in total (n <= C): the list holds everything, nothing can be missing
     const bool certified = (key_c == ~0ull) || ((double)ac - (double)ak > 2.0 * E);
     // rank of every candidate among the C by (exact d2, index): O(C) shuffles per element, C <= 128
@@ -359,13 +534,21 @@ struct KnnArena {
     cudaError_t alloc(void **p, size_t bytes) { cudaError_t e = cudaMalloc(p, bytes ? bytes : 1); if (e == cudaSuccess) v.push_back(*p); return e; }
 };
 
+// GLB_KNN_TC=0 forces the fp32 SIMT distance kernel (A/B runs); default: tensor cores when d >= 64
+static bool knn_use_tc(int d)
+{
+    const char *e = getenv("GLB_KNN_TC");
+    if (e) return atoi(e) != 0;
+    return d >= 64;
+}
+
 template <int NPL>
 static int knn_run(const double *d_X, int64_t n, int d, int k, long long *d_ind, double *d_dist, int *launches, int *fallback_rows,
-                   cudaStream_t st)
+                   cudaStream_t st, bool tc)
 {
     constexpr int C = 32 * NPL;
     KnnArena A;
-    const int dpad = (d + BK - 1) / BK * BK;
+    const int dpad = tc ? (d + TBK - 1) / TBK * TBK : (d + BK - 1) / BK * BK;
     const int n_pad = (int)((n + BN - 1) / BN * BN);
     int QB = 2048;                                            // queries per distance block: QB x n_pad fp32 in HBM
     while ((double)QB * n_pad * 4.0 > 2.0e9 && QB > 128) QB /= 2;
@@ -386,13 +569,27 @@ static int knn_run(const double *d_X, int64_t n, int d, int k, long long *d_ind,
     int nl = 0;
     knn_colsum_kernel<<<d, 256, 0, st>>>(d_X, n, d, mean); ++nl;
     knn_center_kernel<<<sm_count() * 8, 256, 0, st>>>(d_X, mean, n, d, dpad, Xc, norm2, rmax2); ++nl;
+    // bound on |approximate cross term - exact| / (|x||y|):
+    //   fp32 SIMT: (d + 8) roundings of 2^-24;
+    //   tensor cores: 3 * 2^-18 from the hi/lo split + one 2^-23 rounding (truncation) per accumulated product, 3 per k
+    double err_rel = (double)(d + 8) * 5.9604644775390625e-8;
+    __nv_bfloat16 *Xh = nullptr, *Xl = nullptr;
+    if (tc) {
+        GLB_CUDA(A.alloc((void **)&Xh, sizeof(__nv_bfloat16) * (size_t)n * dpad));
+        GLB_CUDA(A.alloc((void **)&Xl, sizeof(__nv_bfloat16) * (size_t)n * dpad));
+        knn_split_kernel<<<sm_count() * 8, 256, 0, st>>>(Xc, (long long)n * dpad, Xh, Xl); ++nl;
+        GLB_CUDA(cudaFuncSetAttribute(knn_dist_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
+        err_rel = 3.0 * 3.814697265625e-6 + (double)(3 * dpad + 8) * 1.1920928955078125e-7;
+    }
     for (int64_t q0 = 0; q0 < n; q0 += QB) {
         const int nq = (int)std::min<int64_t>(QB, n - q0);
         dim3 grid((unsigned)(n_pad / BN), (unsigned)((nq + BM - 1) / BM));
-        knn_dist_kernel<<<grid, kDistThreads, 0, st>>>(Xc, norm2, (int)n, dpad, (int)q0, nq, D, (long long)n_pad); ++nl;
+        if (tc) knn_dist_tc_kernel<<<grid, kTcThreads, kTcSmemBytes, st>>>(Xh, Xl, norm2, (int)n, dpad, (int)q0, nq, D, (long long)n_pad);
+        else knn_dist_kernel<<<grid, kDistThreads, 0, st>>>(Xc, norm2, (int)n, dpad, (int)q0, nq, D, (long long)n_pad);
+        ++nl;
         knn_select_kernel<NPL><<<(nq * 32 + 255) / 256, 256, 0, st>>>(D, (long long)n_pad, n_pad, nq, cand); ++nl;
         knn_rerank_kernel<NPL><<<(nq * 32 + 255) / 256, 256, 0, st>>>(d_X, (int)n, d, norm2, rmax2, cand, (int)q0, nq, k, d_ind, d_dist,
-                                                                       fail_rows, fail_count); ++nl;
+                                                                       fail_rows, fail_count, err_rel); ++nl;
     }
     knn_exact_rows_kernel<<<exact_ctas, 256, 0, st>>>(d_X, (int)n, d, fail_rows, fail_count, k, scratch, d_ind, d_dist); ++nl;
     GLB_LAUNCH_CHECK();
@@ -417,10 +614,13 @@ extern "C" GLB_API int glb_knn_search(const double *d_X, int64_t n, int d, int k
     GLB_CHECK_ARG(k > 0 && k <= n, "k must be in [1, n]");
     if (k > 112) { set_error("glb_knn_search: k = %d (> 112) is not supported", k); return GLB_E_UNSUPPORTED; }
     cudaStream_t st = (cudaStream_t)stream;
-    // candidates: at least k + 8 and 1.25 k, in steps of 32
-    if (k + 8 <= 32 && k * 5 / 4 <= 32) return knn_run<1>(d_X, n, d, k, (long long *)d_ind, d_dist, launches, fallback_rows, st);
-    if (k + 8 <= 64 && k * 5 / 4 <= 64) return knn_run<2>(d_X, n, d, k, (long long *)d_ind, d_dist, launches, fallback_rows, st);
-    return knn_run<4>(d_X, n, d, k, (long long *)d_ind, d_dist, launches, fallback_rows, st);
+    // candidates: at least k + 8 and 1.25 k, in steps of 32; the tensor-core distances carry a ~7x wider error margin,
+    // so that path keeps a list twice as long for the certificate
+    const bool tc = knn_use_tc(d);
+    const int kk = tc ? 2 * k + 16 : k;
+    if (kk + 8 <= 32 && kk * 5 / 4 <= 32) return knn_run<1>(d_X, n, d, k, (long long *)d_ind, d_dist, launches, fallback_rows, st, tc);
+    if (kk + 8 <= 64 && kk * 5 / 4 <= 64) return knn_run<2>(d_X, n, d, k, (long long *)d_ind, d_dist, launches, fallback_rows, st, tc);
+    return knn_run<4>(d_X, n, d, k, (long long *)d_ind, d_dist, launches, fallback_rows, st, tc);
 }
 
 extern "C" GLB_API int glb_knn_search_host(const double *h_X, int64_t n, int d, int k, int64_t *h_ind, double *h_dist, int *launches,
