@@ -74,3 +74,20 @@ def test_trainsets_generate_is_stratified_and_seeded():
 def test_labels_to_onehot_widens():
     oh = gl.utils.labels_to_onehot(np.array([0, 3, 1]), 2)
     assert oh.shape == (3, 4) and oh.sum() == 3
+
+
+def test_drop_in_package_name():
+    """`import graphlearning as gl` (the reference's package name) exposes the hot-path API the examples use
+    (SURVEY.md appendix C): weightmatrix.knn/knnsearch, graph, ssl.poisson/laplace/plaplace/amle/ssl_accuracy,
+    trainsets.generate, utils.conjgrad/labels_to_onehot, clustering.spectral/clustering_accuracy."""
+    import graphlearning as gl
+    import graphlearning.ssl as gssl
+    for mod, names in ((gl.weightmatrix, ("knn", "knnsearch")), (gl.ssl, ("poisson", "laplace", "plaplace", "amle", "ssl_accuracy")),
+                       (gl.trainsets, ("generate",)), (gl.utils, ("conjgrad", "labels_to_onehot", "randomized_svd")),
+                       (gl.clustering, ("spectral", "clustering_accuracy", "purity"))):
+        for n in names:
+            assert callable(getattr(mod, n)), n
+    assert gssl is gl.ssl and callable(gl.graph)
+    G = gl.graph(__import__("scipy.sparse", fromlist=["x"]).identity(4, format="csr"))
+    for n in ("degree_vector", "degree_matrix", "laplacian", "eigen_decomp", "plaplace", "amle"):
+        assert callable(getattr(G, n)), n
