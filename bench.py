@@ -96,6 +96,19 @@ def other_rows(W, labels, ti):
         t = time.perf_counter() - t0
         out["laplace_cg_fit"] = {"seconds": t, "cg_iterations": int(m.iterations), "gpu_launches": int(m.gpu_launches),
                                  "note": "gl.ssl.laplace(W).fit, 5 labels/class, tol 1e-5; includes the scipy system assembly"}
+        # config 4: 50 eigenpairs of the normalised Laplacian (graph.eigen_decomp on the block kernels of spectral.cu)
+        G = gl.graph(W)
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        vals, vecs = G.eigen_decomp(normalization="normalized", k=50)
+        t = time.perf_counter() - t0
+        out["eigen_decomp_k50"] = {"seconds": t, "spmm_launches": int(G.eigen_info["spmm"]), "residual": float(G.eigen_info["residual"]),
+                                   "lambda_50": float(vals[-1]), "reference_cpu_seconds": "6.1 (ARPACK svds, BASELINE.md section 2)"}
+        # p-Laplace / AMLE sweeps (bit-exact Gauss-Seidel / Jacobi of c_code/lp_iterate.cpp), one class against the rest
+        val = (labels[t5] == 0).astype(np.float64)
+        G.plaplace(t5, val, 3, max_num_it=30)
+        for name, fn in (("plaplace_p3_fast", lambda: G.plaplace(t5, val, 3)), ("amle_weighted", lambda: G.amle(t5, val, tol=1e-3, max_num_it=300))):
+            t0 = time.perf_counter(); fn(); t = time.perf_counter() - t0
+            out[name] = {"seconds_host_to_host": t, "sweeps": int(G.sweeps), "us_per_sweep": 1e6 * t / max(1, G.sweeps)}
     except Exception as e:                                   # never lose the headline line over an extra
         out["error"] = repr(e)
     return out

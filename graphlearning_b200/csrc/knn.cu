@@ -186,7 +186,7 @@ knn_dist_kernel(const float *__restrict__ Xc, const float *__restrict__ norm2, i
 // stage and commits them to the stage's mbarrier, so the next stage's loads overlap the tensor-core work.  Epilogue:
 // warp w reads TMEM lanes 32w..32w+31 (one query row per thread) with tcgen05.ld 32x32b.x32, applies
 // max(0, |q|^2 + |x_j|^2 - 2 acc) and writes 128-byte runs of its row of D.
-constexpr int TBM = 128, TBN = 128, TBK = 64;
+constexpr int TBM = 128, TBN = 128, TBK = 32;
 constexpr int kTcThreads = 128;
 constexpr int kTcStageBytes = 4 * TBM * TBK * 2;                 // A hi, A lo, B hi, B lo
 constexpr int kTcSmemBytes = 2 * kTcStageBytes + 64;
@@ -195,7 +195,7 @@ __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)_
 
 __device__ __forceinline__ unsigned long long umma_desc(unsigned saddr)
 {
-    // start address [0,14) | leading byte offset [16,30) = 128 B | stride byte offset [32,46) = 1024 B | version [46,48) = 1
+    // start address [0,14) | leading byte offset [16,30) = 128 B | stride byte offset [32,46) = (TBK/8)*128 B | version [46,48) = 1
     // | layout type [61,64) = 0 (no swizzle); all offsets in 16-byte units
     return (unsigned long long)((saddr & 0x3FFFFu) >> 4) | ((unsigned long long)(128u >> 4) << 16) |
            ((unsigned long long)((TBK / 8 * 128u) >> 4) << 32) | (1ull << 46);
@@ -221,7 +221,7 @@ __device__ __forceinline__ void mbar_wait(unsigned mbar, unsigned parity)
     __trap();
 }
 
-__global__ void __launch_bounds__(kTcThreads, 1)
+__global__ void __launch_bounds__(kTcThreads, 3)
 knn_dist_tc_kernel(const __nv_bfloat16 *__restrict__ Xh, const __nv_bfloat16 *__restrict__ Xl, const float *__restrict__ norm2, int n,
                    int dpad, int q0, int nq, float *__restrict__ D, long long ldD)
 {
@@ -244,17 +244,19 @@ knn_dist_tc_kernel(const __nv_bfloat16 *__restrict__ Xh, const __nv_bfloat16 *__
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const unsigned tmem_d = *tmem_slot;
 
-    // one stage = 4 operand blocks of 128 rows x 64 bf16; 16-byte chunk (r, c) of a block lives at (r/8)*1024 + c*128 + (r%8)*16
+    // one stage = 4 operand blocks of 128 rows x TBK bf16; 16-byte chunk (r, c) of a block lives at
+    // (r/8) * SBO + c * 128 + (r%8) * 16 with SBO = (TBK/8) * 128
+    constexpr int CPR = TBK / 8;                                 // 16-byte chunks per row
     auto fill = [&](int stage, int k0) {
         unsigned char *base = tc_smem + stage * kTcStageBytes;
 #pragma unroll
-        for (int it = 0; it < 4 * TBM * (TBK / 8) / kTcThreads; ++it) {      // 4096 chunks / 128 threads = 32
+        for (int it = 0; it < 4 * TBM * CPR / kTcThreads; ++it) {
             const int ch = it * kTcThreads + tid;
-            const int blk = ch >> 10, r = (ch >> 3) & 127, c = ch & 7;           // consecutive threads: the 8 chunks of a row
+            const int blk = ch / (TBM * CPR), r = (ch / CPR) % TBM, c = ch % CPR;       // consecutive threads: the chunks of a row
             const int grow = (blk < 2 ? row0 : col0) + r;
             const bool ok = blk < 2 ? (grow < q0 + nq && grow < n) : (grow < n);
             const __nv_bfloat16 *src = ((blk & 1) ? Xl : Xh) + (size_t)(ok ? grow : 0) * dpad + k0 + c * 8;
-            const unsigned dst = smem_u32(base + blk * (TBM * TBK * 2) + (r >> 3) * 1024 + c * 128 + (r & 7) * 16);
+            const unsigned dst = smem_u32(base + blk * (TBM * TBK * 2) + (r >> 3) * (CPR * 128) + c * 128 + (r & 7) * 16);
             const int bytes = ok ? 16 : 0;
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
         }
@@ -294,10 +296,11 @@ knn_dist_tc_kernel(const __nv_bfloat16 *__restrict__ Xh, const __nv_bfloat16 *__
     }
     mbar_wait(smem_u32(mbar + 2), 0u);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    // epilogue: thread = query row (TMEM lane), 4 x 32 columns
+    // epilogue: thread = query row (TMEM lane), 4 x 32 columns.  The 32 x 32 block a warp holds is transposed through
+    // shared memory (the operand stages are free now) so that every store instruction writes one 128-byte run of a row.
     const int q = row0 + warp * 32 + lane;
-    const bool qok = q < q0 + nq && q < n;
-    const float na = qok ? __ldg(norm2 + q) : 0.f;
+    const float na = (q < q0 + nq && q < n) ? __ldg(norm2 + q) : 0.f;
+    float *stg = reinterpret_cast<float *>(tc_smem) + warp * (32 * 33);
 #pragma unroll 1
     for (int cb = 0; cb < TBN / 32; ++cb) {
         unsigned v[32];
@@ -309,19 +312,17 @@ knn_dist_tc_kernel(const __nv_bfloat16 *__restrict__ Xh, const __nv_bfloat16 *__
                        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
                      : "r"(taddr) : "memory");
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (qok) {
-            float *dst = D + (size_t)(q - q0) * ldD + col0 + cb * 32;
+        const int p = col0 + cb * 32 + lane;                 // this lane's column after the transpose
+        const float nb = p < n ? __ldg(norm2 + p) : INFINITY;
+        __syncwarp();
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-                float o[4];
-#pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                    const int p = col0 + cb * 32 + j + t;
-                    const float nb = p < n ? __ldg(norm2 + p) : INFINITY;
-                    o[t] = fmaxf(0.f, fmaf(-2.f, __uint_as_float(v[j + t]), na + nb));           // +inf stays +inf
-                }
-                *reinterpret_cast<float4 *>(dst + j) = make_float4(o[0], o[1], o[2], o[3]);
-            }
+        for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = fmaf(-2.f, __uint_as_float(v[j]), na);      // row = lane, column j
+        __syncwarp();
+#pragma unroll 4
+        for (int r = 0; r < 32; ++r) {
+            const int qr = row0 + warp * 32 + r;
+            if (qr < q0 + nq && qr < n)
+                D[(size_t)(qr - q0) * ldD + p] = fmaxf(0.f, stg[r * 33 + lane] + nb);                   // +inf stays +inf
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -550,8 +551,11 @@ static int knn_run(const double *d_X, int64_t n, int d, int k, long long *d_ind,
     KnnArena A;
     const int dpad = tc ? (d + TBK - 1) / TBK * TBK : (d + BK - 1) / BK * BK;
     const int n_pad = (int)((n + BN - 1) / BN * BN);
-    int QB = 2048;                                            // queries per distance block: QB x n_pad fp32 in HBM
-    while ((double)QB * n_pad * 4.0 > 2.0e9 && QB > 128) QB /= 2;
+    // queries per distance block (QB x n_pad fp32 in HBM): large enough that the one-warp-per-query selection fills the
+    // machine (8192 warps = 55 per SM), capped at 4 GB
+    int QB = getenv("GLB_KNN_QB") ? atoi(getenv("GLB_KNN_QB")) : 8192;
+    QB = std::max(128, QB / 128 * 128);
+    while ((double)QB * n_pad * 4.0 > 4.0e9 && QB > 128) QB /= 2;
     if (QB > n) QB = (int)((n + BM - 1) / BM * BM);
     double *mean; float *Xc, *norm2, *D; unsigned long long *rmax2; u64 *cand; int *fail_rows, *fail_count; double *scratch;
     GLB_CUDA(A.alloc((void **)&mean, sizeof(double) * d));
