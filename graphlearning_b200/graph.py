@@ -97,6 +97,47 @@ class graph:
             raise ValueError("Invalid option for graph Laplacian normalization.")
         return L.tocsr()
 
+    def reweight(self, idx, method="poisson", normalization="combinatorial", tau=0, X=None, alpha=2, zeta=1e7, r=0.1):
+        """Reweight the weight matrix near the labelled nodes `idx`.  Reference graphlearning/graph.py:368-466; the
+        'poisson' method's linear solve (utils.conjgrad(L, f, tol=1e-5), :430) runs on the GPU CG."""
+        from . import utils
+        from scipy import spatial
+        n = self.num_nodes
+        if method == "poisson":
+            f = np.zeros(n)
+            f[idx] = 1
+            if normalization == "combinatorial":
+                f -= np.mean(f)
+                L = self.laplacian()
+            elif normalization == "normalized":
+                d = self.degree_vector() ** (0.5)
+                c = np.sum(d * f) / np.sum(d)
+                f -= c
+                L = self.laplacian(normalization=normalization)
+            else:
+                raise ValueError("Unsupported normalization " + str(normalization) + " for graph.reweight.")
+            w = utils.conjgrad(L, f, tol=1e-5)
+            w -= np.min(w)
+            w += 1e-5
+            D = sparse.spdiags(w, 0, n, n).tocsr()
+            return D * self.weight_matrix * D
+        if method == "wnll":
+            m = len(idx)
+            a = np.ones((n,))
+            a[idx] = n / m
+            D = sparse.spdiags(a, 0, n, n).tocsr()
+            return D * self.weight_matrix + self.weight_matrix * D
+        if method == "properly":
+            if X is None:
+                raise ValueError("Must provide data features X for properly weighted graph Laplacian.")
+            rzeta = r / (zeta - 1) ** (1 / alpha)
+            Dn, _ = spatial.cKDTree(X[idx, :]).query(X)
+            Dn[Dn < rzeta] = rzeta
+            gamma = 1 + (r / Dn) ** alpha
+            D = sparse.spdiags(gamma, 0, n, n).tocsr()
+            return D * self.weight_matrix + self.weight_matrix * D
+        raise ValueError("Invalid reweighting method " + str(method) + ".")
+
     # ---- p-Laplace / AMLE sweeps on the GPU (plaplace.cu) ---------------------------------------------------
     def plaplace(self, bdy_set, bdy_val, p, tol=1e-1, max_num_it=1e6, prog=False, fast=True):
         """Game-theoretic p-Laplace equation with Dirichlet data.  Reference graphlearning/graph.py:1177-1279;

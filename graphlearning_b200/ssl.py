@@ -179,16 +179,13 @@ class laplace(ssl):
 
     Solves tau u + L u = 0 on the unlabelled nodes with the labels as Dirichlet data: the Jacobi-scaled
     sub-system M A M v = M b is assembled with the same scipy expressions as the reference (ssl.py:1222-1246)
-    and solved by the multi-column CG on the GPU (cg.cu).  reweighting other than 'none' needs
-    graph.reweight, which is outside the hot path and not built.
+    and solved by the multi-column CG on the GPU (cg.cu).  reweighting in {'poisson', 'wnll', 'properly'} goes through
+    graph.reweight as in the reference (ssl.py:1209-1214).
     """
 
     def __init__(self, W=None, class_priors=None, X=None, reweighting="none", normalization="combinatorial", tau=0,
                  order=1, mean_shift=False, tol=1e-5, alpha=2, zeta=1e7, r=0.1):
         super().__init__(W, class_priors)
-        if reweighting != "none":
-            raise NotImplementedError("laplace(reweighting=%r) needs graph.reweight, outside the B200 hot path"
-                                      % reweighting)
         self.reweighting = reweighting
         self.normalization = normalization
         self.mean_shift = mean_shift
@@ -205,6 +202,9 @@ class laplace(ssl):
         self.gpu_launches = 0
         fname = "_laplace"
         self.name = "Laplace Learning"
+        if self.reweighting != "none":
+            fname += "_" + self.reweighting
+            self.name += ": " + self.reweighting + " reweighted"
         if self.normalization != "combinatorial":
             fname += "_" + self.normalization
             self.name += " " + self.normalization
@@ -220,8 +220,11 @@ class laplace(ssl):
         self.accuracy_filename = fname
 
     def system(self, train_ind, train_labels):
-        """(M A M, M b, M, idx, F): the linear system of ssl.py:1217-1246."""
-        G = self.graph
+        """(M A M, M b, M, idx, F): the linear system of ssl.py:1208-1246 (reweighting :1209-1214)."""
+        if self.reweighting == "none":
+            G = self.graph
+        else:
+            G = graph.graph(self.graph.reweight(train_ind, method=self.reweighting, normalization=self.normalization, X=self.X))
         n = G.num_nodes
         k = len(np.unique(train_labels))
         L = sparse.spdiags(self.tau, 0, n, n) + G.laplacian(normalization=self.normalization)

@@ -7,8 +7,14 @@ reference (weightmatrix.py:349-352).
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 from scipy import sparse, spatial
+
+# stored kNN searches live in ./knn_data/<dataset>_<metric>.npz with fields J (indices) and D (distances): the wire
+# format between graph build and solve of the reference (weightmatrix.py:17, 416-427, 431-467)
+knn_dir = os.path.abspath(os.path.join(os.getcwd(), "knn_data"))
 
 
 def sparse_max(A, B):
@@ -35,9 +41,22 @@ def knnsearch(X, k, method=None, similarity="euclidean", dataset=None, metric="r
         Y = X / np.linalg.norm(X, axis=1)[:, None] if similarity == "angular" else X
         tree = spatial.cKDTree(Y)
         knn_dist, knn_ind = tree.query(Y, k=k)
-        return knn_ind, knn_dist
-    from . import knn_gpu
-    return knn_gpu.knnsearch_gpu(X, k, similarity=similarity)
+    else:
+        from . import knn_gpu
+        knn_ind, knn_dist = knn_gpu.knnsearch_gpu(X, k, similarity=similarity)
+    if dataset is not None:                                       # weightmatrix.py:416-427
+        os.makedirs(knn_dir, exist_ok=True)
+        np.savez_compressed(os.path.join(knn_dir, dataset.lower() + "_" + metric.lower() + ".npz"), J=knn_ind, D=knn_dist)
+    return knn_ind, knn_dist
+
+
+def load_knn_data(dataset, metric="raw"):
+    """Load a stored kNN search (fields J, D).  Reference weightmatrix.py:431-467; nothing is downloaded here."""
+    path = os.path.join(knn_dir, dataset.lower() + "_" + metric.lower() + ".npz")
+    if not os.path.exists(path):
+        raise FileNotFoundError("no stored kNN data at %s (the B200 backend never downloads)" % path)
+    M = np.load(path, allow_pickle=True)
+    return M["J"], M["D"]
 
 
 def knn(data, k, kernel="gaussian", eta=None, symmetrize=True, metric="raw", similarity="euclidean", knn_data=None):
@@ -46,7 +65,7 @@ def knn(data, k, kernel="gaussian", eta=None, symmetrize=True, metric="raw", sim
     if knn_data is not None:
         knn_ind, knn_dist = knn_data
     elif type(data) is str:
-        raise NotImplementedError("loading stored kNN data by dataset name is outside the B200 hot path")
+        knn_ind, knn_dist = load_knn_data(data, metric=metric)   # :123-124
     else:
         knn_ind, knn_dist = knnsearch(data, k, similarity=similarity)
     knn_ind = np.asarray(knn_ind)

@@ -136,3 +136,25 @@ def test_full_size_cg(gl):
     u_ref, it_ref = orc.laplace_fit(W, ti, labels[ti], return_iters=True)
     assert abs(m.iterations - it_ref) <= 1
     assert rel_err(u, u_ref) <= 1e-6
+
+
+def test_reweight_and_reweighted_laplace_goldens(gl, moons):
+    """graph.reweight ('poisson' runs one GPU CG solve, utils.conjgrad(L, f, tol=1e-5), reference graph.py:412-434) and
+    ssl.laplace(reweighting=...) (ssl.py:1209-1214) against goldens from the reference."""
+    from conftest import Golden
+    from scipy import sparse
+    rw = Golden("reweight")
+    W = moons.csr("W"); ti = moons["train_ind"]; labels = moons["labels"]; X = moons["X"]
+    G = gl.graph(W)
+    for tag, kw in (("poisson", {}), ("poisson_normalized", {"normalization": "normalized"}), ("wnll", {}), ("properly", {"X": X})):
+        Wr = sparse.csr_matrix(G.reweight(ti, method=tag.split("_")[0], **kw)); Wr.sort_indices()
+        assert np.array_equal(Wr.indices, rw["W_%s_indices" % tag]) and np.array_equal(Wr.indptr, rw["W_%s_indptr" % tag])
+        # 'poisson': w comes out of a CG stopped at tol 1e-5, so the weights agree to the solver tolerance, not to the bit
+        tol = 1e-4 if tag.startswith("poisson") else 1e-14
+        assert np.allclose(Wr.data, rw["W_%s_data" % tag], rtol=tol, atol=1e-12)
+    for name in ("poisson", "wnll"):
+        m = gl.ssl.laplace(W, reweighting=name)
+        u = m.fit(ti, labels[ti])
+        assert rel_err(u, rw["u_laplace_" + name]) <= (1e-3 if name == "poisson" else 1e-5)
+        assert np.mean(m.predict() == rw["p_laplace_" + name]) > 0.995
+        assert name in m.accuracy_filename

@@ -91,3 +91,19 @@ def test_drop_in_package_name():
     G = gl.graph(__import__("scipy.sparse", fromlist=["x"]).identity(4, format="csr"))
     for n in ("degree_vector", "degree_matrix", "laplacian", "eigen_decomp", "plaplace", "amle"):
         assert callable(getattr(G, n)), n
+
+
+def test_knn_data_on_disk_format(tmp_path, monkeypatch):
+    """knnsearch(dataset=...) stores J/D in ./knn_data/<dataset>_<metric>.npz and knn('<dataset>', ...) /
+    load_knn_data read it back (reference weightmatrix.py:416-427, 431-467)."""
+    import graphlearning_b200 as gl
+    monkeypatch.setattr(gl.weightmatrix, "knn_dir", str(tmp_path / "knn_data"))
+    X = np.random.default_rng(0).normal(size=(200, 3))           # d <= 5: cKDTree, no GPU needed
+    ind, dist = gl.weightmatrix.knnsearch(X, 8, dataset="Toy", metric="raw")
+    J, D = gl.weightmatrix.load_knn_data("toy")
+    assert np.array_equal(J, ind) and np.array_equal(D, dist)
+    W1 = gl.weightmatrix.knn("toy", 7)
+    W2 = gl.weightmatrix.knn(X, 7, knn_data=(ind, dist))
+    assert (W1 != W2).nnz == 0
+    with pytest.raises(FileNotFoundError):
+        gl.weightmatrix.load_knn_data("absent")
