@@ -111,6 +111,7 @@ extern "C" GLB_API int glb_poisson_graph_create(glb_poisson_graph **out, const i
         return GLB_E_NOGPU;
     }
     cudaStream_t st = 0;
+    PhaseTimer tm("graph_create");
     glb_poisson_graph *g = new glb_poisson_graph();
     struct Guard { glb_poisson_graph *g; ~Guard() { delete g; } } guard{g};
     g->n = n; g->nnz = nnz;
@@ -128,6 +129,7 @@ extern "C" GLB_API int glb_poisson_graph_create(glb_poisson_graph **out, const i
     GLB_CUDA(cudaMemcpyAsync(col, h_col, nnz * sizeof(int), cudaMemcpyHostToDevice, st));
     GLB_CUDA(cudaMemcpyAsync(val, h_val, nnz * sizeof(double), cudaMemcpyHostToDevice, st));
 
+    tm.lap("alloc + upload");
     // W <- W - diag(W) (ssl.py:615-616) is never materialised: the degree kernel skips diagonal entries and
     // glb_poisson_scale writes zeros for them.
     int rc;
@@ -139,6 +141,7 @@ extern "C" GLB_API int glb_poisson_graph_create(glb_poisson_graph **out, const i
     g->setup_launches = 4 + 1 + 1 + 2;
     GLB_LAUNCH_CHECK();
 
+    tm.lap("transpose/degree/scale");
     g->it_rp = g->t_rp; g->it_col = g->t_col; g->it_val = g->P_val;
     // Locality ordering: worth its host time only when the label matrix cannot live in L2 (reorder < 0 = auto).
     const bool want = reorder > 0 || (reorder < 0 && (double)n * 16.0 * 4.0 * 2.0 > kReorderMinBytes);
@@ -155,6 +158,7 @@ extern "C" GLB_API int glb_poisson_graph_create(glb_poisson_graph **out, const i
         g->it_rp = p_rp; g->it_col = p_col; g->it_val = p_val;
     }
     GLB_CUDA(cudaStreamSynchronize(st));
+    tm.lap("locality order");
     guard.g = nullptr;
     *out = g;
     return 0;
@@ -177,6 +181,7 @@ extern "C" GLB_API int glb_poisson_graph_fit(glb_poisson_graph *g, const double 
     const int64_t n = g->n, nnz = g->nnz;
     cudaStream_t st = 0;
     int nl = 0, rc;
+    PhaseTimer tm("graph_fit");
     if (c != g->c_plan) {                                // (re)build the plan and the per-width buffers
         if (g->plan) { glb_poisson_plan_destroy(g->plan); g->plan = nullptr; g->c_plan = 0; }
         if ((rc = glb_poisson_plan_create(&g->plan, g->it_rp, g->it_col, g->it_val, n, nnz, c, GLB_POISSON_KIND_AUTO, st)))
@@ -189,6 +194,7 @@ extern "C" GLB_API int glb_poisson_graph_fit(glb_poisson_graph *g, const double 
         GLB_CUDA(cudaMemsetAsync(g->u1, 0, rows * ld * sizeof(float), st));
         g->rows = rows;
         g->ldu = ld; g->c_plan = c;
+        tm.lap("plan_create + buffers");
     }
     const int ldu = g->ldu;
     if (m > g->m_cap) { GLB_CUDA(g->A.alloc(&g->tind, m)); g->m_cap = m; }
@@ -217,6 +223,7 @@ extern "C" GLB_API int glb_poisson_graph_fit(glb_poisson_graph *g, const double 
     nl += 1;
     GLB_CUDA(cudaMemcpyAsync(h_u_out, g->src64, n * c * sizeof(double), cudaMemcpyDeviceToHost, st));
     if ((rc = glb_poisson_plan_check(g->plan, st))) return rc;          // synchronises
+    tm.lap("upload + iterate + download");
     if (T_done) *T_done = T;
     if (launches) *launches = nl;
     return 0;

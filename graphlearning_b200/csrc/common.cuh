@@ -39,4 +39,14 @@ static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b)
 
 int sm_count();   // cached, current device
 
+// GLB_TIMING=1: wall-clock phases of the host entry points on stderr (setup-cost experiments)
+struct PhaseTimer {
+    bool on;
+    const char *what;
+    double t0;
+    static double now();
+    explicit PhaseTimer(const char *w);
+    void lap(const char *phase);
+};
+
 }  // namespace glb

@@ -1154,6 +1154,7 @@ extern "C" GLB_API int glb_poisson_plan_create(glb_poisson_plan **plan, const in
     cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
     cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     const int sms = sm_count();
+    PhaseTimer tm("plan_create");
     if (kind != GLB_POISSON_KIND_STEP && coop) {
         std::vector<int> h_rp((size_t)n + 1);
         GLB_CUDA(cudaMemcpyAsync(h_rp.data(), d_rowptr, sizeof(int) * (size_t)(n + 1), cudaMemcpyDeviceToHost, st));
@@ -1162,6 +1163,7 @@ extern "C" GLB_API int glb_poisson_plan_create(glb_poisson_plan **plan, const in
         int rc = 0;
         if (kind == GLB_POISSON_KIND_AUTO || kind == GLB_POISSON_KIND_DATAFLOW)
             if ((rc = plan_try_dataflow(p, h_rp, sms, max_smem, st))) return rc;
+        tm.lap("dataflow slabs");
         if (p->kind == GLB_POISSON_KIND_STEP && (kind == GLB_POISSON_KIND_AUTO || kind == GLB_POISSON_KIND_BARRIER))
             if ((rc = plan_try_barrier(p, h_rp, sms, max_smem, st))) return rc;
         const bool tune = !getenv("GLB_POISSON_NOTUNE");
@@ -1178,6 +1180,7 @@ extern "C" GLB_API int glb_poisson_plan_create(glb_poisson_plan **plan, const in
                 if (i == 0 || ms < best) { best = ms; ms_df = ms; p->tuned_gate = cand[i]; }
             }
             p->gate_every = p->tuned_gate;
+            tm.lap("gate tuning");
         }
         if (kind == GLB_POISSON_KIND_AUTO && p->kind == GLB_POISSON_KIND_DATAFLOW && tune) {
             // ... and the dataflow kernel against the barrier kernel (small graphs: too few rows per SM to hide the
@@ -1194,6 +1197,7 @@ extern "C" GLB_API int glb_poisson_plan_create(glb_poisson_plan **plan, const in
                 }
                 p->tuned_ms[0] = ms_df; p->tuned_ms[1] = ms_bar;
                 glb_poisson_plan_destroy(alt);
+                tm.lap("barrier plan + timing");
             } else if (rc != GLB_E_UNSUPPORTED) {
                 return rc;
             }

@@ -1,5 +1,7 @@
 // runtime.cu - version / error string / device info for the C-ABI (include/glb200.h)
 #include <stdarg.h>
+#include <stdlib.h>
+#include <time.h>
 #include <string.h>
 #include "common.cuh"
 
@@ -22,6 +24,21 @@ int sm_count()
         if (cached <= 0) cached = 148;
     }
     return cached;
+}
+double PhaseTimer::now()
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec + 1e-9 * ts.tv_nsec;
+}
+PhaseTimer::PhaseTimer(const char *w) : on(getenv("GLB_TIMING") != nullptr), what(w), t0(now()) {}
+void PhaseTimer::lap(const char *phase)
+{
+    if (!on) return;
+    cudaDeviceSynchronize();
+    const double t = now();
+    fprintf(stderr, "[glb timing] %s: %-28s %8.3f ms\n", what, phase, (t - t0) * 1e3);
+    t0 = t;
 }
 }  // namespace glb
 
