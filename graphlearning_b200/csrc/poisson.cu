@@ -867,6 +867,26 @@ static void balanced_bounds(const std::vector<int> &h_rp, int64_t n, int grid, d
 // is (j,i) stored for every stored (i,j)?  (explicit zeros count: only the pattern matters)
 static bool pattern_symmetric(const std::vector<int> &rp, const std::vector<int> &col, int64_t n)
 {
+    // Rows with ascending columns (canonical CSR, the normal case): one pass with a cursor per row.  Visiting the entries
+    // (i, j) by ascending i, the entries (j, i) of row j are met in ascending order too, so row j's cursor must point
+    // at column i exactly when (i, j) is visited; every cursor must end at its row's end.
+    bool sorted_rows = true;
+    for (int64_t i = 0; i < n && sorted_rows; ++i)
+        for (int j = rp[i] + 1; j < rp[i + 1]; ++j)
+            if (col[j - 1] >= col[j]) { sorted_rows = false; break; }
+    if (sorted_rows) {
+        std::vector<int> cur(rp.begin(), rp.begin() + n);
+        for (int64_t i = 0; i < n; ++i)
+            for (int j = rp[i]; j < rp[i + 1]; ++j) {
+                const int cj = col[j];
+                if (cj < 0 || cj >= n) return false;
+                if (cur[cj] >= rp[cj + 1] || col[cur[cj]] != (int)i) return false;
+                ++cur[cj];
+            }
+        for (int64_t i = 0; i < n; ++i)
+            if (cur[i] != rp[i + 1]) return false;
+        return true;
+    }
     std::vector<int> sorted(col);
     for (int64_t i = 0; i < n; ++i)
         if (!std::is_sorted(sorted.begin() + rp[i], sorted.begin() + rp[i + 1]))
@@ -906,7 +926,10 @@ static int plan_try_dataflow(glb_poisson_plan *p, const std::vector<int> &h_rp, 
         GLB_CUDA(cudaMemcpyAsync(h_val.data(), p->d_val, sizeof(float) * (size_t)nnz, cudaMemcpyDeviceToHost, st));
         GLB_CUDA(cudaStreamSynchronize(st));
     }
+    PhaseTimer tm("dataflow plan");
+    tm.lap("download col/val");
     if (!pattern_symmetric(h_rp, h_col, n)) return 0;
+    tm.lap("symmetry check");
 
     int threads = 0;
     const void *fn = pick_dataflow(lanes, &threads);
@@ -1034,6 +1057,7 @@ static int plan_try_dataflow(glb_poisson_plan *p, const std::vector<int> &h_rp, 
         cap_slots = std::max(cap_slots, (int)(depth * nw));
         cap_parts = std::max(cap_parts, nparts_cta);
     }
+    tm.lap("slab build");
     cap_entries = (cap_entries + 1) & ~1;
     const size_t smem = (size_t)cap_entries * 8 + (size_t)cap_slots * 16 + (size_t)cap_parts * 2 * lanes * 16 + (size_t)cap_slots * rpw * 4;
     if (smem > (size_t)max_smem) return 0;
@@ -1054,6 +1078,7 @@ static int plan_try_dataflow(glb_poisson_plan *p, const std::vector<int> &h_rp, 
     GLB_CUDA(cudaMemcpyAsync(p->d_slot_off, slot_off.data(), sizeof(int) * (grid + 1), cudaMemcpyHostToDevice, st));
     GLB_CUDA(cudaMemcpyAsync(p->d_slot_rows, slot_rows.data(), sizeof(int) * slot_rows.size(), cudaMemcpyHostToDevice, st));
     GLB_CUDA(cudaStreamSynchronize(st));            // the staging vectors are locals
+    tm.lap("upload slabs");
     p->kind = GLB_POISSON_KIND_DATAFLOW;
     p->ldu = lanes * 4;
     p->grid = grid; p->threads = threads; p->fn = fn; p->smem_bytes = smem;
@@ -1105,13 +1130,18 @@ static int plan_try_barrier(glb_poisson_plan *p, const std::vector<int> &h_rp, i
 }
 
 // device time of a short trial run of the plan's kernel on an all-zero problem (second of two launches)
-static int plan_time(glb_poisson_plan *p, float *ms, cudaStream_t st)
+// rows x ldu floats a trial run needs for Db, u0, u1
+static size_t plan_time_floats(const glb_poisson_plan *p) { return 3 * ((size_t)p->n + (size_t)p->scratch_row) * p->ldu; }
+
+// Trial run on zeros: T iterations twice, the second one timed.  `buf` (plan_time_floats(p) floats) may be shared by
+// several trials; nullptr = allocate here.
+static int plan_time(glb_poisson_plan *p, float *ms, cudaStream_t st, float *shared_buf = nullptr)
 {
-    const int T = 96;
-    const size_t rows = (size_t)p->n + (size_t)p->scratch_row;             // label matrices carry the scratch row
+    const int T = 64;
+    const size_t rows = (size_t)p->n + (size_t)p->scratch_row;             // label matrices carry the scratch rows
     const size_t bytes = rows * p->ldu * sizeof(float);
-    float *buf = nullptr;
-    GLB_CUDA(cudaMalloc(&buf, 3 * bytes));
+    float *buf = shared_buf;
+    if (!buf) GLB_CUDA(cudaMalloc(&buf, 3 * bytes));
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
     int rc = 0;
@@ -1125,7 +1155,7 @@ static int plan_time(glb_poisson_plan *p, float *ms, cudaStream_t st)
     if (ce == cudaSuccess && rc == 0) cudaEventElapsedTime(ms, e0, e1);
     if (ce == cudaSuccess && rc == 0) rc = glb_poisson_plan_check(p, st);
     cudaEventDestroy(e0); cudaEventDestroy(e1);
-    cudaFree(buf);
+    if (!shared_buf) cudaFree(buf);
     if (rc == 0 && ce != cudaSuccess) { set_error("plan_time: %s", cudaGetErrorString(ce)); rc = (int)ce; }
     return rc;
 }
@@ -1173,12 +1203,16 @@ extern "C" GLB_API int glb_poisson_plan_create(glb_poisson_plan **plan, const in
             // point of hundreds of producers) run best with a gate every few iterations, hub-free graphs with rare gates.
             const int cand[3] = {32, 4, 1};
             float best = 0.f;
-            for (int i = 0; i < 3; ++i) {
+            float *trial = nullptr;
+            GLB_CUDA(cudaMalloc(&trial, plan_time_floats(p) * sizeof(float)));
+            for (int i = 0; i < 3 && rc == 0; ++i) {
                 p->gate_every = cand[i];
                 float ms = 0.f;
-                if ((rc = plan_time(p, &ms, st))) return rc;
-                if (i == 0 || ms < best) { best = ms; ms_df = ms; p->tuned_gate = cand[i]; }
+                rc = plan_time(p, &ms, st, trial);
+                if (rc == 0 && (i == 0 || ms < best)) { best = ms; ms_df = ms; p->tuned_gate = cand[i]; }
             }
+            cudaFree(trial);
+            if (rc) return rc;
             p->gate_every = p->tuned_gate;
             tm.lap("gate tuning");
         }
