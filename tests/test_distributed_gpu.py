@@ -35,7 +35,7 @@ def test_world_size_two_over_nccl(tmp_path):
         pytest.skip("needs two GPUs")
     out = tmp_path / "res.npz"
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-           "--master-port", "29671", os.path.join(ROOT, "tools", "bench_cfg5.py"), "--check", str(out), "--n", "20000", "--iters", "15"]
+           "--master-port", "29671", os.path.join(ROOT, "tools", "bench_cfg5.py"), "--check", str(out), "--size", "20000", "--iters", "15"]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr
     z = np.load(out)

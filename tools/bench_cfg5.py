@@ -3,7 +3,7 @@
 with one all-gather of the label matrix per iteration.  Launch with torchrun (one rank per GPU) or plain python
 (one GPU).  Prints one JSON line on rank 0.
 
-    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tools/bench_cfg5.py [--n 2000000]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tools/bench_cfg5.py [--size 2000000]
     ... --check out.npz   small parity run: partitioned result vs the single-GPU step kernel (used by the tests)
 """
 import argparse, json, os, sys, time
@@ -23,7 +23,7 @@ def build_graph(n, k=10, seed=0):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--n", type=int, default=2000000)
+    ap.add_argument("--size", dest="n", type=int, default=2000000, help="nodes (not --n: torchrun reads that as an abbreviation of its own options)")
     ap.add_argument("--iters", type=int, default=100)
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--check", default=None)
