@@ -17,6 +17,29 @@ from scipy import sparse, spatial
 knn_dir = os.path.abspath(os.path.join(os.getcwd(), "knn_data"))
 
 
+# graphs below this size are assembled with scipy on the host (a device round trip costs more than it saves);
+# tests set it to 0 to exercise the device path on the small goldens
+_device_assembly_min_n = 2048
+
+
+def _assemble_on_device(knn_ind, weights, n, k, symmetrize):
+    """weightmatrix.py:166-186 for the gaussian / user kernels through glb_knn_weights_csr_host (knn_graph.cu)."""
+    import ctypes
+    from . import _lib
+    ind = np.ascontiguousarray(knn_ind, dtype=np.int64)
+    w = np.ascontiguousarray(weights, dtype=np.float64)
+    cap = n * k * (2 if symmetrize else 1)
+    rp = np.empty(n + 1, dtype=np.int32)
+    col = np.empty(cap, dtype=np.int32)
+    val = np.empty(cap, dtype=np.float64)
+    nnz, nl = ctypes.c_int64(0), ctypes.c_int(0)
+    p = lambda a: ctypes.c_void_p(a.ctypes.data)
+    _lib.call("glb_knn_weights_csr_host", p(ind), p(w), int(n), int(k), 1 if symmetrize else 0, p(rp), p(col), p(val), int(cap),
+              ctypes.byref(nnz), ctypes.byref(nl))
+    m = nnz.value
+    return sparse.csr_matrix((val[:m].copy(), col[:m].copy(), rp), shape=(n, n))
+
+
 def sparse_max(A, B):
     """Elementwise max of two sparse matrices.  Reference graphlearning/utils.py:263-286."""
     I = (A + B) > 0
@@ -96,6 +119,9 @@ def knn(data, k, kernel="gaussian", eta=None, symmetrize=True, metric="raw", sim
         D = knn_dist * knn_dist
         eps = D[:, k - 1]
         weights = eta(D / eps)
+    if (eta is not None or kernel == "gaussian") and n >= _device_assembly_min_n:
+        # COO -> CSR, (W + W^T)/2, zero diagonal: on the device, bit-identical to the scipy expressions below
+        return _assemble_on_device(knn_ind, weights, n, k, symmetrize)
     knn_ind = knn_ind.flatten()
     weights = weights.flatten()
     self_ind = (np.ones((n, k)) * np.arange(n)[:, None]).flatten()

@@ -251,6 +251,19 @@ GLB_API int glb_gram_f64(const double *d_X, int ldx, int c1, const double *d_Y, 
 GLB_API int glb_right_mul_f64(const double *d_X, int ldx, int64_t n, int c1, const double *d_S, int c2, double *d_Y, int ldy,
                               void *stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * kNN result -> CSR weight matrix.  Replaces the sparse assembly of weightmatrix.knn
+ * (graphlearning/weightmatrix.py:166-186): coo_matrix((weights, (self_ind, knn_ind))).tocsr(), the symmetrisation
+ * (W + W^T) / 2 of the gaussian / user kernels (:183), setdiag(0) and eliminate_zeros() (:185-186).
+ * ind: n x k int64 neighbour indices (row i = neighbours of i, self included), w: n x k float64 kernel weights
+ * (computed by the caller exactly as the reference does, :139-164).  Output: canonical CSR (int32 rowptr[n+1],
+ * int32 col, float64 val, columns ascending), bit-identical to scipy's.  cap = capacity of col / val in entries,
+ * at least n*k (2*n*k when symmetrize != 0).  HOST pointers, synchronous.
+ * ------------------------------------------------------------------------------------------- */
+GLB_API int glb_knn_weights_csr_host(const int64_t *h_ind, const double *h_w, int64_t n, int k, int symmetrize,
+                                     int32_t *h_rowptr, int32_t *h_col, double *h_val, int64_t cap, int64_t *nnz,
+                                     int *launches);
+
 #ifdef __cplusplus
 }
 #endif

@@ -103,3 +103,34 @@ def test_full_size_config2(kg):
     i = rows[:50]
     rec = np.sqrt(((X[i][:, None, :] - X[ind[i]]) ** 2).sum(-1))
     assert np.allclose(rec, dist[i], rtol=1e-12)
+
+
+def test_weight_matrix_assembly_on_device_is_bit_identical(gl, moons, blobs, small, monkeypatch):
+    """weightmatrix.knn for the gaussian kernel: COO -> CSR, (W + W^T)/2, zero diagonal on the device (knn_graph.cu)
+    against the goldens of the reference and against the scipy expressions (weightmatrix.py:166-186), bit for bit."""
+    from scipy import sparse
+    wm = gl.weightmatrix
+
+    def same(A, B):
+        A = sparse.csr_matrix(A); B = sparse.csr_matrix(B); B.sort_indices()
+        assert np.array_equal(A.indptr, B.indptr) and np.array_equal(A.indices, B.indices) and np.array_equal(A.data, B.data)
+
+    monkeypatch.setattr(wm, "_device_assembly_min_n", 0)
+    same(wm.knn(None, 10, knn_data=(moons["knn_ind"], moons["knn_dist"])), moons.csr("W"))
+    same(wm.knn(None, 10, symmetrize=False, knn_data=(moons["knn_ind"], moons["knn_dist"])), moons.csr("Wd"))
+    same(wm.knn(None, 7, knn_data=(small["knn_ind"].astype(np.int64), small["knn_dist"])), small.csr("W_gaussian_1"))
+    same(wm.knn(None, 7, symmetrize=False, knn_data=(small["knn_ind"].astype(np.int64), small["knn_dist"])), small.csr("W_gaussian_0"))
+    k = blobs["knn_ind"].shape[1]
+    same(wm.knn(None, k - 1, knn_data=(blobs["knn_ind"], blobs["knn_dist"])), blobs.csr("W"))
+    # user kernel (eta) and a full-size graph: device path vs the scipy path of the same function
+    X, _ = orc.synthetic_blobs(70000, 8, c=10, seed=0)
+    ind, dist = orc.knnsearch(X.astype(np.float64), 11, method="kdtree")
+    for kw in ({}, {"eta": lambda x: np.exp(-x)}, {"symmetrize": False}):
+        Wd = wm.knn(None, 10, knn_data=(ind, dist), **kw)
+        monkeypatch.setattr(wm, "_device_assembly_min_n", 10 ** 9)
+        Wh = wm.knn(None, 10, knn_data=(ind, dist), **kw)
+        monkeypatch.setattr(wm, "_device_assembly_min_n", 0)
+        same(Wd, Wh)
+    assert (Wd != Wd.T).nnz > 0                                      # the last one is the directed graph
+    with pytest.raises(Exception):
+        wm.knn(None, 3, knn_data=(np.array([[0, 5, 1], [1, 0, 2], [2, 1, 0]]), np.ones((3, 3))))   # index out of range
