@@ -244,6 +244,10 @@ struct LipArgs {
     unsigned long long *ctl;        // [0] sweeps fully completed ("checked"), [1] stop_at (kNoStop = none), [2..2+kCtlSlots) rows done per
                                     // sweep, [2+kCtlSlots..2+2kCtlSlots) error bits per sweep
     int n_rows;                     // unlabelled rows (= rows every sweep must complete)
+    // level-counter schedule of the barrier kernel (nullptr = off): level of every 32-position block of `order`, rows per
+    // level, and one cumulative "rows done" counter per level
+    const int *blk_level, *lvl_size;
+    unsigned long long *lvl_done;
 };
 
 constexpr int kRing = 4;                              // version buffers of the pipelined kernel
@@ -280,6 +284,19 @@ __global__ void __launch_bounds__(256, 2) lip_gauss_seidel_kernel(LipArgs A)
             const int i = p0 + lane < A.n_active ? __ldg(A.order + p0 + lane) : -1;
             const bool active = i >= 0;
             bool pending = active;
+            // level counters: the rows of this warp (one level) may start once every row of the level below has published
+            // its value in this sweep - one poll per warp on one counter instead of one per neighbour cell
+            const int lev = A.blk_level ? __ldg(A.blk_level + (p0 >> 5)) : -1;
+            if (lev > 0) {
+                if (lane == 0) {
+                    const unsigned long long need = (unsigned long long)(it + 1) * (unsigned long long)__ldg(A.lvl_size + lev - 1);
+                    unsigned spins = 0;
+                    long long tw0 = 0;
+                    while (ld_relaxed_u64(A.lvl_done + lev - 1) < need && !wait_expired(A.counter + 1, spins, tw0)) { }
+                    fence_gpu();
+                }
+                __syncwarp();
+            }
             int s = 0, L = 0, k = 0, crit = -1;
             double uv[kLipCap], wv[kLipCap];
             double minu = 0.0, maxu = 0.0, sumu = 0.0, deg = 0.0, uold = 0.0;
@@ -371,6 +388,11 @@ __global__ void __launch_bounds__(256, 2) lip_gauss_seidel_kernel(LipArgs A)
             }
             // lockstep variant: the whole warp updates its rows together (one pass through the 30-step bisection)
             if (LOCKSTEP && active) update_row();
+            if (lev >= 0) {                                       // publish: this warp's rows of level `lev` are done
+                const int nrows = __popc(__ballot_sync(0xffffffffu, active));
+                __syncwarp();
+                if (lane == 0 && nrows) { fence_gpu(); atomicAdd(A.lvl_done + lev, (unsigned long long)nrows); }
+            }
         }
         const double gerr = barrier_max(err, A.slots, A.counter, (unsigned)it);
         if (gerr < A.tol && it > 20) { done = it + 1; break; }
@@ -670,7 +692,8 @@ int upload_common(Common &C, const int32_t *h_nbr, const int32_t *h_row, const d
 // largest level among the unlabelled neighbours j < i of the unlabelled row i (those are the values row i must wait for
 // inside a sweep), rows sorted by (level, index), every level padded with -1 to a multiple of 32; crit[i] = a neighbour attaining that maximum, -1 without producers.
 void level_schedule(const int32_t *h_nbr, const int32_t *h_row, const std::vector<int> &lab, int n, int M,
-                    std::vector<int> &order, std::vector<int> &crit, int *depth)
+                    std::vector<int> &order, std::vector<int> &crit, int *depth, std::vector<int> *blk_level = nullptr,
+                    std::vector<int> *lvl_size = nullptr)
 {
     std::vector<int> start((size_t)n + 1, 0), level((size_t)n, -1);
     for (int k = 0; k < M; ++k) ++start[(size_t)h_row[k] + 1];
@@ -695,6 +718,12 @@ void level_schedule(const int32_t *h_nbr, const int32_t *h_row, const std::vecto
     std::vector<int> pos((size_t)maxl + 2, 0);
     for (int l = 0; l <= maxl; ++l) pos[l + 1] = pos[l] + ((count[l] + 31) & ~31);      // a warp never straddles two levels
     order.assign((size_t)pos[maxl + 1], -1);
+    if (blk_level) {
+        blk_level->assign(order.size() / 32, 0);
+        for (int l = 0; l <= maxl; ++l)
+            for (int b = pos[l] / 32; b < pos[l + 1] / 32; ++b) (*blk_level)[b] = l;
+    }
+    if (lvl_size) lvl_size->assign(count.begin(), count.end());
     for (int i = 0; i < n; ++i)
         if (level[i] >= 0) order[pos[level[i]]++] = i;
     *depth = maxl + 1;
@@ -777,11 +806,14 @@ extern "C" GLB_API int glb_lip_iterate_host(double *h_u, const int32_t *h_nbr, c
     //                    flops, so the shortest path from "last neighbour ready" to "value published" wins.
     //   bit 3: sweeps overlap (ring of version buffers, no barrier between sweeps) - GLB_LIP_MODE without it selects the
     //          one-barrier-per-sweep kernel
+    //   bit 4: level counters - a warp polls one "level below done" counter instead of its rows' neighbour cells
     int mode = weighted ? 7 : 0;
     if (getenv("GLB_LIP_MODE")) mode = atoi(getenv("GLB_LIP_MODE"));
     if (mode & 4) mode |= 1;                                      // lockstep needs warps of one level
     int depth = 0;
-    level_schedule(h_nbr, h_row, lab, n, M, order, crit, &depth);
+    std::vector<int> blk_level, lvl_size;
+    if (mode & 16) mode |= 1;                                     // level counters need warps of one level
+    level_schedule(h_nbr, h_row, lab, n, M, order, crit, &depth, &blk_level, &lvl_size);
     if (!(mode & 1)) {
         order.clear();
         for (int i = 0; i < n; ++i) if (lab[i] < 0) order.push_back(i);
@@ -808,8 +840,17 @@ extern "C" GLB_API int glb_lip_iterate_host(double *h_u, const int32_t *h_nbr, c
         GLB_CUDA(cudaStreamSynchronize(st));                      // h_ctl is a local
         lip_ring_pack_kernel<<<gb, 256, 0, st>>>(u, C.lab, C.labval, ring, n);
     }
+    int *d_blk_level = nullptr, *d_lvl_size = nullptr;
+    unsigned long long *d_lvl_done = nullptr;
+    if ((mode & 16) && !pipelined && !blk_level.empty()) {
+        GLB_CUDA(C.A.alloc(&d_blk_level, blk_level.size())); GLB_CUDA(C.A.alloc(&d_lvl_size, lvl_size.size()));
+        GLB_CUDA(C.A.alloc(&d_lvl_done, lvl_size.size()));
+        GLB_CUDA(cudaMemcpyAsync(d_blk_level, blk_level.data(), blk_level.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+        GLB_CUDA(cudaMemcpyAsync(d_lvl_size, lvl_size.data(), lvl_size.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+        GLB_CUDA(cudaMemsetAsync(d_lvl_done, 0, lvl_size.size() * sizeof(unsigned long long), st));
+    }
     LipArgs A{C.start, C.nbr, C.W, C.lab, d_order, d_crit, C.c0, C.c1, u_out, C.slots, C.counter, C.sweeps, n, M, T,
-              (int)order.size(), (mode & 2) ? 1 : 0, tol, alpha, beta, ring, ctl, n_rows};
+              (int)order.size(), (mode & 2) ? 1 : 0, tol, alpha, beta, ring, ctl, n_rows, d_blk_level, d_lvl_size, d_lvl_done};
     const void *fn;
     if (pipelined)
         fn = weighted ? ((mode & 4) ? (const void *)lip_pipelined_kernel<true, true> : (const void *)lip_pipelined_kernel<true, false>)

@@ -198,10 +198,10 @@ def test_70k_graph_against_oracle():
     assert sw2 == 22 and np.max(np.abs(again - conv)) < 22 * 1e-4      # `it > 20` forces 22 sweeps, each moving < tol
 
 
-@pytest.mark.parametrize("mode", ["8", "15", "3"])
+@pytest.mark.parametrize("mode", ["8", "15", "3", "21", "17"])
 def test_alternative_schedules_are_bit_identical(plap, monkeypatch, mode):
     """GLB_LIP_MODE selects other schedules of the same sweep (bit 0 level order, 1 producer poll, 2 lockstep, 3 sweeps
-    overlapping through a ring of version buffers with per-sweep completion counters).  All of them must reproduce the
+    overlapping through a ring of version buffers with per-sweep completion counters, 4 per-level completion counters).  All of them must reproduce the
     reference's sequential sweep bit for bit, including the sweep at which the stopping rule fires."""
     monkeypatch.setenv("GLB_LIP_MODE", mode)
     I, J, V, ti, val = plap["cI"], plap["cJ"], plap["cV"], plap["train_ind"], plap["val"]
