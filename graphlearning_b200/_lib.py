@@ -65,6 +65,8 @@ SIGNATURES = {
     "glb_right_mul_f64": (c_int, [c_void_p, c_int, c_int64, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p]),
     "glb_knn_weights_csr_host": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int64,
                                          POINTER(c_int64), POINTER(c_int)]),
+    "glb_lip_iterate_multi_host": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_double, c_int,
+                                           c_double, c_double, c_int, c_int, c_int, c_int, POINTER(c_int), POINTER(c_int)]),
     "glb_poisson_gd_host": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int, c_void_p, c_int64,
                                     c_int, c_int, c_void_p, POINTER(c_int), POINTER(c_int)]),
 }

@@ -610,6 +610,188 @@ __global__ void __launch_bounds__(256) lip_pack_kernel(const double *u, const in
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------
+// Batched Gauss-Seidel: c right-hand sides (the one-vs-rest classes of ssl.plaplace / ssl.amle) in one launch
+// ------------------------------------------------------------------------------------------------------------
+// The classes share the graph AND the set of Dirichlet rows, so they share the dependency DAG: one thread per (row, class),
+// cells at index row * c + class, and every latency hop of the sweep carries c values instead of one.  Each class keeps
+// the reference's own stopping rule: the per-sweep barrier carries one error per class, a class whose error drops below
+// tol (after sweep 20) is frozen at that sweep - exactly where the reference's separate run would have stopped - while
+// the others go on.  Results per class are bit-identical to c separate calls.
+struct LipMultiArgs {
+    const int *start, *nbr;
+    const double *W;
+    const int *lab, *order;
+    Cell *c0, *c1;
+    double *u_out;
+    unsigned long long *errs;       // [3][c] per-sweep, per-class error bits
+    unsigned *counter;              // [0] barrier, [1] watchdog
+    int *sweeps;                    // [c]
+    int n, M, T, n_active, c;
+    double tol, alpha, beta;
+};
+
+constexpr int kMaxClasses = 32;
+
+template <bool WEIGHTED>
+__global__ void __launch_bounds__(256, 2) lip_multi_kernel(LipMultiArgs A)
+{
+    __shared__ unsigned long long s_err[kMaxClasses];
+    const int c = A.c;
+    const int NT = (gridDim.x * blockDim.x) / (32 * c) * (32 * c);          // stride: a thread keeps its class in every round
+    const int gt = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const bool worker = gt < NT;                                            // threads beyond the stride only take part in barriers
+    const int cls = gt % c;
+    const long long total = (long long)A.n_active * c;
+    const double qnan = __longlong_as_double(0x7ff8000000000000ll);
+    unsigned stopped_mask = 0u;                                             // classes frozen so far (same in every thread)
+    int my_stop = 0;                                                        // sweeps executed by this thread's class (0 = still running)
+    int it = 0;
+    for (; it < A.T && stopped_mask != (c == 32 ? 0xffffffffu : ((1u << c) - 1u)); ++it) {
+        const Cell *cur = (it & 1) ? A.c1 : A.c0;
+        Cell *nxt = (it & 1) ? A.c0 : A.c1;
+        const unsigned long long want = (unsigned long long)it + 1ull;
+        double err = 0.0;
+        const bool running = worker && !my_stop;
+        for (long long p0 = gt - lane; p0 < total; p0 += NT) {              // warp-uniform trip count
+            const long long idx = p0 + lane;
+            bool pending = running && idx < total;
+            const int i = pending ? __ldg(A.order + (int)(idx / c)) : 0;
+            int s = 0, L = 0, k = 0;
+            double uv[kLipCap], wv[kLipCap];
+            double minu = 0.0, maxu = 0.0, sumu = 0.0, deg = 0.0, uold = 0.0;
+            bool empty_row = false;
+            if (pending) {
+                s = A.start[i];
+                L = A.start[i + 1] - s;
+                uold = ld_cell(cur + (size_t)i * c + cls).a;
+                if (L == 0) {
+                    empty_row = true;
+                    if (s < A.M) L = 1; else { minu = maxu = qnan; }
+                }
+            }
+            unsigned spins = 0;
+            long long tw0 = 0;
+            while (__any_sync(0xffffffffu, pending)) {
+                if (!pending) continue;
+                if (wait_expired(A.counter + 1, spins, tw0)) { pending = false; continue; }
+                int jj[kLipBatch];
+                Cell cc[kLipBatch];
+#pragma unroll
+                for (int q = 0; q < kLipBatch; ++q) {
+                    jj[q] = k + q < L ? __ldg(A.nbr + s + k + q) : -1;
+                    if (jj[q] >= 0) cc[q] = ld_cell((jj[q] < i ? nxt : cur) + (size_t)jj[q] * c + cls);
+                }
+                bool halt = false;
+#pragma unroll
+                for (int q = 0; q < kLipBatch; ++q) {
+                    if (halt || jj[q] < 0) continue;
+                    if (jj[q] < i && cc[q].b < want) { halt = true; continue; }
+                    const double v = cc[q].a;
+                    if (k == 0) { minu = v; maxu = v; }
+                    if (!empty_row) {
+                        const double w = __ldg(A.W + s + k);
+                        if (!WEIGHTED) {
+                            sumu = __dadd_rn(sumu, __dmul_rn(w, v));
+                            deg = __dadd_rn(deg, w);
+                        } else if (k < kLipCap) {
+                            uv[k] = v; wv[k] = w;
+                        }
+                    }
+                    minu = v < minu ? v : minu;
+                    maxu = v > maxu ? v : maxu;
+                    ++k;
+                }
+                if (k < L) continue;
+                pending = false;
+                double ne;
+                if (!WEIGHTED) {
+                    ne = __dadd_rn(__ddiv_rn(__dmul_rn(A.alpha, sumu), deg), __ddiv_rn(__dmul_rn(A.beta, __dadd_rn(minu, maxu)), 2.0));
+                } else {
+                    double a = minu, b = maxu;
+                    const int Lr = empty_row ? 0 : L;
+                    const int Lc = Lr < kLipCap ? Lr : kLipCap;
+                    for (int r = 0; r < 30; ++r) {
+                        const double tm = __ddiv_rn(__dadd_rn(a, b), 2.0);
+                        double minw = 0.0, maxw = 0.0;
+                        for (int kk = 0; kk < Lc; ++kk) {
+                            const double d = __dmul_rn(wv[kk], __dsub_rn(tm, uv[kk]));
+                            minw = d < minw ? d : minw;
+                            maxw = d > maxw ? d : maxw;
+                        }
+                        for (int kk = kLipCap; kk < Lr; ++kk) {
+                            const int j = __ldg(A.nbr + s + kk);
+                            const double d = __dmul_rn(__ldg(A.W + s + kk), __dsub_rn(tm, ld_cell((j < i ? nxt : cur) + (size_t)j * c + cls).a));
+                            minw = d < minw ? d : minw;
+                            maxw = d > maxw ? d : maxw;
+                        }
+                        if (__dadd_rn(minw, maxw) > 0.0) b = tm; else a = tm;
+                    }
+                    ne = __ddiv_rn(__dadd_rn(a, b), 2.0);
+                }
+                double d = __dsub_rn(uold, ne);
+                d = d < 0.0 ? -d : d;
+                if (d > err) err = d;
+                st_cell(nxt + (size_t)i * c + cls, ne, want);
+            }
+        }
+        // barrier that carries one error per class: block-level max in shared memory, one atomic per class and block
+        if (threadIdx.x < kMaxClasses) s_err[threadIdx.x] = 0ull;
+        __syncthreads();
+        if (running && err > 0.0) atomicMax(&s_err[cls], (unsigned long long)__double_as_longlong(err));
+        __syncthreads();
+        unsigned long long *slot = A.errs + (size_t)(it % 3) * c;
+        if ((int)threadIdx.x < c) {
+            if (blockIdx.x == 0) A.errs[(size_t)((it + 1) % 3) * c + threadIdx.x] = 0ull;
+            if (s_err[threadIdx.x]) atomicMax(slot + threadIdx.x, s_err[threadIdx.x]);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            fence_gpu();
+            asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(A.counter), "r"(1u) : "memory");
+            const unsigned wantc = (unsigned)(it + 1) * gridDim.x;
+            unsigned spins = 0;
+            long long t0 = 0;
+            while (ld_relaxed_u32(A.counter) < wantc && !wait_expired(A.counter + 1, spins, t0)) { }
+            fence_gpu();
+        }
+        __syncthreads();
+        for (int k2 = 0; k2 < c; ++k2) {                                   // every thread takes the same decisions
+            if (stopped_mask & (1u << k2)) continue;
+            const double e = __longlong_as_double((long long)ld_relaxed_u64(slot + k2));
+            if (e < A.tol && it > 20) {
+                stopped_mask |= 1u << k2;
+                if (k2 == cls) my_stop = it + 1;
+            }
+        }
+        __syncthreads();
+    }
+    const int nsweeps = my_stop ? my_stop : it;                             // `it` = T, or the sweep at which the last class stopped
+    if (worker) {
+        const Cell *fin = (nsweeps & 1) ? A.c1 : A.c0;
+        for (long long idx = gt; idx < (long long)A.n * c; idx += NT) A.u_out[idx] = ld_cell(fin + idx).a;   // idx % c == cls
+        if (gt < c) A.sweeps[gt] = nsweeps;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+lip_multi_pack_kernel(const double *u, const int *lab, const double *labval, Cell *c0, Cell *c1, int n, int c)
+{
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < (long long)n * c; idx += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(idx / c), k = (int)(idx % c);
+        const int l = lab[i];
+        if (l >= 0) {
+            c0[idx].a = labval[(size_t)l * c + k]; c0[idx].b = kVerFixed;
+            c1[idx].a = labval[(size_t)l * c + k]; c1[idx].b = kVerFixed;
+        } else {
+            c0[idx].a = u[idx]; c0[idx].b = 0ull;
+            c1[idx].a = u[idx]; c1[idx].b = 0ull;
+        }
+    }
+}
+
 struct Arena {
     std::vector<void *> ptrs;
     ~Arena() { for (void *p : ptrs) cudaFree(p); }
@@ -873,6 +1055,61 @@ extern "C" GLB_API int glb_lip_iterate_host(double *h_u, const int32_t *h_nbr, c
     GLB_CUDA(cudaStreamSynchronize(st));
     if (timed_out) { set_error("%s: a waiting loop of the sweep kernel hit its watchdog; results are invalid", __func__); return GLB_E_TIMEOUT; }
     if (sweeps) *sweeps = sw;
+    if (launches) *launches = nl;
+    return 0;
+}
+
+extern "C" GLB_API int glb_lip_iterate_multi_host(double *h_u, const int32_t *h_nbr, const int32_t *h_row, const double *h_w,
+                                                  const int32_t *h_ind, const double *h_val, int T, double tol, int weighted,
+                                                  double alpha, double beta, int n, int M, int m, int c, int *sweeps, int *launches)
+{
+    GLB_CHECK_ARG(h_u && (M == 0 || (h_nbr && h_row && h_w)) && (m == 0 || (h_ind && h_val)), "null pointer");
+    GLB_CHECK_ARG(n > 0 && M >= 0 && m >= 0 && T >= 0, "size out of range");
+    GLB_CHECK_ARG(c >= 1 && c <= kMaxClasses && (long long)n * c < (1ll << 31), "1 <= c <= 32 right-hand sides");
+    int rc = no_gpu();
+    if (rc) return rc;
+    cudaStream_t st = 0;
+    int nl = 0;
+    Common C;
+    std::vector<int> lab, order;
+    // upload_common allocates single-class cells and uploads the first column of val; the per-class arrays follow here
+    if ((rc = upload_common(C, h_nbr, h_row, h_w, h_ind, h_val, n, M, 0, st, &nl, lab))) return rc;
+    if ((rc = build_labels(h_ind, n, m, lab))) return rc;
+    for (int i = 0; i < n; ++i) if (lab[i] < 0) order.push_back(i);
+    double *u, *u_out, *labval;
+    int *d_order, *d_lab, *d_sweeps;
+    Cell *c0, *c1;
+    unsigned long long *errs;
+    const size_t nc = (size_t)n * c;
+    GLB_CUDA(C.A.alloc(&u, nc));            GLB_CUDA(C.A.alloc(&u_out, nc));       GLB_CUDA(C.A.alloc(&labval, (size_t)m * c));
+    GLB_CUDA(C.A.alloc(&d_order, order.size())); GLB_CUDA(C.A.alloc(&d_lab, (size_t)n)); GLB_CUDA(C.A.alloc(&d_sweeps, (size_t)c));
+    GLB_CUDA(C.A.alloc(&c0, nc));           GLB_CUDA(C.A.alloc(&c1, nc));          GLB_CUDA(C.A.alloc(&errs, (size_t)3 * c));
+    GLB_CUDA(cudaMemcpyAsync(u, h_u, nc * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (m) GLB_CUDA(cudaMemcpyAsync(labval, h_val, (size_t)m * c * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (!order.empty()) GLB_CUDA(cudaMemcpyAsync(d_order, order.data(), order.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    GLB_CUDA(cudaMemcpyAsync(d_lab, lab.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice, st));
+    GLB_CUDA(cudaMemsetAsync(errs, 0, (size_t)3 * c * sizeof(unsigned long long), st));
+    GLB_CUDA(cudaMemsetAsync(d_sweeps, 0, (size_t)c * sizeof(int), st));
+    const int gb = sm_count() * 4;
+    lip_multi_pack_kernel<<<gb, 256, 0, st>>>(u, d_lab, labval, c0, c1, n, c);
+    LipMultiArgs A{C.start, C.nbr, C.W, d_lab, d_order, c0, c1, u_out, errs, C.counter, d_sweeps, n, M, T, (int)order.size(), c,
+                   tol, alpha, beta};
+    const void *fn = weighted ? (const void *)lip_multi_kernel<true> : (const void *)lip_multi_kernel<false>;
+    int grid = 0;
+    if ((rc = coop_grid(fn, 256, &grid))) return rc;
+    grid = std::min(grid, std::max(ceil_div(32 * c, 256) + 1, ceil_div((int64_t)n * c, 256)));
+    void *args[] = {&A};
+    GLB_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(256), args, 0, st));
+    nl += 2;
+    GLB_LAUNCH_CHECK();
+    std::vector<int> sw((size_t)c, 0);
+    GLB_CUDA(cudaMemcpyAsync(h_u, u_out, nc * sizeof(double), cudaMemcpyDeviceToHost, st));
+    GLB_CUDA(cudaMemcpyAsync(sw.data(), d_sweeps, (size_t)c * sizeof(int), cudaMemcpyDeviceToHost, st));
+    unsigned timed_out = 0;
+    GLB_CUDA(cudaMemcpyAsync(&timed_out, C.counter + 1, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+    GLB_CUDA(cudaStreamSynchronize(st));
+    if (timed_out) { set_error("%s: a waiting loop of the sweep kernel hit its watchdog; results are invalid", __func__); return GLB_E_TIMEOUT; }
+    if (sweeps) for (int k = 0; k < c; ++k) sweeps[k] = sw[k];
     if (launches) *launches = nl;
     return 0;
 }

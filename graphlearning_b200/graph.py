@@ -138,6 +138,25 @@ class graph:
             return D * self.weight_matrix + self.weight_matrix * D
         raise ValueError("Invalid reweighting method " + str(method) + ".")
 
+    def _lip_multi(self, bdy_set, bdy_val, T, tol, weighted, alpha, beta):
+        """c right-hand sides (bdy_val: m x c) through glb_lip_iterate_multi_host: the classes of a one-vs-rest fit share the
+        graph and the Dirichlet rows, so they run as ONE batched sweep kernel; column k equals the single call on column k."""
+        from . import _lib
+        import ctypes
+        n = self.num_nodes
+        I, J, V = self._ccode_arrays()
+        bs = np.ascontiguousarray(bdy_set, dtype=np.int32)
+        bv = np.ascontiguousarray(bdy_val, dtype=np.float64)
+        c = bv.shape[1]
+        u = np.zeros((n, c), dtype=np.float64)
+        sw = (ctypes.c_int * c)()
+        nl = ctypes.c_int(0)
+        ptr = lambda a: ctypes.c_void_p(a.ctypes.data)
+        _lib.call("glb_lip_iterate_multi_host", ptr(u), ptr(J), ptr(I), ptr(V), ptr(bs), ptr(bv), int(T), float(tol),
+                  1 if weighted else 0, float(alpha), float(beta), n, len(I), len(bs), c, sw, ctypes.byref(nl))
+        self.sweeps, self.gpu_launches = list(sw), nl.value
+        return u
+
     # ---- p-Laplace / AMLE sweeps on the GPU (plaplace.cu) ---------------------------------------------------
     def plaplace(self, bdy_set, bdy_val, p, tol=1e-1, max_num_it=1e6, prog=False, fast=True):
         """Game-theoretic p-Laplace equation with Dirichlet data.  Reference graphlearning/graph.py:1177-1279;
@@ -153,6 +172,8 @@ class graph:
         ptr = lambda a: ctypes.c_void_p(a.ctypes.data)
         sw, nl = ctypes.c_int(0), ctypes.c_int(0)
         T = int(min(float(max_num_it), 2.0 ** 31 - 1))
+        if fast and np.ndim(bdy_val) == 2:                       # batched one-vs-rest classes (not in the reference API)
+            return self._lip_multi(bdy_set, bdy_val, T, 1e-6, False, alpha, beta)
         if fast:
             u = np.zeros((n,), dtype=np.float64)
             bs = np.ascontiguousarray(bdy_set, dtype=np.int32)
@@ -182,6 +203,8 @@ class graph:
         n = self.num_nodes
         u = np.zeros((n,), dtype=np.float64)
         bdy_set, bdy_val = utils._boundary_handling(bdy_set, bdy_val)
+        if np.ndim(bdy_val) == 2:                                 # batched one-vs-rest classes (not in the reference API)
+            return self._lip_multi(bdy_set, bdy_val, int(min(float(max_num_it), 2.0 ** 31 - 1)), tol, weighted, 0.0, 1.0)
         bs = np.ascontiguousarray(bdy_set, dtype=np.int32)
         bv = np.ascontiguousarray(bdy_val, dtype=np.float64)
         I, J, V = self._ccode_arrays()

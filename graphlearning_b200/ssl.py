@@ -79,9 +79,14 @@ class ssl:
         train_labels = np.asarray(train_labels)
         if self.onevsrest:
             unique_labels = np.unique(train_labels)
-            self.prob = np.zeros((self.graph.num_nodes, len(unique_labels)))
-            for i, l in enumerate(unique_labels):
-                self.prob[:, i] = self._fit(train_ind, train_labels == l)
+            if hasattr(self, "_fit_onevsrest") and 1 < len(unique_labels) <= 32:
+                # the classes share the graph and the labelled rows: one batched solve, column i identical to
+                # self._fit(train_ind, train_labels == unique_labels[i]) of the reference loop (ssl.py:469-474)
+                self.prob = self._fit_onevsrest(train_ind, train_labels[:, None] == unique_labels[None, :])
+            else:
+                self.prob = np.zeros((self.graph.num_nodes, len(unique_labels)))
+                for i, l in enumerate(unique_labels):
+                    self.prob[:, i] = self._fit(train_ind, train_labels == l)
         else:
             self.prob = self._fit(train_ind, train_labels, all_labels=all_labels)
         if self.class_priors is not None:
@@ -274,6 +279,10 @@ class amle(ssl):
         return self.graph.amle(train_ind, train_labels, tol=self.tol, max_num_it=self.max_num_it,
                                weighted=self.weighted, prog=self.prog)
 
+    def _fit_onevsrest(self, train_ind, onehot):
+        return self.graph.amle(train_ind, np.asarray(onehot, dtype=np.float64), tol=self.tol, max_num_it=self.max_num_it,
+                               weighted=self.weighted, prog=self.prog)
+
 
 class plaplace(ssl):
     """Graph p-Laplace classifier, one-vs-rest.  Reference graphlearning/ssl.py:1681-1727."""
@@ -293,6 +302,12 @@ class plaplace(ssl):
     def _fit(self, train_ind, train_labels, all_labels=None):
         return self.graph.plaplace(train_ind, train_labels, self.p, max_num_it=self.max_num_it, tol=self.tol,
                                    fast=self.fast)
+
+    def _fit_onevsrest(self, train_ind, onehot):
+        if not self.fast:                                         # the Jacobi barrier-function solver stays one class at a time
+            return np.stack([self._fit(train_ind, onehot[:, k]) for k in range(onehot.shape[1])], axis=1)
+        return self.graph.plaplace(train_ind, np.asarray(onehot, dtype=np.float64), self.p, max_num_it=self.max_num_it,
+                                   tol=self.tol, fast=True)
 
 
 def ssl_accuracy(pred_labels, true_labels, train_ind):

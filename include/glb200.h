@@ -227,6 +227,13 @@ GLB_API int glb_lp_iterate_host(double *h_uu, double *h_ul, const int32_t *h_nbr
 GLB_API int glb_lip_iterate_host(double *h_u, const int32_t *h_nbr, const int32_t *h_row, const double *h_w,
                                  const int32_t *h_ind, const double *h_val, int T, double tol, int weighted, double alpha,
                                  double beta, int n, int M, int m, int *sweeps, int *launches);
+/* The same sweeps for c right-hand sides at once - the one-vs-rest loop of ssl.fit (graphlearning/ssl.py:469-474) over
+ * ssl.plaplace / ssl.amle, whose classes share the graph and the Dirichlet rows.  u: n x c row-major (in/out), val: m x c
+ * row-major, sweeps: c ints (each class keeps its own stopping sweep).  Column k of the result is bit-identical to
+ * glb_lip_iterate_host on column k.  c <= 32. */
+GLB_API int glb_lip_iterate_multi_host(double *h_u, const int32_t *h_nbr, const int32_t *h_row, const double *h_w,
+                                       const int32_t *h_ind, const double *h_val, int T, double tol, int weighted,
+                                       double alpha, double beta, int n, int M, int m, int c, int *sweeps, int *launches);
 
 /* ---------------------------------------------------------------------------------------------
  * fp64 block operations for the spectral path: graph.eigen_decomp (graphlearning/graph.py:623-806, ARPACK svds

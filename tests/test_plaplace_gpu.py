@@ -213,3 +213,27 @@ def test_alternative_schedules_are_bit_identical(plap, monkeypatch, mode):
     assert np.array_equal(u, plap["amle_w"])
     u, _ = lip(np.zeros(2000), plap["dJ"], plap["dI"], plap["dV"], ti, val, 30, 1e-9, 0, 0.0, 1.0)
     assert np.array_equal(u, plap["amle_u_directed_T30"], equal_nan=True)
+
+
+def test_batched_classes_equal_separate_calls(gl, plap, blobs):
+    """glb_lip_iterate_multi_host: the c one-vs-rest right-hand sides in one launch; every column - values AND the sweep at
+    which its own stopping rule fired - must equal the single-class call, and ssl.plaplace / ssl.amle (which use the
+    batched path) must still match the reference goldens."""
+    I, J, V, ti = plap["cI"], plap["cJ"], plap["cV"], plap["train_ind"]
+    labels = blobs["labels"]
+    onehot = (labels[ti][:, None] == np.unique(labels[ti])[None, :]).astype(np.float64)
+    G = gl.graph(blobs.csr("W"))
+    for weighted, tol, T in ((False, 1e-5, 1000), (True, 1e-3, 60)):
+        U = G.amle(ti, onehot, tol=tol, max_num_it=T, weighted=weighted)
+        sw_multi = list(G.sweeps)
+        assert U.shape == (2000, onehot.shape[1]) and len(set(sw_multi)) > 1 or weighted     # classes stop at different sweeps
+        for k in range(onehot.shape[1]):
+            uk, sk = lip(np.zeros(2000), G.J, G.I, G.V, ti, onehot[:, k], T, tol, int(weighted), 0.0, 1.0)
+            assert np.array_equal(U[:, k], uk) and sw_multi[k] == sk, (weighted, k, sw_multi[k], sk)
+    m = gl.ssl.plaplace(blobs.csr("W"), p=3)
+    u = m.fit(ti, labels[ti])
+    exact = np.array_equal(G.J, plap["cJ"]) and np.array_equal(G.I, plap["cI"])
+    assert np.array_equal(u, plap["ssl_plaplace_p3"]) if exact else np.allclose(u, plap["ssl_plaplace_p3"], rtol=1e-9, atol=1e-12)
+    m = gl.ssl.amle(blobs.csr("W"))
+    u = m.fit(ti, labels[ti])
+    assert np.array_equal(u, plap["ssl_amle"]) if exact else np.allclose(u, plap["ssl_amle"], rtol=1e-9, atol=1e-12)
