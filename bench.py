@@ -109,6 +109,10 @@ def other_rows(W, labels, ti):
         for name, fn in (("plaplace_p3_fast", lambda: G.plaplace(t5, val, 3)), ("amle_weighted", lambda: G.amle(t5, val, tol=1e-3, max_num_it=300))):
             t0 = time.perf_counter(); fn(); t = time.perf_counter() - t0
             out[name] = {"seconds_host_to_host": t, "sweeps": int(G.sweeps), "us_per_sweep": 1e6 * t / max(1, G.sweeps)}
+        mp = gl.ssl.plaplace(W, p=3)                                # one-vs-rest over the 10 classes, batched sweep kernel
+        t0 = time.perf_counter(); mp.fit(t5, labels[t5]); t = time.perf_counter() - t0
+        out["ssl_plaplace_p3_fit_10_classes"] = {"seconds": t, "sweeps_per_class": [int(x) for x in mp.graph.sweeps],
+                                                 "reference_cpu_seconds": "15.7 (BASELINE.md section 2, MNIST-size graph)"}
     except Exception as e:                                   # never lose the headline line over an extra
         out["error"] = repr(e)
     return out
