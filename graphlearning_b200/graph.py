@@ -33,9 +33,16 @@ class graph:
         W = self.weight_matrix
         key = (id(W), W.nnz, id(W.data))
         if self._coo is None or self._coo[0] != key:
-            I, J, V = sparse.find(W)
-            ind = np.argsort(I)
-            I, J, V = I[ind], J[ind], V[ind]
+            if W.has_canonical_format:
+                # sparse.find of a canonical CSR lists the stored nonzeros row by row with ascending columns, and the
+                # argsort of that already sorted row index is the identity: same triplets without the 0.4 s of COO work
+                keep = W.data != 0
+                I = np.repeat(np.arange(W.shape[0]), np.diff(W.indptr))[keep]
+                J, V = W.indices[keep], W.data[keep]
+            else:
+                I, J, V = sparse.find(W)
+                ind = np.argsort(I)
+                I, J, V = I[ind], J[ind], V[ind]
             self._coo = (key, np.ascontiguousarray(I, dtype=np.int32), np.ascontiguousarray(J, dtype=np.int32),
                          np.ascontiguousarray(V, dtype=np.float64))
         return self._coo[1:]
