@@ -754,6 +754,7 @@ struct glb_poisson_plan {
     int tuned_gate = 32;
     unsigned *d_gate = nullptr;         // dataflow kernel: start gate counter
     int gate_every = 32;                // dataflow kernel: iterations between re-alignment gates (tuned at plan time)
+    bool has_long_rows = false;         // rows longer than a slice batch exist (dealt over whole warps)
     int scratch_row = 0;                // > 0: the label matrices carry that many rows behind row n-1, owned by the library
                                         // (padding targets of the V2 slabs)
     unsigned long long *d_stats = nullptr;   // GLB_POISSON_STATS=1: {re-polls, batches that had to poll, max warp cycles, CTAs}
@@ -820,8 +821,11 @@ static const void *dataflow2_fn(const PersistVariant &v, int *threads)
     return (const void *)poisson_dataflow_kernel<LANES, 512, 8, true>;
 }
 
+static thread_local int g_df_force = 0;  // plan_create builds the first-generation plan for comparison on hub-heavy graphs
+
 static int dataflow_version()          // GLB_POISSON_DF=1 keeps the first-generation kernel for A/B runs
 {
+    if (g_df_force) return g_df_force;
     const char *e = getenv("GLB_POISSON_DF");
     return (e && atoi(e) == 1) ? 1 : 2;
 }
@@ -967,6 +971,7 @@ static int plan_try_dataflow(glb_poisson_plan *p, const std::vector<int> &h_rp, 
         for (int r = r0; r < r1; ++r) {
             const int len = h_rp[r + 1] - h_rp[r];
             if (len <= kLongRowDf) continue;
+            p->has_long_rows = true;
             const int m = (len + part_max - 1) / part_max;
             const int chunk = (len + m - 1) / m;
             for (int q = 0; q < m; ++q) {
@@ -1214,7 +1219,23 @@ extern "C" GLB_API int glb_poisson_plan_create(glb_poisson_plan **plan, const in
             cudaFree(trial);
             if (rc) return rc;
             p->gate_every = p->tuned_gate;
+            p->tuned_ms[0] = ms_df;
             tm.lap("gate tuning");
+            // Hub-heavy graphs (rows dealt over whole warps): the first-generation inner loop (16 gathers in flight per lane
+            // group) can beat the predicate-free one (8 in flight).  Build it, tune it, keep the faster plan.
+            if (p->has_long_rows && !g_df_force && !getenv("GLB_POISSON_DF")) {
+                glb_poisson_plan *v1 = nullptr;
+                g_df_force = 1;
+                const int rc1 = glb_poisson_plan_create(&v1, d_rowptr, d_col, d_val, n, nnz, c, GLB_POISSON_KIND_DATAFLOW, stream);
+                g_df_force = 0;
+                if (rc1 == 0) {
+                    if (v1->tuned_ms[0] > 0.f && v1->tuned_ms[0] < ms_df) { std::swap(*p, *v1); ms_df = p->tuned_ms[0]; }
+                    glb_poisson_plan_destroy(v1);
+                } else if (rc1 != GLB_E_UNSUPPORTED) {
+                    return rc1;
+                }
+                tm.lap("first-generation plan + timing");
+            }
         }
         if (kind == GLB_POISSON_KIND_AUTO && p->kind == GLB_POISSON_KIND_DATAFLOW && tune) {
             // ... and the dataflow kernel against the barrier kernel (small graphs: too few rows per SM to hide the
