@@ -107,3 +107,48 @@ def test_knn_data_on_disk_format(tmp_path, monkeypatch):
     assert (W1 != W2).nnz == 0
     with pytest.raises(FileNotFoundError):
         gl.weightmatrix.load_knn_data("absent")
+
+
+def test_reweight_host_methods_against_reference_goldens(moons):
+    """graph.reweight 'wnll' and 'properly' are pure host arithmetic (reference graph.py:436-462): bit-comparable with
+    the goldens of the reference on CPU.  ('poisson' solves a linear system on the GPU: tests/test_cg_gpu.py.)"""
+    from conftest import Golden
+    rw = Golden("reweight")
+    G = gl.graph(moons.csr("W"))
+    ti, X = moons["train_ind"], moons["X"]
+    for tag, kw in (("wnll", {}), ("properly", {"X": X})):
+        Wr = sparse.csr_matrix(G.reweight(ti, method=tag, **kw)); Wr.sort_indices()
+        assert np.array_equal(Wr.indices, rw["W_%s_indices" % tag]) and np.array_equal(Wr.indptr, rw["W_%s_indptr" % tag])
+        assert np.allclose(Wr.data, rw["W_%s_data" % tag], rtol=1e-14, atol=0)
+    with pytest.raises(ValueError):
+        G.reweight(ti, method="nope")
+    with pytest.raises(ValueError):
+        G.reweight(ti, method="properly")
+
+
+def test_ccode_triplets_match_reference_expressions(moons, blobs):
+    """graph.I/J/V: the row-sorted COO triplets of graph.__ccode_init__ (graph.py:69-84); the canonical-CSR shortcut must give
+    the arrays of the literal expressions, also with explicit zeros stored and for a non-canonical matrix."""
+    for W in (moons.csr("W"), moons.csr("Wd"), blobs.csr("W")):
+        G = gl.graph(W)
+        I, J, V = orc.ccode_triplets(W)
+        assert np.array_equal(G.I, I) and np.array_equal(G.J, J) and np.array_equal(G.V, V)
+        assert G.I.dtype == np.int32 and G.J.dtype == np.int32 and G.V.dtype == np.float64
+    W = moons.csr("W").copy()
+    W.data[::7] = 0.0                                            # explicit zeros are dropped by sparse.find
+    G = gl.graph(W)
+    I, J, V = orc.ccode_triplets(W)
+    assert np.array_equal(G.I, I) and np.array_equal(G.J, J) and np.array_equal(G.V, V)
+    Wn = sparse.csr_matrix((np.array([1.0, 2.0, 3.0, 4.0]), np.array([2, 0, 1, 0]), np.array([0, 2, 3, 4])), shape=(3, 3))
+    assert not Wn.has_sorted_indices
+    G = gl.graph(Wn)
+    I, J, V = orc.ccode_triplets(Wn)
+    assert np.array_equal(G.I, I) and np.array_equal(G.J, J) and np.array_equal(G.V, V)
+
+
+def test_clustering_scores():
+    pred = np.array([1, 1, 0, 0, 2, 2, 2])
+    true = np.array([5, 5, 7, 7, 9, 9, 7])
+    assert abs(gl.clustering.clustering_accuracy(pred, true) - 100 * 6 / 7) < 1e-12
+    assert abs(gl.clustering.purity(pred, true) - 100 * 6 / 7) < 1e-12
+    assert gl.clustering.clustering_accuracy(true, true) == 100.0
