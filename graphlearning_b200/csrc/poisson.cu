@@ -329,16 +329,6 @@ __device__ __forceinline__ uint4 ld_chunk(const char *p)
     asm volatile("ld.relaxed.gpu.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
     return v;
 }
-// L1-cached variant for the FIRST attempt of a gather (experiment, GLB_POISSON_NOPOLL bit 3): a chunk is self-validating
-// (16-byte atomic write, epoch inside), so a line served by L1 is either the wanted version or recognisably stale - then
-// the re-poll below fetches it from L2.  With a locality ordering most of a CTA's gathers hit rows another warp of the CTA
-// has just fetched, which takes them off the L2 (the bound of this kernel).
-__device__ __forceinline__ uint4 ld_chunk_l1(const char *p)
-{
-    uint4 v;
-    asm volatile("ld.global.ca.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
-    return v;
-}
 __device__ __forceinline__ void st_chunk(char *p, float a, float b, float c, unsigned w)
 {
     asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(__float_as_uint(a)), "r"(__float_as_uint(b)),
@@ -383,13 +373,8 @@ __device__ __forceinline__ void df_batch(const int2 *cvp, const char *in, unsign
             off[2 * i + 1] = (unsigned)e.z; val[2 * i + 1] = __int_as_float(e.w);
         }
     }
-    if (nopoll & 8) {
 #pragma unroll
-        for (int i = 0; i < N; ++i) x[i] = ld_chunk_l1(df_addr(in, off[i]));
-    } else {
-#pragma unroll
-        for (int i = 0; i < N; ++i) x[i] = ld_chunk(df_addr(in, off[i]));
-    }
+    for (int i = 0; i < N; ++i) x[i] = ld_chunk(df_addr(in, off[i]));
     bool ok = true;
 #pragma unroll
     for (int i = 0; i < N; ++i) ok &= x[i].w >= expect;
