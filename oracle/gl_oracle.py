@@ -420,6 +420,84 @@ def lip_iterate(u, I, J, W, ind, val, T, tol, alpha, beta):
     return u, sweeps
 
 
+# ---------------------------------------------------------------------------------------------------
+# spectral decomposition, reweighting  (rows added with the spectral / p-Laplace kernels)
+# ---------------------------------------------------------------------------------------------------
+def eigen_decomp(W, normalization="combinatorial", k=10, tol=0):
+    """graph.eigen_decomp, method='exact', gamma=0.  graphlearning/graph.py:728-765: ARPACK svds of the shifted /
+    normalised matrix, vals = shift - s sorted ascending, random-walk vectors rescaled by D^-1/2."""
+    from scipy.sparse import linalg as splinalg
+    W = sparse.csr_matrix(W)
+    n = W.shape[0]
+    if normalization in ("randomwalk", "normalized"):
+        D = degree_matrix(W, p=-0.5)
+        A = D * W * D
+        u, s, vt = splinalg.svds(A, k=k, tol=tol)
+        vals = 1 - s
+        ind = np.argsort(vals)
+        vals, vecs = vals[ind], u[:, ind]
+        if normalization == "randomwalk":
+            vecs = D @ vecs
+        return vals, vecs
+    if normalization == "combinatorial":
+        L = laplacian(W)
+        M = 2 * np.max(degree_vector(W))
+        A = M * sparse.identity(n) - L
+        u, s, vt = splinalg.svds(A, k=k, tol=tol)
+        vals = M - s
+        ind = np.argsort(vals)
+        return vals[ind], u[:, ind]
+    raise ValueError("Invalid choice of normalization")
+
+
+def poisson_spectral(W, train_ind, train_labels, spectral_cutoff=10, p=1):
+    """ssl.poisson._fit, solver='spectral'.  graphlearning/ssl.py:615-617, 680-688."""
+    W = sparse.csr_matrix(W)
+    n = W.shape[0]
+    source, k = poisson_source(n, train_ind, train_labels)
+    W0 = sparse.csr_matrix(W - sparse.spdiags(W.diagonal(), 0, n, n))
+    vals, vecs = eigen_decomp(W0, normalization="randomwalk", k=spectral_cutoff + 1)
+    V, vals = vecs[:, 1:], vals[1:]
+    if p != 1:
+        vals = vals ** p
+    L = sparse.spdiags(1 / vals, 0, spectral_cutoff, spectral_cutoff)
+    return V @ (L @ (V.T @ source))
+
+
+def reweight(W, idx, method="poisson", normalization="combinatorial", X=None, alpha=2, zeta=1e7, r=0.1):
+    """graph.reweight.  graphlearning/graph.py:412-462."""
+    from scipy import spatial
+    W = sparse.csr_matrix(W)
+    n = W.shape[0]
+    if method == "poisson":
+        f = np.zeros(n)
+        f[idx] = 1
+        if normalization == "combinatorial":
+            f -= np.mean(f)
+            L = laplacian(W)
+        else:
+            d = degree_vector(W) ** 0.5
+            f -= np.sum(d * f) / np.sum(d)
+            L = laplacian(W, normalization=normalization)
+        w = conjgrad(L, f, tol=1e-5)
+        w -= np.min(w)
+        w += 1e-5
+        D = sparse.spdiags(w, 0, n, n).tocsr()
+        return D * W * D
+    if method == "wnll":
+        a = np.ones((n,))
+        a[idx] = n / len(idx)
+        D = sparse.spdiags(a, 0, n, n).tocsr()
+        return D * W + W * D
+    if method == "properly":
+        rzeta = r / (zeta - 1) ** (1 / alpha)
+        Dn, _ = spatial.cKDTree(X[idx, :]).query(X)
+        Dn[Dn < rzeta] = rzeta
+        D = sparse.spdiags(1 + (r / Dn) ** alpha, 0, n, n).tocsr()
+        return D * W + W * D
+    raise ValueError("Invalid reweighting method")
+
+
 # ----------------------------------------------------------------------------
 # synthetic workloads (SURVEY.md 8d) - shared by tests and bench so that both arms
 # of every comparison see identical inputs.
