@@ -310,6 +310,36 @@ class plaplace(ssl):
                                    tol=self.tol, fast=True)
 
 
+class randomwalk(ssl):
+    """Lazy random walk classification.  Reference graphlearning/ssl.py:1731-1793: one Jacobi-scaled multi-column CG
+    solve of ((1 - alpha) I + alpha L_normalized) u = Y, on the GPU (cg.cu) through utils.conjgrad."""
+
+    def __init__(self, W=None, class_priors=None, alpha=0.95):
+        super().__init__(W, class_priors)
+        self.alpha = alpha
+        self.accuracy_filename = "_randomwalk"
+        self.name = "Lazy Random Walks"
+        self.iterations = None
+        self.gpu_launches = 0
+
+    def _fit(self, train_ind, train_labels, all_labels=None):
+        alpha = self.alpha
+        n = self.graph.num_nodes
+        W = self.graph.weight_matrix
+        W = W - sparse.spdiags(W.diagonal(), 0, n, n)
+        G = graph.graph(W)
+        L = (1 - alpha) * sparse.identity(n) + alpha * G.laplacian(normalization="normalized")
+        m = L.shape[0]
+        M = sparse.spdiags(1 / np.sqrt(L.diagonal() + 1e-10), 0, m, m).tocsr()
+        k = len(np.unique(train_labels))
+        onehot = utils.labels_to_onehot(train_labels, k)
+        Y = np.zeros((n, onehot.shape[1]))
+        Y[train_ind, :] = onehot
+        u, (it, err, nl) = utils.conjgrad(M * L * M, M * Y, tol=1e-6, return_info=True)
+        self.iterations, self.gpu_launches = it, nl
+        return M * u
+
+
 def ssl_accuracy(pred_labels, true_labels, train_ind):
     """Accuracy over the unlabelled points, in percent.  Reference graphlearning/ssl.py:1795-1834."""
     pred_labels = np.asarray(pred_labels)

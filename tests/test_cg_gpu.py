@@ -158,3 +158,15 @@ def test_reweight_and_reweighted_laplace_goldens(gl, moons):
         assert rel_err(u, rw["u_laplace_" + name]) <= (1e-3 if name == "poisson" else 1e-5)
         assert np.mean(m.predict() == rw["p_laplace_" + name]) > 0.995
         assert name in m.accuracy_filename
+
+
+def test_randomwalk_golden(gl, moons, blobs):
+    """ssl.randomwalk (reference ssl.py:1731-1793): one Jacobi-scaled CG solve of ((1-alpha) I + alpha L_norm) u = Y on the GPU."""
+    from conftest import Golden
+    rwk = Golden("randomwalk")
+    for name, g, tkey in (("moons", moons, "train_ind"), ("blobs", blobs, "train_ind5")):
+        ti, labels = g[tkey], g["labels"]
+        m = gl.ssl.randomwalk(g.csr("W"))
+        u = m.fit(ti, labels[ti])
+        assert rel_err(u, rwk[name + "_u"]) <= 1e-5 and m.gpu_launches > 0
+        assert np.mean(m.predict() == rwk[name + "_pred"]) > 0.999

@@ -152,3 +152,23 @@ def test_clustering_scores():
     assert abs(gl.clustering.clustering_accuracy(pred, true) - 100 * 6 / 7) < 1e-12
     assert abs(gl.clustering.purity(pred, true) - 100 * 6 / 7) < 1e-12
     assert gl.clustering.clustering_accuracy(true, true) == 100.0
+
+
+def test_randomwalk_host_composition(moons, blobs, monkeypatch):
+    """ssl.randomwalk (reference ssl.py:1731-1793) = scipy assembly + ONE call of utils.conjgrad.  On CPU the solver call is
+    replaced by the oracle's CG (the device solver has its own parity tests), which pins everything around it to the golden
+    of the reference."""
+    from conftest import Golden, rel_err
+    rwk = Golden("randomwalk")
+
+    def cpu_conjgrad(A, b, x0=None, max_iter=1e5, tol=1e-10, return_info=False):
+        x, it = orc.conjgrad(A, b, x0=x0, max_iter=max_iter, tol=tol, return_iters=True)
+        return (x, (it, 0.0, 0)) if return_info else x
+
+    monkeypatch.setattr(gl.utils, "conjgrad", cpu_conjgrad)
+    for name, g, tkey in (("moons", moons, "train_ind"), ("blobs", blobs, "train_ind5")):
+        ti, labels = g[tkey], g["labels"]
+        m = gl.ssl.randomwalk(g.csr("W"))
+        u = m.fit(ti, labels[ti])
+        assert rel_err(u, rwk[name + "_u"]) < 1e-12 and np.array_equal(m.predict(), rwk[name + "_pred"])
+        assert m.accuracy_filename == "_randomwalk" and m.iterations > 0
