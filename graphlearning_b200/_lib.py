@@ -9,7 +9,8 @@ import os
 from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libglb200.so")
+# GLB200_LIB: another build of the same library (tools/ use lib/libglb200_exp.so, the -DGLB_EXPERIMENT build)
+LIB_PATH = os.environ.get("GLB200_LIB") or os.path.join(HERE, "lib", "libglb200.so")
 
 _lib = None
 

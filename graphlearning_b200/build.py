@@ -1,9 +1,13 @@
 """Build libglb200.so (the sm_100a CUDA kernels + C-ABI) in-tree with nvcc.
 
-    python -m graphlearning_b200.build [--force] [--verbose]
+    python -m graphlearning_b200.build [--force] [--verbose] [--exp]
 
 The library lands in graphlearning_b200/lib/libglb200.so (git-ignored, but it travels to the GPU box
 with the gpurun snapshot).  nvcc cross-compiles without a GPU.
+
+--exp builds lib/libglb200_exp.so with -DGLB_EXPERIMENT: the same sources with the experiment switches
+(GLB_POISSON_* environment variables, read once per plan) compiled in.  Only tools/ load it (GLB200_LIB=...);
+the product library has no environment lookups.
 """
 from __future__ import annotations
 
@@ -36,22 +40,28 @@ def _deps_mtime():
     return m
 
 
-def needs_build():
-    return not os.path.exists(LIB) or os.path.getmtime(LIB) < _deps_mtime()
+LIB_EXP = os.path.join(LIBDIR, "libglb200_exp.so")
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
-        return LIB
+def needs_build(lib=LIB):
+    return not os.path.exists(lib) or os.path.getmtime(lib) < _deps_mtime()
+
+
+def build(force=False, verbose=False, exp=False):
+    lib = LIB_EXP if exp else LIB
+    objdir = OBJDIR + ("_exp" if exp else "")
+    extra = ["-DGLB_EXPERIMENT"] if exp else []
+    if not force and not needs_build(lib):
+        return lib
     os.makedirs(LIBDIR, exist_ok=True)
-    os.makedirs(OBJDIR, exist_ok=True)
+    os.makedirs(objdir, exist_ok=True)
     dep_m = _deps_mtime()
 
     def compile_one(src):
-        obj = os.path.join(OBJDIR, os.path.basename(src)[:-3] + ".o")
+        obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
         if not force and os.path.exists(obj) and os.path.getmtime(obj) >= dep_m:
             return obj, ""
-        cmd = [NVCC] + ARCH_FLAGS + CFLAGS + ["-c", src, "-o", obj]
+        cmd = [NVCC] + ARCH_FLAGS + CFLAGS + extra + ["-c", src, "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (src, r.stdout, r.stderr))
@@ -63,15 +73,15 @@ def build(force=False, verbose=False):
     if verbose:
         for _, log in results:
             sys.stderr.write(log)
-    with open(os.path.join(OBJDIR, "ptxas.log"), "w") as f:
+    with open(os.path.join(objdir, "ptxas.log"), "w") as f:
         for _, log in results:
             f.write(log)
-    cmd = [NVCC] + ARCH_FLAGS + ["-shared", "-o", LIB] + objs + ["-Xlinker", "--exclude-libs,ALL"]
+    cmd = [NVCC] + ARCH_FLAGS + ["-shared", "-o", lib] + objs + ["-Xlinker", "--exclude-libs,ALL"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, exp="--exp" in sys.argv))

@@ -319,14 +319,25 @@ poisson_persistent_kernel(const int *__restrict__ rowptr, const int *__restrict_
 // group in every iteration and a lane group finishes iteration t before it starts t + 1, so the chain holds
 // chunk by chunk without any fence.  Progress: the unfinished work item with the smallest iteration number
 // always has all its inputs, all CTAs are co-resident (cooperative launch), so no wait cycle can form.
-constexpr unsigned kPadOff = 0xFFFFFFFFu;        // (offset) of a padding entry of the sliced-ELL slab (first generation)
-constexpr int kScratchRows = 256;                // second generation: rows n .. n+255 of the label matrices are padding targets
+constexpr int kScratchRows = 256;                // rows n .. n+255 of the label matrices are the padding targets of the slabs
 constexpr int kRowSrcBit = 0x40000000;           // slot_rows: row has a nonzero source term Db
+constexpr int kRing = 4;                         // versions of the label matrix in flight: version v lives in buffer v % kRing
 
-__device__ __forceinline__ uint4 ld_chunk(const char *p)
+__device__ __forceinline__ uint4 ld_chunk(const char *p)          // coherent at L2 (L1 bypassed)
 {
     uint4 v;
     asm volatile("ld.relaxed.gpu.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
+// First attempt of a gather: a weak load that may be served by this SM's L1.  Chunks are self-validating (epoch word), so
+// a stale line is harmless: the lane re-polls it at L2.  With kRing = 4 buffers the copy of a line that L1 may still hold
+// is four iterations old, i.e. evicted long ago by the ~180 KB of label rows every iteration streams through L1, so in
+// practice a first attempt either hits a line another warp of this CTA fetched in THIS iteration (under a locality
+// ordering a CTA gathers every distinct row ~2.4 times per iteration) or misses and is filled from L2.
+__device__ __forceinline__ uint4 ld_chunk_l1(const char *p)
+{
+    uint4 v;
+    asm volatile("ld.global.ca.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
     return v;
 }
 __device__ __forceinline__ void st_chunk(char *p, float a, float b, float c, unsigned w)
@@ -342,12 +353,12 @@ __device__ __forceinline__ void st_chunk(char *p, float a, float b, float c, uns
 constexpr int kSlotNormal = 0, kSlotLong = 1, kSlotPart = 2, kSlotOwner = 3;
 constexpr int kLongRowDf = 32;                   // rows with more nonzeros get a warp (or several) of their own
 
-// Inner loop of the second-generation slab format (V2): no per-entry predicates at all.  Entries of a lane group are
-// stored in PAIRS (one LDS.128 = two (offset,value) entries, 8 lane groups side by side = one 128-byte wavefront),
-// padding entries point at the scratch row n of the label matrix (value 0, epoch 0xffffffff: always "ready"), the
-// epoch test is `>=` (a chunk only ever holds version t-2 or t of its row, see the two-buffer argument above), the
-// address is one IMAD.WIDE (64-bit base + 32-bit byte offset), and a slice of width L is walked as 16-entry batches plus
-// 8/4/2/1 tails selected by the bits of L (warp-uniform), so exactly L gathers are issued per row.
+// Inner loop: no per-entry predicates at all.  Entries of a lane group are stored in PAIRS (one LDS.128 = two
+// (offset,value) entries, 8 lane groups side by side = one 128-byte wavefront), padding entries point at the scratch
+// rows behind row n-1 of the label matrix (value 0, epoch 0xffffffff: always "ready"), the epoch test is `>=` (a chunk
+// of buffer t % kRing only ever holds a version congruent to t and never a later one than t, see the argument above),
+// the address is one IMAD.WIDE (64-bit base + 32-bit byte offset), and a slice of width L is walked as U-entry batches
+// plus 4/2/1 tails selected by the bits of L (warp-uniform), so exactly L gathers are issued per row.
 __device__ __forceinline__ const char *df_addr(const char *base, unsigned off)
 {
     unsigned long long a;
@@ -355,8 +366,8 @@ __device__ __forceinline__ const char *df_addr(const char *base, unsigned off)
     return reinterpret_cast<const char *>(a);
 }
 
-template <int N, int RPW>
-__device__ __forceinline__ void df_batch(const int2 *cvp, const char *in, unsigned expect, int nopoll, float &a0, float &a1,
+template <int N, int RPW, bool L1F>
+__device__ __forceinline__ void df_batch(const int2 *cvp, const char *in, unsigned expect, float &a0, float &a1,
                                          float &a2, unsigned long long &n_poll, unsigned long long &n_badbatch, unsigned *watchdog)
 {
     unsigned off[N];
@@ -374,13 +385,13 @@ __device__ __forceinline__ void df_batch(const int2 *cvp, const char *in, unsign
         }
     }
 #pragma unroll
-    for (int i = 0; i < N; ++i) x[i] = ld_chunk(df_addr(in, off[i]));
+    for (int i = 0; i < N; ++i) x[i] = L1F ? ld_chunk_l1(df_addr(in, off[i])) : ld_chunk(df_addr(in, off[i]));
     bool ok = true;
 #pragma unroll
     for (int i = 0; i < N; ++i) ok &= x[i].w >= expect;
     unsigned spins = 0;
     long long t0 = 0;
-    while (!ok && !(nopoll & 1)) {                       // some producer is still behind: re-poll the stale chunks together
+    while (!ok) {                                        // some producer is still behind (or L1 held an old line): re-poll at L2
         ++n_badbatch;
         if (poll_expired(watchdog, spins, t0)) break;
 #pragma unroll
@@ -398,12 +409,14 @@ __device__ __forceinline__ void df_batch(const int2 *cvp, const char *in, unsign
     }
 }
 
-template <int LANES, int THREADS, int U, bool V2>
+struct DfRing { float *b[kRing]; };              // version v of the label matrix lives in b[v % kRing]
+
+template <int LANES, int THREADS, int U, bool L1F>
 __global__ void __launch_bounds__(THREADS, 1)
 poisson_dataflow_kernel(const int2 *__restrict__ slabs, const long long *__restrict__ slab_off,
                         const int4 *__restrict__ slots, const int *__restrict__ slot_off,
-                        const int *__restrict__ slot_rows, const float *__restrict__ Db, float *u0, float *u1, int T,
-                        int cap_entries, int cap_slots, int cap_parts, unsigned long long *stats, int nopoll,
+                        const int *__restrict__ slot_rows, const float *__restrict__ Db, DfRing ring, int T,
+                        int cap_entries, int cap_slots, int cap_parts, unsigned long long *stats,
                         unsigned *start_gate, int gate_every, unsigned *watchdog)
 {
     constexpr int RPW = 32 / LANES;              // rows per warp pass = slice height of the ELL slab
@@ -452,7 +465,7 @@ poisson_dataflow_kernel(const int2 *__restrict__ slabs, const long long *__restr
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane / LANES, li = lane % LANES;
-    unsigned long long n_poll = 0, n_badbatch = 0;      // stats only (GLB_POISSON_STATS)
+    unsigned long long n_poll = 0, n_badbatch = 0;      // stats only (GLB_POISSON_STATS in -DGLB_EXPERIMENT builds)
     const long long clk0 = clock64();
     for (int t = 0; t < T; ++t) {
         // Re-alignment gate every gate_every iterations: the low-polling regime is metastable (a CTA that falls behind
@@ -469,61 +482,210 @@ poisson_dataflow_kernel(const int2 *__restrict__ slabs, const long long *__restr
             }
             __syncthreads();
         }
-        const char *in = reinterpret_cast<const char *>(((t & 1) && !(nopoll & 4)) ? u1 : u0) + li * 16;
-        char *out = reinterpret_cast<char *>(((t & 1) && !(nopoll & 4)) ? u0 : u1) + li * 16;
+        const int vi = t & (kRing - 1), vo = (t + 1) & (kRing - 1);
+        const char *in = reinterpret_cast<const char *>(vi == 0 ? ring.b[0] : vi == 1 ? ring.b[1] : vi == 2 ? ring.b[2] : ring.b[3]) + li * 16;
+        char *out = reinterpret_cast<char *>(vo == 0 ? ring.b[0] : vo == 1 ? ring.b[1] : vo == 2 ? ring.b[2] : ring.b[3]) + li * 16;
         const unsigned expect = 1u + (unsigned)t;
         for (int s = warp; s < nslots; s += NW) {            // slot k of warp w is stored at k * NW + w
             const int4 sl = s_slot[s];                       // (first entry, slice width, type | parts << 8, partial index)
             const int L = sl.y;
             float a0 = 0.f, a1 = 0.f, a2 = 0.f;
-            if constexpr (V2) {
-                const int2 *cv = s_cv + sl.x + g * 2;        // pair q of this lane group: 16 bytes at cv[q * 2 * RPW]
-                int j = 0;
-                for (; j + U <= L; j += U) df_batch<U, RPW>(cv + j * RPW, in, expect, nopoll, a0, a1, a2, n_poll, n_badbatch, watchdog);
-                if (U > 8 && (L & 8)) { df_batch<8, RPW>(cv + j * RPW, in, expect, nopoll, a0, a1, a2, n_poll, n_badbatch, watchdog); j += 8; }
-                if (L & 4) { df_batch<4, RPW>(cv + j * RPW, in, expect, nopoll, a0, a1, a2, n_poll, n_badbatch, watchdog); j += 4; }
-                if (L & 2) { df_batch<2, RPW>(cv + j * RPW, in, expect, nopoll, a0, a1, a2, n_poll, n_badbatch, watchdog); j += 2; }
-                if (L & 1) df_batch<1, RPW>(cv + j * RPW, in, expect, nopoll, a0, a1, a2, n_poll, n_badbatch, watchdog);
-            } else {
-            const int2 *cv = s_cv + sl.x + g;                // entry j of this lane group: cv[j * RPW]
-            for (int j0 = 0; j0 < L; j0 += U) {
-                unsigned off[U];
-                float val[U];
-                uint4 x[U];
+            const int2 *cv = s_cv + sl.x + g * 2;            // pair q of this lane group: 16 bytes at cv[q * 2 * RPW]
+            int j = 0;
+            for (; j + U <= L; j += U) df_batch<U, RPW, L1F>(cv + j * RPW, in, expect, a0, a1, a2, n_poll, n_badbatch, watchdog);
+            if (U > 8 && (L & 8)) { df_batch<8, RPW, L1F>(cv + j * RPW, in, expect, a0, a1, a2, n_poll, n_badbatch, watchdog); j += 8; }
+            if (L & 4) { df_batch<4, RPW, L1F>(cv + j * RPW, in, expect, a0, a1, a2, n_poll, n_badbatch, watchdog); j += 4; }
+            if (L & 2) { df_batch<2, RPW, L1F>(cv + j * RPW, in, expect, a0, a1, a2, n_poll, n_badbatch, watchdog); j += 2; }
+            if (L & 1) df_batch<1, RPW, L1F>(cv + j * RPW, in, expect, a0, a1, a2, n_poll, n_badbatch, watchdog);
+            const int type = sl.z & 0xff;
+            if (type != kSlotNormal) {                       // warp-uniform: one long row dealt over the lane groups
 #pragma unroll
-                for (int i = 0; i < U; ++i) {
-                    int2 e = make_int2((int)kPadOff, 0);
-                    if (j0 + i < L) e = cv[(j0 + i) * RPW];
-                    off[i] = (unsigned)e.x;
-                    val[i] = __int_as_float(e.y);
+                for (int o = LANES; o < 32; o <<= 1) {
+                    a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+                    a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+                    a2 += __shfl_xor_sync(0xffffffffu, a2, o);
                 }
-#pragma unroll
-                for (int i = 0; i < U; ++i) {
-                    x[i] = make_uint4(0u, 0u, 0u, expect);
-                    if (off[i] != kPadOff) x[i] = ld_chunk(in + off[i]);
+                if (type == kSlotPart) {
+                    if (g == 0) {
+                        volatile float *pb = s_part + ((size_t)(sl.w * 2 + (t & 1)) * LANES + li) * 4;
+                        pb[0] = a0; pb[1] = a1; pb[2] = a2;
+                        __threadfence_block();
+                        pb[3] = __uint_as_float(expect + 1u);
+                    }
+                    continue;
                 }
-                unsigned bad = 0;
-#pragma unroll
-                for (int i = 0; i < U; ++i) bad |= x[i].w ^ expect;
-                unsigned spins = 0;
-                long long tw0 = 0;
-                while (bad && !(nopoll & 1)) {               // some producer is still behind: re-poll the stale chunks together
-                    ++n_badbatch;
-                    if (poll_expired(watchdog, spins, tw0)) break;
-#pragma unroll
-                    for (int i = 0; i < U; ++i)
-                        if (x[i].w != expect) { x[i] = ld_chunk(in + off[i]); ++n_poll; }
-                    bad = 0;
-#pragma unroll
-                    for (int i = 0; i < U; ++i) bad |= x[i].w ^ expect;
-                }
-#pragma unroll
-                for (int i = 0; i < U; ++i) {
-                    a0 = fmaf(val[i], __uint_as_float(x[i].x), a0);
-                    a1 = fmaf(val[i], __uint_as_float(x[i].y), a1);
-                    a2 = fmaf(val[i], __uint_as_float(x[i].z), a2);
+                if (type == kSlotOwner) {
+                    const int nparts = sl.z >> 8;
+                    for (int q = 0; q < nparts; ++q) {       // partial sums of the other warps, fixed order
+                        volatile float *pb = s_part + ((size_t)((sl.w + q) * 2 + (t & 1)) * LANES + li) * 4;
+                        unsigned spins = 0;
+                        long long tw0 = 0;
+                        while (__float_as_uint(pb[3]) != expect + 1u && !poll_expired(watchdog, spins, tw0)) { }
+                        __threadfence_block();
+                        a0 += pb[0]; a1 += pb[1]; a2 += pb[2];
+                    }
                 }
             }
+            const int rinfo = s_rows[s * RPW + g];
+            if (rinfo >= 0) {
+                const unsigned row = (unsigned)(rinfo & (kRowSrcBit - 1));
+                if (rinfo & kRowSrcBit) {
+                    const float4 b = __ldg(reinterpret_cast<const float4 *>(Db + (size_t)row * (ROWB / 4)) + li);
+                    a0 += b.x; a1 += b.y; a2 += b.z;
+                }
+                st_chunk(out + (size_t)row * ROWB, a0, a1, a2, expect + 1u);
+            }
+        }
+    }
+    if (stats) {
+        atomicAdd(stats + 0, n_poll);
+        atomicAdd(stats + 1, n_badbatch);
+        if (lane == 0) atomicMax(stats + 2, (unsigned long long)(clock64() - clk0));
+        if (threadIdx.x == 0) atomicAdd(stats + 3, 1ull);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3p: the same dataflow iterate with a software-pipelined gather stream
+// ------------------------------------------------------------------------------------------------
+// What bounds the batch kernel above (ncu, r1): one warp has ONE batch of gathers in flight, waits for it (an L2 round
+// trip of ~500-1000 cycles under load), consumes it, and only then issues the next - 11 serialised round trips plus ~740
+// dependent instructions per warp and iteration with 4 warps per scheduler; the LSU pipe idles a third of the time.
+// Here every warp walks ONE contiguous stream of "octets" (8 entries per lane group, 512 bytes, all slots of the warp
+// back to back, slice widths padded to a multiple of 8 with always-ready scratch-row entries) with two register sets of
+// four gathers: while set A is validated and consumed set B is in flight and vice versa, across slot boundaries, so 4-8
+// gathers per lane are outstanding all the time and the instruction stream overlaps the memory latency.
+template <int RPW, bool L1F>
+__device__ __forceinline__ void dfp_issue(const int4 *cv, const char *in, float (&val)[4], uint4 (&x)[4])
+{
+    const int4 e0 = cv[0], e1 = cv[RPW];                      // two pairs = four (offset, value) entries of this lane group
+    val[0] = __int_as_float(e0.y); val[1] = __int_as_float(e0.w);
+    val[2] = __int_as_float(e1.y); val[3] = __int_as_float(e1.w);
+    const unsigned off[4] = {(unsigned)e0.x, (unsigned)e0.z, (unsigned)e1.x, (unsigned)e1.z};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) x[i] = L1F ? ld_chunk_l1(df_addr(in, off[i])) : ld_chunk(df_addr(in, off[i]));
+}
+
+// cv: where dfp_issue read the entries of this set (the offsets are re-read from shared memory on the rare re-poll path
+// instead of being held in registers)
+template <int RPW>
+__device__ __forceinline__ void dfp_consume(const int4 *cv, const char *in, unsigned expect, const float (&val)[4],
+                                            uint4 (&x)[4], float &a0, float &a1, float &a2, unsigned &n_poll,
+                                            unsigned &n_badbatch, unsigned *watchdog)
+{
+    bool ok = (x[0].w >= expect) & (x[1].w >= expect) & (x[2].w >= expect) & (x[3].w >= expect);
+    if (!ok) {                                           // a producer is still behind (or L1 held an old line): re-poll at L2
+        const int4 e0 = cv[0], e1 = cv[RPW];
+        const unsigned off[4] = {(unsigned)e0.x, (unsigned)e0.z, (unsigned)e1.x, (unsigned)e1.z};
+        unsigned spins = 0;
+        long long t0 = 0;
+        do {
+            ++n_badbatch;
+            if (poll_expired(watchdog, spins, t0)) break;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (x[i].w < expect) { x[i] = ld_chunk(df_addr(in, off[i])); ++n_poll; }
+            ok = (x[0].w >= expect) & (x[1].w >= expect) & (x[2].w >= expect) & (x[3].w >= expect);
+        } while (!ok);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        a0 = fmaf(val[i], __uint_as_float(x[i].x), a0);
+        a1 = fmaf(val[i], __uint_as_float(x[i].y), a1);
+        a2 = fmaf(val[i], __uint_as_float(x[i].z), a2);
+    }
+}
+
+template <int LANES, int THREADS, bool L1F>
+__global__ void __launch_bounds__(THREADS, 1)
+poisson_dataflow_pipe_kernel(const int2 *__restrict__ slabs, const long long *__restrict__ slab_off,
+                             const int4 *__restrict__ slots, const int *__restrict__ slot_off,
+                             const int *__restrict__ slot_rows, const float *__restrict__ Db, DfRing ring, int T,
+                             int cap_entries, int cap_slots, int cap_parts, unsigned long long *stats,
+                             unsigned *start_gate, int gate_every, unsigned *watchdog)
+{
+    constexpr int RPW = 32 / LANES;
+    constexpr int NW = THREADS / 32;
+    constexpr unsigned ROWB = LANES * 16;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    int2 *s_cv = reinterpret_cast<int2 *>(smem_raw);
+    int4 *s_slot = reinterpret_cast<int4 *>(s_cv + cap_entries);
+    volatile float *s_part = reinterpret_cast<volatile float *>(s_slot + cap_slots);     // [cap_parts][2][LANES][4]
+    int *s_rows = reinterpret_cast<int *>(const_cast<float *>(s_part) + (size_t)cap_parts * 2 * LANES * 4);
+
+    const long long e0 = slab_off[blockIdx.x];
+    const int nent = (int)(slab_off[blockIdx.x + 1] - e0);
+    const int sl0 = slot_off[blockIdx.x];
+    const int nslots = slot_off[blockIdx.x + 1] - sl0;
+    for (int i = threadIdx.x; i < nent; i += THREADS) s_cv[i] = slabs[e0 + i];
+    for (int i = threadIdx.x; i < nslots; i += THREADS) s_slot[i] = slots[sl0 + i];
+    for (int i = threadIdx.x; i < cap_parts * 2 * LANES * 4; i += THREADS) s_part[i] = 0.f;
+    for (int i = threadIdx.x; i < nslots * RPW; i += THREADS) {          // which rows have a source term (see the batch kernel)
+        int r = slot_rows[(size_t)sl0 * RPW + i];
+        if (r >= 0) {
+            bool nz = false;
+            const float4 *b = reinterpret_cast<const float4 *>(Db + (size_t)r * (ROWB / 4));
+            for (int q = 0; q < LANES; ++q) {
+                const float4 v = __ldg(b + q);
+                nz |= (v.x != 0.f) | (v.y != 0.f) | (v.z != 0.f);
+            }
+            if (nz) r |= kRowSrcBit;
+        }
+        s_rows[i] = r;
+    }
+    __syncthreads();
+    if (start_gate) {                                                    // all CTAs enter iteration 0 together
+        if (threadIdx.x == 0) {
+            red_relaxed_add(start_gate, 1u);
+            unsigned spins = 0;
+            long long t0 = 0;
+            while (ld_relaxed(start_gate) < gridDim.x && !poll_expired(watchdog, spins, t0)) { }
+        }
+        __syncthreads();
+    }
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane / LANES, li = lane % LANES;
+    const int nsw = (nslots - warp + NW - 1) / NW;                       // slots of this warp: k * NW + warp
+    int n_oct = 0;                                                       // octets of this warp's stream
+    for (int k = 0; k < nsw; ++k) n_oct += (s_slot[k * NW + warp].y + 7) >> 3;
+    const int4 *stream = nsw > 0 ? reinterpret_cast<const int4 *>(s_cv + s_slot[warp].x) + g : nullptr;
+    unsigned n_poll = 0, n_badbatch = 0;
+    const long long clk0 = clock64();
+    for (int t = 0; t < T; ++t) {
+        if (start_gate && gate_every > 0 && t > 0 && t % gate_every == 0) {      // re-alignment gate (see the batch kernel)
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                red_relaxed_add(start_gate, 1u);
+                const unsigned want = gridDim.x * (unsigned)(t / gate_every + 1);
+                unsigned spins = 0;
+                long long t0 = 0;
+                while (ld_relaxed(start_gate) < want && !poll_expired(watchdog, spins, t0)) { }
+            }
+            __syncthreads();
+        }
+        if (n_oct == 0) continue;
+        const int vi = t & (kRing - 1), vo = (t + 1) & (kRing - 1);
+        const char *in = reinterpret_cast<const char *>(vi == 0 ? ring.b[0] : vi == 1 ? ring.b[1] : vi == 2 ? ring.b[2] : ring.b[3]) + li * 16;
+        char *out = reinterpret_cast<char *>(vo == 0 ? ring.b[0] : vo == 1 ? ring.b[1] : vo == 2 ? ring.b[2] : ring.b[3]) + li * 16;
+        const unsigned expect = 1u + (unsigned)t;
+        float valA[4], valB[4];
+        uint4 xA[4], xB[4];
+        const int4 *cv = stream;
+        int left = n_oct;                                    // octets not yet issued (set A)
+        dfp_issue<RPW, L1F>(cv, in, valA, xA);
+        --left;
+        for (int k = 0; k < nsw; ++k) {
+            const int s = k * NW + warp;
+            const int4 sl = s_slot[s];                       // (first entry, slice width, type | parts << 8, partial index)
+            const int no = (sl.y + 7) >> 3;
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+            for (int i = 0; i < no; ++i) {
+                dfp_issue<RPW, L1F>(cv + 2 * RPW, in, valB, xB);
+                dfp_consume<RPW>(cv, in, expect, valA, xA, a0, a1, a2, n_poll, n_badbatch, watchdog);
+                cv += 4 * RPW;
+                if (left > 0) { dfp_issue<RPW, L1F>(cv, in, valA, xA); --left; }
+                dfp_consume<RPW>(cv - 2 * RPW, in, expect, valB, xB, a0, a1, a2, n_poll, n_badbatch, watchdog);
             }
             const int type = sl.z & 0xff;
             if (type != kSlotNormal) {                       // warp-uniform: one long row dealt over the lane groups
@@ -548,7 +710,7 @@ poisson_dataflow_kernel(const int2 *__restrict__ slabs, const long long *__restr
                         volatile float *pb = s_part + ((size_t)((sl.w + q) * 2 + (t & 1)) * LANES + li) * 4;
                         unsigned spins = 0;
                         long long tw0 = 0;
-                        while (__float_as_uint(pb[3]) != expect + 1u && !(nopoll & 1) && !poll_expired(watchdog, spins, tw0)) { }
+                        while (__float_as_uint(pb[3]) != expect + 1u && !poll_expired(watchdog, spins, tw0)) { }
                         __threadfence_block();
                         a0 += pb[0]; a1 += pb[1]; a2 += pb[2];
                     }
@@ -561,29 +723,31 @@ poisson_dataflow_kernel(const int2 *__restrict__ slabs, const long long *__restr
                     const float4 b = __ldg(reinterpret_cast<const float4 *>(Db + (size_t)row * (ROWB / 4)) + li);
                     a0 += b.x; a1 += b.y; a2 += b.z;
                 }
-                if (!(nopoll & 2) || a0 == 123.456f) st_chunk(out + (size_t)row * ROWB, a0, a1, a2, expect + 1u);
+                st_chunk(out + (size_t)row * ROWB, a0, a1, a2, expect + 1u);
             }
         }
     }
     if (stats) {
-        atomicAdd(stats + 0, n_poll);
-        atomicAdd(stats + 1, n_badbatch);
+        atomicAdd(stats + 0, (unsigned long long)n_poll);
+        atomicAdd(stats + 1, (unsigned long long)n_badbatch);
         if (lane == 0) atomicMax(stats + 2, (unsigned long long)(clock64() - clk0));
         if (threadIdx.x == 0) atomicAdd(stats + 3, 1ull);
     }
 }
 
-// epoch words of the two buffers before a launch: version 0 in u0 (word 1), nothing valid in u1 (word 0)
-// chunks nchunks .. nchunks + nscratch - 1 (the scratch row n, if the plan has one): value 0, epoch 0xffffffff in both
-__global__ void __launch_bounds__(256) stamp_kernel(float *u0, float *u1, long long nchunks, int nscratch)
+// epoch words of the ring before a launch: version 0 in buffer 0 (word 1), nothing valid in the others (word 0: whatever
+// an earlier launch left there must not pass for a version of this one)
+// chunks nchunks .. nchunks + nscratch - 1 (the scratch rows): value 0, epoch 0xffffffff in every buffer
+__global__ void __launch_bounds__(256) stamp_kernel(DfRing ring, long long nchunks, int nscratch)
 {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nchunks + nscratch; i += (long long)gridDim.x * blockDim.x) {
         if (i < nchunks) {
-            reinterpret_cast<unsigned *>(u0)[i * 4 + 3] = 1u;
-            reinterpret_cast<unsigned *>(u1)[i * 4 + 3] = 0u;
+            reinterpret_cast<unsigned *>(ring.b[0])[i * 4 + 3] = 1u;
+#pragma unroll
+            for (int q = 1; q < kRing; ++q) reinterpret_cast<unsigned *>(ring.b[q])[i * 4 + 3] = 0u;
         } else {
-            reinterpret_cast<uint4 *>(u0)[i] = make_uint4(0u, 0u, 0u, 0xffffffffu);
-            reinterpret_cast<uint4 *>(u1)[i] = make_uint4(0u, 0u, 0u, 0xffffffffu);
+#pragma unroll
+            for (int q = 0; q < kRing; ++q) reinterpret_cast<uint4 *>(ring.b[q])[i] = make_uint4(0u, 0u, 0u, 0xffffffffu);
         }
     }
 }
@@ -752,27 +916,28 @@ struct glb_poisson_plan {
     double ell_fill = 0.0;              // nnz / stored entries of the slabs
     float tuned_ms[2] = {0.f, 0.f};     // AUTO: measured ms of the trial run, {dataflow, barrier}
     int tuned_gate = 32;
+    float *d_ring = nullptr;            // dataflow kernel: buffers 2 and 3 of the version ring (0 and 1 are the caller's u0/u1)
+    bool l1_first = true;               // dataflow kernel: first attempt of a gather through L1
+    bool pipelined = true;              // dataflow kernel: software-pipelined gather stream (poisson_dataflow_pipe_kernel)
     unsigned *d_gate = nullptr;         // dataflow kernel: start gate counter
     int gate_every = 32;                // dataflow kernel: iterations between re-alignment gates (tuned at plan time)
     bool has_long_rows = false;         // rows longer than a slice batch exist (dealt over whole warps)
     int scratch_row = 0;                // > 0: the label matrices carry that many rows behind row n-1, owned by the library
-                                        // (padding targets of the V2 slabs)
-    unsigned long long *d_stats = nullptr;   // GLB_POISSON_STATS=1: {re-polls, batches that had to poll, max warp cycles, CTAs}
+                                        // (padding targets of the slabs)
+    unsigned long long *d_stats = nullptr;   // -DGLB_EXPERIMENT, GLB_POISSON_STATS=1: {re-polls, polling batches, max warp cycles, CTAs}
 };
 
-// Launch geometry of the persistent kernels.  GLB_POISSON_VARIANT="threads,unroll" selects another
-// instantiation for experiments (tools/poisson_sweep.py); unknown combinations fall back to the default.
-struct PersistVariant { int threads, unroll; };
-
-static PersistVariant persist_variant(int def_threads, int def_unroll)
+// Experiment switches exist only in -DGLB_EXPERIMENT builds (libglb200_exp.so, python -m graphlearning_b200.build --exp)
+// and are read ONCE, when a plan is created; the product library has no environment lookups on the iterate path.
+static int exp_env(const char *name, int def)
 {
-    PersistVariant v{def_threads, def_unroll};
-    const char *e = getenv("GLB_POISSON_VARIANT");
-    if (e) {
-        int t = 0, u = 0;
-        if (sscanf(e, "%d,%d", &t, &u) == 2) { v.threads = t; v.unroll = u; }
-    }
-    return v;
+#ifdef GLB_EXPERIMENT
+    const char *e = getenv(name);
+    if (e) return atoi(e);
+#else
+    (void)name;
+#endif
+    return def;
 }
 
 template <int LANES>
@@ -794,63 +959,31 @@ static const void *pick_barrier(int ldu, int *threads)
     }
 }
 
+// 512 threads x 8 gathers in flight per lane (16-entry batches spill at the 128-register cap, r1 visit 4)
 template <int LANES>
-static const void *dataflow_fn(const PersistVariant &v, int *threads)
+static const void *dataflow_fn(bool pipelined, bool l1_first, int *threads)
 {
-#define GLB_DV(T_, U_)                                                  \
-    if (v.threads == T_ && v.unroll == U_) {                            \
-        *threads = T_;                                                  \
-        return (const void *)poisson_dataflow_kernel<LANES, T_, U_, false>;    \
+    const int pt = exp_env("GLB_POISSON_THREADS", 512);
+    if (pipelined) {
+        if (pt == 768) { *threads = 768; return l1_first ? (const void *)poisson_dataflow_pipe_kernel<LANES, 768, true> : (const void *)poisson_dataflow_pipe_kernel<LANES, 768, false>; }
+        if (pt == 1024) { *threads = 1024; return l1_first ? (const void *)poisson_dataflow_pipe_kernel<LANES, 1024, true> : (const void *)poisson_dataflow_pipe_kernel<LANES, 1024, false>; }
+        *threads = 512;
+        return l1_first ? (const void *)poisson_dataflow_pipe_kernel<LANES, 512, true> : (const void *)poisson_dataflow_pipe_kernel<LANES, 512, false>;
     }
-    GLB_DV(1024, 4) GLB_DV(1024, 8) GLB_DV(768, 8) GLB_DV(512, 8) GLB_DV(512, 16) GLB_DV(256, 16)
-#undef GLB_DV
     *threads = 512;
-    return (const void *)poisson_dataflow_kernel<LANES, 512, 16, false>;
+    return l1_first ? (const void *)poisson_dataflow_kernel<LANES, 512, 8, true>
+                    : (const void *)poisson_dataflow_kernel<LANES, 512, 8, false>;
 }
 
-// second-generation slab format (pairs + scratch-row padding); GLB_POISSON_VARIANT picks the CTA size
-template <int LANES>
-static const void *dataflow2_fn(const PersistVariant &v, int *threads)
+static const void *pick_dataflow(int lanes, bool pipelined, bool l1_first, int *threads)
 {
-    if (v.threads == 1024) { *threads = 1024; return (const void *)poisson_dataflow_kernel<LANES, 1024, 8, true>; }
-    if (v.threads == 768) { *threads = 768; return (const void *)poisson_dataflow_kernel<LANES, 768, 8, true>; }
-    if (v.threads == 512 && v.unroll == 8) { *threads = 512; return (const void *)poisson_dataflow_kernel<LANES, 512, 8, true>; }
-    if (v.threads == 256) { *threads = 256; return (const void *)poisson_dataflow_kernel<LANES, 256, 16, true>; }
-    if (v.threads == 512 && v.unroll == 16) { *threads = 512; return (const void *)poisson_dataflow_kernel<LANES, 512, 16, true>; }
-    *threads = 512;
-    return (const void *)poisson_dataflow_kernel<LANES, 512, 8, true>;
-}
-
-static thread_local int g_df_force = 0;  // plan_create builds the first-generation plan for comparison on hub-heavy graphs
-
-static int dataflow_version()          // GLB_POISSON_DF=1 keeps the first-generation kernel for A/B runs
-{
-    if (g_df_force) return g_df_force;
-    const char *e = getenv("GLB_POISSON_DF");
-    return (e && atoi(e) == 1) ? 1 : 2;
-}
-
-static const void *pick_dataflow(int lanes, int *threads)
-{
-    const PersistVariant v = dataflow_version() == 2 ? persist_variant(512, 8)      // r1 visit 4: 16-entry batches spill
-                                                     : persist_variant(512, 16);    // r1i probe: one batch per row
-    if (dataflow_version() == 2) {
-        switch (lanes) {
-            case 1: return dataflow2_fn<1>(v, threads);
-            case 2: return dataflow2_fn<2>(v, threads);
-            case 4: return dataflow2_fn<4>(v, threads);
-            case 8: return dataflow2_fn<8>(v, threads);
-            case 16: return dataflow2_fn<16>(v, threads);
-            default: return dataflow2_fn<32>(v, threads);
-        }
-    }
     switch (lanes) {
-        case 1: return dataflow_fn<1>(v, threads);
-        case 2: return dataflow_fn<2>(v, threads);
-        case 4: return dataflow_fn<4>(v, threads);
-        case 8: return dataflow_fn<8>(v, threads);
-        case 16: return dataflow_fn<16>(v, threads);
-        default: return dataflow_fn<32>(v, threads);
+        case 1: return dataflow_fn<1>(pipelined, l1_first, threads);
+        case 2: return dataflow_fn<2>(pipelined, l1_first, threads);
+        case 4: return dataflow_fn<4>(pipelined, l1_first, threads);
+        case 8: return dataflow_fn<8>(pipelined, l1_first, threads);
+        case 16: return dataflow_fn<16>(pipelined, l1_first, threads);
+        default: return dataflow_fn<32>(pipelined, l1_first, threads);
     }
 }
 
@@ -913,11 +1046,16 @@ static int plan_try_dataflow(glb_poisson_plan *p, const std::vector<int> &h_rp, 
     if (!lanes) return 0;
     const int rowb = lanes * 16, rpw = 32 / lanes;
     if ((double)(n + kScratchRows) * rowb >= 4294967295.0 || n >= kRowSrcBit) return 0;
-    const bool v2 = dataflow_version() == 2;
-    // V2: padding entries gather one of the kScratchRows scratch rows behind row n-1 (value 0, always ready), dealt round
-    // robin so that no single L2 line takes all of them
+    p->l1_first = exp_env("GLB_POISSON_L1", 1) != 0;
+    p->pipelined = exp_env("GLB_POISSON_PIPE", 1) != 0;
+    const int pad_to = p->pipelined ? 8 : 2;
+    // padding entries gather a scratch row behind row n-1 (value 0, always ready).  Through L1 one row per CTA (it stays
+    // resident in that SM's L1); at L2 they are dealt round robin so that no single L2 line takes all of them.
     unsigned pad_next = 0;
-    auto pad_off = [&]() -> unsigned { return v2 ? (unsigned)(n + (pad_next++ % kScratchRows)) * (unsigned)rowb : kPadOff; };
+    auto pad_off = [&](int cta) -> unsigned {
+        const unsigned r = p->l1_first ? (unsigned)(cta % kScratchRows) : (pad_next++ % kScratchRows);
+        return (unsigned)(n + r) * (unsigned)rowb;
+    };
     int grid = (int)((n + 63) / 64);                  // tiny graphs: at least ~64 rows per CTA
     if (grid > sms) grid = sms;
     if (grid < 1) grid = 1;
@@ -936,14 +1074,14 @@ static int plan_try_dataflow(glb_poisson_plan *p, const std::vector<int> &h_rp, 
     tm.lap("symmetry check");
 
     int threads = 0;
-    const void *fn = pick_dataflow(lanes, &threads);
+    const void *fn = pick_dataflow(lanes, p->pipelined, p->l1_first, &threads);
     const int nw = threads / 32;
     std::vector<int> bounds;
     balanced_bounds(h_rp, n, grid, 2.0, bounds);
     std::vector<int2> slab;
     std::vector<int4> slots;
     std::vector<long long> slab_off((size_t)grid + 1, 0);
-    std::vector<int> slot_off((size_t)grid + 1, 0), slot_rows, order;
+    std::vector<int> slot_off((size_t)grid + 1, 0), slot_rows, order, slot_first;
     slab.reserve((size_t)nnz + (size_t)nnz / 4 + 1024);
     int cap_entries = 0, cap_slots = 0, cap_parts = 0;
     const int part_max = kLongRowDf * rpw;            // nonzeros of one warp-wide piece of a long row (2 batches per lane group)
@@ -963,7 +1101,7 @@ static int plan_try_dataflow(glb_poisson_plan *p, const std::vector<int> &h_rp, 
             sl.type = kSlotNormal;
             sl.L = h_rp[order[k0] + 1] - h_rp[order[k0]];
             for (int g = 0; g < rpw; ++g) sl.rows[g] = k0 + g < order.size() ? order[k0 + g] : -1;
-            sl.cost = (sl.L + 15) / 16 + 1;
+            sl.cost = p->pipelined ? (sl.L + 7) / 8 + 1 : (sl.L + 15) / 16 + 1;
             cta_slots.push_back(sl);
         }
         // long rows: one warp-wide slot per piece of at most part_max nonzeros
@@ -989,7 +1127,7 @@ static int plan_try_dataflow(glb_poisson_plan *p, const std::vector<int> &h_rp, 
                     sl.type = kSlotPart;
                     sl.pbuf = nparts_cta + q - 1;
                 }
-                sl.cost = (sl.L + 15) / 16 + 1 + (q == 0 ? m - 1 : 0);
+                sl.cost = (p->pipelined ? (sl.L + 7) / 8 : (sl.L + 15) / 16) + 1 + (q == 0 ? m - 1 : 0);
                 cta_slots.push_back(sl);
             }
             nparts_cta += m - 1;
@@ -1005,42 +1143,30 @@ static int plan_try_dataflow(glb_poisson_plan *p, const std::vector<int> &h_rp, 
             if (cls(a) != cls(c2)) return cls(a) < cls(c2);
             return cta_slots[a].cost > cta_slots[c2].cost;
         });
-        // Experiment (GLB_POISSON_HUBWARPS=1): warps of their own for the long rows, as many as their share of the
-        // work.  Measured slower than mixing them (r1q probe, profiles/): 40 vs 23 us/iteration on the 128-d graph.
-        long long cost_long = 0, cost_all = 0;
-        for (int i : idx) { cost_all += cta_slots[i].cost; if (cls(i) != 2) cost_long += cta_slots[i].cost; }
-        int hub_warps = 0;
-        if (cost_long > 0 && cost_long < cost_all && getenv("GLB_POISSON_HUBWARPS")) {
-            hub_warps = (int)((double)cost_long / (double)cost_all * nw + 0.5);
-            hub_warps = std::max(1, std::min(nw - 1, hub_warps));
-        }
+        // (warps of their own for the long rows were measured slower than mixing them: 40 vs 23 us/iteration on the
+        // 128-d graph, r1q probe under profiles/)
         for (int i : idx) {
-            int lo = 0, hi = nw;
-            if (hub_warps) { if (cls(i) != 2) hi = hub_warps; else lo = hub_warps; }
-            int w = lo;
-            for (int q = lo + 1; q < hi; ++q) if (load[q] < load[w]) w = q;
+            int w = 0;
+            for (int q = 1; q < nw; ++q) if (load[q] < load[w]) w = q;
             per_warp[w].push_back(i);
             load[w] += cta_slots[i].cost;
         }
         size_t depth = 0;
         for (auto &v : per_warp) depth = std::max(depth, v.size());
         const long long base0 = (long long)slab.size();
-        for (size_t k = 0; k < depth; ++k)
-            for (int w = 0; w < nw; ++w) {
-                if (k >= per_warp[w].size()) {            // empty slot: nothing to gather, nothing to store
-                    slots.push_back(make_int4(0, 0, kSlotNormal, 0));
-                    for (int g = 0; g < rpw; ++g) slot_rows.push_back(-1);
-                    continue;
-                }
+        // The entries of one warp's slots are stored back to back (the pipelined kernel walks them as one stream);
+        // the slot table is interleaved: slot k of warp w at k * nw + w.
+        slot_first.assign(depth * (size_t)nw, 0);
+        for (int w = 0; w < nw; ++w)
+            for (size_t k = 0; k < per_warp[w].size(); ++k) {
                 const Slot &sl = cta_slots[per_warp[w][k]];
-                slots.push_back(make_int4((int)((long long)slab.size() - base0), sl.L, sl.type | (sl.nparts << 8), sl.pbuf));
-                for (int g = 0; g < rpw; ++g) slot_rows.push_back(sl.rows[g]);
-                // V1: entry j of lane group g at j * rpw + g.  V2: entries in pairs, (j/2 * rpw + g) * 2 + (j & 1), width
-                // rounded up to even.
-                const int Lst = v2 ? (sl.L + 1) & ~1 : sl.L;
+                slot_first[k * nw + w] = (int)((long long)slab.size() - base0);
+                // entries in pairs: entry j of lane group g at (j/2 * rpw + g) * 2 + (j & 1); width rounded up to a
+                // multiple of pad_to (2: pairs; 8: the octets of the pipelined kernel) with always-ready scratch entries
+                const int Lst = (sl.L + pad_to - 1) / pad_to * pad_to;
                 const size_t s0 = slab.size();
                 slab.resize(s0 + (size_t)Lst * rpw);
-                for (size_t q = s0; q < slab.size(); ++q) slab[q] = make_int2((int)pad_off(), 0);
+                for (size_t q = s0; q < slab.size(); ++q) slab[q] = make_int2((int)pad_off(b), 0);
                 for (int j = 0; j < sl.L; ++j)
                     for (int g = 0; g < rpw; ++g) {
                         int q = -1;
@@ -1052,9 +1178,20 @@ static int plan_try_dataflow(glb_poisson_plan *p, const std::vector<int> &h_rp, 
                             if (qq < sl.nz1) q = qq;
                         }
                         if (q < 0) continue;
-                        const size_t at = v2 ? s0 + ((size_t)(j / 2) * rpw + g) * 2 + (j & 1) : s0 + (size_t)j * rpw + g;
+                        const size_t at = s0 + ((size_t)(j / 2) * rpw + g) * 2 + (j & 1);
                         slab[at] = make_int2((int)((unsigned)h_col[q] * (unsigned)rowb), float_bits(h_val[q]));
                     }
+            }
+        for (size_t k = 0; k < depth; ++k)
+            for (int w = 0; w < nw; ++w) {
+                if (k >= per_warp[w].size()) {            // empty slot: nothing to gather, nothing to store
+                    slots.push_back(make_int4(0, 0, kSlotNormal, 0));
+                    for (int g = 0; g < rpw; ++g) slot_rows.push_back(-1);
+                    continue;
+                }
+                const Slot &sl = cta_slots[per_warp[w][k]];
+                slots.push_back(make_int4(slot_first[k * nw + w], sl.L, sl.type | (sl.nparts << 8), sl.pbuf));
+                for (int g = 0; g < rpw; ++g) slot_rows.push_back(sl.rows[g]);
             }
         slab_off[b + 1] = (long long)slab.size();
         slot_off[b + 1] = (int)slots.size();
@@ -1088,13 +1225,12 @@ static int plan_try_dataflow(glb_poisson_plan *p, const std::vector<int> &h_rp, 
     p->ldu = lanes * 4;
     p->grid = grid; p->threads = threads; p->fn = fn; p->smem_bytes = smem;
     p->cap_entries = cap_entries; p->cap_slots = cap_slots; p->cap_parts = cap_parts;
-    p->scratch_row = v2 ? kScratchRows : 0;
+    p->scratch_row = kScratchRows;
+    GLB_CUDA(cudaMalloc(&p->d_ring, sizeof(float) * 2 * ((size_t)n + kScratchRows) * (size_t)(lanes * 4)));
     p->ell_fill = slab.size() ? (double)nnz / (double)slab.size() : 1.0;
     GLB_CUDA(cudaMalloc(&p->d_gate, 2 * sizeof(unsigned)));          // [0] gate counter, [1] watchdog flag
     GLB_CUDA(cudaMemsetAsync(p->d_gate, 0, 2 * sizeof(unsigned), st));
-    if (getenv("GLB_POISSON_STATS")) {
-        GLB_CUDA(cudaMalloc(&p->d_stats, 4 * sizeof(unsigned long long)));
-    }
+    if (exp_env("GLB_POISSON_STATS", 0)) GLB_CUDA(cudaMalloc(&p->d_stats, 4 * sizeof(unsigned long long)));
     return 0;
 }
 
@@ -1179,9 +1315,8 @@ extern "C" GLB_API int glb_poisson_plan_create(glb_poisson_plan **plan, const in
     p->d_rowptr = d_rowptr; p->d_col = d_col; p->d_val = d_val;
     struct Guard { glb_poisson_plan *p; ~Guard() { if (p) glb_poisson_plan_destroy(p); } } guard{p};
 
-    const char *env_kind = getenv("GLB_POISSON_KIND");          // experiments / tests: overrides AUTO only
-    if (kind == GLB_POISSON_KIND_AUTO && env_kind) {
-        const int k = atoi(env_kind);
+    if (kind == GLB_POISSON_KIND_AUTO) {                        // -DGLB_EXPERIMENT builds only: overrides AUTO
+        const int k = exp_env("GLB_POISSON_KIND", GLB_POISSON_KIND_AUTO);
         if (k >= GLB_POISSON_KIND_STEP && k <= GLB_POISSON_KIND_DATAFLOW) kind = k;
     }
     int dev = 0, coop = 0, max_smem = 0;
@@ -1201,9 +1336,11 @@ extern "C" GLB_API int glb_poisson_plan_create(glb_poisson_plan **plan, const in
         tm.lap("dataflow slabs");
         if (p->kind == GLB_POISSON_KIND_STEP && (kind == GLB_POISSON_KIND_AUTO || kind == GLB_POISSON_KIND_BARRIER))
             if ((rc = plan_try_barrier(p, h_rp, sms, max_smem, st))) return rc;
-        const bool tune = !getenv("GLB_POISSON_NOTUNE");
+        const bool tune = !exp_env("GLB_POISSON_NOTUNE", 0);
+        const int forced_gate = exp_env("GLB_POISSON_GATE_EVERY", -1);
+        if (forced_gate >= 0) p->gate_every = p->tuned_gate = forced_gate;
         float ms_df = 0.f;
-        if (p->kind == GLB_POISSON_KIND_DATAFLOW && tune && !getenv("GLB_POISSON_GATE_EVERY")) {
+        if (p->kind == GLB_POISSON_KIND_DATAFLOW && tune && forced_gate < 0) {
             // Measure, don't guess.  Gate period of the dataflow kernel: graphs with hub rows (every hub is a meeting
             // point of hundreds of producers) run best with a gate every few iterations, hub-free graphs with rare gates.
             const int cand[3] = {32, 4, 1};
@@ -1221,21 +1358,6 @@ extern "C" GLB_API int glb_poisson_plan_create(glb_poisson_plan **plan, const in
             p->gate_every = p->tuned_gate;
             p->tuned_ms[0] = ms_df;
             tm.lap("gate tuning");
-            // Hub-heavy graphs (rows dealt over whole warps): the first-generation inner loop (16 gathers in flight per lane
-            // group) can beat the predicate-free one (8 in flight).  Build it, tune it, keep the faster plan.
-            if (p->has_long_rows && !g_df_force && !getenv("GLB_POISSON_DF")) {
-                glb_poisson_plan *v1 = nullptr;
-                g_df_force = 1;
-                const int rc1 = glb_poisson_plan_create(&v1, d_rowptr, d_col, d_val, n, nnz, c, GLB_POISSON_KIND_DATAFLOW, stream);
-                g_df_force = 0;
-                if (rc1 == 0) {
-                    if (v1->tuned_ms[0] > 0.f && v1->tuned_ms[0] < ms_df) { std::swap(*p, *v1); ms_df = p->tuned_ms[0]; }
-                    glb_poisson_plan_destroy(v1);
-                } else if (rc1 != GLB_E_UNSUPPORTED) {
-                    return rc1;
-                }
-                tm.lap("first-generation plan + timing");
-            }
         }
         if (kind == GLB_POISSON_KIND_AUTO && p->kind == GLB_POISSON_KIND_DATAFLOW && tune) {
             // ... and the dataflow kernel against the barrier kernel (small graphs: too few rows per SM to hide the
@@ -1273,6 +1395,7 @@ extern "C" GLB_API int glb_poisson_plan_destroy(glb_poisson_plan *plan)
     cudaFree(plan->d_counter);  cudaFree(plan->d_cta_rows);
     cudaFree(plan->d_slabs);    cudaFree(plan->d_slots);
     cudaFree(plan->d_slab_off); cudaFree(plan->d_slot_off); cudaFree(plan->d_slot_rows); cudaFree(plan->d_stats); cudaFree(plan->d_gate);
+    cudaFree(plan->d_ring);
     delete plan;
     return 0;
 }
@@ -1358,27 +1481,35 @@ extern "C" GLB_API int glb_poisson_iterate(glb_poisson_plan *plan, const float *
     const int *rp = plan->d_rowptr, *col = plan->d_col;
     const float *val = plan->d_val;
     if (plan->kind == GLB_POISSON_KIND_DATAFLOW) {
-        int nopoll = getenv("GLB_POISSON_NOPOLL") ? atoi(getenv("GLB_POISSON_NOPOLL")) : 0;     // experiment only: ignores the epoch words (results are wrong)
-        unsigned *gate = getenv("GLB_POISSON_NOGATE") ? nullptr : plan->d_gate;
+        unsigned *gate = plan->d_gate;
         unsigned *watchdog = plan->d_gate + 1;                // sticky: cleared only by glb_poisson_plan_check
-        if (gate) GLB_CUDA(cudaMemsetAsync(gate, 0, sizeof(unsigned), st));
-        int gate_every = getenv("GLB_POISSON_GATE_EVERY") ? atoi(getenv("GLB_POISSON_GATE_EVERY")) : plan->gate_every;
-        stamp_kernel<<<stream_blocks_p(plan->n * (plan->ldu / 4)), 256, 0, st>>>(d_u0, d_u1, plan->n * (plan->ldu / 4),
+        GLB_CUDA(cudaMemsetAsync(gate, 0, sizeof(unsigned), st));
+        int gate_every = plan->gate_every;
+        // version ring: the caller's u0 / u1 are buffers 0 / 1, the plan owns buffers 2 / 3
+        const size_t buf_floats = ((size_t)plan->n + (size_t)plan->scratch_row) * (size_t)plan->ldu;
+        DfRing ring;
+        ring.b[0] = d_u0; ring.b[1] = d_u1; ring.b[2] = plan->d_ring; ring.b[3] = plan->d_ring + buf_floats;
+        stamp_kernel<<<stream_blocks_p(plan->n * (plan->ldu / 4)), 256, 0, st>>>(ring, plan->n * (plan->ldu / 4),
                                                                                  plan->scratch_row * (plan->ldu / 4));
         void *args[] = {(void *)&plan->d_slabs, (void *)&plan->d_slab_off, (void *)&plan->d_slots, (void *)&plan->d_slot_off,
-                        (void *)&plan->d_slot_rows, (void *)&d_Db, (void *)&d_u0, (void *)&d_u1, (void *)&T,
+                        (void *)&plan->d_slot_rows, (void *)&d_Db, (void *)&ring, (void *)&T,
                         (void *)&plan->cap_entries, (void *)&plan->cap_slots, (void *)&plan->cap_parts, (void *)&plan->d_stats,
-                        (void *)&nopoll, (void *)&gate, (void *)&gate_every, (void *)&watchdog};
+                        (void *)&gate, (void *)&gate_every, (void *)&watchdog};
         if (plan->d_stats) GLB_CUDA(cudaMemsetAsync(plan->d_stats, 0, 4 * sizeof(unsigned long long), st));
         GLB_CUDA(cudaLaunchCooperativeKernel(plan->fn, dim3(plan->grid), dim3(plan->threads), args, plan->smem_bytes, st));
+        if (launches) *launches += 2;
+        if ((T & (kRing - 1)) >= 2) {                         // version T sits in a plan-owned buffer: hand it to the caller
+            GLB_CUDA(cudaMemcpyAsync((T & 1) ? d_u1 : d_u0, ring.b[T & (kRing - 1)], sizeof(float) * (size_t)plan->n * plan->ldu,
+                                     cudaMemcpyDeviceToDevice, st));
+            if (launches) *launches += 1;
+        }
         if (plan->d_stats) {
             unsigned long long h[4];
             GLB_CUDA(cudaMemcpyAsync(h, plan->d_stats, sizeof(h), cudaMemcpyDeviceToHost, st));
             GLB_CUDA(cudaStreamSynchronize(st));
-            fprintf(stderr, "[glb] dataflow T=%d grid=%d: re-polls %llu (%.2f per nonzero-lane), polling batches %llu, max warp cycles/iter %.0f\n",
+            fprintf(stderr, "[glb] dataflow T=%d grid=%d: re-polls %llu (%.4f per nonzero-lane), polling batches %llu, max warp cycles/iter %.0f\n",
                     T, plan->grid, h[0], (double)h[0] / ((double)plan->nnz * (plan->ldu / 4) * T + 1), h[1], (double)h[2] / T);
         }
-        if (launches) *launches += 2;
     } else if (plan->kind == GLB_POISSON_KIND_BARRIER) {
         GLB_CUDA(cudaMemsetAsync(plan->d_counter, 0, sizeof(unsigned) * kFlagStride * plan->grid, st));
         int n = (int)plan->n, ldu = plan->ldu, max_rows = plan->max_rows, cap = plan->slab_cap;

@@ -219,7 +219,7 @@ def test_kernel_choice(dev):
     with pytest.raises(dev._lib.GlbError, match="not applicable"):
         dev.PoissonOperator(Wd, kind="dataflow").plan(10)
     op = dev.PoissonOperator(Ws, kind="dataflow")
-    assert 0.8 < op.fill(10) <= 1.0                               # sliced-ELL padding stays small
+    assert 0.5 < op.fill(10) <= 1.0                               # slice widths are padded to the 8-entry octets of the pipelined stream
 
 
 @pytest.mark.parametrize("c", [5, 10, 40])

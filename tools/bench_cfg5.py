@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--iters", type=int, default=100)
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--check", default=None)
+    ap.add_argument("--reorder", type=int, default=0, help="1: relabel the nodes with the library's RCM locality ordering first")
     a = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -39,6 +40,17 @@ def main():
     t0 = time.perf_counter()
     W = build_graph(a.n)
     t_graph = time.perf_counter() - t0
+    t_order = 0.0
+    if a.reorder:
+        import ctypes
+        from graphlearning_b200 import _lib
+        t0 = time.perf_counter()
+        rp = np.ascontiguousarray(W.indptr, dtype=np.int32); ci = np.ascontiguousarray(W.indices, dtype=np.int32)
+        perm = np.empty(W.shape[0], dtype=np.int32)
+        _lib.call("glb_locality_order_host", ctypes.c_void_p(rp.ctypes.data), ctypes.c_void_p(ci.ctypes.data), W.shape[0],
+                  ctypes.c_void_p(perm.ctypes.data))
+        W = W[perm][:, perm].tocsr()
+        t_order = time.perf_counter() - t0
     n, nnz, c = W.shape[0], W.nnz, 10
     pp = gd.PartitionedPoisson(W, rank=rank, world=world)
     if a.check:
@@ -72,7 +84,7 @@ def main():
                           "bytes_per_iteration": b_iter, "achieved_GBs_all_gpus": b_iter * its / 1e9,
                           "frac_of_hbm_peak_x_gpus": b_iter * its / 1e9 / (peak * world),
                           "allgather_bytes_per_iteration_per_gpu": int((world - 1) * pp._plans[c][1].rows_pad * pp._plans[c][2] * 4),
-                          "graph_build_s": t_graph, "kernel": "poisson_step_kernel + ncclAllGather"}), flush=True)
+                          "graph_build_s": t_graph, "reorder": a.reorder, "reorder_s": t_order, "kernel": "poisson_step_kernel + ncclAllGather"}), flush=True)
     if world > 1:
         dist.barrier(); dist.destroy_process_group()
 

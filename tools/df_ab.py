@@ -1,41 +1,67 @@
-"""GPU experiment: A/B of the dataflow Poisson kernel generations and CTA shapes on the bench graph, same process, same
-box.  GLB_POISSON_DF=1 is the first-generation kernel.  Prints one line per configuration.  Not part of the product."""
+"""GPU experiment: A/B of the dataflow Poisson kernel variants on the bench graph (and optionally the 128-d hub graph),
+same process, same box.  Needs the -DGLB_EXPERIMENT library (python -m graphlearning_b200.build --exp), whose plan
+creation reads the switches below.  Prints one line per configuration.  Not part of the product.
+
+    GLB200_LIB=graphlearning_b200/lib/libglb200_exp.so python tools/df_ab.py [hub] [stats]
+
+switches: GLB_POISSON_PIPE (0 batch kernel / 1 pipelined stream), GLB_POISSON_L1 (first gather attempt through L1),
+GLB_POISSON_THREADS (CTA size of the pipelined kernel), reorder (RCM locality ordering of the operator)."""
 import os, sys
-import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+os.environ.setdefault("GLB200_LIB", os.path.join(ROOT, "graphlearning_b200", "lib", "libglb200_exp.so"))
+import numpy as np, torch
 import bench
 from graphlearning_b200 import device as gdev
-from oracle import gl_oracle as orc
+from oracle import gl_oracle as orc, c_oracle
 
-W, labels = bench.build_workload()
+hub = "hub" in sys.argv
+if "stats" in sys.argv:
+    os.environ["GLB_POISSON_STATS"] = "1"
+if hub:
+    from graphlearning_b200 import knn_gpu
+    X, labels = orc.synthetic_blobs(70000, 128, c=10, seed=0)
+    ind, dist_ = knn_gpu.knnsearch_gpu(X.astype(np.float64), 11)
+    W = orc.knn_weights(ind, dist_, 10)
+else:
+    W, labels = bench.build_workload()
+n = W.shape[0]
 ti = orc.one_per_class(labels, rate=1, seed=0)
-src = orc.poisson_source(W.shape[0], ti, labels[ti])[0]
-ref = None
-configs = [("1", "512,16", "0"), ("2", "512,16", "0"), ("2", "512,8", "0"), ("2", "1024,8", "0"), ("2", "768,8", "0"), ("2", "256,16", "0"),
-           ("1", "512,16", "1"), ("2", "512,16", "1"), ("2", "1024,8", "1"), ("2", "512,16", "3"), ("1", "512,16", "0"), ("2", "512,16", "0")]
-if len(sys.argv) > 1 and sys.argv[1] == "short":
-    configs = [("1", "512,16", "0"), ("2", "512,8", "0"), ("2", "512,8", "1"), ("2", "512,8", "3"), ("1", "512,16", "0"), ("2", "512,8", "0")]
-for df, variant, nopoll in configs:
-    os.environ["GLB_POISSON_DF"] = df
-    os.environ["GLB_POISSON_VARIANT"] = variant
-    if nopoll != "0":
-        os.environ["GLB_POISSON_NOPOLL"] = nopoll
-    else:
-        os.environ.pop("GLB_POISSON_NOPOLL", None)
-    op = gdev.PoissonOperator(W, kind="dataflow")
-    Db = op.source_to_Db(src)
-    u0 = torch.zeros_like(Db); u1 = torch.zeros_like(Db)
-    times = []
-    for _ in range(5):
-        u0.zero_()
-        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-        e0.record(); u, _ = op.iterate(Db, 1000, u0, u1); e1.record(); torch.cuda.synchronize()
-        times.append(e0.elapsed_time(e1))
-    res = op.unpack(u, 10).clone()
-    if ref is None:
-        ref = res
-    err = float((res - ref).abs().max() / ref.abs().max())
-    print("DF=%s variant=%-8s nopoll=%s  gate=%d fill=%.3f  us/iter: best %.3f median %.3f  rel diff vs first=%.1e" % (
-        df, variant, nopoll, op.gate(10), op.fill(10), min(times), float(np.median(times)), err), flush=True)
-    del op
+src = orc.poisson_source(n, ti, labels[ti])[0]
+s = orc.poisson_gd_setup(W, ti, labels[ti])
+ref50 = c_oracle.poisson_iterate(s["P"], np.asarray(s["Db"]), 50)
+b_iter = bench.algorithmic_bytes(n, W.nnz, 10)
+print("graph: n=%d nnz=%d max row %d; bytes/iteration %d" % (n, W.nnz, int(np.diff(W.indptr).max()), b_iter), flush=True)
+
+#          pipe l1  threads reorder
+configs = [(0, 0, 512, 0), (0, 1, 512, 0), (0, 0, 512, 1), (0, 1, 512, 1),
+           (1, 0, 512, 0), (1, 1, 512, 0), (1, 0, 512, 1), (1, 1, 512, 1),
+           (1, 1, 768, 1), (1, 0, 768, 0), (1, 1, 1024, 1), (1, 1, 512, 1)]
+first = None
+for pipe, l1, threads, reorder in configs:
+    os.environ["GLB_POISSON_PIPE"] = str(pipe)
+    os.environ["GLB_POISSON_L1"] = str(l1)
+    os.environ["GLB_POISSON_THREADS"] = str(threads)
+    try:
+        op = gdev.PoissonOperator(W, kind="dataflow", reorder=bool(reorder))
+        Db = op.source_to_Db(src)
+        u50 = op.unpack(op.iterate(Db, 50)[0], 10).cpu().numpy()
+        err = float(np.abs(u50 - ref50).max() / np.abs(ref50).max())
+        u0 = torch.zeros_like(Db); u1 = torch.zeros_like(Db)
+        times = []
+        for _ in range(5):
+            u0.zero_()
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            e0.record(); u, _ = op.iterate(Db, 1000, u0, u1); e1.record(); torch.cuda.synchronize()
+            times.append(e0.elapsed_time(e1))
+        res = op.unpack(u, 10).clone()
+        if first is None:
+            first = res
+        d = float((res - first).abs().max() / first.abs().max())
+        best = min(times)
+        print("pipe=%d l1=%d threads=%-4d reorder=%d  gate=%-2d fill=%.3f  us/iter best %.3f median %.3f  frac %.3f  "
+              "err vs oracle@50 %.1e  diff vs first@1000 %.1e" % (pipe, l1, threads, reorder, op.gate(10), op.fill(10), best, float(np.median(times)),
+                                                                 b_iter * 1000 / (best * 1e-3) / 1e9 / 6451.8, err, d), flush=True)
+        del op, Db, u0, u1
+    except Exception as e:
+        print("pipe=%d l1=%d threads=%d reorder=%d FAILED: %r" % (pipe, l1, threads, reorder, e), flush=True)
