@@ -68,6 +68,24 @@ SIGNATURES = {
                                          POINTER(c_int64), POINTER(c_int)]),
     "glb_lip_iterate_multi_host": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_double, c_int,
                                            c_double, c_double, c_int, c_int, c_int, c_int, POINTER(c_int), POINTER(c_int)]),
+    "glb_slab_create": (c_int, [POINTER(c_void_p), c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p,
+                                c_void_p, c_void_p, c_void_p]),
+    "glb_slab_destroy": (c_int, [c_void_p]),
+    "glb_slab_rows": (c_int64, [c_void_p]),
+    "glb_slab_ld": (c_int, [c_void_p]),
+    "glb_slab_fill": (c_double, [c_void_p]),
+    "glb_slab_region_bytes": (c_int64, [c_void_p]),
+    "glb_slab_attach": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, ctypes.c_uint32]),
+    "glb_slab_buffer": (c_int, [c_void_p, c_int, POINTER(c_void_p)]),
+    "glb_slab_pack": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "glb_slab_unpack": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
+    "glb_slab_reset": (c_int, [c_void_p, c_void_p]),
+    "glb_slab_iterate": (c_int, [c_void_p, c_void_p, c_int, POINTER(c_int), POINTER(c_int), c_void_p]),
+    "glb_slab_check": (c_int, [c_void_p, c_void_p]),
+    "glb_ipc_alloc": (c_int, [c_int64, POINTER(c_void_p), c_void_p]),
+    "glb_ipc_open": (c_int, [c_void_p, POINTER(c_void_p)]),
+    "glb_ipc_close": (c_int, [c_void_p]),
+    "glb_ipc_free": (c_int, [c_void_p]),
     "glb_poisson_gd_host": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int, c_void_p, c_int64,
                                     c_int, c_int, c_void_p, POINTER(c_int), POINTER(c_int)]),
 }

@@ -368,7 +368,8 @@ __device__ __forceinline__ const char *df_addr(const char *base, unsigned off)
 
 template <int N, int RPW, bool L1F>
 __device__ __forceinline__ void df_batch(const int2 *cvp, const char *in, unsigned expect, float &a0, float &a1,
-                                         float &a2, unsigned long long &n_poll, unsigned long long &n_badbatch, unsigned *watchdog)
+                                         float &a2, unsigned long long &n_poll, unsigned long long &n_badbatch, unsigned *watchdog,
+                                         unsigned poll_sleep)
 {
     unsigned off[N];
     float val[N];
@@ -394,6 +395,7 @@ __device__ __forceinline__ void df_batch(const int2 *cvp, const char *in, unsign
     while (!ok) {                                        // some producer is still behind (or L1 held an old line): re-poll at L2
         ++n_badbatch;
         if (poll_expired(watchdog, spins, t0)) break;
+        if ((poll_sleep & 0xffffu) && spins > 1) __nanosleep(poll_sleep & 0xffffu);   // this warp is ahead of its producers: leave L2 and the LSU to them
 #pragma unroll
         for (int i = 0; i < N; ++i)
             if (x[i].w < expect) { x[i] = ld_chunk(df_addr(in, off[i])); ++n_poll; }
@@ -417,7 +419,7 @@ poisson_dataflow_kernel(const int2 *__restrict__ slabs, const long long *__restr
                         const int4 *__restrict__ slots, const int *__restrict__ slot_off,
                         const int *__restrict__ slot_rows, const float *__restrict__ Db, DfRing ring, int T,
                         int cap_entries, int cap_slots, int cap_parts, unsigned long long *stats,
-                        unsigned *start_gate, int gate_every, unsigned *watchdog)
+                        unsigned *start_gate, int gate_every, unsigned *watchdog, unsigned poll_sleep)
 {
     constexpr int RPW = 32 / LANES;              // rows per warp pass = slice height of the ELL slab
     constexpr int NW = THREADS / 32;
@@ -485,18 +487,24 @@ poisson_dataflow_kernel(const int2 *__restrict__ slabs, const long long *__restr
         const int vi = t & (kRing - 1), vo = (t + 1) & (kRing - 1);
         const char *in = reinterpret_cast<const char *>(vi == 0 ? ring.b[0] : vi == 1 ? ring.b[1] : vi == 2 ? ring.b[2] : ring.b[3]) + li * 16;
         char *out = reinterpret_cast<char *>(vo == 0 ? ring.b[0] : vo == 1 ? ring.b[1] : vo == 2 ? ring.b[2] : ring.b[3]) + li * 16;
+#ifdef GLB_EXPERIMENT
+        // ceiling probes (results are wrong): bit 30 of poll_sleep = every chunk counts as ready (pure gather throughput, no
+        // synchronisation), bit 31 = no stores either (the label matrix stays read-only)
+        const unsigned expect = (poll_sleep & 0x40000000u) ? 0u : 1u + (unsigned)t;
+#else
         const unsigned expect = 1u + (unsigned)t;
+#endif
         for (int s = warp; s < nslots; s += NW) {            // slot k of warp w is stored at k * NW + w
             const int4 sl = s_slot[s];                       // (first entry, slice width, type | parts << 8, partial index)
             const int L = sl.y;
             float a0 = 0.f, a1 = 0.f, a2 = 0.f;
             const int2 *cv = s_cv + sl.x + g * 2;            // pair q of this lane group: 16 bytes at cv[q * 2 * RPW]
             int j = 0;
-            for (; j + U <= L; j += U) df_batch<U, RPW, L1F>(cv + j * RPW, in, expect, a0, a1, a2, n_poll, n_badbatch, watchdog);
-            if (U > 8 && (L & 8)) { df_batch<8, RPW, L1F>(cv + j * RPW, in, expect, a0, a1, a2, n_poll, n_badbatch, watchdog); j += 8; }
-            if (L & 4) { df_batch<4, RPW, L1F>(cv + j * RPW, in, expect, a0, a1, a2, n_poll, n_badbatch, watchdog); j += 4; }
-            if (L & 2) { df_batch<2, RPW, L1F>(cv + j * RPW, in, expect, a0, a1, a2, n_poll, n_badbatch, watchdog); j += 2; }
-            if (L & 1) df_batch<1, RPW, L1F>(cv + j * RPW, in, expect, a0, a1, a2, n_poll, n_badbatch, watchdog);
+            for (; j + U <= L; j += U) df_batch<U, RPW, L1F>(cv + j * RPW, in, expect, a0, a1, a2, n_poll, n_badbatch, watchdog, poll_sleep);
+            if (U > 8 && (L & 8)) { df_batch<8, RPW, L1F>(cv + j * RPW, in, expect, a0, a1, a2, n_poll, n_badbatch, watchdog, poll_sleep); j += 8; }
+            if (L & 4) { df_batch<4, RPW, L1F>(cv + j * RPW, in, expect, a0, a1, a2, n_poll, n_badbatch, watchdog, poll_sleep); j += 4; }
+            if (L & 2) { df_batch<2, RPW, L1F>(cv + j * RPW, in, expect, a0, a1, a2, n_poll, n_badbatch, watchdog, poll_sleep); j += 2; }
+            if (L & 1) df_batch<1, RPW, L1F>(cv + j * RPW, in, expect, a0, a1, a2, n_poll, n_badbatch, watchdog, poll_sleep);
             const int type = sl.z & 0xff;
             if (type != kSlotNormal) {                       // warp-uniform: one long row dealt over the lane groups
 #pragma unroll
@@ -510,7 +518,7 @@ poisson_dataflow_kernel(const int2 *__restrict__ slabs, const long long *__restr
                         volatile float *pb = s_part + ((size_t)(sl.w * 2 + (t & 1)) * LANES + li) * 4;
                         pb[0] = a0; pb[1] = a1; pb[2] = a2;
                         __threadfence_block();
-                        pb[3] = __uint_as_float(expect + 1u);
+                        pb[3] = __uint_as_float(2u + (unsigned)t);
                     }
                     continue;
                 }
@@ -520,7 +528,7 @@ poisson_dataflow_kernel(const int2 *__restrict__ slabs, const long long *__restr
                         volatile float *pb = s_part + ((size_t)((sl.w + q) * 2 + (t & 1)) * LANES + li) * 4;
                         unsigned spins = 0;
                         long long tw0 = 0;
-                        while (__float_as_uint(pb[3]) != expect + 1u && !poll_expired(watchdog, spins, tw0)) { }
+                        while (__float_as_uint(pb[3]) != 2u + (unsigned)t && !poll_expired(watchdog, spins, tw0)) { }
                         __threadfence_block();
                         a0 += pb[0]; a1 += pb[1]; a2 += pb[2];
                     }
@@ -533,7 +541,10 @@ poisson_dataflow_kernel(const int2 *__restrict__ slabs, const long long *__restr
                     const float4 b = __ldg(reinterpret_cast<const float4 *>(Db + (size_t)row * (ROWB / 4)) + li);
                     a0 += b.x; a1 += b.y; a2 += b.z;
                 }
-                st_chunk(out + (size_t)row * ROWB, a0, a1, a2, expect + 1u);
+#ifdef GLB_EXPERIMENT
+                if (!(poll_sleep & 0x80000000u) || a0 == 123.456f)
+#endif
+                st_chunk(out + (size_t)row * ROWB, a0, a1, a2, 2u + (unsigned)t);
             }
         }
     }
@@ -571,7 +582,7 @@ __device__ __forceinline__ void dfp_issue(const int4 *cv, const char *in, float 
 template <int RPW>
 __device__ __forceinline__ void dfp_consume(const int4 *cv, const char *in, unsigned expect, const float (&val)[4],
                                             uint4 (&x)[4], float &a0, float &a1, float &a2, unsigned &n_poll,
-                                            unsigned &n_badbatch, unsigned *watchdog)
+                                            unsigned &n_badbatch, unsigned *watchdog, unsigned poll_sleep)
 {
     bool ok = (x[0].w >= expect) & (x[1].w >= expect) & (x[2].w >= expect) & (x[3].w >= expect);
     if (!ok) {                                           // a producer is still behind (or L1 held an old line): re-poll at L2
@@ -582,6 +593,7 @@ __device__ __forceinline__ void dfp_consume(const int4 *cv, const char *in, unsi
         do {
             ++n_badbatch;
             if (poll_expired(watchdog, spins, t0)) break;
+            if ((poll_sleep & 0xffffu) && spins > 1) __nanosleep(poll_sleep & 0xffffu);   // this warp is ahead of its producers: leave L2 and the LSU to them
 #pragma unroll
             for (int i = 0; i < 4; ++i)
                 if (x[i].w < expect) { x[i] = ld_chunk(df_addr(in, off[i])); ++n_poll; }
@@ -602,7 +614,7 @@ poisson_dataflow_pipe_kernel(const int2 *__restrict__ slabs, const long long *__
                              const int4 *__restrict__ slots, const int *__restrict__ slot_off,
                              const int *__restrict__ slot_rows, const float *__restrict__ Db, DfRing ring, int T,
                              int cap_entries, int cap_slots, int cap_parts, unsigned long long *stats,
-                             unsigned *start_gate, int gate_every, unsigned *watchdog)
+                             unsigned *start_gate, int gate_every, unsigned *watchdog, unsigned poll_sleep)
 {
     constexpr int RPW = 32 / LANES;
     constexpr int NW = THREADS / 32;
@@ -668,7 +680,13 @@ poisson_dataflow_pipe_kernel(const int2 *__restrict__ slabs, const long long *__
         const int vi = t & (kRing - 1), vo = (t + 1) & (kRing - 1);
         const char *in = reinterpret_cast<const char *>(vi == 0 ? ring.b[0] : vi == 1 ? ring.b[1] : vi == 2 ? ring.b[2] : ring.b[3]) + li * 16;
         char *out = reinterpret_cast<char *>(vo == 0 ? ring.b[0] : vo == 1 ? ring.b[1] : vo == 2 ? ring.b[2] : ring.b[3]) + li * 16;
+#ifdef GLB_EXPERIMENT
+        // ceiling probes (results are wrong): bit 30 of poll_sleep = every chunk counts as ready (pure gather throughput, no
+        // synchronisation), bit 31 = no stores either (the label matrix stays read-only)
+        const unsigned expect = (poll_sleep & 0x40000000u) ? 0u : 1u + (unsigned)t;
+#else
         const unsigned expect = 1u + (unsigned)t;
+#endif
         float valA[4], valB[4];
         uint4 xA[4], xB[4];
         const int4 *cv = stream;
@@ -682,10 +700,10 @@ poisson_dataflow_pipe_kernel(const int2 *__restrict__ slabs, const long long *__
             float a0 = 0.f, a1 = 0.f, a2 = 0.f;
             for (int i = 0; i < no; ++i) {
                 dfp_issue<RPW, L1F>(cv + 2 * RPW, in, valB, xB);
-                dfp_consume<RPW>(cv, in, expect, valA, xA, a0, a1, a2, n_poll, n_badbatch, watchdog);
+                dfp_consume<RPW>(cv, in, expect, valA, xA, a0, a1, a2, n_poll, n_badbatch, watchdog, poll_sleep);
                 cv += 4 * RPW;
                 if (left > 0) { dfp_issue<RPW, L1F>(cv, in, valA, xA); --left; }
-                dfp_consume<RPW>(cv - 2 * RPW, in, expect, valB, xB, a0, a1, a2, n_poll, n_badbatch, watchdog);
+                dfp_consume<RPW>(cv - 2 * RPW, in, expect, valB, xB, a0, a1, a2, n_poll, n_badbatch, watchdog, poll_sleep);
             }
             const int type = sl.z & 0xff;
             if (type != kSlotNormal) {                       // warp-uniform: one long row dealt over the lane groups
@@ -700,7 +718,7 @@ poisson_dataflow_pipe_kernel(const int2 *__restrict__ slabs, const long long *__
                         volatile float *pb = s_part + ((size_t)(sl.w * 2 + (t & 1)) * LANES + li) * 4;
                         pb[0] = a0; pb[1] = a1; pb[2] = a2;
                         __threadfence_block();
-                        pb[3] = __uint_as_float(expect + 1u);
+                        pb[3] = __uint_as_float(2u + (unsigned)t);
                     }
                     continue;
                 }
@@ -710,7 +728,7 @@ poisson_dataflow_pipe_kernel(const int2 *__restrict__ slabs, const long long *__
                         volatile float *pb = s_part + ((size_t)((sl.w + q) * 2 + (t & 1)) * LANES + li) * 4;
                         unsigned spins = 0;
                         long long tw0 = 0;
-                        while (__float_as_uint(pb[3]) != expect + 1u && !poll_expired(watchdog, spins, tw0)) { }
+                        while (__float_as_uint(pb[3]) != 2u + (unsigned)t && !poll_expired(watchdog, spins, tw0)) { }
                         __threadfence_block();
                         a0 += pb[0]; a1 += pb[1]; a2 += pb[2];
                     }
@@ -723,7 +741,10 @@ poisson_dataflow_pipe_kernel(const int2 *__restrict__ slabs, const long long *__
                     const float4 b = __ldg(reinterpret_cast<const float4 *>(Db + (size_t)row * (ROWB / 4)) + li);
                     a0 += b.x; a1 += b.y; a2 += b.z;
                 }
-                st_chunk(out + (size_t)row * ROWB, a0, a1, a2, expect + 1u);
+#ifdef GLB_EXPERIMENT
+                if (!(poll_sleep & 0x80000000u) || a0 == 123.456f)
+#endif
+                st_chunk(out + (size_t)row * ROWB, a0, a1, a2, 2u + (unsigned)t);
             }
         }
     }
@@ -921,6 +942,7 @@ struct glb_poisson_plan {
     bool pipelined = true;              // dataflow kernel: software-pipelined gather stream (poisson_dataflow_pipe_kernel)
     unsigned *d_gate = nullptr;         // dataflow kernel: start gate counter
     int gate_every = 32;                // dataflow kernel: iterations between re-alignment gates (tuned at plan time)
+    unsigned poll_sleep = 0;            // dataflow kernel: nanoseconds a warp sleeps between re-polls of a stale batch
     bool has_long_rows = false;         // rows longer than a slice batch exist (dealt over whole warps)
     int scratch_row = 0;                // > 0: the label matrices carry that many rows behind row n-1, owned by the library
                                         // (padding targets of the slabs)
@@ -1048,6 +1070,8 @@ static int plan_try_dataflow(glb_poisson_plan *p, const std::vector<int> &h_rp, 
     if ((double)(n + kScratchRows) * rowb >= 4294967295.0 || n >= kRowSrcBit) return 0;
     p->l1_first = exp_env("GLB_POISSON_L1", 1) != 0;
     p->pipelined = exp_env("GLB_POISSON_PIPE", 1) != 0;
+    p->poll_sleep = (unsigned)exp_env("GLB_POISSON_SLEEP", 0) & 0xffffu;
+    p->poll_sleep |= (unsigned)exp_env("GLB_POISSON_FREE", 0) << 30;        // ceiling probes, -DGLB_EXPERIMENT only
     const int pad_to = p->pipelined ? 8 : 2;
     // padding entries gather a scratch row behind row n-1 (value 0, always ready).  Through L1 one row per CTA (it stays
     // resident in that SM's L1); at L2 they are dealt round robin so that no single L2 line takes all of them.
@@ -1343,11 +1367,11 @@ extern "C" GLB_API int glb_poisson_plan_create(glb_poisson_plan **plan, const in
         if (p->kind == GLB_POISSON_KIND_DATAFLOW && tune && forced_gate < 0) {
             // Measure, don't guess.  Gate period of the dataflow kernel: graphs with hub rows (every hub is a meeting
             // point of hundreds of producers) run best with a gate every few iterations, hub-free graphs with rare gates.
-            const int cand[3] = {32, 4, 1};
+            const int cand[4] = {0, 32, 4, 1};               // 0 = no gate after the start gate
             float best = 0.f;
             float *trial = nullptr;
             GLB_CUDA(cudaMalloc(&trial, plan_time_floats(p) * sizeof(float)));
-            for (int i = 0; i < 3 && rc == 0; ++i) {
+            for (int i = 0; i < 4 && rc == 0; ++i) {
                 p->gate_every = cand[i];
                 float ms = 0.f;
                 rc = plan_time(p, &ms, st, trial);
@@ -1494,7 +1518,7 @@ extern "C" GLB_API int glb_poisson_iterate(glb_poisson_plan *plan, const float *
         void *args[] = {(void *)&plan->d_slabs, (void *)&plan->d_slab_off, (void *)&plan->d_slots, (void *)&plan->d_slot_off,
                         (void *)&plan->d_slot_rows, (void *)&d_Db, (void *)&ring, (void *)&T,
                         (void *)&plan->cap_entries, (void *)&plan->cap_slots, (void *)&plan->cap_parts, (void *)&plan->d_stats,
-                        (void *)&gate, (void *)&gate_every, (void *)&watchdog};
+                        (void *)&gate, (void *)&gate_every, (void *)&watchdog, (void *)&plan->poll_sleep};
         if (plan->d_stats) GLB_CUDA(cudaMemsetAsync(plan->d_stats, 0, 4 * sizeof(unsigned long long), st));
         GLB_CUDA(cudaLaunchCooperativeKernel(plan->fn, dim3(plan->grid), dim3(plan->threads), args, plan->smem_bytes, st));
         if (launches) *launches += 2;

@@ -142,6 +142,57 @@ GLB_API int glb_poisson_mixing_T(const int32_t *d_rw_rowptr, const int32_t *d_rw
                          int *T_out, int *launches, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Row-slab Poisson iterate: one block of rows of u <- Db + P u per launch (the loop body
+ * graphlearning/ssl.py:668 for rows [r0, r1)), for graphs beyond the shared-memory kernels above and for the
+ * row-partitioned multi-GPU run (one slab per GPU, one process per GPU).  No counterpart in the reference, which is
+ * single process; what it replaces is scipy's csr_matvecs on the row block.
+ *
+ * Local index space of a slab: own rows 0..m-1, then its n_halo halo rows (label rows owned by other ranks that a
+ * column of the slab points to), then one all-zero scratch row.  glb_slab_create takes the slab's CSR in that space
+ * (h_col in [0, m + n_halo), fp32 values = D^-1 W^T rounded once, rows summed in stored order), the rows that must
+ * run first (h_boundary[r] != 0: rows a peer needs or rows that read halo rows; NULL = none) and, per row, the puts
+ * that deliver it (CSR over the m rows: h_send_ptr[m+1], peer rank, destination row in THAT peer's local space).
+ * HOST pointers; the device copy (sliced ELL, see csrc/slab.cu) is owned by the handle.
+ *
+ * Label matrices live in one "region" per rank: 64 uint32 flag words followed by three (m + n_halo + 1) x
+ * glb_padded_ld(c) fp32 buffers (version v of u in buffer v % 3).  The owner allocates its region with
+ * glb_ipc_alloc(glb_slab_region_bytes) and sends the 64-byte handle to its peers, which map it with glb_ipc_open
+ * (CUDA IPC; all GPUs on one NVLink/NVSwitch node).  glb_slab_attach binds the slab to the regions of all ranks
+ * (region_base[rank] = own region; neighbour_mask = ranks this one exchanges rows with, its own bit clear;
+ * world <= 16).  A single-GPU run is world = 1, neighbour_mask = 0.
+ *
+ * glb_slab_reset zeroes the three buffers (u_0 = 0, ssl.py:638); synchronise stream and ranks before
+ * glb_slab_iterate, which enqueues T launches of the step kernel: boundary rows first - they wait for the
+ * neighbours' flags of this version, are written locally AND into every peer that gathers them (stores to mapped
+ * peer memory over NVLink, from the kernel that computes them) and are followed by a release of this rank's flag in
+ * every neighbour's region - then the interior rows, which overlap the transfer.  d_Db: m x ld, plain layout.
+ * *result_buffer = T % 3.  glb_slab_check synchronises and reports GLB_E_TIMEOUT if a wait for a neighbour ran into
+ * its ~3 s watchdog.  glb_slab_pack / glb_slab_unpack convert the m own rows from / to m x c float64.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct glb_slab glb_slab;
+GLB_API int glb_slab_create(glb_slab **slab, const int32_t *h_rowptr, const int32_t *h_col, const float *h_val, int64_t m,
+                            int64_t n_halo, int c, const uint8_t *h_boundary, const int64_t *h_send_ptr,
+                            const int32_t *h_send_peer, const int32_t *h_send_dst, void *stream);
+GLB_API int glb_slab_destroy(glb_slab *slab);
+GLB_API int64_t glb_slab_rows(const glb_slab *slab);          /* m + n_halo + 1 */
+GLB_API int glb_slab_ld(const glb_slab *slab);
+GLB_API double glb_slab_fill(const glb_slab *slab);           /* nnz / stored entries of the sliced ELL */
+GLB_API int64_t glb_slab_region_bytes(const glb_slab *slab);
+GLB_API int glb_slab_attach(glb_slab *slab, int rank, int world, void *const *region_base, const int64_t *region_rows,
+                            uint32_t neighbour_mask);
+GLB_API int glb_slab_buffer(const glb_slab *slab, int v, float **d_buf);
+GLB_API int glb_slab_pack(const glb_slab *slab, const double *d_src, const double *d_deg, float *d_dst, void *stream);
+GLB_API int glb_slab_unpack(const glb_slab *slab, int v, double *d_dst, void *stream);
+GLB_API int glb_slab_reset(glb_slab *slab, void *stream);
+GLB_API int glb_slab_iterate(glb_slab *slab, const float *d_Db, int T, int *result_buffer, int *launches, void *stream);
+GLB_API int glb_slab_check(glb_slab *slab, void *stream);
+/* Peer-mappable device memory (cudaMalloc + cudaIpcGetMemHandle / cudaIpcOpenMemHandle).  handle64: 64 bytes. */
+GLB_API int glb_ipc_alloc(int64_t bytes, void **d_ptr, void *handle64);
+GLB_API int glb_ipc_open(const void *handle64, void **d_ptr);
+GLB_API int glb_ipc_close(void *d_ptr);
+GLB_API int glb_ipc_free(void *d_ptr);
+
+/* ---------------------------------------------------------------------------------------------
  * Host-buffer entry points: the gradient-descent branch of ssl.poisson._fit (graphlearning/ssl.py:615-670)
  * with HOST inputs/outputs in the reference's own dtypes - what the reference's Python binds in place of
  * its `while` loop.

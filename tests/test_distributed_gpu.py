@@ -1,5 +1,6 @@
-"""Row-partitioned Poisson iterate on the GPU: world size 1 in-process; world size 2 over NCCL when the box has
-two GPUs (skipped otherwise).  Results must be bitwise those of the single-GPU step kernel."""
+"""Row-partitioned Poisson iterate on the GPU: world size 1 in-process; world size 2 over NVLink / NCCL when the box has
+two GPUs (skipped otherwise).  The halo-put kernel (csrc/slab.cu), the all-gather baseline and the single-GPU step kernel
+must agree bitwise (same per-row arithmetic in the same order)."""
 import os
 import subprocess
 import sys
@@ -15,28 +16,72 @@ from test_poisson_gpu import random_knn_graph
 pytestmark = pytest.mark.gpu
 
 
-def test_world_size_one_equals_step_kernel():
+def _hub_graph(n, seed):
+    from scipy import sparse
+    rng = np.random.default_rng(seed)
+    W = random_knn_graph(n, 9, seed=seed).tolil()
+    for hub_node, deg in ((3, 700), (n - 2, 150)):                 # rows longer than a slice: dealt over a whole warp
+        hub = rng.choice(n, deg, replace=False)
+        hub = hub[hub != hub_node]
+        W[hub_node, hub] = 0.5; W[hub, hub_node] = 0.5
+    W = sparse.csr_matrix(W); W.eliminate_zeros()
+    return W
+
+
+@pytest.mark.parametrize("reorder", [False, True])
+@pytest.mark.parametrize("c", [10, 3, 40])
+def test_slab_kernel_world_one(reorder, c):
+    """glb_slab_* on one GPU (no peers): against the plain-C oracle and, without relabelling, bitwise against the step kernel."""
+    from graphlearning_b200 import device as gdev, distributed as gd
+    n = 6000
+    W = _hub_graph(n, seed=4)
+    src = np.random.default_rng(0).normal(size=(n, c)) * (np.random.default_rng(1).random((n, 1)) < 0.01)
+    pp = gd.PartitionedPoisson(W, rank=0, world=1, reorder=reorder, c=c)
+    u = pp.iterate(src, 17)
+    u_again = pp.iterate(src, 17)
+    u4 = pp.iterate(src, 4)
+    pp.close()
+    assert np.array_equal(u, u_again)
+    s = orc.poisson_gd_setup(W, np.array([0]), np.array([0]))
+    Db = (1.0 / (W * np.ones(n)))[:, None] * src
+    assert rel_err(u, c_oracle.poisson_iterate(s["P"], Db, 17)) <= 1e-5
+    assert rel_err(u4, c_oracle.poisson_iterate(s["P"], Db, 4)) <= 1e-5
+    if not reorder:
+        op = gdev.PoissonOperator(W, kind="step")
+        ref = op.unpack(op.iterate(op.source_to_Db(src), 17)[0], c).cpu().numpy()
+        assert np.array_equal(u, ref), float(np.abs(u - ref).max())
+
+
+def test_allgather_baseline_world_one():
     from graphlearning_b200 import device as gdev, distributed as gd
     W = random_knn_graph(6000, 9, seed=4)
     src = np.random.default_rng(0).normal(size=(6000, 10)) * (np.random.default_rng(1).random((6000, 1)) < 0.01)
-    pp = gd.PartitionedPoisson(W, rank=0, world=1)
+    pp = gd.AllGatherPoisson(W, rank=0, world=1)
     u = pp.iterate(src, 17)
     op = gdev.PoissonOperator(W, kind="step")
     ref = op.unpack(op.iterate(op.source_to_Db(src), 17)[0], 10).cpu().numpy()
     assert np.array_equal(u, ref), float(np.abs(u - ref).max())
-    s = orc.poisson_gd_setup(W, np.array([0]), np.array([0]))
-    oracle = c_oracle.poisson_iterate(s["P"], (1.0 / (W * np.ones(6000)))[:, None] * src, 17)
-    assert rel_err(u, oracle) <= 1e-5
 
 
-def test_world_size_two_over_nccl(tmp_path):
+@pytest.mark.parametrize("reorder", [1, 0])
+def test_world_size_two_over_nvlink(tmp_path, reorder):
+    """two ranks: halo rows put into the peer's label matrix by the kernel == all-gather baseline == one GPU, bitwise"""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
+    from graphlearning_b200 import distributed as gd
     out = tmp_path / "res.npz"
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-           "--master-port", "29671", os.path.join(ROOT, "tools", "bench_cfg5.py"), "--check", str(out), "--size", "20000", "--iters", "15"]
+           "--master-port", "29671", os.path.join(ROOT, "tools", "bench_cfg5.py"), "--check", str(out), "--size", "20000", "--iters", "15",
+           "--reorder", str(reorder)]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr
     z = np.load(out)
-    assert np.array_equal(z["u_partitioned"], z["u_single"])
+    assert np.array_equal(z["u_put"], z["u_allgather"])
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import bench_cfg5
+    W = bench_cfg5.build_graph(20000)
+    pp = gd.PartitionedPoisson(W, rank=0, world=1, reorder=bool(reorder), c=10)
+    single = pp.iterate(z["src"], 15)
+    pp.close()
+    assert np.array_equal(z["u_put"], single)

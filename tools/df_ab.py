@@ -33,15 +33,11 @@ ref50 = c_oracle.poisson_iterate(s["P"], np.asarray(s["Db"]), 50)
 b_iter = bench.algorithmic_bytes(n, W.nnz, 10)
 print("graph: n=%d nnz=%d max row %d; bytes/iteration %d" % (n, W.nnz, int(np.diff(W.indptr).max()), b_iter), flush=True)
 
-#          pipe l1  threads reorder
-configs = [(0, 0, 512, 0), (0, 1, 512, 0), (0, 0, 512, 1), (0, 1, 512, 1),
-           (1, 0, 512, 0), (1, 1, 512, 0), (1, 0, 512, 1), (1, 1, 512, 1),
-           (1, 1, 768, 1), (1, 0, 768, 0), (1, 1, 1024, 1), (1, 1, 512, 1)]
-first = None
-for pipe, l1, threads, reorder in configs:
-    os.environ["GLB_POISSON_PIPE"] = str(pipe)
-    os.environ["GLB_POISSON_L1"] = str(l1)
-    os.environ["GLB_POISSON_THREADS"] = str(threads)
+def run(label, env, reorder):
+    global first
+    for k in ("GLB_POISSON_PIPE", "GLB_POISSON_L1", "GLB_POISSON_THREADS", "GLB_POISSON_SLEEP", "GLB_POISSON_GATE_EVERY", "GLB_POISSON_FREE"):
+        os.environ.pop(k, None)
+    os.environ.update({k: str(v) for k, v in env.items()})
     try:
         op = gdev.PoissonOperator(W, kind="dataflow", reorder=bool(reorder))
         Db = op.source_to_Db(src)
@@ -59,9 +55,30 @@ for pipe, l1, threads, reorder in configs:
             first = res
         d = float((res - first).abs().max() / first.abs().max())
         best = min(times)
-        print("pipe=%d l1=%d threads=%-4d reorder=%d  gate=%-2d fill=%.3f  us/iter best %.3f median %.3f  frac %.3f  "
-              "err vs oracle@50 %.1e  diff vs first@1000 %.1e" % (pipe, l1, threads, reorder, op.gate(10), op.fill(10), best, float(np.median(times)),
-                                                                 b_iter * 1000 / (best * 1e-3) / 1e9 / 6451.8, err, d), flush=True)
-        del op, Db, u0, u1
+        print("%-44s reorder=%d gate=%-2d fill=%.3f  us/iter best %.3f median %.3f worst %.3f  frac %.3f  err@50 %.1e  diff@1000 %.1e" % (
+            label, reorder, op.gate(10), op.fill(10), best, float(np.median(times)), max(times),
+            b_iter * 1000 / (best * 1e-3) / 1e9 / 6451.8, err, d), flush=True)
     except Exception as e:
-        print("pipe=%d l1=%d threads=%d reorder=%d FAILED: %r" % (pipe, l1, threads, reorder, e), flush=True)
+        print("%s reorder=%d FAILED: %r" % (label, reorder, e), flush=True)
+
+
+first = None
+if "free" in sys.argv:
+    # ceiling probes: no synchronisation at all (free=1), and no stores either (free=3); results are wrong by design
+    for pipe, l1, reorder in ((1, 1, 1), (1, 1, 0), (1, 0, 0), (0, 0, 0), (0, 1, 1)):
+        for free in (0, 1, 3):
+            run("pipe=%d l1=%d free=%d" % (pipe, l1, free),
+                {"GLB_POISSON_PIPE": pipe, "GLB_POISSON_L1": l1, "GLB_POISSON_FREE": free, "GLB_POISSON_GATE_EVERY": 1 if free == 0 else 0}, reorder)
+elif "sleep" in sys.argv:
+    for pipe, l1, reorder in ((1, 1, 1), (1, 1, 0), (0, 0, 0), (0, 1, 1)):
+        for sleep in (0, 100, 400, 1500):
+            for gate in (0, 32, 4, 1):
+                run("pipe=%d l1=%d sleep=%d gate_forced=%d" % (pipe, l1, sleep, gate),
+                    {"GLB_POISSON_PIPE": pipe, "GLB_POISSON_L1": l1, "GLB_POISSON_SLEEP": sleep, "GLB_POISSON_GATE_EVERY": gate}, reorder)
+else:
+    #          pipe l1  threads reorder
+    configs = [(0, 0, 512, 0), (0, 1, 512, 0), (0, 0, 512, 1), (0, 1, 512, 1),
+               (1, 0, 512, 0), (1, 1, 512, 0), (1, 0, 512, 1), (1, 1, 512, 1),
+               (1, 1, 768, 1), (1, 0, 768, 0), (1, 1, 1024, 1), (1, 1, 512, 1)]
+    for pipe, l1, threads, reorder in configs:
+        run("pipe=%d l1=%d threads=%d" % (pipe, l1, threads), {"GLB_POISSON_PIPE": pipe, "GLB_POISSON_L1": l1, "GLB_POISSON_THREADS": threads}, reorder)
