@@ -6,9 +6,11 @@ import sys as _sys
 
 import graphlearning_b200 as _b
 
-from graphlearning_b200 import clustering, ssl, trainsets, utils, weightmatrix  # noqa: F401
+from graphlearning_b200 import clustering, datasets, ssl, trainsets, utils, weightmatrix  # noqa: F401
+from graphlearning_b200 import graph as _graph_module
 from graphlearning_b200.graph import graph  # noqa: F401
 
-for _name in ("clustering", "ssl", "trainsets", "utils", "weightmatrix"):
+for _name in ("clustering", "datasets", "ssl", "trainsets", "utils", "weightmatrix"):
     _sys.modules[__name__ + "." + _name] = getattr(_b, _name)
+_sys.modules[__name__ + ".graph"] = _graph_module          # `import graphlearning.graph` resolves to the module, gl.graph to the class
 __version__ = _b.__version__

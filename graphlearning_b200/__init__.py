@@ -13,6 +13,7 @@ libglb200.so (include/glb200.h).  There is no CPU fallback: without the library 
 """
 from . import utils        # noqa: F401
 from . import trainsets    # noqa: F401
+from . import datasets     # noqa: F401
 from . import weightmatrix  # noqa: F401
 from . import graph as _graph_module
 from . import ssl          # noqa: F401

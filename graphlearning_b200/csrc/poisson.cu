@@ -559,49 +559,46 @@ poisson_dataflow_kernel(const int2 *__restrict__ slabs, const long long *__restr
 // ------------------------------------------------------------------------------------------------
 // K3p: the same dataflow iterate with a software-pipelined gather stream
 // ------------------------------------------------------------------------------------------------
-// What bounds the batch kernel above (ncu, r1): one warp has ONE batch of gathers in flight, waits for it (an L2 round
-// trip of ~500-1000 cycles under load), consumes it, and only then issues the next - 11 serialised round trips plus ~740
-// dependent instructions per warp and iteration with 4 warps per scheduler; the LSU pipe idles a third of the time.
-// Here every warp walks ONE contiguous stream of "octets" (8 entries per lane group, 512 bytes, all slots of the warp
-// back to back, slice widths padded to a multiple of 8 with always-ready scratch-row entries) with two register sets of
-// four gathers: while set A is validated and consumed set B is in flight and vice versa, across slot boundaries, so 4-8
-// gathers per lane are outstanding all the time and the instruction stream overlaps the memory latency.
+// What bounds the batch kernel above (ncu, r1/r2): one warp has ONE batch of gathers in flight, waits for it (an L2 round
+// trip of ~500-1000 cycles under load), consumes it, and only then issues the next; the LSU data pipe (one 128-byte line
+// per cycle and SM, i.e. one label row per cycle) idles a third of the time.  Here every warp walks ONE contiguous
+// stream of entry PAIRS (all slots of the warp back to back, slice widths padded to even only) through a ring of four
+// register slots: pair p+4 is issued as soon as pair p has been validated and consumed, across slot boundaries, so 6-8
+// gathers per lane are outstanding all the time and the instruction stream overlaps the memory latency.  With every
+// synchronisation removed (GLB_POISSON_FREE probe of the experiment build) the data pipe runs at 88 % of its peak.
 template <int RPW, bool L1F>
-__device__ __forceinline__ void dfp_issue(const int4 *cv, const char *in, float (&val)[4], uint4 (&x)[4])
+__device__ __forceinline__ void dfp_issue(const int4 *cv, const char *in, float (&val)[2], uint4 (&x)[2])
 {
-    const int4 e0 = cv[0], e1 = cv[RPW];                      // two pairs = four (offset, value) entries of this lane group
-    val[0] = __int_as_float(e0.y); val[1] = __int_as_float(e0.w);
-    val[2] = __int_as_float(e1.y); val[3] = __int_as_float(e1.w);
-    const unsigned off[4] = {(unsigned)e0.x, (unsigned)e0.z, (unsigned)e1.x, (unsigned)e1.z};
-#pragma unroll
-    for (int i = 0; i < 4; ++i) x[i] = L1F ? ld_chunk_l1(df_addr(in, off[i])) : ld_chunk(df_addr(in, off[i]));
+    const int4 e = cv[0];                                     // one pair = two (offset, value) entries of this lane group
+    val[0] = __int_as_float(e.y); val[1] = __int_as_float(e.w);
+    x[0] = L1F ? ld_chunk_l1(df_addr(in, (unsigned)e.x)) : ld_chunk(df_addr(in, (unsigned)e.x));
+    x[1] = L1F ? ld_chunk_l1(df_addr(in, (unsigned)e.z)) : ld_chunk(df_addr(in, (unsigned)e.z));
 }
 
-// cv: where dfp_issue read the entries of this set (the offsets are re-read from shared memory on the rare re-poll path
+// cv: where dfp_issue read the entries of this pair (the offsets are re-read from shared memory on the rare re-poll path
 // instead of being held in registers)
-template <int RPW>
-__device__ __forceinline__ void dfp_consume(const int4 *cv, const char *in, unsigned expect, const float (&val)[4],
-                                            uint4 (&x)[4], float &a0, float &a1, float &a2, unsigned &n_poll,
+__device__ __forceinline__ void dfp_consume(const int4 *cv, const char *in, unsigned expect, const float (&val)[2],
+                                            uint4 (&x)[2], float &a0, float &a1, float &a2, unsigned &n_poll,
                                             unsigned &n_badbatch, unsigned *watchdog, unsigned poll_sleep)
 {
-    bool ok = (x[0].w >= expect) & (x[1].w >= expect) & (x[2].w >= expect) & (x[3].w >= expect);
+    bool ok = (x[0].w >= expect) & (x[1].w >= expect);
     if (!ok) {                                           // a producer is still behind (or L1 held an old line): re-poll at L2
-        const int4 e0 = cv[0], e1 = cv[RPW];
-        const unsigned off[4] = {(unsigned)e0.x, (unsigned)e0.z, (unsigned)e1.x, (unsigned)e1.z};
+        const int4 e = cv[0];
+        const unsigned off[2] = {(unsigned)e.x, (unsigned)e.z};
         unsigned spins = 0;
         long long t0 = 0;
         do {
             ++n_badbatch;
             if (poll_expired(watchdog, spins, t0)) break;
-            if ((poll_sleep & 0xffffu) && spins > 1) __nanosleep(poll_sleep & 0xffffu);   // this warp is ahead of its producers: leave L2 and the LSU to them
+            if ((poll_sleep & 0xffffu) && spins > 1) __nanosleep(poll_sleep & 0xffffu);   // this warp is ahead of its producers
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < 2; ++i)
                 if (x[i].w < expect) { x[i] = ld_chunk(df_addr(in, off[i])); ++n_poll; }
-            ok = (x[0].w >= expect) & (x[1].w >= expect) & (x[2].w >= expect) & (x[3].w >= expect);
+            ok = (x[0].w >= expect) & (x[1].w >= expect);
         } while (!ok);
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < 2; ++i) {
         a0 = fmaf(val[i], __uint_as_float(x[i].x), a0);
         a1 = fmaf(val[i], __uint_as_float(x[i].y), a1);
         a2 = fmaf(val[i], __uint_as_float(x[i].z), a2);
@@ -659,8 +656,8 @@ poisson_dataflow_pipe_kernel(const int2 *__restrict__ slabs, const long long *__
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane / LANES, li = lane % LANES;
     const int nsw = (nslots - warp + NW - 1) / NW;                       // slots of this warp: k * NW + warp
-    int n_oct = 0;                                                       // octets of this warp's stream
-    for (int k = 0; k < nsw; ++k) n_oct += (s_slot[k * NW + warp].y + 7) >> 3;
+    int n_pairs = 0;                                                     // pairs of this warp's stream
+    for (int k = 0; k < nsw; ++k) n_pairs += (s_slot[k * NW + warp].y + 1) >> 1;
     const int4 *stream = nsw > 0 ? reinterpret_cast<const int4 *>(s_cv + s_slot[warp].x) + g : nullptr;
     unsigned n_poll = 0, n_badbatch = 0;
     const long long clk0 = clock64();
@@ -676,7 +673,7 @@ poisson_dataflow_pipe_kernel(const int2 *__restrict__ slabs, const long long *__
             }
             __syncthreads();
         }
-        if (n_oct == 0) continue;
+        if (nsw == 0) continue;
         const int vi = t & (kRing - 1), vo = (t + 1) & (kRing - 1);
         const char *in = reinterpret_cast<const char *>(vi == 0 ? ring.b[0] : vi == 1 ? ring.b[1] : vi == 2 ? ring.b[2] : ring.b[3]) + li * 16;
         char *out = reinterpret_cast<char *>(vo == 0 ? ring.b[0] : vo == 1 ? ring.b[1] : vo == 2 ? ring.b[2] : ring.b[3]) + li * 16;
@@ -687,25 +684,21 @@ poisson_dataflow_pipe_kernel(const int2 *__restrict__ slabs, const long long *__
 #else
         const unsigned expect = 1u + (unsigned)t;
 #endif
-        float valA[4], valB[4];
-        uint4 xA[4], xB[4];
-        const int4 *cv = stream;
-        int left = n_oct;                                    // octets not yet issued (set A)
-        dfp_issue<RPW, L1F>(cv, in, valA, xA);
-        --left;
-        for (int k = 0; k < nsw; ++k) {
+        float v0[2], v1[2], v2[2], v3[2];
+        uint4 x0[2], x1[2], x2[2], x3[2];
+        if (0 < n_pairs) dfp_issue<RPW, L1F>(stream, in, v0, x0);
+        if (1 < n_pairs) dfp_issue<RPW, L1F>(stream + RPW, in, v1, x1);
+        if (2 < n_pairs) dfp_issue<RPW, L1F>(stream + 2 * RPW, in, v2, x2);
+        if (3 < n_pairs) dfp_issue<RPW, L1F>(stream + 3 * RPW, in, v3, x3);
+        int p = 0, k = 0;                                    // pair being consumed, slot it belongs to
+        int4 sl = s_slot[warp];                              // (first entry, slice width, type | parts << 8, partial index)
+        int left = (sl.y + 1) >> 1;                          // pairs of slot k not yet consumed
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+        // finish slot k (sum of a long row's pieces, source term, store) and move to the next one
+        auto finish = [&]() {
             const int s = k * NW + warp;
-            const int4 sl = s_slot[s];                       // (first entry, slice width, type | parts << 8, partial index)
-            const int no = (sl.y + 7) >> 3;
-            float a0 = 0.f, a1 = 0.f, a2 = 0.f;
-            for (int i = 0; i < no; ++i) {
-                dfp_issue<RPW, L1F>(cv + 2 * RPW, in, valB, xB);
-                dfp_consume<RPW>(cv, in, expect, valA, xA, a0, a1, a2, n_poll, n_badbatch, watchdog, poll_sleep);
-                cv += 4 * RPW;
-                if (left > 0) { dfp_issue<RPW, L1F>(cv, in, valA, xA); --left; }
-                dfp_consume<RPW>(cv - 2 * RPW, in, expect, valB, xB, a0, a1, a2, n_poll, n_badbatch, watchdog, poll_sleep);
-            }
             const int type = sl.z & 0xff;
+            bool store = true;
             if (type != kSlotNormal) {                       // warp-uniform: one long row dealt over the lane groups
 #pragma unroll
                 for (int o = LANES; o < 32; o <<= 1) {
@@ -720,9 +713,8 @@ poisson_dataflow_pipe_kernel(const int2 *__restrict__ slabs, const long long *__
                         __threadfence_block();
                         pb[3] = __uint_as_float(2u + (unsigned)t);
                     }
-                    continue;
-                }
-                if (type == kSlotOwner) {
+                    store = false;
+                } else if (type == kSlotOwner) {
                     const int nparts = sl.z >> 8;
                     for (int q = 0; q < nparts; ++q) {       // partial sums of the other warps, fixed order
                         volatile float *pb = s_part + ((size_t)((sl.w + q) * 2 + (t & 1)) * LANES + li) * 4;
@@ -735,7 +727,7 @@ poisson_dataflow_pipe_kernel(const int2 *__restrict__ slabs, const long long *__
                 }
             }
             const int rinfo = s_rows[s * RPW + g];
-            if (rinfo >= 0) {
+            if (store && rinfo >= 0) {
                 const unsigned row = (unsigned)(rinfo & (kRowSrcBit - 1));
                 if (rinfo & kRowSrcBit) {
                     const float4 b = __ldg(reinterpret_cast<const float4 *>(Db + (size_t)row * (ROWB / 4)) + li);
@@ -746,7 +738,27 @@ poisson_dataflow_pipe_kernel(const int2 *__restrict__ slabs, const long long *__
 #endif
                 st_chunk(out + (size_t)row * ROWB, a0, a1, a2, 2u + (unsigned)t);
             }
+            a0 = a1 = a2 = 0.f;
+            ++k;
+            if (k < nsw) { sl = s_slot[k * NW + warp]; left = (sl.y + 1) >> 1; }
+        };
+        while (k < nsw && left == 0) finish();               // slots of empty rows
+#define GLB_DFP_STEP(V, X)                                                                                              \
+        {                                                                                                               \
+            if (p >= n_pairs) break;                                                                                    \
+            const int4 *cv = stream + (size_t)p * RPW;                                                                  \
+            dfp_consume(cv, in, expect, V, X, a0, a1, a2, n_poll, n_badbatch, watchdog, poll_sleep);                    \
+            if (p + 4 < n_pairs) dfp_issue<RPW, L1F>(cv + 4 * RPW, in, V, X);                                           \
+            ++p;                                                                                                        \
+            if (--left == 0) { finish(); while (k < nsw && left == 0) finish(); }                                       \
         }
+        for (;;) {
+            GLB_DFP_STEP(v0, x0)
+            GLB_DFP_STEP(v1, x1)
+            GLB_DFP_STEP(v2, x2)
+            GLB_DFP_STEP(v3, x3)
+        }
+#undef GLB_DFP_STEP
     }
     if (stats) {
         atomicAdd(stats + 0, (unsigned long long)n_poll);
@@ -1072,7 +1084,7 @@ static int plan_try_dataflow(glb_poisson_plan *p, const std::vector<int> &h_rp, 
     p->pipelined = exp_env("GLB_POISSON_PIPE", 1) != 0;
     p->poll_sleep = (unsigned)exp_env("GLB_POISSON_SLEEP", 0) & 0xffffu;
     p->poll_sleep |= (unsigned)exp_env("GLB_POISSON_FREE", 0) << 30;        // ceiling probes, -DGLB_EXPERIMENT only
-    const int pad_to = p->pipelined ? 8 : 2;
+    const int pad_to = 2;
     // padding entries gather a scratch row behind row n-1 (value 0, always ready).  Through L1 one row per CTA (it stays
     // resident in that SM's L1); at L2 they are dealt round robin so that no single L2 line takes all of them.
     unsigned pad_next = 0;
@@ -1125,7 +1137,7 @@ static int plan_try_dataflow(glb_poisson_plan *p, const std::vector<int> &h_rp, 
             sl.type = kSlotNormal;
             sl.L = h_rp[order[k0] + 1] - h_rp[order[k0]];
             for (int g = 0; g < rpw; ++g) sl.rows[g] = k0 + g < order.size() ? order[k0 + g] : -1;
-            sl.cost = p->pipelined ? (sl.L + 7) / 8 + 1 : (sl.L + 15) / 16 + 1;
+            sl.cost = p->pipelined ? (sl.L + 1) / 2 + 2 : (sl.L + 15) / 16 + 1;
             cta_slots.push_back(sl);
         }
         // long rows: one warp-wide slot per piece of at most part_max nonzeros
@@ -1151,7 +1163,7 @@ static int plan_try_dataflow(glb_poisson_plan *p, const std::vector<int> &h_rp, 
                     sl.type = kSlotPart;
                     sl.pbuf = nparts_cta + q - 1;
                 }
-                sl.cost = (p->pipelined ? (sl.L + 7) / 8 : (sl.L + 15) / 16) + 1 + (q == 0 ? m - 1 : 0);
+                sl.cost = (p->pipelined ? (sl.L + 1) / 2 + 1 : (sl.L + 15) / 16) + 1 + (q == 0 ? m - 1 : 0);
                 cta_slots.push_back(sl);
             }
             nparts_cta += m - 1;
@@ -1186,7 +1198,7 @@ static int plan_try_dataflow(glb_poisson_plan *p, const std::vector<int> &h_rp, 
                 const Slot &sl = cta_slots[per_warp[w][k]];
                 slot_first[k * nw + w] = (int)((long long)slab.size() - base0);
                 // entries in pairs: entry j of lane group g at (j/2 * rpw + g) * 2 + (j & 1); width rounded up to a
-                // multiple of pad_to (2: pairs; 8: the octets of the pipelined kernel) with always-ready scratch entries
+                // multiple of pad_to (pairs) with always-ready scratch entries
                 const int Lst = (sl.L + pad_to - 1) / pad_to * pad_to;
                 const size_t s0 = slab.size();
                 slab.resize(s0 + (size_t)Lst * rpw);

@@ -10,15 +10,16 @@
 //     one all-zero scratch row (padding target).  Label matrices are (m + H + 1) x ld fp32, ld = glb_padded_ld(c),
 //     a row of c = 10 classes = one 64-byte piece of a 128-byte line.
 //   * sliced ELL: slices of 32/LANES rows (LANES lanes own one row, 16 bytes each), rows sorted by length inside
-//     windows of 256 rows so that locality survives, slice width padded to a multiple of 8 ("octets"); entries
-//     (byte offset of the column's label row, fp32 value) interleaved so that one warp-wide 16-byte load fetches two
-//     entries of every lane group from one contiguous 128-byte run.  All slices back to back = ONE stream per warp.
+//     windows of 256 rows so that locality survives, slice width padded to even; entries (byte offset of the column's
+//     label row, fp32 value) in PAIRS, interleaved so that one warp-wide 16-byte load fetches one pair of every lane
+//     group from one contiguous 128-byte run.  All slices back to back = ONE stream of pairs per warp.
 //   * boundary rows (rows a peer needs, or rows that read halo rows) come first, interior rows after them.
 //
 // Kernel (slab_step_kernel, one launch per iteration): 8 warps x 4 slices per CTA.  Lane 0 of every warp brings the
 // warp's part of the entry stream into shared memory with ONE bulk copy (cp.async.bulk -> mbarrier, TMA unit, SASS
-// UBLKCP), then the warp walks it with two register sets of four label-row gathers in flight (the same software pipeline
-// as poisson_dataflow_pipe_kernel); gathers go through L1 (a locality ordering makes neighbouring rows share most of
+// UBLKCP), then the warp walks it through a ring of four pair slots - pair p+4 is issued when pair p has been consumed,
+// across slice boundaries, 6-8 label-row gathers per lane in flight (the same software pipeline as
+// poisson_dataflow_pipe_kernel); gathers go through L1 (a locality ordering makes neighbouring rows share most of
 // their columns).  Boundary CTAs (lowest block indices, scheduled first) wait until the neighbours' halo rows of this
 // version have arrived (one flag per neighbour in this rank's memory, acquire at system scope), write every finished row
 // to the local matrix AND to each peer that needs it (plain 16-byte stores to peer memory mapped through CUDA IPC), and
@@ -111,21 +112,17 @@ __device__ __forceinline__ const char *slab_addr(const char *base, unsigned off)
     return reinterpret_cast<const char *>(a);
 }
 
-template <int RPW>
-__device__ __forceinline__ void slab_issue(const int4 *cv, const char *in, float (&val)[4], float4 (&x)[4])
+__device__ __forceinline__ void slab_issue(const int4 *cv, const char *in, float (&val)[2], float4 (&x)[2])
 {
-    const int4 e0 = cv[0], e1 = cv[RPW];
-    val[0] = __int_as_float(e0.y); val[1] = __int_as_float(e0.w);
-    val[2] = __int_as_float(e1.y); val[3] = __int_as_float(e1.w);
-    x[0] = ld_row_l1(slab_addr(in, (unsigned)e0.x));
-    x[1] = ld_row_l1(slab_addr(in, (unsigned)e0.z));
-    x[2] = ld_row_l1(slab_addr(in, (unsigned)e1.x));
-    x[3] = ld_row_l1(slab_addr(in, (unsigned)e1.z));
+    const int4 e = cv[0];                                    // one pair = two (offset, value) entries of this lane group
+    val[0] = __int_as_float(e.y); val[1] = __int_as_float(e.w);
+    x[0] = ld_row_l1(slab_addr(in, (unsigned)e.x));
+    x[1] = ld_row_l1(slab_addr(in, (unsigned)e.z));
 }
-__device__ __forceinline__ void slab_consume(const float (&val)[4], const float4 (&x)[4], float4 &acc)
+__device__ __forceinline__ void slab_consume(const float (&val)[2], const float4 (&x)[2], float4 &acc)
 {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < 2; ++i) {
         acc.x = fmaf(val[i], x[i].x, acc.x);
         acc.y = fmaf(val[i], x[i].y, acc.y);
         acc.z = fmaf(val[i], x[i].z, acc.z);
@@ -134,7 +131,7 @@ __device__ __forceinline__ void slab_consume(const float (&val)[4], const float4
 }
 
 template <int LANES>
-__global__ void __launch_bounds__(kSlabWarps * 32)
+__global__ void __launch_bounds__(kSlabWarps * 32, 3)
 slab_step_kernel(const SlabParams p)
 {
     constexpr int RPW = 32 / LANES;
@@ -175,25 +172,22 @@ slab_step_kernel(const SlabParams p)
         __syncthreads();
     }
     __syncwarp();
-    if (f1 > f0) {
-        mbar_wait(&bars[warp], 0);
+    if (s1 > s0) {
+        if (f1 > f0) mbar_wait(&bars[warp], 0);
         const char *in = reinterpret_cast<const char *>(p.u_in) + li * 16;
-        const int4 *cv = stream + g;
-        int left = (f1 - f0) / (4 * RPW);                    // octets of this warp's stream
-        float valA[4], valB[4];
-        float4 xA[4], xB[4];
-        slab_issue<RPW>(cv, in, valA, xA);
-        --left;
-        for (int s = s0; s < s1; ++s) {
-            const int no = (p.slice_first[s + 1] - p.slice_first[s]) / (4 * RPW);
-            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int i = 0; i < no; ++i) {
-                slab_issue<RPW>(cv + 2 * RPW, in, valB, xB);
-                slab_consume(valA, xA, acc);
-                cv += 4 * RPW;
-                if (left > 0) { slab_issue<RPW>(cv, in, valA, xA); --left; }
-                slab_consume(valB, xB, acc);
-            }
+        const int4 *cv0 = stream + g;
+        const int n_pairs = (f1 - f0) / RPW;                 // pairs of this warp's stream
+        float v0[2], v1[2], v2[2], v3[2];
+        float4 x0[2], x1[2], x2[2], x3[2];
+        if (0 < n_pairs) slab_issue(cv0, in, v0, x0);
+        if (1 < n_pairs) slab_issue(cv0 + RPW, in, v1, x1);
+        if (2 < n_pairs) slab_issue(cv0 + 2 * RPW, in, v2, x2);
+        if (3 < n_pairs) slab_issue(cv0 + 3 * RPW, in, v3, x3);
+        int q = 0, s = s0;                                   // pair being consumed, slice it belongs to
+        int left = (p.slice_first[s0 + 1] - f0) / RPW;       // pairs of slice s not yet consumed
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        // finish slice s (sum of a long row's pieces, source term, store, puts) and move to the next one
+        auto finish = [&]() {
             int rinfo = p.slice_rows[(size_t)s * RPW + g];
             const int r0info = __shfl_sync(0xffffffffu, rinfo, 0);
             if (r0info >= 0 && (r0info & kSlabLongBit)) {    // warp-uniform: one long row dealt over the lane groups
@@ -215,13 +209,32 @@ slab_step_kernel(const SlabParams p)
                 *reinterpret_cast<float4 *>(reinterpret_cast<char *>(p.u_out) + (size_t)row * ROWB + li * 16) = acc;
                 if (boundary && p.send_ptr) {                // put the row into every peer that gathers it
                     const long long q0 = p.send_ptr[(size_t)s * RPW + g], q1 = p.send_ptr[(size_t)s * RPW + g + 1];
-                    for (long long q = q0; q < q1; ++q) {
-                        const int2 e = p.send_ent[q];
+                    for (long long k = q0; k < q1; ++k) {
+                        const int2 e = p.send_ent[k];
                         *reinterpret_cast<float4 *>(reinterpret_cast<char *>(p.peer_out[e.x]) + (size_t)(unsigned)e.y * ROWB + li * 16) = acc;
                     }
                 }
             }
+            acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            ++s;
+            if (s < s1) left = (p.slice_first[s + 1] - p.slice_first[s]) / RPW;
+        };
+        while (s < s1 && left == 0) finish();                // slices of empty rows
+#define GLB_SLAB_STEP(V, X)                                                                          \
+        {                                                                                            \
+            if (q >= n_pairs) break;                                                                 \
+            slab_consume(V, X, acc);                                                                 \
+            if (q + 4 < n_pairs) slab_issue(cv0 + (size_t)(q + 4) * RPW, in, V, X);                  \
+            ++q;                                                                                     \
+            if (--left == 0) { finish(); while (s < s1 && left == 0) finish(); }                     \
         }
+        for (;;) {
+            GLB_SLAB_STEP(v0, x0)
+            GLB_SLAB_STEP(v1, x1)
+            GLB_SLAB_STEP(v2, x2)
+            GLB_SLAB_STEP(v3, x3)
+        }
+#undef GLB_SLAB_STEP
     }
     if (boundary && p.nbr_mask) {
         __syncthreads();                                     // every put of this CTA is issued ...
@@ -370,7 +383,7 @@ extern "C" GLB_API int glb_slab_create(glb_slab **out, const int32_t *h_rowptr, 
     const int nslices = (int)slices.size();
     std::vector<int> slice_first((size_t)nslices + 1, 0), slice_rows((size_t)nslices * rpw, -1);
     for (int s = 0; s < nslices; ++s) {
-        const int Lst = (slices[s].L + 7) / 8 * 8;
+        const int Lst = (slices[s].L + 1) / 2 * 2;
         slice_first[s + 1] = slice_first[s] + Lst / 2 * rpw;
         stored += (int64_t)Lst * rpw;
         GLB_CHECK_ARG(slice_first[s + 1] >= slice_first[s], "slab too large (entry index overflows 32 bits)");
@@ -447,6 +460,10 @@ extern "C" GLB_API int glb_slab_create(glb_slab **out, const int32_t *h_rowptr, 
     s->fill = stored ? (double)nnz / (double)stored : 1.0;
     s->fn = slab_pick(lanes);
     GLB_CUDA(cudaFuncSetAttribute(s->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes));
+    {   // shared-memory carve-out for three resident CTAs (80 registers x 256 threads); the rest of the 228 KB stays L1 for the label-row gathers
+        const size_t want = std::min<size_t>(3 * (s->smem_bytes + 1024), (size_t)max_smem);
+        cudaFuncSetAttribute(s->fn, cudaFuncAttributePreferredSharedMemoryCarveout, (int)std::min<size_t>(100, (want * 100 + max_smem - 1) / max_smem));
+    }
     GLB_CUDA(cudaMalloc(&s->d_ent, sizeof(int4) * std::max<size_t>(ent.size(), 1)));
     GLB_CUDA(cudaMalloc(&s->d_slice_first, sizeof(int) * (nslices + 1)));
     GLB_CUDA(cudaMalloc(&s->d_slice_rows, sizeof(int) * std::max<size_t>(slice_rows.size(), 1)));

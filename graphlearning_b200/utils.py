@@ -7,6 +7,22 @@ import numpy as np
 from scipy import sparse
 
 
+def class_priors(labels):
+    """Fraction of the (non-negative) labels in each class.  Reference graphlearning/utils.py:117-142."""
+    labels = np.asarray(labels)
+    classes = np.unique(labels)
+    classes = classes[classes >= 0]
+    return np.array([np.sum(labels == cls) for cls in classes]) / np.sum(labels >= 0)
+
+
+def numpy_load(file, field):
+    """One array of an .npz file.  Reference graphlearning/utils.py:219-239 (sys.exit there, an exception here)."""
+    try:
+        return np.load(file, allow_pickle=True)[field]
+    except Exception as e:
+        raise OSError("Error: Cannot open " + str(file) + ".") from e
+
+
 def labels_to_onehot(labels, k=None):
     """One-hot encoding, width max(k, max(label)+1).  Reference graphlearning/utils.py:536-572."""
     labels = np.asarray(labels)

@@ -31,7 +31,8 @@ def _hub_graph(n, seed):
 @pytest.mark.parametrize("reorder", [False, True])
 @pytest.mark.parametrize("c", [10, 3, 40])
 def test_slab_kernel_world_one(reorder, c):
-    """glb_slab_* on one GPU (no peers): against the plain-C oracle and, without relabelling, bitwise against the step kernel."""
+    """glb_slab_* on one GPU (no peers): against the plain-C oracle and bitwise against the step kernel on the same fp32 P
+    (the all-gather baseline with one rank: same host-built slab, poisson_step_kernel)."""
     from graphlearning_b200 import device as gdev, distributed as gd
     n = 6000
     W = _hub_graph(n, seed=4)
@@ -46,10 +47,13 @@ def test_slab_kernel_world_one(reorder, c):
     Db = (1.0 / (W * np.ones(n)))[:, None] * src
     assert rel_err(u, c_oracle.poisson_iterate(s["P"], Db, 17)) <= 1e-5
     assert rel_err(u4, c_oracle.poisson_iterate(s["P"], Db, 4)) <= 1e-5
-    if not reorder:
-        op = gdev.PoissonOperator(W, kind="step")
-        ref = op.unpack(op.iterate(op.source_to_Db(src), 17)[0], c).cpu().numpy()
-        assert np.array_equal(u, ref), float(np.abs(u - ref).max())
+    # without rows longer than a slice (those are summed by a whole warp, in another order) the arithmetic is the step kernel's
+    W2 = random_knn_graph(n, 9, seed=5)
+    pp = gd.PartitionedPoisson(W2, rank=0, world=1, reorder=reorder, c=c)
+    u2 = pp.iterate(src, 17)
+    pp.close()
+    ref = gd.AllGatherPoisson(W2, rank=0, world=1, reorder=reorder).iterate(src, 17)
+    assert np.array_equal(u2, ref), float(np.abs(u2 - ref).max())
 
 
 def test_allgather_baseline_world_one():
@@ -60,7 +64,9 @@ def test_allgather_baseline_world_one():
     u = pp.iterate(src, 17)
     op = gdev.PoissonOperator(W, kind="step")
     ref = op.unpack(op.iterate(op.source_to_Db(src), 17)[0], 10).cpu().numpy()
-    assert np.array_equal(u, ref), float(np.abs(u - ref).max())
+    # P is rounded to fp32 from D^-1 * w on the host here (as the reference forms it, ssl.py:634-635) and from w / d on the
+    # device there: the last bit of a few entries differs
+    assert rel_err(u, ref) <= 1e-6
 
 
 @pytest.mark.parametrize("reorder", [1, 0])

@@ -77,8 +77,10 @@ elif "sleep" in sys.argv:
                     {"GLB_POISSON_PIPE": pipe, "GLB_POISSON_L1": l1, "GLB_POISSON_SLEEP": sleep, "GLB_POISSON_GATE_EVERY": gate}, reorder)
 else:
     #          pipe l1  threads reorder
-    configs = [(0, 0, 512, 0), (0, 1, 512, 0), (0, 0, 512, 1), (0, 1, 512, 1),
-               (1, 0, 512, 0), (1, 1, 512, 0), (1, 0, 512, 1), (1, 1, 512, 1),
-               (1, 1, 768, 1), (1, 0, 768, 0), (1, 1, 1024, 1), (1, 1, 512, 1)]
+    configs = [(0, 0, 512, 0), (1, 1, 512, 0), (1, 1, 512, 1), (1, 1, 768, 0), (1, 1, 768, 1), (1, 1, 1024, 1), (1, 0, 512, 0), (1, 0, 768, 0)]
     for pipe, l1, threads, reorder in configs:
         run("pipe=%d l1=%d threads=%d" % (pipe, l1, threads), {"GLB_POISSON_PIPE": pipe, "GLB_POISSON_L1": l1, "GLB_POISSON_THREADS": threads}, reorder)
+    for threads in (512, 768):
+        for free in (1, 3):
+            run("pipe=1 l1=1 threads=%d free=%d" % (threads, free), {"GLB_POISSON_PIPE": 1, "GLB_POISSON_L1": 1, "GLB_POISSON_THREADS": threads,
+                                                                     "GLB_POISSON_FREE": free, "GLB_POISSON_GATE_EVERY": 0}, 1)
