@@ -38,9 +38,9 @@ def build_workload(seed=0):
     """The synthetic 70k-node graph BASELINE.md section 2 measured the reference on ("Poisson GD iterate, synthetic":
     70 000 points, 10 Gaussian blobs in R^8, k=10, nnz = 1 004 292 - within 1 % of the real MNIST graph's 1 014 572
     that section 3 quotes the roofline on), built with scipy's cKDTree exactly as the reference does for low d
-    (~10 s, untimed setup, identical for both arms).  The graph the GPU kNN search builds from 128-d features is
-    measured too (`other_rows`): isotropic 128-d Gaussians give hub nodes with > 1000 neighbours, which real
-    kNN graphs (MNIST: max 45) do not have."""
+    (~10 s, untimed setup, identical for both arms).  The literal config-2 graph (128-d features, built by the GPU kNN
+    search) is measured too and reported as `cfg2_literal_128d`: isotropic 128-d Gaussians give hub nodes with > 1000
+    neighbours, which real kNN graphs (MNIST: max 45) do not have."""
     from oracle import gl_oracle as orc
     from scipy import sparse
     X, labels = orc.synthetic_blobs(N_NODES, 8, c=N_CLASSES, seed=seed)
@@ -49,45 +49,87 @@ def build_workload(seed=0):
     return sparse.csr_matrix(W), labels
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel (ncu --set full,
-# profiles/r1_dataflow_v2_nopoll_ncu_details.txt / r1_barrier_ncu_details.txt)
-NCU_DRAM_BYTES_PER_LAUNCH = {"dataflow": 18776064 + 1025024, "barrier": 17295360 + 296704, "step": None}
+WORKLOAD = "cfg2 (synthetic, d=8): 70k points of 10 Gaussian blobs in R^8, k=10 kNN graph, 10 classes, 1 label/class"
+
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch (T = 100 iterations) of the dominant kernel, ncu --set full,
+# profiles/r2_dataflow_pipe_ncu_raw.csv
+NCU_DRAM_BYTES_PER_LAUNCH = {"dataflow": None, "barrier": 17295360 + 296704, "step": None}
+
+
+def timed(fn, reps=1):
+    best = 1e30
+    for _ in range(reps):
+        t0 = time.perf_counter(); out = fn(); best = min(best, time.perf_counter() - t0)
+    return best, out
+
+
+def literal_cfg2(labels_unused=None):
+    """The literal config 2: 70 000 x 128 features -> GPU kNN search -> Poisson iterate on the graph it builds."""
+    import torch
+    from graphlearning_b200 import device as gdev, knn_gpu
+    from oracle import gl_oracle as orc
+    X, lab = orc.synthetic_blobs(N_NODES, 128, c=N_CLASSES, seed=0)
+    X = X.astype(np.float64)
+    knn_gpu.knnsearch_gpu(X[:4096], K_NN + 1)
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    ind, dist_ = knn_gpu.knnsearch_gpu(X, K_NN + 1)
+    torch.cuda.synchronize(); t_knn = time.perf_counter() - t0
+    fallback = knn_gpu.last_stats.get("fallback_rows")
+    Wh = orc.knn_weights(ind, dist_, K_NN)
+    deg = np.diff(Wh.indptr)
+    th = orc.one_per_class(lab, rate=1, seed=0)
+    op = gdev.PoissonOperator(Wh, reorder=True)
+    Db = op.source_to_Db(orc.poisson_source(N_NODES, th, lab[th])[0])
+    u0 = torch.zeros_like(Db); u1 = torch.zeros_like(Db)
+    best = 1e30
+    for _ in range(3):
+        u0.zero_()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(); op.iterate(Db, 500, u0, u1); e1.record(); torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    b = algorithmic_bytes(N_NODES, Wh.nnz, N_CLASSES)
+    # CPU baseline of the search, measured here: the reference's exact branch (cKDTree, weightmatrix.py:349-352) on a
+    # sub-sample of query rows against all points, extrapolated to n rows
+    from scipy import spatial
+    rows = 100
+    tree = spatial.cKDTree(X)
+    t_tree, _ = timed(lambda: tree.query(X[:rows], k=K_NN + 1))
+    return {
+        "knn_70k_x_128_k10": {"seconds_host_to_host": t_knn, "fp32_TFLOPs_on_2n2d": 2.0 * N_NODES * N_NODES * 128 / t_knn / 1e12,
+                              "fallback_rows": fallback,
+                              "reference_cpu": {"seconds_extrapolated": t_tree / rows * N_NODES, "measured": "%d query rows against all 70 000 points in %.2f s, "
+                                                "scipy cKDTree, 1 thread (the reference's call, weightmatrix.py:351-352), scaled to 70 000 rows" % (rows, t_tree)}},
+        "poisson_iterate": {"nnz": int(Wh.nnz), "max_row": int(deg.max()), "p99_row": int(np.percentile(deg, 99)), "kernel": op.kind(N_CLASSES),
+                            "gate_every": op.gate(N_CLASSES), "us_per_iteration": best * 1e3 / 500, "iterations_per_s": 500 / (best * 1e-3),
+                            "bytes_per_iteration": b, "achieved_GBs": b * 500 / (best * 1e-3) / 1e9},
+    }
+
+
+def reference_use_cuda(W, labels, ti, iters):
+    """The reference's OWN GPU path (`use_cuda=True`: torch COO fp32 sparse.addmm, ssl.py:649-663) on this B200 - the
+    "GPU baseline to beat" of SURVEY 8a row a14 / BASELINE.md 4.3 - restated in oracle/gl_oracle.py."""
+    import torch
+    from oracle import gl_oracle as orc
+    orc.poisson_gd_use_cuda(W, ti, labels[ti], min_iter=5, max_iter=5)                       # warm-up (cuSPARSE handles)
+    torch.cuda.synchronize()
+    t_host, _ = timed(lambda: (orc.poisson_gd_use_cuda(W, ti, labels[ti], min_iter=iters, max_iter=iters), torch.cuda.synchronize()))
+    t_dev, _ = timed(lambda: (orc.poisson_gd_use_cuda(W, ti, labels[ti], min_iter=iters, max_iter=iters, host_mixing=False), torch.cuda.synchronize()))
+    t_setup, _ = timed(lambda: (orc.poisson_gd_use_cuda(W, ti, labels[ti], min_iter=0, max_iter=0), torch.cuda.synchronize()))
+    return {"iterations": iters,
+            "iterations_per_s_as_shipped": iters / max(t_host - t_setup, 1e-9),
+            "iterations_per_s_addmm_only": iters / max(t_dev - t_setup, 1e-9),
+            "note": "as shipped: torch.sparse.addmm on the device + v = RW*v and np.max on the host every iteration (ssl.py:657-660); "
+                    "addmm only: the same loop without the host-side stopping vector.  Setup (P to COO, uploads) subtracted: %.3f s" % t_setup}
 
 
 def other_rows(W, labels, ti):
-    """Short measurements of the other rows of SURVEY.md 8(a) on this box (rank 0, untimed part of the bench line):
-    kNN build at config-2 size, the iterate on the 128-d (hub-heavy) graph that search produces, Laplace CG."""
+    """Short measurements of the other rows of SURVEY.md 8(a) on this box (rank 0, untimed part of the bench line), each
+    next to the reference's CPU implementation of the same step measured here (bounded samples)."""
     import torch
     import graphlearning_b200 as gl
-    from graphlearning_b200 import device as gdev, knn_gpu
-    from oracle import gl_oracle as orc
+    from oracle import gl_oracle as orc, c_oracle
     out = {}
     try:
-        X, lab = orc.synthetic_blobs(N_NODES, 128, c=N_CLASSES, seed=0)
-        X = X.astype(np.float64)
-        knn_gpu.knnsearch_gpu(X[:4096], K_NN + 1)
-        torch.cuda.synchronize(); t0 = time.perf_counter()
-        ind, dist_ = knn_gpu.knnsearch_gpu(X, K_NN + 1)
-        torch.cuda.synchronize(); t = time.perf_counter() - t0
-        out["knn_70k_x_128_k10"] = {"seconds_host_to_host": t, "fp32_TFLOPs_on_2n2d": 2.0 * N_NODES * N_NODES * 128 / t / 1e12,
-                                    "fallback_rows": knn_gpu.last_stats.get("fallback_rows"),
-                                    "reference_cpu_seconds": "2460 (cKDTree, 1 thread, BASELINE.md section 2)"}
-        Wh = orc.knn_weights(ind, dist_, K_NN)
-        deg = np.diff(Wh.indptr)
-        th = orc.one_per_class(lab, rate=1, seed=0)
-        op = gdev.PoissonOperator(Wh)
-        Db = op.source_to_Db(orc.poisson_source(N_NODES, th, lab[th])[0])
-        u0 = torch.zeros_like(Db); u1 = torch.zeros_like(Db)
-        best = 1e30
-        for _ in range(3):
-            u0.zero_()
-            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-            e0.record(); op.iterate(Db, 500, u0, u1); e1.record(); torch.cuda.synchronize()
-            best = min(best, e0.elapsed_time(e1))
-        b = algorithmic_bytes(N_NODES, Wh.nnz, N_CLASSES)
-        out["poisson_on_128d_graph"] = {"nnz": int(Wh.nnz), "max_row": int(deg.max()), "p99_row": int(np.percentile(deg, 99)),
-                                        "kernel": op.kind(N_CLASSES), "gate_every": op.gate(N_CLASSES), "us_per_iteration": best * 1e3 / 500,
-                                        "iterations_per_s": 500 / (best * 1e-3), "achieved_GBs": b * 500 / (best * 1e-3) / 1e9}
         m = gl.ssl.laplace(W)
         t5 = orc.one_per_class(labels, rate=5, seed=0)
         m.fit(t5, labels[t5])
@@ -95,24 +137,30 @@ def other_rows(W, labels, ti):
         m.fit(t5, labels[t5])
         t = time.perf_counter() - t0
         out["laplace_cg_fit"] = {"seconds": t, "cg_iterations": int(m.iterations), "gpu_launches": int(m.gpu_launches),
-                                 "note": "gl.ssl.laplace(W).fit, 5 labels/class, tol 1e-5; includes the scipy system assembly"}
+                                 "note": "gl.ssl.laplace(W).fit, 5 labels/class, tol 1e-5, host buffers in and out"}
         # config 4: 50 eigenpairs of the normalised Laplacian (graph.eigen_decomp on the block kernels of spectral.cu)
         G = gl.graph(W)
         torch.cuda.synchronize(); t0 = time.perf_counter()
         vals, vecs = G.eigen_decomp(normalization="normalized", k=50)
         t = time.perf_counter() - t0
+        t_arpack, ref = timed(lambda: orc.eigen_decomp(W, normalization="normalized", k=50))
         out["eigen_decomp_k50"] = {"seconds": t, "spmm_launches": int(G.eigen_info["spmm"]), "residual": float(G.eigen_info["residual"]),
-                                   "lambda_50": float(vals[-1]), "reference_cpu_seconds": "6.1 (ARPACK svds, BASELINE.md section 2)"}
+                                   "lambda_50": float(vals[-1]), "max_abs_eigenvalue_diff_vs_reference": float(np.max(np.abs(vals - ref[0]))),
+                                   "reference_cpu_seconds": t_arpack, "reference_cpu": "scipy ARPACK svds as graph.py:728-746, measured here"}
         # p-Laplace / AMLE sweeps (bit-exact Gauss-Seidel / Jacobi of c_code/lp_iterate.cpp), one class against the rest
         val = (labels[t5] == 0).astype(np.float64)
         G.plaplace(t5, val, 3, max_num_it=30)
         for name, fn in (("plaplace_p3_fast", lambda: G.plaplace(t5, val, 3)), ("amle_weighted", lambda: G.amle(t5, val, tol=1e-3, max_num_it=300))):
             t0 = time.perf_counter(); fn(); t = time.perf_counter() - t0
             out[name] = {"seconds_host_to_host": t, "sweeps": int(G.sweeps), "us_per_sweep": 1e6 * t / max(1, G.sweeps)}
+        I, J, V = orc.ccode_triplets(W)
+        sweeps = 40
+        t_c, _ = timed(lambda: c_oracle.lip_iterate(np.zeros(len(labels)), J, I, V, t5.astype(np.int32), val, sweeps, 0.0, 1.0 / 3, 2.0 / 3))
+        out["plaplace_p3_fast"]["reference_cpu_us_per_sweep"] = 1e6 * t_c / sweeps
+        out["plaplace_p3_fast"]["reference_cpu"] = "lip_iterate_main of c_code/lp_iterate.cpp (plain-C restatement, gcc -O2), %d sweeps measured here, 1 core" % sweeps
         mp = gl.ssl.plaplace(W, p=3)                                # one-vs-rest over the 10 classes, batched sweep kernel
         t0 = time.perf_counter(); mp.fit(t5, labels[t5]); t = time.perf_counter() - t0
-        out["ssl_plaplace_p3_fit_10_classes"] = {"seconds": t, "sweeps_per_class": [int(x) for x in mp.graph.sweeps],
-                                                 "reference_cpu_seconds": "15.7 (BASELINE.md section 2, MNIST-size graph)"}
+        out["ssl_plaplace_p3_fit_10_classes"] = {"seconds": t, "sweeps_per_class": [int(x) for x in mp.graph.sweeps]}
     except Exception as e:                                   # never lose the headline line over an extra
         out["error"] = repr(e)
     return out
@@ -188,13 +236,85 @@ def run_reference(args, rank):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "cfg2: 70k nodes, k=10 kNN graph (10 Gaussian blobs), 10 classes, 1 label/class",
-                   "n": int(W.shape[0]), "nnz": int(W.nnz), "classes": N_CLASSES, "iterations_per_step": iters},
+        "config": {"workload": WORKLOAD, "n": int(W.shape[0]), "nnz": int(W.nnz), "classes": N_CLASSES, "iterations_per_step": iters},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(out), flush=True)
+
+
+def parity_gate(W, labels, ti):
+    """every number ships with its parity check on the benched graph - scores after T = 50 iterations
+    against the fp64 oracle (max|u - u_ref| / max|u_ref| <= 1e-5) and identical predict() labels."""
+    import graphlearning_b200 as gl
+    from oracle import gl_oracle as orc, c_oracle
+    T = 50
+    model = gl.ssl.poisson(W, solver="gradient_descent", min_iter=T, max_iter=T)
+    u = model.fit(ti, labels[ti])
+    s = orc.poisson_gd_setup(W, ti, labels[ti])
+    u_ref = c_oracle.poisson_iterate(s["P"], np.asarray(s["Db"]), T)
+    err = float(np.max(np.abs(u - u_ref)) / np.max(np.abs(u_ref)))
+    same = bool(np.array_equal(model.predict(), orc.predict(u_ref)))
+    # default stopping rule: the iteration count must be the reference's (mixing of v <- RW v in fp64, ssl.py:667,669)
+    T_ref = 0
+    v, vinf, RW = s["v"], s["vinf"], s["RW"]
+    while (T_ref < 50 or np.max(np.absolute(v - vinf)) > 1 / s["n"]) and T_ref < 1000:
+        v = RW * v; T_ref += 1
+    return {"T": T, "max_rel_err_vs_fp64_oracle": err, "tolerance": 1e-5, "predict_equal": same, "T_default_rule_reference": T_ref,
+            "ok": bool(err <= 1e-5 and same)}
+
+
+def cfg5_rowpart(rank, world, full):
+    """BASELINE config 5 through graphlearning_b200.distributed: the 2M-node graph row-partitioned over the ranks, halo
+    rows put into the neighbours' label matrices by the step kernel (csrc/slab.cu); the all-gather variant of the north
+    star is measured next to it.  N = 1 runs the same kernel on one slab (no peers), so the driver's 1/2/4/8 curve is
+    this row.  Returns a dict on rank 0."""
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import bench_cfg5
+    from graphlearning_b200 import distributed as gd
+    n = 2000000
+    t0 = time.perf_counter()
+    W = bench_cfg5.build_graph(n)
+    t_graph = time.perf_counter() - t0
+    peak = hbm_peak()[0]
+    out = {"workload": "cfg5: 2M points uniform in the unit cube, k=10 kNN graph, 10 classes, T=100 iterations per run",
+           "n": n, "nnz": int(W.nnz), "n_gpus": world, "graph_build_s": t_graph}
+    put = bench_cfg5.measure(W, rank, world, "put", 1, 100, 3)
+    out.update({"iterations_per_s": put["iterations_per_s"], "ms_per_iteration": put["ms_per_iteration"],
+                "achieved_GBs_all_gpus": put["bytes_per_iteration"] * put["iterations_per_s"] / 1e9,
+                "frac_of_hbm_peak_per_gpu": put["bytes_per_iteration"] * put["iterations_per_s"] / 1e9 / (peak * world),
+                "exchange": "halo rows put into peer memory (NVLink, CUDA IPC) by slab_step_kernel, interior rows overlap",
+                "put_bytes_per_iteration_per_gpu_max": put.get("put_bytes_per_iteration_per_gpu_max"),
+                "boundary_rows_per_gpu_max": put.get("boundary_rows_per_gpu_max"), "rows_per_gpu_max": put.get("rows_per_gpu_max"),
+                "setup_s": put["setup_s"]})
+    if world > 1 or full:
+        ag = bench_cfg5.measure(W, rank, world, "allgather", 1, 100, 2)
+        out["allgather_baseline"] = {"iterations_per_s": ag["iterations_per_s"], "kernel": ag["kernel"],
+                                     "allgather_bytes_per_iteration_per_gpu": ag.get("allgather_bytes_per_iteration_per_gpu")}
+    if world > 1:
+        # parity: the partitioned run against ONE slab holding the whole (smaller) graph, bitwise
+        Ws = bench_cfg5.build_graph(100000)
+        src = np.random.default_rng(1).normal(size=(Ws.shape[0], N_CLASSES)) * (np.random.default_rng(2).random((Ws.shape[0], 1)) < 0.01)
+        pp = gd.PartitionedPoisson(Ws, rank=rank, world=world, reorder=True, c=N_CLASSES)
+        u_part = pp.iterate(src, 12)
+        pp.close()
+        if rank == 0:
+            one = gd.PartitionedPoisson(Ws, rank=0, world=1, reorder=True, c=N_CLASSES)
+            u_one = one.iterate(src, 12)
+            one.close()
+            out["parity_vs_single_gpu"] = bool(np.array_equal(u_part, u_one))
+        dist.barrier()
+    return out
+
+
+def hbm_peak():
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        return json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json, burst copy)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
 
 
 def run_ours(args, rank, world):
@@ -216,7 +336,7 @@ def run_ours(args, rank, world):
     source = orc.poisson_source(n, ti, labels[ti])[0]
     iters = args.iters
 
-    op = gdev.PoissonOperator(W, kind=os.environ.get("GLB_BENCH_KIND", "auto"))   # profiler runs pin the kernel: the plan's trial timing is meaningless under ncu
+    op = gdev.PoissonOperator(W, kind=os.environ.get("GLB_BENCH_KIND", "auto"), reorder=True)   # profiler runs pin the kernel: the plan's trial timing is meaningless under ncu
     Db = op.source_to_Db(source)
     ldu = int(Db.shape[1])
     kind = op.kind(c)
@@ -253,7 +373,7 @@ def run_ours(args, rank, world):
     model = gl.ssl.poisson(W, solver="gradient_descent", min_iter=iters, max_iter=iters)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    model.fit(ti, labels[ti])                              # first fit on this graph: uploads W, builds P/RW on the device
+    model.fit(ti, labels[ti])                              # first fit on this graph: uploads W, builds P/RW, ordering and plan on the device
     cold_s = time.perf_counter() - t0
     model.fit(ti, labels[ti])
     barrier()
@@ -263,29 +383,54 @@ def run_ours(args, rank, world):
         u_host = model.fit(ti, labels[ti])
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    launches += e2e_steps * int(model.gpu_launches)
+    # the same call with the reference's defaults (min_iter=50, max_iter=1000: the stopping rule runs on the device too)
+    dmodel = gl.ssl.poisson(W, solver="gradient_descent")
+    dmodel.fit(ti, labels[ti])
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        dmodel.fit(ti, labels[ti])
+    torch.cuda.synchronize()
+    e2e_default_s = (time.perf_counter() - t0) / e2e_steps
+    T_default = int(dmodel.iterations)
+    launches += e2e_steps * int(dmodel.gpu_launches)
     clocks = sampler.stop() if rank == 0 else None
     h2d = n * c * 8                                        # per fit: the fp64 source term (graph state is cached)
     graph_h2d = (n + 1) * 4 + nnz * 4 + nnz * 8           # once per graph, inside the first fit
     d2h = n * c * 8
 
     if world > 1:
-        t = torch.tensor([total_ms, e2e_s], dtype=torch.float64, device="cuda")
+        t = torch.tensor([total_ms, e2e_s, e2e_default_s], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms, e2e_s = float(t[0]), float(t[1])
+        total_ms, e2e_s, e2e_default_s = float(t[0]), float(t[1]), float(t[2])
         dist.barrier()
+    del flush
+    torch.cuda.empty_cache()
+    rowpart = None
+    if not args.no_cfg5:
+        try:
+            rowpart = cfg5_rowpart(rank, world, full=not args.no_extras)
+        except Exception as e:
+            rowpart = {"error": repr(e)}
     if rank != 0:
         if world > 1:
+            dist.barrier()
             dist.destroy_process_group()
         return
 
     value = world * iters * args.steps / (total_ms * 1e-3)
     e2e_value = world * iters * e2e_steps / e2e_s
-    extras = other_rows(W, labels, ti) if not args.no_extras else None
-    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(peaks_path):
-        peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json, burst copy)"
-    else:
-        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    parity = parity_gate(W, labels, ti)
+    extras = None
+    if not args.no_extras and world == 1:
+        extras = other_rows(W, labels, ti)
+        try:
+            extras["cfg2_literal_128d"] = literal_cfg2()
+            extras["reference_gpu_path_use_cuda"] = reference_use_cuda(W, labels, ti, 200)
+        except Exception as e:
+            extras["error_2"] = repr(e)
+    peak, peak_src = hbm_peak()
     # roofline of the dominant kernel = the persistent iterate: algorithmic bytes per launch / launch duration
     ms_launch = float(np.mean(kernel_ms))
     achieved = algorithmic_bytes(n, nnz, c) * iters / (ms_launch * 1e-3) / 1e9
@@ -296,14 +441,15 @@ def run_ours(args, rank, world):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "cfg2: 70k nodes, k=10 kNN graph (10 Gaussian blobs), 10 classes, 1 label/class",
+        "config": {"workload": WORKLOAD,
                    "n": int(n), "nnz": int(nnz), "classes": c, "iterations_per_step": iters, "ldu": ldu,
-                   "kernel": {"dataflow": "poisson_dataflow_kernel", "barrier": "poisson_persistent_kernel",
+                   "kernel": {"dataflow": "poisson_dataflow_pipe_kernel", "barrier": "poisson_persistent_kernel",
                               "step": "poisson_step_kernel"}[kind],
-                   "gate_every": op.gate(c),
+                   "gate_every": op.gate(c), "node_ordering": "reverse Cuthill-McKee (library, per graph)",
                    "l2": "flushed between steps (256 MiB write); inside a step the 16.8 MB working set is "
                          "L2 resident by construction",
-                   "parallelism": "replicas x%d (independent label sets, no collective)" % world},
+                   "parallelism": "replicas x%d (independent label sets, no collective); the row-partitioned multi-GPU "
+                                  "iterate of config 5 is `cfg5_rowpart`" % world},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get(kind), "peak_source": peak_src,
                      "traffic_note": "dram__bytes_read+write of one launch from the ncu capture under profiles/ (T=100 "
@@ -314,16 +460,25 @@ def run_ours(args, rank, world):
                          "sample": "%d iterations of the reference loop (ssl.py:667-669, scipy csr_matvecs fp64) on the "
                                    "same graph, best of 2; host has %d cores, scipy SpMM uses 1" % (cpu_iters, os.cpu_count())},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "steps": e2e_steps, "call": "gl.ssl.poisson(W, solver='gradient_descent').fit -> glb_poisson_graph_fit "
-                "(device graph state cached on the gl.graph object after the first fit, as in ssl_trials)",
-                "first_fit_value": iters / cold_s, "graph_h2d_bytes_once": int(graph_h2d)},
+                "steps": e2e_steps, "call": "gl.ssl.poisson(W, solver='gradient_descent', min_iter=max_iter=%d).fit -> glb_poisson_graph_fit "
+                "(device graph state cached on the gl.graph object after the first fit, as in ssl_trials)" % iters,
+                "first_fit_value": iters / cold_s, "first_fit_ms": 1e3 * cold_s, "graph_h2d_bytes_once": int(graph_h2d)},
+        "e2e_default": {"call": "gl.ssl.poisson(W, solver='gradient_descent').fit with the reference's defaults min_iter=50, max_iter=1000: "
+                                "the stopping vector v <- RW v (fp64) is iterated on the device as well", "T": T_default,
+                        "ms_per_fit": 1e3 * e2e_default_s, "value": T_default / e2e_default_s, "unit": UNIT},
+        "parity": parity,
+        "cfg5_rowpart": rowpart,
         "gpu_launches": int(launches),
         "clocks": clocks,
         "other_rows": extras,
     }
     assert np.isfinite(u_host).all()
+    if not parity["ok"]:
+        print(json.dumps(out), flush=True)
+        raise SystemExit("parity gate failed: %r" % (parity,))
     print(json.dumps(out), flush=True)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
@@ -337,6 +492,7 @@ def main():
     ap.add_argument("--ref-iters", type=int, default=100, help="iterations per step of the CPU reference arm")
     ap.add_argument("--cpu-iters", type=int, default=200, help="bounded CPU sample inside the GPU arm")
     ap.add_argument("--no-extras", action="store_true", help="skip the short measurements of the other 8(a) rows")
+    ap.add_argument("--no-cfg5", action="store_true", help="skip the row-partitioned config-5 measurement")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))

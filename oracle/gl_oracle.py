@@ -286,6 +286,42 @@ def poisson_gd(W, train_ind, train_labels, min_iter=50, max_iter=1000, return_it
     return u
 
 
+def torch_sparse(A):
+    """scipy sparse -> torch COO float32 (utils.py:288-317; torch.sparse.FloatTensor(i, v, size) in today's spelling)."""
+    import torch
+    A = A.tocoo()
+    i = torch.from_numpy(np.vstack((A.row, A.col)).astype(np.int64))
+    v = torch.from_numpy(A.data.astype(np.float32))
+    return torch.sparse_coo_tensor(i, v, torch.Size(A.shape))
+
+
+def poisson_gd_use_cuda(W, train_ind, train_labels, min_iter=50, max_iter=1000, return_iters=False, host_mixing=True):
+    """The reference's OWN GPU variant of the gradient-descent branch, `use_cuda=True` (ssl.py:649-663): P as a torch COO
+    fp32 matrix, u <- torch.sparse.addmm(Db, P, u) on the device while the stopping vector v <- RW*v and its np.max stay on
+    the host in every iteration.  Needs a CUDA device; used by bench.py as the "GPU baseline to beat" (SURVEY 8a row a14).
+    host_mixing=False leaves the host-side v update out (an upper bound of what the torch path could do)."""
+    import torch
+    s = poisson_gd_setup(W, train_ind, train_labels)
+    n, P, Db, v, vinf, RW = s["n"], s["P"], s["Db"], s["v"], s["vinf"], s["RW"]
+    Pt = torch_sparse(P).cuda()                                   # :653
+    ut = torch.from_numpy(np.zeros_like(Db)).float().cuda()       # :654
+    Dbt = torch.from_numpy(Db).float().cuda()                     # :655
+    T = 0
+    if host_mixing:
+        while (T < min_iter or np.max(np.absolute(v - vinf)) > 1 / n) and (T < max_iter):   # :657
+            ut = torch.sparse.addmm(Dbt, Pt, ut)                  # :658
+            v = RW * v                                            # :659
+            T = T + 1
+    else:
+        while T < max_iter:
+            ut = torch.sparse.addmm(Dbt, Pt, ut)
+            T = T + 1
+    u = ut.cpu().numpy()                                          # :663
+    if return_iters:
+        return u, T
+    return u
+
+
 def poisson_cg(W, train_ind, train_labels, tol=1e-3, return_iters=False):
     """Poisson learning, default solver='conjugate_gradient'.  ssl.py:624-629."""
     W = sparse.csr_matrix(W)

@@ -1,0 +1,137 @@
+"""The north star's "examples/ scripts run unmodified against the new backend" (SURVEY.md Appendix C).
+
+The reference's own scripts are executed with runpy against the alias package `graphlearning` (= graphlearning_b200)
+and a stand-in `matplotlib`.  The scripts live in the reference checkout, which exists in the build container only:
+  * not gpu:  the unmodified reference scripts run here with the two device entry points they reach (utils.conjgrad,
+              graph.poisson_handle) replaced by the CPU oracle - this pins the API surface (names, kwargs, return types,
+              host logic) the scripts rely on;
+  * gpu:      on the B200 box the same scripts run against the real backend when the checkout is present; otherwise
+              the same call sequences, restated below, do.
+"""
+import io
+import os
+import runpy
+import sys
+import types
+from contextlib import redirect_stdout
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from oracle import gl_oracle as orc
+
+REF_EXAMPLES = os.path.join(os.environ.get("GL_REFERENCE_ROOT", "/root/reference"), "examples")
+
+
+@pytest.fixture
+def headless(monkeypatch):
+    """matplotlib is not installed: a module whose pyplot accepts every call (the scripts only plot at the end)."""
+    class _Anything(types.ModuleType):
+        def __getattr__(self, name):
+            return lambda *a, **k: None
+    mpl, plt = _Anything("matplotlib"), _Anything("matplotlib.pyplot")
+    mpl.pyplot = plt
+    mpl.rcParams = {}
+    monkeypatch.setitem(sys.modules, "matplotlib", mpl)
+    monkeypatch.setitem(sys.modules, "matplotlib.pyplot", plt)
+    monkeypatch.syspath_prepend(ROOT)
+    np.random.seed(0)                       # make_moons / trainsets.generate draw from the global numpy stream
+    return plt
+
+
+def _run_script(path):
+    out = io.StringIO()
+    with redirect_stdout(out):
+        runpy.run_path(path, run_name="__main__")
+    return out.getvalue()
+
+
+def _accuracy(text):
+    return float(text.split("Accuracy:")[1].split("%")[0])
+
+
+@pytest.fixture
+def oracle_device(monkeypatch):
+    """CPU stand-ins for the two device entry points the scripts reach (test only: the product has no CPU path)."""
+    import graphlearning_b200 as glb
+
+    def conjgrad(A, b, x0=None, max_iter=1e5, tol=1e-10, return_info=False):
+        x, it = orc.conjgrad(A, b, x0=x0, max_iter=max_iter, tol=tol, return_iters=True)
+        return (x, (it, 0.0, 0)) if return_info else x
+
+    class Handle:
+        def __init__(self, W):
+            self.W = W
+
+        def fit(self, source, train_ind, min_iter, max_iter):
+            from scipy import sparse
+            n = self.W.shape[0]
+            W = self.W - sparse.spdiags(self.W.diagonal(), 0, n, n)
+            deg = np.asarray(W.sum(axis=1)).ravel()
+            D = sparse.spdiags(1.0 / deg, 0, n, n)
+            P, Db, RW = D * W.transpose(), D * source, W.transpose() * D
+            v = np.zeros(n); v[train_ind] = 1; v = v / np.sum(v)
+            vinf = deg / np.sum(deg)
+            u, T = np.zeros_like(Db), 0
+            while (T < min_iter or np.max(np.absolute(v - vinf)) > 1 / n) and T < max_iter:      # ssl.py:667-669
+                u = Db + P * u; v = RW * v; T += 1
+            return u, T, 0
+
+    monkeypatch.setattr(glb.utils, "conjgrad", conjgrad)
+    monkeypatch.setattr(glb.graph, "poisson_handle", lambda self: Handle(self.weight_matrix))      # glb.graph is the class
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_EXAMPLES), reason="reference checkout not present")
+@pytest.mark.parametrize("script", ["ssl_twomoons.py", "poisson_directed.py"])
+def test_reference_examples_run_unmodified_host_side(headless, oracle_device, script):
+    text = _run_script(os.path.join(REF_EXAMPLES, script))
+    assert _accuracy(text) > 90.0, text
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("script", ["ssl_twomoons.py", "poisson_directed.py"])
+def test_examples_on_the_device(headless, script):
+    path = os.path.join(REF_EXAMPLES, script)
+    if os.path.exists(path):
+        assert _accuracy(_run_script(path)) > 90.0
+        return
+    # the same call sequence as the script (reference examples/ssl_twomoons.py:6-15, poisson_directed.py:6-15)
+    import graphlearning as gl
+    import sklearn.datasets as datasets
+    X, labels = datasets.make_moons(n_samples=500, noise=0.1)
+    if script == "ssl_twomoons.py":
+        W = gl.weightmatrix.knn(X, 10)
+        model_of = lambda: gl.ssl.laplace(W)
+    else:
+        W = gl.weightmatrix.knn(X, 10, symmetrize=False)
+        model_of = lambda: gl.ssl.poisson(W, solver="gradient_descent")
+    train_ind = gl.trainsets.generate(labels, rate=5)
+    train_labels = labels[train_ind]
+    pred_labels = model_of().fit_predict(train_ind, train_labels)
+    assert gl.ssl.ssl_accuracy(pred_labels, labels, train_ind) > 90.0
+
+
+def test_datasets_and_trainsets_read_the_reference_files(tmp_path, monkeypatch):
+    """gl.datasets.load(labels_only=True) / gl.trainsets.load read the reference's own .npz files and never download
+    (examples/ssl_mnist.py:3, ssl_trials.py)."""
+    import graphlearning as gl
+    labels = np.random.default_rng(0).integers(0, 10, 500)
+    os.makedirs(tmp_path / "data"); os.makedirs(tmp_path / "trainsets")
+    np.savez_compressed(tmp_path / "data" / "MNIST_labels.npz", labels=labels)          # the repository's spelling
+    perm = np.array([np.arange(3), np.arange(5)], dtype=object)
+    np.savez_compressed(tmp_path / "trainsets" / "mnist_permutations.npz", perm=perm)
+    monkeypatch.setattr(gl.datasets, "data_dir", str(tmp_path / "data"))
+    monkeypatch.setattr(gl.trainsets, "trainset_dir", str(tmp_path / "trainsets"))
+    assert np.array_equal(gl.datasets.load("mnist", labels_only=True), labels)
+    got = gl.trainsets.load("mnist")
+    assert len(got) == 2 and np.array_equal(got[1], np.arange(5))
+    with pytest.raises(FileNotFoundError, match="does not download"):
+        gl.datasets.load("cifar", labels_only=True)
+    with pytest.raises(FileNotFoundError, match="does not download"):
+        gl.trainsets.load("cifar")
+    pri = gl.utils.class_priors(np.array([0, 0, 1, 2, 2, 2, -1]))
+    assert np.allclose(pri, [2 / 6, 1 / 6, 3 / 6])
+    saved = gl.trainsets.generate(labels, rate=1, num_trials=2, dataset="toy", seed=1)
+    again = gl.trainsets.load("toy")
+    assert all(np.array_equal(a, b) for a, b in zip(saved, again))
