@@ -6,9 +6,10 @@
 
 namespace glb {
 
-// auto mode reorders the graph only when two ping-pong label matrices exceed this many bytes (about the L2
-// size): below it every gather is an L2 hit anyway and the r1c/r1e sweeps (profiles/) show no gain from RCM
-constexpr double kReorderMinBytes = 120.0 * 1024 * 1024;
+// auto mode relabels every graph that is big enough for the ordering to pay for its host time: the dataflow kernel's
+// first gather attempt goes through L1 and the slab kernel streams HBM, both live on neighbouring rows sharing columns
+// (profiles/r2_dataflow_pair_stream_ab.txt: 7.76 us/iteration in the caller's numbering, 6.40 relabelled)
+constexpr int64_t kReorderMinNodes = 4096;
 
 struct DeviceArena {           // frees everything on scope exit, whatever the return path
     std::vector<void *> ptrs;
@@ -143,8 +144,8 @@ extern "C" GLB_API int glb_poisson_graph_create(glb_poisson_graph **out, const i
 
     tm.lap("transpose/degree/scale");
     g->it_rp = g->t_rp; g->it_col = g->t_col; g->it_val = g->P_val;
-    // Locality ordering: worth its host time only when the label matrix cannot live in L2 (reorder < 0 = auto).
-    const bool want = reorder > 0 || (reorder < 0 && (double)n * 16.0 * 4.0 * 2.0 > kReorderMinBytes);
+    // Locality ordering (reorder < 0 = auto)
+    const bool want = reorder > 0 || (reorder < 0 && n >= kReorderMinNodes);
     if (want && nnz > 0) {
         std::vector<int> h_perm((size_t)n);
         if ((rc = glb_locality_order_host(h_rowptr, h_col, n, h_perm.data()))) return rc;

@@ -10,14 +10,16 @@
 // graph = 3.5 us, and every cycle spent elsewhere (grid barriers, instruction issue, divergence) is on top.
 //
 // Three kernels, chosen per graph by glb_poisson_plan_create:
-//   poisson_dataflow_kernel    T iterations in ONE launch, one CTA per SM, NO grid barrier: every 16-byte chunk
-//                              of a label row carries three values plus the iteration number that produced it
-//                              ("flag in data"), so a gather doubles as the synchronisation - a lane whose chunk
-//                              is still from an older iteration simply re-polls it.  Rows of the CTA are sorted by
-//                              length and stored as sliced ELL (8 rows per warp pass) in shared memory, so warps
-//                              run without divergence and read their (offset,value) pairs conflict-free.  Needs a
-//                              structurally symmetric pattern (then two ping-pong buffers are race-free: a row
-//                              can only be overwritten after every reader of it has moved on, see below).
+//   poisson_dataflow_kernel    T iterations in ONE launch, one CTA per SM, no grid barrier in the data path: every
+//                              16-byte chunk of a label row carries three values plus the iteration number that
+//                              produced it ("flag in data"), so a gather doubles as the synchronisation - a lane whose
+//                              chunk is still from an older iteration re-polls it.  Rows of the CTA are sorted by length
+//                              and stored as sliced ELL in shared memory; every warp walks its slices as ONE stream of
+//                              entry pairs with 6-8 gathers per lane in flight.  Four versions of the label matrix
+//                              rotate, so the first attempt of a gather may be served by L1 (under the locality ordering
+//                              of reorder.cu a CTA gathers every distinct row ~2.4 times per iteration).  A gate every
+//                              `gate_every` iterations (tuned per graph, usually 1) keeps the CTAs in phase.  Needs a
+//                              structurally symmetric pattern (argument below).
 //   poisson_persistent_kernel  T iterations in one cooperative launch with a hand-rolled grid barrier between
 //                              iterations; CSR slab in shared memory.  For directed graphs (symmetrize=False).
 //   poisson_step_kernel        one iteration per launch, CSR read from global memory.  For graphs too big for the
@@ -366,202 +368,11 @@ __device__ __forceinline__ const char *df_addr(const char *base, unsigned off)
     return reinterpret_cast<const char *>(a);
 }
 
-template <int N, int RPW, bool L1F>
-__device__ __forceinline__ void df_batch(const int2 *cvp, const char *in, unsigned expect, float &a0, float &a1,
-                                         float &a2, unsigned long long &n_poll, unsigned long long &n_badbatch, unsigned *watchdog,
-                                         unsigned poll_sleep)
-{
-    unsigned off[N];
-    float val[N];
-    uint4 x[N];
-    if (N == 1) {
-        const int2 e = cvp[0];
-        off[0] = (unsigned)e.x; val[0] = __int_as_float(e.y);
-    } else {
-#pragma unroll
-        for (int i = 0; i < N / 2; ++i) {
-            const int4 e = *reinterpret_cast<const int4 *>(cvp + i * 2 * RPW);
-            off[2 * i] = (unsigned)e.x;     val[2 * i] = __int_as_float(e.y);
-            off[2 * i + 1] = (unsigned)e.z; val[2 * i + 1] = __int_as_float(e.w);
-        }
-    }
-#pragma unroll
-    for (int i = 0; i < N; ++i) x[i] = L1F ? ld_chunk_l1(df_addr(in, off[i])) : ld_chunk(df_addr(in, off[i]));
-    bool ok = true;
-#pragma unroll
-    for (int i = 0; i < N; ++i) ok &= x[i].w >= expect;
-    unsigned spins = 0;
-    long long t0 = 0;
-    while (!ok) {                                        // some producer is still behind (or L1 held an old line): re-poll at L2
-        ++n_badbatch;
-        if (poll_expired(watchdog, spins, t0)) break;
-        if ((poll_sleep & 0xffffu) && spins > 1) __nanosleep(poll_sleep & 0xffffu);   // this warp is ahead of its producers: leave L2 and the LSU to them
-#pragma unroll
-        for (int i = 0; i < N; ++i)
-            if (x[i].w < expect) { x[i] = ld_chunk(df_addr(in, off[i])); ++n_poll; }
-        ok = true;
-#pragma unroll
-        for (int i = 0; i < N; ++i) ok &= x[i].w >= expect;
-    }
-#pragma unroll
-    for (int i = 0; i < N; ++i) {
-        a0 = fmaf(val[i], __uint_as_float(x[i].x), a0);
-        a1 = fmaf(val[i], __uint_as_float(x[i].y), a1);
-        a2 = fmaf(val[i], __uint_as_float(x[i].z), a2);
-    }
-}
-
 struct DfRing { float *b[kRing]; };              // version v of the label matrix lives in b[v % kRing]
 
-template <int LANES, int THREADS, int U, bool L1F>
-__global__ void __launch_bounds__(THREADS, 1)
-poisson_dataflow_kernel(const int2 *__restrict__ slabs, const long long *__restrict__ slab_off,
-                        const int4 *__restrict__ slots, const int *__restrict__ slot_off,
-                        const int *__restrict__ slot_rows, const float *__restrict__ Db, DfRing ring, int T,
-                        int cap_entries, int cap_slots, int cap_parts, unsigned long long *stats,
-                        unsigned *start_gate, int gate_every, unsigned *watchdog, unsigned poll_sleep)
-{
-    constexpr int RPW = 32 / LANES;              // rows per warp pass = slice height of the ELL slab
-    constexpr int NW = THREADS / 32;
-    constexpr unsigned ROWB = LANES * 16;        // bytes per label row
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    int2 *s_cv = reinterpret_cast<int2 *>(smem_raw);
-    int4 *s_slot = reinterpret_cast<int4 *>(s_cv + cap_entries);
-    volatile float *s_part = reinterpret_cast<volatile float *>(s_slot + cap_slots);     // [cap_parts][2][LANES][4]
-    int *s_rows = reinterpret_cast<int *>(const_cast<float *>(s_part) + (size_t)cap_parts * 2 * LANES * 4);
-
-    const long long e0 = slab_off[blockIdx.x];
-    const int nent = (int)(slab_off[blockIdx.x + 1] - e0);
-    const int sl0 = slot_off[blockIdx.x];
-    const int nslots = slot_off[blockIdx.x + 1] - sl0;
-    for (int i = threadIdx.x; i < nent; i += THREADS) s_cv[i] = slabs[e0 + i];
-    for (int i = threadIdx.x; i < nslots; i += THREADS) s_slot[i] = slots[sl0 + i];
-    for (int i = threadIdx.x; i < cap_parts * 2 * LANES * 4; i += THREADS) s_part[i] = 0.f;
-    // The Poisson source Db is zero except on the labelled rows: remember which rows have one
-    for (int i = threadIdx.x; i < nslots * RPW; i += THREADS) {
-        int r = slot_rows[(size_t)sl0 * RPW + i];
-        if (r >= 0) {
-            bool nz = false;
-            const float4 *b = reinterpret_cast<const float4 *>(Db + (size_t)r * (ROWB / 4));
-            for (int q = 0; q < LANES; ++q) {
-                const float4 v = __ldg(b + q);
-                nz |= (v.x != 0.f) | (v.y != 0.f) | (v.z != 0.f);               // NaN != 0 is true
-            }
-            if (nz) r |= kRowSrcBit;
-        }
-        s_rows[i] = r;
-    }
-    __syncthreads();
-    // One-time start gate: all CTAs enter iteration 0 together.  Without it the CTAs leave this prologue up to a few
-    // microseconds apart and about one launch in seven never recovers from that skew (consumers stay on the heels
-    // of their producers and every batch re-polls: 26 instead of 6.3 us/iteration, profiles/r1_stability.txt).
-    if (start_gate) {
-        if (threadIdx.x == 0) {
-            red_relaxed_add(start_gate, 1u);
-            unsigned spins = 0;
-            long long t0 = 0;
-            while (ld_relaxed(start_gate) < gridDim.x && !poll_expired(watchdog, spins, t0)) { }
-        }
-        __syncthreads();
-    }
-
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int g = lane / LANES, li = lane % LANES;
-    unsigned long long n_poll = 0, n_badbatch = 0;      // stats only (GLB_POISSON_STATS in -DGLB_EXPERIMENT builds)
-    const long long clk0 = clock64();
-    for (int t = 0; t < T; ++t) {
-        // Re-alignment gate every gate_every iterations: the low-polling regime is metastable (a CTA that falls behind
-        // drags its consumers into re-polling and they theirs); bringing all CTAs back into phase - exactly what
-        // the start gate does - ends such an episode.  ~3 us per gate, amortised over gate_every iterations.
-        if (start_gate && gate_every > 0 && t > 0 && t % gate_every == 0) {
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                red_relaxed_add(start_gate, 1u);
-                const unsigned want = gridDim.x * (unsigned)(t / gate_every + 1);
-                unsigned spins = 0;
-                long long t0 = 0;
-                while (ld_relaxed(start_gate) < want && !poll_expired(watchdog, spins, t0)) { }
-            }
-            __syncthreads();
-        }
-        const int vi = t & (kRing - 1), vo = (t + 1) & (kRing - 1);
-        const char *in = reinterpret_cast<const char *>(vi == 0 ? ring.b[0] : vi == 1 ? ring.b[1] : vi == 2 ? ring.b[2] : ring.b[3]) + li * 16;
-        char *out = reinterpret_cast<char *>(vo == 0 ? ring.b[0] : vo == 1 ? ring.b[1] : vo == 2 ? ring.b[2] : ring.b[3]) + li * 16;
-#ifdef GLB_EXPERIMENT
-        // ceiling probes (results are wrong): bit 30 of poll_sleep = every chunk counts as ready (pure gather throughput, no
-        // synchronisation), bit 31 = no stores either (the label matrix stays read-only)
-        const unsigned expect = (poll_sleep & 0x40000000u) ? 0u : 1u + (unsigned)t;
-#else
-        const unsigned expect = 1u + (unsigned)t;
-#endif
-        for (int s = warp; s < nslots; s += NW) {            // slot k of warp w is stored at k * NW + w
-            const int4 sl = s_slot[s];                       // (first entry, slice width, type | parts << 8, partial index)
-            const int L = sl.y;
-            float a0 = 0.f, a1 = 0.f, a2 = 0.f;
-            const int2 *cv = s_cv + sl.x + g * 2;            // pair q of this lane group: 16 bytes at cv[q * 2 * RPW]
-            int j = 0;
-            for (; j + U <= L; j += U) df_batch<U, RPW, L1F>(cv + j * RPW, in, expect, a0, a1, a2, n_poll, n_badbatch, watchdog, poll_sleep);
-            if (U > 8 && (L & 8)) { df_batch<8, RPW, L1F>(cv + j * RPW, in, expect, a0, a1, a2, n_poll, n_badbatch, watchdog, poll_sleep); j += 8; }
-            if (L & 4) { df_batch<4, RPW, L1F>(cv + j * RPW, in, expect, a0, a1, a2, n_poll, n_badbatch, watchdog, poll_sleep); j += 4; }
-            if (L & 2) { df_batch<2, RPW, L1F>(cv + j * RPW, in, expect, a0, a1, a2, n_poll, n_badbatch, watchdog, poll_sleep); j += 2; }
-            if (L & 1) df_batch<1, RPW, L1F>(cv + j * RPW, in, expect, a0, a1, a2, n_poll, n_badbatch, watchdog, poll_sleep);
-            const int type = sl.z & 0xff;
-            if (type != kSlotNormal) {                       // warp-uniform: one long row dealt over the lane groups
-#pragma unroll
-                for (int o = LANES; o < 32; o <<= 1) {
-                    a0 += __shfl_xor_sync(0xffffffffu, a0, o);
-                    a1 += __shfl_xor_sync(0xffffffffu, a1, o);
-                    a2 += __shfl_xor_sync(0xffffffffu, a2, o);
-                }
-                if (type == kSlotPart) {
-                    if (g == 0) {
-                        volatile float *pb = s_part + ((size_t)(sl.w * 2 + (t & 1)) * LANES + li) * 4;
-                        pb[0] = a0; pb[1] = a1; pb[2] = a2;
-                        __threadfence_block();
-                        pb[3] = __uint_as_float(2u + (unsigned)t);
-                    }
-                    continue;
-                }
-                if (type == kSlotOwner) {
-                    const int nparts = sl.z >> 8;
-                    for (int q = 0; q < nparts; ++q) {       // partial sums of the other warps, fixed order
-                        volatile float *pb = s_part + ((size_t)((sl.w + q) * 2 + (t & 1)) * LANES + li) * 4;
-                        unsigned spins = 0;
-                        long long tw0 = 0;
-                        while (__float_as_uint(pb[3]) != 2u + (unsigned)t && !poll_expired(watchdog, spins, tw0)) { }
-                        __threadfence_block();
-                        a0 += pb[0]; a1 += pb[1]; a2 += pb[2];
-                    }
-                }
-            }
-            const int rinfo = s_rows[s * RPW + g];
-            if (rinfo >= 0) {
-                const unsigned row = (unsigned)(rinfo & (kRowSrcBit - 1));
-                if (rinfo & kRowSrcBit) {
-                    const float4 b = __ldg(reinterpret_cast<const float4 *>(Db + (size_t)row * (ROWB / 4)) + li);
-                    a0 += b.x; a1 += b.y; a2 += b.z;
-                }
-#ifdef GLB_EXPERIMENT
-                if (!(poll_sleep & 0x80000000u) || a0 == 123.456f)
-#endif
-                st_chunk(out + (size_t)row * ROWB, a0, a1, a2, 2u + (unsigned)t);
-            }
-        }
-    }
-    if (stats) {
-        atomicAdd(stats + 0, n_poll);
-        atomicAdd(stats + 1, n_badbatch);
-        if (lane == 0) atomicMax(stats + 2, (unsigned long long)(clock64() - clk0));
-        if (threadIdx.x == 0) atomicAdd(stats + 3, 1ull);
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// K3p: the same dataflow iterate with a software-pipelined gather stream
-// ------------------------------------------------------------------------------------------------
-// What bounds the batch kernel above (ncu, r1/r2): one warp has ONE batch of gathers in flight, waits for it (an L2 round
-// trip of ~500-1000 cycles under load), consumes it, and only then issues the next; the LSU data pipe (one 128-byte line
-// per cycle and SM, i.e. one label row per cycle) idles a third of the time.  Here every warp walks ONE contiguous
+// Gather stream.  The round-1 kernel gave one warp ONE batch of 8 gathers in flight: wait for it (an L2 round trip of
+// ~500-1000 cycles under load), consume it, only then issue the next; the LSU data pipe (one 128-byte line per cycle and
+// SM, i.e. one label row per cycle) idled a third of the time.  Here every warp walks ONE contiguous
 // stream of entry PAIRS (all slots of the warp back to back, slice widths padded to even only) through a ring of four
 // register slots: pair p+4 is issued as soon as pair p has been validated and consumed, across slot boundaries, so 6-8
 // gathers per lane are outstanding all the time and the instruction stream overlaps the memory latency.  With every
@@ -607,7 +418,7 @@ __device__ __forceinline__ void dfp_consume(const int4 *cv, const char *in, unsi
 
 template <int LANES, int THREADS, bool L1F>
 __global__ void __launch_bounds__(THREADS, 1)
-poisson_dataflow_pipe_kernel(const int2 *__restrict__ slabs, const long long *__restrict__ slab_off,
+poisson_dataflow_kernel(const int2 *__restrict__ slabs, const long long *__restrict__ slab_off,
                              const int4 *__restrict__ slots, const int *__restrict__ slot_off,
                              const int *__restrict__ slot_rows, const float *__restrict__ Db, DfRing ring, int T,
                              int cap_entries, int cap_slots, int cap_parts, unsigned long long *stats,
@@ -951,7 +762,6 @@ struct glb_poisson_plan {
     int tuned_gate = 32;
     float *d_ring = nullptr;            // dataflow kernel: buffers 2 and 3 of the version ring (0 and 1 are the caller's u0/u1)
     bool l1_first = true;               // dataflow kernel: first attempt of a gather through L1
-    bool pipelined = true;              // dataflow kernel: software-pipelined gather stream (poisson_dataflow_pipe_kernel)
     unsigned *d_gate = nullptr;         // dataflow kernel: start gate counter
     int gate_every = 32;                // dataflow kernel: iterations between re-alignment gates (tuned at plan time)
     unsigned poll_sleep = 0;            // dataflow kernel: nanoseconds a warp sleeps between re-polls of a stale batch
@@ -995,29 +805,24 @@ static const void *pick_barrier(int ldu, int *threads)
 
 // 512 threads x 8 gathers in flight per lane (16-entry batches spill at the 128-register cap, r1 visit 4)
 template <int LANES>
-static const void *dataflow_fn(bool pipelined, bool l1_first, int *threads)
+static const void *dataflow_fn(bool l1_first, int *threads)
 {
-    const int pt = exp_env("GLB_POISSON_THREADS", 512);
-    if (pipelined) {
-        if (pt == 768) { *threads = 768; return l1_first ? (const void *)poisson_dataflow_pipe_kernel<LANES, 768, true> : (const void *)poisson_dataflow_pipe_kernel<LANES, 768, false>; }
-        if (pt == 1024) { *threads = 1024; return l1_first ? (const void *)poisson_dataflow_pipe_kernel<LANES, 1024, true> : (const void *)poisson_dataflow_pipe_kernel<LANES, 1024, false>; }
-        *threads = 512;
-        return l1_first ? (const void *)poisson_dataflow_pipe_kernel<LANES, 512, true> : (const void *)poisson_dataflow_pipe_kernel<LANES, 512, false>;
-    }
+    const int pt = exp_env("GLB_POISSON_THREADS", 512);           // CTA size: 512 measured best (profiles/r2_dataflow_pair_stream_ab.txt)
+    if (pt == 768) { *threads = 768; return l1_first ? (const void *)poisson_dataflow_kernel<LANES, 768, true> : (const void *)poisson_dataflow_kernel<LANES, 768, false>; }
+    if (pt == 1024) { *threads = 1024; return l1_first ? (const void *)poisson_dataflow_kernel<LANES, 1024, true> : (const void *)poisson_dataflow_kernel<LANES, 1024, false>; }
     *threads = 512;
-    return l1_first ? (const void *)poisson_dataflow_kernel<LANES, 512, 8, true>
-                    : (const void *)poisson_dataflow_kernel<LANES, 512, 8, false>;
+    return l1_first ? (const void *)poisson_dataflow_kernel<LANES, 512, true> : (const void *)poisson_dataflow_kernel<LANES, 512, false>;
 }
 
-static const void *pick_dataflow(int lanes, bool pipelined, bool l1_first, int *threads)
+static const void *pick_dataflow(int lanes, bool l1_first, int *threads)
 {
     switch (lanes) {
-        case 1: return dataflow_fn<1>(pipelined, l1_first, threads);
-        case 2: return dataflow_fn<2>(pipelined, l1_first, threads);
-        case 4: return dataflow_fn<4>(pipelined, l1_first, threads);
-        case 8: return dataflow_fn<8>(pipelined, l1_first, threads);
-        case 16: return dataflow_fn<16>(pipelined, l1_first, threads);
-        default: return dataflow_fn<32>(pipelined, l1_first, threads);
+        case 1: return dataflow_fn<1>(l1_first, threads);
+        case 2: return dataflow_fn<2>(l1_first, threads);
+        case 4: return dataflow_fn<4>(l1_first, threads);
+        case 8: return dataflow_fn<8>(l1_first, threads);
+        case 16: return dataflow_fn<16>(l1_first, threads);
+        default: return dataflow_fn<32>(l1_first, threads);
     }
 }
 
@@ -1081,7 +886,6 @@ static int plan_try_dataflow(glb_poisson_plan *p, const std::vector<int> &h_rp, 
     const int rowb = lanes * 16, rpw = 32 / lanes;
     if ((double)(n + kScratchRows) * rowb >= 4294967295.0 || n >= kRowSrcBit) return 0;
     p->l1_first = exp_env("GLB_POISSON_L1", 1) != 0;
-    p->pipelined = exp_env("GLB_POISSON_PIPE", 1) != 0;
     p->poll_sleep = (unsigned)exp_env("GLB_POISSON_SLEEP", 0) & 0xffffu;
     p->poll_sleep |= (unsigned)exp_env("GLB_POISSON_FREE", 0) << 30;        // ceiling probes, -DGLB_EXPERIMENT only
     const int pad_to = 2;
@@ -1110,7 +914,7 @@ static int plan_try_dataflow(glb_poisson_plan *p, const std::vector<int> &h_rp, 
     tm.lap("symmetry check");
 
     int threads = 0;
-    const void *fn = pick_dataflow(lanes, p->pipelined, p->l1_first, &threads);
+    const void *fn = pick_dataflow(lanes, p->l1_first, &threads);
     const int nw = threads / 32;
     std::vector<int> bounds;
     balanced_bounds(h_rp, n, grid, 2.0, bounds);
@@ -1137,7 +941,7 @@ static int plan_try_dataflow(glb_poisson_plan *p, const std::vector<int> &h_rp, 
             sl.type = kSlotNormal;
             sl.L = h_rp[order[k0] + 1] - h_rp[order[k0]];
             for (int g = 0; g < rpw; ++g) sl.rows[g] = k0 + g < order.size() ? order[k0 + g] : -1;
-            sl.cost = p->pipelined ? (sl.L + 1) / 2 + 2 : (sl.L + 15) / 16 + 1;
+            sl.cost = (sl.L + 1) / 2 + 2;
             cta_slots.push_back(sl);
         }
         // long rows: one warp-wide slot per piece of at most part_max nonzeros
@@ -1163,7 +967,7 @@ static int plan_try_dataflow(glb_poisson_plan *p, const std::vector<int> &h_rp, 
                     sl.type = kSlotPart;
                     sl.pbuf = nparts_cta + q - 1;
                 }
-                sl.cost = (p->pipelined ? (sl.L + 1) / 2 + 1 : (sl.L + 15) / 16) + 1 + (q == 0 ? m - 1 : 0);
+                sl.cost = (sl.L + 1) / 2 + 2 + (q == 0 ? m - 1 : 0);
                 cta_slots.push_back(sl);
             }
             nparts_cta += m - 1;

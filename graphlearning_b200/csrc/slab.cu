@@ -15,16 +15,17 @@
 //     group from one contiguous 128-byte run.  All slices back to back = ONE stream of pairs per warp.
 //   * boundary rows (rows a peer needs, or rows that read halo rows) come first, interior rows after them.
 //
-// Kernel (slab_step_kernel, one launch per iteration): 8 warps x 4 slices per CTA.  Lane 0 of every warp brings the
-// warp's part of the entry stream into shared memory with ONE bulk copy (cp.async.bulk -> mbarrier, TMA unit, SASS
-// UBLKCP), then the warp walks it through a ring of four pair slots - pair p+4 is issued when pair p has been consumed,
+// Kernel (slab_step_kernel, one launch per iteration): persistent CTAs of 8 warps walk the tiles (8 warps x 2 slices)
+// b, b + grid, b + 2 grid, ...  Lane 0 of every warp brings the warp's part of a tile's entry stream into shared memory
+// with ONE bulk copy (cp.async.bulk -> mbarrier, TMA unit, SASS UBLKCP) - the copy for the NEXT tile is issued before the
+// current one is processed (two stream buffers per CTA) - then the warp walks it through a ring of four pair slots - pair p+4 is issued when pair p has been consumed,
 // across slice boundaries, 6-8 label-row gathers per lane in flight (the same software pipeline as
 // poisson_dataflow_pipe_kernel); gathers go through L1 (a locality ordering makes neighbouring rows share most of
-// their columns).  Boundary CTAs (lowest block indices, scheduled first) wait until the neighbours' halo rows of this
-// version have arrived (one flag per neighbour in this rank's memory, acquire at system scope), write every finished row
-// to the local matrix AND to each peer that needs it (plain 16-byte stores to peer memory mapped through CUDA IPC), and
-// the last of them to finish releases this rank's flag in every neighbour's memory.  Interior CTAs never wait: they run
-// while the halo rows are in flight.  Three label buffers rotate (version v in buffer v % 3): a peer may already write
+// their columns).  Boundary tiles (lowest tile indices, i.e. the first pass of the CTAs) wait until the neighbours' halo
+// rows of this version have arrived (one flag per neighbour in this rank's memory, acquire at system scope), write every
+// finished row to the local matrix AND to each peer that needs it (plain 16-byte stores to peer memory mapped through
+// CUDA IPC), and the last of them to finish releases this rank's flag in every neighbour's memory.  Interior tiles never
+// wait: they run while the halo rows are in flight.  Three label buffers rotate (version v in buffer v % 3): a peer may already write
 // version t+2 while this rank still reads version t.
 //
 // Arithmetic per row: acc = 0; acc = fma(val_j, u[col_j], acc) in stored order; + Db - the same chain as
@@ -38,8 +39,8 @@
 namespace glb {
 
 constexpr int kSlabWarps = 8;                    // warps per CTA
-constexpr int kSlabSPW = 4;                      // slices per warp
-constexpr int kSlabSPC = kSlabWarps * kSlabSPW;  // slices per CTA
+constexpr int kSlabSPW = 2;                      // slices per warp and tile
+constexpr int kSlabSPC = kSlabWarps * kSlabSPW;  // slices per tile (one tile = one pass of a CTA)
 constexpr int kSlabWindow = 256;                 // rows are sorted by length inside windows of this many rows
 constexpr int kSlabLong = 64;                    // rows with more nonzeros get a slice of their own (dealt over the lane groups)
 constexpr int kSlabLongBit = 0x40000000;         // slice_rows: this slice holds ONE long row
@@ -65,7 +66,8 @@ struct SlabParams {
     unsigned *bnd_counter;           // finished boundary CTAs, monotone over launches
     unsigned bnd_target;             // counter value that means "all boundary CTAs of THIS launch are done"
     unsigned *err_flag;              // watchdog
-    int nslices, n_bnd_ctas;
+    int nslices, n_bnd_tiles;
+    int tile_entries;                // capacity of one stream buffer of a CTA, in int4
 };
 
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -137,114 +139,133 @@ slab_step_kernel(const SlabParams p)
     constexpr int RPW = 32 / LANES;
     constexpr unsigned ROWB = LANES * 16;
     extern __shared__ __align__(128) unsigned char smem[];
-    __shared__ uint64_t bars[kSlabWarps];
+    __shared__ uint64_t bars[2][kSlabWarps];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane / LANES, li = lane % LANES;
-    const int cta_s0 = min((int)blockIdx.x * kSlabSPC, p.nslices);
-    const int s0 = min(cta_s0 + warp * kSlabSPW, p.nslices), s1 = min(s0 + kSlabSPW, p.nslices);
-    const int cta_first = p.slice_first[cta_s0];
-    const int f0 = p.slice_first[s0], f1 = p.slice_first[s1];
-    const int4 *stream = reinterpret_cast<const int4 *>(smem) + (f0 - cta_first);
+    const int ntiles = (p.nslices + kSlabSPC - 1) / kSlabSPC;
     if (lane == 0) {
-        mbar_init(&bars[warp], 1);
+        mbar_init(&bars[0][warp], 1);
+        mbar_init(&bars[1][warp], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        if (f1 > f0) {                                       // this warp's part of the entry stream: one bulk copy
-            const unsigned bytes = (unsigned)(f1 - f0) * 16u;
-            mbar_expect_tx(&bars[warp], bytes);
-            bulk_g2s(const_cast<int4 *>(stream), p.ent + f0, bytes, &bars[warp]);
-        }
-    }
-    const bool boundary = (int)blockIdx.x < p.n_bnd_ctas;
-    if (boundary && p.wait_epoch) {                          // the neighbours' halo rows of this version must have landed
-        if (threadIdx.x < kMaxPeers && ((p.nbr_mask >> threadIdx.x) & 1u)) {
-            long long t0 = 0;
-            unsigned spins = 0;
-            while (ld_acquire_sys(p.my_flags + threadIdx.x) < p.wait_epoch) {
-                if ((++spins & 255u) == 0u) {
-                    if (t0 == 0) t0 = clock64();
-                    else if (clock64() - t0 > 6000000000ll || *reinterpret_cast<volatile unsigned *>(p.err_flag)) {
-                        *reinterpret_cast<volatile unsigned *>(p.err_flag) = 1u;       // a peer is gone: drain instead of hanging
-                        break;
-                    }
-                }
-            }
-        }
-        __syncthreads();
     }
     __syncwarp();
-    if (s1 > s0) {
-        if (f1 > f0) mbar_wait(&bars[warp], 0);
-        const char *in = reinterpret_cast<const char *>(p.u_in) + li * 16;
-        const int4 *cv0 = stream + g;
-        const int n_pairs = (f1 - f0) / RPW;                 // pairs of this warp's stream
-        float v0[2], v1[2], v2[2], v3[2];
-        float4 x0[2], x1[2], x2[2], x3[2];
-        if (0 < n_pairs) slab_issue(cv0, in, v0, x0);
-        if (1 < n_pairs) slab_issue(cv0 + RPW, in, v1, x1);
-        if (2 < n_pairs) slab_issue(cv0 + 2 * RPW, in, v2, x2);
-        if (3 < n_pairs) slab_issue(cv0 + 3 * RPW, in, v3, x3);
-        int q = 0, s = s0;                                   // pair being consumed, slice it belongs to
-        int left = (p.slice_first[s0 + 1] - f0) / RPW;       // pairs of slice s not yet consumed
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        // finish slice s (sum of a long row's pieces, source term, store, puts) and move to the next one
-        auto finish = [&]() {
-            int rinfo = p.slice_rows[(size_t)s * RPW + g];
-            const int r0info = __shfl_sync(0xffffffffu, rinfo, 0);
-            if (r0info >= 0 && (r0info & kSlabLongBit)) {    // warp-uniform: one long row dealt over the lane groups
-#pragma unroll
-                for (int o = LANES; o < 32; o <<= 1) {
-                    acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
-                    acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
-                    acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o);
-                    acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
-                }
-                rinfo = g == 0 ? (r0info & ~kSlabLongBit) : -1;
-            }
-            if (rinfo >= 0) {
-                const unsigned row = (unsigned)rinfo;
-                if (p.src_flag[row]) {
-                    const float4 b = __ldg(reinterpret_cast<const float4 *>(p.Db + (size_t)row * (ROWB / 4)) + li);
-                    acc.x += b.x; acc.y += b.y; acc.z += b.z; acc.w += b.w;
-                }
-                *reinterpret_cast<float4 *>(reinterpret_cast<char *>(p.u_out) + (size_t)row * ROWB + li * 16) = acc;
-                if (boundary && p.send_ptr) {                // put the row into every peer that gathers it
-                    const long long q0 = p.send_ptr[(size_t)s * RPW + g], q1 = p.send_ptr[(size_t)s * RPW + g + 1];
-                    for (long long k = q0; k < q1; ++k) {
-                        const int2 e = p.send_ent[k];
-                        *reinterpret_cast<float4 *>(reinterpret_cast<char *>(p.peer_out[e.x]) + (size_t)(unsigned)e.y * ROWB + li * 16) = acc;
+    // this warp's part of tile `tile`: slices [s0, s1), entries [f0, f1) of the stream; one bulk copy into buffer `buf`
+    auto load_tile = [&](int tile, int buf) {
+        const int cta_s0 = min(tile * kSlabSPC, p.nslices);
+        const int s0 = min(cta_s0 + warp * kSlabSPW, p.nslices), s1 = min(s0 + kSlabSPW, p.nslices);
+        const int f0 = p.slice_first[s0], f1 = p.slice_first[s1];
+        if (f1 > f0) {
+            int4 *dst = reinterpret_cast<int4 *>(smem) + (size_t)buf * p.tile_entries + (f0 - p.slice_first[cta_s0]);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // the warp's earlier reads of this buffer are done
+            mbar_expect_tx(&bars[buf][warp], (unsigned)(f1 - f0) * 16u);
+            bulk_g2s(dst, p.ent + f0, (unsigned)(f1 - f0) * 16u, &bars[buf][warp]);
+        }
+    };
+    int tile = blockIdx.x, buf = 0;
+    unsigned par0 = 0u, par1 = 0u;                           // phase parity of the two stream buffers' barriers
+    if (lane == 0 && tile < ntiles) load_tile(tile, 0);
+    bool waited = p.wait_epoch == 0u;
+    const char *in = reinterpret_cast<const char *>(p.u_in) + li * 16;
+    for (; tile < ntiles; tile += gridDim.x, buf ^= 1) {
+        __syncwarp();
+        if (lane == 0 && tile + (int)gridDim.x < ntiles) load_tile(tile + gridDim.x, buf ^ 1);      // prefetch the next tile's stream
+        const bool boundary = tile < p.n_bnd_tiles;
+        if (boundary && !waited) {                           // the neighbours' halo rows of this version must have landed
+            if (threadIdx.x < kMaxPeers && ((p.nbr_mask >> threadIdx.x) & 1u)) {
+                long long t0 = 0;
+                unsigned spins = 0;
+                while (ld_acquire_sys(p.my_flags + threadIdx.x) < p.wait_epoch) {
+                    if ((++spins & 255u) == 0u) {
+                        if (t0 == 0) t0 = clock64();
+                        else if (clock64() - t0 > 6000000000ll || *reinterpret_cast<volatile unsigned *>(p.err_flag)) {
+                            *reinterpret_cast<volatile unsigned *>(p.err_flag) = 1u;       // a peer is gone: drain instead of hanging
+                            break;
+                        }
                     }
                 }
             }
-            acc = make_float4(0.f, 0.f, 0.f, 0.f);
-            ++s;
-            if (s < s1) left = (p.slice_first[s + 1] - p.slice_first[s]) / RPW;
-        };
-        while (s < s1 && left == 0) finish();                // slices of empty rows
+            __syncthreads();
+            waited = true;
+        }
+        const int cta_s0 = min(tile * kSlabSPC, p.nslices);
+        const int s0 = min(cta_s0 + warp * kSlabSPW, p.nslices), s1 = min(s0 + kSlabSPW, p.nslices);
+        const int f0 = p.slice_first[s0], f1 = p.slice_first[s1];
+        if (s1 > s0) {
+            if (f1 > f0) {
+                mbar_wait(&bars[buf][warp], buf ? par1 : par0);
+                if (buf) par1 ^= 1u; else par0 ^= 1u;
+            }
+            const int4 *cv0 = reinterpret_cast<const int4 *>(smem) + (size_t)buf * p.tile_entries + (f0 - p.slice_first[cta_s0]) + g;
+            const int n_pairs = (f1 - f0) / RPW;             // pairs of this warp's stream
+            float v0[2], v1[2], v2[2], v3[2];
+            float4 x0[2], x1[2], x2[2], x3[2];
+            if (0 < n_pairs) slab_issue(cv0, in, v0, x0);
+            if (1 < n_pairs) slab_issue(cv0 + RPW, in, v1, x1);
+            if (2 < n_pairs) slab_issue(cv0 + 2 * RPW, in, v2, x2);
+            if (3 < n_pairs) slab_issue(cv0 + 3 * RPW, in, v3, x3);
+            int q = 0, s = s0;                               // pair being consumed, slice it belongs to
+            int left = (p.slice_first[s0 + 1] - f0) / RPW;   // pairs of slice s not yet consumed
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            // finish slice s (sum of a long row's pieces, source term, store, puts) and move to the next one
+            auto finish = [&]() {
+                int rinfo = p.slice_rows[(size_t)s * RPW + g];
+                const int r0info = __shfl_sync(0xffffffffu, rinfo, 0);
+                if (r0info >= 0 && (r0info & kSlabLongBit)) {    // warp-uniform: one long row dealt over the lane groups
+#pragma unroll
+                    for (int o = LANES; o < 32; o <<= 1) {
+                        acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
+                        acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+                        acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o);
+                        acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
+                    }
+                    rinfo = g == 0 ? (r0info & ~kSlabLongBit) : -1;
+                }
+                if (rinfo >= 0) {
+                    const unsigned row = (unsigned)rinfo;
+                    if (p.src_flag[row]) {
+                        const float4 b = __ldg(reinterpret_cast<const float4 *>(p.Db + (size_t)row * (ROWB / 4)) + li);
+                        acc.x += b.x; acc.y += b.y; acc.z += b.z; acc.w += b.w;
+                    }
+                    *reinterpret_cast<float4 *>(reinterpret_cast<char *>(p.u_out) + (size_t)row * ROWB + li * 16) = acc;
+                    if (boundary && p.send_ptr) {            // put the row into every peer that gathers it
+                        const long long q0 = p.send_ptr[(size_t)s * RPW + g], q1 = p.send_ptr[(size_t)s * RPW + g + 1];
+                        for (long long k = q0; k < q1; ++k) {
+                            const int2 e = p.send_ent[k];
+                            *reinterpret_cast<float4 *>(reinterpret_cast<char *>(p.peer_out[e.x]) + (size_t)(unsigned)e.y * ROWB + li * 16) = acc;
+                        }
+                    }
+                }
+                acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                ++s;
+                if (s < s1) left = (p.slice_first[s + 1] - p.slice_first[s]) / RPW;
+            };
+            while (s < s1 && left == 0) finish();            // slices of empty rows
 #define GLB_SLAB_STEP(V, X)                                                                          \
-        {                                                                                            \
-            if (q >= n_pairs) break;                                                                 \
-            slab_consume(V, X, acc);                                                                 \
-            if (q + 4 < n_pairs) slab_issue(cv0 + (size_t)(q + 4) * RPW, in, V, X);                  \
-            ++q;                                                                                     \
-            if (--left == 0) { finish(); while (s < s1 && left == 0) finish(); }                     \
-        }
-        for (;;) {
-            GLB_SLAB_STEP(v0, x0)
-            GLB_SLAB_STEP(v1, x1)
-            GLB_SLAB_STEP(v2, x2)
-            GLB_SLAB_STEP(v3, x3)
-        }
+            {                                                                                        \
+                if (q >= n_pairs) break;                                                             \
+                slab_consume(V, X, acc);                                                             \
+                if (q + 4 < n_pairs) slab_issue(cv0 + (size_t)(q + 4) * RPW, in, V, X);              \
+                ++q;                                                                                 \
+                if (--left == 0) { finish(); while (s < s1 && left == 0) finish(); }                 \
+            }
+            for (;;) {
+                GLB_SLAB_STEP(v0, x0)
+                GLB_SLAB_STEP(v1, x1)
+                GLB_SLAB_STEP(v2, x2)
+                GLB_SLAB_STEP(v3, x3)
+            }
 #undef GLB_SLAB_STEP
-    }
-    if (boundary && p.nbr_mask) {
-        __syncthreads();                                     // every put of this CTA is issued ...
-        if (threadIdx.x == 0) {
-            __threadfence_system();                          // ... and ordered before the count
-            const unsigned done = atomicAdd(p.bnd_counter, 1u) + 1u;
-            if (done == p.bnd_target) {                      // last boundary CTA of this launch: release the neighbours
-                __threadfence_system();
-                for (int r = 0; r < kMaxPeers; ++r)
-                    if ((p.nbr_mask >> r) & 1u) st_release_sys(p.peer_flag[r], p.signal_epoch);
+        }
+        if (boundary && p.nbr_mask) {
+            __syncthreads();                                 // every put of this tile is issued ...
+            if (threadIdx.x == 0) {
+                __threadfence_system();                      // ... and ordered before the count
+                const unsigned done = atomicAdd(p.bnd_counter, 1u) + 1u;
+                if (done == p.bnd_target) {                  // last boundary tile of this launch: release the neighbours
+                    __threadfence_system();
+                    for (int r = 0; r < kMaxPeers; ++r)
+                        if ((p.nbr_mask >> r) & 1u) st_release_sys(p.peer_flag[r], p.signal_epoch);
+                }
             }
         }
     }
@@ -288,7 +309,7 @@ using namespace glb;
 struct glb_slab {
     int64_t m = 0, rows_total = 0, nnz = 0;
     int c = 0, ld = 0, lanes = 0, rpw = 0;
-    int nslices = 0, n_bnd_slices = 0, grid = 0;
+    int nslices = 0, n_bnd_slices = 0, grid = 0, tile_entries = 0;
     size_t smem_bytes = 0;
     double fill = 1.0;
     int4 *d_ent = nullptr;
@@ -371,7 +392,7 @@ extern "C" GLB_API int glb_slab_create(glb_slab **out, const int32_t *h_rowptr, 
                 slices.push_back(sl);
             }
         }
-        if (pass == 0) {                                     // boundary slices fill whole CTAs
+        if (pass == 0) {                                     // boundary slices fill whole tiles
             while (slices.size() % kSlabSPC) {
                 Slice sl{};
                 for (int q = 0; q < rpw; ++q) sl.rows[q] = -1;
@@ -447,22 +468,26 @@ extern "C" GLB_API int glb_slab_create(glb_slab **out, const int32_t *h_rowptr, 
     int dev = 0, max_smem = 0;
     GLB_CUDA(cudaGetDevice(&dev));
     cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-    if (max_cta + 1024 > (size_t)max_smem) {
-        set_error("glb_slab_create: a CTA's entry stream needs %zu bytes of shared memory (a row is too long for the slab kernel)", max_cta);
+    if (2 * max_cta + 1024 > (size_t)max_smem) {
+        set_error("glb_slab_create: a tile's entry stream needs 2 x %zu bytes of shared memory (a row is too long for the slab kernel)", max_cta);
         return GLB_E_UNSUPPORTED;
     }
     glb_slab *s = new glb_slab();
     struct Guard { glb_slab *s; ~Guard() { if (s) glb_slab_destroy(s); } } guard{s};
     s->m = m; s->rows_total = rows_total; s->nnz = nnz; s->c = c; s->ld = ld; s->lanes = lanes; s->rpw = rpw;
     s->nslices = nslices; s->n_bnd_slices = n_bnd_slices;
-    s->grid = (nslices + kSlabSPC - 1) / kSlabSPC;
-    s->smem_bytes = std::max<size_t>(max_cta, 16);
+    s->tile_entries = (int)(std::max<size_t>(max_cta, 16) / 16);
+    s->smem_bytes = 2 * (size_t)s->tile_entries * 16;
     s->fill = stored ? (double)nnz / (double)stored : 1.0;
     s->fn = slab_pick(lanes);
     GLB_CUDA(cudaFuncSetAttribute(s->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes));
     {   // shared-memory carve-out for three resident CTAs (80 registers x 256 threads); the rest of the 228 KB stays L1 for the label-row gathers
         const size_t want = std::min<size_t>(3 * (s->smem_bytes + 1024), (size_t)max_smem);
         cudaFuncSetAttribute(s->fn, cudaFuncAttributePreferredSharedMemoryCarveout, (int)std::min<size_t>(100, (want * 100 + max_smem - 1) / max_smem));
+        int per_sm = 0;
+        GLB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, s->fn, kSlabWarps * 32, s->smem_bytes));
+        const int ntiles = (nslices + kSlabSPC - 1) / kSlabSPC;
+        s->grid = std::max(1, std::min(ntiles, std::max(1, per_sm) * sm_count()));        // persistent: every CTA walks tiles b, b + grid, ...
     }
     GLB_CUDA(cudaMalloc(&s->d_ent, sizeof(int4) * std::max<size_t>(ent.size(), 1)));
     GLB_CUDA(cudaMalloc(&s->d_slice_first, sizeof(int) * (nslices + 1)));
@@ -565,7 +590,7 @@ extern "C" GLB_API int glb_slab_iterate(glb_slab *s, const float *d_Db, int T, i
     p.my_flags = reinterpret_cast<const unsigned *>(s->region[s->rank]);
     p.nbr_mask = s->nbr_mask;
     p.bnd_counter = s->d_sync; p.err_flag = s->d_sync + 1;
-    p.nslices = s->nslices; p.n_bnd_ctas = s->n_bnd_slices / kSlabSPC;
+    p.nslices = s->nslices; p.n_bnd_tiles = s->n_bnd_slices / kSlabSPC; p.tile_entries = s->tile_entries;
     for (int r = 0; r < s->world; ++r)
         if ((s->nbr_mask >> r) & 1u) p.peer_flag[r] = reinterpret_cast<unsigned *>(s->region[r]) + s->rank;
     for (int t = 0; t < T; ++t) {
@@ -577,7 +602,7 @@ extern "C" GLB_API int glb_slab_iterate(glb_slab *s, const float *d_Db, int T, i
         p.wait_epoch = t == 0 ? 0u : s->epoch;               // version 0 is the caller's (reset + barrier before the run)
         p.signal_epoch = ++s->epoch;
         s->launches += 1;
-        p.bnd_target = (unsigned)p.n_bnd_ctas * s->launches;
+        p.bnd_target = (unsigned)p.n_bnd_tiles * s->launches;
         void *args[] = {(void *)&p};
         GLB_CUDA(cudaLaunchKernel(s->fn, dim3(s->grid), dim3(kSlabWarps * 32), args, s->smem_bytes, st));
     }

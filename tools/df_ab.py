@@ -4,7 +4,7 @@ creation reads the switches below.  Prints one line per configuration.  Not part
 
     GLB200_LIB=graphlearning_b200/lib/libglb200_exp.so python tools/df_ab.py [hub] [stats]
 
-switches: GLB_POISSON_PIPE (0 batch kernel / 1 pipelined stream), GLB_POISSON_L1 (first gather attempt through L1),
+switches: GLB_POISSON_L1 (first gather attempt through L1),
 GLB_POISSON_THREADS (CTA size of the pipelined kernel), reorder (RCM locality ordering of the operator)."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -35,7 +35,7 @@ print("graph: n=%d nnz=%d max row %d; bytes/iteration %d" % (n, W.nnz, int(np.di
 
 def run(label, env, reorder):
     global first
-    for k in ("GLB_POISSON_PIPE", "GLB_POISSON_L1", "GLB_POISSON_THREADS", "GLB_POISSON_SLEEP", "GLB_POISSON_GATE_EVERY", "GLB_POISSON_FREE"):
+    for k in ("GLB_POISSON_L1", "GLB_POISSON_THREADS", "GLB_POISSON_SLEEP", "GLB_POISSON_GATE_EVERY", "GLB_POISSON_FREE"):
         os.environ.pop(k, None)
     os.environ.update({k: str(v) for k, v in env.items()})
     try:
@@ -65,22 +65,14 @@ def run(label, env, reorder):
 first = None
 if "free" in sys.argv:
     # ceiling probes: no synchronisation at all (free=1), and no stores either (free=3); results are wrong by design
-    for pipe, l1, reorder in ((1, 1, 1), (1, 1, 0), (1, 0, 0), (0, 0, 0), (0, 1, 1)):
+    for l1, reorder in ((1, 1), (1, 0), (0, 0)):
         for free in (0, 1, 3):
-            run("pipe=%d l1=%d free=%d" % (pipe, l1, free),
-                {"GLB_POISSON_PIPE": pipe, "GLB_POISSON_L1": l1, "GLB_POISSON_FREE": free, "GLB_POISSON_GATE_EVERY": 1 if free == 0 else 0}, reorder)
+            run("l1=%d free=%d" % (l1, free), {"GLB_POISSON_L1": l1, "GLB_POISSON_FREE": free, "GLB_POISSON_GATE_EVERY": 1 if free == 0 else 0}, reorder)
 elif "sleep" in sys.argv:
-    for pipe, l1, reorder in ((1, 1, 1), (1, 1, 0), (0, 0, 0), (0, 1, 1)):
+    for l1, reorder in ((1, 1), (0, 0)):
         for sleep in (0, 100, 400, 1500):
             for gate in (0, 32, 4, 1):
-                run("pipe=%d l1=%d sleep=%d gate_forced=%d" % (pipe, l1, sleep, gate),
-                    {"GLB_POISSON_PIPE": pipe, "GLB_POISSON_L1": l1, "GLB_POISSON_SLEEP": sleep, "GLB_POISSON_GATE_EVERY": gate}, reorder)
+                run("l1=%d sleep=%d gate_forced=%d" % (l1, sleep, gate), {"GLB_POISSON_L1": l1, "GLB_POISSON_SLEEP": sleep, "GLB_POISSON_GATE_EVERY": gate}, reorder)
 else:
-    #          pipe l1  threads reorder
-    configs = [(0, 0, 512, 0), (1, 1, 512, 0), (1, 1, 512, 1), (1, 1, 768, 0), (1, 1, 768, 1), (1, 1, 1024, 1), (1, 0, 512, 0), (1, 0, 768, 0)]
-    for pipe, l1, threads, reorder in configs:
-        run("pipe=%d l1=%d threads=%d" % (pipe, l1, threads), {"GLB_POISSON_PIPE": pipe, "GLB_POISSON_L1": l1, "GLB_POISSON_THREADS": threads}, reorder)
-    for threads in (512, 768):
-        for free in (1, 3):
-            run("pipe=1 l1=1 threads=%d free=%d" % (threads, free), {"GLB_POISSON_PIPE": 1, "GLB_POISSON_L1": 1, "GLB_POISSON_THREADS": threads,
-                                                                     "GLB_POISSON_FREE": free, "GLB_POISSON_GATE_EVERY": 0}, 1)
+    for l1, threads, reorder in ((1, 512, 1), (1, 512, 0), (0, 512, 0), (0, 512, 1), (1, 768, 1), (1, 1024, 1)):
+        run("l1=%d threads=%d" % (l1, threads), {"GLB_POISSON_L1": l1, "GLB_POISSON_THREADS": threads}, reorder)
