@@ -17,6 +17,7 @@ _lib = None
 # name -> (restype, argtypes).  Mirrors include/glb200.h one to one (tests/test_abi.py checks that).
 SIGNATURES = {
     "glb_version": (c_int, []),
+    "glb_release_workspace": (c_int, []),
     "glb_last_error": (c_char_p, []),
     "glb_device_info": (c_int, [POINTER(c_int), POINTER(c_int), POINTER(c_int), POINTER(c_int64)]),
     "glb_padded_ld": (c_int, [c_int]),
@@ -86,6 +87,10 @@ SIGNATURES = {
     "glb_ipc_open": (c_int, [c_void_p, POINTER(c_void_p)]),
     "glb_ipc_close": (c_int, [c_void_p]),
     "glb_ipc_free": (c_int, [c_void_p]),
+    "glb_volume_projection": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_int, c_int, c_double, c_void_p, c_void_p, c_void_p,
+                                      c_void_p, c_void_p]),
+    "glb_onehot_f64": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p]),
+    "glb_max_abs_diff_f64": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, POINTER(c_double), c_void_p]),
     "glb_poisson_gd_host": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int, c_void_p, c_int64,
                                     c_int, c_int, c_void_p, POINTER(c_int), POINTER(c_int)]),
 }

@@ -13,12 +13,12 @@ constexpr int64_t kReorderMinNodes = 4096;
 
 struct DeviceArena {           // frees everything on scope exit, whatever the return path
     std::vector<void *> ptrs;
-    ~DeviceArena() { for (void *p : ptrs) cudaFree(p); }
+    ~DeviceArena() { for (void *p : ptrs) dev_free(p); }
     template <typename T>
     cudaError_t alloc(T **p, size_t count)
     {
         void *q = nullptr;
-        cudaError_t e = cudaMalloc(&q, (count ? count : 1) * sizeof(T));
+        cudaError_t e = dev_alloc(&q, (count ? count : 1) * sizeof(T));
         if (e == cudaSuccess) ptrs.push_back(q);
         *p = (T *)q;
         return e;

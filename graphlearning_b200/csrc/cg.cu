@@ -390,8 +390,8 @@ extern "C" GLB_API int glb_cg_host(const int32_t *h_rowptr, const int32_t *h_col
     if (wb < 0) { set_error("glb_cg_host: unsupported shape (c = %d)", c); return (int)wb; }
     const int ldu = glb_padded_ld(c);
     cudaStream_t st = 0;
-    struct Arena { std::vector<void *> v; ~Arena() { for (void *p : v) cudaFree(p); } } A;
-    auto alloc = [&](void **p, size_t bytes) { cudaError_t e = cudaMalloc(p, bytes ? bytes : 1); if (e == cudaSuccess) A.v.push_back(*p); return e; };
+    struct Arena { std::vector<void *> v; ~Arena() { for (void *p : v) dev_free(p); } } A;
+    auto alloc = [&](void **p, size_t bytes) { cudaError_t e = dev_alloc(p, bytes ? bytes : 1); if (e == cudaSuccess) A.v.push_back(*p); return e; };
     int *rp, *col; double *val, *b, *x, *x0 = nullptr, *stage; void *work;
     const size_t nz = (size_t)(nnz > 0 ? nnz : 1);
     GLB_CUDA(alloc((void **)&rp, (n + 1) * sizeof(int)));   GLB_CUDA(alloc((void **)&col, nz * sizeof(int)));

@@ -39,6 +39,16 @@ static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b)
 
 int sm_count();   // cached, current device
 
+// Device memory of the library's own scratch and plans comes from the CUDA stream-ordered pool (cudaMallocAsync) with the
+// release threshold lifted: a freed block stays mapped, so the next plan / search does not pay the driver's map and unmap
+// again (53 of the 96 ms of a first fit and 68 of the 83 ms of a kNN search went there, profiles/r2_first_fit_timing.txt).
+// Blocks are usable on every stream once dev_alloc has returned; dev_free may be called when the work that uses the block
+// has been synchronised.  glb_release_workspace() hands the cached blocks back to the driver.
+cudaError_t dev_alloc_bytes(void **p, size_t bytes);
+cudaError_t dev_free(void *p);
+template <typename T>
+static inline cudaError_t dev_alloc(T **p, size_t bytes) { return dev_alloc_bytes(reinterpret_cast<void **>(p), bytes); }
+
 // GLB_TIMING=1: wall-clock phases of the host entry points on stderr (setup-cost experiments)
 struct PhaseTimer {
     bool on;

@@ -27,6 +27,7 @@
 //                       k-step into one fp32 TMEM accumulator (see the kernel).
 // Roofline: stage 2 is 2 n^2 d flops (fp32 FMA for d < 64, 3 x bf16 tensor-core MMAs for d >= 64); stages 2+3 move
 // 2 * 4 n^2 bytes through HBM/L2 (the distance block), stage 4 gathers C rows of fp64 features per query.
+#include <cuda.h>
 #include <cuda_bf16.h>
 #include <float.h>
 #include <stdlib.h>
@@ -423,7 +424,7 @@ __global__ void __launch_bounds__(256)
 knn_rerank_kernel(const double *__restrict__ X, int n, int d, const float *__restrict__ norm2,
                   const unsigned long long *__restrict__ rmax2_bits, const u64 *__restrict__ cand, int q0, int nq, int k,
                   long long *__restrict__ out_ind, double *__restrict__ out_dist, int *__restrict__ fail_rows,
-                  int *__restrict__ fail_count, double err_rel)
+                  int *__restrict__ fail_count, double err_rel, const float *__restrict__ outside_bound)
 {
     constexpr int C = 32 * NPL;
     const int lane = threadIdx.x & 31;
@@ -459,8 +460,10 @@ knn_rerank_kernel(const double *__restrict__ X, int n, int d, const float *__res
     const double R = sqrt(__longlong_as_double((long long)*rmax2_bits));
     const double ni = sqrt((double)norm2[q]);
     const double E = 2.0 * err_rel * (ni + R) * (ni + R);      // err_rel: bound on |approx cross term - exact| / (|x||y|)
-    // fewer than C points in total (n <= C): the list holds everything, nothing can be missing
-    const bool certified = (key_c == ~0ull) || ((double)ac - (double)ak > 2.0 * E);
+    // fewer than C points in total (n <= C): the list holds everything, nothing can be missing.
+    // outside_bound (fused search): a lower bound on the approximate distance of every point that is NOT in the list.
+    const bool certified = outside_bound ? (key_k != ~0ull && (double)outside_bound[wq] - (double)ak > 2.0 * E)
+                                         : ((key_c == ~0ull) || ((double)ac - (double)ak > 2.0 * E));
     // rank of every candidate among the C by (exact d2, index): O(C) shuffles per element, C <= 128
     int rank[NPL];
 #pragma unroll
@@ -529,18 +532,396 @@ knn_exact_rows_kernel(const double *__restrict__ X, int n, int d, const int *__r
     }
 }
 
-struct KnnArena {
-    std::vector<void *> v;
-    ~KnnArena() { for (void *p : v) cudaFree(p); }
-    cudaError_t alloc(void **p, size_t bytes) { cudaError_t e = cudaMalloc(p, bytes ? bytes : 1); if (e == cudaSuccess) v.push_back(*p); return e; }
+// ---------------------------------------------------------------------------------------------------------
+// 2c + 3c. fused distance block + candidate filter on the tensor cores: D never leaves the SM
+// ---------------------------------------------------------------------------------------------------------
+// One CTA = 128 queries against ALL database points, 128 at a time.  Warp roles (192 threads):
+//   warp 0   TMA producer: cp.async.bulk.tensor (SASS UTMALDG) of 128 x 64 bf16 operand tiles (hi and lo halves of the split
+//            features) into 128-byte-swizzled shared memory, a ring of stages with full/empty mbarriers.  The query tiles
+//            are loaded once and stay resident when they fit (d <= 256), the database tiles stream.
+//   warp 1   MMA issuer: one thread issues tcgen05.mma (M = N = 128, K = 16, SASS UTCHMMA) hi.hi + hi.lo + lo.hi per k-step
+//            into one of TWO 128-column fp32 accumulators in TMEM, commits the stage (frees it for the producer) and, after
+//            the last k-block, the accumulator (hands it to the epilogue) - the tensor pipe starts the next database tile
+//            while the epilogue drains the previous one.
+//   warps 2-9  epilogue: thread = (query row = TMEM lane, half of the tile's 128 columns); two warps per scheduler so that the
+//            dependent ALU chains of one hide behind the other.  tcgen05.ld 32 columns at a time, d = |q|^2 + |x_j|^2 - 2 acc
+//            for all 32 (branch-free, a hit mask), then only the hits:
+//            MODE_SAMPLE  keep the R smallest distances in registers -> written per (row, half); the R-th smallest of the
+//                         union is tau_row
+//            MODE_EMIT    append (d, j) to the (row, half) candidate buffer in HBM when d <= tau_row (0.2 % of the points)
+// Two passes: MODE_SAMPLE against a fixed pseudo-random sample of s database points gives every row a threshold tau_row
+// whose expected rank in the full set is n R / s (137 for n = 70 000, R = 16, s = 8192); MODE_EMIT then writes only the
+// points below it.  A row's candidate list = its C smallest emitted points (knn_pick_kernel); every point outside the list
+// has an approximate distance >= min(tau_row, C-th smallest emitted), which is what the certificate of stage 4 needs.
+// Rows whose buffer overflows (> cap candidates) or that miss the certificate go to the exact fp64 fallback.
+constexpr int FBM = 128, FBN = 128, FBK = 64;
+constexpr int kFusedThreads = 320;                               // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
+constexpr int kEpiThreads = 256;
+constexpr int kFTile = FBM * FBK * 2;                            // 16 KB: one 128 x 64 bf16 operand tile, 128-byte swizzle
+constexpr int kSampleR = 16;                                     // rank of the threshold inside the sample
+constexpr int MODE_SAMPLE = 0, MODE_EMIT = 1;
+
+__device__ __forceinline__ void mbar_init_n(unsigned mbar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect(unsigned mbar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned mbar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mbar) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(unsigned dst, const CUtensorMap *map, int c0, int c1, unsigned mbar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(mbar) : "memory");
+}
+__device__ __forceinline__ unsigned long long umma_desc_sw128(unsigned saddr)
+{
+    // K-major, 128-byte swizzle: start address [0,14) | LBO [16,30) = 1 (unused) | SBO [32,46) = 1024 B (8 rows x 128 B)
+    // | version [46,48) = 1 | layout type [61,64) = 2 (SWIZZLE_128B); offsets in 16-byte units
+    return (unsigned long long)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((unsigned long long)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ void umma_commit(unsigned mbar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar) : "memory");
+}
+
+struct FusedArgs {
+    const float *norm_q;             // |q|^2 of the queries (index = global query row)
+    const float *norm_d;             // |x_j|^2 of the database (or sample) points
+    int q0, nq;                      // query rows [q0, q0 + nq)
+    int nd;                          // database points
+    int kb_per_tile;                 // dpad / 64
+    int stages;                      // ring depth
+    int a_resident;                  // query tiles loaded once
+    // MODE_SAMPLE: the kSampleR smallest sample distances of every (row, column half), ascending
+    float *best_out;                 // [((row - q0) * 2 + half) * kSampleR]
+    // MODE_EMIT
+    const float *best_in;            // the same array: tau_row = kSampleR-th smallest of the two lists
+    float *tau_out;                  // [row - q0] (written by half 0; knn_pick_kernel needs it)
+    u64 *cand_buf;                   // [((row - q0) * 2 + half) * cap]
+    int *cand_count;                 // [(row - q0) * 2 + half]; cap + 1 = overflow
+    int cap;                         // per (row, half)
 };
 
-// GLB_KNN_TC=0 forces the fp32 SIMT distance kernel (A/B runs); default: tensor cores when d >= 64
-static bool knn_use_tc(int d)
+template <int MODE>
+__global__ void __launch_bounds__(kFusedThreads, 1)
+knn_fused_kernel(const __grid_constant__ CUtensorMap tm_qh, const __grid_constant__ CUtensorMap tm_ql,
+                 const __grid_constant__ CUtensorMap tm_dh, const __grid_constant__ CUtensorMap tm_dl, const FusedArgs a)
 {
-    const char *e = getenv("GLB_KNN_TC");
-    if (e) return atoi(e) != 0;
-    return d >= 64;
+    extern __shared__ unsigned char fused_raw[];
+    const unsigned raw = smem_u32(fused_raw);
+    const unsigned base = (raw + 1023u) & ~1023u;                // swizzle atoms want 1024-byte alignment
+    unsigned char *gen = fused_raw + (base - raw);
+    const int S = a.stages, KB = a.kb_per_tile;
+    const int tiles_per_stage = a.a_resident ? 2 : 4;            // (B hi, B lo) or (A hi, A lo, B hi, B lo)
+    const unsigned a_res = base;                                 // resident query tiles: KB x (hi, lo)
+    const unsigned ring = base + (a.a_resident ? (unsigned)KB * 2u * kFTile : 0u);
+    const unsigned ctl = ring + (unsigned)S * tiles_per_stage * kFTile;
+    // control block: full[S], empty[S], tmem_full[2], tmem_empty[2], a_full, tmem slot; then the norm tiles
+    const unsigned bar_full = ctl, bar_empty = ctl + 8u * S, bar_tfull = ctl + 16u * S, bar_tempty = bar_tfull + 16u, bar_afull = bar_tempty + 16u;
+    const unsigned tmem_slot_a = bar_afull + 8u;
+    const unsigned nb_a = (tmem_slot_a + 8u + 15u) & ~15u;      // |x_j|^2 of the current database tiles: [2][128] floats
+    volatile unsigned *tmem_slot = reinterpret_cast<volatile unsigned *>(gen + (tmem_slot_a - base));
+    float *s_nb = reinterpret_cast<float *>(gen + (nb_a - base));
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int row0 = a.q0 + blockIdx.x * FBM;
+    const int ntiles = (a.nd + FBN - 1) / FBN;
+
+    if (tid == 0) {
+        for (int i = 0; i < S; ++i) { mbar_init_n(bar_full + 8u * i, 1); mbar_init_n(bar_empty + 8u * i, 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init_n(bar_tfull + 8u * i, 1); mbar_init_n(bar_tempty + 8u * i, kEpiThreads); }
+        mbar_init_n(bar_afull, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(tmem_slot_a) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const unsigned tmem_d = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            if (a.a_resident) {
+                mbar_expect(bar_afull, (unsigned)KB * 2u * kFTile);
+                for (int kb = 0; kb < KB; ++kb) {
+                    tma_load_2d(a_res + (unsigned)(2 * kb) * kFTile, &tm_qh, kb * FBK, row0, bar_afull);
+                    tma_load_2d(a_res + (unsigned)(2 * kb + 1) * kFTile, &tm_ql, kb * FBK, row0, bar_afull);
+                }
+            }
+            int it = 0;
+            for (int tile = 0; tile < ntiles; ++tile)
+                for (int kb = 0; kb < KB; ++kb, ++it) {
+                    const int st = it % S;
+                    mbar_wait(bar_empty + 8u * st, (unsigned)(((it / S) & 1) ^ 1));      // a fresh barrier passes parity 1
+                    mbar_expect(bar_full + 8u * st, (unsigned)tiles_per_stage * kFTile);
+                    const unsigned sb = ring + (unsigned)st * tiles_per_stage * kFTile;
+                    tma_load_2d(sb, &tm_dh, kb * FBK, tile * FBN, bar_full + 8u * st);
+                    tma_load_2d(sb + kFTile, &tm_dl, kb * FBK, tile * FBN, bar_full + 8u * st);
+                    if (!a.a_resident) {
+                        tma_load_2d(sb + 2 * kFTile, &tm_qh, kb * FBK, row0, bar_full + 8u * st);
+                        tma_load_2d(sb + 3 * kFTile, &tm_ql, kb * FBK, row0, bar_full + 8u * st);
+                    }
+                }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            const unsigned idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(FBN >> 3) << 17) | ((unsigned)(FBM >> 4) << 24);
+            if (a.a_resident) mbar_wait(bar_afull, 0u);
+            int it = 0;
+            for (int tile = 0; tile < ntiles; ++tile) {
+                const int acc = tile & 1;
+                mbar_wait(bar_tempty + 8u * acc, (unsigned)(((tile >> 1) & 1) ^ 1));       // the epilogue has drained this accumulator
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const unsigned d_tmem = tmem_d + (unsigned)(acc * FBN);
+                for (int kb = 0; kb < KB; ++kb, ++it) {
+                    const int st = it % S;
+                    mbar_wait(bar_full + 8u * st, (unsigned)((it / S) & 1));
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const unsigned sb = ring + (unsigned)st * tiles_per_stage * kFTile;
+                    const unsigned b_hi = sb, b_lo = sb + kFTile;
+                    const unsigned a_hi = a.a_resident ? a_res + (unsigned)(2 * kb) * kFTile : sb + 2 * kFTile;
+                    const unsigned a_lo = a_hi + kFTile;
+#pragma unroll
+                    for (int ks = 0; ks < FBK / 16; ++ks) {      // K = 16 per instruction = 32 bytes along the swizzled row
+                        const unsigned o = ks * 32;
+                        umma_bf16(d_tmem, umma_desc_sw128(a_hi + o), umma_desc_sw128(b_hi + o), idesc, (kb | ks) ? 1u : 0u);
+                        umma_bf16(d_tmem, umma_desc_sw128(a_hi + o), umma_desc_sw128(b_lo + o), idesc, 1u);
+                        umma_bf16(d_tmem, umma_desc_sw128(a_lo + o), umma_desc_sw128(b_hi + o), idesc, 1u);
+                    }
+                    umma_commit(bar_empty + 8u * st);            // the stage is free once these MMAs have read it
+                }
+                umma_commit(bar_tfull + 8u * acc);               // accumulator complete -> epilogue
+            }
+        }
+    } else {
+        // ===== epilogue: thread = (query row, column half) =====
+        const int wq = warp & 3;                                 // a warp may only touch TMEM lanes 32 (warp % 4) ...
+        const int half = (warp - 2) >> 2;                        // warps 2-5: columns 0-63 of a tile, warps 6-9: columns 64-127
+        const int r = wq * 32 + lane;
+        const int et = (warp - 2) * 32 + lane;                   // 0..255 among the epilogue threads
+        const int q = row0 + r;
+        const bool live = q < a.q0 + a.nq;
+        const float na = live ? __ldg(a.norm_q + q) : 0.f;
+        const size_t slot = (size_t)(live ? q - a.q0 : 0) * 2 + half;
+        float tau = -1.f;
+        int cnt = 0;
+        float best[kSampleR];
+        if (MODE == MODE_SAMPLE) {
+#pragma unroll
+            for (int i = 0; i < kSampleR; ++i) best[i] = INFINITY;
+            tau = live ? INFINITY : -1.f;
+        } else if (live) {
+            // tau_row = kSampleR-th smallest of the union of the two halves' sorted lists
+            const float *l0 = a.best_in + (size_t)(q - a.q0) * 2 * kSampleR, *l1 = l0 + kSampleR;
+            int i0 = 0, i1 = 0;
+            float t = INFINITY;
+            for (int i = 0; i < kSampleR; ++i) {
+                const float x0 = l0[i0], x1 = l1[i1];
+                if (x0 <= x1) { t = x0; ++i0; } else { t = x1; ++i1; }
+            }
+            tau = t;
+            if (half == 0) a.tau_out[q - a.q0] = tau;
+        }
+        u64 *mybuf = MODE == MODE_EMIT ? a.cand_buf + slot * a.cap : nullptr;
+        for (int tile = 0; tile < ntiles; ++tile) {
+            const int acc = tile & 1;
+            const int col0 = tile * FBN;
+            if (et < FBN) s_nb[acc * FBN + et] = (col0 + et < a.nd) ? __ldg(a.norm_d + col0 + et) : INFINITY;     // +inf: never a candidate
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            mbar_wait(bar_tfull + 8u * acc, (unsigned)((tile >> 1) & 1));
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+            for (int cb = half * 2; cb < half * 2 + 2; ++cb) {
+                unsigned v[32];
+                const unsigned taddr = tmem_d + ((unsigned)(wq * 32) << 16) + (unsigned)(acc * FBN + cb * 32);
+                asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                             : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+                               "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+                               "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+                               "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                             : "r"(taddr) : "memory");
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                const float4 *nb4 = reinterpret_cast<const float4 *>(s_nb + acc * FBN + cb * 32);
+                // all 32 distances first (independent fused multiply-adds, no branch), as a hit mask
+                float d2[32];
+                unsigned hits = 0u;
+#pragma unroll
+                for (int j4 = 0; j4 < 8; ++j4) {
+                    const float4 nb = nb4[j4];
+                    d2[j4 * 4 + 0] = fmaf(-2.f, __uint_as_float(v[j4 * 4 + 0]), na + nb.x);
+                    d2[j4 * 4 + 1] = fmaf(-2.f, __uint_as_float(v[j4 * 4 + 1]), na + nb.y);
+                    d2[j4 * 4 + 2] = fmaf(-2.f, __uint_as_float(v[j4 * 4 + 2]), na + nb.z);
+                    d2[j4 * 4 + 3] = fmaf(-2.f, __uint_as_float(v[j4 * 4 + 3]), na + nb.w);
+                }
+#pragma unroll
+                for (int j = 0; j < 32; ++j) hits |= (MODE == MODE_SAMPLE ? d2[j] < tau : d2[j] <= tau) ? (1u << j) : 0u;
+                if (hits) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        if (hits & (1u << j)) {
+                            const float dd = fmaxf(d2[j], 0.f);
+                            if (MODE == MODE_SAMPLE) {
+                                if (dd < best[kSampleR - 1]) {       // tau shrinks while the hits of this chunk are taken
+                                    best[kSampleR - 1] = dd;         // replace the largest, bubble it into place
+#pragma unroll
+                                    for (int i = kSampleR - 1; i > 0; --i) {
+                                        const float lo = fminf(best[i - 1], best[i]), hi = fmaxf(best[i - 1], best[i]);
+                                        best[i - 1] = lo; best[i] = hi;
+                                    }
+                                    tau = best[kSampleR - 1];
+                                }
+                            } else {
+                                if (cnt < a.cap) mybuf[cnt] = make_key(dd, col0 + cb * 32 + j);
+                                ++cnt;
+                            }
+                        }
+                    }
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(bar_tempty + 8u * acc);
+        }
+        if (live) {
+            if (MODE == MODE_SAMPLE) {
+#pragma unroll
+                for (int i = 0; i < kSampleR; ++i) a.best_out[slot * kSampleR + i] = best[i];
+            } else {
+                a.cand_count[slot] = cnt <= a.cap ? cnt : a.cap + 1;
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem_d) : "memory");
+}
+
+// the C smallest of a row's emitted candidates (sorted, as knn_select_kernel leaves them) + the bound on everything else
+template <int NPL>
+__global__ void __launch_bounds__(256)
+knn_pick_kernel(const u64 *__restrict__ cand_buf, const int *__restrict__ cand_count, const float *__restrict__ tau, int cap, int q0, int nq,
+                u64 *__restrict__ cand, float *__restrict__ outside_bound, int *__restrict__ fail_rows, int *__restrict__ fail_count)
+{
+    constexpr int C = 32 * NPL;
+    const int lane = threadIdx.x & 31;
+    const int wq = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (wq >= nq) return;
+    WarpList<NPL> list;
+    list.init();
+    u64 tau_key = ~0ull;
+    int total = 0;
+    bool overflow = false;
+    for (int half = 0; half < 2; ++half) {                   // the two column halves of the fused kernel's epilogue
+        const int cnt = cand_count[(size_t)wq * 2 + half];
+        overflow |= cnt > cap;
+        const u64 *row = cand_buf + ((size_t)wq * 2 + half) * cap;
+        const int m = min(cnt, cap);
+        total += m;
+        for (int base = 0; base < m; base += 32) {
+            const u64 key = base + lane < m ? row[base + lane] : ~0ull;
+            unsigned mask = __ballot_sync(0xffffffffu, key < tau_key);
+            while (mask) {
+                const int src = __ffs(mask) - 1;
+                mask &= mask - 1;
+                const u64 kx = __shfl_sync(0xffffffffu, key, src);
+                if (kx < tau_key) {
+                    list.insert(kx, lane);
+                    tau_key = list.last(lane);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < NPL; ++i) cand[(size_t)wq * C + lane * NPL + i] = list.e[i];
+    if (lane == 0) {
+        // more than C emitted: everything outside the list is at least the list's last element; otherwise at least tau
+        outside_bound[wq] = total > C ? __uint_as_float((unsigned)(tau_key >> 32)) : tau[wq];
+        if (overflow) fail_rows[atomicAdd(fail_count, 1)] = q0 + wq;           // buffer overflow: exact fallback for this row
+    }
+}
+
+__global__ void __launch_bounds__(256)
+knn_gather_rows_kernel(const __nv_bfloat16 *__restrict__ Xh, const __nv_bfloat16 *__restrict__ Xl, const float *__restrict__ norm2,
+                       const int *__restrict__ rows, int s, int dpad, __nv_bfloat16 *__restrict__ Sh, __nv_bfloat16 *__restrict__ Sl,
+                       float *__restrict__ norm_s)
+{
+    const long long total = (long long)s * (dpad / 8);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int r = (int)(i / (dpad / 8)), c = (int)(i % (dpad / 8));
+        const size_t src = (size_t)rows[r] * dpad + c * 8, dst = (size_t)r * dpad + c * 8;
+        *reinterpret_cast<uint4 *>(Sh + dst) = *reinterpret_cast<const uint4 *>(Xh + src);
+        *reinterpret_cast<uint4 *>(Sl + dst) = *reinterpret_cast<const uint4 *>(Xl + src);
+        if (c == 0) norm_s[r] = norm2[rows[r]];
+    }
+}
+
+typedef CUresult (*TmapEncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                 const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// 2-D map over a row-major (rows x dpad) bf16 matrix, box = 64 columns x 128 rows, 128-byte swizzle, zero fill out of range
+static int make_feature_map(CUtensorMap *map, const void *ptr, int64_t rows, int dpad)
+{
+    static TmapEncodeFn fn = nullptr;
+    if (!fn) {
+        void *f = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres);
+        if (e != cudaSuccess || !f) { cudaGetLastError(); set_error("cuTensorMapEncodeTiled is not available from this driver"); return GLB_E_UNSUPPORTED; }
+        fn = (TmapEncodeFn)f;
+    }
+    cuuint64_t gdim[2] = {(cuuint64_t)dpad, (cuuint64_t)rows};
+    cuuint64_t gstr[1] = {(cuuint64_t)dpad * 2};
+    cuuint32_t box[2] = {FBK, FBM};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed: %d", (int)r); return GLB_E_UNSUPPORTED; }
+    return 0;
+}
+
+struct KnnArena {
+    std::vector<void *> v;
+    ~KnnArena() { for (void *p : v) dev_free(p); }
+    cudaError_t alloc(void **p, size_t bytes) { cudaError_t e = dev_alloc(p, bytes ? bytes : 1); if (e == cudaSuccess) v.push_back(*p); return e; }
+};
+
+// tensor cores when d >= 64 (-DGLB_EXPERIMENT builds: GLB_KNN_TC=0 forces the fp32 SIMT distance kernel for A/B runs,
+// GLB_KNN_FUSED=0 the unfused tensor-core path)
+static int knn_exp_env(const char *name, int def)
+{
+#ifdef GLB_EXPERIMENT
+    const char *e = getenv(name);
+    if (e) return atoi(e);
+#else
+    (void)name;
+#endif
+    return def;
+}
+static bool knn_use_tc(int d) { return knn_exp_env("GLB_KNN_TC", d >= 64 ? 1 : 0) != 0; }
+
+constexpr int64_t kFusedMinN = 16384;             // below this the distance block is small enough to go through HBM
+constexpr int kFusedSample = 8192;                // sample size of the threshold pass
+constexpr int kFusedCap = 512;                    // candidate buffer per (query row, column half); expected fill n R / 2s = 68 at n = 70 000
+
+static size_t fused_smem_bytes(int kb_per_tile, int *stages, int *a_resident, int max_smem)
+{
+    const size_t a_bytes = (size_t)kb_per_tile * 2 * kFTile;
+    *a_resident = a_bytes <= 128 * 1024 ? 1 : 0;
+    const size_t per_stage = (size_t)(*a_resident ? 2 : 4) * kFTile;
+    const size_t fixed = 1024 /* alignment */ + (*a_resident ? a_bytes : 0) + 2048 /* barriers, norm tiles */;
+    int S = (int)(((size_t)max_smem - fixed) / per_stage);
+    S = std::max(2, std::min(S, 6));
+    *stages = S;
+    return fixed + (size_t)S * per_stage;
 }
 
 template <int NPL>
@@ -549,20 +930,24 @@ static int knn_run(const double *d_X, int64_t n, int d, int k, long long *d_ind,
 {
     constexpr int C = 32 * NPL;
     KnnArena A;
-    const int dpad = tc ? (d + TBK - 1) / TBK * TBK : (d + BK - 1) / BK * BK;
+    const bool fused = tc && n >= kFusedMinN && knn_exp_env("GLB_KNN_FUSED", 1) != 0;
+    const int dpad = fused ? (d + FBK - 1) / FBK * FBK : tc ? (d + TBK - 1) / TBK * TBK : (d + BK - 1) / BK * BK;
     const int n_pad = (int)((n + BN - 1) / BN * BN);
-    // queries per distance block (QB x n_pad fp32 in HBM): large enough that the one-warp-per-query selection fills the
-    // machine (8192 warps = 55 per SM), capped at 4 GB
-    int QB = getenv("GLB_KNN_QB") ? atoi(getenv("GLB_KNN_QB")) : 8192;
-    QB = std::max(128, QB / 128 * 128);
-    while ((double)QB * n_pad * 4.0 > 4.0e9 && QB > 128) QB /= 2;
-    if (QB > n) QB = (int)((n + BM - 1) / BM * BM);
-    double *mean; float *Xc, *norm2, *D; unsigned long long *rmax2; u64 *cand; int *fail_rows, *fail_count; double *scratch;
+    // queries per block.  Unfused: QB x n_pad fp32 distances in HBM, large enough that the one-warp-per-query selection
+    // fills the machine (8192 warps = 55 per SM), capped at 4 GB.  Fused: one CTA of 128 queries per SM and launch.
+    int QB = 8192;
+    if (fused) {
+        QB = sm_count() * FBM;
+    } else {
+        while ((double)QB * n_pad * 4.0 > 4.0e9 && QB > 128) QB /= 2;
+        if (QB > n) QB = (int)((n + BM - 1) / BM * BM);
+    }
+    double *mean; float *Xc, *norm2, *D = nullptr; unsigned long long *rmax2; u64 *cand; int *fail_rows, *fail_count; double *scratch;
     GLB_CUDA(A.alloc((void **)&mean, sizeof(double) * d));
     GLB_CUDA(A.alloc((void **)&Xc, sizeof(float) * (size_t)n * dpad));
     GLB_CUDA(A.alloc((void **)&norm2, sizeof(float) * (size_t)n));
     GLB_CUDA(A.alloc((void **)&rmax2, sizeof(unsigned long long)));
-    GLB_CUDA(A.alloc((void **)&D, sizeof(float) * (size_t)QB * n_pad));
+    if (!fused) GLB_CUDA(A.alloc((void **)&D, sizeof(float) * (size_t)QB * n_pad));
     GLB_CUDA(A.alloc((void **)&cand, sizeof(u64) * (size_t)QB * C));
     GLB_CUDA(A.alloc((void **)&fail_rows, sizeof(int) * (size_t)n));
     GLB_CUDA(A.alloc((void **)&fail_count, sizeof(int)));
@@ -582,18 +967,71 @@ static int knn_run(const double *d_X, int64_t n, int d, int k, long long *d_ind,
         GLB_CUDA(A.alloc((void **)&Xh, sizeof(__nv_bfloat16) * (size_t)n * dpad));
         GLB_CUDA(A.alloc((void **)&Xl, sizeof(__nv_bfloat16) * (size_t)n * dpad));
         knn_split_kernel<<<sm_count() * 8, 256, 0, st>>>(Xc, (long long)n * dpad, Xh, Xl); ++nl;
-        GLB_CUDA(cudaFuncSetAttribute(knn_dist_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
         err_rel = 3.0 * 3.814697265625e-6 + (double)(3 * dpad + 8) * 1.1920928955078125e-7;
     }
-    for (int64_t q0 = 0; q0 < n; q0 += QB) {
-        const int nq = (int)std::min<int64_t>(QB, n - q0);
-        dim3 grid((unsigned)(n_pad / BN), (unsigned)((nq + BM - 1) / BM));
-        if (tc) knn_dist_tc_kernel<<<grid, kTcThreads, kTcSmemBytes, st>>>(Xh, Xl, norm2, (int)n, dpad, (int)q0, nq, D, (long long)n_pad);
-        else knn_dist_kernel<<<grid, kDistThreads, 0, st>>>(Xc, norm2, (int)n, dpad, (int)q0, nq, D, (long long)n_pad);
-        ++nl;
-        knn_select_kernel<NPL><<<(nq * 32 + 255) / 256, 256, 0, st>>>(D, (long long)n_pad, n_pad, nq, cand); ++nl;
-        knn_rerank_kernel<NPL><<<(nq * 32 + 255) / 256, 256, 0, st>>>(d_X, (int)n, d, norm2, rmax2, cand, (int)q0, nq, k, d_ind, d_dist,
-                                                                       fail_rows, fail_count, err_rel); ++nl;
+    if (fused) {
+        // ---- thresholds from a fixed pseudo-random sample of the database, then one filtered pass over all of it ----
+        const int s_n = (int)std::min<int64_t>(kFusedSample, n);
+        std::vector<int> h_rows((size_t)s_n);
+        {   // s_n distinct rows: a multiplicative walk through the residues mod n (an odd stride coprime to n), fixed seed
+            unsigned long long x = 0x9E3779B97F4A7C15ull % (unsigned long long)n, stride = (unsigned long long)(0.6180339887 * (double)n) | 1ull;
+            auto gcd = [](unsigned long long a, unsigned long long b) { while (b) { const unsigned long long t = a % b; a = b; b = t; } return a; };
+            while (gcd(stride, (unsigned long long)n) != 1ull) stride += 2;
+            for (int i = 0; i < s_n; ++i) { h_rows[i] = (int)x; x = (x + stride) % (unsigned long long)n; }
+        }
+        int *d_rows; __nv_bfloat16 *Sh, *Sl; float *norm_s, *tau, *best, *bound; u64 *cand_buf; int *cand_count;
+        GLB_CUDA(A.alloc((void **)&d_rows, sizeof(int) * s_n));
+        GLB_CUDA(A.alloc((void **)&Sh, sizeof(__nv_bfloat16) * (size_t)s_n * dpad));
+        GLB_CUDA(A.alloc((void **)&Sl, sizeof(__nv_bfloat16) * (size_t)s_n * dpad));
+        GLB_CUDA(A.alloc((void **)&norm_s, sizeof(float) * s_n));
+        GLB_CUDA(A.alloc((void **)&tau, sizeof(float) * (size_t)QB));
+        GLB_CUDA(A.alloc((void **)&best, sizeof(float) * (size_t)n * 2 * kSampleR));
+        GLB_CUDA(A.alloc((void **)&bound, sizeof(float) * (size_t)QB));
+        GLB_CUDA(A.alloc((void **)&cand_buf, sizeof(u64) * (size_t)QB * 2 * kFusedCap));
+        GLB_CUDA(A.alloc((void **)&cand_count, sizeof(int) * (size_t)QB * 2));
+        GLB_CUDA(cudaMemcpyAsync(d_rows, h_rows.data(), sizeof(int) * s_n, cudaMemcpyHostToDevice, st));
+        knn_gather_rows_kernel<<<sm_count() * 4, 256, 0, st>>>(Xh, Xl, norm2, d_rows, s_n, dpad, Sh, Sl, norm_s); ++nl;
+        CUtensorMap tm_xh, tm_xl, tm_sh, tm_sl;
+        int rc;
+        if ((rc = make_feature_map(&tm_xh, Xh, n, dpad)) || (rc = make_feature_map(&tm_xl, Xl, n, dpad)) ||
+            (rc = make_feature_map(&tm_sh, Sh, s_n, dpad)) || (rc = make_feature_map(&tm_sl, Sl, s_n, dpad)))
+            return rc;
+        int dev = 0, max_smem = 0;
+        GLB_CUDA(cudaGetDevice(&dev));
+        cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        FusedArgs fa{};
+        fa.norm_q = norm2; fa.kb_per_tile = dpad / FBK; fa.cap = kFusedCap;
+        const size_t smem = fused_smem_bytes(fa.kb_per_tile, &fa.stages, &fa.a_resident, max_smem);
+        GLB_CUDA(cudaFuncSetAttribute(knn_fused_kernel<MODE_SAMPLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        GLB_CUDA(cudaFuncSetAttribute(knn_fused_kernel<MODE_EMIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        for (int64_t q0 = 0; q0 < n; q0 += QB) {             // thresholds: every query against the sample
+            const int nq = (int)std::min<int64_t>(QB, n - q0);
+            fa.q0 = (int)q0; fa.nq = nq; fa.norm_d = norm_s; fa.nd = s_n; fa.best_out = best + (size_t)q0 * 2 * kSampleR;
+            knn_fused_kernel<MODE_SAMPLE><<<(nq + FBM - 1) / FBM, kFusedThreads, smem, st>>>(tm_xh, tm_xl, tm_sh, tm_sl, fa); ++nl;
+        }
+        err_rel += 1.0e-6;                                   // the filter compares in fp32: a few ulps of |q|^2 + |x|^2
+        for (int64_t q0 = 0; q0 < n; q0 += QB) {
+            const int nq = (int)std::min<int64_t>(QB, n - q0);
+            fa.q0 = (int)q0; fa.nq = nq; fa.norm_d = norm2; fa.nd = (int)n; fa.best_in = best + (size_t)q0 * 2 * kSampleR; fa.tau_out = tau;
+            fa.cand_buf = cand_buf; fa.cand_count = cand_count;
+            knn_fused_kernel<MODE_EMIT><<<(nq + FBM - 1) / FBM, kFusedThreads, smem, st>>>(tm_xh, tm_xl, tm_xh, tm_xl, fa); ++nl;
+            knn_pick_kernel<NPL><<<(nq * 32 + 255) / 256, 256, 0, st>>>(cand_buf, cand_count, tau, kFusedCap, (int)q0, nq, cand, bound,
+                                                                         fail_rows, fail_count); ++nl;
+            knn_rerank_kernel<NPL><<<(nq * 32 + 255) / 256, 256, 0, st>>>(d_X, (int)n, d, norm2, rmax2, cand, (int)q0, nq, k, d_ind, d_dist,
+                                                                           fail_rows, fail_count, err_rel, bound); ++nl;
+        }
+    } else {
+        if (tc) GLB_CUDA(cudaFuncSetAttribute(knn_dist_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
+        for (int64_t q0 = 0; q0 < n; q0 += QB) {
+            const int nq = (int)std::min<int64_t>(QB, n - q0);
+            dim3 grid((unsigned)(n_pad / BN), (unsigned)((nq + BM - 1) / BM));
+            if (tc) knn_dist_tc_kernel<<<grid, kTcThreads, kTcSmemBytes, st>>>(Xh, Xl, norm2, (int)n, dpad, (int)q0, nq, D, (long long)n_pad);
+            else knn_dist_kernel<<<grid, kDistThreads, 0, st>>>(Xc, norm2, (int)n, dpad, (int)q0, nq, D, (long long)n_pad);
+            ++nl;
+            knn_select_kernel<NPL><<<(nq * 32 + 255) / 256, 256, 0, st>>>(D, (long long)n_pad, n_pad, nq, cand); ++nl;
+            knn_rerank_kernel<NPL><<<(nq * 32 + 255) / 256, 256, 0, st>>>(d_X, (int)n, d, norm2, rmax2, cand, (int)q0, nq, k, d_ind, d_dist,
+                                                                           fail_rows, fail_count, err_rel, nullptr); ++nl;
+        }
     }
     knn_exact_rows_kernel<<<exact_ctas, 256, 0, st>>>(d_X, (int)n, d, fail_rows, fail_count, k, scratch, d_ind, d_dist); ++nl;
     GLB_LAUNCH_CHECK();

@@ -87,12 +87,12 @@ kg_rowptr_kernel(const u64 *__restrict__ keys, long long nnz, long long n, int *
 
 struct Arena {
     std::vector<void *> ptrs;
-    ~Arena() { for (void *p : ptrs) cudaFree(p); }
+    ~Arena() { for (void *p : ptrs) dev_free(p); }
     template <typename T>
     cudaError_t alloc(T **p, size_t count)
     {
         void *q = nullptr;
-        cudaError_t e = cudaMalloc(&q, (count ? count : 1) * sizeof(T));
+        cudaError_t e = dev_alloc(&q, (count ? count : 1) * sizeof(T));
         if (e == cudaSuccess) ptrs.push_back(q);
         *p = (T *)q;
         return e;

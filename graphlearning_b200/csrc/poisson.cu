@@ -689,6 +689,27 @@ maxdiff_kernel(const double *__restrict__ v, const double *__restrict__ vinf, in
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
+// is (j,i) stored for every stored (i,j)?  (explicit zeros count: only the pattern matters; rows need not be sorted)
+// One thread per stored entry scans row j for column i: nnz x (row length) steps, a fraction of a millisecond at 10^6
+// nonzeros - the host version of round 1 took 30-40 ms on a relabelled (unsorted) matrix.
+__global__ void __launch_bounds__(256)
+pattern_symmetric_kernel(const int *__restrict__ rowptr, const int *__restrict__ col, int n, int *__restrict__ asym)
+{
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long i = warp; i < n; i += nwarps) {
+        const int beg = rowptr[i], end = rowptr[i + 1];
+        for (int e = beg + lane; e < end; e += 32) {
+            const int j = col[e];
+            bool found = false;
+            if (j >= 0 && j < n)
+                for (int q = rowptr[j]; q < rowptr[j + 1]; ++q) found |= col[q] == (int)i;
+            if (!found) *asym = 1;
+        }
+    }
+}
+
 template <int LANES, bool FLAGGED>
 static int launch_step(const int *rp, const int *col, const float *val, const float *Db, const float *u_in,
                        float *u_out, int64_t n, int ldu, cudaStream_t st)
@@ -840,42 +861,6 @@ static void balanced_bounds(const std::vector<int> &h_rp, int64_t n, int grid, d
     bounds[grid] = (int)n;
 }
 
-// is (j,i) stored for every stored (i,j)?  (explicit zeros count: only the pattern matters)
-static bool pattern_symmetric(const std::vector<int> &rp, const std::vector<int> &col, int64_t n)
-{
-    // Rows with ascending columns (canonical CSR, the normal case): one pass with a cursor per row.  Visiting the entries
-    // (i, j) by ascending i, the entries (j, i) of row j are met in ascending order too, so row j's cursor must point
-    // at column i exactly when (i, j) is visited; every cursor must end at its row's end.
-    bool sorted_rows = true;
-    for (int64_t i = 0; i < n && sorted_rows; ++i)
-        for (int j = rp[i] + 1; j < rp[i + 1]; ++j)
-            if (col[j - 1] >= col[j]) { sorted_rows = false; break; }
-    if (sorted_rows) {
-        std::vector<int> cur(rp.begin(), rp.begin() + n);
-        for (int64_t i = 0; i < n; ++i)
-            for (int j = rp[i]; j < rp[i + 1]; ++j) {
-                const int cj = col[j];
-                if (cj < 0 || cj >= n) return false;
-                if (cur[cj] >= rp[cj + 1] || col[cur[cj]] != (int)i) return false;
-                ++cur[cj];
-            }
-        for (int64_t i = 0; i < n; ++i)
-            if (cur[i] != rp[i + 1]) return false;
-        return true;
-    }
-    std::vector<int> sorted(col);
-    for (int64_t i = 0; i < n; ++i)
-        if (!std::is_sorted(sorted.begin() + rp[i], sorted.begin() + rp[i + 1]))
-            std::sort(sorted.begin() + rp[i], sorted.begin() + rp[i + 1]);
-    for (int64_t i = 0; i < n; ++i)
-        for (int j = rp[i]; j < rp[i + 1]; ++j) {
-            const int cj = sorted[j];
-            if (cj < 0 || cj >= n) return false;
-            if (!std::binary_search(sorted.begin() + rp[cj], sorted.begin() + rp[cj + 1], (int)i)) return false;
-        }
-    return true;
-}
-
 // Try to set the plan up for the dataflow kernel.  Returns 0 and leaves kind untouched when the graph does not
 // qualify (pattern not symmetric, slabs too large for shared memory, label rows too wide).
 static int plan_try_dataflow(glb_poisson_plan *p, const std::vector<int> &h_rp, int sms, int max_smem, cudaStream_t st)
@@ -901,17 +886,26 @@ static int plan_try_dataflow(glb_poisson_plan *p, const std::vector<int> &h_rp, 
     if (grid < 1) grid = 1;
     if ((double)nnz * 8.0 / grid > (double)max_smem) return 0;
 
+    PhaseTimer tm("dataflow plan");
     std::vector<int> h_col((size_t)nnz);
     std::vector<float> h_val((size_t)nnz);
-    if (nnz) {
-        GLB_CUDA(cudaMemcpyAsync(h_col.data(), p->d_col, sizeof(int) * (size_t)nnz, cudaMemcpyDeviceToHost, st));
-        GLB_CUDA(cudaMemcpyAsync(h_val.data(), p->d_val, sizeof(float) * (size_t)nnz, cudaMemcpyDeviceToHost, st));
-        GLB_CUDA(cudaStreamSynchronize(st));
+    int h_asym = 0;
+    {
+        int *d_asym = nullptr;
+        GLB_CUDA(dev_alloc(&d_asym, sizeof(int)));
+        cudaMemsetAsync(d_asym, 0, sizeof(int), st);
+        if (nnz) pattern_symmetric_kernel<<<sms * 8, 256, 0, st>>>(p->d_rowptr, p->d_col, (int)n, d_asym);
+        cudaMemcpyAsync(&h_asym, d_asym, sizeof(int), cudaMemcpyDeviceToHost, st);
+        if (nnz) {
+            cudaMemcpyAsync(h_col.data(), p->d_col, sizeof(int) * (size_t)nnz, cudaMemcpyDeviceToHost, st);
+            cudaMemcpyAsync(h_val.data(), p->d_val, sizeof(float) * (size_t)nnz, cudaMemcpyDeviceToHost, st);
+        }
+        const cudaError_t e = cudaStreamSynchronize(st);
+        dev_free(d_asym);
+        if (e != cudaSuccess) { set_error("plan_try_dataflow: %s", cudaGetErrorString(e)); return (int)e; }
     }
-    PhaseTimer tm("dataflow plan");
-    tm.lap("download col/val");
-    if (!pattern_symmetric(h_rp, h_col, n)) return 0;
-    tm.lap("symmetry check");
+    tm.lap("symmetry check (device) + download col/val");
+    if (h_asym) return 0;
 
     int threads = 0;
     const void *fn = pick_dataflow(lanes, p->l1_first, &threads);
@@ -1049,11 +1043,11 @@ static int plan_try_dataflow(glb_poisson_plan *p, const std::vector<int> &h_rp, 
     if (per_sm < 1 || grid > per_sm * sms) return 0;
 
     const size_t nslab = slab.size() ? slab.size() : 1, nsl = slots.size() ? slots.size() : 1;
-    GLB_CUDA(cudaMalloc(&p->d_slabs, sizeof(int2) * nslab));
-    GLB_CUDA(cudaMalloc(&p->d_slots, sizeof(int4) * nsl));
-    GLB_CUDA(cudaMalloc(&p->d_slab_off, sizeof(long long) * (grid + 1)));
-    GLB_CUDA(cudaMalloc(&p->d_slot_off, sizeof(int) * (grid + 1)));
-    GLB_CUDA(cudaMalloc(&p->d_slot_rows, sizeof(int) * nsl * rpw));
+    GLB_CUDA(dev_alloc(&p->d_slabs, sizeof(int2) * nslab));
+    GLB_CUDA(dev_alloc(&p->d_slots, sizeof(int4) * nsl));
+    GLB_CUDA(dev_alloc(&p->d_slab_off, sizeof(long long) * (grid + 1)));
+    GLB_CUDA(dev_alloc(&p->d_slot_off, sizeof(int) * (grid + 1)));
+    GLB_CUDA(dev_alloc(&p->d_slot_rows, sizeof(int) * nsl * rpw));
     GLB_CUDA(cudaMemcpyAsync(p->d_slabs, slab.data(), sizeof(int2) * slab.size(), cudaMemcpyHostToDevice, st));
     GLB_CUDA(cudaMemcpyAsync(p->d_slots, slots.data(), sizeof(int4) * slots.size(), cudaMemcpyHostToDevice, st));
     GLB_CUDA(cudaMemcpyAsync(p->d_slab_off, slab_off.data(), sizeof(long long) * (grid + 1), cudaMemcpyHostToDevice, st));
@@ -1066,11 +1060,11 @@ static int plan_try_dataflow(glb_poisson_plan *p, const std::vector<int> &h_rp, 
     p->grid = grid; p->threads = threads; p->fn = fn; p->smem_bytes = smem;
     p->cap_entries = cap_entries; p->cap_slots = cap_slots; p->cap_parts = cap_parts;
     p->scratch_row = kScratchRows;
-    GLB_CUDA(cudaMalloc(&p->d_ring, sizeof(float) * 2 * ((size_t)n + kScratchRows) * (size_t)(lanes * 4)));
+    GLB_CUDA(dev_alloc(&p->d_ring, sizeof(float) * 2 * ((size_t)n + kScratchRows) * (size_t)(lanes * 4)));
     p->ell_fill = slab.size() ? (double)nnz / (double)slab.size() : 1.0;
-    GLB_CUDA(cudaMalloc(&p->d_gate, 2 * sizeof(unsigned)));          // [0] gate counter, [1] watchdog flag
+    GLB_CUDA(dev_alloc(&p->d_gate, 2 * sizeof(unsigned)));          // [0] gate counter, [1] watchdog flag
     GLB_CUDA(cudaMemsetAsync(p->d_gate, 0, 2 * sizeof(unsigned), st));
-    if (exp_env("GLB_POISSON_STATS", 0)) GLB_CUDA(cudaMalloc(&p->d_stats, 4 * sizeof(unsigned long long)));
+    if (exp_env("GLB_POISSON_STATS", 0)) GLB_CUDA(dev_alloc(&p->d_stats, 4 * sizeof(unsigned long long)));
     return 0;
 }
 
@@ -1099,8 +1093,8 @@ static int plan_try_barrier(glb_poisson_plan *p, const std::vector<int> &h_rp, i
     int per_sm = 0;
     GLB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, threads, smem));
     if (per_sm < 1 || grid > per_sm * sms || grid > threads) return 0;
-    GLB_CUDA(cudaMalloc(&p->d_counter, sizeof(unsigned) * kFlagStride * grid));
-    GLB_CUDA(cudaMalloc(&p->d_cta_rows, sizeof(int) * (grid + 1)));
+    GLB_CUDA(dev_alloc(&p->d_counter, sizeof(unsigned) * kFlagStride * grid));
+    GLB_CUDA(dev_alloc(&p->d_cta_rows, sizeof(int) * (grid + 1)));
     GLB_CUDA(cudaMemcpyAsync(p->d_cta_rows, bounds.data(), sizeof(int) * (grid + 1), cudaMemcpyHostToDevice, st));
     GLB_CUDA(cudaStreamSynchronize(st));        // bounds is a local
     p->kind = GLB_POISSON_KIND_BARRIER;
@@ -1118,11 +1112,11 @@ static size_t plan_time_floats(const glb_poisson_plan *p) { return 3 * ((size_t)
 // several trials; nullptr = allocate here.
 static int plan_time(glb_poisson_plan *p, float *ms, cudaStream_t st, float *shared_buf = nullptr)
 {
-    const int T = 64;
+    const int T = 32;
     const size_t rows = (size_t)p->n + (size_t)p->scratch_row;             // label matrices carry the scratch rows
     const size_t bytes = rows * p->ldu * sizeof(float);
     float *buf = shared_buf;
-    if (!buf) GLB_CUDA(cudaMalloc(&buf, 3 * bytes));
+    if (!buf) GLB_CUDA(dev_alloc(&buf, 3 * bytes));
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
     int rc = 0;
@@ -1136,7 +1130,7 @@ static int plan_time(glb_poisson_plan *p, float *ms, cudaStream_t st, float *sha
     if (ce == cudaSuccess && rc == 0) cudaEventElapsedTime(ms, e0, e1);
     if (ce == cudaSuccess && rc == 0) rc = glb_poisson_plan_check(p, st);
     cudaEventDestroy(e0); cudaEventDestroy(e1);
-    if (!shared_buf) cudaFree(buf);
+    if (!shared_buf) dev_free(buf);
     if (rc == 0 && ce != cudaSuccess) { set_error("plan_time: %s", cudaGetErrorString(ce)); rc = (int)ce; }
     return rc;
 }
@@ -1183,23 +1177,25 @@ extern "C" GLB_API int glb_poisson_plan_create(glb_poisson_plan **plan, const in
         if (p->kind == GLB_POISSON_KIND_DATAFLOW && tune && forced_gate < 0) {
             // Measure, don't guess.  Gate period of the dataflow kernel: graphs with hub rows (every hub is a meeting
             // point of hundreds of producers) run best with a gate every few iterations, hub-free graphs with rare gates.
-            const int cand[4] = {0, 32, 4, 1};               // 0 = no gate after the start gate
+            // (longer periods and no gate at all run 3-4x slower with the pipelined stream: profiles/r2_dataflow_gate_x_backoff_sweep.txt)
+            const int cand[2] = {1, 4};
             float best = 0.f;
             float *trial = nullptr;
-            GLB_CUDA(cudaMalloc(&trial, plan_time_floats(p) * sizeof(float)));
-            for (int i = 0; i < 4 && rc == 0; ++i) {
+            GLB_CUDA(dev_alloc(&trial, plan_time_floats(p) * sizeof(float)));
+            for (int i = 0; i < 2 && rc == 0; ++i) {
                 p->gate_every = cand[i];
                 float ms = 0.f;
                 rc = plan_time(p, &ms, st, trial);
                 if (rc == 0 && (i == 0 || ms < best)) { best = ms; ms_df = ms; p->tuned_gate = cand[i]; }
             }
-            cudaFree(trial);
+            dev_free(trial);
             if (rc) return rc;
             p->gate_every = p->tuned_gate;
             p->tuned_ms[0] = ms_df;
             tm.lap("gate tuning");
         }
-        if (kind == GLB_POISSON_KIND_AUTO && p->kind == GLB_POISSON_KIND_DATAFLOW && tune) {
+        // the barrier kernel only wins on small graphs (too few rows per SM to hide the producer-consumer latency)
+        if (kind == GLB_POISSON_KIND_AUTO && p->kind == GLB_POISSON_KIND_DATAFLOW && tune && n < 64 * (int64_t)sms) {
             // ... and the dataflow kernel against the barrier kernel (small graphs: too few rows per SM to hide the
             // producer-consumer latency).  Both timed on zeros.
             glb_poisson_plan *alt = nullptr;
@@ -1232,10 +1228,10 @@ extern "C" GLB_API int glb_poisson_plan_create(glb_poisson_plan **plan, const in
 extern "C" GLB_API int glb_poisson_plan_destroy(glb_poisson_plan *plan)
 {
     if (!plan) return 0;
-    cudaFree(plan->d_counter);  cudaFree(plan->d_cta_rows);
-    cudaFree(plan->d_slabs);    cudaFree(plan->d_slots);
-    cudaFree(plan->d_slab_off); cudaFree(plan->d_slot_off); cudaFree(plan->d_slot_rows); cudaFree(plan->d_stats); cudaFree(plan->d_gate);
-    cudaFree(plan->d_ring);
+    dev_free(plan->d_counter);  dev_free(plan->d_cta_rows);
+    dev_free(plan->d_slabs);    dev_free(plan->d_slots);
+    dev_free(plan->d_slab_off); dev_free(plan->d_slot_off); dev_free(plan->d_slot_rows); dev_free(plan->d_stats); dev_free(plan->d_gate);
+    dev_free(plan->d_ring);
     delete plan;
     return 0;
 }
@@ -1380,7 +1376,7 @@ extern "C" GLB_API int glb_poisson_mixing_T(const int32_t *d_rw_rowptr, const in
     cudaStream_t st = (cudaStream_t)stream;
     const int BATCH = 64;
     unsigned long long *d_err = nullptr;
-    GLB_CUDA(cudaMalloc(&d_err, sizeof(unsigned long long) * (BATCH + 1)));
+    GLB_CUDA(dev_alloc(&d_err, sizeof(unsigned long long) * (BATCH + 1)));
     unsigned long long h_err[BATCH + 1];
     const double thr = 1.0 / (double)n;
     const int threads = 256;
@@ -1418,7 +1414,7 @@ extern "C" GLB_API int glb_poisson_mixing_T(const int32_t *d_rw_rowptr, const in
             if (!((T < min_iter || err > thr) && T < max_iter)) { done = true; break; }
         }
     }
-    cudaFree(d_err);
+    dev_free(d_err);
     if (rc == 0) {
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) { rc = (int)e; set_error("glb_poisson_mixing_T: %s", cudaGetErrorString(e)); }

@@ -98,9 +98,9 @@ extern "C" GLB_API int glb_csr_permute(const int32_t *d_rowptr, const int32_t *d
     void *temp = nullptr;
     size_t temp_bytes = 0;
     GLB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, temp_bytes, (const int *)nullptr, (int *)nullptr, (int)(n + 1), st));
-    GLB_CUDA(cudaMalloc(&len, sizeof(int) * (size_t)(n + 1)));
-    cudaError_t e = cudaMalloc(&temp, temp_bytes ? temp_bytes : 1);
-    if (e != cudaSuccess) { cudaFree(len); set_error("glb_csr_permute: %s", cudaGetErrorString(e)); return (int)e; }
+    GLB_CUDA(dev_alloc(&len, sizeof(int) * (size_t)(n + 1)));
+    cudaError_t e = dev_alloc(&temp, temp_bytes ? temp_bytes : 1);
+    if (e != cudaSuccess) { dev_free(len); set_error("glb_csr_permute: %s", cudaGetErrorString(e)); return (int)e; }
     const int blocks = std::min<int64_t>((n + 256) / 256, (int64_t)sm_count() * 16);
     perm_rowlen_kernel<<<blocks, 256, 0, st>>>(d_rowptr, d_perm, (int)n, len, d_iperm);
     e = cub::DeviceScan::ExclusiveSum(temp, temp_bytes, len, d_out_rowptr, (int)(n + 1), st);
@@ -108,8 +108,8 @@ extern "C" GLB_API int glb_csr_permute(const int32_t *d_rowptr, const int32_t *d
     perm_fill_kernel<<<wblocks, 256, 0, st>>>(d_rowptr, d_col, d_val, d_perm, d_iperm, d_out_rowptr, (int)n, d_out_col,
                                               d_out_val);
     cudaError_t e2 = cudaStreamSynchronize(st);        // len/temp are freed below
-    cudaFree(len);
-    cudaFree(temp);
+    dev_free(len);
+    dev_free(temp);
     if (e == cudaSuccess) e = e2;
     if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("glb_csr_permute: %s", cudaGetErrorString(e)); return (int)e; }

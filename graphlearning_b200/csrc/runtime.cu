@@ -25,6 +25,39 @@ int sm_count()
     }
     return cached;
 }
+static bool pool_ready()
+{
+    static int state = 0;                                   // 0 unknown, 1 pooled, -1 plain cudaMalloc
+    if (state == 0) {
+        int dev = 0, ok = 0;
+        cudaMemPool_t pool;
+        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&ok, cudaDevAttrMemoryPoolsSupported, dev) == cudaSuccess && ok &&
+            cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            unsigned long long keep = ~0ull;                // never trim on synchronisation
+            state = cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep) == cudaSuccess ? 1 : -1;
+        } else {
+            state = -1;
+        }
+        cudaGetLastError();
+    }
+    return state == 1;
+}
+cudaError_t dev_alloc_bytes(void **p, size_t bytes)
+{
+    if (!bytes) bytes = 1;
+    if (pool_ready()) {
+        cudaError_t e = cudaMallocAsync(p, bytes, (cudaStream_t)0);
+        if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)0);      // usable on every stream from here on
+        return e;
+    }
+    return cudaMalloc(p, bytes);
+}
+cudaError_t dev_free(void *p)
+{
+    if (!p) return cudaSuccess;
+    if (pool_ready()) return cudaFreeAsync(p, (cudaStream_t)0);
+    return cudaFree(p);
+}
 double PhaseTimer::now()
 {
     struct timespec ts;
@@ -42,7 +75,17 @@ void PhaseTimer::lap(const char *phase)
 }
 }  // namespace glb
 
-extern "C" GLB_API int glb_version(void) { return 100; }
+extern "C" GLB_API int glb_version(void) { return 200; }
+
+extern "C" GLB_API int glb_release_workspace(void)
+{
+    int dev = 0;
+    cudaMemPool_t pool;
+    GLB_CUDA(cudaDeviceSynchronize());
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
+    cudaGetLastError();
+    return 0;
+}
 extern "C" GLB_API const char *glb_last_error(void) { return glb::g_err; }
 
 extern "C" GLB_API int glb_device_info(int *sm_count, int *cc_major, int *cc_minor, int64_t *hbm_bytes)

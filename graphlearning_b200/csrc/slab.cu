@@ -15,13 +15,15 @@
 //     group from one contiguous 128-byte run.  All slices back to back = ONE stream of pairs per warp.
 //   * boundary rows (rows a peer needs, or rows that read halo rows) come first, interior rows after them.
 //
-// Kernel (slab_step_kernel, one launch per iteration): persistent CTAs of 8 warps walk the tiles (8 warps x 2 slices)
-// b, b + grid, b + 2 grid, ...  Lane 0 of every warp brings the warp's part of a tile's entry stream into shared memory
+// Kernel (slab_step_kernel, one launch per iteration): persistent CTAs of 8 warps walk tiles (8 warps x 2 slices) in a
+// static order - about half of the CTAs take the boundary tiles first so that the puts leave early (then a share of the
+// interior tiles that evens out the work), the others start on interior tiles at once and never wait for a neighbour.
+// Lane 0 of every warp brings the warp's part of a tile's entry stream into shared memory
 // with ONE bulk copy (cp.async.bulk -> mbarrier, TMA unit, SASS UBLKCP) - the copy for the NEXT tile is issued before the
 // current one is processed (two stream buffers per CTA) - then the warp walks it through a ring of four pair slots - pair p+4 is issued when pair p has been consumed,
 // across slice boundaries, 6-8 label-row gathers per lane in flight (the same software pipeline as
 // poisson_dataflow_pipe_kernel); gathers go through L1 (a locality ordering makes neighbouring rows share most of
-// their columns).  Boundary tiles (lowest tile indices, i.e. the first pass of the CTAs) wait until the neighbours' halo
+// their columns).  Boundary tiles wait until the neighbours' halo
 // rows of this version have arrived (one flag per neighbour in this rank's memory, acquire at system scope), write every
 // finished row to the local matrix AND to each peer that needs it (plain 16-byte stores to peer memory mapped through
 // CUDA IPC), and the last of them to finish releases this rank's flag in every neighbour's memory.  Interior tiles never
@@ -68,6 +70,8 @@ struct SlabParams {
     unsigned *err_flag;              // watchdog
     int nslices, n_bnd_tiles;
     int tile_entries;                // capacity of one stream buffer of a CTA, in int4
+    int bnd_ctas;                    // CTAs 0 .. bnd_ctas-1 take the boundary tiles first (then their share of the interior tiles)
+    int bnd_group_interior;          // interior tiles that belong to that group of CTAs
 };
 
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -161,14 +165,29 @@ slab_step_kernel(const SlabParams p)
             bulk_g2s(dst, p.ent + f0, (unsigned)(f1 - f0) * 16u, &bars[buf][warp]);
         }
     };
-    int tile = blockIdx.x, buf = 0;
+    // step -> tile of this CTA (static schedule, -1 = done).  Group B (CTAs < bnd_ctas): boundary tiles b, b + |B|, ...,
+    // then interior tiles [n_bnd, n_bnd + bnd_group_interior) with the same stride; group I: the remaining interior tiles.
+    const int n_bnd = p.n_bnd_tiles, gB = p.bnd_ctas, gI = (int)gridDim.x - gB;
+    auto tile_at = [&](int step) -> int {
+        const int b = blockIdx.x;
+        if (b < gB) {
+            const int mine_bnd = b < n_bnd ? (n_bnd - b + gB - 1) / gB : 0;
+            if (step < mine_bnd) return b + step * gB;
+            const int t = b + (step - mine_bnd) * gB;
+            return t < p.bnd_group_interior ? n_bnd + t : -1;
+        }
+        const int t = (b - gB) + step * gI;
+        return n_bnd + p.bnd_group_interior + t < ntiles ? n_bnd + p.bnd_group_interior + t : -1;
+    };
+    int tile = tile_at(0), buf = 0;
     unsigned par0 = 0u, par1 = 0u;                           // phase parity of the two stream buffers' barriers
-    if (lane == 0 && tile < ntiles) load_tile(tile, 0);
+    if (lane == 0 && tile >= 0) load_tile(tile, 0);
     bool waited = p.wait_epoch == 0u;
     const char *in = reinterpret_cast<const char *>(p.u_in) + li * 16;
-    for (; tile < ntiles; tile += gridDim.x, buf ^= 1) {
+    for (int step = 0; tile >= 0; ++step, buf ^= 1) {
         __syncwarp();
-        if (lane == 0 && tile + (int)gridDim.x < ntiles) load_tile(tile + gridDim.x, buf ^ 1);      // prefetch the next tile's stream
+        const int next = tile_at(step + 1);
+        if (lane == 0 && next >= 0) load_tile(next, buf ^ 1);           // prefetch the next tile's stream
         const bool boundary = tile < p.n_bnd_tiles;
         if (boundary && !waited) {                           // the neighbours' halo rows of this version must have landed
             if (threadIdx.x < kMaxPeers && ((p.nbr_mask >> threadIdx.x) & 1u)) {
@@ -268,6 +287,7 @@ slab_step_kernel(const SlabParams p)
                 }
             }
         }
+        tile = next;
     }
 }
 
@@ -489,18 +509,18 @@ extern "C" GLB_API int glb_slab_create(glb_slab **out, const int32_t *h_rowptr, 
         const int ntiles = (nslices + kSlabSPC - 1) / kSlabSPC;
         s->grid = std::max(1, std::min(ntiles, std::max(1, per_sm) * sm_count()));        // persistent: every CTA walks tiles b, b + grid, ...
     }
-    GLB_CUDA(cudaMalloc(&s->d_ent, sizeof(int4) * std::max<size_t>(ent.size(), 1)));
-    GLB_CUDA(cudaMalloc(&s->d_slice_first, sizeof(int) * (nslices + 1)));
-    GLB_CUDA(cudaMalloc(&s->d_slice_rows, sizeof(int) * std::max<size_t>(slice_rows.size(), 1)));
-    GLB_CUDA(cudaMalloc(&s->d_src_flag, (size_t)m));
-    GLB_CUDA(cudaMalloc(&s->d_sync, 2 * sizeof(unsigned)));
+    GLB_CUDA(dev_alloc(&s->d_ent, sizeof(int4) * std::max<size_t>(ent.size(), 1)));
+    GLB_CUDA(dev_alloc(&s->d_slice_first, sizeof(int) * (nslices + 1)));
+    GLB_CUDA(dev_alloc(&s->d_slice_rows, sizeof(int) * std::max<size_t>(slice_rows.size(), 1)));
+    GLB_CUDA(dev_alloc(&s->d_src_flag, (size_t)m));
+    GLB_CUDA(dev_alloc(&s->d_sync, 2 * sizeof(unsigned)));
     GLB_CUDA(cudaMemsetAsync(s->d_sync, 0, 2 * sizeof(unsigned), st));
     GLB_CUDA(cudaMemcpyAsync(s->d_ent, ent.data(), sizeof(int4) * ent.size(), cudaMemcpyHostToDevice, st));
     GLB_CUDA(cudaMemcpyAsync(s->d_slice_first, slice_first.data(), sizeof(int) * (nslices + 1), cudaMemcpyHostToDevice, st));
     GLB_CUDA(cudaMemcpyAsync(s->d_slice_rows, slice_rows.data(), sizeof(int) * slice_rows.size(), cudaMemcpyHostToDevice, st));
     if (!send_ptr.empty()) {
-        GLB_CUDA(cudaMalloc(&s->d_send_ptr, sizeof(long long) * send_ptr.size()));
-        GLB_CUDA(cudaMalloc(&s->d_send_ent, sizeof(int2) * std::max<size_t>(send_ent.size(), 1)));
+        GLB_CUDA(dev_alloc(&s->d_send_ptr, sizeof(long long) * send_ptr.size()));
+        GLB_CUDA(dev_alloc(&s->d_send_ent, sizeof(int2) * std::max<size_t>(send_ent.size(), 1)));
         GLB_CUDA(cudaMemcpyAsync(s->d_send_ptr, send_ptr.data(), sizeof(long long) * send_ptr.size(), cudaMemcpyHostToDevice, st));
         GLB_CUDA(cudaMemcpyAsync(s->d_send_ent, send_ent.data(), sizeof(int2) * send_ent.size(), cudaMemcpyHostToDevice, st));
     }
@@ -514,8 +534,8 @@ extern "C" GLB_API int glb_slab_create(glb_slab **out, const int32_t *h_rowptr, 
 extern "C" GLB_API int glb_slab_destroy(glb_slab *s)
 {
     if (!s) return 0;
-    cudaFree(s->d_ent); cudaFree(s->d_slice_first); cudaFree(s->d_slice_rows); cudaFree(s->d_send_ptr); cudaFree(s->d_send_ent);
-    cudaFree(s->d_src_flag); cudaFree(s->d_sync);
+    dev_free(s->d_ent); dev_free(s->d_slice_first); dev_free(s->d_slice_rows); dev_free(s->d_send_ptr); dev_free(s->d_send_ent);
+    dev_free(s->d_src_flag); dev_free(s->d_sync);
     delete s;
     return 0;
 }
@@ -591,6 +611,16 @@ extern "C" GLB_API int glb_slab_iterate(glb_slab *s, const float *d_Db, int T, i
     p.nbr_mask = s->nbr_mask;
     p.bnd_counter = s->d_sync; p.err_flag = s->d_sync + 1;
     p.nslices = s->nslices; p.n_bnd_tiles = s->n_bnd_slices / kSlabSPC; p.tile_entries = s->tile_entries;
+    {   // half of the CTAs start on the boundary tiles (the puts leave in the first half of the launch), the rest on interior
+        // tiles; the boundary group then takes as many interior tiles as evens out the number of tiles per CTA
+        const int ntiles = (s->nslices + kSlabSPC - 1) / kSlabSPC, G = s->grid;
+        const double bfrac = ntiles ? (double)p.n_bnd_tiles / ntiles : 0.0;
+        p.bnd_ctas = p.n_bnd_tiles == 0 ? 0 : (p.n_bnd_tiles >= ntiles || G < 2) ? G : std::min(G - 1, std::max(1, (int)(G * std::max(0.5, bfrac) + 0.5)));
+        const long long quota = ((long long)ntiles + G - 1) / G;                 // tiles per CTA
+        const long long share = quota * p.bnd_ctas - p.n_bnd_tiles;              // interior tiles of the boundary group
+        p.bnd_group_interior = (int)std::max<long long>(0, std::min<long long>(share, ntiles - p.n_bnd_tiles));
+        if (p.bnd_ctas >= G) p.bnd_group_interior = ntiles - p.n_bnd_tiles;     // no interior group: the boundary group does everything
+    }
     for (int r = 0; r < s->world; ++r)
         if ((s->nbr_mask >> r) & 1u) p.peer_flag[r] = reinterpret_cast<unsigned *>(s->region[r]) + s->rank;
     for (int t = 0; t < T; ++t) {

@@ -7,6 +7,8 @@ runs (graph_ops.cu), so nothing here is on the timed path.
 """
 from __future__ import annotations
 
+import ctypes
+
 import numpy as np
 from scipy import sparse
 
@@ -224,6 +226,31 @@ class graph:
         return u
 
     # ---- spectral decomposition on the GPU (spectral.cu / spectral.py) --------------------------------------
+    def page_rank(self, alpha=0.85, v=None, tol=1e-10):
+        """PageRank by the power iteration u <- alpha P u + (1 - alpha) v, P = W^T D^-1, until max |u_new - u| <= tol.
+        Reference graphlearning/graph.py:1374-1412; the products run on the device (fp64 block SpMM of spectral.cu, one
+        launch per iteration plus the max-norm reduction of mbo.cu), same iteration count as the reference."""
+        from . import _lib, device, spectral
+        n = self.num_nodes
+        u0 = np.ones((n,)) / n
+        v = u0.copy() if v is None else np.asarray(v, dtype=np.float64)
+        D = self.degree_matrix(p=-1)
+        ops = spectral.BlockOps(sparse.csr_matrix(self.weight_matrix.T @ D))
+        u, vt = ops.upload(u0[:, None]), ops.upload(v[:, None])
+        w = ops.new(1)
+        err, it = tol + 1, 0
+        e = ctypes.c_double(0.0)
+        while err > tol:
+            ops.spmm(u, 1, out=w, alpha=alpha, Y2=vt, gamma=1 - alpha)
+            _lib.call("glb_max_abs_diff_f64", device.ptr(w), device.ptr(u), n, 1, int(w.shape[1]), int(u.shape[1]), ctypes.byref(e),
+                      device.cur_stream())
+            err = e.value
+            u, w = w, u
+            it += 1
+        self.page_rank_iterations = it
+        self.gpu_launches = ops.launches + it
+        return u[:, 0].cpu().numpy()
+
     def eigen_decomp(self, normalization="combinatorial", method="exact", k=10, c=None, gamma=0, tol=0, q=1):
         """Smallest k eigenpairs of the graph Laplacian.  Reference graphlearning/graph.py:623-806: same shifted /
         normalised matrices, same post-processing (vals = 1 - s or M - s, randomwalk vectors scaled by D^-1/2), same

@@ -39,21 +39,15 @@ class ssl:
         self.graph = W if type(W) == graph.graph else graph.graph(W)
 
     def volume_label_projection(self):
-        """ssl.py:172-209 (host post-processing of the scores; not on the device path)."""
+        """ssl.py:172-209: up to 10^4 rounds of predict -> class sizes -> weight update, in ONE kernel launch on the device
+        (csrc/mbo.cu, glb_volume_projection): the same fp64 operations in the same order, so `weights`, the labels and
+        `class_priors_error` are the reference's."""
         k = self.prob.shape[1]
         if type(self.weights) == int:
             self.weights = np.ones((k,))
-        dt = -0.1 if self.similarity else 0.1
-        i, err = 0, 1
-        while i < 1e4 and err > 1e-3:
-            i += 1
-            class_size = np.mean(utils.labels_to_onehot(self.predict(), k), axis=0)
-            grad = class_size - self.class_priors
-            err = np.max(np.absolute(grad))
-            self.weights += dt * grad
-            self.weights = self.weights / self.weights[0]
-        self.class_priors_error = err
-        return self.predict()
+        labels, self.weights, self.class_priors_error, self.projection_rounds = project_labels(
+            self.prob, self.class_priors, self.weights, self.similarity)
+        return labels
 
     def predict(self, ignore_class_priors=False):
         """ssl.py:230-266: global min-max scaling, then argmax (first maximum wins)."""
@@ -99,6 +93,29 @@ class ssl:
 
 def _as_ptr(a):
     return ctypes.c_void_p(a.ctypes.data)
+
+
+def project_labels(prob, class_priors, weights, similarity=True, device_prob=None):
+    """Volume-constrained label projection on the device (glb_volume_projection; reference ssl.py:172-209).
+    prob: (n,k) float64 host array, or device_prob = (torch tensor (n, ld) float64, k) already in HBM.
+    Returns (labels int64 (n,), weights (k,), max |class size - prior|, rounds)."""
+    from . import device
+    torch = device._torch()
+    if device_prob is None:
+        P = torch.from_numpy(np.ascontiguousarray(prob, dtype=np.float64)).cuda()
+        n, k = P.shape
+        ld = k
+    else:
+        P, k = device_prob
+        n, ld = P.shape
+    pri = torch.from_numpy(np.ascontiguousarray(class_priors, dtype=np.float64)).cuda()
+    w = torch.from_numpy(np.ascontiguousarray(weights, dtype=np.float64).copy()).cuda()
+    labels = torch.empty(n, dtype=torch.int64, device="cuda")
+    err = torch.zeros(1, dtype=torch.float64, device="cuda")
+    rounds = torch.zeros(1, dtype=torch.int32, device="cuda")
+    _lib.call("glb_volume_projection", device.ptr(P), n, int(k), int(ld), device.ptr(pri), int(bool(similarity)), 10000, 1e-3,
+              device.ptr(w), device.ptr(labels), device.ptr(err), device.ptr(rounds), device.cur_stream())
+    return labels.cpu().numpy(), w.cpu().numpy(), float(err.item()), int(rounds.item())
 
 
 class poisson(ssl):
@@ -177,6 +194,72 @@ class poisson(ssl):
             vals = vals ** self.p
         L = sparse.spdiags(1 / vals, 0, self.spectral_cutoff, self.spectral_cutoff)
         return V @ (L @ (V.T @ source))
+
+
+class poisson_mbo(ssl):
+    """PoissonMBO.  Reference graphlearning/ssl.py:696-839: Poisson learning as the initial guess, then T rounds of Ns heat
+    steps u <- (I - dt L) u + mu dt source (the same CSR x dense-label-matrix product as the Poisson iterate, here in fp64
+    like the reference's CPU branch :822-823, on the block SpMM of spectral.cu) followed by the volume-constrained
+    projection (device, csrc/mbo.cu).  The label matrix stays in HBM for the whole loop; only the result comes back.
+    `use_cuda` is accepted for API compatibility: the GPU is always used."""
+
+    def __init__(self, W=None, class_priors=None, solver="conjugate_gradient", use_cuda=False, min_iter=50, max_iter=1000,
+                 tol=1e-3, spectral_cutoff=10, Ns=40, mu=1, T=20):
+        super().__init__(W, class_priors)
+        if class_priors is None:
+            raise ValueError("PoissonMBO needs class_priors")
+        self.poisson_model = poisson(W, solver=solver, use_cuda=use_cuda, min_iter=min_iter, max_iter=max_iter, tol=tol,
+                                     spectral_cutoff=spectral_cutoff)
+        self.Ns, self.mu, self.T, self.use_cuda = Ns, mu, T, use_cuda
+        fname = "_poisson_mbo"
+        if solver == "spectral":
+            fname += "_N%d" % spectral_cutoff
+        fname += "_Ns_%d_mu_%.2f_T_%d" % (Ns, mu, T)
+        self.accuracy_filename = fname
+        self.name = "Poisson MBO"
+        self.gpu_launches = 0
+
+    def _fit(self, train_ind, train_labels, all_labels=None):
+        from . import device, spectral
+        torch = device._torch()
+        Ns, mu, T = self.Ns, self.mu, self.T
+        n = self.graph.num_nodes
+        k = len(np.unique(train_labels))
+        W = self.graph.weight_matrix
+        W = sparse.csr_matrix(W - sparse.spdiags(W.diagonal(), 0, n, n))               # :793-795
+        G = graph.graph(W)
+        onehot = utils.labels_to_onehot(train_labels, k)
+        source = np.zeros((n, onehot.shape[1]))
+        source[train_ind] = onehot - np.mean(onehot, axis=0)                            # :798-800
+        labels = self.poisson_model.fit_predict(train_ind, train_labels, all_labels=all_labels)      # :803
+        dt = 1 / np.max(G.degree_vector())                                              # :807
+        P = sparse.csr_matrix(sparse.identity(n) - dt * G.laplacian())                  # :810
+        ops = spectral.BlockOps(P)
+        Db = ops.upload(mu * dt * source)                                               # :811
+        u = ops.upload(utils.labels_to_onehot(labels, k))                               # :804
+        tmp = ops.new(k)
+        ld = int(u.shape[1])
+        pri = torch.from_numpy(np.ascontiguousarray(self.class_priors, dtype=np.float64)).cuda()
+        if type(self.weights) == int:
+            self.weights = np.ones((k,))
+        w = torch.from_numpy(np.ascontiguousarray(self.weights, dtype=np.float64).copy()).cuda()
+        lab = torch.empty(n, dtype=torch.int64, device="cuda")
+        err = torch.zeros(1, dtype=torch.float64, device="cuda")
+        rounds = torch.zeros(1, dtype=torch.int32, device="cuda")
+        for i in range(T):
+            for _ in range(Ns):                                                         # heat steps, :822-823
+                ops.spmm(u, k, out=tmp, Y2=Db, gamma=1.0)
+                u, tmp = tmp, u
+            # projection step, :826-829 (weights persist from round to round, as self.weights does in the reference)
+            _lib.call("glb_volume_projection", device.ptr(u), n, k, ld, device.ptr(pri), int(bool(self.similarity)), 10000, 1e-3,
+                      device.ptr(w), device.ptr(lab), device.ptr(err), device.ptr(rounds), device.cur_stream())
+            _lib.call("glb_onehot_f64", device.ptr(lab), n, k, ld, device.ptr(u), device.cur_stream())
+            if all_labels is not None:
+                print("%d, Accuracy = %.2f" % (i, ssl_accuracy(lab.cpu().numpy(), all_labels, train_ind)))
+        self.weights = w.cpu().numpy()
+        self.class_priors_error = float(err.item())
+        self.gpu_launches = ops.launches + 2 * T
+        return u[:, :k].cpu().numpy()
 
 
 class laplace(ssl):

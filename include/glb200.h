@@ -38,6 +38,9 @@ extern "C" {
 #define GLB_E_TIMEOUT   (-5)   /* a polling loop of a persistent kernel hit its watchdog; results are invalid */
 
 GLB_API int glb_version(void);
+/* The library keeps freed device scratch (plans, search buffers) mapped in the CUDA stream-ordered memory pool so that the
+ * next call does not pay the driver's map / unmap again; this returns all of it to the driver.  Synchronises the device. */
+GLB_API int glb_release_workspace(void);
 GLB_API const char *glb_last_error(void);
 /* Number of SMs etc. of the current device; fails with GLB_E_NOGPU when there is none. */
 GLB_API int glb_device_info(int *sm_count, int *cc_major, int *cc_minor, int64_t *hbm_bytes);
@@ -308,6 +311,25 @@ GLB_API int glb_gram_f64(const double *d_X, int ldx, int c1, const double *d_Y, 
                          void *d_work, int64_t work_bytes, void *stream);
 GLB_API int glb_right_mul_f64(const double *d_X, int ldx, int64_t n, int c1, const double *d_S, int c2, double *d_Y, int ldy,
                               void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Label post-processing that follows the iterate (device pointers, stream-ordered).
+ *
+ * glb_volume_projection: ssl.volume_label_projection (graphlearning/ssl.py:172-209) - the projection step of PoissonMBO
+ *   (:826-829) and of every model fitted with class_priors (:476-477): up to max_rounds (10^4) rounds of
+ *   labels = predict() (global min-max scaling, argmax of scores * weights, ssl.py:257-264; argmin when similarity == 0),
+ *   grad = class sizes - priors, weights += -+0.1 * grad, weights /= weights[0], until max|grad| <= tol (1e-3) - in ONE
+ *   launch, the reference's fp64 operations in the reference's order.  prob: n x ld fp64 (k used columns); weights (k,
+ *   in/out), labels (n, int64), err (1 double), rounds (1 int) are device arrays.  k <= 64.
+ * glb_onehot_f64:        dst (n x ld fp64) = one-hot of labels with k columns (utils.labels_to_onehot, utils.py:536-572).
+ * glb_max_abs_diff_f64:  *h_out = max |x - y| over n x c entries (y may be NULL) - the stopping tests of the fixed-point
+ *   loops (graph.page_rank, graphlearning/graph.py:1408).  Synchronises the stream (host result).
+ * ------------------------------------------------------------------------------------------- */
+GLB_API int glb_volume_projection(const double *d_prob, int64_t n, int k, int ld, const double *d_priors, int similarity,
+                                  int max_rounds, double tol, double *d_weights, int64_t *d_labels, double *d_err, int *d_rounds,
+                                  void *stream);
+GLB_API int glb_onehot_f64(const int64_t *d_labels, int64_t n, int k, int ld, double *d_dst, void *stream);
+GLB_API int glb_max_abs_diff_f64(const double *d_x, const double *d_y, int64_t n, int c, int ldx, int ldy, double *h_out, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * kNN result -> CSR weight matrix.  Replaces the sparse assembly of weightmatrix.knn

@@ -105,6 +105,30 @@ def test_full_size_config2(kg):
     assert np.allclose(rec, dist[i], rtol=1e-12)
 
 
+@pytest.mark.parametrize("n,d,k,nrows", [(60000, 512, 21, 2000), (20000, 64, 11, 600), (17001, 100, 16, 600), (33000, 300, 51, 400)])
+def test_fused_tensor_core_search(kg, n, d, k, nrows):
+    """n >= 16384 and d >= 64: the fused TMA + tcgen05 search (thresholds from a sample, one filtered pass, the distance
+    block never leaves the SM).  Config 3 (60 000 x 512, k + 1 = 21) on 2 000 rows; sizes that are no multiple of the
+    128-point / 64-feature tiles; a k that needs the 128-candidate list."""
+    X, _ = orc.synthetic_blobs(n, d, c=10, seed=n % 97)
+    X = X.astype(np.float64)
+    ind, dist = kg.knnsearch_gpu(X, k)
+    assert kg.last_stats["fallback_rows"] < n // 500              # the certificate holds for (nearly) every row
+    rows = np.random.default_rng(2).choice(n, nrows, replace=False)
+    rows[:3] = (0, n - 1, n // 2)
+    Xr = X[rows]
+    # fp64 brute force for the sampled rows (|x|^2 + |y|^2 - 2xy picks a shortlist, exact differences rank it)
+    d2 = (Xr ** 2).sum(1)[:, None] + (X ** 2).sum(1)[None, :] - 2.0 * Xr @ X.T
+    short = np.argpartition(d2, 4 * k, axis=1)[:, :4 * k]
+    for t, i in enumerate(rows):
+        ex = np.linalg.norm(X[short[t]] - X[i], axis=1)
+        o = np.lexsort((short[t], ex))[:k]
+        assert np.array_equal(ind[i], short[t][o]), (i, ind[i], short[t][o])
+        assert np.allclose(dist[i], ex[o], rtol=1e-12, atol=1e-300)
+    assert np.array_equal(ind[:, 0], np.arange(n)) and np.all(dist[:, 0] == 0)
+    assert np.all(np.diff(dist, axis=1) >= 0)
+
+
 def test_weight_matrix_assembly_on_device_is_bit_identical(gl, moons, blobs, small, monkeypatch):
     """weightmatrix.knn for the gaussian kernel: COO -> CSR, (W + W^T)/2, zero diagonal on the device (knn_graph.cu)
     against the goldens of the reference and against the scipy expressions (weightmatrix.py:166-186), bit for bit."""

@@ -1,5 +1,5 @@
 """GPU experiment: where the time of the FIRST fit on a graph goes (GLB_TIMING=1 phases + Python-side wall clock)."""
-import os, sys, time
+import gc, os, sys, time
 os.environ["GLB_TIMING"] = "1"
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -9,7 +9,10 @@ from oracle import gl_oracle as orc
 W, labels = bench.build_workload()
 ti = orc.one_per_class(labels, rate=1, seed=0)
 torch.zeros(1, device="cuda"); torch.cuda.synchronize()
-for rep in range(2):
+m = None
+for rep in range(3):
+    m = None
+    gc.collect(); torch.cuda.synchronize()               # the previous graph's device state is freed BEFORE the clock starts
     Wc = W.copy()
     t0 = time.perf_counter()
     m = gl.ssl.poisson(Wc, solver="gradient_descent", min_iter=200, max_iter=200)
