@@ -971,7 +971,12 @@ static int knn_run(const double *d_X, int64_t n, int d, int k, long long *d_ind,
     }
     if (fused) {
         // ---- thresholds from a fixed pseudo-random sample of the database, then one filtered pass over all of it ----
-        const int s_n = (int)std::min<int64_t>(kFusedSample, n);
+        // sample size: the threshold is the R-th smallest of s sample distances, so its rank in the full set is ~ n R / s
+        // with a relative spread of 1 / sqrt(R) = 25 %; it has to stay above the ~2k + 16 candidates the certificate wants
+        // for (nearly) every row, so the expected rank is held at max(137, 8 k): s = 8192 at config 2 (k + 1 = 11),
+        // 5632 at config 3 (k + 1 = 21), where 8192 sent 100-170 of the 60 000 rows to the exact fallback
+        int s_n = (int)std::min<double>((double)kFusedSample, (double)n * kSampleR / std::max(137.0, 8.0 * k));
+        s_n = std::max(1024, s_n / 128 * 128);
         std::vector<int> h_rows((size_t)s_n);
         {   // s_n distinct rows: a multiplicative walk through the residues mod n (an odd stride coprime to n), fixed seed
             unsigned long long x = 0x9E3779B97F4A7C15ull % (unsigned long long)n, stride = (unsigned long long)(0.6180339887 * (double)n) | 1ull;

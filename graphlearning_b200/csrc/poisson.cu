@@ -33,9 +33,12 @@
 //   plain    row-major n x ldu fp32, ldu = glb_padded_ld(c)                        (step / barrier kernels)
 //   flagged  row-major n x ldu fp32, ldu = 4 * LANES; chunk q of a row = {x[3q], x[3q+1], x[3q+2], epoch}
 //            (dataflow kernel; the step kernel can read and write it too, ignoring the epoch word)
+#include <math.h>
 #include <stdlib.h>
 #include <string.h>
 #include <algorithm>
+#include <atomic>
+#include <thread>
 #include <vector>
 #include "common.cuh"
 
@@ -353,7 +356,7 @@ __device__ __forceinline__ void st_chunk(char *p, float a, float b, float c, uns
 // LONG = whole row; OWNER/PART = a hub row split over several warps, the PART warps leave their partial sums
 // (3 floats + iteration number per lane) in shared memory and the OWNER warp adds them in a fixed order.
 constexpr int kSlotNormal = 0, kSlotLong = 1, kSlotPart = 2, kSlotOwner = 3;
-constexpr int kLongRowDf = 32;                   // rows with more nonzeros get a warp (or several) of their own
+constexpr int kLongRowDf = GLB_DATAFLOW_LONG_ROW;                   // rows with more nonzeros get a warp (or several) of their own
 
 // Inner loop: no per-entry predicates at all.  Entries of a lane group are stored in PAIRS (one LDS.128 = two
 // (offset,value) entries, 8 lane groups side by side = one 128-byte wavefront), padding entries point at the scratch
@@ -779,6 +782,8 @@ struct glb_poisson_plan {
     int *d_slot_off = nullptr, *d_slot_rows = nullptr;
     int cap_entries = 0, cap_slots = 0, cap_parts = 0;
     double ell_fill = 0.0;              // nnz / stored entries of the slabs
+    int scheme = 0;                     // dataflow kernel: 0 = slots of rows sorted by length, 1 = slots of consecutive rows
+    double est_wavefronts = 0.0, est_steps = 0.0;   // gather wavefronts (distinct lines per warp-wide gather) and warp-steps per iteration
     float tuned_ms[2] = {0.f, 0.f};     // AUTO: measured ms of the trial run, {dataflow, barrier}
     int tuned_gate = 32;
     float *d_ring = nullptr;            // dataflow kernel: buffers 2 and 3 of the version ring (0 and 1 are the caller's u0/u1)
@@ -861,6 +866,302 @@ static void balanced_bounds(const std::vector<int> &h_rp, int64_t n, int grid, d
     bounds[grid] = (int)n;
 }
 
+// Sliced-ELL slabs of the dataflow kernel, built on the host from the CSR arrays of P (host copies).
+struct DfSlabs {
+    std::vector<int2> slab;            // entries of all CTAs back to back: (byte offset of the gathered row, value bits)
+    std::vector<int4> slots;           // (first entry relative to the CTA's slab, width, type | parts << 8, partial index)
+    std::vector<long long> slab_off;   // grid + 1
+    std::vector<int> slot_off, slot_rows, bounds;
+    int cap_entries = 0, cap_slots = 0, cap_parts = 0, scheme = 0;
+    long long wavefronts = 0, steps = 0;
+    bool has_long_rows = false;
+};
+
+static void build_dataflow_slabs(const std::vector<int> &h_rp, const int *h_col, const float *h_val, int64_t n, int lanes,
+                                 int grid, int nw, bool l1_first, int scheme_request, DfSlabs &S)
+{
+    const int rowb = lanes * 16, rpw = 32 / lanes;
+    const int64_t nnz = h_rp[n];
+    std::vector<int> bounds;
+    balanced_bounds(h_rp, n, grid, 2.0, bounds);
+    // CTA boundaries where the number of SHORT rows before them is a multiple of rpw: the aligned groups of the octet
+    // ordering (reorder.cu) then are the slots of scheme 1 below
+    {
+        std::vector<int> short_before((size_t)n + 1, 0);
+        for (int64_t i = 0; i < n; ++i) short_before[i + 1] = short_before[i] + (h_rp[i + 1] - h_rp[i] <= kLongRowDf ? 1 : 0);
+        for (int b = 1; b < grid; ++b) {
+            int i = std::max(bounds[b], bounds[b - 1]);
+            while (i < n && short_before[i] % rpw != 0) ++i;
+            bounds[b] = i;
+        }
+    }
+    const int line_shift = rowb >= 128 ? 0 : (rowb == 64 ? 1 : rowb == 32 ? 2 : 3);       // label rows per 128-byte line
+    const int part_max = kLongRowDf * rpw;            // nonzeros of one warp-wide piece of a long row (2 batches per lane group)
+    struct Slot { int type, nparts, pbuf, L, cost; int rows[32]; int nz0, nz1; std::vector<int2> ent; /* NORMAL: L x rpw (col, value bits) */ };
+    struct CtaOut {
+        std::vector<int2> slab;
+        std::vector<int4> slots;
+        std::vector<int> slot_rows;
+        int nparts = 0, depth = 0;
+        long long wavefronts = 0, steps = 0;
+        bool has_long = false;
+    };
+    // Schedule of one NORMAL slot: the entries of its rows (one row per lane group) are dealt to steps; one step = one
+    // warp-wide gather instruction = one L1 wavefront per DISTINCT 128-byte line.  The order of the entries inside a
+    // row is free, so entries of different rows that live in the same line are put into the same step: lines needed by
+    // many rows first, each into the step where most of those rows are still free.  Holes (a row with nothing to do
+    // in a step) re-gather a line another lane group of the step gathers anyway, with value 0: no extra wavefront and
+    // no predicate in the kernel's inner loop.
+    auto schedule = [&](Slot &sl, long long &wavefronts) {
+        struct Ref { int line, g, q; };
+        struct Item { unsigned mask; int line, first; };
+        std::vector<Ref> refs;
+        int maxlen = 0;
+        for (int g = 0; g < rpw; ++g) {
+            const int r = sl.rows[g];
+            if (r < 0) continue;
+            maxlen = std::max(maxlen, h_rp[r + 1] - h_rp[r]);
+            for (int q = h_rp[r]; q < h_rp[r + 1]; ++q) refs.push_back({h_col[q] >> line_shift, g, q});
+        }
+        sl.L = 0;
+        sl.ent.clear();
+        if (refs.empty()) return;
+        std::sort(refs.begin(), refs.end(), [](const Ref &a, const Ref &b) { return a.line != b.line ? a.line < b.line : (a.g != b.g ? a.g < b.g : a.q < b.q); });
+        std::vector<Item> items;
+        std::vector<int> item_q;
+        for (size_t a = 0; a < refs.size();) {
+            size_t e = a;
+            while (e < refs.size() && refs[e].line == refs[a].line) ++e;
+            for (int pass = 0;; ++pass) {                  // pass t: the t-th entry of every row that has one in this line
+                Item it{0u, refs[a].line, (int)item_q.size()};
+                for (size_t k = a; k < e;) {
+                    size_t ke = k;
+                    while (ke < e && refs[ke].g == refs[k].g) ++ke;
+                    if (k + pass < ke) { it.mask |= 1u << refs[k].g; item_q.push_back(refs[k + pass].q); }
+                    k = ke;
+                }
+                if (!it.mask) break;
+                items.push_back(it);
+            }
+            a = e;
+        }
+        std::stable_sort(items.begin(), items.end(), [](const Item &a, const Item &b) { return __builtin_popcount(a.mask) > __builtin_popcount(b.mask); });
+        std::vector<unsigned> busy((size_t)maxlen, 0u);
+        sl.ent.assign((size_t)maxlen * rpw, make_int2(-1, 0));
+        for (const Item &it : items) {
+            unsigned rem = it.mask;
+            while (rem) {
+                int best = -1, bc = 0;
+                const int want = __builtin_popcount(rem);
+                for (size_t st = 0; st < busy.size(); ++st) {
+                    const int c = __builtin_popcount(rem & ~busy[st]);
+                    if (c > bc) { bc = c; best = (int)st; if (c == want) break; }
+                }
+                if (best < 0) { busy.push_back(0u); sl.ent.resize(busy.size() * rpw, make_int2(-1, 0)); continue; }
+                const unsigned placed = rem & ~busy[best];
+                int k = 0;
+                for (int g = 0; g < rpw; ++g) {
+                    if (!(it.mask >> g & 1u)) continue;
+                    if (placed >> g & 1u) {
+                        const int q = item_q[it.first + k];
+                        sl.ent[(size_t)best * rpw + g] = make_int2(h_col[q], float_bits(h_val[q]));
+                    }
+                    ++k;
+                }
+                busy[best] |= placed;
+                rem &= ~placed;
+            }
+        }
+        while (!busy.empty() && busy.back() == 0u) busy.pop_back();
+        sl.L = (int)busy.size();
+        std::vector<int> lines;
+        for (int st = 0; st < sl.L; ++st) {
+            int donor = -1;
+            lines.clear();
+            for (int g = 0; g < rpw; ++g) {
+                const int c = sl.ent[(size_t)st * rpw + g].x;
+                if (c >= 0) { if (donor < 0) donor = c; lines.push_back(c >> line_shift); }
+            }
+            if (donor < 0) donor = st > 0 ? sl.ent[(size_t)(st - 1) * rpw].x : 0;    // (cannot happen: a step is never left empty)
+            for (int g = 0; g < rpw; ++g)
+                if (sl.ent[(size_t)st * rpw + g].x < 0) sl.ent[(size_t)st * rpw + g] = make_int2(donor, 0);
+            std::sort(lines.begin(), lines.end());
+            wavefronts += std::unique(lines.begin(), lines.end()) - lines.begin();
+        }
+    };
+    // Slabs of CTA b.  scheme 0: short rows sorted by length, rpw per slot (few holes); scheme 1: consecutive short rows
+    // (the aligned groups of the octet ordering: rows with many common neighbours side by side, more holes).
+    auto build_cta = [&](int b, int scheme, CtaOut &out) {
+        const int r0 = bounds[b], r1 = bounds[b + 1];
+        std::vector<Slot> cta_slots;
+        std::vector<int> order;
+        unsigned pad_next = (unsigned)b * 131u;
+        auto pad_off = [&]() -> unsigned {
+            // padding of the long-row slots gathers a scratch row behind row n-1 (value 0, always ready).  Through L1 one
+            // row per CTA (it stays resident in that SM's L1); at L2 they are dealt round robin over the scratch rows.
+            const unsigned r = l1_first ? (unsigned)(b % kScratchRows) : (pad_next++ % kScratchRows);
+            return (unsigned)(n + r) * (unsigned)rowb;
+        };
+        for (int r = r0; r < r1; ++r) if (h_rp[r + 1] - h_rp[r] <= kLongRowDf) order.push_back(r);
+        if (scheme == 0)
+            std::stable_sort(order.begin(), order.end(), [&](int a, int c2) { return h_rp[a + 1] - h_rp[a] > h_rp[c2 + 1] - h_rp[c2]; });
+        for (size_t k0 = 0; k0 < order.size(); k0 += rpw) {
+            cta_slots.emplace_back();
+            Slot &sl = cta_slots.back();
+            sl.type = kSlotNormal; sl.nparts = 0; sl.pbuf = 0; sl.nz0 = sl.nz1 = 0;
+            for (int g = 0; g < 32; ++g) sl.rows[g] = g < rpw && k0 + g < order.size() ? order[k0 + g] : -1;
+            schedule(sl, out.wavefronts);
+            out.steps += sl.L;
+            sl.cost = (sl.L + 1) / 2 + 2;
+        }
+        // long rows: one warp-wide slot per piece of at most part_max nonzeros
+        int nparts_cta = 0;
+        for (int r = r0; r < r1; ++r) {
+            const int len = h_rp[r + 1] - h_rp[r];
+            if (len <= kLongRowDf) continue;
+            out.has_long = true;
+            const int m = (len + part_max - 1) / part_max;
+            const int chunk = (len + m - 1) / m;
+            for (int q = 0; q < m; ++q) {
+                cta_slots.emplace_back();
+                Slot &sl = cta_slots.back();
+                sl.nparts = 0; sl.pbuf = 0;
+                sl.nz0 = h_rp[r] + q * chunk;
+                sl.nz1 = std::min(h_rp[r + 1], sl.nz0 + chunk);
+                sl.L = (sl.nz1 - sl.nz0 + rpw - 1) / rpw;
+                for (int g = 0; g < 32; ++g) sl.rows[g] = -1;
+                if (q == 0) {
+                    sl.type = m == 1 ? kSlotLong : kSlotOwner;
+                    sl.nparts = m - 1;
+                    sl.pbuf = nparts_cta;                 // partial sums nparts_cta .. nparts_cta + m - 2
+                    sl.rows[0] = r;
+                } else {
+                    sl.type = kSlotPart;
+                    sl.pbuf = nparts_cta + q - 1;
+                }
+                sl.cost = (sl.L + 1) / 2 + 2 + (q == 0 ? m - 1 : 0);
+                out.wavefronts += sl.nz1 - sl.nz0;
+                out.steps += sl.L;
+            }
+            nparts_cta += m - 1;
+        }
+        // deal the slots to the warps: PART pieces first, then OWNER/LONG, then NORMAL (a warp never waits in shared
+        // memory for a piece it has not produced yet itself); inside a class longest first to the least loaded warp
+        std::vector<std::vector<int>> per_warp((size_t)nw);
+        std::vector<long long> load((size_t)nw, 0ll);
+        std::vector<int> idx(cta_slots.size());
+        for (size_t i = 0; i < idx.size(); ++i) idx[i] = (int)i;
+        auto cls = [&](int i) { const int t = cta_slots[i].type; return t == kSlotPart ? 0 : (t == kSlotNormal ? 2 : 1); };
+        std::stable_sort(idx.begin(), idx.end(), [&](int a, int c2) {
+            if (cls(a) != cls(c2)) return cls(a) < cls(c2);
+            return cta_slots[a].cost > cta_slots[c2].cost;
+        });
+        // (warps of their own for the long rows were measured slower than mixing them: 40 vs 23 us/iteration on the
+        // 128-d graph, r1q probe under profiles/)
+        for (int i : idx) {
+            int w = 0;
+            for (int q = 1; q < nw; ++q) if (load[q] < load[w]) w = q;
+            per_warp[w].push_back(i);
+            load[w] += cta_slots[i].cost;
+        }
+        size_t depth = 0;
+        for (auto &v : per_warp) depth = std::max(depth, v.size());
+        // The entries of one warp's slots are stored back to back (the kernel walks them as one stream of pairs);
+        // the slot table is interleaved: slot k of warp w at k * nw + w.
+        std::vector<int> slot_first(depth * (size_t)nw, 0);
+        std::vector<int2> &slab = out.slab;
+        for (int w = 0; w < nw; ++w)
+            for (size_t k = 0; k < per_warp[w].size(); ++k) {
+                const Slot &sl = cta_slots[per_warp[w][k]];
+                slot_first[k * nw + w] = (int)slab.size();
+                // entries in pairs: entry j of lane group g at (j/2 * rpw + g) * 2 + (j & 1); width rounded up to even
+                const int Lst = (sl.L + 1) & ~1;
+                const size_t s0 = slab.size();
+                slab.resize(s0 + (size_t)Lst * rpw);
+                if (sl.type == kSlotNormal) {
+                    for (int j = 0; j < Lst; ++j)
+                        for (int g = 0; g < rpw; ++g) {
+                            // the odd step behind the last one: every lane group re-gathers ONE line of the last step
+                            const int2 e = j < sl.L ? sl.ent[(size_t)j * rpw + g] : make_int2(sl.ent[(size_t)(sl.L - 1) * rpw].x, 0);
+                            slab[s0 + ((size_t)(j / 2) * rpw + g) * 2 + (j & 1)] = make_int2((int)((unsigned)e.x * (unsigned)rowb), e.y);
+                        }
+                } else {
+                    for (size_t q = s0; q < slab.size(); ++q) slab[q] = make_int2((int)pad_off(), 0);
+                    for (int j = 0; j < sl.L; ++j)
+                        for (int g = 0; g < rpw; ++g) {
+                            const int qq = sl.nz0 + j * rpw + g;          // round-robin over the lane groups
+                            if (qq >= sl.nz1) continue;
+                            slab[s0 + ((size_t)(j / 2) * rpw + g) * 2 + (j & 1)] =
+                                make_int2((int)((unsigned)h_col[qq] * (unsigned)rowb), float_bits(h_val[qq]));
+                        }
+                }
+            }
+        for (size_t k = 0; k < depth; ++k)
+            for (int w = 0; w < nw; ++w) {
+                if (k >= per_warp[w].size()) {            // empty slot: nothing to gather, nothing to store
+                    out.slots.push_back(make_int4(0, 0, kSlotNormal, 0));
+                    for (int g = 0; g < rpw; ++g) out.slot_rows.push_back(-1);
+                    continue;
+                }
+                const Slot &sl = cta_slots[per_warp[w][k]];
+                out.slots.push_back(make_int4(slot_first[k * nw + w], sl.L, sl.type | (sl.nparts << 8), sl.pbuf));
+                for (int g = 0; g < rpw; ++g) out.slot_rows.push_back(sl.rows[g]);
+            }
+        out.nparts = nparts_cta;
+        out.depth = (int)depth;
+    };
+    // which grouping?  Estimated cost of an iteration = gather wavefronts (LSU pipe, one per cycle and SM) + 3.5 cycles
+    // of issue per warp-step (~14 instructions over 4 schedulers), on a sample of the CTAs.
+    int scheme = scheme_request;
+    if (scheme != 0 && scheme != 1) {
+        double cost[2] = {0.0, 0.0};
+        for (int sc = 0; sc < 2; ++sc)
+            for (int b = 0; b < grid; b += 16) {
+                CtaOut o;
+                build_cta(b, sc, o);
+                cost[sc] += (double)o.wavefronts + 3.5 * (double)o.steps;
+            }
+        scheme = cost[1] < cost[0] ? 1 : 0;
+    }
+    std::vector<CtaOut> ctas((size_t)grid);
+    {
+        const int nthreads = std::max(1, std::min({8, (int)std::thread::hardware_concurrency(), grid}));
+        std::atomic<int> next{0};
+        auto worker = [&]() { for (int b; (b = next.fetch_add(1)) < grid;) build_cta(b, scheme, ctas[b]); };
+        std::vector<std::thread> pool;
+        for (int t = 1; t < nthreads; ++t) pool.emplace_back(worker);
+        worker();
+        for (auto &t : pool) t.join();
+    }
+    std::vector<int2> &slab = S.slab;
+    std::vector<int4> &slots = S.slots;
+    std::vector<long long> &slab_off = S.slab_off;
+    std::vector<int> &slot_off = S.slot_off, &slot_rows = S.slot_rows;
+    slab.clear(); slots.clear(); slot_rows.clear();
+    slab_off.assign((size_t)grid + 1, 0);
+    slot_off.assign((size_t)grid + 1, 0);
+    slab.reserve((size_t)nnz + (size_t)nnz / 2 + 1024);
+    int cap_entries = 0, cap_slots = 0, cap_parts = 0;
+    long long wavefronts = 0, steps = 0;
+    S.has_long_rows = false;
+    for (int b = 0; b < grid; ++b) {
+        const CtaOut &o = ctas[b];
+        slab.insert(slab.end(), o.slab.begin(), o.slab.end());
+        slots.insert(slots.end(), o.slots.begin(), o.slots.end());
+        slot_rows.insert(slot_rows.end(), o.slot_rows.begin(), o.slot_rows.end());
+        slab_off[b + 1] = (long long)slab.size();
+        slot_off[b + 1] = (int)slots.size();
+        cap_entries = std::max(cap_entries, (int)o.slab.size());
+        cap_slots = std::max(cap_slots, o.depth * nw);
+        cap_parts = std::max(cap_parts, o.nparts);
+        wavefronts += o.wavefronts; steps += o.steps;
+        if (o.has_long) S.has_long_rows = true;
+    }
+    S.scheme = scheme; S.wavefronts = wavefronts; S.steps = steps;
+    S.cap_entries = cap_entries; S.cap_slots = cap_slots; S.cap_parts = cap_parts;
+    S.bounds = bounds;
+}
+
 // Try to set the plan up for the dataflow kernel.  Returns 0 and leaves kind untouched when the graph does not
 // qualify (pattern not symmetric, slabs too large for shared memory, label rows too wide).
 static int plan_try_dataflow(glb_poisson_plan *p, const std::vector<int> &h_rp, int sms, int max_smem, cudaStream_t st)
@@ -873,14 +1174,6 @@ static int plan_try_dataflow(glb_poisson_plan *p, const std::vector<int> &h_rp, 
     p->l1_first = exp_env("GLB_POISSON_L1", 1) != 0;
     p->poll_sleep = (unsigned)exp_env("GLB_POISSON_SLEEP", 0) & 0xffffu;
     p->poll_sleep |= (unsigned)exp_env("GLB_POISSON_FREE", 0) << 30;        // ceiling probes, -DGLB_EXPERIMENT only
-    const int pad_to = 2;
-    // padding entries gather a scratch row behind row n-1 (value 0, always ready).  Through L1 one row per CTA (it stays
-    // resident in that SM's L1); at L2 they are dealt round robin so that no single L2 line takes all of them.
-    unsigned pad_next = 0;
-    auto pad_off = [&](int cta) -> unsigned {
-        const unsigned r = p->l1_first ? (unsigned)(cta % kScratchRows) : (pad_next++ % kScratchRows);
-        return (unsigned)(n + r) * (unsigned)rowb;
-    };
     int grid = (int)((n + 63) / 64);                  // tiny graphs: at least ~64 rows per CTA
     if (grid > sms) grid = sms;
     if (grid < 1) grid = 1;
@@ -910,129 +1203,16 @@ static int plan_try_dataflow(glb_poisson_plan *p, const std::vector<int> &h_rp, 
     int threads = 0;
     const void *fn = pick_dataflow(lanes, p->l1_first, &threads);
     const int nw = threads / 32;
-    std::vector<int> bounds;
-    balanced_bounds(h_rp, n, grid, 2.0, bounds);
-    std::vector<int2> slab;
-    std::vector<int4> slots;
-    std::vector<long long> slab_off((size_t)grid + 1, 0);
-    std::vector<int> slot_off((size_t)grid + 1, 0), slot_rows, order, slot_first;
-    slab.reserve((size_t)nnz + (size_t)nnz / 4 + 1024);
-    int cap_entries = 0, cap_slots = 0, cap_parts = 0;
-    const int part_max = kLongRowDf * rpw;            // nonzeros of one warp-wide piece of a long row (2 batches per lane group)
-    struct Slot { int type, nparts, pbuf, L, first /*entry or row list start*/, cost; int rows[32]; int nz0, nz1; };
-    std::vector<Slot> cta_slots;
-    std::vector<std::vector<int>> per_warp((size_t)nw);
-    std::vector<long long> load((size_t)nw);
-    for (int b = 0; b < grid; ++b) {
-        const int r0 = bounds[b], r1 = bounds[b + 1];
-        cta_slots.clear();
-        // short rows: sorted by length, rpw per slot
-        order.clear();
-        for (int r = r0; r < r1; ++r) if (h_rp[r + 1] - h_rp[r] <= kLongRowDf) order.push_back(r);
-        std::stable_sort(order.begin(), order.end(), [&](int a, int c2) { return h_rp[a + 1] - h_rp[a] > h_rp[c2 + 1] - h_rp[c2]; });
-        for (size_t k0 = 0; k0 < order.size(); k0 += rpw) {
-            Slot sl{};
-            sl.type = kSlotNormal;
-            sl.L = h_rp[order[k0] + 1] - h_rp[order[k0]];
-            for (int g = 0; g < rpw; ++g) sl.rows[g] = k0 + g < order.size() ? order[k0 + g] : -1;
-            sl.cost = (sl.L + 1) / 2 + 2;
-            cta_slots.push_back(sl);
-        }
-        // long rows: one warp-wide slot per piece of at most part_max nonzeros
-        int nparts_cta = 0;
-        for (int r = r0; r < r1; ++r) {
-            const int len = h_rp[r + 1] - h_rp[r];
-            if (len <= kLongRowDf) continue;
-            p->has_long_rows = true;
-            const int m = (len + part_max - 1) / part_max;
-            const int chunk = (len + m - 1) / m;
-            for (int q = 0; q < m; ++q) {
-                Slot sl{};
-                sl.nz0 = h_rp[r] + q * chunk;
-                sl.nz1 = std::min(h_rp[r + 1], sl.nz0 + chunk);
-                sl.L = (sl.nz1 - sl.nz0 + rpw - 1) / rpw;
-                for (int g = 0; g < rpw; ++g) sl.rows[g] = -1;
-                if (q == 0) {
-                    sl.type = m == 1 ? kSlotLong : kSlotOwner;
-                    sl.nparts = m - 1;
-                    sl.pbuf = nparts_cta;                 // partial sums nparts_cta .. nparts_cta + m - 2
-                    sl.rows[0] = r;
-                } else {
-                    sl.type = kSlotPart;
-                    sl.pbuf = nparts_cta + q - 1;
-                }
-                sl.cost = (sl.L + 1) / 2 + 2 + (q == 0 ? m - 1 : 0);
-                cta_slots.push_back(sl);
-            }
-            nparts_cta += m - 1;
-        }
-        // deal the slots to the warps: PART pieces first, then OWNER/LONG, then NORMAL (a warp never waits in shared
-        // memory for a piece it has not produced yet itself); inside a class longest first to the least loaded warp
-        for (auto &v : per_warp) v.clear();
-        std::fill(load.begin(), load.end(), 0ll);
-        std::vector<int> idx(cta_slots.size());
-        for (size_t i = 0; i < idx.size(); ++i) idx[i] = (int)i;
-        auto cls = [&](int i) { const int t = cta_slots[i].type; return t == kSlotPart ? 0 : (t == kSlotNormal ? 2 : 1); };
-        std::stable_sort(idx.begin(), idx.end(), [&](int a, int c2) {
-            if (cls(a) != cls(c2)) return cls(a) < cls(c2);
-            return cta_slots[a].cost > cta_slots[c2].cost;
-        });
-        // (warps of their own for the long rows were measured slower than mixing them: 40 vs 23 us/iteration on the
-        // 128-d graph, r1q probe under profiles/)
-        for (int i : idx) {
-            int w = 0;
-            for (int q = 1; q < nw; ++q) if (load[q] < load[w]) w = q;
-            per_warp[w].push_back(i);
-            load[w] += cta_slots[i].cost;
-        }
-        size_t depth = 0;
-        for (auto &v : per_warp) depth = std::max(depth, v.size());
-        const long long base0 = (long long)slab.size();
-        // The entries of one warp's slots are stored back to back (the pipelined kernel walks them as one stream);
-        // the slot table is interleaved: slot k of warp w at k * nw + w.
-        slot_first.assign(depth * (size_t)nw, 0);
-        for (int w = 0; w < nw; ++w)
-            for (size_t k = 0; k < per_warp[w].size(); ++k) {
-                const Slot &sl = cta_slots[per_warp[w][k]];
-                slot_first[k * nw + w] = (int)((long long)slab.size() - base0);
-                // entries in pairs: entry j of lane group g at (j/2 * rpw + g) * 2 + (j & 1); width rounded up to a
-                // multiple of pad_to (pairs) with always-ready scratch entries
-                const int Lst = (sl.L + pad_to - 1) / pad_to * pad_to;
-                const size_t s0 = slab.size();
-                slab.resize(s0 + (size_t)Lst * rpw);
-                for (size_t q = s0; q < slab.size(); ++q) slab[q] = make_int2((int)pad_off(b), 0);
-                for (int j = 0; j < sl.L; ++j)
-                    for (int g = 0; g < rpw; ++g) {
-                        int q = -1;
-                        if (sl.type == kSlotNormal) {
-                            const int r = sl.rows[g];
-                            if (r >= 0 && j < h_rp[r + 1] - h_rp[r]) q = h_rp[r] + j;
-                        } else {
-                            const int qq = sl.nz0 + j * rpw + g;          // round-robin over the lane groups
-                            if (qq < sl.nz1) q = qq;
-                        }
-                        if (q < 0) continue;
-                        const size_t at = s0 + ((size_t)(j / 2) * rpw + g) * 2 + (j & 1);
-                        slab[at] = make_int2((int)((unsigned)h_col[q] * (unsigned)rowb), float_bits(h_val[q]));
-                    }
-            }
-        for (size_t k = 0; k < depth; ++k)
-            for (int w = 0; w < nw; ++w) {
-                if (k >= per_warp[w].size()) {            // empty slot: nothing to gather, nothing to store
-                    slots.push_back(make_int4(0, 0, kSlotNormal, 0));
-                    for (int g = 0; g < rpw; ++g) slot_rows.push_back(-1);
-                    continue;
-                }
-                const Slot &sl = cta_slots[per_warp[w][k]];
-                slots.push_back(make_int4(slot_first[k * nw + w], sl.L, sl.type | (sl.nparts << 8), sl.pbuf));
-                for (int g = 0; g < rpw; ++g) slot_rows.push_back(sl.rows[g]);
-            }
-        slab_off[b + 1] = (long long)slab.size();
-        slot_off[b + 1] = (int)slots.size();
-        cap_entries = std::max(cap_entries, (int)(slab_off[b + 1] - slab_off[b]));
-        cap_slots = std::max(cap_slots, (int)(depth * nw));
-        cap_parts = std::max(cap_parts, nparts_cta);
-    }
+    DfSlabs S;
+    build_dataflow_slabs(h_rp, h_col.data(), h_val.data(), n, lanes, grid, nw, p->l1_first, exp_env("GLB_POISSON_SCHEME", -1), S);
+    std::vector<int2> &slab = S.slab;
+    std::vector<int4> &slots = S.slots;
+    std::vector<long long> &slab_off = S.slab_off;
+    std::vector<int> &slot_off = S.slot_off, &slot_rows = S.slot_rows;
+    int cap_entries = S.cap_entries;
+    const int cap_slots = S.cap_slots, cap_parts = S.cap_parts;
+    p->has_long_rows = S.has_long_rows;
+    p->scheme = S.scheme; p->est_wavefronts = (double)S.wavefronts; p->est_steps = (double)S.steps;
     tm.lap("slab build");
     cap_entries = (cap_entries + 1) & ~1;
     const size_t smem = (size_t)cap_entries * 8 + (size_t)cap_slots * 16 + (size_t)cap_parts * 2 * lanes * 16 + (size_t)cap_slots * rpw * 4;
@@ -1260,6 +1440,80 @@ extern "C" GLB_API int glb_poisson_plan_kind(const glb_poisson_plan *plan) { ret
 extern "C" GLB_API int glb_poisson_plan_ld(const glb_poisson_plan *plan) { return plan ? plan->ldu : GLB_E_INVALID; }
 extern "C" GLB_API int64_t glb_poisson_plan_rows(const glb_poisson_plan *plan) { return plan ? plan->n + plan->scratch_row : GLB_E_INVALID; }
 extern "C" GLB_API double glb_poisson_plan_fill(const glb_poisson_plan *plan) { return plan ? plan->ell_fill : 0.0; }
+// Host-only check of the slab builder (tests, no GPU needed): builds the slabs of a c-column plan with `grid` CTAs
+// of 512 threads and walks them exactly as poisson_dataflow_kernel does (pairs of one warp's slots back to back, lane
+// group g of slot s owns row slot_rows[s * rpw + g], long rows summed over the lane groups and over their PART pieces),
+// computing y = P x for a fixed pseudo-random x in double precision.
+// out6 = {max |y - P x| / max |P x|, gather wavefronts, warp-steps, fill, scheme chosen, rows stored other than once}
+extern "C" GLB_API int glb_dataflow_slabs_check_host(const int32_t *h_rowptr, const int32_t *h_col, const float *h_val, int64_t n,
+                                                     int c, int grid, int scheme, double *out6)
+{
+    GLB_CHECK_ARG(h_rowptr && out6 && n > 0 && grid > 0 && c > 0, "bad argument");
+    const int lanes = flagged_lanes(c);
+    GLB_CHECK_ARG(lanes > 0, "c too wide for the dataflow kernel");
+    const int rowb = lanes * 16, rpw = 32 / lanes, nw = 16;
+    std::vector<int> h_rp(h_rowptr, h_rowptr + n + 1);
+    DfSlabs S;
+    build_dataflow_slabs(h_rp, h_col, h_val, n, lanes, grid, nw, true, scheme, S);
+    std::vector<double> x((size_t)n + kScratchRows, 0.0), y((size_t)n, 0.0), ref((size_t)n, 0.0);
+    unsigned long long lcg = 88172645463325252ull;
+    for (int64_t i = 0; i < n; ++i) { lcg = lcg * 6364136223846793005ull + 1442695040888963407ull; x[i] = (double)(lcg >> 11) / 9007199254740992.0 - 0.5; }
+    std::vector<int> stored((size_t)n, 0);
+    for (int b = 0; b < grid; ++b) {
+        const int2 *cv = S.slab.data() + S.slab_off[b];
+        const int sl0 = S.slot_off[b], nslots = S.slot_off[b + 1] - sl0;
+        std::vector<double> part((size_t)S.cap_parts + 1, 0.0);
+        for (int pass = 0; pass < 2; ++pass)                       // PART pieces first (the kernel's owner waits for them)
+            for (int w = 0; w < nw; ++w)
+                for (int k = 0; k * nw + w < nslots; ++k) {
+                    const int4 sl = S.slots[sl0 + k * nw + w];
+                    const int type = sl.z & 0xff;
+                    if ((type == kSlotPart) != (pass == 0)) continue;
+                    std::vector<double> acc((size_t)rpw, 0.0);
+                    const int npairs = (sl.y + 1) >> 1;
+                    for (int pp = 0; pp < npairs; ++pp)
+                        for (int g = 0; g < rpw; ++g)
+                            for (int h = 0; h < 2; ++h) {
+                                const int2 e = cv[sl.x + ((size_t)pp * rpw + g) * 2 + h];
+                                const unsigned off = (unsigned)e.x;
+                                if (off % (unsigned)rowb != 0 || off / rowb >= (unsigned)(n + kScratchRows)) { out6[0] = 1e300; return 0; }
+                                float v; memcpy(&v, &e.y, sizeof(v));
+                                acc[g] += (double)v * x[off / rowb];
+                            }
+                    const int *rows = S.slot_rows.data() + (size_t)(sl0 + k * nw + w) * rpw;
+                    if (type == kSlotNormal) {
+                        for (int g = 0; g < rpw; ++g) if (rows[g] >= 0) { y[rows[g]] = acc[g]; ++stored[rows[g]]; }
+                    } else {
+                        double sum = 0.0;
+                        for (int g = 0; g < rpw; ++g) sum += acc[g];
+                        if (type == kSlotPart) { part[sl.w] = sum; continue; }
+                        if (type == kSlotOwner) for (int q = 0; q < (sl.z >> 8); ++q) sum += part[sl.w + q];
+                        if (rows[0] >= 0) { y[rows[0]] = sum; ++stored[rows[0]]; }
+                    }
+                }
+    }
+    double worst = 0.0, big = 0.0;
+    long long bad = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        double r = 0.0;
+        for (int q = h_rp[i]; q < h_rp[i + 1]; ++q) r += (double)h_val[q] * x[h_col[q]];
+        worst = std::max(worst, fabs(r - y[i]));
+        big = std::max(big, fabs(r));
+        if (stored[i] != 1) ++bad;
+    }
+    out6[0] = big > 0.0 ? worst / big : worst;
+    out6[1] = (double)S.wavefronts; out6[2] = (double)S.steps;
+    out6[3] = S.slab.size() ? (double)h_rp[n] / (double)S.slab.size() : 1.0;
+    out6[4] = (double)S.scheme; out6[5] = (double)bad;
+    return 0;
+}
+
+extern "C" GLB_API int glb_poisson_plan_stats(const glb_poisson_plan *plan, double *out4)
+{
+    GLB_CHECK_ARG(plan && out4, "null pointer");
+    out4[0] = plan->est_wavefronts; out4[1] = plan->est_steps; out4[2] = plan->ell_fill; out4[3] = (double)plan->scheme;
+    return 0;
+}
 extern "C" GLB_API int glb_poisson_plan_gate(const glb_poisson_plan *plan) { return plan && plan->kind == GLB_POISSON_KIND_DATAFLOW ? plan->gate_every : 0; }
 
 extern "C" GLB_API int glb_poisson_pack(const glb_poisson_plan *plan, const double *d_src, const double *d_deg,

@@ -75,6 +75,13 @@ GLB_API int glb_poisson_scale(const int32_t *d_t_rowptr, const int32_t *d_t_col,
  * numbering).  Reverse Cuthill-McKee on the HOST from the CSR pattern the caller holds there; integers only.
  * h_perm[new] = old.  glb_csr_permute relabels an fp32 CSR matrix on the device: B = Pi A Pi^T. */
 GLB_API int glb_locality_order_host(const int32_t *h_rowptr, const int32_t *h_col, int64_t n, int32_t *h_perm);
+/* Octet ordering for the dataflow kernel: aligned groups of 2/4/8 consecutive rows are nodes with many common
+ * neighbours (three rounds of heavy-edge matching on shared-neighbour counts), octets in reverse Cuthill-McKee order of
+ * the octet graph.  One warp-wide gather of the dataflow kernel then touches few distinct 128-byte lines (the kernel is
+ * bound by L1 wavefronts, one per distinct line).  Rows longer than GLB_DATAFLOW_LONG_ROW nonzeros take no part and are
+ * spread between the octets.  Same conventions as glb_locality_order_host. */
+#define GLB_DATAFLOW_LONG_ROW 32
+GLB_API int glb_octet_order_host(const int32_t *h_rowptr, const int32_t *h_col, int64_t n, int32_t *h_perm);
 GLB_API int glb_csr_permute(const int32_t *d_rowptr, const int32_t *d_col, const float *d_val, int64_t n, int64_t nnz,
                             const int32_t *d_perm, int32_t *d_iperm, int32_t *d_out_rowptr, int32_t *d_out_col,
                             float *d_out_val, void *stream);
@@ -119,6 +126,14 @@ GLB_API int glb_poisson_plan_check(glb_poisson_plan *plan, void *stream);
 GLB_API double glb_poisson_plan_fill(const glb_poisson_plan *plan);
 /* iterations between two re-alignment gates of the dataflow kernel (tuned at plan time; 0 for other kinds) */
 GLB_API int glb_poisson_plan_gate(const glb_poisson_plan *plan);
+/* dataflow kernel, per iteration: out4 = {gather wavefronts (distinct 128-byte lines per warp-wide gather, summed),
+ * warp-steps (warp-wide gather instructions), slab fill, slot scheme (0 rows sorted by length, 1 consecutive rows)} */
+GLB_API int glb_poisson_plan_stats(const glb_poisson_plan *plan, double *out4);
+/* Host-only self-check of the dataflow slab builder (no GPU): builds the slabs for `grid` CTAs and walks them as the
+ * kernel does, computing y = P x in double precision.  out6 = {max |y - P x| / max |P x|, gather wavefronts,
+ * warp-steps, fill, scheme chosen (scheme < 0 = automatic), rows not stored exactly once}. */
+GLB_API int glb_dataflow_slabs_check_host(const int32_t *h_rowptr, const int32_t *h_col, const float *h_val, int64_t n, int c,
+                                          int grid, int scheme, double *out6);
 
 /* d_dst (n x ld fp32, plan layout) <- d_src (n x c fp64), each row divided by d_deg[row] when d_deg is not
  * NULL (Db = D^-1 source, ssl.py:636).  d_perm (may be NULL) is a locality ordering: device row r holds the
@@ -202,8 +217,9 @@ GLB_API int glb_ipc_free(void *d_ptr);
  *
  * glb_poisson_graph_create uploads the scipy CSR weight matrix W (canonical or not, diagonal ignored) and
  * builds, on the device, everything the reference recomputes in every _fit call: degrees, P = D^-1 W^T,
- * RW = W^T D^-1, vinf = deg/sum(deg).  reorder: 0 = keep the node numbering, 1 = relabel with a locality
- * ordering (results are still returned in the caller's numbering), -1 = automatic.
+ * RW = W^T D^-1, vinf = deg/sum(deg).  reorder: 0 = keep the node numbering, 1 = relabel with reverse
+ * Cuthill-McKee, 2 = relabel with the octet ordering (glb_octet_order_host), -1 = automatic; results are
+ * always returned in the caller's numbering.
  * glb_poisson_graph_fit runs one fit on that graph: source is the n x c fp64 Poisson source term
  * (ssl.py:619-622), train_ind the m labelled nodes (used by the stopping rule of ssl.py:639-641,667,669
  * when min_iter < max_iter; T = max_iter otherwise), u_out the n x c fp64 scores.  Synchronous.
