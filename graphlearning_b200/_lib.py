@@ -27,7 +27,6 @@ SIGNATURES = {
                                   c_void_p, c_int64, c_void_p]),
     "glb_poisson_scale": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "glb_locality_order_host": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
-    "glb_octet_order_host": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     "glb_csr_permute": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
                                 c_void_p, c_void_p]),
     "glb_poisson_plan_create": (c_int, [POINTER(c_void_p), c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int,
@@ -39,8 +38,11 @@ SIGNATURES = {
     "glb_poisson_plan_check": (c_int, [c_void_p, c_void_p]),
     "glb_poisson_plan_fill": (c_double, [c_void_p]),
     "glb_poisson_plan_gate": (c_int, [c_void_p]),
-    "glb_poisson_plan_stats": (c_int, [c_void_p, c_void_p]),
-    "glb_dataflow_slabs_check_host": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p]),
+    "glb_laplacian_csr_host": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
+                                        c_void_p, c_void_p]),
+    "glb_laplace_fit_host": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
+                                      c_void_p, c_int64, c_void_p, c_int, c_double, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "glb_dataflow_slabs_check_host": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p]),
     "glb_poisson_pack": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "glb_poisson_unpack": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "glb_poisson_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -144,14 +144,11 @@ extern "C" GLB_API int glb_poisson_graph_create(glb_poisson_graph **out, const i
 
     tm.lap("transpose/degree/scale");
     g->it_rp = g->t_rp; g->it_col = g->t_col; g->it_val = g->P_val;
-    // Node ordering: reorder < 0 = auto, 0 = caller's, 1 = reverse Cuthill-McKee, 2 = octets.  Auto: octets when the
-    // graph is a candidate for the dataflow kernel (its slabs, ~12 bytes per nonzero, fit the shared memory of all SMs),
-    // reverse Cuthill-McKee beyond.
+    // Locality ordering (reorder < 0 = auto)
     const bool want = reorder > 0 || (reorder < 0 && n >= kReorderMinNodes);
     if (want && nnz > 0) {
         std::vector<int> h_perm((size_t)n);
-        const bool octets = reorder == 2 || (reorder < 0 && (double)nnz * 12.0 <= (double)sm_count() * 200e3);
-        if ((rc = (octets ? glb_octet_order_host : glb_locality_order_host)(h_rowptr, h_col, n, h_perm.data()))) return rc;
+        if ((rc = glb_locality_order_host(h_rowptr, h_col, n, h_perm.data()))) return rc;
         int *iperm, *p_rp, *p_col;
         float *p_val;
         GLB_CUDA(g->A.alloc(&g->perm, n));  GLB_CUDA(tmp.alloc(&iperm, n));

@@ -433,23 +433,10 @@ knn_rerank_kernel(const double *__restrict__ X, int n, int d, const float *__res
     const int q = q0 + wq;
     const double *xq = X + (size_t)q * d;
     u64 keys[NPL];
-    double d2[NPL];
-    int idx[NPL];
 #pragma unroll
-    for (int i = 0; i < NPL; ++i) {
-        keys[i] = cand[(size_t)wq * C + lane * NPL + i];
-        idx[i] = (int)(unsigned)(keys[i] & 0xffffffffull);
-        d2[i] = INFINITY;
-        if (keys[i] != ~0ull) {
-            const double *xc = X + (size_t)idx[i] * d;
-            double s = 0.0;
-            for (int t = 0; t < d; ++t) { const double df = xq[t] - xc[t]; s = fma(df, df, s); }
-            d2[i] = s;
-        } else {
-            idx[i] = 0x7fffffff;
-        }
-    }
-    // certificate: approximate distances of list positions k-1 and C-1 (list is sorted ascending by approximate key)
+    for (int i = 0; i < NPL; ++i) keys[i] = cand[(size_t)wq * C + lane * NPL + i];
+    // certificate: approximate distances of list positions k-1 and C-1 (list is sorted ascending by approximate key;
+    // position p is slot p % NPL of lane p / NPL)
     const int pk = k - 1;
     u64 mine_k = keys[0];
 #pragma unroll
@@ -464,6 +451,46 @@ knn_rerank_kernel(const double *__restrict__ X, int n, int d, const float *__res
     // outside_bound (fused search): a lower bound on the approximate distance of every point that is NOT in the list.
     const bool certified = outside_bound ? (key_k != ~0ull && (double)outside_bound[wq] - (double)ak > 2.0 * E)
                                          : ((key_c == ~0ull) || ((double)ac - (double)ak > 2.0 * E));
+    // Only candidates with approx <= approx[k-1] + 2E can be among the k nearest: the k first of the list have a true
+    // distance <= approx[k-1] + E, every other point beyond that threshold a true distance > approx[k-1] + E.  The list is
+    // sorted, so they are its first m positions; position p goes to lane p % 32 (all lanes busy, one candidate each per
+    // round) and is evaluated as sum((x_i - x_j)^2) in fp64 from the original features, coordinates in order.
+    int m = 0;
+#pragma unroll
+    for (int i = 0; i < NPL; ++i) {
+        const bool in = keys[i] != ~0ull && (double)__uint_as_float((unsigned)(keys[i] >> 32)) <= (double)ak + 2.0 * E;
+        m += __popc(__ballot_sync(0xffffffffu, in));
+    }
+    if (key_k == ~0ull) m = C;                                 // fewer than k valid candidates: keep whatever there is
+    double d2[NPL];
+    int idx[NPL];
+#pragma unroll
+    for (int r = 0; r < NPL; ++r) {
+        d2[r] = INFINITY; idx[r] = 0x7fffffff;
+        if (r * 32 >= m) continue;                             // warp-uniform
+        const int pos = r * 32 + lane;
+        u64 key = ~0ull;
+#pragma unroll
+        for (int i = 0; i < NPL; ++i) {
+            const u64 got = __shfl_sync(0xffffffffu, keys[i], pos / NPL);
+            if (i == pos % NPL) key = got;
+        }
+        if (pos < m && key != ~0ull) {
+            idx[r] = (int)(unsigned)(key & 0xffffffffull);
+            const double *xc = X + (size_t)idx[r] * d;
+            double s = 0.0;
+            if ((d & 1) == 0) {                                // 16-byte loads, same order of the sum
+                for (int t = 0; t < d; t += 2) {
+                    const double2 a = *reinterpret_cast<const double2 *>(xq + t), b = __ldg(reinterpret_cast<const double2 *>(xc + t));
+                    const double d0 = a.x - b.x, d1 = a.y - b.y;
+                    s = fma(d0, d0, s); s = fma(d1, d1, s);
+                }
+            } else {
+                for (int t = 0; t < d; ++t) { const double df = xq[t] - xc[t]; s = fma(df, df, s); }
+            }
+            d2[r] = s;
+        }
+    }
     // rank of every candidate among the C by (exact d2, index): O(C) shuffles per element, C <= 128
     int rank[NPL];
 #pragma unroll
@@ -471,6 +498,7 @@ knn_rerank_kernel(const double *__restrict__ X, int n, int d, const float *__res
     for (int src = 0; src < 32; ++src) {
 #pragma unroll
         for (int j = 0; j < NPL; ++j) {
+            if (j * 32 >= m) continue;                         // warp-uniform: nothing was evaluated in that round
             const double od = __shfl_sync(0xffffffffu, d2[j], src);
             const int oi = __shfl_sync(0xffffffffu, idx[j], src);
 #pragma unroll
@@ -750,38 +778,53 @@ knn_fused_kernel(const __grid_constant__ CUtensorMap tm_qh, const __grid_constan
                                "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
                              : "r"(taddr) : "memory");
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                const float4 *nb4 = reinterpret_cast<const float4 *>(s_nb + acc * FBN + cb * 32);
-                // all 32 distances first (independent fused multiply-adds, no branch), as a hit mask
-                float d2[32];
+                const float *nbp = s_nb + acc * FBN + cb * 32;
+                const float4 *nb4 = reinterpret_cast<const float4 *>(nbp);
+                // Filter first, distances only for the hits: d = na + nb - 2 acc <= tau  <=>  acc >= nb / 2 + (na - tau) / 2, i.e.
+                // one multiply-add and one compare per element (the rounding of the threshold moves the cut by a few ulps of
+                // na + nb, which the error margin of the certificate covers, see knn_run).  0.2 % of the elements are hits, so
+                // the hit path is entered per group of 4 columns (a warp has a hit in a given group 1 time out of 4).
+                const float c0 = 0.5f * (na - tau);
                 unsigned hits = 0u;
 #pragma unroll
                 for (int j4 = 0; j4 < 8; ++j4) {
                     const float4 nb = nb4[j4];
-                    d2[j4 * 4 + 0] = fmaf(-2.f, __uint_as_float(v[j4 * 4 + 0]), na + nb.x);
-                    d2[j4 * 4 + 1] = fmaf(-2.f, __uint_as_float(v[j4 * 4 + 1]), na + nb.y);
-                    d2[j4 * 4 + 2] = fmaf(-2.f, __uint_as_float(v[j4 * 4 + 2]), na + nb.z);
-                    d2[j4 * 4 + 3] = fmaf(-2.f, __uint_as_float(v[j4 * 4 + 3]), na + nb.w);
+                    const float t0 = fmaf(0.5f, nb.x, c0), t1 = fmaf(0.5f, nb.y, c0), t2 = fmaf(0.5f, nb.z, c0), t3 = fmaf(0.5f, nb.w, c0);
+                    if (MODE == MODE_SAMPLE) {
+                        hits |= (__uint_as_float(v[j4 * 4 + 0]) > t0 ? 1u : 0u) << (j4 * 4 + 0);
+                        hits |= (__uint_as_float(v[j4 * 4 + 1]) > t1 ? 1u : 0u) << (j4 * 4 + 1);
+                        hits |= (__uint_as_float(v[j4 * 4 + 2]) > t2 ? 1u : 0u) << (j4 * 4 + 2);
+                        hits |= (__uint_as_float(v[j4 * 4 + 3]) > t3 ? 1u : 0u) << (j4 * 4 + 3);
+                    } else {
+                        hits |= (__uint_as_float(v[j4 * 4 + 0]) >= t0 ? 1u : 0u) << (j4 * 4 + 0);
+                        hits |= (__uint_as_float(v[j4 * 4 + 1]) >= t1 ? 1u : 0u) << (j4 * 4 + 1);
+                        hits |= (__uint_as_float(v[j4 * 4 + 2]) >= t2 ? 1u : 0u) << (j4 * 4 + 2);
+                        hits |= (__uint_as_float(v[j4 * 4 + 3]) >= t3 ? 1u : 0u) << (j4 * 4 + 3);
+                    }
                 }
+                if (MODE == MODE_SAMPLE && !(tau < INFINITY)) hits = live ? 0xffffffffu : 0u;     // list not full yet: c0 = -inf
 #pragma unroll
-                for (int j = 0; j < 32; ++j) hits |= (MODE == MODE_SAMPLE ? d2[j] < tau : d2[j] <= tau) ? (1u << j) : 0u;
-                if (hits) {
+                for (int j4 = 0; j4 < 8; ++j4) {
+                    if (hits & (0xfu << (j4 * 4))) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        if (hits & (1u << j)) {
-                            const float dd = fmaxf(d2[j], 0.f);
-                            if (MODE == MODE_SAMPLE) {
-                                if (dd < best[kSampleR - 1]) {       // tau shrinks while the hits of this chunk are taken
-                                    best[kSampleR - 1] = dd;         // replace the largest, bubble it into place
+                        for (int jj = 0; jj < 4; ++jj) {
+                            const int j = j4 * 4 + jj;
+                            if (hits & (1u << j)) {
+                                const float dd = fmaxf(fmaf(-2.f, __uint_as_float(v[j]), na + nbp[j]), 0.f);
+                                if (MODE == MODE_SAMPLE) {
+                                    if (dd < best[kSampleR - 1]) {       // the threshold shrinks while the hits of this chunk are taken
+                                        best[kSampleR - 1] = dd;         // replace the largest, bubble it into place
 #pragma unroll
-                                    for (int i = kSampleR - 1; i > 0; --i) {
-                                        const float lo = fminf(best[i - 1], best[i]), hi = fmaxf(best[i - 1], best[i]);
-                                        best[i - 1] = lo; best[i] = hi;
+                                        for (int i = kSampleR - 1; i > 0; --i) {
+                                            const float lo = fminf(best[i - 1], best[i]), hi = fmaxf(best[i - 1], best[i]);
+                                            best[i - 1] = lo; best[i] = hi;
+                                        }
+                                        tau = best[kSampleR - 1];
                                     }
-                                    tau = best[kSampleR - 1];
+                                } else {
+                                    if (cnt < a.cap) mybuf[cnt] = make_key(dd, col0 + cb * 32 + j);
+                                    ++cnt;
                                 }
-                            } else {
-                                if (cnt < a.cap) mybuf[cnt] = make_key(dd, col0 + cb * 32 + j);
-                                ++cnt;
                             }
                         }
                     }

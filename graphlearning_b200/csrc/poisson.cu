@@ -782,8 +782,6 @@ struct glb_poisson_plan {
     int *d_slot_off = nullptr, *d_slot_rows = nullptr;
     int cap_entries = 0, cap_slots = 0, cap_parts = 0;
     double ell_fill = 0.0;              // nnz / stored entries of the slabs
-    int scheme = 0;                     // dataflow kernel: 0 = slots of rows sorted by length, 1 = slots of consecutive rows
-    double est_wavefronts = 0.0, est_steps = 0.0;   // gather wavefronts (distinct lines per warp-wide gather) and warp-steps per iteration
     float tuned_ms[2] = {0.f, 0.f};     // AUTO: measured ms of the trial run, {dataflow, barrier}
     int tuned_gate = 32;
     float *d_ring = nullptr;            // dataflow kernel: buffers 2 and 3 of the version ring (0 and 1 are the caller's u0/u1)
@@ -872,32 +870,20 @@ struct DfSlabs {
     std::vector<int4> slots;           // (first entry relative to the CTA's slab, width, type | parts << 8, partial index)
     std::vector<long long> slab_off;   // grid + 1
     std::vector<int> slot_off, slot_rows, bounds;
-    int cap_entries = 0, cap_slots = 0, cap_parts = 0, scheme = 0;
+    int cap_entries = 0, cap_slots = 0, cap_parts = 0;
     long long wavefronts = 0, steps = 0;
     bool has_long_rows = false;
 };
 
 static void build_dataflow_slabs(const std::vector<int> &h_rp, const int *h_col, const float *h_val, int64_t n, int lanes,
-                                 int grid, int nw, bool l1_first, int scheme_request, DfSlabs &S)
+                                 int grid, int nw, bool l1_first, DfSlabs &S)
 {
     const int rowb = lanes * 16, rpw = 32 / lanes;
     const int64_t nnz = h_rp[n];
     std::vector<int> bounds;
     balanced_bounds(h_rp, n, grid, 2.0, bounds);
-    // CTA boundaries where the number of SHORT rows before them is a multiple of rpw: the aligned groups of the octet
-    // ordering (reorder.cu) then are the slots of scheme 1 below
-    {
-        std::vector<int> short_before((size_t)n + 1, 0);
-        for (int64_t i = 0; i < n; ++i) short_before[i + 1] = short_before[i] + (h_rp[i + 1] - h_rp[i] <= kLongRowDf ? 1 : 0);
-        for (int b = 1; b < grid; ++b) {
-            int i = std::max(bounds[b], bounds[b - 1]);
-            while (i < n && short_before[i] % rpw != 0) ++i;
-            bounds[b] = i;
-        }
-    }
-    const int line_shift = rowb >= 128 ? 0 : (rowb == 64 ? 1 : rowb == 32 ? 2 : 3);       // label rows per 128-byte line
     const int part_max = kLongRowDf * rpw;            // nonzeros of one warp-wide piece of a long row (2 batches per lane group)
-    struct Slot { int type, nparts, pbuf, L, cost; int rows[32]; int nz0, nz1; std::vector<int2> ent; /* NORMAL: L x rpw (col, value bits) */ };
+    struct Slot { int type, nparts, pbuf, L, cost; int rows[32]; int nz0, nz1; };
     struct CtaOut {
         std::vector<int2> slab;
         std::vector<int4> slots;
@@ -906,92 +892,8 @@ static void build_dataflow_slabs(const std::vector<int> &h_rp, const int *h_col,
         long long wavefronts = 0, steps = 0;
         bool has_long = false;
     };
-    // Schedule of one NORMAL slot: the entries of its rows (one row per lane group) are dealt to steps; one step = one
-    // warp-wide gather instruction = one L1 wavefront per DISTINCT 128-byte line.  The order of the entries inside a
-    // row is free, so entries of different rows that live in the same line are put into the same step: lines needed by
-    // many rows first, each into the step where most of those rows are still free.  Holes (a row with nothing to do
-    // in a step) re-gather a line another lane group of the step gathers anyway, with value 0: no extra wavefront and
-    // no predicate in the kernel's inner loop.
-    auto schedule = [&](Slot &sl, long long &wavefronts) {
-        struct Ref { int line, g, q; };
-        struct Item { unsigned mask; int line, first; };
-        std::vector<Ref> refs;
-        int maxlen = 0;
-        for (int g = 0; g < rpw; ++g) {
-            const int r = sl.rows[g];
-            if (r < 0) continue;
-            maxlen = std::max(maxlen, h_rp[r + 1] - h_rp[r]);
-            for (int q = h_rp[r]; q < h_rp[r + 1]; ++q) refs.push_back({h_col[q] >> line_shift, g, q});
-        }
-        sl.L = 0;
-        sl.ent.clear();
-        if (refs.empty()) return;
-        std::sort(refs.begin(), refs.end(), [](const Ref &a, const Ref &b) { return a.line != b.line ? a.line < b.line : (a.g != b.g ? a.g < b.g : a.q < b.q); });
-        std::vector<Item> items;
-        std::vector<int> item_q;
-        for (size_t a = 0; a < refs.size();) {
-            size_t e = a;
-            while (e < refs.size() && refs[e].line == refs[a].line) ++e;
-            for (int pass = 0;; ++pass) {                  // pass t: the t-th entry of every row that has one in this line
-                Item it{0u, refs[a].line, (int)item_q.size()};
-                for (size_t k = a; k < e;) {
-                    size_t ke = k;
-                    while (ke < e && refs[ke].g == refs[k].g) ++ke;
-                    if (k + pass < ke) { it.mask |= 1u << refs[k].g; item_q.push_back(refs[k + pass].q); }
-                    k = ke;
-                }
-                if (!it.mask) break;
-                items.push_back(it);
-            }
-            a = e;
-        }
-        std::stable_sort(items.begin(), items.end(), [](const Item &a, const Item &b) { return __builtin_popcount(a.mask) > __builtin_popcount(b.mask); });
-        std::vector<unsigned> busy((size_t)maxlen, 0u);
-        sl.ent.assign((size_t)maxlen * rpw, make_int2(-1, 0));
-        for (const Item &it : items) {
-            unsigned rem = it.mask;
-            while (rem) {
-                int best = -1, bc = 0;
-                const int want = __builtin_popcount(rem);
-                for (size_t st = 0; st < busy.size(); ++st) {
-                    const int c = __builtin_popcount(rem & ~busy[st]);
-                    if (c > bc) { bc = c; best = (int)st; if (c == want) break; }
-                }
-                if (best < 0) { busy.push_back(0u); sl.ent.resize(busy.size() * rpw, make_int2(-1, 0)); continue; }
-                const unsigned placed = rem & ~busy[best];
-                int k = 0;
-                for (int g = 0; g < rpw; ++g) {
-                    if (!(it.mask >> g & 1u)) continue;
-                    if (placed >> g & 1u) {
-                        const int q = item_q[it.first + k];
-                        sl.ent[(size_t)best * rpw + g] = make_int2(h_col[q], float_bits(h_val[q]));
-                    }
-                    ++k;
-                }
-                busy[best] |= placed;
-                rem &= ~placed;
-            }
-        }
-        while (!busy.empty() && busy.back() == 0u) busy.pop_back();
-        sl.L = (int)busy.size();
-        std::vector<int> lines;
-        for (int st = 0; st < sl.L; ++st) {
-            int donor = -1;
-            lines.clear();
-            for (int g = 0; g < rpw; ++g) {
-                const int c = sl.ent[(size_t)st * rpw + g].x;
-                if (c >= 0) { if (donor < 0) donor = c; lines.push_back(c >> line_shift); }
-            }
-            if (donor < 0) donor = st > 0 ? sl.ent[(size_t)(st - 1) * rpw].x : 0;    // (cannot happen: a step is never left empty)
-            for (int g = 0; g < rpw; ++g)
-                if (sl.ent[(size_t)st * rpw + g].x < 0) sl.ent[(size_t)st * rpw + g] = make_int2(donor, 0);
-            std::sort(lines.begin(), lines.end());
-            wavefronts += std::unique(lines.begin(), lines.end()) - lines.begin();
-        }
-    };
-    // Slabs of CTA b.  scheme 0: short rows sorted by length, rpw per slot (few holes); scheme 1: consecutive short rows
-    // (the aligned groups of the octet ordering: rows with many common neighbours side by side, more holes).
-    auto build_cta = [&](int b, int scheme, CtaOut &out) {
+    // Slabs of CTA b: short rows sorted by length, rpw per slot (few holes); long rows dealt over whole warps.
+    auto build_cta = [&](int b, CtaOut &out) {
         const int r0 = bounds[b], r1 = bounds[b + 1];
         std::vector<Slot> cta_slots;
         std::vector<int> order;
@@ -1003,14 +905,14 @@ static void build_dataflow_slabs(const std::vector<int> &h_rp, const int *h_col,
             return (unsigned)(n + r) * (unsigned)rowb;
         };
         for (int r = r0; r < r1; ++r) if (h_rp[r + 1] - h_rp[r] <= kLongRowDf) order.push_back(r);
-        if (scheme == 0)
-            std::stable_sort(order.begin(), order.end(), [&](int a, int c2) { return h_rp[a + 1] - h_rp[a] > h_rp[c2 + 1] - h_rp[c2]; });
+        std::stable_sort(order.begin(), order.end(), [&](int a, int c2) { return h_rp[a + 1] - h_rp[a] > h_rp[c2 + 1] - h_rp[c2]; });
         for (size_t k0 = 0; k0 < order.size(); k0 += rpw) {
             cta_slots.emplace_back();
             Slot &sl = cta_slots.back();
             sl.type = kSlotNormal; sl.nparts = 0; sl.pbuf = 0; sl.nz0 = sl.nz1 = 0;
             for (int g = 0; g < 32; ++g) sl.rows[g] = g < rpw && k0 + g < order.size() ? order[k0 + g] : -1;
-            schedule(sl, out.wavefronts);
+            sl.L = h_rp[order[k0] + 1] - h_rp[order[k0]];
+            for (int g = 0; g < rpw; ++g) if (sl.rows[g] >= 0) out.wavefronts += h_rp[sl.rows[g] + 1] - h_rp[sl.rows[g]];
             out.steps += sl.L;
             sl.cost = (sl.L + 1) / 2 + 2;
         }
@@ -1078,23 +980,20 @@ static void build_dataflow_slabs(const std::vector<int> &h_rp, const int *h_col,
                 const int Lst = (sl.L + 1) & ~1;
                 const size_t s0 = slab.size();
                 slab.resize(s0 + (size_t)Lst * rpw);
-                if (sl.type == kSlotNormal) {
-                    for (int j = 0; j < Lst; ++j)
-                        for (int g = 0; g < rpw; ++g) {
-                            // the odd step behind the last one: every lane group re-gathers ONE line of the last step
-                            const int2 e = j < sl.L ? sl.ent[(size_t)j * rpw + g] : make_int2(sl.ent[(size_t)(sl.L - 1) * rpw].x, 0);
-                            slab[s0 + ((size_t)(j / 2) * rpw + g) * 2 + (j & 1)] = make_int2((int)((unsigned)e.x * (unsigned)rowb), e.y);
-                        }
-                } else {
-                    for (size_t q = s0; q < slab.size(); ++q) slab[q] = make_int2((int)pad_off(), 0);
-                    for (int j = 0; j < sl.L; ++j)
-                        for (int g = 0; g < rpw; ++g) {
+                for (size_t q = s0; q < slab.size(); ++q) slab[q] = make_int2((int)pad_off(), 0);
+                for (int j = 0; j < sl.L; ++j)
+                    for (int g = 0; g < rpw; ++g) {
+                        int q = -1;
+                        if (sl.type == kSlotNormal) {
+                            const int r = sl.rows[g];
+                            if (r >= 0 && j < h_rp[r + 1] - h_rp[r]) q = h_rp[r] + j;      // entries in CSR order: same sums as the step kernel
+                        } else {
                             const int qq = sl.nz0 + j * rpw + g;          // round-robin over the lane groups
-                            if (qq >= sl.nz1) continue;
-                            slab[s0 + ((size_t)(j / 2) * rpw + g) * 2 + (j & 1)] =
-                                make_int2((int)((unsigned)h_col[qq] * (unsigned)rowb), float_bits(h_val[qq]));
+                            if (qq < sl.nz1) q = qq;
                         }
-                }
+                        if (q < 0) continue;
+                        slab[s0 + ((size_t)(j / 2) * rpw + g) * 2 + (j & 1)] = make_int2((int)((unsigned)h_col[q] * (unsigned)rowb), float_bits(h_val[q]));
+                    }
             }
         for (size_t k = 0; k < depth; ++k)
             for (int w = 0; w < nw; ++w) {
@@ -1110,24 +1009,11 @@ static void build_dataflow_slabs(const std::vector<int> &h_rp, const int *h_col,
         out.nparts = nparts_cta;
         out.depth = (int)depth;
     };
-    // which grouping?  Estimated cost of an iteration = gather wavefronts (LSU pipe, one per cycle and SM) + 3.5 cycles
-    // of issue per warp-step (~14 instructions over 4 schedulers), on a sample of the CTAs.
-    int scheme = scheme_request;
-    if (scheme != 0 && scheme != 1) {
-        double cost[2] = {0.0, 0.0};
-        for (int sc = 0; sc < 2; ++sc)
-            for (int b = 0; b < grid; b += 16) {
-                CtaOut o;
-                build_cta(b, sc, o);
-                cost[sc] += (double)o.wavefronts + 3.5 * (double)o.steps;
-            }
-        scheme = cost[1] < cost[0] ? 1 : 0;
-    }
     std::vector<CtaOut> ctas((size_t)grid);
     {
         const int nthreads = std::max(1, std::min({8, (int)std::thread::hardware_concurrency(), grid}));
         std::atomic<int> next{0};
-        auto worker = [&]() { for (int b; (b = next.fetch_add(1)) < grid;) build_cta(b, scheme, ctas[b]); };
+        auto worker = [&]() { for (int b; (b = next.fetch_add(1)) < grid;) build_cta(b, ctas[b]); };
         std::vector<std::thread> pool;
         for (int t = 1; t < nthreads; ++t) pool.emplace_back(worker);
         worker();
@@ -1157,7 +1043,7 @@ static void build_dataflow_slabs(const std::vector<int> &h_rp, const int *h_col,
         wavefronts += o.wavefronts; steps += o.steps;
         if (o.has_long) S.has_long_rows = true;
     }
-    S.scheme = scheme; S.wavefronts = wavefronts; S.steps = steps;
+    S.wavefronts = wavefronts; S.steps = steps;
     S.cap_entries = cap_entries; S.cap_slots = cap_slots; S.cap_parts = cap_parts;
     S.bounds = bounds;
 }
@@ -1204,7 +1090,7 @@ static int plan_try_dataflow(glb_poisson_plan *p, const std::vector<int> &h_rp, 
     const void *fn = pick_dataflow(lanes, p->l1_first, &threads);
     const int nw = threads / 32;
     DfSlabs S;
-    build_dataflow_slabs(h_rp, h_col.data(), h_val.data(), n, lanes, grid, nw, p->l1_first, exp_env("GLB_POISSON_SCHEME", -1), S);
+    build_dataflow_slabs(h_rp, h_col.data(), h_val.data(), n, lanes, grid, nw, p->l1_first, S);
     std::vector<int2> &slab = S.slab;
     std::vector<int4> &slots = S.slots;
     std::vector<long long> &slab_off = S.slab_off;
@@ -1212,7 +1098,6 @@ static int plan_try_dataflow(glb_poisson_plan *p, const std::vector<int> &h_rp, 
     int cap_entries = S.cap_entries;
     const int cap_slots = S.cap_slots, cap_parts = S.cap_parts;
     p->has_long_rows = S.has_long_rows;
-    p->scheme = S.scheme; p->est_wavefronts = (double)S.wavefronts; p->est_steps = (double)S.steps;
     tm.lap("slab build");
     cap_entries = (cap_entries + 1) & ~1;
     const size_t smem = (size_t)cap_entries * 8 + (size_t)cap_slots * 16 + (size_t)cap_parts * 2 * lanes * 16 + (size_t)cap_slots * rpw * 4;
@@ -1444,17 +1329,17 @@ extern "C" GLB_API double glb_poisson_plan_fill(const glb_poisson_plan *plan) { 
 // of 512 threads and walks them exactly as poisson_dataflow_kernel does (pairs of one warp's slots back to back, lane
 // group g of slot s owns row slot_rows[s * rpw + g], long rows summed over the lane groups and over their PART pieces),
 // computing y = P x for a fixed pseudo-random x in double precision.
-// out6 = {max |y - P x| / max |P x|, gather wavefronts, warp-steps, fill, scheme chosen, rows stored other than once}
+// out4 = {max |y - P x| / max |P x|, warp-steps per iteration, fill, rows stored other than once}
 extern "C" GLB_API int glb_dataflow_slabs_check_host(const int32_t *h_rowptr, const int32_t *h_col, const float *h_val, int64_t n,
-                                                     int c, int grid, int scheme, double *out6)
+                                                     int c, int grid, double *out4)
 {
-    GLB_CHECK_ARG(h_rowptr && out6 && n > 0 && grid > 0 && c > 0, "bad argument");
+    GLB_CHECK_ARG(h_rowptr && out4 && n > 0 && grid > 0 && c > 0, "bad argument");
     const int lanes = flagged_lanes(c);
     GLB_CHECK_ARG(lanes > 0, "c too wide for the dataflow kernel");
     const int rowb = lanes * 16, rpw = 32 / lanes, nw = 16;
     std::vector<int> h_rp(h_rowptr, h_rowptr + n + 1);
     DfSlabs S;
-    build_dataflow_slabs(h_rp, h_col, h_val, n, lanes, grid, nw, true, scheme, S);
+    build_dataflow_slabs(h_rp, h_col, h_val, n, lanes, grid, nw, true, S);
     std::vector<double> x((size_t)n + kScratchRows, 0.0), y((size_t)n, 0.0), ref((size_t)n, 0.0);
     unsigned long long lcg = 88172645463325252ull;
     for (int64_t i = 0; i < n; ++i) { lcg = lcg * 6364136223846793005ull + 1442695040888963407ull; x[i] = (double)(lcg >> 11) / 9007199254740992.0 - 0.5; }
@@ -1476,7 +1361,7 @@ extern "C" GLB_API int glb_dataflow_slabs_check_host(const int32_t *h_rowptr, co
                             for (int h = 0; h < 2; ++h) {
                                 const int2 e = cv[sl.x + ((size_t)pp * rpw + g) * 2 + h];
                                 const unsigned off = (unsigned)e.x;
-                                if (off % (unsigned)rowb != 0 || off / rowb >= (unsigned)(n + kScratchRows)) { out6[0] = 1e300; return 0; }
+                                if (off % (unsigned)rowb != 0 || off / rowb >= (unsigned)(n + kScratchRows)) { out4[0] = 1e300; return 0; }
                                 float v; memcpy(&v, &e.y, sizeof(v));
                                 acc[g] += (double)v * x[off / rowb];
                             }
@@ -1501,19 +1386,13 @@ extern "C" GLB_API int glb_dataflow_slabs_check_host(const int32_t *h_rowptr, co
         big = std::max(big, fabs(r));
         if (stored[i] != 1) ++bad;
     }
-    out6[0] = big > 0.0 ? worst / big : worst;
-    out6[1] = (double)S.wavefronts; out6[2] = (double)S.steps;
-    out6[3] = S.slab.size() ? (double)h_rp[n] / (double)S.slab.size() : 1.0;
-    out6[4] = (double)S.scheme; out6[5] = (double)bad;
+    out4[0] = big > 0.0 ? worst / big : worst;
+    out4[1] = (double)S.steps;
+    out4[2] = S.slab.size() ? (double)h_rp[n] / (double)S.slab.size() : 1.0;
+    out4[3] = (double)bad;
     return 0;
 }
 
-extern "C" GLB_API int glb_poisson_plan_stats(const glb_poisson_plan *plan, double *out4)
-{
-    GLB_CHECK_ARG(plan && out4, "null pointer");
-    out4[0] = plan->est_wavefronts; out4[1] = plan->est_steps; out4[2] = plan->ell_fill; out4[3] = (double)plan->scheme;
-    return 0;
-}
 extern "C" GLB_API int glb_poisson_plan_gate(const glb_poisson_plan *plan) { return plan && plan->kind == GLB_POISSON_KIND_DATAFLOW ? plan->gate_every : 0; }
 
 extern "C" GLB_API int glb_poisson_pack(const glb_poisson_plan *plan, const double *d_src, const double *d_deg,

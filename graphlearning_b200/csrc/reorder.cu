@@ -7,9 +7,7 @@
 // it runs once per graph on the host from the CSR pattern the caller already holds there; all relabelling of
 // matrices and label matrices is done on the device.  Results are returned in the caller's numbering.
 #include <algorithm>
-#include <atomic>
 #include <numeric>
-#include <thread>
 #include <vector>
 #include <cub/device/device_scan.cuh>
 #include "common.cuh"
@@ -92,224 +90,6 @@ extern "C" GLB_API int glb_locality_order_host(const int32_t *h_rowptr, const in
     std::vector<int> order;
     rcm_order(h_rowptr, h_col, n, order);
     std::copy(order.begin(), order.end(), h_perm);
-    return 0;
-}
-
-// ------------------------------------------------------------------------------------------------
-// Octet ordering for the dataflow iterate (poisson.cu).
-//
-// The dataflow kernel is bound by L1 wavefronts: one warp-wide gather instruction touches 32/LANES rows of the label
-// matrix and costs one wavefront per DISTINCT 128-byte line.  The 32/LANES matrix rows that one warp processes side by
-// side (a "slot") therefore should have as many neighbours in common as possible, and neighbours that are needed
-// together should share a line.  This ordering makes aligned groups of 2, 4 and 8 consecutive rows out of nodes with
-// many common neighbours: three rounds of heavy-edge matching on the shared-neighbour counts |N(i) & N(j)| of adjacent
-// nodes (the weights of a coarser level are the sums over the pairs of members), then the octets are put in reverse
-// Cuthill-McKee order of the octet graph so that a CTA's row block stays compact for L1/L2 locality.  Rows longer than
-// kLongRowDf nonzeros ("long" rows, processed warp-wide by the kernel) take no part: they are spread evenly between the
-// octets, so that counting SHORT rows every octet starts at a multiple of 8.  Groups that stayed incomplete go last.
-// Integers only; no arithmetic of the path.  h_perm[new] = old.
-namespace glb {
-
-// fn(begin, end) over [0, n) in chunks on up to 8 host threads
-template <typename F>
-static void parallel_chunks(int n, int chunk, F &&fn)
-{
-    const int nchunks = (n + chunk - 1) / chunk;
-    const int nt = std::max(1, std::min({8, (int)std::thread::hardware_concurrency(), nchunks}));
-    std::atomic<int> next{0};
-    auto worker = [&]() { for (int c; (c = next.fetch_add(1)) < nchunks;) fn(c * chunk, std::min(n, (c + 1) * chunk)); };
-    std::vector<std::thread> pool;
-    for (int t = 1; t < nt; ++t) pool.emplace_back(worker);
-    worker();
-    for (auto &t : pool) t.join();
-}
-
-struct WGraph {                       // symmetric weighted graph, CSR
-    std::vector<int> rp, col;
-    std::vector<float> w;
-    int n() const { return (int)rp.size() - 1; }
-};
-
-// heavy-edge matching; gid[i] = group of node i, returns the number of groups.  Nodes in order of increasing degree,
-// each takes its heaviest unmatched neighbour; leftovers are paired in index order.
-static int match_level(const WGraph &G, std::vector<int> &gid)
-{
-    const int n = G.n();
-    std::vector<int> mate((size_t)n, -1), order((size_t)n);
-    std::iota(order.begin(), order.end(), 0);
-    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return G.rp[a + 1] - G.rp[a] < G.rp[b + 1] - G.rp[b]; });
-    for (int i : order) {
-        if (mate[i] >= 0) continue;
-        int best = -1;
-        float bw = -1.f;
-        for (int p = G.rp[i]; p < G.rp[i + 1]; ++p) {
-            const int j = G.col[p];
-            if (j != i && mate[j] < 0 && (G.w[p] > bw || (G.w[p] == bw && j < best))) { best = j; bw = G.w[p]; }
-        }
-        if (best >= 0) { mate[i] = best; mate[best] = i; }
-    }
-    int prev = -1;
-    for (int i = 0; i < n; ++i) {
-        if (mate[i] >= 0) continue;
-        if (prev < 0) { prev = i; } else { mate[i] = prev; mate[prev] = i; prev = -1; }
-    }
-    gid.assign((size_t)n, -1);
-    int g = 0;
-    for (int i = 0; i < n; ++i) {
-        if (gid[i] >= 0) continue;
-        gid[i] = g;
-        if (mate[i] >= 0) gid[mate[i]] = g;
-        ++g;
-    }
-    return g;
-}
-
-static void coarsen(const WGraph &G, const std::vector<int> &gid, int ng, WGraph &C)
-{
-    const int n = G.n();
-    std::vector<int> mrp((size_t)ng + 1, 0), mem((size_t)n);
-    for (int i = 0; i < n; ++i) ++mrp[gid[i] + 1];
-    for (int g = 0; g < ng; ++g) mrp[g + 1] += mrp[g];
-    {
-        std::vector<int> fill(mrp.begin(), mrp.end() - 1);
-        for (int i = 0; i < n; ++i) mem[fill[gid[i]]++] = i;
-    }
-    // upper bound of the merged list of group g = sum of its members' degrees; merged in place in that window
-    std::vector<long long> win((size_t)ng + 1, 0);
-    for (int g = 0; g < ng; ++g) {
-        long long d = 0;
-        for (int q = mrp[g]; q < mrp[g + 1]; ++q) d += G.rp[mem[q] + 1] - G.rp[mem[q]];
-        win[g + 1] = win[g] + d;
-    }
-    std::vector<int> tcol((size_t)win[ng]);
-    std::vector<float> tw((size_t)win[ng]);
-    std::vector<int> clen((size_t)ng);
-    parallel_chunks(ng, 1024, [&](int g0, int g1) {
-        std::vector<std::pair<int, float>> acc;
-        for (int g = g0; g < g1; ++g) {
-            acc.clear();
-            for (int q = mrp[g]; q < mrp[g + 1]; ++q) {
-                const int i = mem[q];
-                for (int p = G.rp[i]; p < G.rp[i + 1]; ++p) {
-                    const int h = gid[G.col[p]];
-                    if (h != g) acc.emplace_back(h, G.w[p]);
-                }
-            }
-            std::sort(acc.begin(), acc.end(), [](const std::pair<int, float> &a, const std::pair<int, float> &b) { return a.first < b.first; });
-            long long o = win[g];
-            for (size_t q = 0; q < acc.size();) {
-                size_t e = q;
-                float s = 0.f;
-                while (e < acc.size() && acc[e].first == acc[q].first) s += acc[e++].second;
-                tcol[o] = acc[q].first; tw[o] = s; ++o;
-                q = e;
-            }
-            clen[g] = (int)(o - win[g]);
-        }
-    });
-    C.rp.assign((size_t)ng + 1, 0);
-    for (int g = 0; g < ng; ++g) C.rp[g + 1] = C.rp[g] + clen[g];
-    C.col.resize((size_t)C.rp[ng]); C.w.resize((size_t)C.rp[ng]);
-    for (int g = 0; g < ng; ++g) {
-        std::copy(tcol.begin() + win[g], tcol.begin() + win[g] + clen[g], C.col.begin() + C.rp[g]);
-        std::copy(tw.begin() + win[g], tw.begin() + win[g] + clen[g], C.w.begin() + C.rp[g]);
-    }
-}
-
-}  // namespace glb
-
-extern "C" GLB_API int glb_octet_order_host(const int32_t *h_rowptr, const int32_t *h_col, int64_t n, int32_t *h_perm)
-{
-    GLB_CHECK_ARG(h_rowptr && h_perm && (h_col || h_rowptr[n] == 0), "null pointer");
-    GLB_CHECK_ARG(n > 0 && n < (1ll << 31), "n out of range");
-    const int N = (int)n;
-    PhaseTimer tm("octet order");
-    // symmetric simple adjacency of the SHORT rows (sorted, unique, no self loops, no long rows)
-    std::vector<char> is_short((size_t)N);
-    std::vector<int> sid((size_t)N, -1), short_nodes, long_nodes;
-    for (int i = 0; i < N; ++i) {
-        is_short[i] = h_rowptr[i + 1] - h_rowptr[i] <= GLB_DATAFLOW_LONG_ROW;
-        if (is_short[i]) { sid[i] = (int)short_nodes.size(); short_nodes.push_back(i); } else long_nodes.push_back(i);
-    }
-    const int ns = (int)short_nodes.size();
-    WGraph G;
-    {
-        std::vector<int> cnt((size_t)ns + 1, 0);
-        auto each_edge = [&](auto &&f) {
-            for (int i = 0; i < N; ++i) {
-                if (!is_short[i]) continue;
-                for (int p = h_rowptr[i]; p < h_rowptr[i + 1]; ++p) {
-                    const int j = h_col[p];
-                    if (j < 0 || j >= N || j == i || !is_short[j]) continue;
-                    f(sid[i], sid[j]);
-                }
-            }
-        };
-        each_edge([&](int a, int b) { ++cnt[a + 1]; ++cnt[b + 1]; });
-        for (int i = 0; i < ns; ++i) cnt[i + 1] += cnt[i];
-        std::vector<int> adj((size_t)cnt[ns]), fill(cnt.begin(), cnt.end() - 1);
-        each_edge([&](int a, int b) { adj[fill[a]++] = b; adj[fill[b]++] = a; });
-        G.rp.assign((size_t)ns + 1, 0);
-        G.col.reserve(adj.size() / 2 + 16);
-        std::vector<int> ulen((size_t)ns);
-        parallel_chunks(ns, 2048, [&](int i0, int i1) {
-            for (int i = i0; i < i1; ++i) {
-                std::sort(adj.begin() + cnt[i], adj.begin() + cnt[i + 1]);
-                ulen[i] = (int)(std::unique(adj.begin() + cnt[i], adj.begin() + cnt[i + 1]) - (adj.begin() + cnt[i]));
-            }
-        });
-        for (int i = 0; i < ns; ++i) {
-            G.col.insert(G.col.end(), adj.begin() + cnt[i], adj.begin() + cnt[i] + ulen[i]);
-            G.rp[i + 1] = (int)G.col.size();
-        }
-        // weight of edge (i,j) = 1 + number of common neighbours (sorted-list intersection)
-        G.w.resize(G.col.size());
-        parallel_chunks(ns, 2048, [&](int i0, int i1) {
-        for (int i = i0; i < i1; ++i)
-            for (int p = G.rp[i]; p < G.rp[i + 1]; ++p) {
-                const int j = G.col[p];
-                int a = G.rp[i], b = G.rp[j], c = 0;
-                const int ae = G.rp[i + 1], be = G.rp[j + 1];
-                while (a < ae && b < be) {
-                    const int x = G.col[a], y = G.col[b];
-                    c += x == y; a += x <= y; b += y <= x;
-                }
-                G.w[p] = 1.f + (float)c;
-            }
-        });
-    }
-    tm.lap("adjacency + shared-neighbour weights");
-    // three levels of matching: groups of up to 2, 4, 8 short rows
-    std::vector<std::vector<int>> members((size_t)ns);
-    for (int i = 0; i < ns; ++i) members[i].push_back(short_nodes[i]);
-    WGraph C;
-    for (int lvl = 0; lvl < 3; ++lvl) {
-        std::vector<int> gid;
-        const int ng = match_level(G, gid);
-        coarsen(G, gid, ng, C);
-        std::vector<std::vector<int>> nm((size_t)ng);
-        for (size_t i = 0; i < members.size(); ++i) nm[gid[i]].insert(nm[gid[i]].end(), members[i].begin(), members[i].end());
-        members.swap(nm);
-        std::swap(G, C);
-        tm.lap("matching level");
-    }
-    // octets in reverse Cuthill-McKee order of the octet graph; complete octets first
-    std::vector<int> gorder;
-    if (G.n() > 0) rcm_order(G.rp.data(), G.col.data(), G.n(), gorder);
-    std::vector<int> full, rest;
-    for (int g : gorder) (members[g].size() == 8 ? full : rest).push_back(g);
-    size_t at = 0, next_long = 0;
-    const size_t nl = long_nodes.size(), nf = full.size();
-    for (size_t k = 0; k < nf; ++k) {
-        for (int v : members[full[k]]) h_perm[at++] = v;
-        // long rows spread evenly between the octets
-        const size_t upto = nf ? (k + 1) * nl / nf : nl;
-        while (next_long < upto) h_perm[at++] = long_nodes[next_long++];
-    }
-    while (next_long < nl) h_perm[at++] = long_nodes[next_long++];
-    for (int g : rest) for (int v : members[g]) h_perm[at++] = v;
-    tm.lap("octet RCM + output");
-    if ((int64_t)at != n) { set_error("glb_octet_order_host: internal error (%zu of %lld rows placed)", at, (long long)n); return GLB_E_INVALID; }
     return 0;
 }
 

@@ -76,14 +76,11 @@ class PoissonOperator:
     Setup lines of ssl.poisson._fit, reference graphlearning/ssl.py:615-617, 634-644."""
 
     KINDS = {"auto": -1, "step": 0, "barrier": 1, "dataflow": 2}
-    OCTET_MAX_NNZ = 4_000_000        # beyond: the slabs of the dataflow kernel no longer fit 148 x 227 KB of shared memory
 
     def __init__(self, W, reorder=False, kind="auto"):
-        """W: scipy CSR (host) or DeviceCSR.  reorder relabels the nodes for the iterate; inputs/outputs keep
-        the caller's numbering.  "octet": aligned groups of 8 rows with many common neighbours (one warp-wide gather
-        of the dataflow kernel then touches few distinct 128-byte lines), "rcm": reverse Cuthill-McKee, True: "octet"
-        for graphs whose slabs fit the dataflow kernel's shared memory, "rcm" beyond.  Computed on the host from the
-        pattern, so only possible when W arrives as a host matrix.  kind: which iterate kernel the plans
+        """W: scipy CSR (host) or DeviceCSR.  reorder=True relabels the nodes with a locality ordering
+        (reverse Cuthill-McKee from the host pattern) for the iterate; inputs/outputs keep the caller's
+        numbering.  Only possible when W arrives as a host matrix.  kind: which iterate kernel the plans
         of this operator use ("auto" picks dataflow -> barrier -> step, see include/glb200.h)."""
         torch = _torch()
         host_W = None if isinstance(W, DeviceCSR) else sparse.csr_matrix(W)
@@ -99,16 +96,12 @@ class PoissonOperator:
                   ptr(self.P_val), ptr(self.RW_val), cur_stream())
         # the arrays the iterate reads (relabelled when a locality ordering is in use)
         self.perm = None
-        self.ordering = "caller"
         self.it_rowptr, self.it_col, self.it_val = self.rowptr, self.col, self.P_val
         if reorder and host_W is not None and self.nnz > 0:
             rp = np.ascontiguousarray(host_W.indptr, dtype=np.int32)
             ci = np.ascontiguousarray(host_W.indices, dtype=np.int32)
             perm = np.empty(self.n, dtype=np.int32)
-            how = reorder if isinstance(reorder, str) else ("octet" if self.nnz <= self.OCTET_MAX_NNZ else "rcm")
-            self.ordering = how
-            _lib.call({"octet": "glb_octet_order_host", "rcm": "glb_locality_order_host"}[how],
-                      ctypes.c_void_p(rp.ctypes.data), ctypes.c_void_p(ci.ctypes.data),
+            _lib.call("glb_locality_order_host", ctypes.c_void_p(rp.ctypes.data), ctypes.c_void_p(ci.ctypes.data),
                       self.n, ctypes.c_void_p(perm.ctypes.data))
             dev = self.deg.device
             self.perm = torch.from_numpy(perm).to(dev)
@@ -157,12 +150,6 @@ class PoissonOperator:
 
     def gate(self, c=None):
         return int(_lib.load().glb_poisson_plan_gate(self.plan(c)))
-
-    def stats(self, c=None):
-        """dataflow plans: estimated gather wavefronts and warp-steps per iteration, slab fill, slot scheme."""
-        out = np.zeros(4)
-        _lib.call("glb_poisson_plan_stats", self.plan(c), ctypes.c_void_p(out.ctypes.data))
-        return {"gather_wavefronts": out[0], "warp_steps": out[1], "fill": out[2], "scheme": int(out[3])}
 
     def is_persistent(self, c=None):
         return self.kind(c) != "step"

@@ -88,23 +88,46 @@ class graph:
         A.data[:] = 1
         return A
 
-    def laplacian(self, normalization="combinatorial", alpha=1):
-        """graph.py:469-513."""
-        I = sparse.identity(self.num_nodes)
-        D = self.degree_matrix()
+    def _laplacian_scalings(self, normalization):
+        """(left, right, diag) of L = Diag(diag) - Diag(left) W Diag(right), with d^p computed as the reference computes
+        it (numpy power of the degree vector, graph.py:230)."""
+        d = self.degree_vector()
         if normalization == "combinatorial":
-            L = D - self.weight_matrix
-        elif normalization == "randomwalk":
-            L = I - self.degree_matrix(p=-1) * self.weight_matrix
-        elif normalization == "normalized":
-            Dinv2 = self.degree_matrix(p=-0.5)
-            L = I - Dinv2 * self.weight_matrix * Dinv2
-        elif normalization == "coifmanlafon":
+            return None, None, d
+        one = np.ones(self.num_nodes)
+        if normalization == "randomwalk":
+            return d ** -1, None, one
+        if normalization == "normalized":
+            dl = d ** -0.5
+            return dl, dl, one
+        raise ValueError("Invalid option for graph Laplacian normalization.")
+
+    def _canonical_weights(self):
+        W = self.weight_matrix
+        if not W.has_canonical_format:
+            W = W.copy()
+            W.sum_duplicates()
+        return (W, np.ascontiguousarray(W.indptr, dtype=np.int32), np.ascontiguousarray(W.indices, dtype=np.int32),
+                np.ascontiguousarray(W.data, dtype=np.float64))
+
+    def laplacian(self, normalization="combinatorial", alpha=1):
+        """graph.py:469-513.  The O(nnz) assembly runs on the device (glb_laplacian_csr_host, csrc/laplace.cu): same
+        values as the reference's scipy expressions bit for bit, canonical CSR."""
+        from . import _lib
+        if normalization == "coifmanlafon":
             D = self.degree_matrix(p=-alpha)
-            L = graph(D * self.weight_matrix * D).laplacian(normalization="randomwalk")
-        else:
-            raise ValueError("Invalid option for graph Laplacian normalization.")
-        return L.tocsr()
+            return graph(D * self.weight_matrix * D).laplacian(normalization="randomwalk")
+        left, right, diag = self._laplacian_scalings(normalization)
+        W, rp, ci, val = self._canonical_weights()
+        n = self.num_nodes
+        out_rp = np.empty(n + 1, dtype=np.int32)
+        out_ci = np.empty(W.nnz + n, dtype=np.int32)
+        out_val = np.empty(W.nnz + n, dtype=np.float64)
+        vp = lambda a: ctypes.c_void_p(a.ctypes.data) if a is not None else None
+        _lib.call("glb_laplacian_csr_host", vp(rp), vp(ci), vp(val), n, W.nnz, vp(left), vp(right), vp(diag), vp(out_rp),
+                  vp(out_ci), vp(out_val))
+        m = int(out_rp[n])
+        return sparse.csr_matrix((out_val[:m], out_ci[:m], out_rp), shape=(n, n))
 
     def reweight(self, idx, method="poisson", normalization="combinatorial", tau=0, X=None, alpha=2, zeta=1e7, r=0.1):
         """Reweight the weight matrix near the labelled nodes `idx`.  Reference graphlearning/graph.py:368-466; the

@@ -266,8 +266,8 @@ class laplace(ssl):
     """Laplace learning (label propagation).  Reference graphlearning/ssl.py:1106-1261.
 
     Solves tau u + L u = 0 on the unlabelled nodes with the labels as Dirichlet data: the Jacobi-scaled
-    sub-system M A M v = M b is assembled with the same scipy expressions as the reference (ssl.py:1222-1246)
-    and solved by the multi-column CG on the GPU (cg.cu).  reweighting in {'poisson', 'wnll', 'properly'} goes through
+    sub-system M A M v = M b (ssl.py:1222-1246) is assembled on the device (laplace.cu) and solved by the
+    multi-column CG (cg.cu) without leaving HBM; `system` restates the reference's scipy assembly (order > 1).  reweighting in {'poisson', 'wnll', 'properly'} goes through
     graph.reweight as in the reference (ssl.py:1209-1214).
     """
 
@@ -331,15 +331,48 @@ class laplace(ssl):
 
     def _fit(self, train_ind, train_labels, all_labels=None):
         n = self.graph.num_nodes
-        MAM, Mb, M, idx, F = self.system(train_ind, train_labels)
-        v, (it, err, nl) = utils.conjgrad(MAM, Mb, tol=self.tol, return_info=True)
-        self.iterations = it
-        self.gpu_launches = nl
-        u = np.zeros((n, F.shape[1]))
-        u[idx, :] = M * v
-        u[train_ind, :] = F
+        train_ind = np.asarray(train_ind)
+        fused = (int(self.order) == 1 and self.normalization in ("combinatorial", "randomwalk", "normalized")
+                 and len(np.unique(train_ind)) == len(train_ind) < n)
+        if fused:
+            u = self._fit_device(train_ind, train_labels)
+        else:
+            # order > 1 (powers of L are sparse-sparse products), repeated labelled nodes: the reference's scipy assembly,
+            # then the CG on the device
+            MAM, Mb, M, idx, F = self.system(train_ind, train_labels)
+            v, (it, err, nl) = utils.conjgrad(MAM, Mb, tol=self.tol, return_info=True)
+            self.iterations = it
+            self.gpu_launches = nl
+            u = np.zeros((n, F.shape[1]))
+            u[idx, :] = M * v
+            u[train_ind, :] = F
         if self.mean_shift:
             u -= np.mean(u, axis=0)
+        return u
+
+    def _fit_device(self, train_ind, train_labels):
+        """ssl.py:1208-1255 in one call of glb_laplace_fit_host: Laplacian, tau, Dirichlet sub-system, Jacobi scaling, CG and
+        the scatter of the solution all stay in HBM; the host computes the n values of d^p (numpy, as the reference)."""
+        import ctypes
+        from . import _lib
+        if self.reweighting == "none":
+            G = self.graph
+        else:
+            G = graph.graph(self.graph.reweight(train_ind, method=self.reweighting, normalization=self.normalization, X=self.X))
+        n = G.num_nodes
+        k = len(np.unique(train_labels))
+        F = np.ascontiguousarray(utils.labels_to_onehot(train_labels, k), dtype=np.float64)
+        left, right, diag = G._laplacian_scalings(self.normalization)
+        W, rp, ci, val = G._canonical_weights()
+        tau = np.ascontiguousarray(self.tau, dtype=np.float64) if np.any(self.tau != 0) else None
+        ti = np.ascontiguousarray(np.where(train_ind < 0, train_ind + n, train_ind), dtype=np.int64)
+        u = np.empty((n, F.shape[1]), dtype=np.float64)
+        it, err, nl = ctypes.c_int64(0), ctypes.c_double(0.0), ctypes.c_int(0)
+        vp = lambda a: ctypes.c_void_p(a.ctypes.data) if a is not None else None
+        _lib.call("glb_laplace_fit_host", vp(rp), vp(ci), vp(val), n, W.nnz, vp(left), vp(right), vp(diag), vp(tau), vp(ti),
+                  len(ti), vp(F), F.shape[1], float(self.tol), vp(u), ctypes.byref(it), ctypes.byref(err), ctypes.byref(nl))
+        self.iterations = it.value
+        self.gpu_launches = nl.value
         return u
 
 

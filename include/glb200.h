@@ -75,13 +75,7 @@ GLB_API int glb_poisson_scale(const int32_t *d_t_rowptr, const int32_t *d_t_col,
  * numbering).  Reverse Cuthill-McKee on the HOST from the CSR pattern the caller holds there; integers only.
  * h_perm[new] = old.  glb_csr_permute relabels an fp32 CSR matrix on the device: B = Pi A Pi^T. */
 GLB_API int glb_locality_order_host(const int32_t *h_rowptr, const int32_t *h_col, int64_t n, int32_t *h_perm);
-/* Octet ordering for the dataflow kernel: aligned groups of 2/4/8 consecutive rows are nodes with many common
- * neighbours (three rounds of heavy-edge matching on shared-neighbour counts), octets in reverse Cuthill-McKee order of
- * the octet graph.  One warp-wide gather of the dataflow kernel then touches few distinct 128-byte lines (the kernel is
- * bound by L1 wavefronts, one per distinct line).  Rows longer than GLB_DATAFLOW_LONG_ROW nonzeros take no part and are
- * spread between the octets.  Same conventions as glb_locality_order_host. */
-#define GLB_DATAFLOW_LONG_ROW 32
-GLB_API int glb_octet_order_host(const int32_t *h_rowptr, const int32_t *h_col, int64_t n, int32_t *h_perm);
+#define GLB_DATAFLOW_LONG_ROW 32   /* dataflow kernel: rows with more nonzeros are dealt over whole warps */
 GLB_API int glb_csr_permute(const int32_t *d_rowptr, const int32_t *d_col, const float *d_val, int64_t n, int64_t nnz,
                             const int32_t *d_perm, int32_t *d_iperm, int32_t *d_out_rowptr, int32_t *d_out_col,
                             float *d_out_val, void *stream);
@@ -126,14 +120,11 @@ GLB_API int glb_poisson_plan_check(glb_poisson_plan *plan, void *stream);
 GLB_API double glb_poisson_plan_fill(const glb_poisson_plan *plan);
 /* iterations between two re-alignment gates of the dataflow kernel (tuned at plan time; 0 for other kinds) */
 GLB_API int glb_poisson_plan_gate(const glb_poisson_plan *plan);
-/* dataflow kernel, per iteration: out4 = {gather wavefronts (distinct 128-byte lines per warp-wide gather, summed),
- * warp-steps (warp-wide gather instructions), slab fill, slot scheme (0 rows sorted by length, 1 consecutive rows)} */
-GLB_API int glb_poisson_plan_stats(const glb_poisson_plan *plan, double *out4);
 /* Host-only self-check of the dataflow slab builder (no GPU): builds the slabs for `grid` CTAs and walks them as the
- * kernel does, computing y = P x in double precision.  out6 = {max |y - P x| / max |P x|, gather wavefronts,
- * warp-steps, fill, scheme chosen (scheme < 0 = automatic), rows not stored exactly once}. */
+ * kernel does, computing y = P x in double precision.  out4 = {max |y - P x| / max |P x|, warp-wide gather
+ * instructions per iteration, fill, rows not stored exactly once}. */
 GLB_API int glb_dataflow_slabs_check_host(const int32_t *h_rowptr, const int32_t *h_col, const float *h_val, int64_t n, int c,
-                                          int grid, int scheme, double *out6);
+                                          int grid, double *out4);
 
 /* d_dst (n x ld fp32, plan layout) <- d_src (n x c fp64), each row divided by d_deg[row] when d_deg is not
  * NULL (Db = D^-1 source, ssl.py:636).  d_perm (may be NULL) is a locality ordering: device row r holds the
@@ -217,9 +208,8 @@ GLB_API int glb_ipc_free(void *d_ptr);
  *
  * glb_poisson_graph_create uploads the scipy CSR weight matrix W (canonical or not, diagonal ignored) and
  * builds, on the device, everything the reference recomputes in every _fit call: degrees, P = D^-1 W^T,
- * RW = W^T D^-1, vinf = deg/sum(deg).  reorder: 0 = keep the node numbering, 1 = relabel with reverse
- * Cuthill-McKee, 2 = relabel with the octet ordering (glb_octet_order_host), -1 = automatic; results are
- * always returned in the caller's numbering.
+ * RW = W^T D^-1, vinf = deg/sum(deg).  reorder: 0 = keep the node numbering, 1 = relabel with a locality
+ * ordering (results are still returned in the caller's numbering), -1 = automatic.
  * glb_poisson_graph_fit runs one fit on that graph: source is the n x c fp64 Poisson source term
  * (ssl.py:619-622), train_ind the m labelled nodes (used by the stopping rule of ssl.py:639-641,667,669
  * when min_iter < max_iter; T = max_iter otherwise), u_out the n x c fp64 scores.  Synchronous.
@@ -234,6 +224,31 @@ GLB_API int glb_poisson_graph_fit(glb_poisson_graph *graph, const double *h_sour
 GLB_API int glb_poisson_gd_host(const int32_t *h_rowptr, const int32_t *h_col, const double *h_val, int64_t n, int64_t nnz,
                                 const double *h_source, int c, const int64_t *h_train_ind, int64_t m, int min_iter,
                                 int max_iter, double *h_u_out, int *T_done, int *launches);
+
+/* ---------------------------------------------------------------------------------------------
+ * Graph Laplacians and the linear system of Laplace learning, assembled on the device (csrc/laplace.cu).
+ *
+ * glb_laplacian_csr_host replaces graph.laplacian (graphlearning/graph.py:469-513):
+ *     L = Diag(h_diag) - Diag(h_left) W Diag(h_right)        h_left / h_right may be NULL (= identity)
+ *     combinatorial: diag = d;   randomwalk: diag = 1, left = d^-1;   normalized: diag = 1, left = right = d^-1/2
+ * with d = W 1 and d^p computed by the caller exactly as the reference does (numpy, n values).  W: canonical scipy
+ * CSR (int32 / float64).  Every entry is rounded as scipy rounds it ((left_i w_ij) right_j, then the difference);
+ * exact zeros are dropped, columns are sorted, the diagonal is always present unless it is zero.  Outputs: HOST
+ * arrays, h_out_col / h_out_val with room for nnz + n entries; h_out_rowptr[n] is the number stored.
+ *
+ * glb_laplace_fit_host replaces ssl.laplace._fit for order = 1 (graphlearning/ssl.py:1222-1255): the matrix
+ * tau + L above, restricted to the unlabelled nodes and Jacobi scaled (M A M, M b with M = diag(A)^-1/2, b = -L[:, train] F),
+ * is assembled in HBM, solved by glb_cg_solve (tol, at most 1e5 iterations, as utils.conjgrad) and scattered back:
+ * h_u (n x c) = M v on the unlabelled nodes, F on the labelled ones.  h_tau: n values or NULL; h_train_ind: m distinct
+ * nodes in [0, n); h_F: m x c one-hot labels (utils.labels_to_onehot).  iters / err / launches may be NULL.
+ * ------------------------------------------------------------------------------------------- */
+GLB_API int glb_laplacian_csr_host(const int32_t *h_rowptr, const int32_t *h_col, const double *h_val, int64_t n, int64_t nnz,
+                                   const double *h_left, const double *h_right, const double *h_diag, int32_t *h_out_rowptr,
+                                   int32_t *h_out_col, double *h_out_val);
+GLB_API int glb_laplace_fit_host(const int32_t *h_rowptr, const int32_t *h_col, const double *h_val, int64_t n, int64_t nnz,
+                                 const double *h_left, const double *h_right, const double *h_diag, const double *h_tau,
+                                 const int64_t *h_train_ind, int64_t m, const double *h_F, int c, double tol, double *h_u,
+                                 int64_t *iters, double *err, int *launches);
 
 /* ---------------------------------------------------------------------------------------------
  * Conjugate gradient with c right-hand sides.  Replaces utils.conjgrad (graphlearning/utils.py:483-532):

@@ -2,8 +2,8 @@
 
 The reference's own scripts are executed with runpy against the alias package `graphlearning` (= graphlearning_b200)
 and a stand-in `matplotlib`.  The scripts live in the reference checkout, which exists in the build container only:
-  * not gpu:  the unmodified reference scripts run here with the two device entry points they reach (utils.conjgrad,
-              graph.poisson_handle) replaced by the CPU oracle - this pins the API surface (names, kwargs, return types,
+  * not gpu:  the unmodified reference scripts run here with the three device entry points they reach (utils.conjgrad,
+              graph.poisson_handle, ssl.laplace._fit_device) replaced by the CPU oracle - this pins the API surface (names, kwargs, return types,
               host logic) the scripts rely on;
   * gpu:      on the B200 box the same scripts run against the real backend when the checkout is present; otherwise
               the same call sequences, restated below, do.
@@ -78,7 +78,14 @@ def oracle_device(monkeypatch):
                 u = Db + P * u; v = RW * v; T += 1
             return u, T, 0
 
+    def laplace_fit_device(self, train_ind, train_labels):
+        u, it = orc.laplace_fit(self.graph.weight_matrix, train_ind, train_labels, normalization=self.normalization,
+                                tau=self.tau, tol=self.tol, return_iters=True)
+        self.iterations = it
+        return u
+
     monkeypatch.setattr(glb.utils, "conjgrad", conjgrad)
+    monkeypatch.setattr(glb.ssl.laplace, "_fit_device", laplace_fit_device)
     monkeypatch.setattr(glb.graph, "poisson_handle", lambda self: Handle(self.weight_matrix))      # glb.graph is the class
 
 

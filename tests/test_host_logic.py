@@ -29,12 +29,11 @@ def test_knn_kdtree_path_matches_reference(moons):
     same_csr(gl.weightmatrix.knn(moons["X"], 10, symmetrize=False), moons.csr("Wd"))
 
 
-def test_graph_degree_and_laplacian(moons):
+def test_graph_degree(moons):
+    """degree vector on the host as the reference; the Laplacians are assembled on the device (tests/test_laplace_gpu.py)."""
     G = gl.graph(moons.csr("W"))
     assert G.num_nodes == 500
     assert np.array_equal(G.degree_vector(), moons["deg"])
-    for nm in ("combinatorial", "randomwalk", "normalized"):
-        same_csr(G.laplacian(normalization=nm), moons.csr("L_" + nm))
     with pytest.raises(ValueError):
         G.laplacian(normalization="bogus")
 
@@ -155,9 +154,9 @@ def test_clustering_scores():
 
 
 def test_randomwalk_host_composition(moons, blobs, monkeypatch):
-    """ssl.randomwalk (reference ssl.py:1731-1793) = scipy assembly + ONE call of utils.conjgrad.  On CPU the solver call is
-    replaced by the oracle's CG (the device solver has its own parity tests), which pins everything around it to the golden
-    of the reference."""
+    """ssl.randomwalk (reference ssl.py:1731-1793) = Laplacian + host composition + ONE call of utils.conjgrad.  On CPU the
+    two device calls (graph.laplacian, utils.conjgrad) are replaced by the oracle's (they have their own parity tests on the
+    GPU), which pins everything around them to the golden of the reference."""
     from conftest import Golden, rel_err
     rwk = Golden("randomwalk")
 
@@ -166,9 +165,45 @@ def test_randomwalk_host_composition(moons, blobs, monkeypatch):
         return (x, (it, 0.0, 0)) if return_info else x
 
     monkeypatch.setattr(gl.utils, "conjgrad", cpu_conjgrad)
+    monkeypatch.setattr(gl.graph, "laplacian", lambda self, normalization="combinatorial", alpha=1: orc.laplacian(self.weight_matrix, normalization))
     for name, g, tkey in (("moons", moons, "train_ind"), ("blobs", blobs, "train_ind5")):
         ti, labels = g[tkey], g["labels"]
         m = gl.ssl.randomwalk(g.csr("W"))
         u = m.fit(ti, labels[ti])
         assert rel_err(u, rwk[name + "_u"]) < 1e-12 and np.array_equal(m.predict(), rwk[name + "_pred"])
         assert m.accuracy_filename == "_randomwalk" and m.iterations > 0
+
+
+# ---- dataflow kernel slabs (host-side builder of csrc/poisson.cu, checked without a GPU) ---------------------------
+def _slab_check(P, c, grid):
+    import ctypes
+    from graphlearning_b200 import _lib
+    P = sparse.csr_matrix(P)
+    rp = np.ascontiguousarray(P.indptr, dtype=np.int32)
+    ci = np.ascontiguousarray(P.indices, dtype=np.int32)
+    v = np.ascontiguousarray(P.data, dtype=np.float32)
+    out = np.zeros(4)
+    _lib.call("glb_dataflow_slabs_check_host", ctypes.c_void_p(rp.ctypes.data), ctypes.c_void_p(ci.ctypes.data),
+              ctypes.c_void_p(v.ctypes.data), P.shape[0], c, grid, ctypes.c_void_p(out.ctypes.data))
+    return {"err": out[0], "steps": out[1], "fill": out[2], "bad_rows": out[3]}
+
+
+@pytest.mark.parametrize("c,grid", [(10, 148), (1, 7), (3, 16), (17, 148), (40, 33)])
+def test_dataflow_slabs_hold_every_entry_once(c, grid):
+    """The sliced-ELL slabs of the dataflow kernel, walked on the host exactly as the kernel walks them, give y = P x:
+    every stored entry of P appears once, in the lane group of its row, padding entries carry the value 0, every row
+    is stored by exactly one slot.  Includes empty rows and hub rows split over several warps."""
+    rng = np.random.default_rng(c)
+    n = 5000
+    rows = np.repeat(np.arange(n), 9); cols = rng.integers(0, n, n * 9)
+    hub = rng.integers(0, n, 3)                                     # three hubs: rows of 40, 300 and 2000 nonzeros
+    rows = np.concatenate([rows] + [np.full(m, h) for h, m in zip(hub, (40, 300, 2000))])
+    cols = np.concatenate([cols] + [rng.choice(n, m, replace=False) for m in (40, 300, 2000)])
+    P = sparse.coo_matrix((rng.random(len(rows)), (rows, cols)), shape=(n, n)).tocsr()
+    P = sparse.csr_matrix(P + P.T)
+    keep = np.ones(n, bool); keep[rng.integers(0, n, 50)] = False   # 50 empty rows (and columns)
+    D = sparse.diags(keep.astype(float)); P = sparse.csr_matrix(D @ P @ D); P.eliminate_zeros()
+    r = _slab_check(P, c, grid)
+    assert r["bad_rows"] == 0
+    assert r["err"] < 1e-12
+    assert 0.3 < r["fill"] <= 1.0

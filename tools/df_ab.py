@@ -35,11 +35,11 @@ print("graph: n=%d nnz=%d max row %d; bytes/iteration %d" % (n, W.nnz, int(np.di
 
 def run(label, env, reorder):
     global first
-    for k in ("GLB_POISSON_L1", "GLB_POISSON_THREADS", "GLB_POISSON_SLEEP", "GLB_POISSON_GATE_EVERY", "GLB_POISSON_FREE", "GLB_POISSON_SCHEME"):
+    for k in ("GLB_POISSON_L1", "GLB_POISSON_THREADS", "GLB_POISSON_SLEEP", "GLB_POISSON_GATE_EVERY", "GLB_POISSON_FREE"):
         os.environ.pop(k, None)
     os.environ.update({k: str(v) for k, v in env.items()})
     try:
-        op = gdev.PoissonOperator(W, kind="dataflow", reorder={0: False, 1: "rcm", 2: "octet"}[reorder])
+        op = gdev.PoissonOperator(W, kind="dataflow", reorder=bool(reorder))
         Db = op.source_to_Db(src)
         u50 = op.unpack(op.iterate(Db, 50)[0], 10).cpu().numpy()
         err = float(np.abs(u50 - ref50).max() / np.abs(ref50).max())
@@ -55,9 +55,7 @@ def run(label, env, reorder):
             first = res
         d = float((res - first).abs().max() / first.abs().max())
         best = min(times)
-        st = op.stats(10)
-        label = "%s wf=%dk steps=%dk scheme=%d" % (label, st["gather_wavefronts"] / 1e3, st["warp_steps"] / 1e3, st["scheme"])
-        print("%-60s reorder=%d gate=%-2d fill=%.3f  us/iter best %.3f median %.3f worst %.3f  frac %.3f  err@50 %.1e  diff@1000 %.1e" % (
+        print("%-44s reorder=%d gate=%-2d fill=%.3f  us/iter best %.3f median %.3f worst %.3f  frac %.3f  err@50 %.1e  diff@1000 %.1e" % (
             label, reorder, op.gate(10), op.fill(10), best, float(np.median(times)), max(times),
             b_iter * 1000 / (best * 1e-3) / 1e9 / 6451.8, err, d), flush=True)
     except Exception as e:
@@ -65,17 +63,7 @@ def run(label, env, reorder):
 
 
 first = None
-if "octet" in sys.argv:
-    # node ordering (1 = RCM, 2 = octets) x slot scheme (0 = rows sorted by length, 1 = consecutive rows), with the
-    # ceiling probes of the winner
-    for reorder, scheme in ((1, 0), (2, 1), (1, 1), (2, 0), (0, 0)):
-        run("scheme=%d" % scheme, {"GLB_POISSON_SCHEME": scheme}, reorder)
-    for free in (1, 3):
-        run("scheme=1 free=%d" % free, {"GLB_POISSON_SCHEME": 1, "GLB_POISSON_FREE": free, "GLB_POISSON_GATE_EVERY": 0}, 2)
-    for threads in (768, 1024):
-        run("scheme=1 threads=%d" % threads, {"GLB_POISSON_SCHEME": 1, "GLB_POISSON_THREADS": threads}, 2)
-    run("scheme=1 gate4", {"GLB_POISSON_SCHEME": 1, "GLB_POISSON_GATE_EVERY": 4}, 2)
-elif "free" in sys.argv:
+if "free" in sys.argv:
     # ceiling probes: no synchronisation at all (free=1), and no stores either (free=3); results are wrong by design
     for l1, reorder in ((1, 1), (1, 0), (0, 0)):
         for free in (0, 1, 3):
