@@ -41,7 +41,7 @@ SIGNATURES = {
     "glb_laplacian_csr_host": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
                                         c_void_p, c_void_p]),
     "glb_laplace_fit_host": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
-                                      c_void_p, c_int64, c_void_p, c_int, c_double, c_void_p, c_void_p, c_void_p, c_void_p]),
+                                      c_void_p, c_int64, c_void_p, c_int, c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "glb_dataflow_slabs_check_host": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p]),
     "glb_poisson_pack": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "glb_poisson_unpack": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
@@ -96,6 +96,10 @@ SIGNATURES = {
                                       c_void_p, c_void_p]),
     "glb_onehot_f64": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p]),
     "glb_max_abs_diff_f64": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, POINTER(c_double), c_void_p]),
+    "glb_centered_step_f64": (c_int, [c_void_p, c_int, c_void_p, c_double, c_void_p, c_int, c_void_p, c_int64, c_int,
+                                       POINTER(c_double), c_void_p]),
+    "glb_min_nonneg_f64": (c_int, [c_void_p, c_int64, c_int, c_int, POINTER(c_double), c_void_p]),
+    "glb_argmax_rows_f64": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p]),
     "glb_poisson_gd_host": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int, c_void_p, c_int64,
                                     c_int, c_int, c_void_p, POINTER(c_int), POINTER(c_int)]),
 }

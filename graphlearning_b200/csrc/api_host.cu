@@ -78,7 +78,8 @@ using namespace glb;
 // (graph.graph(W), D, P = D^-1 W^T, RW = W^T D^-1, deg/sum(deg); ssl.py:615-617, 634-644) is built once here.
 struct glb_poisson_graph {
     int64_t n = 0, nnz = 0;
-    DeviceArena A;                       // owns every device buffer below
+    DeviceArena A;                       // owns the per-graph device buffers below
+    DeviceArena Aw;                      // owns the per-width buffers (src64, Db, u0, u1, tind): released when the width changes
     int *t_rp = nullptr, *t_col = nullptr;               // pattern of W^T
     float *P_val = nullptr;
     double *rw_val = nullptr, *deg = nullptr, *vinf = nullptr, *v = nullptr, *vtmp = nullptr, *part = nullptr;
@@ -185,12 +186,15 @@ extern "C" GLB_API int glb_poisson_graph_fit(glb_poisson_graph *g, const double 
     PhaseTimer tm("graph_fit");
     if (c != g->c_plan) {                                // (re)build the plan and the per-width buffers
         if (g->plan) { glb_poisson_plan_destroy(g->plan); g->plan = nullptr; g->c_plan = 0; }
+        for (void *q : g->Aw.ptrs) dev_free(q);                    // buffers of the previous width (nothing is in flight: fits are synchronous)
+        g->Aw.ptrs.clear();
+        g->src64 = nullptr; g->Db = g->u0 = g->u1 = nullptr; g->tind = nullptr; g->m_cap = 0;
         if ((rc = glb_poisson_plan_create(&g->plan, g->it_rp, g->it_col, g->it_val, n, nnz, c, GLB_POISSON_KIND_AUTO, st)))
             return rc;
         const int ld = glb_poisson_plan_ld(g->plan);
         const int64_t rows = glb_poisson_plan_rows(g->plan);          // n, or n + 1 with the library's scratch row
-        GLB_CUDA(g->A.alloc(&g->src64, n * c));  GLB_CUDA(g->A.alloc(&g->Db, rows * ld));
-        GLB_CUDA(g->A.alloc(&g->u0, rows * ld)); GLB_CUDA(g->A.alloc(&g->u1, rows * ld));
+        GLB_CUDA(g->Aw.alloc(&g->src64, n * c));  GLB_CUDA(g->Aw.alloc(&g->Db, rows * ld));
+        GLB_CUDA(g->Aw.alloc(&g->u0, rows * ld)); GLB_CUDA(g->Aw.alloc(&g->u1, rows * ld));
         GLB_CUDA(cudaMemsetAsync(g->Db, 0, rows * ld * sizeof(float), st));
         GLB_CUDA(cudaMemsetAsync(g->u1, 0, rows * ld * sizeof(float), st));
         g->rows = rows;
@@ -198,7 +202,7 @@ extern "C" GLB_API int glb_poisson_graph_fit(glb_poisson_graph *g, const double 
         tm.lap("plan_create + buffers");
     }
     const int ldu = g->ldu;
-    if (m > g->m_cap) { GLB_CUDA(g->A.alloc(&g->tind, m)); g->m_cap = m; }
+    if (m > g->m_cap) { GLB_CUDA(g->Aw.alloc(&g->tind, m)); g->m_cap = m; }
     GLB_CUDA(cudaMemcpyAsync(g->src64, h_source, n * c * sizeof(double), cudaMemcpyHostToDevice, st));
     if ((rc = glb_poisson_pack(g->plan, g->src64, g->deg, g->perm, g->Db, st))) return rc;
     nl += 1;

@@ -54,6 +54,7 @@ __device__ __forceinline__ void st4(double *p, const real4 &v)
 constexpr int kCgMaxLd = 128;
 constexpr int kCgThreads = 256;
 constexpr int kCgHist = 64;                 // iterations per batch = length of the err history window
+constexpr int kCgLongRow = 64;              // rows with more nonzeros are spread over a whole warp
 
 struct CgState {
     double rsold[kCgMaxLd];
@@ -139,6 +140,7 @@ cg_spmm_dot(const int *__restrict__ rowptr, const int *__restrict__ col, const d
     double d[4] = {0.0, 0.0, 0.0, 0.0};
     for (int row = rid; row < n; row += nrid) {
         const int beg = __ldg(rowptr + row), end = __ldg(rowptr + row + 1);
+        if (end - beg > kCgLongRow) continue;                         // hub rows: second loop, a whole warp per row
         real4 acc; acc.x = acc.y = acc.z = acc.w = 0.0;
         int j = beg;
         for (; j + 4 <= end; j += 4) {
@@ -162,6 +164,58 @@ cg_spmm_dot(const int *__restrict__ rowptr, const int *__restrict__ col, const d
         if (MODE == 0) {
             const real4 pr = ld4(p + (size_t)row * LDU + li * 4);
             d[0] += pr.x * acc.x; d[1] += pr.y * acc.y; d[2] += pr.z * acc.z; d[3] += pr.w * acc.w;
+        }
+    }
+    // Rows with more than kCgLongRow nonzeros (the hubs of high-dimensional kNN graphs: thousands of neighbours at
+    // d = 512): one lane group walking such a row alone would hold the whole launch.  Every warp looks through its
+    // own contiguous share of the rows (a fixed partition: deterministic) and spreads each long row it finds over
+    // its 32 / LANES lane groups; the partial sums are folded with shuffles in a fixed order.
+    {
+        constexpr int NG = 32 / LANES;
+        const int lane = threadIdx.x & 31, g = lane / LANES;
+        const int gw = (blockIdx.x * kCgThreads + threadIdx.x) >> 5, nwarps = (gridDim.x * kCgThreads) >> 5;
+        const int chunk = (n + nwarps - 1) / nwarps;
+        const int r0 = min(n, gw * chunk), r1 = min(n, r0 + chunk);
+        for (int base = r0; base < r1; base += 32) {
+            const int mine = base + lane;
+            const bool is_long = mine < r1 && __ldg(rowptr + mine + 1) - __ldg(rowptr + mine) > kCgLongRow;
+            unsigned todo = __ballot_sync(0xffffffffu, is_long);
+            while (todo) {
+                const int row = base + __ffs(todo) - 1;
+                todo &= todo - 1;
+                const int beg = __ldg(rowptr + row), end = __ldg(rowptr + row + 1);
+                real4 acc; acc.x = acc.y = acc.z = acc.w = 0.0;
+                int j = beg + g;
+                for (; j + 3 * NG < end; j += 4 * NG) {
+                    int cj[4]; double a[4]; real4 x[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) { cj[i] = __ldg(col + j + i * NG); a[i] = __ldg(val + j + i * NG); }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) x[i] = ld4(p + (size_t)cj[i] * LDU + li * 4);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        acc.x = fma(a[i], x[i].x, acc.x); acc.y = fma(a[i], x[i].y, acc.y);
+                        acc.z = fma(a[i], x[i].z, acc.z); acc.w = fma(a[i], x[i].w, acc.w);
+                    }
+                }
+                for (; j < end; j += NG) {
+                    const double a = __ldg(val + j);
+                    const real4 x = ld4(p + (size_t)__ldg(col + j) * LDU + li * 4);
+                    acc.x = fma(a, x.x, acc.x); acc.y = fma(a, x.y, acc.y); acc.z = fma(a, x.z, acc.z); acc.w = fma(a, x.w, acc.w);
+                }
+#pragma unroll
+                for (int off = LANES; off < 32; off <<= 1) {
+                    acc.x += __shfl_xor_sync(0xffffffffu, acc.x, off); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, off);
+                    acc.z += __shfl_xor_sync(0xffffffffu, acc.z, off); acc.w += __shfl_xor_sync(0xffffffffu, acc.w, off);
+                }
+                if (g == 0) {
+                    st4(Ap + (size_t)row * LDU + li * 4, acc);
+                    if (MODE == 0) {
+                        const real4 pr = ld4(p + (size_t)row * LDU + li * 4);
+                        d[0] += pr.x * acc.x; d[1] += pr.y * acc.y; d[2] += pr.z * acc.z; d[3] += pr.w * acc.w;
+                    }
+                }
+            }
         }
     }
     if (MODE != 0) return;
@@ -283,7 +337,7 @@ cg_unpack_kernel(const double *__restrict__ src, long long n, int c, int ldu, do
         dst[i] = src[r * ldu + (i - r * c)];
     }
 }
-static int cg_grid() { return sm_count() * 2; }
+static int cg_grid() { return sm_count() * 4; }      // 4 x 256 threads per SM: gather kernels, latency bound
 
 static size_t a256(size_t x) { return (x + 255) & ~(size_t)255; }
 
@@ -317,9 +371,11 @@ static int cg_run(const int *rp, const int *col, const double *val, int64_t n, c
     h.done = 0; h.iters = 0; h.err = 1.0;
     // the reference's loop test is evaluated before every iteration with err initialised to 1 (utils.py:519-521)
     if (!(1.0 > tol) || max_iter <= 0) { if (iters_out) *iters_out = 0; if (err_out) *err_out = 1.0; if (launches) *launches += nl; return 0; }
+    int64_t ramp = 16;                     // batches of 16, 32, 64, 64, ...: a solve that ends early leaves few idle launches behind
     while (!h.done && enq < max_iter) {
         int64_t batch = max_iter - enq;
-        if (batch > kCgHist) batch = kCgHist;
+        if (batch > ramp) batch = ramp;
+        if (ramp < kCgHist) ramp *= 2;
         for (int64_t i = 0; i < batch; ++i) {
             cg_spmm_dot<LANES, 0><<<grid, kCgThreads, 0, st>>>(rp, col, val, p, Ap, (int)n, c, partial, state);
             cg_update<LANES, false><<<grid, kCgThreads, 0, st>>>(x, r, p, Ap, b, (int)n, c, tol, partial, state);

@@ -2,7 +2,8 @@
 //
 // Replaces the sparse assembly of weightmatrix.knn (reference graphlearning/weightmatrix.py:166-186):
 //     W = coo_matrix((weights, (self_ind, knn_ind))).tocsr()      # duplicates summed, columns ascending
-//     W = (W + W.transpose()) / 2                                 # symmetrize (gaussian / user kernels)
+//     W = (W + W.transpose()) / 2                                 # symmetrize (gaussian / user kernels; sparse_max and the
+//                                                                 # symgaussian rule for the other kernels, :176-181)
 //     W.setdiag(0); W.eliminate_zeros()
 // - 0.18 s of scipy COO/CSC conversions at n = 70 000, k = 10, four times the GPU kNN search that feeds it.
 // The kernel weights themselves (exp(-4 d^2 / d_k^2) etc.) stay numpy on the host so that they are bit-identical to
@@ -30,29 +31,41 @@ kg_keys_kernel(const long long *__restrict__ ind, const double *__restrict__ w, 
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
         const long long i = e / k, j = ind[e];
         if (j < 0 || j >= n) { atomicOr(bad, 1); continue; }
-        keys[e] = ((u64)i << 32) | (u64)j;
+        keys[e] = ((u64)i << 32) | ((u64)j << 1);                 // lowest bit: 0 = entry of W, 1 = entry of W^T
         vals[e] = w[e];
         if (symmetrize) {
-            keys[total + e] = ((u64)j << 32) | (u64)i;
+            keys[total + e] = ((u64)j << 32) | ((u64)i << 1) | 1ull;
             vals[total + e] = w[e];
         }
     }
 }
 
-// head of a run of equal keys: value of the output entry, keep flag
+// head of a run of equal (row, column): value of the output entry, keep flag.  Inside a run the entries of W come before
+// those of W^T (origin bit), each group in its original order (stable sort): a = W_ij, b = W^T_ij with duplicates summed
+// as scipy's COO -> CSR conversion sums them, then the reference's rule (weightmatrix.py:176-183):
+//   mode 1  (a + b) / 2                                    gaussian and user kernels
+//   mode 2  max(a, b)                                      utils.sparse_max: 'distance', 'uniform', 'singular'
+//   mode 3  b > a ? (a + b) - a : a                        'symgaussian': W + W^T.multiply(W^T > W) - W.multiply(W^T > W)
 __global__ void __launch_bounds__(256)
-kg_runs_kernel(const u64 *__restrict__ keys, const double *__restrict__ vals, long long m, int symmetrize,
+kg_runs_kernel(const u64 *__restrict__ keys, const double *__restrict__ vals, long long m, int mode,
                double *__restrict__ run_val, int *__restrict__ keep)
 {
     for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < m; p += (long long)gridDim.x * blockDim.x) {
-        const u64 key = keys[p];
+        const u64 key = keys[p] >> 1;
         int kp = 0;
         double s = 0.0;
-        if (p == 0 || keys[p - 1] != key) {
-            s = vals[p];
-            for (long long q = p + 1; q < m && keys[q] == key; ++q) s += vals[q];      // at most two entries unless the kNN list repeats a column
-            if (symmetrize) s = s / 2;
-            kp = ((unsigned)(key >> 32) != (unsigned)key) && (s != 0.0);               // setdiag(0) + eliminate_zeros
+        if (p == 0 || (keys[p - 1] >> 1) != key) {
+            double a = 0.0, b = 0.0;
+            bool has_a = false, has_b = false;
+            for (long long q = p; q < m && (keys[q] >> 1) == key; ++q) {               // at most two entries unless the kNN list repeats a column
+                if (keys[q] & 1ull) { b = has_b ? b + vals[q] : vals[q]; has_b = true; }
+                else { a = has_a ? a + vals[q] : vals[q]; has_a = true; }
+            }
+            if (mode == 0) s = a;
+            else if (mode == 1) s = (has_a && has_b ? a + b : (has_a ? a : b)) / 2;
+            else if (mode == 2) s = b > a ? b : a;
+            else s = b > a ? __dsub_rn(__dadd_rn(a, b), a) : a;
+            kp = ((unsigned)(key >> 31) != (unsigned)(key & 0x7fffffffull)) && (s != 0.0);   // setdiag(0) + eliminate_zeros
         }
         run_val[p] = s;
         keep[p] = kp;
@@ -67,7 +80,7 @@ kg_scatter_kernel(const u64 *__restrict__ keys, const double *__restrict__ run_v
         if (!keep[p]) continue;
         const int o = pos[p];
         out_keys[o] = keys[p];
-        col[o] = (int)(unsigned)keys[p];
+        col[o] = (int)((unsigned)keys[p] >> 1);
         val[o] = run_val[p];
     }
 }
@@ -117,6 +130,7 @@ extern "C" GLB_API int glb_knn_weights_csr_host(const int64_t *h_ind, const doub
 {
     GLB_CHECK_ARG(h_ind && h_w && h_rowptr && h_col && h_val && nnz_out, "null pointer");
     GLB_CHECK_ARG(n > 0 && n < (1ll << 31) && k > 0 && n * (long long)k * 2 < (1ll << 31), "size out of range");
+    GLB_CHECK_ARG(symmetrize >= 0 && symmetrize <= 3, "symmetrize: 0 none, 1 average, 2 max, 3 symgaussian");
     const long long m = n * (long long)k * (symmetrize ? 2 : 1);
     GLB_CHECK_ARG(cap >= m, "output capacity must be at least n*k (2*n*k when symmetrizing)");
     int ndev = 0;

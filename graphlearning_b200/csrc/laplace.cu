@@ -255,7 +255,7 @@ extern "C" GLB_API int glb_laplacian_csr_host(const int32_t *h_rowptr, const int
 extern "C" GLB_API int glb_laplace_fit_host(const int32_t *h_rowptr, const int32_t *h_col, const double *h_val, int64_t n,
                                             int64_t nnz, const double *h_left, const double *h_right, const double *h_diag,
                                             const double *h_tau, const int64_t *h_train_ind, int64_t m, const double *h_F, int c,
-                                            double tol, double *h_u, int64_t *iters, double *err, int *launches)
+                                            double tol, double *h_u, int64_t *iters, double *err, int *launches, double *h_ms)
 {
     GLB_CHECK_ARG(h_rowptr && (nnz == 0 || (h_col && h_val)) && h_diag && h_train_ind && h_F && h_u, "null pointer");
     GLB_CHECK_ARG(n > 0 && nnz >= 0 && n + nnz < (1ll << 31), "size out of range");
@@ -304,7 +304,20 @@ extern "C" GLB_API int glb_laplace_fit_host(const int32_t *h_rowptr, const int32
     tm.lap("upload + system assembly");
     int64_t it = 0;
     double e = 0.0;
-    if ((rc = glb_cg_solve(a_rp, a_col, a_val, nu, a_nnz, Mb, nullptr, c, tol, 100000, x, work, wb, &it, &e, &nl, st))) return rc;
+    cudaEvent_t ev0, ev1;
+    cudaEventCreate(&ev0); cudaEventCreate(&ev1);
+    cudaEventRecord(ev0, st);
+    rc = glb_cg_solve(a_rp, a_col, a_val, nu, a_nnz, Mb, nullptr, c, tol, 100000, x, work, wb, &it, &e, &nl, st);
+    cudaEventRecord(ev1, st);
+    if (rc == 0 && cudaEventSynchronize(ev1) == cudaSuccess && h_ms) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ev0, ev1);
+        h_ms[0] = (double)ms;                                 // device time of the CG iterations
+        h_ms[1] = (double)a_nnz;                              // stored entries of the system matrix
+        h_ms[2] = (double)nu;                                 // unknowns
+    }
+    cudaEventDestroy(ev0); cudaEventDestroy(ev1);
+    if (rc) return rc;
     sys_scatter_kernel<<<sm_count() * 8, 256, 0, st>>>(lab, pos, M, x, ldb, F, c, (int)n, u); ++nl;
     GLB_LAUNCH_CHECK();
     GLB_CUDA(cudaMemcpyAsync(h_u, u, (size_t)n * c * sizeof(double), cudaMemcpyDeviceToHost, st));

@@ -125,9 +125,111 @@ __global__ void __launch_bounds__(256) max_abs_diff_kernel(const double *__restr
     if ((threadIdx.x & 31) == 0) atomicMax(out, (unsigned long long)__double_as_longlong(worst));
 }
 
+// One step of the centred-kernel fixed point (ssl.centered_kernel._fit, graphlearning/ssl.py:1409-1413):
+//     w = (1/alpha) (y - 1 mean_y^T) - u;  w[train] = 0;  err = max |w|;  u = u + w
+__global__ void __launch_bounds__(256)
+centered_step_kernel(const double *__restrict__ y, int ldy, const double *__restrict__ mean_y, double inv_alpha, double *__restrict__ u, int ldu,
+                     const unsigned char *__restrict__ labelled, long long n, int c, unsigned long long *__restrict__ err_bits)
+{
+    double worst = 0.0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n * c; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / c;
+        const int j = (int)(i - r * c);
+        const double uo = u[r * ldu + j];
+        double w = __dsub_rn(__dmul_rn(inv_alpha, __dsub_rn(y[r * ldy + j], mean_y[j])), uo);
+        if (labelled[r]) w = 0.0;
+        const double a = fabs(w);
+        worst = (a > worst || a != a) ? a : worst;
+        u[r * ldu + j] = __dadd_rn(uo, w);
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+        const double o = __shfl_xor_sync(0xffffffffu, worst, off);
+        worst = (__double_as_longlong(o) > __double_as_longlong(worst)) ? o : worst;
+    }
+    if ((threadIdx.x & 31) == 0) atomicMax(err_bits, (unsigned long long)__double_as_longlong(worst));
+}
+
+// out = min over the n x c entries, for non-negative matrices (bit patterns order like the values): the `np.min(F) == 0`
+// test of the grow loop of clustering.incres (graphlearning/clustering.py:357)
+__global__ void __launch_bounds__(256)
+min_nonneg_kernel(const double *__restrict__ x, long long n, int c, int ld, unsigned long long *__restrict__ out)
+{
+    unsigned long long best = ~0ull;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n * c; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / c;
+        const unsigned long long b = (unsigned long long)__double_as_longlong(fabs(x[r * ld + (i - r * c)]));
+        best = b < best ? b : best;
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+        const unsigned long long o = __shfl_xor_sync(0xffffffffu, best, off);
+        best = o < best ? o : best;
+    }
+    if ((threadIdx.x & 31) == 0) atomicMin(out, best);
+}
+
+// labels[i] = first column holding the row maximum (np.argmax(F, axis=1), clustering.py:361)
+__global__ void __launch_bounds__(256)
+argmax_rows_kernel(const double *__restrict__ x, long long n, int c, int ld, long long *__restrict__ labels)
+{
+    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (long long)gridDim.x * blockDim.x) {
+        const double *row = x + r * ld;
+        int best = 0;
+        double bv = row[0];
+        bool nan = bv != bv;                          // numpy: the first NaN wins
+        for (int j = 1; j < c && !nan; ++j) {
+            const double v = row[j];
+            if (v != v) { best = j; nan = true; }
+            else if (v > bv) { bv = v; best = j; }
+        }
+        labels[r] = best;
+    }
+}
+
 }  // namespace glb
 
 using namespace glb;
+
+extern "C" GLB_API int glb_centered_step_f64(const double *d_y, int ldy, const double *d_mean_y, double inv_alpha, double *d_u, int ldu,
+                                             const unsigned char *d_labelled, int64_t n, int c, double *h_err, void *stream)
+{
+    GLB_CHECK_ARG(d_y && d_mean_y && d_u && d_labelled && h_err && n > 0 && c > 0 && ldy >= c && ldu >= c, "bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    static thread_local unsigned long long *d_out = nullptr;
+    if (!d_out) GLB_CUDA(dev_alloc(&d_out, sizeof(unsigned long long)));
+    GLB_CUDA(cudaMemsetAsync(d_out, 0, sizeof(unsigned long long), st));
+    const int blocks = (int)std::min<int64_t>((n * c + 255) / 256, (int64_t)sm_count() * 8);
+    centered_step_kernel<<<blocks, 256, 0, st>>>(d_y, ldy, d_mean_y, inv_alpha, d_u, ldu, d_labelled, n, c, d_out);
+    unsigned long long bits = 0;
+    GLB_CUDA(cudaMemcpyAsync(&bits, d_out, sizeof(bits), cudaMemcpyDeviceToHost, st));
+    GLB_CUDA(cudaStreamSynchronize(st));
+    memcpy(h_err, &bits, sizeof(double));
+    return 0;
+}
+
+extern "C" GLB_API int glb_min_nonneg_f64(const double *d_x, int64_t n, int c, int ld, double *h_out, void *stream)
+{
+    GLB_CHECK_ARG(d_x && h_out && n > 0 && c > 0 && ld >= c, "bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    static thread_local unsigned long long *d_out = nullptr;
+    if (!d_out) GLB_CUDA(dev_alloc(&d_out, sizeof(unsigned long long)));
+    GLB_CUDA(cudaMemsetAsync(d_out, 0xff, sizeof(unsigned long long), st));
+    const int blocks = (int)std::min<int64_t>((n * c + 255) / 256, (int64_t)sm_count() * 8);
+    min_nonneg_kernel<<<blocks, 256, 0, st>>>(d_x, n, c, ld, d_out);
+    unsigned long long bits = 0;
+    GLB_CUDA(cudaMemcpyAsync(&bits, d_out, sizeof(bits), cudaMemcpyDeviceToHost, st));
+    GLB_CUDA(cudaStreamSynchronize(st));
+    memcpy(h_out, &bits, sizeof(double));
+    return 0;
+}
+
+extern "C" GLB_API int glb_argmax_rows_f64(const double *d_x, int64_t n, int c, int ld, int64_t *d_labels, void *stream)
+{
+    GLB_CHECK_ARG(d_x && d_labels && n > 0 && c > 0 && ld >= c, "bad argument");
+    const int blocks = (int)std::min<int64_t>((n + 255) / 256, (int64_t)sm_count() * 16);
+    argmax_rows_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(d_x, n, c, ld, (long long *)d_labels);
+    GLB_LAUNCH_CHECK();
+    return 0;
+}
 
 extern "C" GLB_API int glb_volume_projection(const double *d_prob, int64_t n, int k, int ld, const double *d_priors, int similarity,
                                              int max_rounds, double tol, double *d_weights, int64_t *d_labels, double *d_err, int *d_rounds,

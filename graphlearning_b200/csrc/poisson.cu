@@ -678,6 +678,43 @@ mixing_step_kernel(const int *__restrict__ rowptr, const int *__restrict__ col, 
     block_max_to_global(worst, err_out);
 }
 
+// The same recurrence, `steps` steps in ONE cooperative launch: a grid barrier between steps instead of a kernel boundary
+// (a step is 0.56 MB of gathers at 70k nodes - a launch per step costs more than the step).  Same per-row arithmetic in the
+// same order as mixing_step_kernel (bit-identical v), v ping-pongs between v0 (even steps read it) and v1; err_out[s] = max
+// |v_{s+1} - vinf|.  v is read with ld.global.cg: L1 may hold the lines of two steps ago.
+__global__ void __launch_bounds__(512, 1)
+mixing_persistent_kernel(const int *__restrict__ rowptr, const int *__restrict__ col, const double *__restrict__ val,
+                         const double *__restrict__ vinf, double *v0, double *v1, int n, int steps, unsigned long long *err_out,
+                         unsigned *sync_words)
+{
+    constexpr int G = 8;
+    const int lane = threadIdx.x & 31;
+    const int gl = lane % G;
+    const long long gid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const long long ngroups = ((long long)gridDim.x * blockDim.x) / G;
+    for (int st = 0; st < steps; ++st) {
+        const double *v_in = (st & 1) ? v1 : v0;
+        double *v_out = (st & 1) ? v0 : v1;
+        double worst = 0.0;
+        for (long long rb = 0; rb < n; rb += ngroups) {
+            const long long row = rb + gid;
+            double s = 0.0;
+            if (row < n) {
+                const int beg = rowptr[row], end = rowptr[row + 1];
+                for (int j = beg + gl; j < end; j += G) s += val[j] * __ldcg(v_in + col[j]);
+            }
+            for (int off = G / 2; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off, G);
+            if (row < n && gl == 0) {
+                v_out[row] = s;
+                const double d = fabs(s - vinf[row]);
+                worst = (d > worst || d != d) ? d : worst;
+            }
+        }
+        block_max_to_global(worst, err_out + st);
+        if (st + 1 < steps) grid_barrier<false>(sync_words, (unsigned)(st + 1));
+    }
+}
+
 __global__ void __launch_bounds__(256)
 maxdiff_kernel(const double *__restrict__ v, const double *__restrict__ vinf, int n, unsigned long long *err_out)
 {
@@ -1510,6 +1547,19 @@ extern "C" GLB_API int glb_poisson_mixing_T(const int32_t *d_rw_rowptr, const in
     const int BATCH = 64;
     unsigned long long *d_err = nullptr;
     GLB_CUDA(dev_alloc(&d_err, sizeof(unsigned long long) * (BATCH + 1)));
+    // one cooperative launch per batch when the device supports it (grid = resident CTAs of 512 threads, at most one per SM)
+    int dev = 0, coop = 0, coop_grid = 0;
+    unsigned *d_sync = nullptr;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+    if (coop) {
+        int per_sm = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mixing_persistent_kernel, 512, 0);
+        coop_grid = per_sm >= 1 ? sm_count() : 0;
+        if (coop_grid > (int)((n * 8 + 511) / 512)) coop_grid = (int)((n * 8 + 511) / 512);
+        if (coop_grid < 1) coop = 0;
+        if (coop && dev_alloc(&d_sync, sizeof(unsigned)) != cudaSuccess) { cudaGetLastError(); coop = 0; }
+    }
     unsigned long long h_err[BATCH + 1];
     const double thr = 1.0 / (double)n;
     const int threads = 256;
@@ -1532,12 +1582,23 @@ extern "C" GLB_API int glb_poisson_mixing_T(const int32_t *d_rw_rowptr, const in
         int steps = max_iter - T;
         if (steps > BATCH) steps = BATCH;
         cudaMemsetAsync(d_err, 0, sizeof(unsigned long long) * (BATCH + 1), st);
-        for (int s = 0; s < steps; ++s) {
-            mixing_step_kernel<<<blocks, threads, 0, st>>>(d_rw_rowptr, d_rw_col, d_rw_val, d_vinf, cur, nxt, (int)n,
-                                                           d_err + s);
-            double *t = cur; cur = nxt; nxt = t;
+        if (coop) {
+            cudaMemsetAsync(d_sync, 0, sizeof(unsigned), st);
+            int ni = (int)n;
+            void *args[] = {(void *)&d_rw_rowptr, (void *)&d_rw_col, (void *)&d_rw_val, (void *)&d_vinf, (void *)&cur, (void *)&nxt,
+                            (void *)&ni, (void *)&steps, (void *)&d_err, (void *)&d_sync};
+            cudaError_t le = cudaLaunchCooperativeKernel((const void *)mixing_persistent_kernel, dim3(coop_grid), dim3(512), args, 0, st);
+            if (le != cudaSuccess) { rc = (int)le; set_error("glb_poisson_mixing_T: %s", cudaGetErrorString(le)); break; }
+            if (steps & 1) { double *t = cur; cur = nxt; nxt = t; }
+            if (launches) *launches += 1;
+        } else {
+            for (int s = 0; s < steps; ++s) {
+                mixing_step_kernel<<<blocks, threads, 0, st>>>(d_rw_rowptr, d_rw_col, d_rw_val, d_vinf, cur, nxt, (int)n,
+                                                               d_err + s);
+                double *t = cur; cur = nxt; nxt = t;
+            }
+            if (launches) *launches += steps;
         }
-        if (launches) *launches += steps;
         cudaError_t e = cudaMemcpyAsync(h_err, d_err, sizeof(unsigned long long) * steps, cudaMemcpyDeviceToHost, st);
         if (e == cudaSuccess) e = cudaStreamSynchronize(st);
         if (e != cudaSuccess) { rc = (int)e; set_error("glb_poisson_mixing_T: %s", cudaGetErrorString(e)); break; }
@@ -1548,6 +1609,7 @@ extern "C" GLB_API int glb_poisson_mixing_T(const int32_t *d_rw_rowptr, const in
         }
     }
     dev_free(d_err);
+    dev_free(d_sync);
     if (rc == 0) {
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) { rc = (int)e; set_error("glb_poisson_mixing_T: %s", cudaGetErrorString(e)); }

@@ -24,9 +24,9 @@ namespace {
 template <int CP, int UN>
 __global__ void __launch_bounds__(256)
 spmm_f64_kernel(const int *__restrict__ rowptr, const int *__restrict__ col, const double *__restrict__ val, long long n,
-                const double *__restrict__ X, int ldx, double *__restrict__ Z, int ldz, int c, double alpha,
-                const double *__restrict__ Y1, int ldy1, double beta, const double *__restrict__ bcol,
-                const double *__restrict__ Y2, int ldy2, double gamma)
+                const double *__restrict__ X, int ldx, double *Z, int ldz, int c, double alpha,
+                const double *Y1, int ldy1, double beta, const double *__restrict__ bcol,
+                const double *Y2, int ldy2, double gamma)      // Z may alias Y1 / Y2 (in-place recurrences): no __restrict__ on those
 {
     const int lane = threadIdx.x & 31;
     const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;

@@ -308,6 +308,14 @@ class graph:
             u, s, vt, info = spectral.randomized_svd(A, k=k, c=c, q=q, return_info=True)
         self.gpu_launches = info["launches"]
         self.eigen_info = info
+        if not info.get("converged", True):
+            msg = ("eigen_decomp: the block solver stopped at a residual of %.2e (wanted %.2e) after %d outer iterations"
+                   % (info["residual"], info["rtol"], info["outer"] + 1))
+            if not info.get("stagnated", False):
+                # ARPACK raises ArpackNoConvergence at this point (the reference's svds call, graph.py:734); nothing is cached
+                raise RuntimeError(msg)
+            import warnings
+            warnings.warn(msg + " (stagnation at the rounding floor, residual below 1e-9)", RuntimeWarning)
         vals = shift - s
         ind = np.argsort(vals)
         vals = vals[ind]

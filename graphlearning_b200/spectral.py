@@ -171,10 +171,11 @@ def svd_topk(A, k, tol=0.0, guard=None, degree=None, max_outer=200, seed=0, retu
         rn = np.sqrt(np.maximum(np.diag(ops.gram(R, nb, R, nb)), 0.0))
         info["spmm"] += 2
         res = float(np.max(rn[:k]) / max(w[0], 1e-300))
-        info.update(outer=outer, residual=res)
+        info.update(outer=outer, residual=res, converged=bool(res <= rtol), rtol=rtol)
         if res <= rtol:
             break
         if outer > 12 and res > 0.5 * best and res < 1e-9:                 # stagnation at the rounding floor
+            info["stagnated"] = True
             break
         best = min(best, res)
         # Chebyshev filter: damp [0, b], amplify above; scaled three-term recurrence (Zhou & Saad)

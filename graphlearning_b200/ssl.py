@@ -368,11 +368,13 @@ class laplace(ssl):
         ti = np.ascontiguousarray(np.where(train_ind < 0, train_ind + n, train_ind), dtype=np.int64)
         u = np.empty((n, F.shape[1]), dtype=np.float64)
         it, err, nl = ctypes.c_int64(0), ctypes.c_double(0.0), ctypes.c_int(0)
+        ms = np.zeros(3)
         vp = lambda a: ctypes.c_void_p(a.ctypes.data) if a is not None else None
         _lib.call("glb_laplace_fit_host", vp(rp), vp(ci), vp(val), n, W.nnz, vp(left), vp(right), vp(diag), vp(tau), vp(ti),
-                  len(ti), vp(F), F.shape[1], float(self.tol), vp(u), ctypes.byref(it), ctypes.byref(err), ctypes.byref(nl))
+                  len(ti), vp(F), F.shape[1], float(self.tol), vp(u), ctypes.byref(it), ctypes.byref(err), ctypes.byref(nl), vp(ms))
         self.iterations = it.value
         self.gpu_launches = nl.value
+        self.cg_info = {"device_ms": float(ms[0]), "system_nnz": int(ms[1]), "unknowns": int(ms[2])}
         return u
 
 
@@ -454,6 +456,97 @@ class randomwalk(ssl):
         u, (it, err, nl) = utils.conjgrad(M * L * M, M * Y, tol=1e-6, return_info=True)
         self.iterations, self.gpu_launches = it, nl
         return M * u
+
+
+class centered_kernel(ssl):
+    """Centered kernel method of Mai & Couillet.  Reference graphlearning/ssl.py:1345-1424: a power iteration for the largest
+    eigenvalue of the doubly centred weight matrix A = H W H (H = I - 11^T / n), then the fixed point
+    u <- (1/alpha) A u with the labelled rows held fixed, until max |change| <= tol.  A is never formed: with d = W 1 and
+    s = 1^T x, H W H x = y - 1 mean(y)^T, y = W x - d s^T / n, i.e. one fp64 block SpMM with the rank-one term fused into
+    its epilogue (spectral.cu), one column-sum reduction and one fused update kernel (mbo.cu) per iteration; the label
+    matrix stays in HBM.  The start vector comes from numpy's global stream exactly as in the reference (:1399)."""
+
+    def __init__(self, W=None, class_priors=None, tol=1e-10, power_it=100, alpha=1.05):
+        super().__init__(W, class_priors)
+        self.tol = tol
+        self.power_it = power_it
+        self.alpha = alpha
+        self.accuracy_filename = "_centered_kernel"
+        self.name = "Centered Kernel"
+        self.iterations = None
+        self.gpu_launches = 0
+
+    def _fit(self, train_ind, train_labels, all_labels=None):
+        from . import device, spectral
+        torch = device._torch()
+        n = self.graph.num_nodes
+        k = len(np.unique(train_labels))
+        W = self.graph.weight_matrix
+        W = sparse.csr_matrix(W - sparse.spdiags(W.diagonal(), 0, n, n))               # :1385-1386
+        onehot = utils.labels_to_onehot(train_labels, k)
+        kk = onehot.shape[1]
+        K = np.zeros((n, kk))
+        K[train_ind] = onehot
+        K[train_ind, :] -= np.sum(K, axis=0) / len(train_ind)                           # :1389-1393
+        ops = spectral.BlockOps(W)
+        d = W * np.ones(n)
+        ones = ops.upload(np.ones((n, 1)))
+        nl = 0
+
+        def centred_product(x, c, dcols, y):
+            """y = W (x - 1 mean(x)^T) = W x - d s^T / n  and the column means of y"""
+            nonlocal nl
+            s = ops.gram(ones, 1, x, c)[0]
+            ops.spmm(x, c, out=y, Y1=dcols, beta=1.0, bcol=-(1 / n) * s)
+            t = ops.gram(ones, 1, y, c)[0]
+            nl += 5
+            return (1 / n) * t
+
+        # largest eigenvalue of A by power iteration (:1399-1404)
+        e = ops.upload(np.random.rand(n, 1))
+        e2 = ops.new(1)
+        d1 = ops.upload(d[:, None])
+        y = ops.new(1)
+        lam = 0.0
+        for _ in range(self.power_it):
+            m = centred_product(e, 1, d1, y)
+            ee = ops.gram(e, 1, e, 1)[0, 0]
+            # w = y - mean(y);  e^T w = e^T y - mean(y) sum(e);  |w|^2 = y^T y - n mean(y)^2
+            ey = ops.gram(e, 1, y, 1)[0, 0]
+            se = ops.gram(ones, 1, e, 1)[0, 0]
+            yy = ops.gram(y, 1, y, 1)[0, 0]
+            lam = abs((ey - m[0] * se) / ee)
+            wn = np.sqrt(max(yy - n * m[0] * m[0], 0.0))
+            # e = (y - mean(y)) / |w|   (the epilogue of the block kernel as a linear combination: alpha = 0)
+            ops.spmm(e, 1, out=e2, alpha=0.0, Y1=y, beta=1.0 / wn, Y2=ones, gamma=-m[0] / wn)
+            e, e2 = e2, e
+            nl += 9
+        # fixed point (:1407-1413)
+        alpha = self.alpha * lam
+        u = ops.upload(K)
+        yk = ops.new(kk)
+        dk = ops.upload(np.repeat(d[:, None], kk, axis=1))
+        mask = np.zeros(n, dtype=np.uint8)
+        mask[train_ind] = 1
+        mask_d = torch.from_numpy(mask).cuda()
+        mean_d = torch.empty(kk, dtype=torch.float64, device="cuda")
+        err, it = 1.0, 0
+        e_host = ctypes.c_double(0.0)
+        while err > self.tol:
+            m = centred_product(u, kk, dk, yk)
+            mean_d.copy_(torch.from_numpy(np.ascontiguousarray(m)))
+            _lib.call("glb_centered_step_f64", device.ptr(yk), int(yk.shape[1]), device.ptr(mean_d), float(1 / alpha), device.ptr(u),
+                      int(u.shape[1]), device.ptr(mask_d), n, kk, ctypes.byref(e_host), device.cur_stream())
+            err = e_host.value
+            it += 1
+            nl += 1
+            if all_labels is not None:
+                self.prob = u[:, :kk].cpu().numpy()
+                print("%d,Accuracy = %.2f" % (it, ssl_accuracy(self.predict(), all_labels, train_ind)))
+        self.iterations = it
+        self.eigenvalue = lam
+        self.gpu_launches = nl
+        return u[:, :kk].cpu().numpy()
 
 
 def ssl_accuracy(pred_labels, true_labels, train_ind):

@@ -23,7 +23,8 @@ _device_assembly_min_n = 2048
 
 
 def _assemble_on_device(knn_ind, weights, n, k, symmetrize):
-    """weightmatrix.py:166-186 for the gaussian / user kernels through glb_knn_weights_csr_host (knn_graph.cu)."""
+    """weightmatrix.py:166-186 through glb_knn_weights_csr_host (knn_graph.cu).  symmetrize: 0 none, 1 average,
+    2 sparse_max, 3 the symgaussian rule."""
     import ctypes
     from . import _lib
     ind = np.ascontiguousarray(knn_ind, dtype=np.int64)
@@ -34,7 +35,7 @@ def _assemble_on_device(knn_ind, weights, n, k, symmetrize):
     val = np.empty(cap, dtype=np.float64)
     nnz, nl = ctypes.c_int64(0), ctypes.c_int(0)
     p = lambda a: ctypes.c_void_p(a.ctypes.data)
-    _lib.call("glb_knn_weights_csr_host", p(ind), p(w), int(n), int(k), 1 if symmetrize else 0, p(rp), p(col), p(val), int(cap),
+    _lib.call("glb_knn_weights_csr_host", p(ind), p(w), int(n), int(k), int(symmetrize), p(rp), p(col), p(val), int(cap),
               ctypes.byref(nnz), ctypes.byref(nl))
     m = nnz.value
     return sparse.csr_matrix((val[:m].copy(), col[:m].copy(), rp), shape=(n, n))
@@ -119,9 +120,11 @@ def knn(data, k, kernel="gaussian", eta=None, symmetrize=True, metric="raw", sim
         D = knn_dist * knn_dist
         eps = D[:, k - 1]
         weights = eta(D / eps)
-    if (eta is not None or kernel == "gaussian") and n >= _device_assembly_min_n:
-        # COO -> CSR, (W + W^T)/2, zero diagonal: on the device, bit-identical to the scipy expressions below
-        return _assemble_on_device(knn_ind, weights, n, k, symmetrize)
+    if n >= _device_assembly_min_n:
+        # COO -> CSR, symmetrisation by the kernel's rule (also when eta is given, as in the reference), zero diagonal:
+        # on the device, bit-identical to the scipy expressions below
+        rule = 2 if kernel in ["distance", "uniform", "singular"] else 3 if kernel == "symgaussian" else 1
+        return _assemble_on_device(knn_ind, weights, n, k, rule if symmetrize else 0)
     knn_ind = knn_ind.flatten()
     weights = weights.flatten()
     self_ind = (np.ones((n, k)) * np.arange(n)[:, None]).flatten()

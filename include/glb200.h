@@ -240,7 +240,8 @@ GLB_API int glb_poisson_gd_host(const int32_t *h_rowptr, const int32_t *h_col, c
  * tau + L above, restricted to the unlabelled nodes and Jacobi scaled (M A M, M b with M = diag(A)^-1/2, b = -L[:, train] F),
  * is assembled in HBM, solved by glb_cg_solve (tol, at most 1e5 iterations, as utils.conjgrad) and scattered back:
  * h_u (n x c) = M v on the unlabelled nodes, F on the labelled ones.  h_tau: n values or NULL; h_train_ind: m distinct
- * nodes in [0, n); h_F: m x c one-hot labels (utils.labels_to_onehot).  iters / err / launches may be NULL.
+ * nodes in [0, n); h_F: m x c one-hot labels (utils.labels_to_onehot).  iters / err / launches / h_ms may be NULL;
+ * h_ms[3] = {device milliseconds of the CG iterations (CUDA events), stored entries of the system matrix, unknowns}.
  * ------------------------------------------------------------------------------------------- */
 GLB_API int glb_laplacian_csr_host(const int32_t *h_rowptr, const int32_t *h_col, const double *h_val, int64_t n, int64_t nnz,
                                    const double *h_left, const double *h_right, const double *h_diag, int32_t *h_out_rowptr,
@@ -248,7 +249,7 @@ GLB_API int glb_laplacian_csr_host(const int32_t *h_rowptr, const int32_t *h_col
 GLB_API int glb_laplace_fit_host(const int32_t *h_rowptr, const int32_t *h_col, const double *h_val, int64_t n, int64_t nnz,
                                  const double *h_left, const double *h_right, const double *h_diag, const double *h_tau,
                                  const int64_t *h_train_ind, int64_t m, const double *h_F, int c, double tol, double *h_u,
-                                 int64_t *iters, double *err, int *launches);
+                                 int64_t *iters, double *err, int *launches, double *h_ms);
 
 /* ---------------------------------------------------------------------------------------------
  * Conjugate gradient with c right-hand sides.  Replaces utils.conjgrad (graphlearning/utils.py:483-532):
@@ -361,11 +362,23 @@ GLB_API int glb_volume_projection(const double *d_prob, int64_t n, int k, int ld
                                   void *stream);
 GLB_API int glb_onehot_f64(const int64_t *d_labels, int64_t n, int k, int ld, double *d_dst, void *stream);
 GLB_API int glb_max_abs_diff_f64(const double *d_x, const double *d_y, int64_t n, int c, int ldx, int ldy, double *h_out, void *stream);
+/* glb_centered_step_f64: one step of the fixed point of ssl.centered_kernel._fit (graphlearning/ssl.py:1409-1413) on
+ *   device label matrices: w = inv_alpha (y - 1 mean_y^T) - u, w[labelled] = 0, *h_err = max |w|, u += w.  d_mean_y: c
+ *   doubles, d_labelled: n bytes (non-zero = labelled node).  Synchronises the stream (host result).
+ * glb_min_nonneg_f64:    *h_out = min over the n x c entries of a non-negative matrix (the `np.min(F) == 0` test of the grow
+ *   loop of clustering.incres, graphlearning/clustering.py:357).  Synchronises the stream.
+ * glb_argmax_rows_f64:   labels[i] = first column of the row maximum (np.argmax(F, axis=1), clustering.py:361). */
+GLB_API int glb_centered_step_f64(const double *d_y, int ldy, const double *d_mean_y, double inv_alpha, double *d_u, int ldu,
+                                  const unsigned char *d_labelled, int64_t n, int c, double *h_err, void *stream);
+GLB_API int glb_min_nonneg_f64(const double *d_x, int64_t n, int c, int ld, double *h_out, void *stream);
+GLB_API int glb_argmax_rows_f64(const double *d_x, int64_t n, int c, int ld, int64_t *d_labels, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * kNN result -> CSR weight matrix.  Replaces the sparse assembly of weightmatrix.knn
  * (graphlearning/weightmatrix.py:166-186): coo_matrix((weights, (self_ind, knn_ind))).tocsr(), the symmetrisation
- * (W + W^T) / 2 of the gaussian / user kernels (:183), setdiag(0) and eliminate_zeros() (:185-186).
+ * (:176-183), setdiag(0) and eliminate_zeros() (:185-186).  symmetrize: 0 = none, 1 = (W + W^T) / 2 (gaussian and
+ * user kernels), 2 = utils.sparse_max(W, W^T) ('distance', 'uniform', 'singular'; graphlearning/utils.py:263-286),
+ * 3 = W + W^T.multiply(W^T > W) - W.multiply(W^T > W) ('symgaussian').
  * ind: n x k int64 neighbour indices (row i = neighbours of i, self included), w: n x k float64 kernel weights
  * (computed by the caller exactly as the reference does, :139-164).  Output: canonical CSR (int32 rowptr[n+1],
  * int32 col, float64 val, columns ascending), bit-identical to scipy's.  cap = capacity of col / val in entries,

@@ -149,7 +149,8 @@ def test_clustering_scores():
     pred = np.array([1, 1, 0, 0, 2, 2, 2])
     true = np.array([5, 5, 7, 7, 9, 9, 7])
     assert abs(gl.clustering.clustering_accuracy(pred, true) - 100 * 6 / 7) < 1e-12
-    assert abs(gl.clustering.purity(pred, true) - 100 * 6 / 7) < 1e-12
+    overall, per_cluster = gl.clustering.purity(pred, true)                 # the reference returns both (clustering.py:550)
+    assert abs(overall - 100 * 6 / 7) < 1e-12 and len(per_cluster) == len(np.unique(pred)) and per_cluster.max() <= 1
     assert gl.clustering.clustering_accuracy(true, true) == 100.0
 
 

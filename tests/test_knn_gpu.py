@@ -130,7 +130,7 @@ def test_fused_tensor_core_search(kg, n, d, k, nrows):
 
 
 def test_weight_matrix_assembly_on_device_is_bit_identical(gl, moons, blobs, small, monkeypatch):
-    """weightmatrix.knn for the gaussian kernel: COO -> CSR, (W + W^T)/2, zero diagonal on the device (knn_graph.cu)
+    """weightmatrix.knn: COO -> CSR, symmetrisation by the kernel's rule, zero diagonal on the device (knn_graph.cu)
     against the goldens of the reference and against the scipy expressions (weightmatrix.py:166-186), bit for bit."""
     from scipy import sparse
     wm = gl.weightmatrix
@@ -157,5 +157,30 @@ def test_weight_matrix_assembly_on_device_is_bit_identical(gl, moons, blobs, sma
         monkeypatch.setattr(wm, "_device_assembly_min_n", 0)
         same(Wd, Wh)
     assert (Wd != Wd.T).nnz > 0                                      # the last one is the directed graph
+    # every other kernel: sparse_max for distance / uniform / singular, the symgaussian rule (weightmatrix.py:176-181),
+    # against the goldens of the reference and against the scipy path at full size; a user kernel `eta` keeps the rule of `kernel`
+    for kernel in ("uniform", "symgaussian", "distance", "singular"):
+        for sym in (True, False):
+            same(wm.knn(None, 7, kernel=kernel, symmetrize=sym, knn_data=(small["knn_ind"].astype(np.int64), small["knn_dist"])),
+                 small.csr("W_%s_%d" % (kernel, int(sym))))
+        Wd = wm.knn(None, 10, kernel=kernel, knn_data=(ind, dist))
+        monkeypatch.setattr(wm, "_device_assembly_min_n", 10 ** 9)
+        Wh = wm.knn(None, 10, kernel=kernel, knn_data=(ind, dist))
+        monkeypatch.setattr(wm, "_device_assembly_min_n", 0)
+        same(Wd, Wh)
+    # a repeated column inside a row (the COO conversion sums duplicates first), one-directional edges, an exact zero weight
+    dup_ind = np.array([[0, 1, 1], [1, 2, 0], [2, 0, 0], [3, 3, 1]])
+    dup_w = np.array([[0.0, 0.25, 0.5], [0.0, 0.3, 0.9], [0.0, 0.7, 0.0], [0.0, 0.0, 0.4]])
+    for rule, kernel in ((1, "gaussian"), (2, "uniform"), (3, "symgaussian")):
+        got = wm._assemble_on_device(dup_ind, dup_w, 4, 3, rule)
+        W0 = sparse.coo_matrix((dup_w.flatten(), (np.repeat(np.arange(4), 3), dup_ind.flatten())), shape=(4, 4)).tocsr()
+        if rule == 1:
+            want = (W0 + W0.T) / 2
+        elif rule == 2:
+            want = wm.sparse_max(W0, W0.transpose())
+        else:
+            want = W0 + W0.T.multiply(W0.T > W0) - W0.multiply(W0.T > W0)
+        want = sparse.csr_matrix(want); want.setdiag(0); want.eliminate_zeros()
+        same(got, want)
     with pytest.raises(Exception):
         wm.knn(None, 3, knn_data=(np.array([[0, 5, 1], [1, 0, 2], [2, 1, 0]]), np.ones((3, 3))))   # index out of range

@@ -117,4 +117,4 @@ def test_laplace_fit_rejects_bad_input(gl, moons):
     for ti in (np.array([0, 700], np.int64), np.array([-1, 3], np.int64)):
         with pytest.raises(_lib.GlbError):
             _lib.call("glb_laplace_fit_host", vp(rp), vp(ci), vp(v), 500, W.nnz, None, None, vp(d), None, vp(ti), 2, vp(F), 2, 1e-5,
-                      vp(u), None, None, None)
+                      vp(u), None, None, None, None)

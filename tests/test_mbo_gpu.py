@@ -61,3 +61,39 @@ def test_page_rank(gl, gold, blobs):
     u2 = G.page_rank(alpha=0.7, v=v, tol=1e-8)
     assert rel_err(u2, gold["pagerank_personalised"]) <= 1e-7
     assert G.gpu_launches > 0
+
+
+def test_centered_kernel_matches_reference_golden(gl, moons, blobs):
+    """ssl.centered_kernel (reference ssl.py:1345-1424): power iteration + fixed point on the device against the golden of
+    the reference, same numpy seed (the start vector of the power iteration is np.random.rand)."""
+    from conftest import Golden
+    f3 = Golden("f3")
+    for name, g, tkey in (("moons", moons, "train_ind"), ("blobs", blobs, "train_ind5")):
+        ti, labels = g[tkey], g["labels"]
+        np.random.seed(11)
+        m = gl.ssl.centered_kernel(g.csr("W"))
+        u = m.fit(ti, labels[ti])
+        ref = f3[name + "_ck_u"]
+        assert u.shape == ref.shape and m.iterations > 10 and m.gpu_launches > 0
+        assert float(np.abs(u - ref).max() / np.abs(ref).max()) <= 1e-7      # stopping tol 1e-10 on values of order 0.1
+        assert np.mean(m.predict() == f3[name + "_ck_pred"]) >= 0.998
+        assert m.accuracy_filename == "_centered_kernel"
+
+
+def test_incres_matches_reference_golden(gl, moons):
+    """clustering.incres (reference clustering.py:283-371): plant on the host with numpy's stream, grow + harvest on the
+    device.  The grown matrices are fp64 sums in CSR order like scipy's, so the harvested labels - and with them the
+    seeds of the next round - follow the reference; near-ties in the argmax may flip single nodes."""
+    from conftest import Golden
+    from scipy import sparse
+    f3 = Golden("f3")
+    np.random.seed(5)
+    got = gl.clustering.incres(moons.csr("W"), 2, T=30).fit_predict()
+    assert np.mean(got == f3["moons_incres"]) >= 0.99
+    W3 = sparse.csr_matrix((f3["clouds_W_data"], f3["clouds_W_indices"], f3["clouds_W_indptr"]), shape=(1500, 1500))
+    np.random.seed(7)
+    c = gl.clustering.incres(W3, 3, T=40)
+    got = c.fit_predict()
+    assert c.gpu_launches > 40
+    assert np.mean(got == f3["clouds_incres"]) >= 0.99
+    assert gl.clustering.clustering_accuracy(got, f3["clouds_labels"]) > 80
