@@ -51,9 +51,10 @@ def build_workload(seed=0):
 
 WORKLOAD = "cfg2 (synthetic, d=8): 70k points of 10 Gaussian blobs in R^8, k=10 kNN graph, 10 classes, 1 label/class"
 
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch (T = 100 iterations) of the dominant kernel, ncu --set full,
-# profiles/r2_dataflow_pipe_ncu_raw.csv
-NCU_DRAM_BYTES_PER_LAUNCH = {"dataflow": None, "barrier": 17295360 + 296704, "step": None}
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel, ncu --set full
+# (profiles/r2_dataflow_T1000_ncu_details.txt: 19.34 MB + 0.28 MB; profiles/r2_dataflow_pipe_gate1_ncu_details.txt, another
+# launch length: 19.67 MB + 0.35 MB - the traffic does not depend on the number of iterations of the launch)
+NCU_DRAM_BYTES_PER_LAUNCH = {"dataflow": 19336704 + 284672, "barrier": 17295360 + 296704, "step": None}
 
 
 def timed(fn, reps=1):
@@ -463,7 +464,7 @@ def run_ours(args, rank, world):
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD,
                    "n": int(n), "nnz": int(nnz), "classes": c, "iterations_per_step": iters, "ldu": ldu,
-                   "kernel": {"dataflow": "poisson_dataflow_pipe_kernel", "barrier": "poisson_persistent_kernel",
+                   "kernel": {"dataflow": "poisson_dataflow_kernel", "barrier": "poisson_persistent_kernel",
                               "step": "poisson_step_kernel"}[kind],
                    "gate_every": op.gate(c), "node_ordering": "reverse Cuthill-McKee (library, per graph)",
                    "l2": "flushed between steps (256 MiB write); inside a step the 16.8 MB working set is "
@@ -472,9 +473,10 @@ def run_ours(args, rank, world):
                                   "iterate of config 5 is `cfg5_rowpart`" % world},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get(kind), "peak_source": peak_src,
-                     "traffic_note": "dram__bytes_read+write of one launch from the ncu capture under profiles/ (T=100 "
-                                     "iterations per launch there; the traffic is the one-time load of slabs, Db and u - every "
-                                     "iteration after the first runs out of L2, which is why achieved > traffic/time)",
+                     "traffic_note": "dram__bytes_read+write of ONE launch (all iterations of a step) from the ncu --set full "
+                                     "capture under profiles/: the one-time load of slabs, Db and u - every iteration after the "
+                                     "first runs out of L2, so the DRAM traffic of a launch does not grow with its iteration count "
+                                     "(algorithmic bytes per launch = bytes_per_iteration x iterations_per_step)",
                      "bytes_per_iteration": algorithmic_bytes(n, nnz, c)},
         "cpu_baseline": {"value": cpu_iters / cpu_s, "unit": UNIT, "cores": 1, "kind": "port",
                          "sample": "%d iterations of the reference loop (ssl.py:667-669, scipy csr_matvecs fp64) on the "

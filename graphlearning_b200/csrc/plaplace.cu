@@ -239,20 +239,7 @@ struct LipArgs {
     int n, M, T, n_active;
     int use_crit;                   // poll the latest-level producer alone before gathering the whole row
     double tol, alpha, beta;
-    // pipelined kernel: ring of kRing version buffers (ring + v % kRing * n) and the sweep bookkeeping
-    Cell *ring;
-    unsigned long long *ctl;        // [0] sweeps fully completed ("checked"), [1] stop_at (kNoStop = none), [2..2+kCtlSlots) rows done per
-                                    // sweep, [2+kCtlSlots..2+2kCtlSlots) error bits per sweep
-    int n_rows;                     // unlabelled rows (= rows every sweep must complete)
-    // level-counter schedule of the barrier kernel (nullptr = off): level of every 32-position block of `order`, rows per
-    // level, and one cumulative "rows done" counter per level
-    const int *blk_level, *lvl_size;
-    unsigned long long *lvl_done;
 };
-
-constexpr int kRing = 4;                              // version buffers of the pipelined kernel
-constexpr int kCtlSlots = kRing + 2;
-constexpr unsigned long long kNoStop = ~0ull;
 
 constexpr unsigned long long kVerFixed = ~0ull;      // Dirichlet rows: valid in every sweep
 constexpr int kLipBatch = 16;                        // neighbour cells in flight per retry (most rows: one round trip)
@@ -284,19 +271,6 @@ __global__ void __launch_bounds__(256, 2) lip_gauss_seidel_kernel(LipArgs A)
             const int i = p0 + lane < A.n_active ? __ldg(A.order + p0 + lane) : -1;
             const bool active = i >= 0;
             bool pending = active;
-            // level counters: the rows of this warp (one level) may start once every row of the level below has published
-            // its value in this sweep - one poll per warp on one counter instead of one per neighbour cell
-            const int lev = A.blk_level ? __ldg(A.blk_level + (p0 >> 5)) : -1;
-            if (lev > 0) {
-                if (lane == 0) {
-                    const unsigned long long need = (unsigned long long)(it + 1) * (unsigned long long)__ldg(A.lvl_size + lev - 1);
-                    unsigned spins = 0;
-                    long long tw0 = 0;
-                    while (ld_relaxed_u64(A.lvl_done + lev - 1) < need && !wait_expired(A.counter + 1, spins, tw0)) { }
-                    fence_gpu();
-                }
-                __syncwarp();
-            }
             int s = 0, L = 0, k = 0, crit = -1;
             double uv[kLipCap], wv[kLipCap];
             double minu = 0.0, maxu = 0.0, sumu = 0.0, deg = 0.0, uold = 0.0;
@@ -388,11 +362,6 @@ __global__ void __launch_bounds__(256, 2) lip_gauss_seidel_kernel(LipArgs A)
             }
             // lockstep variant: the whole warp updates its rows together (one pass through the 30-step bisection)
             if (LOCKSTEP && active) update_row();
-            if (lev >= 0) {                                       // publish: this warp's rows of level `lev` are done
-                const int nrows = __popc(__ballot_sync(0xffffffffu, active));
-                __syncwarp();
-                if (lane == 0 && nrows) { fence_gpu(); atomicAdd(A.lvl_done + lev, (unsigned long long)nrows); }
-            }
         }
         const double gerr = barrier_max(err, A.slots, A.counter, (unsigned)it);
         if (gerr < A.tol && it > 20) { done = it + 1; break; }
@@ -401,199 +370,6 @@ __global__ void __launch_bounds__(256, 2) lip_gauss_seidel_kernel(LipArgs A)
     const Cell *fin = (nsweeps & 1) ? A.c1 : A.c0;      // sweep t writes buffer (t+1)&1
     for (int i = gt; i < A.n; i += NT) A.u_out[i] = ld_cell(fin + i).a;
     if (gt == 0) *A.sweeps = nsweeps;
-}
-
-// Gauss-Seidel sweeps WITHOUT a barrier between sweeps.  Version v of a row (its value after v sweeps) lives in ring buffer
-// v % kRing, stamped v.  Row i in sweep s needs version s+1 of its neighbours j < i and version s of its neighbours
-// j >= i - both are just cells to wait for, so sweeps overlap: an edge costs a sweep only when it is walked downwards, and
-// the steady-state rate is set by the worst up/down cycle of the graph, not by the depth of the whole dependency DAG.
-// Bookkeeping for the reference's stopping rule (err < tol && it > 20, evaluated per sweep): every warp adds its rows and
-// its error to the sweep's counters; the warp that completes a sweep publishes either `checked = s + 1` or `stop = s + 1`.
-// A sweep may start only when sweep s + 1 - kRing is complete (checked >= s + 2 - kRing): then nobody still reads the
-// versions it overwrites, and the versions of the stopping sweep are still intact when the stop is published.
-template <bool WEIGHTED, bool LOCKSTEP>
-__global__ void __launch_bounds__(256, 2) lip_pipelined_kernel(LipArgs A)
-{
-    const int NT = gridDim.x * blockDim.x, gt = blockIdx.x * blockDim.x + threadIdx.x;
-    const int lane = threadIdx.x & 31;
-    const double qnan = __longlong_as_double(0x7ff8000000000000ll);
-    unsigned long long *checked = A.ctl, *stop = A.ctl + 1, *rows_done = A.ctl + 2, *errs = A.ctl + 2 + kCtlSlots;
-    unsigned long long stop_at = kNoStop;
-    for (int s = 0; s < A.T && stop_at == kNoStop; ++s) {
-        // gate: sweep s + 1 - kRing complete, or a stop published
-        if (lane == 0) {
-            unsigned spins = 0;
-            long long tw0 = 0;
-            for (;;) {
-                stop_at = ld_relaxed_u64(stop);
-                if (stop_at != kNoStop || (long long)ld_relaxed_u64(checked) + (kRing - 2) >= (long long)s) break;
-                if (wait_expired(A.counter + 1, spins, tw0)) { stop_at = 0; break; }
-            }
-        }
-        stop_at = __shfl_sync(0xffffffffu, stop_at, 0);
-        if (stop_at != kNoStop) break;
-        const Cell *cur = A.ring + (size_t)(s % kRing) * A.n;            // versions s   (neighbours j >= i, own old value)
-        Cell *nxt = A.ring + (size_t)((s + 1) % kRing) * A.n;            // versions s+1 (neighbours j < i, own new value)
-        const unsigned long long want_lo = (unsigned long long)s + 1ull, want_hi = (unsigned long long)s;
-        double err = 0.0;
-        int done_rows = 0;
-        bool abandoned = false;
-        for (int p0 = gt - lane; p0 < A.n_active && !abandoned; p0 += NT) {   // warp-uniform trip count
-            const int i = p0 + lane < A.n_active ? __ldg(A.order + p0 + lane) : -1;
-            const bool active = i >= 0;
-            bool pending = active;
-            int rs = 0, L = 0, k = 0, crit = -1;
-            double uv[kLipCap], wv[kLipCap];
-            double minu = 0.0, maxu = 0.0, sumu = 0.0, deg = 0.0, uold = 0.0;
-            bool empty_row = false, have_old = false;
-            if (active) {
-                rs = A.start[i];
-                L = A.start[i + 1] - rs;
-                crit = A.use_crit ? __ldg(A.crit + i) : -1;
-                if (L == 0) {
-                    empty_row = true;
-                    if (rs < A.M) L = 1; else { minu = maxu = qnan; }
-                }
-            }
-            auto update_row = [&]() {
-                double ne;
-                if (!WEIGHTED) {
-                    ne = __dadd_rn(__ddiv_rn(__dmul_rn(A.alpha, sumu), deg), __ddiv_rn(__dmul_rn(A.beta, __dadd_rn(minu, maxu)), 2.0));
-                } else {
-                    double a = minu, b = maxu;
-                    const int Lr = empty_row ? 0 : L;
-                    const int Lc = Lr < kLipCap ? Lr : kLipCap;
-                    for (int r = 0; r < 30; ++r) {
-                        const double tm = __ddiv_rn(__dadd_rn(a, b), 2.0);
-                        double minw = 0.0, maxw = 0.0;
-                        for (int kk = 0; kk < Lc; ++kk) {
-                            const double d = __dmul_rn(wv[kk], __dsub_rn(tm, uv[kk]));
-                            minw = d < minw ? d : minw;
-                            maxw = d > maxw ? d : maxw;
-                        }
-                        for (int kk = kLipCap; kk < Lr; ++kk) {            // beyond the local cache: still valid (see the gate), read again
-                            const int j = __ldg(A.nbr + rs + kk);
-                            const double d = __dmul_rn(__ldg(A.W + rs + kk), __dsub_rn(tm, ld_cell((j < i ? nxt : cur) + j).a));
-                            minw = d < minw ? d : minw;
-                            maxw = d > maxw ? d : maxw;
-                        }
-                        if (__dadd_rn(minw, maxw) > 0.0) b = tm; else a = tm;
-                    }
-                    ne = __ddiv_rn(__dadd_rn(a, b), 2.0);
-                }
-                double d = __dsub_rn(uold, ne);
-                d = d < 0.0 ? -d : d;
-                if (d > err) err = d;
-                st_cell(nxt + i, ne, want_lo);
-                ++done_rows;
-            };
-            unsigned spins = 0;
-            long long tw0 = 0;
-            while (__any_sync(0xffffffffu, pending)) {
-                if (!pending) continue;
-                if ((++spins & 255u) == 0u) {                        // a stop published while waiting: the producers are gone
-                    if (ld_relaxed_u64(stop) != kNoStop) { pending = false; abandoned = true; continue; }
-                    if ((spins & 1023u) == 0u) {
-                        if (tw0 == 0) tw0 = clock64();
-                        else if (ld_relaxed_u32(A.counter + 1) != 0u || clock64() - tw0 > kWaitLimit) {
-                            asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(A.counter + 1), "r"(1u) : "memory");
-                            pending = false; abandoned = true; continue;
-                        }
-                    }
-                }
-                if (!have_old) {                                     // own version s (written by this lane one sweep ago)
-                    const Cell c = ld_cell(cur + i);
-                    if (c.b < want_hi) continue;
-                    uold = c.a; have_old = true;
-                }
-                if (crit >= 0) {                                     // one cheap poll on the producer expected last
-                    if (ld_cell(nxt + crit).b < want_lo) continue;
-                    crit = -1;
-                }
-                int jj[kLipBatch];
-                Cell c[kLipBatch];
-#pragma unroll
-                for (int q = 0; q < kLipBatch; ++q) {
-                    jj[q] = k + q < L ? __ldg(A.nbr + rs + k + q) : -1;
-                    if (jj[q] >= 0) c[q] = ld_cell((jj[q] < i ? nxt : cur) + jj[q]);
-                }
-                bool halt = false;
-#pragma unroll
-                for (int q = 0; q < kLipBatch; ++q) {
-                    if (halt || jj[q] < 0) continue;
-                    if (c[q].b < (jj[q] < i ? want_lo : want_hi)) { halt = true; continue; }   // producer not there yet: retry from here
-                    const double v = c[q].a;
-                    if (k == 0) { minu = v; maxu = v; }
-                    if (!empty_row) {
-                        const double w = __ldg(A.W + rs + k);
-                        if (!WEIGHTED) {
-                            sumu = __dadd_rn(sumu, __dmul_rn(w, v));
-                            deg = __dadd_rn(deg, w);
-                        } else if (k < kLipCap) {
-                            uv[k] = v; wv[k] = w;
-                        }
-                    }
-                    minu = v < minu ? v : minu;
-                    maxu = v > maxu ? v : maxu;
-                    ++k;
-                }
-                if (k < L) continue;
-                pending = false;
-                if (!LOCKSTEP) update_row();
-            }
-            abandoned = __any_sync(0xffffffffu, abandoned);
-            if (LOCKSTEP && active && !abandoned) update_row();
-        }
-        if (__any_sync(0xffffffffu, abandoned)) { stop_at = ld_relaxed_u64(stop); if (stop_at == kNoStop) stop_at = 0; break; }
-        // the warp's share of sweep s: rows done and error
-        unsigned long long ebits = (unsigned long long)__double_as_longlong(err);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const unsigned long long other = __shfl_xor_sync(0xffffffffu, ebits, o);
-            ebits = other > ebits ? other : ebits;
-            done_rows += __shfl_xor_sync(0xffffffffu, done_rows, o);
-        }
-        if (lane == 0 && done_rows > 0) {
-            const int slot = s % kCtlSlots;
-            if (ebits) atomicMax(errs + slot, ebits);
-            __threadfence();
-            const unsigned long long before = atomicAdd(rows_done + slot, (unsigned long long)done_rows);
-            if (before + (unsigned long long)done_rows == (unsigned long long)A.n_rows) {     // this warp completed sweep s
-                __threadfence();
-                const double e = __longlong_as_double((long long)atomicMax(errs + slot, 0ull));
-                errs[slot] = 0ull; rows_done[slot] = 0ull;            // the slot is reused by sweep s + kCtlSlots, which cannot have started
-                __threadfence();
-                // decisions are taken in sweep order (rows running ahead can complete sweep s + 1 before the decision on
-                // sweep s is published); after a stop nothing else is decided
-                unsigned spins2 = 0;
-                long long tw2 = 0;
-                while (ld_relaxed_u64(stop) == kNoStop && ld_relaxed_u64(checked) < (unsigned long long)s &&
-                       !wait_expired(A.counter + 1, spins2, tw2)) { }
-                if (ld_relaxed_u64(stop) != kNoStop || ld_relaxed_u64(checked) < (unsigned long long)s) { }
-                else if (e < A.tol && s > 20) asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(stop), "l"((unsigned long long)s + 1ull) : "memory");
-                else asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(checked), "l"((unsigned long long)s + 1ull) : "memory");
-            }
-        }
-    }
-    // everybody has left the sweep loop (stop published, T reached or watchdog): agree on the number of sweeps
-    barrier_max(0.0, A.slots, A.counter, 0u);
-    const unsigned long long st = ld_relaxed_u64(stop);
-    const int nsweeps = st != kNoStop ? (int)st : A.T;
-    const Cell *fin = A.ring + (size_t)(nsweeps % kRing) * A.n;
-    for (int i = gt; i < A.n; i += NT) A.u_out[i] = ld_cell(fin + i).a;
-    if (gt == 0) *A.sweeps = nsweeps;
-}
-
-__global__ void __launch_bounds__(256) lip_ring_pack_kernel(const double *u, const int *lab, const double *labval, Cell *ring, int n)
-{
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const int l = lab[i];
-        for (int v = 0; v < kRing; ++v) {
-            Cell *c = ring + (size_t)v * n + i;
-            if (l >= 0) { c->a = labval[l]; c->b = kVerFixed; }
-            else { c->a = u[i]; c->b = 0ull; }                    // version 0 in buffer 0; stale (0 < v) everywhere else
-        }
-    }
 }
 
 __global__ void __launch_bounds__(256) lip_pack_kernel(const double *u, const int *lab, const double *labval, Cell *c0, Cell *c1, int n)
@@ -874,8 +650,7 @@ int upload_common(Common &C, const int32_t *h_nbr, const int32_t *h_row, const d
 // largest level among the unlabelled neighbours j < i of the unlabelled row i (those are the values row i must wait for
 // inside a sweep), rows sorted by (level, index), every level padded with -1 to a multiple of 32; crit[i] = a neighbour attaining that maximum, -1 without producers.
 void level_schedule(const int32_t *h_nbr, const int32_t *h_row, const std::vector<int> &lab, int n, int M,
-                    std::vector<int> &order, std::vector<int> &crit, int *depth, std::vector<int> *blk_level = nullptr,
-                    std::vector<int> *lvl_size = nullptr)
+                    std::vector<int> &order, std::vector<int> &crit, int *depth)
 {
     std::vector<int> start((size_t)n + 1, 0), level((size_t)n, -1);
     for (int k = 0; k < M; ++k) ++start[(size_t)h_row[k] + 1];
@@ -900,12 +675,6 @@ void level_schedule(const int32_t *h_nbr, const int32_t *h_row, const std::vecto
     std::vector<int> pos((size_t)maxl + 2, 0);
     for (int l = 0; l <= maxl; ++l) pos[l + 1] = pos[l] + ((count[l] + 31) & ~31);      // a warp never straddles two levels
     order.assign((size_t)pos[maxl + 1], -1);
-    if (blk_level) {
-        blk_level->assign(order.size() / 32, 0);
-        for (int l = 0; l <= maxl; ++l)
-            for (int b = pos[l] / 32; b < pos[l + 1] / 32; ++b) (*blk_level)[b] = l;
-    }
-    if (lvl_size) lvl_size->assign(count.begin(), count.end());
     for (int i = 0; i < n; ++i)
         if (level[i] >= 0) order[pos[level[i]]++] = i;
     *depth = maxl + 1;
@@ -981,22 +750,16 @@ extern "C" GLB_API int glb_lip_iterate_host(double *h_u, const int32_t *h_nbr, c
     Common C;
     std::vector<int> lab, order, crit;
     if ((rc = upload_common(C, h_nbr, h_row, h_w, h_ind, h_val, n, M, m, st, &nl, lab))) return rc;
-    // Schedule (GLB_LIP_MODE overrides for experiments; bit 0 level order, bit 1 critical-producer poll, bit 2 lockstep):
-    //   AMLE (weighted): level order + producer poll + lockstep - the 30-step bisection dominates and runs once per
-    //                    warp with all 32 lanes busy;
+    // Schedule (the alternatives - sweeps overlapping through a ring of version buffers, per-level completion counters - were
+    // bit-identical and not faster, profiles/r1_lip_schedules.txt; they are gone from the product):
+    //   AMLE (weighted): rows dealt to warps by level of the dependency DAG, a waiting lane polls only its latest-level
+    //                    producer, the warp runs the 30-step bisection in lockstep with all 32 lanes busy;
     //   unweighted:      rows in natural order, every lane gathers and stores on its own - the update is a handful of
     //                    flops, so the shortest path from "last neighbour ready" to "value published" wins.
-    //   bit 3: sweeps overlap (ring of version buffers, no barrier between sweeps) - GLB_LIP_MODE without it selects the
-    //          one-barrier-per-sweep kernel
-    //   bit 4: level counters - a warp polls one "level below done" counter instead of its rows' neighbour cells
-    int mode = weighted ? 7 : 0;
-    if (getenv("GLB_LIP_MODE")) mode = atoi(getenv("GLB_LIP_MODE"));
-    if (mode & 4) mode |= 1;                                      // lockstep needs warps of one level
+    const bool by_level = weighted != 0;
     int depth = 0;
-    std::vector<int> blk_level, lvl_size;
-    if (mode & 16) mode |= 1;                                     // level counters need warps of one level
-    level_schedule(h_nbr, h_row, lab, n, M, order, crit, &depth, &blk_level, &lvl_size);
-    if (!(mode & 1)) {
+    level_schedule(h_nbr, h_row, lab, n, M, order, crit, &depth);
+    if (!by_level) {
         order.clear();
         for (int i = 0; i < n; ++i) if (lab[i] < 0) order.push_back(i);
     }
@@ -1009,37 +772,9 @@ extern "C" GLB_API int glb_lip_iterate_host(double *h_u, const int32_t *h_nbr, c
     GLB_CUDA(cudaMemcpyAsync(u, h_u, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, st));
     const int gb = sm_count() * 4;
     lip_pack_kernel<<<gb, 256, 0, st>>>(u, C.lab, C.labval, C.c0, C.c1, n);
-    int n_rows = 0;
-    for (int i : order) n_rows += i >= 0 ? 1 : 0;
-    const bool pipelined = (mode & 8) && n_rows > 0;
-    Cell *ring = nullptr;
-    unsigned long long *ctl = nullptr;
-    if (pipelined) {
-        GLB_CUDA(C.A.alloc(&ring, (size_t)kRing * n));
-        GLB_CUDA(C.A.alloc(&ctl, (size_t)2 + 2 * kCtlSlots));
-        unsigned long long h_ctl[2 + 2 * kCtlSlots] = {0ull, kNoStop};
-        GLB_CUDA(cudaMemcpyAsync(ctl, h_ctl, sizeof(h_ctl), cudaMemcpyHostToDevice, st));
-        GLB_CUDA(cudaStreamSynchronize(st));                      // h_ctl is a local
-        lip_ring_pack_kernel<<<gb, 256, 0, st>>>(u, C.lab, C.labval, ring, n);
-    }
-    int *d_blk_level = nullptr, *d_lvl_size = nullptr;
-    unsigned long long *d_lvl_done = nullptr;
-    if ((mode & 16) && !pipelined && !blk_level.empty()) {
-        GLB_CUDA(C.A.alloc(&d_blk_level, blk_level.size())); GLB_CUDA(C.A.alloc(&d_lvl_size, lvl_size.size()));
-        GLB_CUDA(C.A.alloc(&d_lvl_done, lvl_size.size()));
-        GLB_CUDA(cudaMemcpyAsync(d_blk_level, blk_level.data(), blk_level.size() * sizeof(int), cudaMemcpyHostToDevice, st));
-        GLB_CUDA(cudaMemcpyAsync(d_lvl_size, lvl_size.data(), lvl_size.size() * sizeof(int), cudaMemcpyHostToDevice, st));
-        GLB_CUDA(cudaMemsetAsync(d_lvl_done, 0, lvl_size.size() * sizeof(unsigned long long), st));
-    }
     LipArgs A{C.start, C.nbr, C.W, C.lab, d_order, d_crit, C.c0, C.c1, u_out, C.slots, C.counter, C.sweeps, n, M, T,
-              (int)order.size(), (mode & 2) ? 1 : 0, tol, alpha, beta, ring, ctl, n_rows, d_blk_level, d_lvl_size, d_lvl_done};
-    const void *fn;
-    if (pipelined)
-        fn = weighted ? ((mode & 4) ? (const void *)lip_pipelined_kernel<true, true> : (const void *)lip_pipelined_kernel<true, false>)
-                      : ((mode & 4) ? (const void *)lip_pipelined_kernel<false, true> : (const void *)lip_pipelined_kernel<false, false>);
-    else
-        fn = weighted ? ((mode & 4) ? (const void *)lip_gauss_seidel_kernel<true, true> : (const void *)lip_gauss_seidel_kernel<true, false>)
-                      : ((mode & 4) ? (const void *)lip_gauss_seidel_kernel<false, true> : (const void *)lip_gauss_seidel_kernel<false, false>);
+              (int)order.size(), by_level ? 1 : 0, tol, alpha, beta};
+    const void *fn = weighted ? (const void *)lip_gauss_seidel_kernel<true, true> : (const void *)lip_gauss_seidel_kernel<false, false>;
     int grid = 0;
     if ((rc = coop_grid(fn, 256, &grid))) return rc;
     grid = std::min(grid, std::max(1, ceil_div(n, 256)));

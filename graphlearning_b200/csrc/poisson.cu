@@ -868,11 +868,18 @@ static const void *pick_barrier(int ldu, int *threads)
 template <int LANES>
 static const void *dataflow_fn(bool l1_first, int *threads)
 {
-    const int pt = exp_env("GLB_POISSON_THREADS", 512);           // CTA size: 512 measured best (profiles/r2_dataflow_pair_stream_ab.txt)
+#ifdef GLB_EXPERIMENT
+    // A/B switches of the experiment build: CTA size (512 measured best, profiles/r2_dataflow_pair_stream_ab.txt) and the
+    // first gather attempt through L1 (on: 6.4 us, off: 6.9-10 us per iteration)
+    const int pt = exp_env("GLB_POISSON_THREADS", 512);
     if (pt == 768) { *threads = 768; return l1_first ? (const void *)poisson_dataflow_kernel<LANES, 768, true> : (const void *)poisson_dataflow_kernel<LANES, 768, false>; }
     if (pt == 1024) { *threads = 1024; return l1_first ? (const void *)poisson_dataflow_kernel<LANES, 1024, true> : (const void *)poisson_dataflow_kernel<LANES, 1024, false>; }
+    if (!l1_first) { *threads = 512; return (const void *)poisson_dataflow_kernel<LANES, 512, false>; }
+#else
+    (void)l1_first;
+#endif
     *threads = 512;
-    return l1_first ? (const void *)poisson_dataflow_kernel<LANES, 512, true> : (const void *)poisson_dataflow_kernel<LANES, 512, false>;
+    return (const void *)poisson_dataflow_kernel<LANES, 512, true>;
 }
 
 static const void *pick_dataflow(int lanes, bool l1_first, int *threads)

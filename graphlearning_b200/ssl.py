@@ -159,6 +159,25 @@ class poisson(ssl):
         source[train_ind] = onehot - np.mean(onehot, axis=0)
         return source, k
 
+    def _fit_gd_verbose(self, source, train_ind, all_labels):
+        """all_labels given: the reference prints the accuracy after EVERY iteration (ssl.py:672-677).  Same iterate, one
+        launch per iteration (glb_poisson_iterate with T = 1) and a download of the scores for predict() in between."""
+        from . import device
+        op = device.PoissonOperator(self.graph.weight_matrix)
+        T = op.mixing_T(train_ind, self.min_iter, self.max_iter)
+        Db = op.source_to_Db(source)
+        c = source.shape[1]
+        u = device._torch().zeros_like(Db)
+        nl = 0
+        for t in range(1, T + 1):
+            u, l = op.iterate(Db, 1, u0=u, c=c)
+            nl += l
+            self.prob = op.unpack(u, c).cpu().numpy()
+            print("%d,Accuracy = %.2f" % (t, ssl_accuracy(self.predict(), all_labels, train_ind)))
+        self.iterations = T
+        self.gpu_launches = nl
+        return op.unpack(u, c).cpu().numpy()
+
     def _fit(self, train_ind, train_labels, all_labels=None):
         W = self.graph.weight_matrix
         n = self.graph.num_nodes
@@ -167,6 +186,8 @@ class poisson(ssl):
             if source.shape[1] != k:
                 # the reference adds an (n,k) array to an (n,width) one here and fails in numpy broadcasting
                 raise ValueError("train_labels must be 0..k-1 for the gradient_descent solver")
+            if all_labels is not None:
+                return self._fit_gd_verbose(source, train_ind, all_labels)
             u, T, nl = self.graph.poisson_handle().fit(source, train_ind, self.min_iter, self.max_iter)
             self.iterations = T
             self.gpu_launches = nl

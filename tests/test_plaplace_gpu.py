@@ -198,23 +198,6 @@ def test_70k_graph_against_oracle():
     assert sw2 == 22 and np.max(np.abs(again - conv)) < 22 * 1e-4      # `it > 20` forces 22 sweeps, each moving < tol
 
 
-@pytest.mark.parametrize("mode", ["8", "15", "3", "21", "17"])
-def test_alternative_schedules_are_bit_identical(plap, monkeypatch, mode):
-    """GLB_LIP_MODE selects other schedules of the same sweep (bit 0 level order, 1 producer poll, 2 lockstep, 3 sweeps
-    overlapping through a ring of version buffers with per-sweep completion counters, 4 per-level completion counters).  All of them must reproduce the
-    reference's sequential sweep bit for bit, including the sweep at which the stopping rule fires."""
-    monkeypatch.setenv("GLB_LIP_MODE", mode)
-    I, J, V, ti, val = plap["cI"], plap["cJ"], plap["cV"], plap["train_ind"], plap["val"]
-    u, sw = lip(np.zeros(2000), J, I, V, ti, val, 10 ** 6, 1e-6, 0, 0.5, 0.5)
-    assert np.array_equal(u, plap["pl_fast_p3"])
-    u, sw = lip(np.zeros(2000), J, I, V, ti, val, 25, 1e-5, 1)
-    assert np.array_equal(u, plap["amle_w_T25"]) and sw == 25
-    u, sw = lip(np.zeros(2000), J, I, V, ti, val, 1000, 1e-5, 1)
-    assert np.array_equal(u, plap["amle_w"])
-    u, _ = lip(np.zeros(2000), plap["dJ"], plap["dI"], plap["dV"], ti, val, 30, 1e-9, 0, 0.0, 1.0)
-    assert np.array_equal(u, plap["amle_u_directed_T30"], equal_nan=True)
-
-
 def test_batched_classes_equal_separate_calls(gl, plap, blobs):
     """glb_lip_iterate_multi_host: the c one-vs-rest right-hand sides in one launch; every column - values AND the sweep at
     which its own stopping rule fired - must equal the single-class call, and ssl.plaplace / ssl.amle (which use the

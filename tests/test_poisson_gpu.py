@@ -57,6 +57,19 @@ def test_two_moons_default_stopping_rule(gl, moons):
     assert m.gpu_launches > 0
 
 
+def test_all_labels_prints_the_accuracy_of_every_iteration(gl, moons, capsys):
+    """fit(..., all_labels=labels): one line per iteration, as the reference's loop prints them (ssl.py:672-677), and the
+    same scores as the silent fit."""
+    ti = moons["train_ind"]; tl = moons["labels"][ti]
+    m = gl.ssl.poisson(moons.csr("W"), solver="gradient_descent", min_iter=7, max_iter=7)
+    u_quiet = m.fit(ti, tl)
+    capsys.readouterr()
+    u = gl.ssl.poisson(moons.csr("W"), solver="gradient_descent", min_iter=7, max_iter=7).fit(ti, tl, all_labels=moons["labels"])
+    lines = [l for l in capsys.readouterr().out.splitlines() if "Accuracy" in l]
+    assert len(lines) == 7 and lines[0].startswith("1,Accuracy = ") and lines[-1].startswith("7,Accuracy = ")
+    assert rel_err(u, u_quiet) <= 1e-6
+
+
 def test_two_moons_fixed_T_and_directed(gl, moons):
     ti = moons["train_ind"]; tl = moons["labels"][ti]
     u = gl.ssl.poisson(moons.csr("W"), solver="gradient_descent", min_iter=80, max_iter=80).fit(ti, tl)
