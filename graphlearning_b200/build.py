@@ -50,7 +50,8 @@ def needs_build(lib=LIB):
 def build(force=False, verbose=False, exp=False):
     lib = LIB_EXP if exp else LIB
     objdir = OBJDIR + ("_exp" if exp else "")
-    extra = ["-DGLB_EXPERIMENT"] if exp else []
+    # GLB_NVCC_EXTRA: more -D switches for the experiment build only (compile-time A/B runs of tools/)
+    extra = ["-DGLB_EXPERIMENT"] + os.environ.get("GLB_NVCC_EXTRA", "").split() if exp else []
     if not force and not needs_build(lib):
         return lib
     os.makedirs(LIBDIR, exist_ok=True)

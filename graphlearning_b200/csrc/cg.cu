@@ -54,7 +54,8 @@ __device__ __forceinline__ void st4(double *p, const real4 &v)
 constexpr int kCgMaxLd = 128;
 constexpr int kCgThreads = 256;
 constexpr int kCgHist = 64;                 // iterations per batch = length of the err history window
-constexpr int kCgLongRow = 64;              // rows with more nonzeros are spread over a whole warp
+constexpr int kCgLongRow = 64;              // rows with more nonzeros are spread over a whole warp ...
+constexpr int kCgHubRow = 768;              // ... and beyond this over a whole CTA
 
 struct CgState {
     double rsold[kCgMaxLd];
@@ -178,7 +179,8 @@ cg_spmm_dot(const int *__restrict__ rowptr, const int *__restrict__ col, const d
         const int r0 = min(n, gw * chunk), r1 = min(n, r0 + chunk);
         for (int base = r0; base < r1; base += 32) {
             const int mine = base + lane;
-            const bool is_long = mine < r1 && __ldg(rowptr + mine + 1) - __ldg(rowptr + mine) > kCgLongRow;
+            const int mylen = mine < r1 ? __ldg(rowptr + mine + 1) - __ldg(rowptr + mine) : 0;
+            const bool is_long = mylen > kCgLongRow && mylen <= kCgHubRow;
             unsigned todo = __ballot_sync(0xffffffffu, is_long);
             while (todo) {
                 const int row = base + __ffs(todo) - 1;
@@ -218,7 +220,67 @@ cg_spmm_dot(const int *__restrict__ rowptr, const int *__restrict__ col, const d
             }
         }
     }
+    // Rows with more than kCgHubRow nonzeros (5 000 neighbours happen at d = 512): the whole CTA takes one such row - 64
+    // lane groups x 4 gathers in flight instead of a warp's 8 x 4 - and folds the partial sums through shared memory
+    // in a fixed order.  Every CTA looks through its own contiguous share of the rows.
+    {
+        constexpr int NGB = kCgThreads / LANES;                        // lane groups of the CTA
+        const int gb = threadIdx.x / LANES, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        const int chunk = (n + (int)gridDim.x - 1) / (int)gridDim.x;
+        const int r0 = min(n, (int)blockIdx.x * chunk), r1 = min(n, r0 + chunk);
+        for (int base = r0; base < r1; base += kCgThreads) {
+            const int mine = base + threadIdx.x;
+            const bool hub = mine < r1 && __ldg(rowptr + mine + 1) - __ldg(rowptr + mine) > kCgHubRow;
+            if (!__syncthreads_or(hub)) continue;
+            for (int t = 0; t < kCgThreads && base + t < r1; ++t) {
+                const int row = base + t;
+                const int beg = __ldg(rowptr + row), end = __ldg(rowptr + row + 1);
+                if (end - beg <= kCgHubRow) continue;                  // block-uniform
+                real4 acc; acc.x = acc.y = acc.z = acc.w = 0.0;
+                int j = beg + gb;
+                for (; j + 3 * NGB < end; j += 4 * NGB) {
+                    int cj[4]; double a[4]; real4 x[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) { cj[i] = __ldg(col + j + i * NGB); a[i] = __ldg(val + j + i * NGB); }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) x[i] = ld4(p + (size_t)cj[i] * LDU + li * 4);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        acc.x = fma(a[i], x[i].x, acc.x); acc.y = fma(a[i], x[i].y, acc.y);
+                        acc.z = fma(a[i], x[i].z, acc.z); acc.w = fma(a[i], x[i].w, acc.w);
+                    }
+                }
+                for (; j < end; j += NGB) {
+                    const double a = __ldg(val + j);
+                    const real4 x = ld4(p + (size_t)__ldg(col + j) * LDU + li * 4);
+                    acc.x = fma(a, x.x, acc.x); acc.y = fma(a, x.y, acc.y); acc.z = fma(a, x.z, acc.z); acc.w = fma(a, x.w, acc.w);
+                }
+#pragma unroll
+                for (int off = LANES; off < 32; off <<= 1) {
+                    acc.x += __shfl_xor_sync(0xffffffffu, acc.x, off); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, off);
+                    acc.z += __shfl_xor_sync(0xffffffffu, acc.z, off); acc.w += __shfl_xor_sync(0xffffffffu, acc.w, off);
+                }
+                __syncthreads();                                       // sh is free (previous hub row / nothing yet)
+                if (lane < LANES) { sh[warp * LDU + li * 4 + 0] = acc.x; sh[warp * LDU + li * 4 + 1] = acc.y; sh[warp * LDU + li * 4 + 2] = acc.z; sh[warp * LDU + li * 4 + 3] = acc.w; }
+                __syncthreads();
+                if (threadIdx.x < LANES) {
+                    real4 tot; tot.x = tot.y = tot.z = tot.w = 0.0;
+                    for (int w = 0; w < kCgThreads / 32; ++w) {
+                        tot.x += sh[w * LDU + li * 4 + 0]; tot.y += sh[w * LDU + li * 4 + 1];
+                        tot.z += sh[w * LDU + li * 4 + 2]; tot.w += sh[w * LDU + li * 4 + 3];
+                    }
+                    st4(Ap + (size_t)row * LDU + li * 4, tot);
+                    if (MODE == 0) {
+                        const real4 pr = ld4(p + (size_t)row * LDU + li * 4);
+                        d[0] += pr.x * tot.x; d[1] += pr.y * tot.y; d[2] += pr.z * tot.z; d[3] += pr.w * tot.w;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
     if (MODE != 0) return;
+    __syncthreads();
     block_reduce_columns<LANES>(d, sh, partial);
     if (last_block_totals<LDU>(partial, &st->ticket[0], sh, sh_tot)) {
         if (threadIdx.x < LDU) st->alpha[threadIdx.x] = threadIdx.x < c ? st->rsold[threadIdx.x] / sh_tot[threadIdx.x] : 0.0;

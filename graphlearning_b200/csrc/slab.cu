@@ -136,8 +136,11 @@ __device__ __forceinline__ void slab_consume(const float (&val)[2], const float4
     }
 }
 
+#ifndef GLB_SLAB_MINB
+#define GLB_SLAB_MINB 3                          // resident CTAs per SM the register budget is cut for
+#endif
 template <int LANES>
-__global__ void __launch_bounds__(kSlabWarps * 32, 3)
+__global__ void __launch_bounds__(kSlabWarps * 32, GLB_SLAB_MINB)
 slab_step_kernel(const SlabParams p)
 {
     constexpr int RPW = 32 / LANES;
