@@ -475,8 +475,14 @@ poisson_dataflow_kernel(const int2 *__restrict__ slabs, const long long *__restr
     const int4 *stream = nsw > 0 ? reinterpret_cast<const int4 *>(s_cv + s_slot[warp].x) + g : nullptr;
     unsigned n_poll = 0, n_badbatch = 0;
     const long long clk0 = clock64();
+#ifdef GLB_EXPERIMENT
+    long long busy = 0;                                                  // GLB_POISSON_STATS: cycles this warp spent working (not at a gate)
+#endif
     for (int t = 0; t < T; ++t) {
-        if (start_gate && gate_every > 0 && t > 0 && t % gate_every == 0) {      // re-alignment gate (see the batch kernel)
+        if (start_gate && gate_every > 0 && t > 0 && t % gate_every == 0) {
+            // Re-alignment gate: nobody starts iteration t before every CTA has finished iteration t - 1 (relaxed: no fence, the
+            // flags keep the data correct).  ONE poller per CTA: with every warp polling the counter itself (2 368 pollers on
+            // one L2 line, tried) the arrivals queue behind the polls and the iterate slows from 6.3 to 9.0 us.
             __syncthreads();
             if (threadIdx.x == 0) {
                 red_relaxed_add(start_gate, 1u);
@@ -488,6 +494,9 @@ poisson_dataflow_kernel(const int2 *__restrict__ slabs, const long long *__restr
             __syncthreads();
         }
         if (nsw == 0) continue;
+#ifdef GLB_EXPERIMENT
+        const long long tb0 = stats ? clock64() : 0;
+#endif
         const int vi = t & (kRing - 1), vo = (t + 1) & (kRing - 1);
         const char *in = reinterpret_cast<const char *>(vi == 0 ? ring.b[0] : vi == 1 ? ring.b[1] : vi == 2 ? ring.b[2] : ring.b[3]) + li * 16;
         char *out = reinterpret_cast<char *>(vo == 0 ? ring.b[0] : vo == 1 ? ring.b[1] : vo == 2 ? ring.b[2] : ring.b[3]) + li * 16;
@@ -573,12 +582,35 @@ poisson_dataflow_kernel(const int2 *__restrict__ slabs, const long long *__restr
             GLB_DFP_STEP(v3, x3)
         }
 #undef GLB_DFP_STEP
+#ifdef GLB_EXPERIMENT
+        if (stats) busy += clock64() - tb0;
+#endif
     }
     if (stats) {
         atomicAdd(stats + 0, (unsigned long long)n_poll);
         atomicAdd(stats + 1, (unsigned long long)n_badbatch);
         if (lane == 0) atomicMax(stats + 2, (unsigned long long)(clock64() - clk0));
         if (threadIdx.x == 0) atomicAdd(stats + 3, 1ull);
+#ifdef GLB_EXPERIMENT
+        if (lane == 0) {                                                 // busy cycles: sum and max over warps, max over CTAs of the CTA's mean
+            atomicAdd(stats + 4, (unsigned long long)busy);
+            atomicMax(stats + 5, (unsigned long long)busy);
+            atomicAdd(stats + 6, 1ull);
+        }
+        __syncthreads();
+        {
+            __shared__ unsigned long long cta_sum, cta_max;
+            if (threadIdx.x == 0) { cta_sum = 0ull; cta_max = 0ull; }
+            __syncthreads();
+            if (lane == 0) { atomicAdd(&cta_sum, (unsigned long long)busy); atomicMax(&cta_max, (unsigned long long)busy); }
+            __syncthreads();
+            if (threadIdx.x == 0) { atomicMax(stats + 7, cta_sum / NW); atomicAdd(stats + 8, cta_max); }
+        }
+        if (lane == 0) {                                                 // per-warp record behind the 16 summary words: busy, pairs, slots
+            unsigned long long *rec = stats + 16 + ((size_t)blockIdx.x * NW + warp) * 3;
+            rec[0] = (unsigned long long)busy; rec[1] = (unsigned long long)n_pairs; rec[2] = (unsigned long long)nsw;
+        }
+#endif
     }
 }
 
@@ -958,7 +990,7 @@ static void build_dataflow_slabs(const std::vector<int> &h_rp, const int *h_col,
             sl.L = h_rp[order[k0] + 1] - h_rp[order[k0]];
             for (int g = 0; g < rpw; ++g) if (sl.rows[g] >= 0) out.wavefronts += h_rp[sl.rows[g] + 1] - h_rp[sl.rows[g]];
             out.steps += sl.L;
-            sl.cost = (sl.L + 1) / 2 + 2;
+            sl.cost = (sl.L + 1) / 2 + 3;                    // measured: 237 cycles per pair + 840 per slot (store, bookkeeping)
         }
         // long rows: one warp-wide slot per piece of at most part_max nonzeros
         int nparts_cta = 0;
@@ -985,7 +1017,7 @@ static void build_dataflow_slabs(const std::vector<int> &h_rp, const int *h_col,
                     sl.type = kSlotPart;
                     sl.pbuf = nparts_cta + q - 1;
                 }
-                sl.cost = (sl.L + 1) / 2 + 2 + (q == 0 ? m - 1 : 0);
+                sl.cost = (sl.L + 1) / 2 + 3 + (q == 0 ? m - 1 : 0);
                 out.wavefronts += sl.nz1 - sl.nz0;
                 out.steps += sl.L;
             }
@@ -1173,7 +1205,7 @@ static int plan_try_dataflow(glb_poisson_plan *p, const std::vector<int> &h_rp, 
     p->ell_fill = slab.size() ? (double)nnz / (double)slab.size() : 1.0;
     GLB_CUDA(dev_alloc(&p->d_gate, 2 * sizeof(unsigned)));          // [0] gate counter, [1] watchdog flag
     GLB_CUDA(cudaMemsetAsync(p->d_gate, 0, 2 * sizeof(unsigned), st));
-    if (exp_env("GLB_POISSON_STATS", 0)) GLB_CUDA(dev_alloc(&p->d_stats, 4 * sizeof(unsigned long long)));
+    if (exp_env("GLB_POISSON_STATS", 0)) GLB_CUDA(dev_alloc(&p->d_stats, (16 + (size_t)grid * 32 * 3) * sizeof(unsigned long long)));
     return 0;
 }
 
@@ -1508,7 +1540,7 @@ extern "C" GLB_API int glb_poisson_iterate(glb_poisson_plan *plan, const float *
                         (void *)&plan->d_slot_rows, (void *)&d_Db, (void *)&ring, (void *)&T,
                         (void *)&plan->cap_entries, (void *)&plan->cap_slots, (void *)&plan->cap_parts, (void *)&plan->d_stats,
                         (void *)&gate, (void *)&gate_every, (void *)&watchdog, (void *)&plan->poll_sleep};
-        if (plan->d_stats) GLB_CUDA(cudaMemsetAsync(plan->d_stats, 0, 4 * sizeof(unsigned long long), st));
+        if (plan->d_stats) GLB_CUDA(cudaMemsetAsync(plan->d_stats, 0, 16 * sizeof(unsigned long long), st));
         GLB_CUDA(cudaLaunchCooperativeKernel(plan->fn, dim3(plan->grid), dim3(plan->threads), args, plan->smem_bytes, st));
         if (launches) *launches += 2;
         if ((T & (kRing - 1)) >= 2) {                         // version T sits in a plan-owned buffer: hand it to the caller
@@ -1517,11 +1549,26 @@ extern "C" GLB_API int glb_poisson_iterate(glb_poisson_plan *plan, const float *
             if (launches) *launches += 1;
         }
         if (plan->d_stats) {
-            unsigned long long h[4];
+            unsigned long long h[16];
             GLB_CUDA(cudaMemcpyAsync(h, plan->d_stats, sizeof(h), cudaMemcpyDeviceToHost, st));
             GLB_CUDA(cudaStreamSynchronize(st));
             fprintf(stderr, "[glb] dataflow T=%d grid=%d: re-polls %llu (%.4f per nonzero-lane), polling batches %llu, max warp cycles/iter %.0f\n",
                     T, plan->grid, h[0], (double)h[0] / ((double)plan->nnz * (plan->ldu / 4) * T + 1), h[1], (double)h[2] / T);
+            if (h[6] && getenv("GLB_POISSON_WSTATS_FILE")) {           // experiment build only (d_stats is never allocated otherwise)
+                const size_t nrec = (size_t)plan->grid * (plan->threads / 32) * 3;
+                std::vector<unsigned long long> rec(nrec);
+                GLB_CUDA(cudaMemcpy(rec.data(), plan->d_stats + 16, nrec * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+                if (FILE *f = fopen(getenv("GLB_POISSON_WSTATS_FILE"), "w")) {
+                    fprintf(f, "# T=%d grid=%d warps=%d: cta warp busy_cycles pairs slots\n", T, plan->grid, plan->threads / 32);
+                    for (size_t i = 0; i < nrec / 3; ++i)
+                        fprintf(f, "%zu %zu %llu %llu %llu\n", i / (plan->threads / 32), i % (plan->threads / 32), rec[3 * i], rec[3 * i + 1], rec[3 * i + 2]);
+                    fclose(f);
+                }
+            }
+            if (h[6])
+                fprintf(stderr, "[glb]   busy cycles per iteration: mean over warps %.0f, slowest warp %.0f, slowest CTA (mean of its warps) %.0f, "
+                                "mean over CTAs of the CTA's slowest warp %.0f\n", (double)h[4] / (double)h[6] / T, (double)h[5] / T, (double)h[7] / T,
+                        (double)h[8] / (double)plan->grid / T);
         }
     } else if (plan->kind == GLB_POISSON_KIND_BARRIER) {
         GLB_CUDA(cudaMemsetAsync(plan->d_counter, 0, sizeof(unsigned) * kFlagStride * plan->grid, st));
