@@ -136,11 +136,10 @@ __device__ __forceinline__ void slab_consume(const float (&val)[2], const float4
     }
 }
 
-#ifndef GLB_SLAB_MINB
-#define GLB_SLAB_MINB 3                          // resident CTAs per SM the register budget is cut for
-#endif
+// 3 resident CTAs per SM (80 registers): with 4 the kernel spills and runs at half the speed; an L2 run-ahead prefetch of
+// a tile's label rows costs more LSU slots than it saves latency (0.210 vs 0.173 ms on config 5) - both measured in round 2
 template <int LANES>
-__global__ void __launch_bounds__(kSlabWarps * 32, GLB_SLAB_MINB)
+__global__ void __launch_bounds__(kSlabWarps * 32, 3)
 slab_step_kernel(const SlabParams p)
 {
     constexpr int RPW = 32 / LANES;
