@@ -901,7 +901,8 @@ template <int LANES>
 static const void *dataflow_fn(bool l1_first, int *threads)
 {
 #ifdef GLB_EXPERIMENT
-    // A/B switches of the experiment build: CTA size (512 measured best, profiles/r2_dataflow_pair_stream_ab.txt) and the
+    // A/B switches of the experiment build: CTA size (512 measured best, profiles/r2_dataflow_pair_stream_ab.txt; 256 threads
+    // with the same ring of four pairs: 10.6 us) and the
     // first gather attempt through L1 (on: 6.4 us, off: 6.9-10 us per iteration)
     const int pt = exp_env("GLB_POISSON_THREADS", 512);
     if (pt == 768) { *threads = 768; return l1_first ? (const void *)poisson_dataflow_kernel<LANES, 768, true> : (const void *)poisson_dataflow_kernel<LANES, 768, false>; }
