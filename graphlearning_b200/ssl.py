@@ -7,11 +7,15 @@ Reference errors that were sys.exit(...) strings are ValueError / RuntimeError h
 from __future__ import annotations
 
 import ctypes
+import os
 
 import numpy as np
 from scipy import sparse
 
 from . import _lib, graph, utils
+
+
+results_dir = os.path.join(os.getcwd(), "results")          # ssl.py:129
 
 
 class ssl:
@@ -63,6 +67,55 @@ class ssl:
     def fit_predict(self, train_ind, train_labels, all_labels=None):
         self.fit(train_ind, train_labels, all_labels=all_labels)
         return self.predict()
+
+    def get_accuracy_filename(self):
+        """ssl.py:212-227: `<accuracy_filename>[_classpriors]_accuracy.csv`."""
+        return self.accuracy_filename + ("_classpriors" if self.class_priors is not None else "") + "_accuracy.csv"
+
+    def ssl_trials(self, trainsets, labels, num_cores=1, tag="", save_results=True, overwrite=False, num_trials=-1):
+        """Fit on every training set of a list and record `number of labels, accuracy[, with priors, priors error]` per trial:
+        on the screen and, with save_results, as results/<tag><get_accuracy_filename()> - the file format of the reference's
+        harness (ssl.py:292-396), which its trials_statistics / accuracy tables read.  The reference spreads the trials
+        over `num_cores` joblib workers, each rebuilding the graph state; here the trials run one after the other on the GPU
+        against the device state cached on the graph object (poisson_handle etc.), so `num_cores` is accepted and unused."""
+        import os
+        trainsets = list(trainsets)[:num_trials] if num_trials > 0 else list(trainsets)
+        with_priors = self.class_priors is not None
+        header = "Number of labels,Accuracy" + (",Accuracy with class priors,Class priors error" if with_priors else "")
+        print("\nModel: " + self.name)
+        outfile = None
+        if save_results:
+            os.makedirs(results_dir, exist_ok=True)
+            outfile = os.path.join(results_dir, tag + self.get_accuracy_filename())
+            if os.path.exists(outfile) and not overwrite:
+                print("Aborting: SSL trial (" + self.get_accuracy_filename() + ") already completed , and overwrite is False.")
+                return
+            with open(outfile, "w") as f:
+                f.write(header + "\n")
+            print("Results File: " + outfile)
+        print("\n" + header)
+        for train_ind in trainsets:
+            train_ind = np.asarray(train_ind)
+            pred = self.fit_predict(train_ind, labels[train_ind])
+            acc = ssl_accuracy(pred, labels, train_ind)
+            if with_priors:
+                plain = ssl_accuracy(self.predict(ignore_class_priors=True), labels, train_ind)
+                line = "%d,%.2f,%.2f,%.5f" % (len(train_ind), plain, acc, self.class_priors_error)
+            else:
+                line = "%d,%.2f" % (len(train_ind), acc)
+            print(line)
+            if outfile:
+                with open(outfile, "a+") as f:
+                    f.write(line + "\n")
+
+    def trials_statistics(self, tag=""):
+        """(label counts, mean accuracy, std of accuracy, trials per label count) from the csv of ssl_trials (ssl.py:398-437)."""
+        import os
+        X = np.atleast_2d(np.loadtxt(os.path.join(results_dir, tag + self.get_accuracy_filename()), delimiter=",", skiprows=1))
+        counts = np.unique(X[:, 0])
+        mean = np.array([np.mean(X[X[:, 0] == m, 1:], axis=0) for m in counts])
+        std = np.array([np.std(X[X[:, 0] == m, 1:], axis=0) for m in counts])
+        return counts, mean, std, int(len(X[:, 0]) / len(counts))
 
     def fit(self, train_ind, train_labels, all_labels=None):
         """ssl.py:439-481."""

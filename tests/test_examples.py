@@ -29,6 +29,8 @@ def headless(monkeypatch):
     """matplotlib is not installed: a module whose pyplot accepts every call (the scripts only plot at the end)."""
     class _Anything(types.ModuleType):
         def __getattr__(self, name):
+            if name.startswith("__"):                  # inspect / importlib probe __file__, __path__, ... of every module
+                raise AttributeError(name)
             return lambda *a, **k: None
     mpl, plt = _Anything("matplotlib"), _Anything("matplotlib.pyplot")
     mpl.pyplot = plt
@@ -202,3 +204,44 @@ def test_datasets_and_trainsets_read_the_reference_files(tmp_path, monkeypatch):
     saved = gl.trainsets.generate(labels, rate=1, num_trials=2, dataset="toy", seed=1)
     again = gl.trainsets.load("toy")
     assert all(np.array_equal(a, b) for a, b in zip(saved, again))
+
+
+def test_ssl_trials_harness_writes_the_reference_csv(tmp_path, monkeypatch, oracle_device, moons, capsys):
+    """model.ssl_trials / trials_statistics (reference ssl.py:292-437), the many-fits-on-one-graph caller of the hot path: same
+    csv layout and console lines; the fits themselves go through the CPU stand-ins here (GPU: test_ssl_trials_on_the_device)."""
+    import graphlearning as gl
+    monkeypatch.setattr(gl.ssl, "results_dir", str(tmp_path / "results"))
+    labels = moons["labels"]
+    np.random.seed(3)
+    sets = gl.trainsets.generate(labels, rate=np.array([[2], [4]]), num_trials=3)
+    m = gl.ssl.laplace(moons.csr("W"))
+    m.ssl_trials(sets, labels, num_cores=4, tag="t_")
+    out = capsys.readouterr().out
+    assert "Model: Laplace Learning" in out and "Number of labels,Accuracy" in out
+    path = tmp_path / "results" / "t__laplace_accuracy.csv"
+    rows = path.read_text().strip().splitlines()
+    assert rows[0] == "Number of labels,Accuracy" and len(rows) == 1 + len(sets)
+    assert all(int(r.split(",")[0]) in (4, 8) and 50.0 < float(r.split(",")[1]) <= 100.0 for r in rows[1:])
+    counts, mean, std, ntr = m.trials_statistics(tag="t_")
+    assert list(counts) == [4, 8] and ntr == 3 and mean.shape == (2, 1)
+    m.ssl_trials(sets, labels, tag="t_")                                  # existing file, overwrite=False: aborts
+    assert "Aborting" in capsys.readouterr().out and len(path.read_text().strip().splitlines()) == 1 + len(sets)
+    mp = gl.ssl.laplace(moons.csr("W"), class_priors=gl.utils.class_priors(labels))
+    monkeypatch.setattr(type(mp), "volume_label_projection", lambda self: None)       # device kernel: not on CPU
+    mp.ssl_trials(sets, labels, save_results=False, num_trials=2)
+    lines = [l for l in capsys.readouterr().out.splitlines() if l[:1].isdigit()]
+    assert len(lines) == 2 and all(len(l.split(",")) == 4 for l in lines)
+    assert mp.get_accuracy_filename() == "_laplace_classpriors_accuracy.csv"
+
+
+@pytest.mark.gpu
+def test_ssl_trials_on_the_device(tmp_path, monkeypatch, moons):
+    import graphlearning as gl
+    monkeypatch.setattr(gl.ssl, "results_dir", str(tmp_path / "results"))
+    labels = moons["labels"]
+    np.random.seed(3)
+    sets = gl.trainsets.generate(labels, rate=np.array([[2], [5]]), num_trials=4)
+    for model in (gl.ssl.poisson(moons.csr("W"), solver="gradient_descent"), gl.ssl.laplace(moons.csr("W"), class_priors=gl.utils.class_priors(labels))):
+        model.ssl_trials(sets, labels)
+        counts, mean, std, ntr = model.trials_statistics()
+        assert list(counts) == [4, 10] and ntr == 4 and np.all(mean[:, 0] > 70.0) and mean.shape[1] in (1, 3)
