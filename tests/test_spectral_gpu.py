@@ -128,3 +128,12 @@ def test_70k_top50_eigenpairs_properties(gl):
     assert np.max(np.abs(vecs.T @ vecs - np.eye(50))) < 1e-9
     assert np.all(np.diff(vals) >= -1e-12) and abs(vals[0]) < 1e-10
     assert G.eigen_info["residual"] < 1e-10
+    # ... and that these ARE the 50 lowest: (1) a run with a larger block (k = 64: other start vectors, other filter degrees)
+    # finds the same 50 values below its 51st; (2) deflation - Lanczos (scipy eigsh, smallest algebraic) on L + 2 V V^T, whose
+    # spectrum is that of L with the 50 found values moved to >= 2, must not find anything below lambda_50
+    vals64, _ = gl.graph(W).eigen_decomp(normalization="normalized", k=64)
+    assert np.max(np.abs(vals64[:50] - vals)) < 1e-9 and vals64[50] >= vals[49] - 1e-12
+    from scipy.sparse import linalg as splinalg
+    Ld = splinalg.LinearOperator((n, n), matvec=lambda x: L @ x + 2.0 * (vecs @ (vecs.T @ x)), dtype=np.float64)
+    lo = splinalg.eigsh(Ld, k=1, which="SA", tol=1e-4, ncv=40, maxiter=20000, return_eigenvectors=False)[0]
+    assert lo >= vals[49] - 1e-6, (lo, vals[49])
