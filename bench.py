@@ -326,7 +326,7 @@ def cfg5_rowpart(rank, world, full):
     peak = hbm_peak()[0]
     out = {"workload": "cfg5: 2M points uniform in the unit cube, k=10 kNN graph, 10 classes, T=100 iterations per run",
            "n": n, "nnz": int(W.nnz), "n_gpus": world, "graph_build_s": t_graph}
-    put = bench_cfg5.measure(W, rank, world, "put", 1, 100, 3)
+    put = bench_cfg5.measure(W, rank, world, "put", 1, 100, 5)
     out.update({"iterations_per_s": put["iterations_per_s"], "ms_per_iteration": put["ms_per_iteration"],
                 "achieved_GBs_all_gpus": put["bytes_per_iteration"] * put["iterations_per_s"] / 1e9,
                 "frac_of_hbm_peak_per_gpu": put["bytes_per_iteration"] * put["iterations_per_s"] / 1e9 / (peak * world),

@@ -1555,7 +1555,8 @@ extern "C" GLB_API int glb_poisson_iterate(glb_poisson_plan *plan, const float *
             GLB_CUDA(cudaStreamSynchronize(st));
             fprintf(stderr, "[glb] dataflow T=%d grid=%d: re-polls %llu (%.4f per nonzero-lane), polling batches %llu, max warp cycles/iter %.0f\n",
                     T, plan->grid, h[0], (double)h[0] / ((double)plan->nnz * (plan->ldu / 4) * T + 1), h[1], (double)h[2] / T);
-            if (h[6] && getenv("GLB_POISSON_WSTATS_FILE")) {           // experiment build only (d_stats is never allocated otherwise)
+#ifdef GLB_EXPERIMENT
+            if (h[6] && getenv("GLB_POISSON_WSTATS_FILE")) {
                 const size_t nrec = (size_t)plan->grid * (plan->threads / 32) * 3;
                 std::vector<unsigned long long> rec(nrec);
                 GLB_CUDA(cudaMemcpy(rec.data(), plan->d_stats + 16, nrec * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
@@ -1566,6 +1567,7 @@ extern "C" GLB_API int glb_poisson_iterate(glb_poisson_plan *plan, const float *
                     fclose(f);
                 }
             }
+#endif
             if (h[6])
                 fprintf(stderr, "[glb]   busy cycles per iteration: mean over warps %.0f, slowest warp %.0f, slowest CTA (mean of its warps) %.0f, "
                                 "mean over CTAs of the CTA's slowest warp %.0f\n", (double)h[4] / (double)h[6] / T, (double)h[5] / T, (double)h[7] / T,

@@ -64,7 +64,12 @@ double PhaseTimer::now()
     clock_gettime(CLOCK_MONOTONIC, &ts);
     return ts.tv_sec + 1e-9 * ts.tv_nsec;
 }
-PhaseTimer::PhaseTimer(const char *w) : on(getenv("GLB_TIMING") != nullptr), what(w), t0(now()) {}
+static bool phase_timing_enabled()
+{
+    static const bool on = getenv("GLB_TIMING") != nullptr;       // read once per process
+    return on;
+}
+PhaseTimer::PhaseTimer(const char *w) : on(phase_timing_enabled()), what(w), t0(now()) {}
 void PhaseTimer::lap(const char *phase)
 {
     if (!on) return;
