@@ -54,6 +54,15 @@ SIGNATURES = {
     "glb_poisson_graph_destroy": (c_int, [c_void_p]),
     "glb_poisson_graph_fit": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int64, c_int, c_int, c_void_p,
                                       POINTER(c_int), POINTER(c_int)]),
+    "glb_laplace_graph_create": (c_int, [POINTER(c_void_p), c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p,
+                                         c_void_p, c_void_p]),
+    "glb_laplace_graph_fit": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int, c_double, c_void_p, POINTER(c_int64),
+                                      POINTER(c_double), POINTER(c_int), c_void_p]),
+    "glb_laplace_graph_destroy": (c_int, [c_void_p]),
+    "glb_poisson_graph_fit_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_int64, c_int, c_int,
+                                           c_void_p, POINTER(c_int), POINTER(c_int)]),
+    "glb_host_alloc": (c_int, [c_int64, POINTER(c_void_p)]),
+    "glb_host_free": (c_int, [c_void_p]),
     "glb_knn_search": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, POINTER(c_int), POINTER(c_int), c_void_p]),
     "glb_knn_search_host": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, POINTER(c_int), POINTER(c_int)]),
     "glb_cg_work_bytes": (c_int64, [c_int64, c_int]),

@@ -1,6 +1,10 @@
 // api_host.cu - host-buffer entry points of the C-ABI: what the reference's Python binds in place of its own
 // CPU loops.  Inputs and outputs are HOST arrays in the reference's own dtypes (scipy CSR int32/float64,
 // numpy float64); all device memory is allocated, used and freed inside the call.
+#include <string.h>
+#include <algorithm>
+#include <thread>
+#include <utility>
 #include <vector>
 #include "common.cuh"
 
@@ -70,6 +74,17 @@ __global__ void __launch_bounds__(256) scale_by_sum_kernel(double *__restrict__ 
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) v[i] = v[i] / tot;
 }
 
+// source[idx[i], :] = rows[i, :] for the m labelled nodes (idx unique and in range: prepared on the host); the rest of
+// the source term is zero (ssl.py:619-622)
+__global__ void __launch_bounds__(256)
+scatter_source_rows_kernel(const long long *__restrict__ idx, const double *__restrict__ rows, long long m, int c, double *__restrict__ src)
+{
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < m * c; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / c;
+        src[idx[r] * c + (i - r * c)] = rows[i];
+    }
+}
+
 }  // namespace glb
 
 using namespace glb;
@@ -94,6 +109,8 @@ struct glb_poisson_graph {
     double *src64 = nullptr;             // n x c staging (source in, result out)
     float *Db = nullptr, *u0 = nullptr, *u1 = nullptr;
     long long *tind = nullptr;
+    unsigned char *rows_stage = nullptr; // labelled rows of a sparse source: m x (8 + 8c) bytes, indices first
+    int64_t rows_cap = 0;                // bytes
     glb_poisson_plan *plan = nullptr;
     int setup_launches = 0;
     ~glb_poisson_graph() { if (plan) glb_poisson_plan_destroy(plan); }
@@ -114,6 +131,17 @@ extern "C" GLB_API int glb_poisson_graph_create(glb_poisson_graph **out, const i
     }
     cudaStream_t st = 0;
     PhaseTimer tm("graph_create");
+    // Locality ordering (reorder < 0 = auto): host work on the pattern the caller holds, started now so that it runs beside
+    // the upload and the device-side transposition / scaling
+    const bool want = (reorder > 0 || (reorder < 0 && n >= kReorderMinNodes)) && nnz > 0;
+    std::vector<int> h_perm;
+    int order_rc = 0;
+    std::thread order_thread;
+    struct Joiner { std::thread &t; ~Joiner() { if (t.joinable()) t.join(); } } joiner{order_thread};
+    if (want) {
+        h_perm.resize((size_t)n);
+        order_thread = std::thread([&]() { order_rc = glb_locality_order_host(h_rowptr, h_col, n, h_perm.data()); });
+    }
     glb_poisson_graph *g = new glb_poisson_graph();
     struct Guard { glb_poisson_graph *g; ~Guard() { delete g; } } guard{g};
     g->n = n; g->nnz = nnz;
@@ -145,11 +173,9 @@ extern "C" GLB_API int glb_poisson_graph_create(glb_poisson_graph **out, const i
 
     tm.lap("transpose/degree/scale");
     g->it_rp = g->t_rp; g->it_col = g->t_col; g->it_val = g->P_val;
-    // Locality ordering (reorder < 0 = auto)
-    const bool want = reorder > 0 || (reorder < 0 && n >= kReorderMinNodes);
-    if (want && nnz > 0) {
-        std::vector<int> h_perm((size_t)n);
-        if ((rc = glb_locality_order_host(h_rowptr, h_col, n, h_perm.data()))) return rc;
+    if (want) {
+        order_thread.join();
+        if (order_rc) return order_rc;
         int *iperm, *p_rp, *p_col;
         float *p_val;
         GLB_CUDA(g->A.alloc(&g->perm, n));  GLB_CUDA(tmp.alloc(&iperm, n));
@@ -172,11 +198,13 @@ extern "C" GLB_API int glb_poisson_graph_destroy(glb_poisson_graph *g)
     return 0;
 }
 
-extern "C" GLB_API int glb_poisson_graph_fit(glb_poisson_graph *g, const double *h_source, int c, const int64_t *h_train_ind,
-                                             int64_t m, int min_iter, int max_iter, double *h_u_out, int *T_done,
-                                             int *launches)
+// One fit.  The source term is either dense (h_source: n x c) or given by its nonzero rows (h_rows: m_rows x c at the nodes
+// h_row_ind, everything else zero - what ssl.py:619-622 builds: a few hundred bytes instead of n x c x 8 over PCIe).
+static int poisson_graph_fit_impl(glb_poisson_graph *g, const double *h_source, const int64_t *h_row_ind, const double *h_rows,
+                                  int64_t m_rows, int c, const int64_t *h_train_ind, int64_t m, int min_iter, int max_iter,
+                                  double *h_u_out, int *T_done, int *launches)
 {
-    GLB_CHECK_ARG(g && h_source && h_u_out, "null pointer");
+    GLB_CHECK_ARG(g && (h_source || m_rows == 0 || (h_row_ind && h_rows)) && h_u_out, "null pointer");
     GLB_CHECK_ARG(c > 0, "c must be positive");
     GLB_CHECK_ARG(min_iter >= 0 && max_iter >= 0, "iteration counts must be >= 0");
     GLB_CHECK_ARG(m == 0 || h_train_ind, "train_ind is null");
@@ -189,6 +217,7 @@ extern "C" GLB_API int glb_poisson_graph_fit(glb_poisson_graph *g, const double 
         for (void *q : g->Aw.ptrs) dev_free(q);                    // buffers of the previous width (nothing is in flight: fits are synchronous)
         g->Aw.ptrs.clear();
         g->src64 = nullptr; g->Db = g->u0 = g->u1 = nullptr; g->tind = nullptr; g->m_cap = 0;
+        g->rows_stage = nullptr; g->rows_cap = 0;
         if ((rc = glb_poisson_plan_create(&g->plan, g->it_rp, g->it_col, g->it_val, n, nnz, c, GLB_POISSON_KIND_AUTO, st)))
             return rc;
         const int ld = glb_poisson_plan_ld(g->plan);
@@ -203,7 +232,43 @@ extern "C" GLB_API int glb_poisson_graph_fit(glb_poisson_graph *g, const double 
     }
     const int ldu = g->ldu;
     if (m > g->m_cap) { GLB_CUDA(g->Aw.alloc(&g->tind, m)); g->m_cap = m; }
-    GLB_CUDA(cudaMemcpyAsync(g->src64, h_source, n * c * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (h_source) {
+        GLB_CUDA(cudaMemcpyAsync(g->src64, h_source, n * c * sizeof(double), cudaMemcpyHostToDevice, st));
+    } else {
+        // numpy's source[ind] = rows: negative indices count from the end, of a repeated index the LAST row stays
+        std::vector<std::pair<long long, long long>> order((size_t)m_rows);
+        for (int64_t i = 0; i < m_rows; ++i) {
+            long long t = h_row_ind[i];
+            if (t < 0) t += n;
+            GLB_CHECK_ARG(t >= 0 && t < n, "source row index out of range");
+            order[(size_t)i] = {t, (long long)i};
+        }
+        std::sort(order.begin(), order.end());
+        const size_t stride = 8 + 8 * (size_t)c;
+        std::vector<unsigned char> stage((size_t)m_rows * stride + 8);
+        long long *s_idx = reinterpret_cast<long long *>(stage.data());
+        int64_t mu = 0;
+        for (int64_t i = 0; i < m_rows; ++i)
+            if (i + 1 == m_rows || order[(size_t)i + 1].first != order[(size_t)i].first) s_idx[mu++] = order[(size_t)i].second;
+        // s_idx holds positions for now; rows go behind the mu indices
+        double *s_rows = reinterpret_cast<double *>(stage.data() + 8 * (size_t)mu);
+        for (int64_t q = 0; q < mu; ++q) {
+            const long long pos = s_idx[q];
+            memcpy(s_rows + (size_t)q * c, h_rows + (size_t)pos * c, sizeof(double) * (size_t)c);
+            long long t = h_row_ind[pos];
+            s_idx[q] = t < 0 ? t + n : t;
+        }
+        const int64_t bytes = (int64_t)(mu * stride);
+        if (bytes > g->rows_cap) { GLB_CUDA(g->Aw.alloc(&g->rows_stage, (size_t)bytes)); g->rows_cap = bytes; }
+        GLB_CUDA(cudaMemsetAsync(g->src64, 0, n * c * sizeof(double), st));
+        if (mu) {
+            // pageable source: the call returns once the bytes sit in the driver's staging buffer, `stage` may go out of scope
+            GLB_CUDA(cudaMemcpyAsync(g->rows_stage, stage.data(), (size_t)bytes, cudaMemcpyHostToDevice, st));
+            scatter_source_rows_kernel<<<ceil_div(mu * c, 256), 256, 0, st>>>(reinterpret_cast<const long long *>(g->rows_stage),
+                                                                             reinterpret_cast<const double *>(g->rows_stage + 8 * (size_t)mu), mu, c, g->src64);
+            nl += 1;
+        }
+    }
     if ((rc = glb_poisson_pack(g->plan, g->src64, g->deg, g->perm, g->Db, st))) return rc;
     nl += 1;
 
@@ -231,6 +296,37 @@ extern "C" GLB_API int glb_poisson_graph_fit(glb_poisson_graph *g, const double 
     tm.lap("upload + iterate + download");
     if (T_done) *T_done = T;
     if (launches) *launches = nl;
+    return 0;
+}
+
+extern "C" GLB_API int glb_poisson_graph_fit(glb_poisson_graph *g, const double *h_source, int c, const int64_t *h_train_ind,
+                                             int64_t m, int min_iter, int max_iter, double *h_u_out, int *T_done,
+                                             int *launches)
+{
+    GLB_CHECK_ARG(h_source, "null pointer");
+    return poisson_graph_fit_impl(g, h_source, nullptr, nullptr, 0, c, h_train_ind, m, min_iter, max_iter, h_u_out, T_done, launches);
+}
+
+extern "C" GLB_API int glb_poisson_graph_fit_rows(glb_poisson_graph *g, const int64_t *h_row_ind, const double *h_rows,
+                                                  int64_t m_rows, int c, const int64_t *h_train_ind, int64_t m, int min_iter,
+                                                  int max_iter, double *h_u_out, int *T_done, int *launches)
+{
+    GLB_CHECK_ARG(m_rows >= 0, "m_rows must be >= 0");
+    return poisson_graph_fit_impl(g, nullptr, h_row_ind, h_rows, m_rows, c, h_train_ind, m, min_iter, max_iter, h_u_out, T_done,
+                                  launches);
+}
+
+// Page-locked host memory for the callers' result buffers: a device-to-host copy into it runs at PCIe speed and needs no
+// staging copy (a 5.6 MB pageable numpy array costs ~1 ms, this ~0.15 ms).
+extern "C" GLB_API int glb_host_alloc(int64_t bytes, void **h_ptr)
+{
+    GLB_CHECK_ARG(bytes > 0 && h_ptr, "bad argument");
+    GLB_CUDA(cudaHostAlloc(h_ptr, (size_t)bytes, cudaHostAllocDefault));
+    return 0;
+}
+extern "C" GLB_API int glb_host_free(void *h_ptr)
+{
+    if (h_ptr) GLB_CUDA(cudaFreeHost(h_ptr));
     return 0;
 }
 

@@ -252,24 +252,52 @@ extern "C" GLB_API int glb_laplacian_csr_host(const int32_t *h_rowptr, const int
     return 0;
 }
 
-extern "C" GLB_API int glb_laplace_fit_host(const int32_t *h_rowptr, const int32_t *h_col, const double *h_val, int64_t n,
-                                            int64_t nnz, const double *h_left, const double *h_right, const double *h_diag,
-                                            const double *h_tau, const int64_t *h_train_ind, int64_t m, const double *h_F, int c,
-                                            double tol, double *h_u, int64_t *iters, double *err, int *launches, double *h_ms)
+// Device-resident weight matrix and Laplacian scalings of one graph: what every fit on that graph shares (ssl_trials runs
+// hundreds of fits on one W; the reference rebuilds L inside each _fit, ssl.py:1208-1222).
+struct glb_laplace_graph {
+    int64_t n = 0, nnz = 0;
+    LapArena A;
+    LapSpec S{};
+};
+
+extern "C" GLB_API int glb_laplace_graph_create(glb_laplace_graph **out, const int32_t *h_rowptr, const int32_t *h_col,
+                                                const double *h_val, int64_t n, int64_t nnz, const double *h_left,
+                                                const double *h_right, const double *h_diag, const double *h_tau)
 {
-    GLB_CHECK_ARG(h_rowptr && (nnz == 0 || (h_col && h_val)) && h_diag && h_train_ind && h_F && h_u, "null pointer");
+    GLB_CHECK_ARG(out && h_rowptr && (nnz == 0 || (h_col && h_val)) && h_diag, "null pointer");
     GLB_CHECK_ARG(n > 0 && nnz >= 0 && n + nnz < (1ll << 31), "size out of range");
+    int rc;
+    if ((rc = check_gpu("glb_laplace_graph_create"))) return rc;
+    glb_laplace_graph *g = new glb_laplace_graph();
+    g->n = n; g->nnz = nnz;
+    cudaStream_t st = 0;
+    if ((rc = upload_spec(g->A, h_rowptr, h_col, h_val, n, nnz, h_left, h_right, h_diag, h_tau, g->S, st))) { delete g; return rc; }
+    cudaError_t e = cudaStreamSynchronize(st);                // the host arrays are the caller's
+    if (e != cudaSuccess) { delete g; set_error("glb_laplace_graph_create: %s", cudaGetErrorString(e)); return (int)e; }
+    *out = g;
+    return 0;
+}
+
+extern "C" GLB_API int glb_laplace_graph_destroy(glb_laplace_graph *g)
+{
+    delete g;
+    return 0;
+}
+
+extern "C" GLB_API int glb_laplace_graph_fit(glb_laplace_graph *g, const int64_t *h_train_ind, int64_t m, const double *h_F, int c,
+                                             double tol, double *h_u, int64_t *iters, double *err, int *launches, double *h_ms)
+{
+    GLB_CHECK_ARG(g && h_train_ind && h_F && h_u, "null pointer");
+    const int64_t n = g->n, nnz = g->nnz;
     GLB_CHECK_ARG(m > 0 && m < n && c > 0, "need 0 < m < n labelled nodes and c > 0 classes");
     for (int64_t t = 0; t < m; ++t) GLB_CHECK_ARG(h_train_ind[t] >= 0 && h_train_ind[t] < n, "train_ind out of range");
     int rc;
-    if ((rc = check_gpu("glb_laplace_fit_host"))) return rc;
     const int64_t wb = glb_cg_work_bytes(n, c);
-    if (wb < 0) { set_error("glb_laplace_fit_host: unsupported number of classes (c = %d)", c); return (int)wb; }
+    if (wb < 0) { set_error("glb_laplace_graph_fit: unsupported number of classes (c = %d)", c); return (int)wb; }
     cudaStream_t st = 0;
     PhaseTimer tm("laplace_fit");
-    LapArena A;
-    LapSpec S;
-    if ((rc = upload_spec(A, h_rowptr, h_col, h_val, n, nnz, h_left, h_right, h_diag, h_tau, S, st))) return rc;
+    LapArena A;                                              // per-fit scratch (pooled allocations)
+    const LapSpec &S = g->S;
     const int ldb = glb_padded_ld(c);
     long long *train;
     int *lab, *flag, *pos, *counts, *a_rp, *a_col;
@@ -298,7 +326,7 @@ extern "C" GLB_API int glb_laplace_fit_host(const int32_t *h_rowptr, const int32
     sys_fill_kernel<<<blocks, 256, 0, st>>>(S, lab, pos, M, F, c, ldb, a_rp, a_col, a_val, Mb); ++nl;
     GLB_LAUNCH_CHECK();
     GLB_CUDA(cudaStreamSynchronize(st));                     // nu
-    if (nu <= 0) { set_error("glb_laplace_fit_host: every node is labelled"); return GLB_E_INVALID; }
+    if (nu <= 0) { set_error("glb_laplace_graph_fit: every node is labelled"); return GLB_E_INVALID; }
     int a_nnz = 0;
     GLB_CUDA(cudaMemcpy(&a_nnz, a_rp + nu, sizeof(int), cudaMemcpyDeviceToHost));
     tm.lap("upload + system assembly");
@@ -327,4 +355,17 @@ extern "C" GLB_API int glb_laplace_fit_host(const int32_t *h_rowptr, const int32
     if (err) *err = e;
     if (launches) *launches = nl;
     return 0;
+}
+
+extern "C" GLB_API int glb_laplace_fit_host(const int32_t *h_rowptr, const int32_t *h_col, const double *h_val, int64_t n,
+                                            int64_t nnz, const double *h_left, const double *h_right, const double *h_diag,
+                                            const double *h_tau, const int64_t *h_train_ind, int64_t m, const double *h_F, int c,
+                                            double tol, double *h_u, int64_t *iters, double *err, int *launches, double *h_ms)
+{
+    glb_laplace_graph *g = nullptr;
+    int rc = glb_laplace_graph_create(&g, h_rowptr, h_col, h_val, n, nnz, h_left, h_right, h_diag, h_tau);
+    if (rc) return rc;
+    rc = glb_laplace_graph_fit(g, h_train_ind, m, h_F, c, tol, h_u, iters, err, launches, h_ms);
+    glb_laplace_graph_destroy(g);
+    return rc;
 }

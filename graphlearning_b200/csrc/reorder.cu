@@ -55,28 +55,43 @@ using namespace glb;
 // unvisited node.  order[new] = old.
 static void rcm_order(const int *rp, const int *col, int64_t n, std::vector<int> &out)
 {
-    std::vector<int> deg((size_t)n), by_deg((size_t)n), order;
+    // start candidates in (degree, index) order: counting sort, degrees are small integers
+    std::vector<int> deg((size_t)n), by_deg((size_t)n), order((size_t)n);
     std::vector<char> seen((size_t)n, 0);
-    order.reserve((size_t)n);
-    for (int64_t i = 0; i < n; ++i) deg[i] = rp[i + 1] - rp[i];
-    std::iota(by_deg.begin(), by_deg.end(), 0);
-    std::stable_sort(by_deg.begin(), by_deg.end(), [&](int a, int b) { return deg[a] < deg[b]; });
-    std::vector<int> nb;
+    int maxdeg = 0;
+    for (int64_t i = 0; i < n; ++i) { deg[i] = rp[i + 1] - rp[i]; maxdeg = std::max(maxdeg, deg[i]); }
+    {
+        std::vector<int64_t> first((size_t)maxdeg + 2, 0);
+        for (int64_t i = 0; i < n; ++i) first[(size_t)deg[i] + 1]++;
+        for (int d = 0; d <= maxdeg; ++d) first[(size_t)d + 1] += first[(size_t)d];
+        for (int64_t i = 0; i < n; ++i) by_deg[(size_t)first[(size_t)deg[i]]++] = (int)i;
+    }
+    std::vector<unsigned long long> nb;                           // (degree << 32 | node): one integer compare per pair
+    size_t tail = 0;
     for (int64_t s = 0; s < n; ++s) {
         const int start = by_deg[s];
         if (seen[start]) continue;
         seen[start] = 1;
-        size_t head = order.size();
-        order.push_back(start);
-        while (head < order.size()) {
+        size_t head = tail;
+        order[tail++] = start;
+        while (head < tail) {
             const int v = order[head++];
             nb.clear();
             for (int j = rp[v]; j < rp[v + 1]; ++j) {
                 const int w = col[j];
-                if (w >= 0 && w < n && !seen[w]) { seen[w] = 1; nb.push_back(w); }
+                if (w >= 0 && w < n && !seen[w]) { seen[w] = 1; nb.push_back(((unsigned long long)(unsigned)deg[w] << 32) | (unsigned)w); }
             }
-            std::sort(nb.begin(), nb.end(), [&](int a, int b) { return deg[a] != deg[b] ? deg[a] < deg[b] : a < b; });
-            order.insert(order.end(), nb.begin(), nb.end());
+            if (nb.size() <= 24) {                                // the usual case: a handful of new neighbours
+                for (size_t a = 1; a < nb.size(); ++a) {
+                    const unsigned long long key = nb[a];
+                    size_t b = a;
+                    for (; b > 0 && nb[b - 1] > key; --b) nb[b] = nb[b - 1];
+                    nb[b] = key;
+                }
+            } else {
+                std::sort(nb.begin(), nb.end());
+            }
+            for (unsigned long long key : nb) order[tail++] = (int)(unsigned)(key & 0xffffffffull);
         }
     }
     out.resize((size_t)n);

@@ -208,6 +208,46 @@ class PoissonOperator:
         return T.value
 
 
+class _PinnedPool:
+    """Result arrays in page-locked host memory (glb_host_alloc): the download of an n x c score matrix into one runs at
+    PCIe speed, into a fresh pageable numpy array it pays a staging copy and a page fault per 4 KB.  A buffer goes back
+    to the pool when the array (and every view of it) is garbage collected; at most `keep` idle buffers per size stay
+    pinned."""
+
+    def __init__(self, keep=4):
+        self.keep = keep
+        self.idle = {}
+
+    def empty(self, shape, dtype=np.float64):
+        import weakref
+        nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        if nbytes == 0:
+            return np.empty(shape, dtype=dtype)
+        lst = self.idle.get(nbytes)
+        if lst:
+            addr = lst.pop()
+        else:
+            p = ctypes.c_void_p()
+            _lib.call("glb_host_alloc", nbytes, ctypes.byref(p))
+            addr = p.value
+        flat = np.frombuffer((ctypes.c_char * nbytes).from_address(addr), dtype=dtype)
+        weakref.finalize(flat, self._release, nbytes, addr)       # views keep `flat` alive through .base
+        return flat.reshape(shape)
+
+    def _release(self, nbytes, addr):
+        lst = self.idle.setdefault(nbytes, [])
+        if len(lst) < self.keep:
+            lst.append(addr)
+            return
+        try:
+            _lib.load().glb_host_free(ctypes.c_void_p(addr))
+        except Exception:
+            pass
+
+
+pinned = _PinnedPool()
+
+
 class PoissonGraphHandle:
     """Owner of a glb_poisson_graph (include/glb200.h): the device-resident P / RW / degree state of one weight
     matrix, reused by every fit on that graph (the reference rebuilds all of it inside each _fit call)."""
@@ -238,10 +278,59 @@ class PoissonGraphHandle:
                   len(ti), int(min_iter), int(max_iter), ctypes.c_void_p(u.ctypes.data), ctypes.byref(T), ctypes.byref(nl))
         return u, T.value, nl.value
 
+    def fit_rows(self, row_ind, rows, train_ind, min_iter, max_iter):
+        """The same fit with the source term given by its nonzero rows (source = zeros((n, c)); source[row_ind] = rows,
+        ssl.py:619-622): a few hundred bytes go up instead of n x c x 8, the scores come down into pinned memory.
+        -> (u (n,c) float64, T, kernel launches)."""
+        rows = np.ascontiguousarray(rows, dtype=np.float64)
+        ri = np.ascontiguousarray(row_ind, dtype=np.int64).ravel()
+        ti = np.ascontiguousarray(train_ind, dtype=np.int64).ravel()
+        if rows.ndim != 2 or rows.shape[0] != len(ri):
+            raise ValueError("rows must be (len(row_ind), c)")
+        c = rows.shape[1]
+        u = pinned.empty((self.n, c))
+        T, nl = ctypes.c_int(0), ctypes.c_int(0)
+        _lib.call("glb_poisson_graph_fit_rows", self._h, ctypes.c_void_p(ri.ctypes.data), ctypes.c_void_p(rows.ctypes.data),
+                  len(ri), c, ctypes.c_void_p(ti.ctypes.data), len(ti), int(min_iter), int(max_iter),
+                  ctypes.c_void_p(u.ctypes.data), ctypes.byref(T), ctypes.byref(nl))
+        return u, T.value, nl.value
+
     def __del__(self):
         try:
             if self._h:
                 _lib.load().glb_poisson_graph_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+
+class LaplaceGraphHandle:
+    """Owner of a glb_laplace_graph: the weight matrix and the scalings of L = Diag(diag) - Diag(left) W Diag(right) (+ tau)
+    resident in HBM, shared by every Laplace-learning fit on the graph with that normalisation."""
+
+    def __init__(self, rp, ci, val, n, left, right, diag, tau):
+        self.n = int(n)
+        self._h = ctypes.c_void_p()
+        vp = lambda a: ctypes.c_void_p(a.ctypes.data) if a is not None else None
+        _lib.call("glb_laplace_graph_create", ctypes.byref(self._h), vp(rp), vp(ci), vp(val), self.n, len(ci), vp(left), vp(right),
+                  vp(diag), vp(tau))
+
+    def fit(self, train_ind, F, tol):
+        """-> (u (n,c) float64 in pinned memory, CG iterations, err, launches, (cg device ms, system nnz, unknowns))."""
+        ti = np.ascontiguousarray(train_ind, dtype=np.int64)
+        F = np.ascontiguousarray(F, dtype=np.float64)
+        u = pinned.empty((self.n, F.shape[1]))
+        it, err, nl = ctypes.c_int64(0), ctypes.c_double(0.0), ctypes.c_int(0)
+        ms = np.zeros(3)
+        vp = lambda a: ctypes.c_void_p(a.ctypes.data)
+        _lib.call("glb_laplace_graph_fit", self._h, vp(ti), len(ti), vp(F), F.shape[1], float(tol), vp(u), ctypes.byref(it),
+                  ctypes.byref(err), ctypes.byref(nl), vp(ms))
+        return u, it.value, err.value, nl.value, ms
+
+    def __del__(self):
+        try:
+            if self._h:
+                _lib.load().glb_laplace_graph_destroy(self._h)
                 self._h = None
         except Exception:
             pass

@@ -73,6 +73,21 @@ class graph:
             self._device["poisson"] = ent
         return ent[1]
 
+    def laplace_handle(self, normalization, tau):
+        """Device-resident W + Laplacian scalings for ssl.laplace fits on this graph (one per normalisation and tau;
+        rebuilt if weight_matrix is replaced)."""
+        from . import device
+        W = self.weight_matrix
+        tau_key = None if tau is None else tau.tobytes()
+        key = (id(W), W.nnz, id(W.data), normalization, tau_key)
+        ent = self._device.get("laplace")
+        if ent is None or ent[0] != key:
+            left, right, diag = self._laplacian_scalings(normalization)
+            Wc, rp, ci, val = self._canonical_weights()
+            ent = (key, device.LaplaceGraphHandle(rp, ci, val, self.num_nodes, left, right, diag, tau))
+            self._device["laplace"] = ent
+        return ent[1]
+
     def degree_vector(self):
         """graph.py:108-122."""
         return self.weight_matrix * np.ones(self.num_nodes)

@@ -234,17 +234,23 @@ class poisson(ssl):
     def _fit(self, train_ind, train_labels, all_labels=None):
         W = self.graph.weight_matrix
         n = self.graph.num_nodes
-        source, k = self._source(train_ind, train_labels)
-        if self.solver == "gradient_descent":
-            if source.shape[1] != k:
+        if self.solver == "gradient_descent" and all_labels is None:
+            # the source term is zero outside the labelled rows (ssl.py:619-622): only those rows go to the device
+            k = len(np.unique(train_labels))
+            onehot = utils.labels_to_onehot(train_labels, k)
+            if onehot.shape[1] != k:
                 # the reference adds an (n,k) array to an (n,width) one here and fails in numpy broadcasting
                 raise ValueError("train_labels must be 0..k-1 for the gradient_descent solver")
-            if all_labels is not None:
-                return self._fit_gd_verbose(source, train_ind, all_labels)
-            u, T, nl = self.graph.poisson_handle().fit(source, train_ind, self.min_iter, self.max_iter)
+            u, T, nl = self.graph.poisson_handle().fit_rows(train_ind, onehot - np.mean(onehot, axis=0), train_ind,
+                                                            self.min_iter, self.max_iter)
             self.iterations = T
             self.gpu_launches = nl
             return u
+        source, k = self._source(train_ind, train_labels)
+        if self.solver == "gradient_descent":
+            if source.shape[1] != k:
+                raise ValueError("train_labels must be 0..k-1 for the gradient_descent solver")
+            return self._fit_gd_verbose(source, train_ind, all_labels)
         if self.solver == "conjugate_gradient":
             # ssl.py:624-629: u = D^-1/2 conjgrad(L_normalized, D^-1/2 source, tol)
             if source.shape[1] != k:
@@ -425,7 +431,7 @@ class laplace(ssl):
         return u
 
     def _fit_device(self, train_ind, train_labels):
-        """ssl.py:1208-1255 in one call of glb_laplace_fit_host: Laplacian, tau, Dirichlet sub-system, Jacobi scaling, CG and
+        """ssl.py:1208-1255 in one call of glb_laplace_graph_fit: Laplacian, tau, Dirichlet sub-system, Jacobi scaling, CG and
         the scatter of the solution all stay in HBM; the host computes the n values of d^p (numpy, as the reference)."""
         import ctypes
         from . import _lib
@@ -436,18 +442,12 @@ class laplace(ssl):
         n = G.num_nodes
         k = len(np.unique(train_labels))
         F = np.ascontiguousarray(utils.labels_to_onehot(train_labels, k), dtype=np.float64)
-        left, right, diag = G._laplacian_scalings(self.normalization)
-        W, rp, ci, val = G._canonical_weights()
-        tau = np.ascontiguousarray(self.tau, dtype=np.float64) if np.any(self.tau != 0) else None
+        tau = np.ascontiguousarray(np.broadcast_to(self.tau, (n,)), dtype=np.float64) if np.any(self.tau != 0) else None
         ti = np.ascontiguousarray(np.where(train_ind < 0, train_ind + n, train_ind), dtype=np.int64)
-        u = np.empty((n, F.shape[1]), dtype=np.float64)
-        it, err, nl = ctypes.c_int64(0), ctypes.c_double(0.0), ctypes.c_int(0)
-        ms = np.zeros(3)
-        vp = lambda a: ctypes.c_void_p(a.ctypes.data) if a is not None else None
-        _lib.call("glb_laplace_fit_host", vp(rp), vp(ci), vp(val), n, W.nnz, vp(left), vp(right), vp(diag), vp(tau), vp(ti),
-                  len(ti), vp(F), F.shape[1], float(self.tol), vp(u), ctypes.byref(it), ctypes.byref(err), ctypes.byref(nl), vp(ms))
-        self.iterations = it.value
-        self.gpu_launches = nl.value
+        # W and the scalings stay in HBM across the fits on this graph (a reweighted graph is new for every labelled set)
+        u, it, err, nl, ms = G.laplace_handle(self.normalization, tau).fit(ti, F, self.tol)
+        self.iterations = it
+        self.gpu_launches = nl
         self.cg_info = {"device_ms": float(ms[0]), "system_nnz": int(ms[1]), "unknowns": int(ms[2])}
         return u
 

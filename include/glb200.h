@@ -213,7 +213,12 @@ GLB_API int glb_ipc_free(void *d_ptr);
  * glb_poisson_graph_fit runs one fit on that graph: source is the n x c fp64 Poisson source term
  * (ssl.py:619-622), train_ind the m labelled nodes (used by the stopping rule of ssl.py:639-641,667,669
  * when min_iter < max_iter; T = max_iter otherwise), u_out the n x c fp64 scores.  Synchronous.
+ * glb_poisson_graph_fit_rows is the same fit with the source term given by its nonzero rows, exactly as
+ * ssl.py:619-622 builds it (source = zeros((n, c)); source[row_ind] = rows - numpy semantics: negative indices
+ * count from the end, of a repeated index the last row stays): m_rows x c doubles cross PCIe instead of n x c.
  * glb_poisson_gd_host = create + fit + destroy.  T_done / launches may be NULL.
+ * glb_host_alloc / glb_host_free: page-locked host memory for result buffers (h_u_out): the download then runs at
+ * PCIe speed without a staging copy.  Any host pointer is accepted by the entry points; pinned ones are faster.
  * ------------------------------------------------------------------------------------------- */
 typedef struct glb_poisson_graph glb_poisson_graph;
 GLB_API int glb_poisson_graph_create(glb_poisson_graph **graph, const int32_t *h_rowptr, const int32_t *h_col,
@@ -221,6 +226,11 @@ GLB_API int glb_poisson_graph_create(glb_poisson_graph **graph, const int32_t *h
 GLB_API int glb_poisson_graph_destroy(glb_poisson_graph *graph);
 GLB_API int glb_poisson_graph_fit(glb_poisson_graph *graph, const double *h_source, int c, const int64_t *h_train_ind,
                                   int64_t m, int min_iter, int max_iter, double *h_u_out, int *T_done, int *launches);
+GLB_API int glb_poisson_graph_fit_rows(glb_poisson_graph *graph, const int64_t *h_row_ind, const double *h_rows, int64_t m_rows,
+                                       int c, const int64_t *h_train_ind, int64_t m, int min_iter, int max_iter,
+                                       double *h_u_out, int *T_done, int *launches);
+GLB_API int glb_host_alloc(int64_t bytes, void **h_ptr);
+GLB_API int glb_host_free(void *h_ptr);
 GLB_API int glb_poisson_gd_host(const int32_t *h_rowptr, const int32_t *h_col, const double *h_val, int64_t n, int64_t nnz,
                                 const double *h_source, int c, const int64_t *h_train_ind, int64_t m, int min_iter,
                                 int max_iter, double *h_u_out, int *T_done, int *launches);
@@ -250,6 +260,16 @@ GLB_API int glb_laplace_fit_host(const int32_t *h_rowptr, const int32_t *h_col, 
                                  const double *h_left, const double *h_right, const double *h_diag, const double *h_tau,
                                  const int64_t *h_train_ind, int64_t m, const double *h_F, int c, double tol, double *h_u,
                                  int64_t *iters, double *err, int *launches, double *h_ms);
+/* The same fit with the weight matrix and the scalings resident in HBM across fits (ssl_trials: hundreds of fits on one
+ * graph): create uploads W, left/right/diag/tau once, every fit then moves only train_ind, F and the result.
+ * glb_laplace_fit_host = create + fit + destroy. */
+typedef struct glb_laplace_graph glb_laplace_graph;
+GLB_API int glb_laplace_graph_create(glb_laplace_graph **graph, const int32_t *h_rowptr, const int32_t *h_col, const double *h_val,
+                                     int64_t n, int64_t nnz, const double *h_left, const double *h_right, const double *h_diag,
+                                     const double *h_tau);
+GLB_API int glb_laplace_graph_fit(glb_laplace_graph *graph, const int64_t *h_train_ind, int64_t m, const double *h_F, int c,
+                                  double tol, double *h_u, int64_t *iters, double *err, int *launches, double *h_ms);
+GLB_API int glb_laplace_graph_destroy(glb_laplace_graph *graph);
 
 /* ---------------------------------------------------------------------------------------------
  * Conjugate gradient with c right-hand sides.  Replaces utils.conjgrad (graphlearning/utils.py:483-532):

@@ -272,6 +272,28 @@ def test_mixing_T_matches_reference_rule(dev, blobs, moons):
         assert op.mixing_T(ti, 5, 5) == 5
 
 
+def test_mixing_T_beyond_one_grid_pass(dev):
+    """More rows than one pass of the persistent mixing kernel holds in registers (75 776 on 148 SMs), rule deciding at a T
+    that is neither min_iter nor max_iter, min_iter = 0 (err_0 is read), odd batch boundaries."""
+    n = 90000
+    W = random_knn_graph(n, 6, seed=5)
+    ti = np.arange(0, n, 9000)
+    s = orc.poisson_gd_setup(W, ti, np.arange(len(ti)) % 2)
+    v, errs = s["v"], []
+    for _ in range(80):
+        errs.append(np.max(np.absolute(v - s["vinf"])))
+        v = s["RW"] * v
+    def rule(lo, hi):
+        T = 0
+        while (T < lo or errs[T] > 1 / n) and T < hi:
+            T += 1
+        return T
+    assert 2 < rule(0, 80) < 80                       # the rule itself decides on this graph
+    op = dev.PoissonOperator(W)
+    for lo, hi in ((0, 80), (3, 80), (0, 5), (70, 80)):
+        assert op.mixing_T(ti, lo, hi) == rule(lo, hi)
+
+
 # ---- north-star size (70k nodes, k=10, 10 classes) ----------------------------------------------------
 @pytest.fixture(scope="module")
 def big():
@@ -331,3 +353,38 @@ def test_full_size_through_host_api(gl, big):
     margin = (srt[:, -1] - srt[:, -2]) / np.max(np.abs(ref))
     assert np.all((pred == pref) | (margin < 2 * TOL))
     assert np.mean(pred == pref) > 0.999
+
+
+def test_sparse_source_fit_is_the_dense_fit(gl, blobs):
+    """glb_poisson_graph_fit_rows (labelled rows only over PCIe, pinned result) = glb_poisson_graph_fit on the dense source,
+    bit for bit, with numpy's assignment semantics: negative indices, of a repeated index the last row stays."""
+    import gc
+    W = blobs.csr("W")
+    n = W.shape[0]
+    h = gl.graph(W).poisson_handle()
+    rng = np.random.default_rng(3)
+    ti = rng.choice(n, 40, replace=False)
+    ti[5] = ti[30]                                  # repeated node: the row of position 30 must win
+    ti[7] -= n                                      # negative index
+    rows = rng.standard_normal((40, 6))
+    src = np.zeros((n, 6))
+    src[ti] = rows
+    for lo, hi in ((30, 30), (20, 200)):
+        u_dense, T_dense, _ = h.fit(src, ti, lo, hi)
+        u_rows, T_rows, nl = h.fit_rows(ti, rows, ti, lo, hi)
+        assert T_rows == T_dense and nl > 0
+        assert np.array_equal(u_rows, u_dense)
+    # the result lives in page-locked memory that returns to the pool once the array and its views are gone
+    from graphlearning_b200 import device
+    view = u_rows[:, 1]
+    del u_rows
+    gc.collect()
+    idle = sum(len(v) for v in device.pinned.idle.values())
+    assert np.array_equal(view, u_dense[:, 1])
+    del view
+    gc.collect()
+    assert sum(len(v) for v in device.pinned.idle.values()) == idle + 1
+    with pytest.raises(Exception):
+        h.fit_rows(np.array([n]), rows[:1], np.array([0]), 5, 5)      # out of range like numpy's IndexError
+    u0, _, _ = h.fit_rows(np.zeros(0, dtype=np.int64), np.zeros((0, 6)), np.zeros(0, dtype=np.int64), 5, 5)
+    assert np.array_equal(u0, np.zeros((n, 6)))
