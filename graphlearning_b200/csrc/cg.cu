@@ -15,11 +15,12 @@
 // tried first and dropped: on ill-conditioned graphs (two-moons: 1475 iterations of the
 // singular normalised Laplacian in the reference) the fp32 recurrence residual never reaches the reference's
 // tolerance, so neither the iteration count nor the scores can be matched.  A row of c = 10 doubles padded to 16
-// is exactly one 128-byte line, i.e. one L1 wavefront per gathered row - the same count as the fp32 layout.
+// is exactly one 128-byte line; 8 lanes x 16 bytes fetch it with one L1 wavefront - the same count as the fp32 layout.
 //
 // Three kernels per iteration, no host round trip inside a batch of iterations:
-//   cg_spmm_dot      Ap = A p (CSR gather, one lane group per row as in poisson.cu) fused with sum(p*Ap);
-//                    the last CTA to finish folds the per-CTA partials and publishes alpha
+//   cg_spmm_dot      Ap = A p (CSR gather, one lane group per row, 8 gathers per lane in flight; rows of more than 64
+//                    nonzeros as a static list of warp-wide work items) fused with sum(p*Ap); the last CTA to
+//                    finish folds the per-CTA partials and publishes alpha
 //   cg_update        x += alpha p, r -= alpha Ap fused with sum(r*r); the last CTA publishes beta, err,
 //                    records err in the history and raises `done` when err <= tol
 //   cg_direction     p = r + beta p
@@ -27,35 +28,41 @@
 // state back once per batch.  All three are HBM/L2-streaming or gather kernels; algorithmic bytes per
 // iteration (doubled for fp64 values): nnz*12 + (n+1)*4 + 11*n*c*8.
 #include <math.h>
+#include <algorithm>
 #include <vector>
 #include "common.cuh"
 
 namespace glb {
 
-struct __align__(32) real4 { double x, y, z, w; };
-__device__ __forceinline__ real4 ld4(const double *p)            // 32-byte aligned
+// ---- layout ----------------------------------------------------------------------------------------------------------
+// A row of the n x LDU matrices is LDU = LPR x CPL doubles: LPR lanes per row, CPL columns (2, or 4 at LDU = 128) per lane,
+// so that one warp-wide 16-byte load fetches a whole 128-byte row of c = 10 classes with 8 lanes - one L1 wavefront per
+// gathered row (the 4-lane x 32-byte layout of round 1 needed two).  Lanes whose columns are all padding (li * CPL >= c:
+// 3 of 8 at c = 10) neither load nor store: the padding beyond them is never read.
+template <int CPL>
+__device__ __forceinline__ void ldv(const double *p, double (&v)[CPL])       // read-only data of this launch
 {
-    const double2 a = __ldg(reinterpret_cast<const double2 *>(p)), b = __ldg(reinterpret_cast<const double2 *>(p) + 1);
-    real4 v; v.x = a.x; v.y = a.y; v.z = b.x; v.w = b.y;
-    return v;
+#pragma unroll
+    for (int q = 0; q < CPL / 2; ++q) { const double2 t = __ldg(reinterpret_cast<const double2 *>(p) + q); v[2 * q] = t.x; v[2 * q + 1] = t.y; }
 }
-__device__ __forceinline__ real4 ld4_rw(const double *p)         // data written earlier in the same kernel sequence by this thread
+template <int CPL>
+__device__ __forceinline__ void ldv_rw(const double *p, double (&v)[CPL])    // data this thread rewrites
 {
-    const double2 a = reinterpret_cast<const double2 *>(p)[0], b = reinterpret_cast<const double2 *>(p)[1];
-    real4 v; v.x = a.x; v.y = a.y; v.z = b.x; v.w = b.y;
-    return v;
+#pragma unroll
+    for (int q = 0; q < CPL / 2; ++q) { const double2 t = reinterpret_cast<const double2 *>(p)[q]; v[2 * q] = t.x; v[2 * q + 1] = t.y; }
 }
-__device__ __forceinline__ void st4(double *p, const real4 &v)
+template <int CPL>
+__device__ __forceinline__ void stv(double *p, const double (&v)[CPL])
 {
-    reinterpret_cast<double2 *>(p)[0] = make_double2(v.x, v.y);
-    reinterpret_cast<double2 *>(p)[1] = make_double2(v.z, v.w);
+#pragma unroll
+    for (int q = 0; q < CPL / 2; ++q) reinterpret_cast<double2 *>(p)[q] = make_double2(v[2 * q], v[2 * q + 1]);
 }
 
 constexpr int kCgMaxLd = 128;
 constexpr int kCgThreads = 256;
 constexpr int kCgHist = 64;                 // iterations per batch = length of the err history window
-constexpr int kCgLongRow = 64;              // rows with more nonzeros are spread over a whole warp ...
-constexpr int kCgHubRow = 768;              // ... and beyond this over a whole CTA
+constexpr int kCgLongRow = 64;              // rows with more nonzeros are cut into work items of a whole warp ...
+constexpr int kCgItem = 256;                // ... of at most this many nonzeros each
 
 struct CgState {
     double rsold[kCgMaxLd];
@@ -68,22 +75,33 @@ struct CgState {
     unsigned ticket[2];                     // last-CTA tickets of cg_spmm_dot / cg_update
 };
 
+// Work lists of the rows with more than kCgLongRow nonzeros (the hubs of high-dimensional kNN graphs: 2 400 neighbours at
+// d = 512), built on the host once per solve from the row pointers.  Static lists dealt round-robin keep the launch
+// balanced AND the summation order fixed: rows of up to kCgItem nonzeros go to warps (item i to warp i % warps), longer
+// ones to CTAs (row m to CTA m % grid, its rounds of 32 entries dealt over the 8 warps, partial sums folded through
+// shared memory in warp order).  Inside a round the entries are dealt to the warp's lane groups in blocks of LPR.
+struct CgLong {
+    const int4 *items;                      // {row, first entry, last entry + 1, 0}: rows of 65 .. kCgItem nonzeros
+    const int4 *hubs;                       // the same for longer rows
+    int n_items, n_hubs;
+};
+
 // ---- block-level deterministic reduction of per-thread column partials -----------------------------------
-// thread layout: li = threadIdx.x % LANES owns columns [4 li, 4 li + 4); d[0..3] are its fp64 partials.
-// Result: partial[blockIdx.x * ldu + k] for k < ldu.
-template <int LANES>
-__device__ __forceinline__ void block_reduce_columns(double d[4], double *sh, double *partial_out)
+// thread layout: li = threadIdx.x % LPR owns columns [CPL li, CPL li + CPL); d[] are its fp64 partials.
+// Result: partial_out[blockIdx.x * LDU + k] for k < LDU.
+template <int LPR, int CPL>
+__device__ __forceinline__ void block_reduce_columns(double (&d)[CPL], double *sh, double *partial_out)
 {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, li = threadIdx.x % LANES;
+    constexpr int LDU = LPR * CPL;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, li = threadIdx.x % LPR;
 #pragma unroll
-    for (int off = LANES; off < 32; off <<= 1) {
+    for (int off = LPR; off < 32; off <<= 1) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) d[q] += __shfl_xor_sync(0xffffffffu, d[q], off);
+        for (int q = 0; q < CPL; ++q) d[q] += __shfl_xor_sync(0xffffffffu, d[q], off);
     }
-    constexpr int LDU = LANES * 4;
-    if (lane < LANES) {
+    if (lane < LPR) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) sh[warp * LDU + li * 4 + q] = d[q];
+        for (int q = 0; q < CPL; ++q) sh[warp * LDU + li * CPL + q] = d[q];
     }
     __syncthreads();
     if (threadIdx.x < LDU) {
@@ -93,10 +111,8 @@ __device__ __forceinline__ void block_reduce_columns(double d[4], double *sh, do
     }
 }
 
-// The last CTA to arrive folds the per-CTA partials in block order.  Returns true in that CTA with the totals in
-// sh_tot[0..LDU) (valid after the __syncthreads inside).
-template <int LDU>
-__device__ __forceinline__ bool last_block_totals(const double *partial, unsigned *ticket, double *sh, double *sh_tot)
+// Is this the last CTA of the launch to get here?  Everything the other CTAs wrote before is visible to it.
+__device__ __forceinline__ bool last_block(unsigned *ticket)
 {
     __shared__ bool is_last;
     __threadfence();
@@ -104,14 +120,22 @@ __device__ __forceinline__ bool last_block_totals(const double *partial, unsigne
     if (threadIdx.x == 0) {
         const unsigned t = atomicAdd(ticket, 1u);
         is_last = (t == gridDim.x - 1);
+        if (is_last) *ticket = 0u;                          // ready for the next launch
     }
     __syncthreads();
-    if (!is_last) return false;
-    __threadfence();
+    if (is_last) __threadfence();
+    return is_last;
+}
+
+// The last CTA folds the per-CTA partials in block order: totals in sh_tot[0..LDU) (valid after the __syncthreads inside).
+template <int LDU>
+__device__ __forceinline__ void fold_partials(const double *partial, double *sh, double *sh_tot)
+{
     constexpr int NSEG = kCgThreads / LDU;                  // LDU <= 128 -> at least 2 segments
     const int k = threadIdx.x % LDU, seg = threadIdx.x / LDU;
     double s = 0.0;
-    for (unsigned b = seg; b < gridDim.x; b += NSEG) s += __ldcg(partial + (size_t)b * LDU + k);
+#pragma unroll 8
+    for (unsigned b = seg; b < gridDim.x; b += NSEG) s += __ldcg(partial + (size_t)b * LDU + k);   // loads independent, adds in block order
     sh[seg * LDU + k] = s;
     __syncthreads();
     if (threadIdx.x < LDU) {
@@ -120,256 +144,282 @@ __device__ __forceinline__ bool last_block_totals(const double *partial, unsigne
         sh_tot[threadIdx.x] = tot;
     }
     __syncthreads();
-    if (threadIdx.x == 0) *ticket = 0u;                     // ready for the next launch
-    return true;
 }
 
 // ---- K1: Ap = A p, pAp = sum(p * Ap) -> alpha ---------------------------------------------------------------
 // MODE 0: CG iteration (dot with p, publishes alpha).  MODE 1: plain product out = A p (initial residual).
-template <int LANES, int MODE>
-__global__ void __launch_bounds__(kCgThreads)
+// Rows of up to kCgLongRow nonzeros: one lane group per row, RPW = 32 / LPR rows per warp.  The entries of a row are
+// fetched LPR (at least 8) at a time - lane li of the group loads entry li, coalesced - and handed round with shuffles;
+// every lane then has 8 label-row gathers in flight.  acc = fma(a_j, x_j, acc) in stored order.
+template <int LPR, int CPL, int MODE>
+__global__ void __launch_bounds__(kCgThreads, CPL == 2 ? 3 : 1)
 cg_spmm_dot(const int *__restrict__ rowptr, const int *__restrict__ col, const double *__restrict__ val,
-            const double *__restrict__ p, double *__restrict__ Ap, int n, int c, double *partial, CgState *st)
+            const double *__restrict__ p, double *__restrict__ Ap, int n, int c, double *partial, CgState *st, const CgLong L)
 {
-    constexpr int LDU = LANES * 4;
+    constexpr int LDU = LPR * CPL, RPW = 32 / LPR;
+    constexpr int EPL = LPR >= 8 ? 1 : 8 / LPR;                  // entries a lane fetches per round
+    constexpr int E = LPR * EPL;                                 // entries of a row per round: 8, 16 or 32
+    constexpr int SB = LPR < 8 ? LPR : 8;                        // gathers per lane and sub-batch of an item round
     __shared__ double sh[(kCgThreads / 32) * LDU > kCgThreads ? (kCgThreads / 32) * LDU : kCgThreads];
     __shared__ double sh_tot[LDU];
     if (MODE == 0 && st->done) return;
-    const int li = threadIdx.x % LANES;
-    const int rid = (blockIdx.x * kCgThreads + threadIdx.x) / LANES;
-    const int nrid = (gridDim.x * kCgThreads) / LANES;
-    double d[4] = {0.0, 0.0, 0.0, 0.0};
-    for (int row = rid; row < n; row += nrid) {
-        const int beg = __ldg(rowptr + row), end = __ldg(rowptr + row + 1);
-        if (end - beg > kCgLongRow) continue;                         // hub rows: second loop, a whole warp per row
-        real4 acc; acc.x = acc.y = acc.z = acc.w = 0.0;
-        int j = beg;
-        for (; j + 4 <= end; j += 4) {
-            int cj[4]; double a[4]; real4 x[4];
+    const int lane = threadIdx.x & 31, li = lane % LPR, g = lane / LPR;
+    const int wid = (blockIdx.x * kCgThreads + threadIdx.x) >> 5, nw = (gridDim.x * kCgThreads) >> 5;
+    const bool active = li * CPL < c;
+    const double *pl = p + li * CPL;
+    double d[CPL];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) { cj[i] = __ldg(col + j + i); a[i] = __ldg(val + j + i); }
+    for (int k = 0; k < CPL; ++k) d[k] = 0.0;
+    int nbeg = 0, nend = 0;                                      // row pointers of the NEXT visit, fetched one visit ahead
+    if (wid * RPW + g < n) { nbeg = __ldg(rowptr + wid * RPW + g); nend = __ldg(rowptr + wid * RPW + g + 1); }
+    for (int base = wid * RPW; base < n; base += nw * RPW) {
+        const int row = base + g;
+        int beg = nbeg, len = nend - nbeg;
+        bool is_long = false;
+        if (len > kCgLongRow) { is_long = true; len = 0; }      // a work item of the list below
+        {
+            const long long nrow = (long long)row + (long long)nw * RPW;
+            nbeg = nend = 0;
+            if (nrow < n) { nbeg = __ldg(rowptr + nrow); nend = __ldg(rowptr + nrow + 1); }
+        }
+        const int maxlen = __reduce_max_sync(0xffffffffu, len);
+        double acc[CPL];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) x[i] = ld4(p + (size_t)cj[i] * LDU + li * 4);
+        for (int k = 0; k < CPL; ++k) acc[k] = 0.0;
+        // entries of the first round; the next round's entries are fetched while this round's gathers are in flight
+        int cj[EPL];
+        double aj[EPL];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                acc.x = fma(a[i], x[i].x, acc.x); acc.y = fma(a[i], x[i].y, acc.y);
-                acc.z = fma(a[i], x[i].z, acc.z); acc.w = fma(a[i], x[i].w, acc.w);
+        for (int e = 0; e < EPL; ++e) {
+            const int t = e * LPR + li;
+            const bool ok = t < len;
+            cj[e] = ok ? __ldg(col + beg + t) : 0;
+            aj[e] = ok ? __ldg(val + beg + t) : 0.0;
+        }
+        for (int j0 = 0; j0 < maxlen; j0 += E) {
+            int cn[EPL];
+            double an[EPL];
+#pragma unroll
+            for (int e = 0; e < EPL; ++e) {
+                const int t = j0 + E + e * LPR + li;
+                const bool ok = t < len;
+                cn[e] = ok ? __ldg(col + beg + t) : 0;
+                an[e] = ok ? __ldg(val + beg + t) : 0.0;
             }
-        }
-        for (; j < end; ++j) {
-            const double a = __ldg(val + j);
-            const real4 x = ld4(p + (size_t)__ldg(col + j) * LDU + li * 4);
-            acc.x = fma(a, x.x, acc.x); acc.y = fma(a, x.y, acc.y); acc.z = fma(a, x.z, acc.z); acc.w = fma(a, x.w, acc.w);
-        }
-        st4(Ap + (size_t)row * LDU + li * 4, acc);
-        if (MODE == 0) {
-            const real4 pr = ld4(p + (size_t)row * LDU + li * 4);
-            d[0] += pr.x * acc.x; d[1] += pr.y * acc.y; d[2] += pr.z * acc.z; d[3] += pr.w * acc.w;
-        }
-    }
-    // Rows with more than kCgLongRow nonzeros (the hubs of high-dimensional kNN graphs: thousands of neighbours at
-    // d = 512): one lane group walking such a row alone would hold the whole launch.  Every warp looks through its
-    // own contiguous share of the rows (a fixed partition: deterministic) and spreads each long row it finds over
-    // its 32 / LANES lane groups; the partial sums are folded with shuffles in a fixed order.
-    {
-        constexpr int NG = 32 / LANES;
-        const int lane = threadIdx.x & 31, g = lane / LANES;
-        const int gw = (blockIdx.x * kCgThreads + threadIdx.x) >> 5, nwarps = (gridDim.x * kCgThreads) >> 5;
-        const int chunk = (n + nwarps - 1) / nwarps;
-        const int r0 = min(n, gw * chunk), r1 = min(n, r0 + chunk);
-        for (int base = r0; base < r1; base += 32) {
-            const int mine = base + lane;
-            const int mylen = mine < r1 ? __ldg(rowptr + mine + 1) - __ldg(rowptr + mine) : 0;
-            const bool is_long = mylen > kCgLongRow && mylen <= kCgHubRow;
-            unsigned todo = __ballot_sync(0xffffffffu, is_long);
-            while (todo) {
-                const int row = base + __ffs(todo) - 1;
-                todo &= todo - 1;
-                const int beg = __ldg(rowptr + row), end = __ldg(rowptr + row + 1);
-                real4 acc; acc.x = acc.y = acc.z = acc.w = 0.0;
-                int j = beg + g;
-                for (; j + 3 * NG < end; j += 4 * NG) {
-                    int cj[4]; double a[4]; real4 x[4];
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) { cj[i] = __ldg(col + j + i * NG); a[i] = __ldg(val + j + i * NG); }
+            for (int sb = 0; sb < E; sb += 8) {
+                if (j0 + sb < maxlen) {                              // warp-uniform
+                    int cc[8];
+                    double aa[8], x[8][CPL];
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) x[i] = ld4(p + (size_t)cj[i] * LDU + li * 4);
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        acc.x = fma(a[i], x[i].x, acc.x); acc.y = fma(a[i], x[i].y, acc.y);
-                        acc.z = fma(a[i], x[i].z, acc.z); acc.w = fma(a[i], x[i].w, acc.w);
+                    for (int q = 0; q < 8; ++q) {
+                        const int src = g * LPR + (sb + q) % LPR;
+                        cc[q] = __shfl_sync(0xffffffffu, cj[(sb + q) / LPR], src);
+                        aa[q] = __shfl_sync(0xffffffffu, aj[(sb + q) / LPR], src);
                     }
-                }
-                for (; j < end; j += NG) {
-                    const double a = __ldg(val + j);
-                    const real4 x = ld4(p + (size_t)__ldg(col + j) * LDU + li * 4);
-                    acc.x = fma(a, x.x, acc.x); acc.y = fma(a, x.y, acc.y); acc.z = fma(a, x.z, acc.z); acc.w = fma(a, x.w, acc.w);
-                }
 #pragma unroll
-                for (int off = LANES; off < 32; off <<= 1) {
-                    acc.x += __shfl_xor_sync(0xffffffffu, acc.x, off); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, off);
-                    acc.z += __shfl_xor_sync(0xffffffffu, acc.z, off); acc.w += __shfl_xor_sync(0xffffffffu, acc.w, off);
+                    for (int q = 0; q < 8; ++q)
+                        if (active && j0 + sb + q < len) ldv<CPL>(pl + (size_t)cc[q] * LDU, x[q]);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q)
+                        if (active && j0 + sb + q < len) {
+#pragma unroll
+                            for (int k = 0; k < CPL; ++k) acc[k] = fma(aa[q], x[q][k], acc[k]);
+                        }
                 }
-                if (g == 0) {
-                    st4(Ap + (size_t)row * LDU + li * 4, acc);
-                    if (MODE == 0) {
-                        const real4 pr = ld4(p + (size_t)row * LDU + li * 4);
-                        d[0] += pr.x * acc.x; d[1] += pr.y * acc.y; d[2] += pr.z * acc.z; d[3] += pr.w * acc.w;
-                    }
-                }
+            }
+#pragma unroll
+            for (int e = 0; e < EPL; ++e) { cj[e] = cn[e]; aj[e] = an[e]; }
+        }
+        if (row < n && active && !is_long) {
+            stv<CPL>(Ap + (size_t)row * LDU + li * CPL, acc);
+            if (MODE == 0) {
+                double pr[CPL];
+                ldv<CPL>(pl + (size_t)row * LDU, pr);
+#pragma unroll
+                for (int k = 0; k < CPL; ++k) d[k] += pr[k] * acc[k];
             }
         }
     }
-    // Rows with more than kCgHubRow nonzeros (5 000 neighbours happen at d = 512): the whole CTA takes one such row - 64
-    // lane groups x 4 gathers in flight instead of a warp's 8 x 4 - and folds the partial sums through shared memory
-    // in a fixed order.  Every CTA looks through its own contiguous share of the rows.
-    {
-        constexpr int NGB = kCgThreads / LANES;                        // lane groups of the CTA
-        const int gb = threadIdx.x / LANES, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-        const int chunk = (n + (int)gridDim.x - 1) / (int)gridDim.x;
-        const int r0 = min(n, (int)blockIdx.x * chunk), r1 = min(n, r0 + chunk);
-        for (int base = r0; base < r1; base += kCgThreads) {
-            const int mine = base + threadIdx.x;
-            const bool hub = mine < r1 && __ldg(rowptr + mine + 1) - __ldg(rowptr + mine) > kCgHubRow;
-            if (!__syncthreads_or(hub)) continue;
-            for (int t = 0; t < kCgThreads && base + t < r1; ++t) {
-                const int row = base + t;
-                const int beg = __ldg(rowptr + row), end = __ldg(rowptr + row + 1);
-                if (end - beg <= kCgHubRow) continue;                  // block-uniform
-                real4 acc; acc.x = acc.y = acc.z = acc.w = 0.0;
-                int j = beg + gb;
-                for (; j + 3 * NGB < end; j += 4 * NGB) {
-                    int cj[4]; double a[4]; real4 x[4];
+    // One warp-wide pass over entries [e0, e1) in rounds of 32 (one coalesced load per lane, the next round's entries in
+    // flight beside the gathers), rounds r0, r0 + rstep, ...; group g gathers entries [g LPR, g LPR + LPR) of a round.
+    // Returns with the groups folded: every lane group holds the sum.
+    auto warp_pass = [&](int e0, int e1, int r0, int rstep, double (&acc)[CPL]) {
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) { cj[i] = __ldg(col + j + i * NGB); a[i] = __ldg(val + j + i * NGB); }
+        for (int k = 0; k < CPL; ++k) acc[k] = 0.0;
+        int j0 = e0 + r0 * 32;
+        int cj = j0 + lane < e1 ? __ldg(col + j0 + lane) : 0;
+        double aj = j0 + lane < e1 ? __ldg(val + j0 + lane) : 0.0;
+        for (; j0 < e1; j0 += rstep * 32) {
+            const int jn = j0 + rstep * 32;
+            const bool okn = jn + lane < e1;
+            const int cn = okn ? __ldg(col + jn + lane) : 0;
+            const double an = okn ? __ldg(val + jn + lane) : 0.0;
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) x[i] = ld4(p + (size_t)cj[i] * LDU + li * 4);
+            for (int sb = 0; sb < LPR; sb += SB) {
+                int cc[SB];
+                double aa[SB], x[SB][CPL];
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        acc.x = fma(a[i], x[i].x, acc.x); acc.y = fma(a[i], x[i].y, acc.y);
-                        acc.z = fma(a[i], x[i].z, acc.z); acc.w = fma(a[i], x[i].w, acc.w);
+                for (int q = 0; q < SB; ++q) {
+                    cc[q] = __shfl_sync(0xffffffffu, cj, g * LPR + sb + q);
+                    aa[q] = __shfl_sync(0xffffffffu, aj, g * LPR + sb + q);
+                }
+#pragma unroll
+                for (int q = 0; q < SB; ++q)
+                    if (active && j0 + g * LPR + sb + q < e1) ldv<CPL>(pl + (size_t)cc[q] * LDU, x[q]);
+#pragma unroll
+                for (int q = 0; q < SB; ++q)
+                    if (active && j0 + g * LPR + sb + q < e1) {
+#pragma unroll
+                        for (int k = 0; k < CPL; ++k) acc[k] = fma(aa[q], x[q][k], acc[k]);
                     }
-                }
-                for (; j < end; j += NGB) {
-                    const double a = __ldg(val + j);
-                    const real4 x = ld4(p + (size_t)__ldg(col + j) * LDU + li * 4);
-                    acc.x = fma(a, x.x, acc.x); acc.y = fma(a, x.y, acc.y); acc.z = fma(a, x.z, acc.z); acc.w = fma(a, x.w, acc.w);
-                }
-#pragma unroll
-                for (int off = LANES; off < 32; off <<= 1) {
-                    acc.x += __shfl_xor_sync(0xffffffffu, acc.x, off); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, off);
-                    acc.z += __shfl_xor_sync(0xffffffffu, acc.z, off); acc.w += __shfl_xor_sync(0xffffffffu, acc.w, off);
-                }
-                __syncthreads();                                       // sh is free (previous hub row / nothing yet)
-                if (lane < LANES) { sh[warp * LDU + li * 4 + 0] = acc.x; sh[warp * LDU + li * 4 + 1] = acc.y; sh[warp * LDU + li * 4 + 2] = acc.z; sh[warp * LDU + li * 4 + 3] = acc.w; }
-                __syncthreads();
-                if (threadIdx.x < LANES) {
-                    real4 tot; tot.x = tot.y = tot.z = tot.w = 0.0;
-                    for (int w = 0; w < kCgThreads / 32; ++w) {
-                        tot.x += sh[w * LDU + li * 4 + 0]; tot.y += sh[w * LDU + li * 4 + 1];
-                        tot.z += sh[w * LDU + li * 4 + 2]; tot.w += sh[w * LDU + li * 4 + 3];
-                    }
-                    st4(Ap + (size_t)row * LDU + li * 4, tot);
-                    if (MODE == 0) {
-                        const real4 pr = ld4(p + (size_t)row * LDU + li * 4);
-                        d[0] += pr.x * tot.x; d[1] += pr.y * tot.y; d[2] += pr.z * tot.z; d[3] += pr.w * tot.w;
-                    }
-                }
             }
-            __syncthreads();
+            cj = cn; aj = an;
+        }
+#pragma unroll
+        for (int off = LPR; off < 32; off <<= 1) {
+#pragma unroll
+            for (int k = 0; k < CPL; ++k) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], off);
+        }
+    };
+    for (int it = wid; it < L.n_items; it += nw) {               // item i belongs to warp i % nw
+        const int4 item = __ldg(L.items + it);
+        double acc[CPL];
+        warp_pass(item.y, item.z, 0, 1, acc);
+        if (g == 0 && active) {
+            stv<CPL>(Ap + (size_t)item.x * LDU + li * CPL, acc);
+            if (MODE == 0) {
+                double pr[CPL];
+                ldv<CPL>(pl + (size_t)item.x * LDU, pr);
+#pragma unroll
+                for (int k = 0; k < CPL; ++k) d[k] += pr[k] * acc[k];
+            }
+        }
+    }
+    for (int m = blockIdx.x; m < L.n_hubs; m += gridDim.x) {     // hub m belongs to CTA m % grid
+        const int4 hub = __ldg(L.hubs + m);
+        const int warp = threadIdx.x >> 5;
+        double acc[CPL];
+        warp_pass(hub.y, hub.z, warp, kCgThreads / 32, acc);
+        __syncthreads();                                         // sh is free (previous hub)
+        if (g == 0) {
+#pragma unroll
+            for (int k = 0; k < CPL; ++k) sh[warp * LDU + li * CPL + k] = active ? acc[k] : 0.0;
+        }
+        __syncthreads();
+        if (warp == 0 && g == 0 && active) {
+            double tot[CPL];
+#pragma unroll
+            for (int k = 0; k < CPL; ++k) {
+                tot[k] = 0.0;
+                for (int w = 0; w < kCgThreads / 32; ++w) tot[k] += sh[w * LDU + li * CPL + k];
+            }
+            stv<CPL>(Ap + (size_t)hub.x * LDU + li * CPL, tot);
+            if (MODE == 0) {
+                double pr[CPL];
+                ldv<CPL>(pl + (size_t)hub.x * LDU, pr);
+#pragma unroll
+                for (int k = 0; k < CPL; ++k) d[k] += pr[k] * tot[k];
+            }
         }
     }
     if (MODE != 0) return;
     __syncthreads();
-    block_reduce_columns<LANES>(d, sh, partial);
-    if (last_block_totals<LDU>(partial, &st->ticket[0], sh, sh_tot)) {
-        if (threadIdx.x < LDU) st->alpha[threadIdx.x] = threadIdx.x < c ? st->rsold[threadIdx.x] / sh_tot[threadIdx.x] : 0.0;
-    }
+    block_reduce_columns<LPR, CPL>(d, sh, partial);
+    if (!last_block(&st->ticket[0])) return;
+    fold_partials<LDU>(partial, sh, sh_tot);
+    if (threadIdx.x < LDU) st->alpha[threadIdx.x] = threadIdx.x < c ? st->rsold[threadIdx.x] / sh_tot[threadIdx.x] : 0.0;
 }
 
 // ---- K2: x += alpha p; r -= alpha Ap; rsnew = sum(r*r) -> beta, err, done ----------------------------------
 // INIT: r = b - Ap (Ap = A x0, or r = b when Ap is NULL), p = r, rsold = sum(r*r); no x update.
-template <int LANES, bool INIT>
+template <int LPR, int CPL, bool INIT>
 __global__ void __launch_bounds__(kCgThreads)
 cg_update(double *__restrict__ x, double *__restrict__ r, double *__restrict__ p, const double *__restrict__ Ap,
           const double *__restrict__ b, int n, int c, double tol, double *partial, CgState *st)
 {
-    constexpr int LDU = LANES * 4;
+    constexpr int LDU = LPR * CPL;
     __shared__ double sh[(kCgThreads / 32) * LDU > kCgThreads ? (kCgThreads / 32) * LDU : kCgThreads];
     __shared__ double sh_tot[LDU];
     if (!INIT && st->done) return;
-    const int li = threadIdx.x % LANES;
-    double al[4] = {0.0, 0.0, 0.0, 0.0};
-    if (!INIT) {
+    const int li = threadIdx.x % LPR;
+    const bool active = li * CPL < c;
+    double al[CPL], d[CPL];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) al[q] = st->alpha[li * 4 + q];
-    }
-    double d[4] = {0.0, 0.0, 0.0, 0.0};
-    const long long total = (long long)n * LANES;                     // groups of 4 doubles
-    const long long stride = (long long)gridDim.x * kCgThreads;       // multiple of LANES: li is loop invariant
-    for (long long i = (long long)blockIdx.x * kCgThreads + threadIdx.x; i < total; i += stride) {
-        real4 rv;
-        if (INIT) {
-            rv = ld4(b + i * 4);
-            if (Ap) {
-                const real4 av = ld4(Ap + i * 4);
-                rv.x -= av.x; rv.y -= av.y; rv.z -= av.z; rv.w -= av.w;
+    for (int q = 0; q < CPL; ++q) { al[q] = INIT ? 0.0 : st->alpha[li * CPL + q]; d[q] = 0.0; }
+    const long long total = (long long)n * LPR;                       // groups of CPL doubles
+    const long long stride = (long long)gridDim.x * kCgThreads;       // multiple of LPR: li is loop invariant
+    if (active)
+        for (long long i = (long long)blockIdx.x * kCgThreads + threadIdx.x; i < total; i += stride) {
+            double rv[CPL];
+            if (INIT) {
+                ldv<CPL>(b + i * CPL, rv);
+                if (Ap) {
+                    double av[CPL];
+                    ldv<CPL>(Ap + i * CPL, av);
+#pragma unroll
+                    for (int q = 0; q < CPL; ++q) rv[q] -= av[q];
+                }
+                stv<CPL>(p + i * CPL, rv);
+            } else {
+                double pv[CPL], av[CPL], xv[CPL];
+                ldv_rw<CPL>(p + i * CPL, pv);
+                ldv<CPL>(Ap + i * CPL, av);
+                ldv_rw<CPL>(x + i * CPL, xv);
+                ldv_rw<CPL>(r + i * CPL, rv);
+                // x += alpha*p ; r -= alpha*Ap  (utils.py:525-526; numpy rounds the product, then the sum)
+#pragma unroll
+                for (int q = 0; q < CPL; ++q) { xv[q] += al[q] * pv[q]; rv[q] -= al[q] * av[q]; }
+                stv<CPL>(x + i * CPL, xv);
             }
-            st4(p + i * 4, rv);
-        } else {
-            const real4 pv = ld4_rw(p + i * 4);
-            const real4 av = ld4(Ap + i * 4);
-            real4 xv = ld4_rw(x + i * 4);
-            rv = ld4_rw(r + i * 4);
-            // x += alpha*p ; r -= alpha*Ap  (utils.py:525-526; numpy rounds the product, then the sum)
-            xv.x += al[0] * pv.x; xv.y += al[1] * pv.y; xv.z += al[2] * pv.z; xv.w += al[3] * pv.w;
-            rv.x -= al[0] * av.x; rv.y -= al[1] * av.y; rv.z -= al[2] * av.z; rv.w -= al[3] * av.w;
-            st4(x + i * 4, xv);
+            stv<CPL>(r + i * CPL, rv);
+#pragma unroll
+            for (int q = 0; q < CPL; ++q) d[q] += rv[q] * rv[q];
         }
-        st4(r + i * 4, rv);
-        d[0] += rv.x * rv.x; d[1] += rv.y * rv.y; d[2] += rv.z * rv.z; d[3] += rv.w * rv.w;
-    }
-    block_reduce_columns<LANES>(d, sh, partial);
-    if (last_block_totals<LDU>(partial, &st->ticket[1], sh, sh_tot)) {
-        if (INIT) {
-            if (threadIdx.x < LDU) st->rsold[threadIdx.x] = sh_tot[threadIdx.x];
-        } else {
-            if (threadIdx.x < LDU) {
-                const double rsnew = sh_tot[threadIdx.x], rsold = st->rsold[threadIdx.x];
-                st->beta[threadIdx.x] = threadIdx.x < c ? rsnew / rsold : 0.0;
-                st->rsold[threadIdx.x] = rsnew;
-            }
-            if (threadIdx.x == 0) {
-                double s = 0.0;
-                for (int k = 0; k < c; ++k) s += sh_tot[k];                // np.sum(rsnew), utils.py:528
-                const double err = sqrt(s);
-                const long long it = st->iters + 1;
-                st->iters = it;
-                st->err = err;
-                st->err_hist[(it - 1) % kCgHist] = err;
-                if (!(err > tol)) st->done = 1;                            // loop test `err > tol`; NaN stops too
-            }
+    block_reduce_columns<LPR, CPL>(d, sh, partial);
+    if (!last_block(&st->ticket[1])) return;
+    fold_partials<LDU>(partial, sh, sh_tot);
+    if (INIT) {
+        if (threadIdx.x < LDU) st->rsold[threadIdx.x] = sh_tot[threadIdx.x];
+    } else {
+        if (threadIdx.x < LDU) {
+            const double rsnew = sh_tot[threadIdx.x], rsold = st->rsold[threadIdx.x];
+            st->beta[threadIdx.x] = threadIdx.x < c ? rsnew / rsold : 0.0;
+            st->rsold[threadIdx.x] = rsnew;
+        }
+        if (threadIdx.x == 0) {
+            double s = 0.0;
+            for (int k = 0; k < c; ++k) s += sh_tot[k];                // np.sum(rsnew), utils.py:528
+            const double err = sqrt(s);
+            const long long it = st->iters + 1;
+            st->iters = it;
+            st->err = err;
+            st->err_hist[(it - 1) % kCgHist] = err;
+            if (!(err > tol)) st->done = 1;                            // loop test `err > tol`; NaN stops too
         }
     }
 }
 
 // ---- K3: p = r + beta p -------------------------------------------------------------------------------------
-template <int LANES>
+template <int LPR, int CPL>
 __global__ void __launch_bounds__(kCgThreads)
-cg_direction(const double *__restrict__ r, double *__restrict__ p, int n, const CgState *st)
+cg_direction(const double *__restrict__ r, double *__restrict__ p, int n, int c, const CgState *st)
 {
     if (st->done) return;          // x is final; the reference's last update of p is never used
-    const int li = threadIdx.x % LANES;
-    double be[4];
+    const int li = threadIdx.x % LPR;
+    if (li * CPL >= c) return;     // padding
+    double be[CPL];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) be[q] = st->beta[li * 4 + q];
-    const long long total = (long long)n * LANES;
+    for (int q = 0; q < CPL; ++q) be[q] = st->beta[li * CPL + q];
+    const long long total = (long long)n * LPR;
     const long long stride = (long long)gridDim.x * kCgThreads;
     for (long long i = (long long)blockIdx.x * kCgThreads + threadIdx.x; i < total; i += stride) {
-        const real4 rv = ld4(r + i * 4);
-        real4 pv = ld4_rw(p + i * 4);
-        pv.x = rv.x + be[0] * pv.x; pv.y = rv.y + be[1] * pv.y; pv.z = rv.z + be[2] * pv.z; pv.w = rv.w + be[3] * pv.w;
-        st4(p + i * 4, pv);
+        double rv[CPL], pv[CPL];
+        ldv<CPL>(r + i * CPL, rv);
+        ldv_rw<CPL>(p + i * CPL, pv);
+#pragma unroll
+        for (int q = 0; q < CPL; ++q) pv[q] = rv[q] + be[q] * pv[q];
+        stv<CPL>(p + i * CPL, pv);
     }
 }
 
@@ -403,12 +453,45 @@ static int cg_grid() { return sm_count() * 4; }      // 4 x 256 threads per SM: 
 
 static size_t a256(size_t x) { return (x + 255) & ~(size_t)255; }
 
-template <int LANES>
+// Work lists of the long rows (CgLong), from the row pointers on the host: one download of n + 1 integers per solve.
+struct CgLongPlan {
+    int4 *d_items = nullptr, *d_hubs = nullptr;
+    CgLong L{nullptr, nullptr, 0, 0};
+    ~CgLongPlan() { dev_free(d_items); dev_free(d_hubs); }
+};
+
+static int cg_plan_long_rows(const int *d_rowptr, int64_t n, CgLongPlan &P, cudaStream_t st)
+{
+    std::vector<int> rp((size_t)n + 1);
+    GLB_CUDA(cudaMemcpyAsync(rp.data(), d_rowptr, sizeof(int) * (size_t)(n + 1), cudaMemcpyDeviceToHost, st));
+    GLB_CUDA(cudaStreamSynchronize(st));
+    std::vector<int4> items, hubs;
+    for (int64_t r = 0; r < n; ++r) {
+        const int beg = rp[(size_t)r], len = rp[(size_t)r + 1] - beg;
+        if (len > kCgItem) hubs.push_back(make_int4((int)r, beg, beg + len, 0));
+        else if (len > kCgLongRow) items.push_back(make_int4((int)r, beg, beg + len, 0));
+    }
+    // longest hubs first: CTA m % grid gets hub m, so the big ones are spread before the small ones fill in
+    std::stable_sort(hubs.begin(), hubs.end(), [](const int4 &a, const int4 &b) { return a.z - a.y > b.z - b.y; });
+    if (!items.empty()) {
+        GLB_CUDA(dev_alloc(&P.d_items, sizeof(int4) * items.size()));
+        GLB_CUDA(cudaMemcpyAsync(P.d_items, items.data(), sizeof(int4) * items.size(), cudaMemcpyHostToDevice, st));
+    }
+    if (!hubs.empty()) {
+        GLB_CUDA(dev_alloc(&P.d_hubs, sizeof(int4) * hubs.size()));
+        GLB_CUDA(cudaMemcpyAsync(P.d_hubs, hubs.data(), sizeof(int4) * hubs.size(), cudaMemcpyHostToDevice, st));
+    }
+    GLB_CUDA(cudaStreamSynchronize(st));                     // the staging vectors are locals
+    P.L = CgLong{P.d_items, P.d_hubs, (int)items.size(), (int)hubs.size()};
+    return 0;
+}
+
+template <int LPR, int CPL>
 static int cg_run(const int *rp, const int *col, const double *val, int64_t n, const double *b, const double *x0, int c,
                   double tol, int64_t max_iter, double *x, void *work, int64_t *iters_out, double *err_out, int *launches,
                   cudaStream_t st)
 {
-    constexpr int LDU = LANES * 4;
+    constexpr int LDU = LPR * CPL;
     const int grid = cg_grid();
     unsigned char *w = (unsigned char *)(((uintptr_t)work + 255) & ~(uintptr_t)255);
     const size_t vec = a256((size_t)n * LDU * sizeof(double));
@@ -417,31 +500,42 @@ static int cg_run(const int *rp, const int *col, const double *val, int64_t n, c
     double *Ap = (double *)w; w += vec;
     double *partial = (double *)w; w += a256((size_t)grid * LDU * sizeof(double));
     CgState *state = (CgState *)w;
+    CgLongPlan plan;
+    int rc = cg_plan_long_rows(rp, n, plan, st);
+    if (rc) return rc;
+    const CgLong L = plan.L;
+    // K1 holds 8 gathers per lane in registers: fewer resident CTAs than the streaming kernels, and one full wave only
+    int per_sm = 0;
+    GLB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cg_spmm_dot<LPR, CPL, 0>, kCgThreads, 0));
+    const int grid1 = std::max(1, std::min(grid, std::max(1, per_sm) * sm_count()));
     int nl = 0;
     cg_state_init<<<1, 128, 0, st>>>(state); ++nl;
     if (x0) {
         GLB_CUDA(cudaMemcpyAsync(x, x0, (size_t)n * LDU * sizeof(double), cudaMemcpyDeviceToDevice, st));
-        cg_spmm_dot<LANES, 1><<<grid, kCgThreads, 0, st>>>(rp, col, val, x, Ap, (int)n, c, partial, state); ++nl;
-        cg_update<LANES, true><<<grid, kCgThreads, 0, st>>>(x, r, p, Ap, b, (int)n, c, tol, partial, state); ++nl;
+        cg_spmm_dot<LPR, CPL, 1><<<grid1, kCgThreads, 0, st>>>(rp, col, val, x, Ap, (int)n, c, partial, state, L); ++nl;
+        cg_update<LPR, CPL, true><<<grid, kCgThreads, 0, st>>>(x, r, p, Ap, b, (int)n, c, tol, partial, state); ++nl;
     } else {
         GLB_CUDA(cudaMemsetAsync(x, 0, (size_t)n * LDU * sizeof(double), st));
-        cg_update<LANES, true><<<grid, kCgThreads, 0, st>>>(x, r, p, nullptr, b, (int)n, c, tol, partial, state); ++nl;
+        cg_update<LPR, CPL, true><<<grid, kCgThreads, 0, st>>>(x, r, p, nullptr, b, (int)n, c, tol, partial, state); ++nl;
     }
     GLB_LAUNCH_CHECK();
     CgState h;
     int64_t enq = 0;                       // iterations enqueued so far
     h.done = 0; h.iters = 0; h.err = 1.0;
     // the reference's loop test is evaluated before every iteration with err initialised to 1 (utils.py:519-521)
-    if (!(1.0 > tol) || max_iter <= 0) { if (iters_out) *iters_out = 0; if (err_out) *err_out = 1.0; if (launches) *launches += nl; return 0; }
+    if (!(1.0 > tol) || max_iter <= 0) {
+        GLB_CUDA(cudaStreamSynchronize(st));                 // the work list is freed on return
+        if (iters_out) *iters_out = 0; if (err_out) *err_out = 1.0; if (launches) *launches += nl; return 0;
+    }
     int64_t ramp = 16;                     // batches of 16, 32, 64, 64, ...: a solve that ends early leaves few idle launches behind
     while (!h.done && enq < max_iter) {
         int64_t batch = max_iter - enq;
         if (batch > ramp) batch = ramp;
         if (ramp < kCgHist) ramp *= 2;
         for (int64_t i = 0; i < batch; ++i) {
-            cg_spmm_dot<LANES, 0><<<grid, kCgThreads, 0, st>>>(rp, col, val, p, Ap, (int)n, c, partial, state);
-            cg_update<LANES, false><<<grid, kCgThreads, 0, st>>>(x, r, p, Ap, b, (int)n, c, tol, partial, state);
-            cg_direction<LANES><<<grid, kCgThreads, 0, st>>>(r, p, (int)n, state);
+            cg_spmm_dot<LPR, CPL, 0><<<grid1, kCgThreads, 0, st>>>(rp, col, val, p, Ap, (int)n, c, partial, state, L);
+            cg_update<LPR, CPL, false><<<grid, kCgThreads, 0, st>>>(x, r, p, Ap, b, (int)n, c, tol, partial, state);
+            cg_direction<LPR, CPL><<<grid, kCgThreads, 0, st>>>(r, p, (int)n, c, state);
         }
         nl += 3 * (int)batch;
         enq += batch;
@@ -480,12 +574,12 @@ extern "C" GLB_API int glb_cg_solve(const int32_t *d_rowptr, const int32_t *d_co
     GLB_CHECK_ARG((double)n * ldu < 2147483648.0 * 4.0, "label matrix too large");
     cudaStream_t st = (cudaStream_t)stream;
     switch (ldu) {
-        case 4: return cg_run<1>(d_rowptr, d_col, d_val, n, d_b, d_x0, c, tol, max_iter, d_x, d_work, iters, err, launches, st);
-        case 8: return cg_run<2>(d_rowptr, d_col, d_val, n, d_b, d_x0, c, tol, max_iter, d_x, d_work, iters, err, launches, st);
-        case 16: return cg_run<4>(d_rowptr, d_col, d_val, n, d_b, d_x0, c, tol, max_iter, d_x, d_work, iters, err, launches, st);
-        case 32: return cg_run<8>(d_rowptr, d_col, d_val, n, d_b, d_x0, c, tol, max_iter, d_x, d_work, iters, err, launches, st);
-        case 64: return cg_run<16>(d_rowptr, d_col, d_val, n, d_b, d_x0, c, tol, max_iter, d_x, d_work, iters, err, launches, st);
-        default: return cg_run<32>(d_rowptr, d_col, d_val, n, d_b, d_x0, c, tol, max_iter, d_x, d_work, iters, err, launches, st);
+        case 4: return cg_run<2, 2>(d_rowptr, d_col, d_val, n, d_b, d_x0, c, tol, max_iter, d_x, d_work, iters, err, launches, st);
+        case 8: return cg_run<4, 2>(d_rowptr, d_col, d_val, n, d_b, d_x0, c, tol, max_iter, d_x, d_work, iters, err, launches, st);
+        case 16: return cg_run<8, 2>(d_rowptr, d_col, d_val, n, d_b, d_x0, c, tol, max_iter, d_x, d_work, iters, err, launches, st);
+        case 32: return cg_run<16, 2>(d_rowptr, d_col, d_val, n, d_b, d_x0, c, tol, max_iter, d_x, d_work, iters, err, launches, st);
+        case 64: return cg_run<32, 2>(d_rowptr, d_col, d_val, n, d_b, d_x0, c, tol, max_iter, d_x, d_work, iters, err, launches, st);
+        default: return cg_run<32, 4>(d_rowptr, d_col, d_val, n, d_b, d_x0, c, tol, max_iter, d_x, d_work, iters, err, launches, st);
     }
 }
 

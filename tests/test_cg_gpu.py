@@ -68,6 +68,33 @@ def test_conjgrad_widths(gl, c):
     assert np.array_equal(x, again)                       # deterministic reductions
 
 
+@pytest.mark.parametrize("c", [2, 10, 40, 128])
+def test_conjgrad_hub_rows(gl, c):
+    """Rows of more than 64 nonzeros are warp-wide work items, beyond 256 several items folded by the last CTA: hubs of
+    65, 256, 257, 700 and 3000 entries next to short and empty-off-diagonal rows; fixed-iteration parity, x0 path
+    (plain product A x0 through the same items), determinism."""
+    rng = np.random.default_rng(100 + c)
+    n = 4000
+    R = sparse.random(n, n, 0.002, format="lil", random_state=c)
+    for row, k in ((3, 65), (500, 256), (501, 257), (1999, 700), (3999, 3000)):
+        cols = rng.choice(n, k, replace=False)
+        R[row, cols] = rng.random(k)
+    R = sparse.csr_matrix(R)
+    S = R + R.T
+    A = sparse.csr_matrix(S + sparse.diags(np.asarray(abs(S).sum(axis=1)).ravel() + 1.0))     # diagonally dominant: SPD
+    assert np.diff(A.indptr).max() > 3000
+    B = rng.normal(size=(n, c))
+    x_ref, it_ref = orc.conjgrad(A, B, tol=1e-8, return_iters=True)
+    x, (it, err, _) = gl.utils.conjgrad(A, B, max_iter=it_ref, tol=0.0, return_info=True)
+    assert it == it_ref
+    assert rel_err(x, x_ref) <= TOL
+    assert np.array_equal(x, gl.utils.conjgrad(A, B, max_iter=it_ref, tol=0.0))
+    x0 = rng.normal(size=(n, c))
+    xw_ref = orc.conjgrad(A, B, x0=x0, max_iter=3, tol=0.0)
+    xw = gl.utils.conjgrad(A, B, x0=x0, max_iter=3, tol=0.0)
+    assert rel_err(xw, xw_ref) <= TOL
+
+
 def test_conjgrad_too_wide_is_an_error(gl):
     A = sparse.identity(10, format="csr")
     with pytest.raises(RuntimeError, match="right-hand sides|unsupported"):
