@@ -134,6 +134,8 @@ def other_rows(W, labels, ti):
         m = gl.ssl.laplace(W)
         t5 = orc.one_per_class(labels, rate=5, seed=0)
         m.fit(t5, labels[t5])
+        from graphlearning_b200 import device as _gdev
+        _gdev.pinned.wait()
         torch.cuda.synchronize(); t0 = time.perf_counter()
         m.fit(t5, labels[t5])
         t = time.perf_counter() - t0
@@ -148,6 +150,7 @@ def other_rows(W, labels, ti):
         t3 = orc.one_per_class(lab3, rate=5, seed=0)
         m3 = gl.ssl.laplace(W3)
         m3.fit(t3, lab3[t3])
+        _gdev.pinned.wait()
         torch.cuda.synchronize(); t0 = time.perf_counter()
         m3.fit(t3, lab3[t3])
         t_fit = time.perf_counter() - t0
@@ -420,6 +423,9 @@ def run_ours(args, rank, world):
     model.fit(ti, labels[ti])                              # first fit on this graph: uploads W, builds P/RW, ordering and plan on the device
     cold_s = time.perf_counter() - t0
     model.fit(ti, labels[ti])
+    from graphlearning_b200 import device as _gdev
+    _gdev.pinned.wait()                                    # steady state: the pool's background thread has pinned the result buffers
+    model.fit(ti, labels[ti])
     barrier()
     t0 = time.perf_counter()
     e2e_steps = max(1, min(args.steps, 5))
@@ -440,6 +446,8 @@ def run_ours(args, rank, world):
     del model2, W2
     # the same call with the reference's defaults (min_iter=50, max_iter=1000: the stopping rule runs on the device too)
     dmodel = gl.ssl.poisson(W, solver="gradient_descent")
+    dmodel.fit(ti, labels[ti])
+    _gdev.pinned.wait()
     dmodel.fit(ti, labels[ti])
     barrier()
     default_ms = []

@@ -210,35 +210,79 @@ class PoissonOperator:
 
 class _PinnedPool:
     """Result arrays in page-locked host memory (glb_host_alloc): the download of an n x c score matrix into one runs at
-    PCIe speed, into a fresh pageable numpy array it pays a staging copy and a page fault per 4 KB.  A buffer goes back
-    to the pool when the array (and every view of it) is garbage collected; at most `keep` idle buffers per size stay
-    pinned."""
+    PCIe speed, into a fresh pageable numpy array it pays a staging copy and a page fault per 4 KB (1 ms for 5.6 MB).
+    Page-locking itself is expensive (3-16 ms for 5.6 MB, profiles/r2_pinned_alloc_probe.txt), so it never happens on the
+    caller's thread: a request that finds no idle buffer of its size gets an ordinary numpy array and starts a background
+    thread that pins two buffers of that size (the result a model still holds + the next one) for the fits to come.  A
+    buffer goes back to the pool when the array (and every view of it) is garbage collected; at most `keep` idle buffers
+    per size stay pinned and at most `cap_bytes` in total."""
 
-    def __init__(self, keep=4):
-        self.keep = keep
-        self.idle = {}
+    def __init__(self, keep=4, cap_bytes=1 << 30):
+        import threading
+        self.keep, self.cap_bytes = keep, cap_bytes
+        self.idle, self.pending, self.total = {}, {}, 0
+        self.lock = threading.Lock()
 
     def empty(self, shape, dtype=np.float64):
         import weakref
         nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
-        if nbytes == 0:
+        addr = None
+        if nbytes:
+            with self.lock:
+                lst = self.idle.get(nbytes)
+                if lst:
+                    addr = lst.pop()
+        if addr is None:
+            if nbytes >= (1 << 16):
+                self._prefetch(nbytes, 2)
             return np.empty(shape, dtype=dtype)
-        lst = self.idle.get(nbytes)
-        if lst:
-            addr = lst.pop()
-        else:
-            p = ctypes.c_void_p()
-            _lib.call("glb_host_alloc", nbytes, ctypes.byref(p))
-            addr = p.value
         flat = np.frombuffer((ctypes.c_char * nbytes).from_address(addr), dtype=dtype)
         weakref.finalize(flat, self._release, nbytes, addr)       # views keep `flat` alive through .base
         return flat.reshape(shape)
 
+    def _prefetch(self, nbytes, count):
+        import threading
+        with self.lock:
+            have = len(self.idle.get(nbytes, ())) + self.pending.get(nbytes, 0)
+            count = min(count - have, (self.cap_bytes - self.total) // nbytes)
+            if count <= 0:
+                return
+            self.pending[nbytes] = self.pending.get(nbytes, 0) + count
+            self.total += count * nbytes
+        dev = _torch().cuda.current_device()
+
+        def work():
+            for _ in range(count):
+                p, ok = ctypes.c_void_p(), False
+                try:
+                    _torch().cuda.set_device(dev)                  # the thread's own current device
+                    ok = _lib.load().glb_host_alloc(ctypes.c_int64(nbytes), ctypes.byref(p)) == 0 and bool(p.value)
+                except Exception:
+                    ok = False
+                with self.lock:
+                    self.pending[nbytes] -= 1
+                    if ok:
+                        self.idle.setdefault(nbytes, []).append(p.value)
+                    else:
+                        self.total -= nbytes
+        threading.Thread(target=work, daemon=True).start()
+
+    def wait(self):
+        """Block until the background allocations are done (tests, benchmarks)."""
+        import time
+        while True:
+            with self.lock:
+                if not any(self.pending.values()):
+                    return
+            time.sleep(0.001)
+
     def _release(self, nbytes, addr):
-        lst = self.idle.setdefault(nbytes, [])
-        if len(lst) < self.keep:
-            lst.append(addr)
-            return
+        with self.lock:
+            lst = self.idle.setdefault(nbytes, [])
+            if len(lst) < self.keep:
+                lst.append(addr)
+                return
+            self.total -= nbytes
         try:
             _lib.load().glb_host_free(ctypes.c_void_p(addr))
         except Exception:

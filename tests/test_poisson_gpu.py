@@ -374,16 +374,22 @@ def test_sparse_source_fit_is_the_dense_fit(gl, blobs):
         u_rows, T_rows, nl = h.fit_rows(ti, rows, ti, lo, hi)
         assert T_rows == T_dense and nl > 0
         assert np.array_equal(u_rows, u_dense)
-    # the result lives in page-locked memory that returns to the pool once the array and its views are gone
+    # results move to page-locked memory once the pool's background thread has pinned buffers of this size; a buffer
+    # returns to the pool when the array and its views are gone
     from graphlearning_b200 import device
-    view = u_rows[:, 1]
-    del u_rows
+    count = lambda: sum(len(v) for v in device.pinned.idle.values())
+    device.pinned.wait()
+    idle = count()
+    assert idle >= 1
+    u_pin, _, _ = h.fit_rows(ti, rows, ti, lo, hi)
+    assert count() == idle - 1 and np.array_equal(u_pin, u_dense)
+    view = u_pin[:, 1]
+    del u_pin
     gc.collect()
-    idle = sum(len(v) for v in device.pinned.idle.values())
-    assert np.array_equal(view, u_dense[:, 1])
+    assert count() == idle - 1 and np.array_equal(view, u_dense[:, 1])
     del view
     gc.collect()
-    assert sum(len(v) for v in device.pinned.idle.values()) == idle + 1
+    assert count() == idle
     with pytest.raises(Exception):
         h.fit_rows(np.array([n]), rows[:1], np.array([0]), 5, 5)      # out of range like numpy's IndexError
     u0, _, _ = h.fit_rows(np.zeros(0, dtype=np.int64), np.zeros((0, 6)), np.zeros(0, dtype=np.int64), 5, 5)
