@@ -350,6 +350,7 @@ cg_update(double *__restrict__ x, double *__restrict__ r, double *__restrict__ p
     const long long total = (long long)n * LPR;                       // groups of CPL doubles
     const long long stride = (long long)gridDim.x * kCgThreads;       // multiple of LPR: li is loop invariant
     if (active)
+#pragma unroll 2
         for (long long i = (long long)blockIdx.x * kCgThreads + threadIdx.x; i < total; i += stride) {
             double rv[CPL];
             if (INIT) {
@@ -413,6 +414,7 @@ cg_direction(const double *__restrict__ r, double *__restrict__ p, int n, int c,
     for (int q = 0; q < CPL; ++q) be[q] = st->beta[li * CPL + q];
     const long long total = (long long)n * LPR;
     const long long stride = (long long)gridDim.x * kCgThreads;
+#pragma unroll 4
     for (long long i = (long long)blockIdx.x * kCgThreads + threadIdx.x; i < total; i += stride) {
         double rv[CPL], pv[CPL];
         ldv<CPL>(r + i * CPL, rv);
