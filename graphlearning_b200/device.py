@@ -267,13 +267,17 @@ class _PinnedPool:
                         self.total -= nbytes
         threading.Thread(target=work, daemon=True).start()
 
-    def wait(self):
-        """Block until the background allocations are done (tests, benchmarks)."""
+    def wait(self, timeout=None):
+        """Block until the background allocations are done (tests, benchmarks; at interpreter exit with a timeout, so that
+        no thread is inside the driver when CUDA is torn down)."""
         import time
+        t0 = time.monotonic()
         while True:
             with self.lock:
                 if not any(self.pending.values()):
                     return
+            if timeout is not None and time.monotonic() - t0 > timeout:
+                return
             time.sleep(0.001)
 
     def _release(self, nbytes, addr):
@@ -290,6 +294,8 @@ class _PinnedPool:
 
 
 pinned = _PinnedPool()
+import atexit
+atexit.register(pinned.wait, 5.0)
 
 
 class PoissonGraphHandle:

@@ -80,6 +80,11 @@ def oracle_device(monkeypatch):
                 u = Db + P * u; v = RW * v; T += 1
             return u, T, 0
 
+        def fit_rows(self, row_ind, rows, train_ind, min_iter, max_iter):
+            source = np.zeros((self.W.shape[0], np.shape(rows)[1]))
+            source[row_ind] = rows                                                               # ssl.py:621-622
+            return self.fit(source, train_ind, min_iter, max_iter)
+
     def laplace_fit_device(self, train_ind, train_labels):
         u, it = orc.laplace_fit(self.graph.weight_matrix, train_ind, train_labels, normalization=self.normalization,
                                 tau=self.tau, tol=self.tol, return_iters=True)
