@@ -32,6 +32,7 @@
 //
 // Arithmetic per row: acc = 0; acc = fma(val_j, u[col_j], acc) in stored order; + Db - the same chain as
 // poisson_step_kernel, so results are bitwise independent of the number of ranks.
+#include <stdlib.h>
 #include <string.h>
 #include <algorithm>
 #include <numeric>
@@ -72,6 +73,7 @@ struct SlabParams {
     int tile_entries;                // capacity of one stream buffer of a CTA, in int4
     int bnd_ctas;                    // CTAs 0 .. bnd_ctas-1 take the boundary tiles first (then their share of the interior tiles)
     int bnd_group_interior;          // interior tiles that belong to that group of CTAs
+    int exp_flags;                   // -DGLB_EXPERIMENT builds: bit 0 = skip the puts (results wrong, cost probe), bit 1 = fence per tile
 };
 
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -185,6 +187,7 @@ slab_step_kernel(const SlabParams p)
     unsigned par0 = 0u, par1 = 0u;                           // phase parity of the two stream buffers' barriers
     if (lane == 0 && tile >= 0) load_tile(tile, 0);
     bool waited = p.wait_epoch == 0u;
+    unsigned bnd_done = 0u;                                  // boundary tiles of this CTA whose puts have not been counted yet
     const char *in = reinterpret_cast<const char *>(p.u_in) + li * 16;
     for (int step = 0; tile >= 0; ++step, buf ^= 1) {
         __syncwarp();
@@ -248,7 +251,11 @@ slab_step_kernel(const SlabParams p)
                         acc.x += b.x; acc.y += b.y; acc.z += b.z; acc.w += b.w;
                     }
                     *reinterpret_cast<float4 *>(reinterpret_cast<char *>(p.u_out) + (size_t)row * ROWB + li * 16) = acc;
+#ifdef GLB_EXPERIMENT
+                    if (boundary && p.send_ptr && !(p.exp_flags & 1)) {
+#else
                     if (boundary && p.send_ptr) {            // put the row into every peer that gathers it
+#endif
                         const long long q0 = p.send_ptr[(size_t)s * RPW + g], q1 = p.send_ptr[(size_t)s * RPW + g + 1];
                         for (long long k = q0; k < q1; ++k) {
                             const int2 e = p.send_ent[k];
@@ -278,15 +285,26 @@ slab_step_kernel(const SlabParams p)
 #undef GLB_SLAB_STEP
         }
         if (boundary && p.nbr_mask) {
-            __syncthreads();                                 // every put of this tile is issued ...
-            if (threadIdx.x == 0) {
-                __threadfence_system();                      // ... and ordered before the count
-                const unsigned done = atomicAdd(p.bnd_counter, 1u) + 1u;
-                if (done == p.bnd_target) {                  // last boundary tile of this launch: release the neighbours
-                    __threadfence_system();
-                    for (int r = 0; r < kMaxPeers; ++r)
-                        if ((p.nbr_mask >> r) & 1u) st_release_sys(p.peer_flag[r], p.signal_epoch);
+            // The puts of this CTA's boundary tiles are counted ONCE, after its last boundary tile: a system-scope fence
+            // waits for the NVLink acknowledgements of everything the CTA has stored to its peers (microseconds), and
+            // one fence per tile put that wait between every two tiles of the boundary phase.
+            ++bnd_done;
+            bool flush = next < 0 || next >= p.n_bnd_tiles;
+#ifdef GLB_EXPERIMENT
+            flush = flush || (p.exp_flags & 2);
+#endif
+            if (flush) {
+                __syncthreads();                             // every put of these tiles is issued ...
+                if (threadIdx.x == 0) {
+                    __threadfence_system();                  // ... and ordered before the count
+                    const unsigned done = atomicAdd(p.bnd_counter, bnd_done) + bnd_done;
+                    if (done == p.bnd_target) {              // last boundary tile of this launch: release the neighbours
+                        __threadfence_system();
+                        for (int r = 0; r < kMaxPeers; ++r)
+                            if ((p.nbr_mask >> r) & 1u) st_release_sys(p.peer_flag[r], p.signal_epoch);
+                    }
                 }
+                bnd_done = 0u;
             }
         }
         tile = next;
@@ -621,6 +639,17 @@ extern "C" GLB_API int glb_slab_iterate(glb_slab *s, const float *d_Db, int T, i
         const long long quota = ((long long)ntiles + G - 1) / G;                 // tiles per CTA
         const long long share = quota * p.bnd_ctas - p.n_bnd_tiles;              // interior tiles of the boundary group
         p.bnd_group_interior = (int)std::max<long long>(0, std::min<long long>(share, ntiles - p.n_bnd_tiles));
+#ifdef GLB_EXPERIMENT
+        if (const char *e = getenv("GLB_SLAB_BND_FRAC")) {                      // share of the CTAs that start on the boundary tiles
+            const double f = atof(e);
+            if (p.n_bnd_tiles > 0 && p.n_bnd_tiles < ntiles && G >= 2) {
+                p.bnd_ctas = std::min(G - (f >= 1.0 ? 0 : 1), std::max(1, (int)(G * f + 0.5)));
+                const long long share2 = quota * p.bnd_ctas - p.n_bnd_tiles;
+                p.bnd_group_interior = (int)std::max<long long>(0, std::min<long long>(share2, ntiles - p.n_bnd_tiles));
+            }
+        }
+        if (const char *e = getenv("GLB_SLAB_EXP")) p.exp_flags = atoi(e);
+#endif
         if (p.bnd_ctas >= G) p.bnd_group_interior = ntiles - p.n_bnd_tiles;     // no interior group: the boundary group does everything
     }
     for (int r = 0; r < s->world; ++r)
