@@ -89,6 +89,7 @@ SIGNATURES = {
     "glb_slab_rows": (c_int64, [c_void_p]),
     "glb_slab_ld": (c_int, [c_void_p]),
     "glb_slab_fill": (c_double, [c_void_p]),
+    "glb_slab_tile_slices": (c_int, [c_void_p]),
     "glb_slab_region_bytes": (c_int64, [c_void_p]),
     "glb_slab_attach": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, ctypes.c_uint32]),
     "glb_slab_buffer": (c_int, [c_void_p, c_int, POINTER(c_void_p)]),

@@ -42,8 +42,12 @@
 namespace glb {
 
 constexpr int kSlabWarps = 8;                    // warps per CTA
-constexpr int kSlabSPW = 2;                      // slices per warp and tile
-constexpr int kSlabSPC = kSlabWarps * kSlabSPW;  // slices per tile (one tile = one pass of a CTA)
+// Slices per warp and tile (one tile = one pass of a CTA = kSlabWarps x spw slices), chosen per slab: a warp's software
+// pipeline drains at every tile boundary, so big tiles pay when there are many of them per CTA (2 M rows on one GPU:
+// 0.174 ms per iteration with 2, 0.159 with 4, 0.230 with 1), small ones keep the static schedule balanced when a rank
+// has only a few tiles per CTA (250 k rows per rank at 8 GPUs).  -DGLB_SLAB_SPW=k in the experiment build forces k.
+constexpr int kSlabSPWSmall = 2, kSlabSPWBig = 4;
+constexpr int kSlabBigTilesPerCta = 8;           // use the big tiles when every CTA still gets at least this many
 constexpr int kSlabWindow = 256;                 // rows are sorted by length inside windows of this many rows
 constexpr int kSlabLong = 64;                    // rows with more nonzeros get a slice of their own (dealt over the lane groups)
 constexpr int kSlabLongBit = 0x40000000;         // slice_rows: this slice holds ONE long row
@@ -70,9 +74,10 @@ struct SlabParams {
     unsigned bnd_target;             // counter value that means "all boundary CTAs of THIS launch are done"
     unsigned *err_flag;              // watchdog
     int nslices, n_bnd_tiles;
-    int tile_entries;                // capacity of one stream buffer of a CTA, in int4
+    int tile_entries;                // capacity of one WARP's region of a stream buffer, in int4
     int bnd_ctas;                    // CTAs 0 .. bnd_ctas-1 take the boundary tiles first (then their share of the interior tiles)
     int bnd_group_interior;          // interior tiles that belong to that group of CTAs
+    int spw;                         // slices per warp and tile
     int exp_flags;                   // -DGLB_EXPERIMENT builds: bit 0 = skip the puts (results wrong, cost probe), bit 1 = fence per tile
 };
 
@@ -150,7 +155,8 @@ slab_step_kernel(const SlabParams p)
     __shared__ uint64_t bars[2][kSlabWarps];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane / LANES, li = lane % LANES;
-    const int ntiles = (p.nslices + kSlabSPC - 1) / kSlabSPC;
+    const int spc = kSlabWarps * p.spw;              // slices per tile
+    const int ntiles = (p.nslices + spc - 1) / spc;
     if (lane == 0) {
         mbar_init(&bars[0][warp], 1);
         mbar_init(&bars[1][warp], 1);
@@ -159,11 +165,13 @@ slab_step_kernel(const SlabParams p)
     __syncwarp();
     // this warp's part of tile `tile`: slices [s0, s1), entries [f0, f1) of the stream; one bulk copy into buffer `buf`
     auto load_tile = [&](int tile, int buf) {
-        const int cta_s0 = min(tile * kSlabSPC, p.nslices);
-        const int s0 = min(cta_s0 + warp * kSlabSPW, p.nslices), s1 = min(s0 + kSlabSPW, p.nslices);
+        const int cta_s0 = min(tile * spc, p.nslices);
+        const int s0 = min(cta_s0 + warp * p.spw, p.nslices), s1 = min(s0 + p.spw, p.nslices);
         const int f0 = p.slice_first[s0], f1 = p.slice_first[s1];
         if (f1 > f0) {
-            int4 *dst = reinterpret_cast<int4 *>(smem) + (size_t)buf * p.tile_entries + (f0 - p.slice_first[cta_s0]);
+            // every warp owns a fixed region of each stream buffer: a warp that runs a tile ahead of its neighbours must not
+            // write its next part over entries a slower warp is still reading (parts of consecutive tiles have different lengths)
+            int4 *dst = reinterpret_cast<int4 *>(smem) + ((size_t)buf * kSlabWarps + warp) * p.tile_entries;
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // the warp's earlier reads of this buffer are done
             mbar_expect_tx(&bars[buf][warp], (unsigned)(f1 - f0) * 16u);
             bulk_g2s(dst, p.ent + f0, (unsigned)(f1 - f0) * 16u, &bars[buf][warp]);
@@ -211,15 +219,15 @@ slab_step_kernel(const SlabParams p)
             __syncthreads();
             waited = true;
         }
-        const int cta_s0 = min(tile * kSlabSPC, p.nslices);
-        const int s0 = min(cta_s0 + warp * kSlabSPW, p.nslices), s1 = min(s0 + kSlabSPW, p.nslices);
+        const int cta_s0 = min(tile * spc, p.nslices);
+        const int s0 = min(cta_s0 + warp * p.spw, p.nslices), s1 = min(s0 + p.spw, p.nslices);
         const int f0 = p.slice_first[s0], f1 = p.slice_first[s1];
         if (s1 > s0) {
             if (f1 > f0) {
                 mbar_wait(&bars[buf][warp], buf ? par1 : par0);
                 if (buf) par1 ^= 1u; else par0 ^= 1u;
             }
-            const int4 *cv0 = reinterpret_cast<const int4 *>(smem) + (size_t)buf * p.tile_entries + (f0 - p.slice_first[cta_s0]) + g;
+            const int4 *cv0 = reinterpret_cast<const int4 *>(smem) + ((size_t)buf * kSlabWarps + warp) * p.tile_entries + g;
             const int n_pairs = (f1 - f0) / RPW;             // pairs of this warp's stream
             float v0[2], v1[2], v2[2], v3[2];
             float4 x0[2], x1[2], x2[2], x3[2];
@@ -349,7 +357,7 @@ using namespace glb;
 struct glb_slab {
     int64_t m = 0, rows_total = 0, nnz = 0;
     int c = 0, ld = 0, lanes = 0, rpw = 0;
-    int nslices = 0, n_bnd_slices = 0, grid = 0, tile_entries = 0;
+    int nslices = 0, n_bnd_slices = 0, grid = 0, tile_entries = 0, spw = 2;
     size_t smem_bytes = 0;
     double fill = 1.0;
     int4 *d_ent = nullptr;
@@ -398,6 +406,16 @@ extern "C" GLB_API int glb_slab_create(glb_slab **out, const int32_t *h_rowptr, 
     cudaStream_t st = (cudaStream_t)stream;
     PhaseTimer tm("slab_create");
 
+    int spw = kSlabSPWSmall;
+    {   // big tiles when the slab has many tiles per CTA and two stream buffers of a big tile leave room for three CTAs per SM
+        const double tiles_big = (double)m / rpw / (kSlabWarps * kSlabSPWBig);
+        const double bytes_big = 2.0 * 1.3 * ((double)nnz / (double)m) * rpw * kSlabWarps * kSlabSPWBig * 8.0;
+        if (tiles_big >= (double)kSlabBigTilesPerCta * 3 * sm_count() && bytes_big <= 72.0 * 1024) spw = kSlabSPWBig;
+#ifdef GLB_SLAB_SPW
+        spw = GLB_SLAB_SPW;
+#endif
+    }
+    const int kSlabSPC = kSlabWarps * spw;                   // slices per tile of THIS slab
     // ---- row order: boundary rows first; inside each group long rows, then windows of rows sorted by length --------------
     struct Slice { int L; int rows[32]; bool is_long; };
     std::vector<Slice> slices;
@@ -424,12 +442,22 @@ extern "C" GLB_API int glb_slab_create(glb_slab **out, const int32_t *h_rowptr, 
             for (size_t k = w0; k < std::min(group.size(), w0 + (size_t)kSlabWindow); ++k)
                 if (h_rowptr[group[k] + 1] - h_rowptr[group[k]] <= kSlabLong) win.push_back(group[k]);
             std::stable_sort(win.begin(), win.end(), [&](int a, int b) { return h_rowptr[a + 1] - h_rowptr[a] > h_rowptr[b + 1] - h_rowptr[b]; });
+            const size_t first_of_window = slices.size();
             for (size_t k0 = 0; k0 < win.size(); k0 += rpw) {
                 Slice sl{};
                 sl.is_long = false;
                 sl.L = h_rowptr[win[k0] + 1] - h_rowptr[win[k0]];
                 for (int q = 0; q < rpw; ++q) sl.rows[q] = k0 + q < win.size() ? win[k0 + q] : -1;
                 slices.push_back(sl);
+            }
+            // The window's slices come out sorted by length.  Fold them - longest, shortest, second longest, second
+            // shortest, ... - so that every run of an even number of slices holds about the same number of entries: the
+            // parts of the warps of a tile are balanced (a warp that always got the longest slices would finish last, and
+            // the longest part sizes every warp's region of the stream buffers).
+            {
+                const size_t cnt = slices.size() - first_of_window;
+                std::vector<Slice> sorted(slices.begin() + first_of_window, slices.end());
+                for (size_t q = 0; q < cnt; ++q) slices[first_of_window + q] = (q & 1) ? sorted[cnt - 1 - q / 2] : sorted[q / 2];
             }
         }
         if (pass == 0) {                                     // boundary slices fill whole tiles
@@ -452,7 +480,7 @@ extern "C" GLB_API int glb_slab_create(glb_slab **out, const int32_t *h_rowptr, 
     const unsigned pad = (unsigned)(rows_total - 1) * rowb;       // the all-zero scratch row
     std::vector<int4> ent((size_t)slice_first[nslices], make_int4((int)pad, 0, (int)pad, 0));
     int2 *e2 = reinterpret_cast<int2 *>(ent.data());
-    size_t max_cta = 0;
+    size_t max_cta = 0;                                      // longest part of one warp, in bytes
     for (int s = 0; s < nslices; ++s) {
         const Slice &sl = slices[s];
         const size_t base = (size_t)slice_first[s] * 2;          // in entries
@@ -478,9 +506,9 @@ extern "C" GLB_API int glb_slab_create(glb_slab **out, const int32_t *h_rowptr, 
                 }
             }
         }
-        if (s % kSlabSPC == kSlabSPC - 1 || s == nslices - 1) {
-            const int c0 = s / kSlabSPC * kSlabSPC;
-            max_cta = std::max(max_cta, (size_t)(slice_first[s + 1] - slice_first[c0]) * 16);
+        if (s % spw == spw - 1 || s == nslices - 1) {            // end of one warp's part of a tile
+            const int w0 = s / spw * spw;
+            max_cta = std::max(max_cta, (size_t)(slice_first[s + 1] - slice_first[w0]) * 16);
         }
     }
     tm.lap("sliced-ELL build");
@@ -508,16 +536,16 @@ extern "C" GLB_API int glb_slab_create(glb_slab **out, const int32_t *h_rowptr, 
     int dev = 0, max_smem = 0;
     GLB_CUDA(cudaGetDevice(&dev));
     cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-    if (2 * max_cta + 1024 > (size_t)max_smem) {
-        set_error("glb_slab_create: a tile's entry stream needs 2 x %zu bytes of shared memory (a row is too long for the slab kernel)", max_cta);
+    if (2 * kSlabWarps * max_cta + 1024 > (size_t)max_smem) {
+        set_error("glb_slab_create: the entry streams of a tile need 2 x %d x %zu bytes of shared memory (a row is too long for the slab kernel)", kSlabWarps, max_cta);
         return GLB_E_UNSUPPORTED;
     }
     glb_slab *s = new glb_slab();
     struct Guard { glb_slab *s; ~Guard() { if (s) glb_slab_destroy(s); } } guard{s};
     s->m = m; s->rows_total = rows_total; s->nnz = nnz; s->c = c; s->ld = ld; s->lanes = lanes; s->rpw = rpw;
-    s->nslices = nslices; s->n_bnd_slices = n_bnd_slices;
+    s->nslices = nslices; s->n_bnd_slices = n_bnd_slices; s->spw = spw;
     s->tile_entries = (int)(std::max<size_t>(max_cta, 16) / 16);
-    s->smem_bytes = 2 * (size_t)s->tile_entries * 16;
+    s->smem_bytes = 2 * (size_t)kSlabWarps * s->tile_entries * 16;
     s->fill = stored ? (double)nnz / (double)stored : 1.0;
     s->fn = slab_pick(lanes);
     GLB_CUDA(cudaFuncSetAttribute(s->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes));
@@ -563,6 +591,7 @@ extern "C" GLB_API int glb_slab_destroy(glb_slab *s)
 extern "C" GLB_API int64_t glb_slab_rows(const glb_slab *s) { return s ? s->rows_total : GLB_E_INVALID; }
 extern "C" GLB_API int glb_slab_ld(const glb_slab *s) { return s ? s->ld : GLB_E_INVALID; }
 extern "C" GLB_API double glb_slab_fill(const glb_slab *s) { return s ? s->fill : 0.0; }
+extern "C" GLB_API int glb_slab_tile_slices(const glb_slab *s) { return s ? kSlabWarps * s->spw : GLB_E_INVALID; }
 extern "C" GLB_API int64_t glb_slab_region_bytes(const glb_slab *s)
 {
     return s ? (int64_t)(kFlagWords * sizeof(unsigned)) + 3 * s->rows_total * s->ld * (int64_t)sizeof(float) : GLB_E_INVALID;
@@ -630,6 +659,8 @@ extern "C" GLB_API int glb_slab_iterate(glb_slab *s, const float *d_Db, int T, i
     p.my_flags = reinterpret_cast<const unsigned *>(s->region[s->rank]);
     p.nbr_mask = s->nbr_mask;
     p.bnd_counter = s->d_sync; p.err_flag = s->d_sync + 1;
+    const int kSlabSPC = kSlabWarps * s->spw;
+    p.spw = s->spw;
     p.nslices = s->nslices; p.n_bnd_tiles = s->n_bnd_slices / kSlabSPC; p.tile_entries = s->tile_entries;
     {   // half of the CTAs start on the boundary tiles (the puts leave in the first half of the launch), the rest on interior
         // tiles; the boundary group then takes as many interior tiles as evens out the number of tiles per CTA

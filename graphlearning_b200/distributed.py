@@ -191,6 +191,7 @@ class PartitionedPoisson:
                   max(p.m, 1) if p.m else 1, len(p.halo), c, vp(p.boundary.ctypes.data) if p.m else None,
                   vp(p.send_ptr.ctypes.data) if p.m else None, vp(send_peer.ctypes.data), vp(send_dst.ctypes.data), gdev.cur_stream())
         self.ld = int(_lib.load().glb_slab_ld(self._slab))
+        self.tile_slices = int(_lib.load().glb_slab_tile_slices(self._slab))
         rows_total = int(_lib.load().glb_slab_rows(self._slab))
         assert rows_total == int(p.rows_total[rank]), (rows_total, p.rows_total)
         # peer-mapped regions

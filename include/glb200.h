@@ -186,6 +186,7 @@ GLB_API int glb_slab_destroy(glb_slab *slab);
 GLB_API int64_t glb_slab_rows(const glb_slab *slab);          /* m + n_halo + 1 */
 GLB_API int glb_slab_ld(const glb_slab *slab);
 GLB_API double glb_slab_fill(const glb_slab *slab);           /* nnz / stored entries of the sliced ELL */
+GLB_API int glb_slab_tile_slices(const glb_slab *slab);       /* slices per tile the library chose for this slab (16 or 32) */
 GLB_API int64_t glb_slab_region_bytes(const glb_slab *slab);
 GLB_API int glb_slab_attach(glb_slab *slab, int rank, int world, void *const *region_base, const int64_t *region_rows,
                             uint32_t neighbour_mask);

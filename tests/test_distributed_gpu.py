@@ -56,6 +56,26 @@ def test_slab_kernel_world_one(reorder, c):
     assert np.array_equal(u2, ref), float(np.abs(u2 - ref).max())
 
 
+def test_slab_kernel_big_tiles():
+    """A slab with many tiles per CTA gets tiles of 32 slices instead of 16 (a million rows on 148 SMs): same arithmetic,
+    bitwise the step kernel's result, and the choice is really taken."""
+    from graphlearning_b200 import distributed as gd
+    n, c = 1000000, 10
+    W = random_knn_graph(n, 5, seed=11)
+    src = np.zeros((n, c))
+    lab = np.random.default_rng(2).choice(n, 200, replace=False)
+    src[lab] = np.random.default_rng(3).normal(size=(200, c))
+    pp = gd.PartitionedPoisson(W, rank=0, world=1, reorder=False, c=c)
+    assert pp.tile_slices == 32
+    u = pp.iterate(src, 6)
+    pp.close()
+    ref = gd.AllGatherPoisson(W, rank=0, world=1, reorder=False).iterate(src, 6)
+    assert np.array_equal(u, ref), float(np.abs(u - ref).max())
+    small = gd.PartitionedPoisson(random_knn_graph(6000, 9, seed=5), rank=0, world=1, reorder=False, c=c)
+    assert small.tile_slices == 16
+    small.close()
+
+
 def test_allgather_baseline_world_one():
     from graphlearning_b200 import device as gdev, distributed as gd
     W = random_knn_graph(6000, 9, seed=4)
