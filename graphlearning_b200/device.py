@@ -234,7 +234,10 @@ class _PinnedPool:
                     addr = lst.pop()
         if addr is None:
             if nbytes >= (1 << 16):
-                self._prefetch(nbytes, 2)
+                try:
+                    self._prefetch(nbytes, 2)
+                except Exception:                                  # the pool is an optimisation: never fail a request over it
+                    pass
             return np.empty(shape, dtype=dtype)
         flat = np.frombuffer((ctypes.c_char * nbytes).from_address(addr), dtype=dtype)
         weakref.finalize(flat, self._release, nbytes, addr)       # views keep `flat` alive through .base

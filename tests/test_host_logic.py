@@ -208,3 +208,67 @@ def test_dataflow_slabs_hold_every_entry_once(c, grid):
     assert r["bad_rows"] == 0
     assert r["err"] < 1e-12
     assert 0.3 < r["fill"] <= 1.0
+
+
+def test_pinned_pool_background_fill_and_recycling(monkeypatch):
+    """device._PinnedPool without a GPU: the allocator and torch are stand-ins.  A miss returns an ordinary array at once and
+    pins two buffers of that size on a background thread; later requests come from the pool; a buffer returns when the array
+    and every view of it are gone; failures of the allocator never fail a request."""
+    import ctypes
+    import gc
+    import types
+    from graphlearning_b200 import device, _lib
+
+    class FakeLib:
+        def __init__(self):
+            self.live, self.fail = {}, False
+
+        def glb_host_alloc(self, nbytes, pp):
+            if self.fail:
+                return 2
+            buf = ctypes.create_string_buffer(nbytes.value)
+            addr = ctypes.addressof(buf)
+            self.live[addr] = buf
+            pp._obj.value = addr
+            return 0
+
+        def glb_host_free(self, p):
+            self.live.pop(p.value, None)
+            return 0
+
+    fake = FakeLib()
+    monkeypatch.setattr(_lib, "load", lambda: fake)
+    cuda = types.SimpleNamespace(current_device=lambda: 0, set_device=lambda d: None)
+    monkeypatch.setattr(device, "_torch", lambda: types.SimpleNamespace(cuda=cuda))
+    pool = device._PinnedPool(keep=2, cap_bytes=10 << 20)
+    shape = (20000, 10)                                         # 1.6 MB
+    a = pool.empty(shape)
+    assert a.shape == shape and a.flags.owndata                 # miss: pageable numpy memory, nothing waited for
+    pool.wait()
+    nbytes = a.nbytes
+    assert len(pool.idle[nbytes]) == 2 and pool.total == 2 * nbytes
+    b = pool.empty(shape); c = pool.empty(shape)
+    assert not b.flags.owndata and not c.flags.owndata and len(pool.idle[nbytes]) == 0
+    b[:] = 3.0
+    view = b[5]
+    del b
+    gc.collect()
+    assert len(pool.idle[nbytes]) == 0 and view[0] == 3.0       # a view keeps the buffer out of the pool
+    del view, c
+    gc.collect()
+    assert len(pool.idle[nbytes]) == 2
+    small = pool.empty((10, 10))
+    assert small.flags.owndata and not any(pool.pending.values()) and 800 not in pool.idle      # below 64 KB nothing is pinned
+    # keep = 2: a third returned buffer is freed, not kept
+    d1, d2 = pool.empty(shape), pool.empty(shape)
+    pool.empty(shape); pool.wait()                              # miss -> two more pinned
+    d3, d4 = pool.empty(shape), pool.empty(shape)
+    del d1, d2, d3, d4
+    gc.collect()
+    assert len(pool.idle[nbytes]) == 2 and pool.total == 2 * nbytes and len(fake.live) == 2
+    # cap and allocator failures
+    big = pool.empty((2000000, 10)); pool.wait()                # 160 MB > cap: never pinned
+    assert big.flags.owndata and 160000000 not in pool.idle
+    fake.fail = True
+    e = pool.empty((30000, 10)); pool.wait()
+    assert e.flags.owndata and pool.total == 2 * nbytes and not pool.idle.get(e.nbytes)
