@@ -5,8 +5,10 @@
 
 One "step" = I iterations (default 1000) of u <- Db + P u on the device-resident graph = ONE launch of the
 persistent kernel.  `value` is whole-job iterations/s with all inputs resident in HBM; `e2e` is the same
-metric through the reference-facing API gl.ssl.poisson(...).fit(...) with HOST buffers (host<->device copies,
-graph normalisation and the result read-back inside the timed region).  N>1: the 70k graph fits one GPU, so
+metric through the reference-facing API gl.ssl.poisson(...).fit(train_ind, train_labels) with HOST buffers: every
+fit uploads the labelled rows of the source term (it is zero elsewhere, ssl.py:619-622) and train_ind, and reads the
+n x c fp64 scores back into host memory (a page-locked array of the library's pool) inside the timed region; the
+graph itself is uploaded and normalised once, in the first fit (`first_fit_ms`).  N>1: the 70k graph fits one GPU, so
 ranks run independent label sets on replicas of the graph (the reference's own ssl_trials parallelism,
 ssl.py:390-396) with no data-path collective - weak scaling.  Timing: CUDA events on the launching stream
 per step, L2 flushed between steps, max over ranks.

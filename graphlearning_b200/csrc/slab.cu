@@ -415,7 +415,7 @@ extern "C" GLB_API int glb_slab_create(glb_slab **out, const int32_t *h_rowptr, 
         spw = GLB_SLAB_SPW;
 #endif
     }
-    const int kSlabSPC = kSlabWarps * spw;                   // slices per tile of THIS slab
+    const int spc = kSlabWarps * spw;                        // slices per tile of THIS slab
     // ---- row order: boundary rows first; inside each group long rows, then windows of rows sorted by length --------------
     struct Slice { int L; int rows[32]; bool is_long; };
     std::vector<Slice> slices;
@@ -461,7 +461,7 @@ extern "C" GLB_API int glb_slab_create(glb_slab **out, const int32_t *h_rowptr, 
             }
         }
         if (pass == 0) {                                     // boundary slices fill whole tiles
-            while (slices.size() % kSlabSPC) {
+            while (slices.size() % spc) {
                 Slice sl{};
                 for (int q = 0; q < rpw; ++q) sl.rows[q] = -1;
                 slices.push_back(sl);
@@ -554,7 +554,7 @@ extern "C" GLB_API int glb_slab_create(glb_slab **out, const int32_t *h_rowptr, 
         cudaFuncSetAttribute(s->fn, cudaFuncAttributePreferredSharedMemoryCarveout, (int)std::min<size_t>(100, (want * 100 + max_smem - 1) / max_smem));
         int per_sm = 0;
         GLB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, s->fn, kSlabWarps * 32, s->smem_bytes));
-        const int ntiles = (nslices + kSlabSPC - 1) / kSlabSPC;
+        const int ntiles = (nslices + spc - 1) / spc;
         s->grid = std::max(1, std::min(ntiles, std::max(1, per_sm) * sm_count()));        // persistent: every CTA walks tiles b, b + grid, ...
     }
     GLB_CUDA(dev_alloc(&s->d_ent, sizeof(int4) * std::max<size_t>(ent.size(), 1)));
@@ -659,12 +659,12 @@ extern "C" GLB_API int glb_slab_iterate(glb_slab *s, const float *d_Db, int T, i
     p.my_flags = reinterpret_cast<const unsigned *>(s->region[s->rank]);
     p.nbr_mask = s->nbr_mask;
     p.bnd_counter = s->d_sync; p.err_flag = s->d_sync + 1;
-    const int kSlabSPC = kSlabWarps * s->spw;
+    const int spc = kSlabWarps * s->spw;
     p.spw = s->spw;
-    p.nslices = s->nslices; p.n_bnd_tiles = s->n_bnd_slices / kSlabSPC; p.tile_entries = s->tile_entries;
+    p.nslices = s->nslices; p.n_bnd_tiles = s->n_bnd_slices / spc; p.tile_entries = s->tile_entries;
     {   // half of the CTAs start on the boundary tiles (the puts leave in the first half of the launch), the rest on interior
         // tiles; the boundary group then takes as many interior tiles as evens out the number of tiles per CTA
-        const int ntiles = (s->nslices + kSlabSPC - 1) / kSlabSPC, G = s->grid;
+        const int ntiles = (s->nslices + spc - 1) / spc, G = s->grid;
         const double bfrac = ntiles ? (double)p.n_bnd_tiles / ntiles : 0.0;
         p.bnd_ctas = p.n_bnd_tiles == 0 ? 0 : (p.n_bnd_tiles >= ntiles || G < 2) ? G : std::min(G - 1, std::max(1, (int)(G * std::max(0.5, bfrac) + 0.5)));
         const long long quota = ((long long)ntiles + G - 1) / G;                 // tiles per CTA
