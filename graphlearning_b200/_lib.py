@@ -88,6 +88,7 @@ SIGNATURES = {
     "glb_slab_destroy": (c_int, [c_void_p]),
     "glb_slab_rows": (c_int64, [c_void_p]),
     "glb_slab_ld": (c_int, [c_void_p]),
+    "glb_slab_check_host": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p, c_int, c_void_p]),
     "glb_slab_fill": (c_double, [c_void_p]),
     "glb_slab_tile_slices": (c_int, [c_void_p]),
     "glb_slab_region_bytes": (c_int64, [c_void_p]),

@@ -32,6 +32,7 @@
 //
 // Arithmetic per row: acc = 0; acc = fma(val_j, u[col_j], acc) in stored order; + Db - the same chain as
 // poisson_step_kernel, so results are bitwise independent of the number of ranks.
+#include <math.h>
 #include <stdlib.h>
 #include <string.h>
 #include <algorithm>
@@ -390,11 +391,23 @@ static const void *slab_pick(int lanes)
     }
 }
 
-extern "C" GLB_API int glb_slab_create(glb_slab **out, const int32_t *h_rowptr, const int32_t *h_col, const float *h_val,
-                                       int64_t m, int64_t n_halo, int c, const uint8_t *h_boundary, const int64_t *h_send_ptr,
-                                       const int32_t *h_send_peer, const int32_t *h_send_dst, void *stream)
+// Everything glb_slab_create builds on the host: the sliced-ELL entry stream in tile / warp / slice order and the puts of
+// the boundary rows.  Pure host code (glb_slab_check_host walks the result without a GPU).
+struct SlabHost {
+    int ld = 0, lanes = 0, rpw = 0, spw = 0, nslices = 0, n_bnd_slices = 0;
+    int64_t rows_total = 0, nnz = 0, stored = 0;
+    size_t max_warp_bytes = 0;                   // longest part of one warp = size of a warp's region of a stream buffer
+    std::vector<int> slice_first, slice_rows;
+    std::vector<int4> ent;
+    std::vector<long long> send_ptr;
+    std::vector<int2> send_ent;
+};
+
+static int slab_build_host(SlabHost &H, const int32_t *h_rowptr, const int32_t *h_col, const float *h_val, int64_t m, int64_t n_halo,
+                           int c, const uint8_t *h_boundary, const int64_t *h_send_ptr, const int32_t *h_send_peer,
+                           const int32_t *h_send_dst, int sms)
 {
-    GLB_CHECK_ARG(out && h_rowptr && m > 0 && n_halo >= 0 && c > 0, "bad argument");
+    GLB_CHECK_ARG(h_rowptr && m > 0 && n_halo >= 0 && c > 0 && sms > 0, "bad argument");
     const int64_t nnz = h_rowptr[m];
     GLB_CHECK_ARG(nnz == 0 || (h_col && h_val), "null pointer");
     const int ld = glb_padded_ld(c);
@@ -403,14 +416,13 @@ extern "C" GLB_API int glb_slab_create(glb_slab **out, const int32_t *h_rowptr, 
     const unsigned rowb = (unsigned)lanes * 16u;
     const int64_t rows_total = m + n_halo + 1;
     GLB_CHECK_ARG((double)rows_total * rowb < 4294967296.0, "label matrix of this slab exceeds 4 GiB: 32-bit row offsets overflow");
-    cudaStream_t st = (cudaStream_t)stream;
-    PhaseTimer tm("slab_create");
+    PhaseTimer tm("slab_build_host");
 
     int spw = kSlabSPWSmall;
     {   // big tiles when the slab has many tiles per CTA and two stream buffers of a big tile leave room for three CTAs per SM
         const double tiles_big = (double)m / rpw / (kSlabWarps * kSlabSPWBig);
         const double bytes_big = 2.0 * 1.3 * ((double)nnz / (double)m) * rpw * kSlabWarps * kSlabSPWBig * 8.0;
-        if (tiles_big >= (double)kSlabBigTilesPerCta * 3 * sm_count() && bytes_big <= 72.0 * 1024) spw = kSlabSPWBig;
+        if (tiles_big >= (double)kSlabBigTilesPerCta * 3 * sms && bytes_big <= 72.0 * 1024) spw = kSlabSPWBig;
 #ifdef GLB_SLAB_SPW
         spw = GLB_SLAB_SPW;
 #endif
@@ -533,6 +545,32 @@ extern "C" GLB_API int glb_slab_create(glb_slab **out, const int32_t *h_rowptr, 
             GLB_CHECK_ARG(h_send_ptr[r + 1] == h_send_ptr[r] || (h_boundary && h_boundary[r]), "a row with puts must be flagged as boundary");
     }
 
+    H.ld = ld; H.lanes = lanes; H.rpw = rpw; H.spw = spw; H.nslices = nslices; H.n_bnd_slices = n_bnd_slices;
+    H.rows_total = rows_total; H.nnz = nnz; H.stored = stored; H.max_warp_bytes = max_cta;
+    H.slice_first.swap(slice_first); H.slice_rows.swap(slice_rows); H.ent.swap(ent);
+    H.send_ptr.swap(send_ptr); H.send_ent.swap(send_ent);
+    return 0;
+}
+
+extern "C" GLB_API int glb_slab_create(glb_slab **out, const int32_t *h_rowptr, const int32_t *h_col, const float *h_val,
+                                       int64_t m, int64_t n_halo, int c, const uint8_t *h_boundary, const int64_t *h_send_ptr,
+                                       const int32_t *h_send_peer, const int32_t *h_send_dst, void *stream)
+{
+    GLB_CHECK_ARG(out, "bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    PhaseTimer tm("slab_create");
+    SlabHost H;
+    int rc = slab_build_host(H, h_rowptr, h_col, h_val, m, n_halo, c, h_boundary, h_send_ptr, h_send_peer, h_send_dst, sm_count());
+    if (rc) return rc;
+    const int ld = H.ld, lanes = H.lanes, rpw = H.rpw, spw = H.spw, nslices = H.nslices, n_bnd_slices = H.n_bnd_slices;
+    const int spc = kSlabWarps * spw;
+    const int64_t rows_total = H.rows_total, nnz = H.nnz, stored = H.stored;
+    const size_t max_cta = H.max_warp_bytes;
+    const std::vector<int> &slice_first = H.slice_first, &slice_rows = H.slice_rows;
+    const std::vector<int4> &ent = H.ent;
+    const std::vector<long long> &send_ptr = H.send_ptr;
+    const std::vector<int2> &send_ent = H.send_ent;
+
     int dev = 0, max_smem = 0;
     GLB_CUDA(cudaGetDevice(&dev));
     cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
@@ -576,6 +614,75 @@ extern "C" GLB_API int glb_slab_create(glb_slab **out, const int32_t *h_rowptr, 
     tm.lap("upload");
     guard.s = nullptr;
     *out = s;
+    return 0;
+}
+
+// Host-only self-check of the slab builder (no GPU): the stream is walked tile by tile, warp by warp, slice by slice as
+// slab_step_kernel walks it, y = P x in double precision.
+extern "C" GLB_API int glb_slab_check_host(const int32_t *h_rowptr, const int32_t *h_col, const float *h_val, int64_t m, int64_t n_halo,
+                                           int c, const uint8_t *h_boundary, int sms, double *out8)
+{
+    GLB_CHECK_ARG(out8, "null pointer");
+    SlabHost H;
+    int rc = slab_build_host(H, h_rowptr, h_col, h_val, m, n_halo, c, h_boundary, nullptr, nullptr, nullptr, sms);
+    if (rc) return rc;
+    const int rpw = H.rpw, spw = H.spw, spc = kSlabWarps * spw;
+    const unsigned rowb = (unsigned)H.lanes * 16u, pad = (unsigned)(H.rows_total - 1) * rowb;
+    std::vector<double> x((size_t)H.rows_total, 0.0), y((size_t)m, 0.0), ref((size_t)m, 0.0);
+    for (int64_t i = 0; i + 1 < H.rows_total; ++i) x[(size_t)i] = 0.25 + (double)((i * 2654435761ull) % 1000) / 1000.0;   // scratch row stays 0
+    std::vector<int> seen((size_t)m, 0);
+    const int2 *e2 = reinterpret_cast<const int2 *>(H.ent.data());
+    const int ntiles = (H.nslices + spc - 1) / spc;
+    int64_t bad = 0, misplaced = 0;
+    size_t longest = 0, total_parts = 0, nparts = 0;
+    for (int t = 0; t < ntiles; ++t)
+        for (int w = 0; w < kSlabWarps; ++w) {
+            const int s0 = std::min(std::min(t * spc, H.nslices) + w * spw, H.nslices), s1 = std::min(s0 + spw, H.nslices);
+            const size_t part = (size_t)(H.slice_first[s1] - H.slice_first[s0]) * 16;
+            if (part > H.max_warp_bytes) ++bad;                                  // would overflow the warp's region of the stream buffer
+            longest = std::max(longest, part);
+            if (s1 > s0) { total_parts += part; ++nparts; }
+            for (int sl = s0; sl < s1; ++sl) {
+                const size_t base = (size_t)H.slice_first[sl] * 2;
+                const int Lst = (H.slice_first[sl + 1] - H.slice_first[sl]) * 2 / rpw;
+                const int r0 = H.slice_rows[(size_t)sl * rpw];
+                const bool is_long = r0 >= 0 && (r0 & kSlabLongBit);
+                for (int g = 0; g < rpw; ++g) {
+                    int row = is_long ? (r0 & ~kSlabLongBit) : H.slice_rows[(size_t)sl * rpw + g];
+                    if (!is_long || g == 0) {
+                        if (row >= 0) {
+                            seen[(size_t)row] += 1;
+                            if (h_boundary && (bool)h_boundary[row] != (sl < H.n_bnd_slices)) ++misplaced;
+                        }
+                    }
+                    for (int j = 0; j < Lst; ++j) {
+                        const int2 e = e2[base + ((size_t)(j / 2) * rpw + g) * 2 + (j & 1)];
+                        float v;
+                        memcpy(&v, &e.y, sizeof(v));
+                        if (row < 0) { if ((unsigned)e.x != pad || v != 0.f) ++bad; continue; }     // padding lane group
+                        if ((unsigned)e.x % rowb) { ++bad; continue; }
+                        y[(size_t)row] += (double)v * x[(size_t)((unsigned)e.x / rowb)];
+                    }
+                }
+            }
+        }
+    double worst = 0.0, big = 0.0;
+    for (int64_t r = 0; r < m; ++r) {
+        double acc = 0.0;
+        for (int j = h_rowptr[r]; j < h_rowptr[r + 1]; ++j) acc += (double)h_val[j] * x[(size_t)h_col[j]];
+        ref[(size_t)r] = acc;
+        big = std::max(big, fabs(acc));
+        worst = std::max(worst, fabs(acc - y[(size_t)r]));
+        if (seen[(size_t)r] != 1) ++bad;
+    }
+    out8[0] = big > 0.0 ? worst / big : worst;
+    out8[1] = (double)bad;
+    out8[2] = (double)misplaced;
+    out8[3] = H.stored ? (double)H.nnz / (double)H.stored : 1.0;
+    out8[4] = (double)spc;
+    out8[5] = (double)H.max_warp_bytes;
+    out8[6] = nparts ? (double)longest / ((double)total_parts / (double)nparts) : 1.0;
+    out8[7] = (double)ntiles;
     return 0;
 }
 

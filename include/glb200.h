@@ -183,6 +183,13 @@ GLB_API int glb_slab_create(glb_slab **slab, const int32_t *h_rowptr, const int3
                             int64_t n_halo, int c, const uint8_t *h_boundary, const int64_t *h_send_ptr,
                             const int32_t *h_send_peer, const int32_t *h_send_dst, void *stream);
 GLB_API int glb_slab_destroy(glb_slab *slab);
+/* Host-only self-check of the slab builder (no GPU): builds the entry stream of one slab as glb_slab_create does for a device of
+ * `sms` SMs and walks it tile by tile, warp by warp as slab_step_kernel does, computing y = P x in double precision.
+ * out8 = {max |y - P x| / max |P x|, structural errors (rows not stored exactly once, padding that is not (scratch row, 0), warp
+ * parts beyond their region), rows on the wrong side of the boundary / interior split, fill, slices per tile, bytes of a warp's
+ * stream region, longest warp part / mean warp part, tiles}. */
+GLB_API int glb_slab_check_host(const int32_t *h_rowptr, const int32_t *h_col, const float *h_val, int64_t m, int64_t n_halo, int c,
+                                const uint8_t *h_boundary, int sms, double *out8);
 GLB_API int64_t glb_slab_rows(const glb_slab *slab);          /* m + n_halo + 1 */
 GLB_API int glb_slab_ld(const glb_slab *slab);
 GLB_API double glb_slab_fill(const glb_slab *slab);           /* nnz / stored entries of the sliced ELL */

@@ -272,3 +272,38 @@ def test_pinned_pool_background_fill_and_recycling(monkeypatch):
     fake.fail = True
     e = pool.empty((30000, 10)); pool.wait()
     assert e.flags.owndata and pool.total == 2 * nbytes and not pool.idle.get(e.nbytes)
+
+
+@pytest.mark.parametrize("c,n,sms", [(10, 6000, 148), (3, 6000, 148), (40, 4000, 148), (10, 60000, 4)])
+def test_row_slab_stream_holds_every_entry_once(c, n, sms):
+    """The entry stream of the row-slab kernel (csrc/slab.cu), walked on the host tile by tile, warp by warp as the kernel
+    walks it, gives y = P x: every row is stored exactly once on its side of the boundary / interior split, padding lane
+    groups gather the zero scratch row with the value 0, no warp part exceeds the warp's region of the stream buffers, and the
+    folded slice order keeps the longest warp part near the mean.  Hub rows (a slice of their own), empty rows, halo columns;
+    the last case has many tiles per CTA (4 SMs), which selects tiles of 32 slices."""
+    import ctypes
+    from graphlearning_b200 import _lib
+    rng = np.random.default_rng(c + n)
+    n_halo = 500
+    rows = np.repeat(np.arange(n), 9); cols = rng.integers(0, n + n_halo, n * 9)
+    hub = rng.choice(n, 2, replace=False)
+    rows = np.concatenate([rows] + [np.full(k, h) for h, k in zip(hub, (150, 700))])
+    cols = np.concatenate([cols] + [rng.choice(n + n_halo, k, replace=False) for k in (150, 700)])
+    P = sparse.coo_matrix((rng.random(len(rows)).astype(np.float32), (rows, cols)), shape=(n, n + n_halo)).tocsr()
+    P.sum_duplicates()
+    keep = np.ones(n, bool); keep[rng.integers(0, n, 40)] = False
+    P = sparse.csr_matrix(sparse.diags(keep.astype(np.float32)) @ P); P.eliminate_zeros()
+    boundary = (P[:, n:].getnnz(axis=1) > 0).astype(np.uint8)                  # rows that read halo rows
+    rp = np.ascontiguousarray(P.indptr, dtype=np.int32); ci = np.ascontiguousarray(P.indices, dtype=np.int32)
+    va = np.ascontiguousarray(P.data, dtype=np.float32)
+    out = np.zeros(8)
+    vp = lambda a: ctypes.c_void_p(a.ctypes.data)
+    _lib.call("glb_slab_check_host", vp(rp), vp(ci), vp(va), n, n_halo, c, vp(boundary), sms, vp(out))
+    err, bad, misplaced, fill, spc, region, longest_over_mean, tiles = out
+    assert bad == 0 and misplaced == 0
+    assert err < 1e-12
+    assert 0.3 < fill <= 1.0
+    assert spc == (32 if sms == 4 else 16)
+    assert 2 * 8 * region + 1024 <= 227 * 1024                                  # two stream buffers of a CTA fit in shared memory
+    if c == 10 and sms == 148:
+        assert longest_over_mean < 8.0                                          # the hub's slice is the longest part
