@@ -10,9 +10,12 @@
 //     one all-zero scratch row (padding target).  Label matrices are (m + H + 1) x ld fp32, ld = glb_padded_ld(c),
 //     a row of c = 10 classes = one 64-byte piece of a 128-byte line.
 //   * sliced ELL: slices of 32/LANES rows (LANES lanes own one row, 16 bytes each), rows sorted by length inside
-//     windows of 256 rows so that locality survives, slice width padded to even; entries (byte offset of the column's
-//     label row, fp32 value) in PAIRS, interleaved so that one warp-wide 16-byte load fetches one pair of every lane
-//     group from one contiguous 128-byte run.  All slices back to back = ONE stream of pairs per warp.
+//     windows of 256 rows so that locality survives, slice width padded to even; the slices of a window are then folded
+//     (longest, shortest, second longest, ...) so that every pair of slices - and with it every warp's part of a tile -
+//     holds about the same number of entries; entries (byte offset of the column's label row, fp32 value) in PAIRS,
+//     interleaved so that one warp-wide 16-byte load fetches one pair of every lane group from one contiguous 128-byte
+//     run.  All slices back to back = ONE stream of pairs per warp.  A tile is 8 warps x 2 slices, or x 4 when the slab
+//     still has 8 tiles per CTA then (the gather pipeline of a warp drains at tile boundaries).
 //   * boundary rows (rows a peer needs, or rows that read halo rows) come first, interior rows after them.
 //
 // Kernel (slab_step_kernel, one launch per iteration): persistent CTAs of 8 warps walk tiles (8 warps x 2 slices) in a
@@ -20,13 +23,16 @@
 // interior tiles that evens out the work), the others start on interior tiles at once and never wait for a neighbour.
 // Lane 0 of every warp brings the warp's part of a tile's entry stream into shared memory
 // with ONE bulk copy (cp.async.bulk -> mbarrier, TMA unit, SASS UBLKCP) - the copy for the NEXT tile is issued before the
-// current one is processed (two stream buffers per CTA) - then the warp walks it through a ring of four pair slots - pair p+4 is issued when pair p has been consumed,
+// current one is processed (two stream buffers per CTA; every warp owns a fixed region of each, because the warps of a CTA
+// are not synchronised between tiles and a warp that is a tile ahead must not write over entries a neighbour still reads) -
+// then the warp walks it through a ring of four pair slots - pair p+4 is issued when pair p has been consumed,
 // across slice boundaries, 6-8 label-row gathers per lane in flight (the same software pipeline as
 // poisson_dataflow_pipe_kernel); gathers go through L1 (a locality ordering makes neighbouring rows share most of
 // their columns).  Boundary tiles wait until the neighbours' halo
 // rows of this version have arrived (one flag per neighbour in this rank's memory, acquire at system scope), write every
 // finished row to the local matrix AND to each peer that needs it (plain 16-byte stores to peer memory mapped through
-// CUDA IPC), and the last of them to finish releases this rank's flag in every neighbour's memory.  Interior tiles never
+// CUDA IPC); a CTA orders and counts the puts of all its boundary tiles with ONE system-scope fence after the last of them,
+// and the last CTA to do so releases this rank's flag in every neighbour's memory.  Interior tiles never
 // wait: they run while the halo rows are in flight.  Three label buffers rotate (version v in buffer v % 3): a peer may already write
 // version t+2 while this rank still reads version t.
 //
